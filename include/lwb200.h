@@ -1,0 +1,224 @@
+/*
+ * lwb200.h -- the C-ABI of the B200 back end for Lightweaver's formal-solution /
+ * Gamma-accumulation / statistical-equilibrium hot path.
+ *
+ * Plain C: POD structs, raw pointers and sizes, int return codes.  No C++, no
+ * torch and no Lightweaver types cross this boundary.  Three things bind it:
+ *   - lightweaver_b200/csrc/lwb200_plugin.cpp, the C++ shim compiled against
+ *     the reference headers that exports `fs_iteration_fns_provider` /
+ *     `fs_provider` (reference: Source/LwFormalInterface.hpp:35-43,110-134,
+ *     Source/FormalInterface.cpp:9-28,62-81);
+ *   - lightweaver_b200/capi.py (ctypes), the Python host side;
+ *   - the oracle (oracle/lw_oracle.c) and the reference harness
+ *     (oracle/ref_harness.cpp), which consume the same LwB200Problem so that
+ *     all implementations see identical inputs.
+ *
+ * Array conventions follow the reference (Source/CmoArray.hpp): row-major,
+ * C-contiguous fp64, depth index k innermost, k = 0 at the TOP of the
+ * atmosphere.  Every per-column array carries a leading [Ncol] dimension; a
+ * classic 1D Lightweaver Context is Ncol == 1, a 1.5D stack is Ncol columns
+ * that share the atomic models / wavelength grids / quadrature and differ in
+ * their atmospheres, populations and line profiles.
+ *
+ * Units as in the reference: wavelengths nm, heights m, populations m^-3.
+ */
+#ifndef LWB200_H
+#define LWB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LWB200_ABI_VERSION 1
+
+/* TransitionType, Source/LwTransition.hpp:10-14 */
+enum { LWB200_LINE = 0, LWB200_CONTINUUM = 1 };
+/* RadiationBc, Source/LwAtmosphere.hpp:6-13 */
+enum {
+    LWB200_BC_UNINITIALISED = 0,
+    LWB200_BC_ZERO = 1,
+    LWB200_BC_THERMALISED = 2,
+    LWB200_BC_PERIODIC = 3,
+    LWB200_BC_CALLABLE = 4
+};
+/* FormalSolverManager order, Source/FormalInterface.cpp:30-37 */
+enum { LWB200_FS_LINEAR = 0, LWB200_FS_BESSER = 1, LWB200_FS_BEZIER3 = 2 };
+
+/* One radiative transition of an atom (Source/LwTransition.hpp:22-91). */
+typedef struct LwB200Transition {
+    int32_t type;          /* LWB200_LINE / LWB200_CONTINUUM */
+    int32_t i, j;          /* lower / upper level */
+    int32_t Nblue, Nred;   /* active on the global grid for la in [Nblue, Nred) */
+    int32_t reserved;
+    double Aji, Bji, Bij;  /* lines */
+    double lambda0;
+    double dopplerWidth;   /* c/lambda0 for lines, 1 for continua (LwMiddleLayer.pyx:1799,1815) */
+    const double* wavelength; /* [Nlambda = Nred - Nblue] */
+    const double* alpha;      /* [Nlambda] continua, else NULL */
+    double* phi;              /* [Ncol][Nlambda][Nrays][2][Nspace] lines, else NULL */
+    double* wphi;             /* [Ncol][Nspace] lines */
+    const double* rhoPrd;     /* [Ncol][Nlambda][Nspace] angle-averaged PRD lines, else NULL */
+    const double* aDamp;      /* [Ncol][Nspace] lines; only read by *_compute_profiles */
+    double* Rij;              /* [Ncol][Nspace] out */
+    double* Rji;              /* [Ncol][Nspace] out */
+} LwB200Transition;
+
+/* One atom (Source/LwAtom.hpp:42-80).  detailedStatic atoms contribute
+ * opacity/emissivity and get rates but no Gamma (ctx.detailedAtoms). */
+typedef struct LwB200Atom {
+    int32_t Nlevel;
+    int32_t Ntrans;
+    int32_t detailedStatic;
+    int32_t reserved;
+    LwB200Transition* trans; /* [Ntrans] */
+    double* n;               /* [Ncol][Nlevel][Nspace] in/out */
+    const double* nStar;     /* [Ncol][Nlevel][Nspace] */
+    const double* nTotal;    /* [Ncol][Nspace] */
+    const double* vBroad;    /* [Ncol][Nspace]; only read by *_compute_profiles */
+    double* Gamma;           /* [Ncol][Nlevel][Nlevel][Nspace] in (crsw*C prefill) / out; NULL if detailedStatic */
+} LwB200Atom;
+
+/* What the hot path reads from / writes to a Context (Source/LwContext.hpp:20-45). */
+typedef struct LwB200Problem {
+    int32_t abiVersion;    /* LWB200_ABI_VERSION */
+    int32_t Ncol;
+    int32_t Nspace;
+    int32_t Nrays;
+    int32_t Nspect;
+    int32_t Natom;         /* active + detailed-static atoms */
+    int32_t formalSolver;  /* LWB200_FS_* */
+    int32_t lowerBc;       /* zLowerBc.type */
+    int32_t upperBc;       /* zUpperBc.type */
+    int32_t NlowerBcMu;    /* bcData second dim when CALLABLE */
+    int32_t NupperBcMu;
+    int32_t reserved;
+    const double* height;      /* [Ncol][Nspace] */
+    const double* temperature; /* [Ncol][Nspace] */
+    const double* vlosMu;      /* [Ncol][Nrays][Nspace]; only read by *_compute_profiles */
+    const double* muz;         /* [Nrays] */
+    const double* wmu;         /* [Nrays] */
+    const double* wavelength;  /* [Nspect] */
+    const double* chiBg;       /* [Ncol][Nspect][Nspace] background.chi */
+    const double* etaBg;       /* [Ncol][Nspect][Nspace] background.eta */
+    const double* scaBg;       /* [Ncol][Nspect][Nspace] background.sca */
+    const double* lowerBcData; /* [Ncol][Nspect][NlowerBcMu] when CALLABLE (bcData(la, muIdx, 0)) */
+    const double* upperBcData; /* [Ncol][Nspect][NupperBcMu] */
+    const int32_t* lowerBcIdx; /* [Nrays][2] zLowerBc.idxs(mu, toObs) */
+    const int32_t* upperBcIdx; /* [Nrays][2] */
+    double* J;                 /* [Ncol][Nspect][Nspace] in (J-dagger) / out */
+    double* I;                 /* [Ncol][Nspect][Nrays] out: spect.I(la, mu, 0) */
+    double* depthChi;          /* [Ncol][Nspect][Nrays][2][Nspace] or NULL (DepthData) */
+    double* depthEta;
+    double* depthI;
+    LwB200Atom* atoms;         /* [Natom] */
+} LwB200Problem;
+
+/* Input/output groups for lwb200_upload / lwb200_download. */
+enum {
+    LWB200_ATMOS   = 1u << 0, /* height, temperature, vlosMu, BC data */
+    LWB200_BACKGR  = 1u << 1, /* chiBg, etaBg, scaBg */
+    LWB200_POPS    = 1u << 2, /* n */
+    LWB200_NSTAR   = 1u << 3, /* nStar, nTotal, vBroad */
+    LWB200_GAMMA   = 1u << 4, /* up: Gamma prefill (crsw*C); down: finalised Gamma */
+    LWB200_JBAR    = 1u << 5, /* J */
+    LWB200_PROFILE = 1u << 6, /* phi, wphi, rhoPrd, aDamp */
+    LWB200_INTENS  = 1u << 7, /* down only: I */
+    LWB200_RATES   = 1u << 8, /* down only: Rij, Rji */
+    LWB200_DEPTH   = 1u << 9, /* down only: depthChi/Eta/I */
+    LWB200_ALL_INPUTS  = 0x7fu,
+    LWB200_ITER_INPUTS = LWB200_POPS | LWB200_NSTAR | LWB200_GAMMA,
+    LWB200_ITER_OUTPUTS = LWB200_GAMMA | LWB200_JBAR | LWB200_INTENS | LWB200_RATES
+};
+
+/* Flags for lwb200_fs_iter. */
+enum {
+    LWB200_LAMBDA_ITERATE = 1u << 0, /* FsMode::PureLambdaIteration */
+    LWB200_STORE_DEPTH    = 1u << 1, /* depthData.fill */
+    LWB200_DEFER_FINALISE = 1u << 2  /* leave [Gamma|R] partial sums un-finalised (lambda-sharded
+                                        ranks all-reduce them, then call lwb200_finalise) */
+};
+
+/* Device buffers a caller may need to hand to a collective. */
+enum {
+    LWB200_BUF_ACCUM = 0,  /* packed fp64 [Ncol][ sum_a Nlevel^2*Nspace | 2*sum_t Nspace ] partial Gamma|R */
+    LWB200_BUF_J     = 1,  /* [Ncol][Nspect][Nspace] */
+    LWB200_BUF_I     = 2,  /* [Ncol][Nspect][Nrays] */
+    LWB200_BUF_POPS  = 3,  /* [Ncol][sum_a Nlevel][Nspace] */
+    LWB200_BUF_GAMMA = 4,  /* [Ncol][sum_a Nlevel^2][Nspace] finalised */
+    LWB200_BUF_DJ    = 5   /* [Ncol][Nspect] per-wavelength max_k |1 - Jdag/J| */
+};
+
+typedef struct LwB200Context LwB200Context; /* opaque */
+
+/* Every call returns 0 on success, non-zero on failure; lwb200_last_error()
+ * (thread-local) then describes it.  The shim turns failures into
+ * std::runtime_error, as the reference expects (LwMiddleLayer.pyx:336-350). */
+const char* lwb200_last_error(void);
+int lwb200_abi_version(void);
+int lwb200_device_count(int* count);
+
+/* Replaces Context::initialise_threads / ThreadData::initialise
+ * (Source/ThreadStorage.cpp:480-536): takes the problem description, keeps the
+ * host pointers (never frees them), builds the wavelength work plan and
+ * allocates the device mirrors.  Nothing is uploaded yet (phi is still zero
+ * when the reference fires alloc_global_scratch, LwMiddleLayer.pyx:2973-2975). */
+int lwb200_create(const LwB200Problem* problem, int device, LwB200Context** out);
+int lwb200_destroy(LwB200Context* ctx);
+
+/* Launch everything on this cudaStream_t (default: the legacy default stream). */
+int lwb200_set_stream(LwB200Context* ctx, void* cudaStream);
+
+/* Wavelength partition for 1D lambda-sharding (replaces the enkiTS task set,
+ * Source/SimdFullIterationTemplates.hpp:675-698): this context only sweeps
+ * la in [laStart, laEnd).  Default [0, Nspect). */
+int lwb200_set_lambda_range(LwB200Context* ctx, int32_t laStart, int32_t laEnd);
+
+/* Host -> device / device -> host copies of the groups in `mask`, using the
+ * host pointers registered at create time.  Asynchronous on the context's
+ * stream; lwb200_sync waits. */
+int lwb200_upload(LwB200Context* ctx, uint32_t mask);
+int lwb200_download(LwB200Context* ctx, uint32_t mask);
+int lwb200_sync(LwB200Context* ctx);
+
+/* Replaces Transition::compute_phi + compute_wphi (Source/FormalScalar.cpp:28-134)
+ * on the device, from aDamp, vBroad, vlosMu already uploaded. */
+int lwb200_compute_profiles(LwB200Context* ctx);
+
+/* Replaces formal_sol_gamma_matrices / formal_sol_iteration_matrices_impl
+ * (Source/FormalScalar.cpp:678-681, Source/SimdFullIterationTemplates.hpp:588-719)
+ * on device-resident data: zeroes rates, sweeps every wavelength, accumulates
+ * J, Gamma (onto the uploaded prefill) and Rij/Rji, finalises Gamma.
+ * dJMax / dJMaxIdx may be NULL (no device->host sync is then forced). */
+int lwb200_fs_iter(LwB200Context* ctx, uint32_t flags, double* dJMax, int64_t* dJMaxIdx);
+/* Gamma = prefill + partial sums, diagonal = -column sum (finalise_Gamma, :491-508);
+ * rates are unpacked.  Only needed after LWB200_DEFER_FINALISE. */
+int lwb200_finalise(LwB200Context* ctx);
+/* Reduce LWB200_BUF_DJ to (max, wavelength index of the max). */
+int lwb200_dj_max(LwB200Context* ctx, double* dJMax, int64_t* dJMaxIdx);
+
+/* Replaces formal_sol / formal_sol_impl (Source/FormalScalar.cpp:691-694,
+ * SimdFullIterationTemplates.hpp:721-781): I only, no J / Gamma / rates. */
+int lwb200_formal_sol(LwB200Context* ctx, int upOnly);
+
+/* Replaces stat_eq_impl + solve_lin_eq (Source/UpdatePopulations.cpp:7-47,
+ * Source/LuSolve.cpp:8-133) for atom `atom` (index into problem->atoms, or -1
+ * for every active atom), depths [kStart, kEnd) (both < 0: all).  *nSingular
+ * receives the number of (column, depth) systems with an all-zero row; the
+ * call then fails like the reference's throw ("Singular Matrix"). */
+int lwb200_stat_eq(LwB200Context* ctx, int32_t atom, int32_t kStart, int32_t kEnd, int32_t* nSingular);
+
+/* Device pointer + byte size of one of the LWB200_BUF_* buffers. */
+int lwb200_device_buffer(LwB200Context* ctx, int32_t which, void** ptr, size_t* nbytes);
+
+/* Work accounting for the roofline: ray-depth points and algorithmic bytes of
+ * one fs_iter over this context's wavelength range, and how many
+ * kernels the last call launched. */
+int lwb200_work_stats(LwB200Context* ctx, double* points, double* algBytes, int64_t* lastLaunches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LWB200_H */

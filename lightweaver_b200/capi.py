@@ -1,0 +1,148 @@
+"""ctypes binding of the C-ABI declared in ``include/lwb200.h``.
+
+This is the whole Python <-> CUDA boundary: plain structs of pointers and sizes,
+int return codes.  The library is built in-tree by ``__graft_entry__.build()``
+(``lightweaver_b200/csrc/build.py``) as ``lightweaver_b200/liblwb200.so``; if it
+is missing, loading fails loudly -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ABI_VERSION = 1
+
+LINE, CONTINUUM = 0, 1
+BC_UNINITIALISED, BC_ZERO, BC_THERMALISED, BC_PERIODIC, BC_CALLABLE = range(5)
+FS_LINEAR, FS_BESSER, FS_BEZIER3 = 0, 1, 2
+FS_NAMES = {'piecewise_linear_1d': FS_LINEAR, 'piecewise_besser_1d': FS_BESSER,
+            'piecewise_bezier3_1d': FS_BEZIER3}
+
+ATMOS, BACKGR, POPS, NSTAR, GAMMA, JBAR, PROFILE, INTENS, RATES, DEPTH = (1 << i for i in range(10))
+ALL_INPUTS = 0x7f
+ITER_INPUTS = POPS | NSTAR | GAMMA
+ITER_OUTPUTS = GAMMA | JBAR | INTENS | RATES
+
+LAMBDA_ITERATE, STORE_DEPTH, DEFER_FINALISE = 1, 2, 4
+
+BUF_ACCUM, BUF_J, BUF_I, BUF_POPS, BUF_GAMMA, BUF_DJ = range(6)
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class LwB200Transition(C.Structure):
+    _fields_ = [
+        ('type', C.c_int32), ('i', C.c_int32), ('j', C.c_int32),
+        ('Nblue', C.c_int32), ('Nred', C.c_int32), ('reserved', C.c_int32),
+        ('Aji', C.c_double), ('Bji', C.c_double), ('Bij', C.c_double),
+        ('lambda0', C.c_double), ('dopplerWidth', C.c_double),
+        ('wavelength', _dp), ('alpha', _dp), ('phi', _dp), ('wphi', _dp),
+        ('rhoPrd', _dp), ('aDamp', _dp), ('Rij', _dp), ('Rji', _dp),
+    ]
+
+
+class LwB200Atom(C.Structure):
+    _fields_ = [
+        ('Nlevel', C.c_int32), ('Ntrans', C.c_int32),
+        ('detailedStatic', C.c_int32), ('reserved', C.c_int32),
+        ('trans', C.POINTER(LwB200Transition)),
+        ('n', _dp), ('nStar', _dp), ('nTotal', _dp), ('vBroad', _dp), ('Gamma', _dp),
+    ]
+
+
+class LwB200Problem(C.Structure):
+    _fields_ = [
+        ('abiVersion', C.c_int32), ('Ncol', C.c_int32), ('Nspace', C.c_int32),
+        ('Nrays', C.c_int32), ('Nspect', C.c_int32), ('Natom', C.c_int32),
+        ('formalSolver', C.c_int32), ('lowerBc', C.c_int32), ('upperBc', C.c_int32),
+        ('NlowerBcMu', C.c_int32), ('NupperBcMu', C.c_int32), ('reserved', C.c_int32),
+        ('height', _dp), ('temperature', _dp), ('vlosMu', _dp), ('muz', _dp), ('wmu', _dp),
+        ('wavelength', _dp), ('chiBg', _dp), ('etaBg', _dp), ('scaBg', _dp),
+        ('lowerBcData', _dp), ('upperBcData', _dp), ('lowerBcIdx', _ip), ('upperBcIdx', _ip),
+        ('J', _dp), ('I', _dp), ('depthChi', _dp), ('depthEta', _dp), ('depthI', _dp),
+        ('atoms', C.POINTER(LwB200Atom)),
+    ]
+
+
+def dptr(a):
+    """Pointer to a C-contiguous float64 array (None -> NULL)."""
+    if a is None:
+        return _dp()
+    assert isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags['C_CONTIGUOUS'], \
+        'expected a C-contiguous float64 ndarray'
+    return a.ctypes.data_as(_dp)
+
+
+def iptr(a):
+    if a is None:
+        return _ip()
+    assert isinstance(a, np.ndarray) and a.dtype == np.int32 and a.flags['C_CONTIGUOUS']
+    return a.ctypes.data_as(_ip)
+
+
+class LwB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'liblwb200.so')
+
+
+def load():
+    """Load liblwb200.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise LwB200Error(
+            f'{path} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            '(there is no CPU fallback for the B200 back end)')
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    lib.lwb200_last_error.restype = C.c_char_p
+    lib.lwb200_abi_version.restype = C.c_int
+    lib.lwb200_device_count.argtypes = [C.POINTER(C.c_int)]
+    lib.lwb200_create.argtypes = [C.POINTER(LwB200Problem), C.c_int, C.POINTER(vp)]
+    lib.lwb200_destroy.argtypes = [vp]
+    lib.lwb200_set_stream.argtypes = [vp, vp]
+    lib.lwb200_set_lambda_range.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.lwb200_upload.argtypes = [vp, C.c_uint32]
+    lib.lwb200_download.argtypes = [vp, C.c_uint32]
+    lib.lwb200_sync.argtypes = [vp]
+    lib.lwb200_compute_profiles.argtypes = [vp]
+    lib.lwb200_fs_iter.argtypes = [vp, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.lwb200_finalise.argtypes = [vp]
+    lib.lwb200_dj_max.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.lwb200_formal_sol.argtypes = [vp, C.c_int]
+    lib.lwb200_stat_eq.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    lib.lwb200_device_buffer.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.lwb200_work_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_int64)]
+    for name in ('device_count', 'create', 'destroy', 'set_stream', 'set_lambda_range', 'upload',
+                 'download', 'sync', 'compute_profiles', 'fs_iter', 'finalise', 'dj_max',
+                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats'):
+        getattr(lib, 'lwb200_' + name).restype = C.c_int
+    if lib.lwb200_abi_version() != ABI_VERSION:
+        raise LwB200Error('liblwb200.so ABI version mismatch; rebuild')
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().lwb200_last_error()
+        raise LwB200Error(msg.decode() if msg else f'lwb200 call failed ({rc})')
+
+
+EXPORTED_SYMBOLS = [
+    'lwb200_last_error', 'lwb200_abi_version', 'lwb200_device_count', 'lwb200_create',
+    'lwb200_destroy', 'lwb200_set_stream', 'lwb200_set_lambda_range', 'lwb200_upload',
+    'lwb200_download', 'lwb200_sync', 'lwb200_compute_profiles', 'lwb200_fs_iter',
+    'lwb200_finalise', 'lwb200_dj_max', 'lwb200_formal_sol', 'lwb200_stat_eq',
+    'lwb200_device_buffer', 'lwb200_work_stats',
+]

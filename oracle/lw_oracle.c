@@ -1,0 +1,963 @@
+/* lw_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see lw_oracle.h).
+ *
+ * Scalar CPU restatement of Lightweaver's hot path.  Each function cites the
+ * reference lines whose arithmetic (including operation order) it follows, so
+ * that agreement with the reference's scalar scheme is at rounding level.
+ * All paths below are relative to /root/reference/Source/.
+ */
+#include "lw_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <stdatomic.h>
+
+/* Constants.hpp:6-47 */
+#define C_CLIGHT 2.99792458E+08
+#define C_HPLANCK 6.6260755E-34
+#define C_HC (C_HPLANCK * C_CLIGHT)
+#define C_KBOLTZMANN 1.380658E-23
+#define C_PI 3.14159265358979323846264338327950288
+#define C_NM_TO_M 1.0E-09
+
+static inline double sq(double x) { return x * x; }
+static inline double cb(double x) { return x * x * x; }
+static inline double dmin(double a, double b) { return b < a ? b : a; } /* std::min */
+static inline double dmax(double a, double b) { return a < b ? b : a; } /* std::max */
+
+/* ------------------------------------------------------------------------ */
+/* LwInternal.hpp:90-110 */
+static void w2(double dtau, double* w)
+{
+    if (dtau < 5.0E-4)
+    {
+        w[0] = dtau * (1.0 - 0.5 * dtau);
+        w[1] = sq(dtau) * (0.5 - dtau * (1.0 / 3.0));
+    }
+    else if (dtau > 50.0)
+    {
+        w[1] = w[0] = 1.0;
+    }
+    else
+    {
+        double expdt = exp(-dtau);
+        w[0] = 1.0 - expdt;
+        w[1] = w[0] - dtau * expdt;
+    }
+}
+
+/* LwMisc.hpp:29-46 */
+static void planck_nu(int n, const double* T, double lambda, double* Bnu)
+{
+    const double hc_k = C_HC / (C_KBOLTZMANN * C_NM_TO_M);
+    const double hc_kla = hc_k / lambda;
+    const double twoh_c2 = (2.0 * C_HC) / cb(C_NM_TO_M);
+    const double twohnu3_c2 = twoh_c2 / cb(lambda);
+    for (int k = 0; k < n; ++k)
+    {
+        double x = hc_kla / T[k];
+        Bnu[k] = (x <= 150.0) ? twohnu3_c2 / (exp(x) - 1.0) : 0.0;
+    }
+}
+
+/* Bezier.hpp:58-65 (Steffen 1990) */
+static double cent_deriv(double dsuw, double dsdw, double yuw, double y0, double ydw)
+{
+    const double S0 = (ydw - y0) / dsdw;
+    const double Suw = (y0 - yuw) / dsuw;
+    const double P0 = fabs((Suw * dsdw + S0 * dsuw) / (dsdw + dsuw));
+    return (copysign(1.0, S0) + copysign(1.0, Suw)) * dmin(fabs(Suw), dmin(fabs(S0), 0.5 * P0));
+}
+
+/* Bezier.hpp:81-127 */
+static void bezier3_coeffs(double dt, double* alpha, double* beta, double* gamma, double* delta,
+                           double* edt)
+{
+    double dt2 = sq(dt);
+    double dt3 = dt2 * dt;
+    if (dt < 5e-2)
+    {
+        *edt = 1.0 - dt + 0.5 * dt2 - dt3 / 6.0;
+        *alpha = 0.25 * dt - 0.2 * dt2 + dt3 / 12.0;
+        *beta = 0.25 * dt - 0.05 * dt2 + dt3 / 120.0;
+        *gamma = 0.25 * dt - 0.15 * dt2 + 0.05 * dt3;
+        *delta = 0.25 * dt - 0.1 * dt2 + 0.025 * dt3;
+    }
+    else if (dt > 30.0)
+    {
+        *edt = 0.0;
+        *alpha = 6.0 / dt3;
+        *beta = (-6.0 + 6.0 * dt - 3.0 * dt2 + dt3) / dt3;
+        *gamma = 3.0 * (2.0 * dt - 6.0) / dt3;
+        *delta = 3.0 * (6.0 - 4.0 * dt + dt2) / dt3;
+    }
+    else
+    {
+        *edt = exp(-dt);
+        *alpha = (6.0 - *edt * (6.0 + 6.0 * dt + 3 * dt2 + dt3)) / dt3;
+        *beta = (6.0 * *edt - 6.0 + 6.0 * dt - 3.0 * dt2 + dt3) / dt3;
+        *gamma = 3.0 * (2.0 * dt - 6.0 + *edt * (6.0 + 4.0 * dt + dt2)) / dt3;
+        *delta = 3.0 * (6.0 - 4.0 * dt + dt2 - 2.0 * *edt * (3.0 + dt)) / dt3;
+    }
+}
+
+/* FormalScalar.cpp:136-207 */
+static void linear_sweep(int K, const double* h, const double* chi, const double* S, double zmu,
+                         int toObs, double Istart, double* I, double* Psi)
+{
+    int dk = -1, ks = K - 1, ke = 0;
+    if (!toObs) { dk = 1; ks = 0; ke = K - 1; }
+    double dtau_uw = zmu * (chi[ks] + chi[ks + dk]) * fabs(h[ks] - h[ks + dk]);
+    double rcp_uw = 1.0 / dtau_uw;
+    double dS_uw = (S[ks] - S[ks + dk]) * rcp_uw;
+    double I_upw = Istart;
+    I[ks] = I_upw;
+    if (Psi) Psi[ks] = 0.0;
+    double w[2];
+    for (int k = ks + dk; k != ke; k += dk)
+    {
+        w2(dtau_uw, w);
+        double dtau_dw = zmu * (chi[k] + chi[k + dk]) * fabs(h[k] - h[k + dk]);
+        double rcp_dw = 1.0 / dtau_dw;
+        double dS_dw = (S[k] - S[k + dk]) * rcp_dw;
+        I[k] = (1.0 - w[0]) * I_upw + w[0] * S[k] + w[1] * dS_uw;
+        if (Psi) Psi[k] = w[0] - w[1] * rcp_uw;
+        I_upw = I[k];
+        dS_uw = dS_dw;
+        dtau_uw = dtau_dw;
+        rcp_uw = rcp_dw;
+    }
+    w2(dtau_uw, w);
+    I[ke] = (1.0 - w[0]) * I_upw + w[0] * S[ke] + w[1] * dS_uw;
+    if (Psi)
+    {
+        Psi[ke] = w[0] - w[1] * rcp_uw;
+        for (int k = 0; k < K; ++k) Psi[k] /= chi[k];
+    }
+}
+
+/* FormalScalar.cpp:209-325 */
+static void bezier3_sweep(int K, const double* h, const double* chi, const double* S, double zmu,
+                          int toObs, double Istart, double* I, double* Psi)
+{
+    int dk = -1, ks = K - 1, ke = 0;
+    if (!toObs) { dk = 1; ks = 0; ke = K - 1; }
+    double I_upw = Istart;
+    I[ks] = I_upw;
+    if (Psi) Psi[ks] = 0.0;
+
+    int k = ks + dk;
+    double ds_uw = fabs(h[k] - h[k - dk]) * zmu;
+    double ds_dw = fabs(h[k + dk] - h[k]) * zmu;
+    double dx_uw = (chi[k] - chi[k - dk]) / ds_uw;
+    double dx_c = cent_deriv(ds_uw, ds_dw, chi[k - dk], chi[k], chi[k + dk]);
+    double Cuw = chi[k - dk] + (ds_uw / 3.0) * dx_uw;
+    double C0 = chi[k] - (ds_uw / 3.0) * dx_c;
+    double dtau_uw = ds_uw * (chi[k] + chi[k - dk] + Cuw + C0) * 0.25;
+    double dS_uw = (S[k] - S[k - dk]) / dtau_uw;
+    double ds_dw2 = 0.0, dtau_dw = 0.0;
+    double alpha, beta, gamma, delta, edt;
+
+    for (; k != ke - dk; k += dk)
+    {
+        ds_dw2 = fabs(h[k + 2 * dk] - h[k + dk]) * zmu;
+        double dx_dw = cent_deriv(ds_dw, ds_dw2, chi[k], chi[k + dk], chi[k + 2 * dk]);
+        Cuw = chi[k] + (ds_dw / 3.0) * dx_c;
+        C0 = chi[k + dk] - (ds_dw / 3.0) * dx_dw;
+        dtau_dw = ds_dw * (chi[k] + chi[k + dk] + Cuw + C0) * 0.25;
+
+        bezier3_coeffs(dtau_uw, &alpha, &beta, &gamma, &delta, &edt);
+        double dS_c = cent_deriv(dtau_uw, dtau_dw, S[k - dk], S[k], S[k + dk]);
+        Cuw = S[k - dk] + (dtau_uw / 3.0) * dS_uw;
+        C0 = S[k] - (dtau_uw / 3.0) * dS_c;
+        I[k] = I_upw * edt + alpha * S[k - dk] + beta * S[k] + gamma * Cuw + delta * C0;
+        if (Psi) Psi[k] = beta + delta;
+
+        I_upw = I[k];
+        ds_uw = ds_dw;
+        ds_dw = ds_dw2;
+        dx_uw = dx_c;
+        dx_c = dx_dw;
+        dtau_uw = dtau_dw;
+        dS_uw = dS_c;
+    }
+    /* second to last point: one-sided downwind derivative (:286-305) */
+    k = ke - dk;
+    ds_dw = fabs(h[k + dk] - h[k]) * zmu;
+    double dx_dw = (chi[k + dk] - chi[k]) / ds_dw;
+    Cuw = chi[k] + (ds_dw / 3.0) * dx_c;
+    C0 = chi[k + dk] - (ds_dw / 3.0) * dx_dw;
+    dtau_dw = ds_dw * (chi[k] + chi[k + dk] + Cuw + C0) * 0.25;
+    bezier3_coeffs(dtau_uw, &alpha, &beta, &gamma, &delta, &edt);
+    double dS_c = cent_deriv(dtau_uw, dtau_dw, S[k - dk], S[k], S[k + dk]);
+    Cuw = S[k - dk] + dtau_uw / 3.0 * dS_uw;
+    C0 = S[k] - dtau_uw / 3.0 * dS_c;
+    I[k] = I_upw * edt + alpha * S[k - dk] + beta * S[k] + gamma * Cuw + delta * C0;
+    if (Psi) Psi[k] = beta + delta;
+    I_upw = I[k];
+
+    /* piecewise linear on the end (:307-323) */
+    k = ke;
+    dtau_uw = 0.5 * zmu * (chi[k] + chi[k - dk]) * fabs(h[k] - h[k - dk]);
+    dS_uw = (S[k] - S[k - dk]) / dtau_uw;
+    double w[2];
+    w2(dtau_uw, w);
+    I[k] = (1.0 - w[0]) * I_upw + w[0] * S[k] - w[1] * dS_uw;
+    if (Psi)
+    {
+        Psi[k] = w[0] - w[1] / dtau_uw;
+        for (int kk = 0; kk < K; ++kk) Psi[kk] /= chi[kk];
+    }
+}
+
+/* FormalScalar.cpp:327-363 */
+static double besser_control_point(double hM, double hP, double yM, double yO, double yP)
+{
+    const double dM = (yO - yM) / hM;
+    const double dP = (yP - yO) / hP;
+    if (dM * dP <= 0.0)
+        return yO;
+    double yOp = (hM * dP + hP * dM) / (hM + hP);
+    double cM = yO - 0.5 * hM * yOp;
+    double cP = yO + 0.5 * hP * yOp;
+    double minYMO = yM, maxYMO = yO, minYOP = yO, maxYOP = yP;
+    if (dM < 0.0) { minYMO = yO; maxYMO = yM; minYOP = yP; maxYOP = yO; }
+    if (cM < minYMO || cM > maxYMO)
+        return yM;
+    if (cP < minYOP || cP > maxYOP)
+    {
+        cP = yP;
+        yOp = (cP - yO) / (0.5 * hP);
+        cM = yO - 0.5 * hM * yOp;
+    }
+    return cM;
+}
+
+/* FormalScalar.cpp:373-393 */
+static void besser_coeffs(double t, double* M, double* O, double* Cc, double* edt)
+{
+    if (t < 0.14)
+    {
+        *M = (t * (t * (t * (t * (t * (t * ((140.0 - 18.0 * t) * t - 945.0) + 5400.0) - 25200.0) + 90720.0) - 226800.0) + 302400.0)) / 907200.0;
+        *O = (t * (t * (t * (t * (t * (t * ((10.0 - t) * t - 90.0) + 720.0) - 5040.0) + 30240.0) - 151200.0) + 604800.0)) / 1814400.0;
+        *Cc = (t * (t * (t * (t * (t * (t * ((35.0 - 4.0 * t) * t - 270.0) + 1800.0) - 10080.0) + 45360.0) - 151200.0) + 302400.0)) / 907200.0;
+        *edt = 1.0 - t + 0.5 * sq(t) - cb(t) / 6.0 + t * cb(t) / 24.0 - sq(t) * cb(t) / 120.0 + cb(t) * cb(t) / 720.0 - cb(t) * cb(t) * t / 5040.0;
+    }
+    else
+    {
+        double t2 = sq(t);
+        *edt = exp(-t);
+        *M = (2.0 - *edt * (t2 + 2.0 * t + 2.0)) / t2;
+        *O = 1.0 - 2.0 * (*edt + t - 1.0) / t2;
+        *Cc = 2.0 * (t - 2.0 + *edt * (t + 2.0)) / t2;
+    }
+}
+
+/* FormalScalar.cpp:395-467 */
+static void besser_sweep(int K, const double* h, const double* chi, const double* S, double zmu,
+                         int toObs, double Istart, double* I, double* Psi)
+{
+    int dk = -1, ks = K - 1, ke = 0;
+    if (!toObs) { dk = 1; ks = 0; ke = K - 1; }
+    double I_upw = Istart;
+    I[ks] = I_upw;
+    if (Psi) Psi[ks] = 0.0;
+    int k = ks + dk;
+    for (; k != ke; k += dk)
+    {
+        double ds_uw = fabs(h[k] - h[k - dk]) * zmu;
+        double ds_dw = fabs(h[k + dk] - h[k]) * zmu;
+        double chi_uw = chi[k - dk], chiLocal = chi[k], chi_dw = chi[k + dk];
+        double chiC = besser_control_point(ds_uw, ds_dw, chi_uw, chiLocal, chi_dw);
+        double dtauUw = (1.0 / 3.0) * (chi_uw + chiC + chiLocal) * ds_uw;
+        double dtauDw = 0.5 * (chiLocal + chi_dw) * ds_dw;
+        double Suw = S[k - dk], SLocal = S[k], Sdw = S[k + dk];
+        double SC = besser_control_point(dtauUw, dtauDw, Suw, SLocal, Sdw);
+        double M, O, Cc, edt;
+        besser_coeffs(dtauUw, &M, &O, &Cc, &edt);
+        I[k] = I_upw * edt + M * Suw + O * SLocal + Cc * SC;
+        if (Psi) Psi[k] = O + Cc;
+        I_upw = I[k];
+    }
+    k = ke;
+    double dtau_uw = 0.5 * zmu * (chi[k] + chi[k - dk]) * fabs(h[k] - h[k - dk]);
+    double dS_uw = (S[k] - S[k - dk]) / dtau_uw;
+    double w[2];
+    w2(dtau_uw, w);
+    I[k] = (1.0 - w[0]) * I_upw + w[0] * S[k] - w[1] * dS_uw;
+    if (Psi)
+    {
+        Psi[k] = w[0] - w[1] / dtau_uw;
+        for (int kk = 0; kk < K; ++kk) Psi[kk] /= chi[kk];
+    }
+}
+
+/* Boundary wrappers: FormalScalar.cpp:471-533 (linear), :535-600 (bezier3),
+ * :602-666 (besser). */
+void lwo_solve_ray(int solver, int K, const double* h, const double* T, const double* chi,
+                   const double* S, double muz, int toObs, double wavelength, int lowerBc,
+                   int upperBc, double bcValue, double* I, double* Psi)
+{
+    double zmu = (solver == LWB200_FS_LINEAR) ? 0.5 / muz : 1.0 / muz;
+    int dk = -1, ks = K - 1;
+    if (!toObs) { dk = 1; ks = 0; }
+    double dtau_uw;
+    if (solver == LWB200_FS_LINEAR)
+        dtau_uw = zmu * (chi[ks] + chi[ks + dk]) * fabs(h[ks] - h[ks + dk]);
+    else
+        dtau_uw = 0.5 * zmu * (chi[ks] + chi[ks + dk]) * fabs(h[ks] - h[ks + dk]);
+
+    double Iupw = 0.0;
+    if (toObs)
+    {
+        if (lowerBc == LWB200_BC_THERMALISED)
+        {
+            double Bnu[2];
+            planck_nu(2, &T[K - 2], wavelength, Bnu);
+            Iupw = Bnu[1] - (Bnu[0] - Bnu[1]) / dtau_uw;
+        }
+        else if (lowerBc == LWB200_BC_CALLABLE)
+            Iupw = bcValue;
+    }
+    else
+    {
+        if (upperBc == LWB200_BC_THERMALISED)
+        {
+            double Bnu[2];
+            planck_nu(2, &T[0], wavelength, Bnu);
+            Iupw = Bnu[0] - (Bnu[1] - Bnu[0]) / dtau_uw;
+        }
+        else if (upperBc == LWB200_BC_CALLABLE)
+            Iupw = bcValue;
+    }
+    if (solver == LWB200_FS_LINEAR)
+        linear_sweep(K, h, chi, S, zmu, toObs, Iupw, I, Psi);
+    else if (solver == LWB200_FS_BESSER)
+        besser_sweep(K, h, chi, S, zmu, toObs, Iupw, I, Psi);
+    else
+        bezier3_sweep(K, h, chi, S, zmu, toObs, Iupw, I, Psi);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Transition::wlambda, LwTransition.hpp:71-81 */
+static double wlambda(const LwB200Transition* t, int lt)
+{
+    int len = t->Nred - t->Nblue;
+    const double* w = t->wavelength;
+    if (lt == 0)
+        return 0.5 * (w[1] - w[0]) * t->dopplerWidth;
+    if (lt == len - 1)
+        return 0.5 * (w[len - 1] - w[len - 2]) * t->dopplerWidth;
+    return 0.5 * (w[lt + 1] - w[lt - 1]) * t->dopplerWidth;
+}
+
+typedef struct
+{
+    int K;
+    double *chiTot, *etaTot, *S, *I, *Psi, *Ieff, *Uji, *Vij, *Vji, *JDag;
+    double** gij;   /* [atom][Ntrans*K] */
+    double** wla;
+    double** aEta;  /* [atom][K] */
+    double** aU;    /* [atom][Nlevel*K] */
+    double** aChi;
+    double* pool;
+} Scratch;
+
+static Scratch* scratch_new(const LwB200Problem* p)
+{
+    Scratch* s = (Scratch*)calloc(1, sizeof(Scratch));
+    int K = p->Nspace;
+    s->K = K;
+    size_t n = 10 * (size_t)K;
+    for (int a = 0; a < p->Natom; ++a)
+        n += (size_t)K * (2 * p->atoms[a].Ntrans + 1 + 2 * p->atoms[a].Nlevel);
+    s->pool = (double*)calloc(n, sizeof(double));
+    double* q = s->pool;
+    s->chiTot = q; q += K; s->etaTot = q; q += K; s->S = q; q += K; s->I = q; q += K;
+    s->Psi = q; q += K; s->Ieff = q; q += K; s->Uji = q; q += K; s->Vij = q; q += K;
+    s->Vji = q; q += K; s->JDag = q; q += K;
+    s->gij = (double**)calloc(p->Natom, sizeof(double*));
+    s->wla = (double**)calloc(p->Natom, sizeof(double*));
+    s->aEta = (double**)calloc(p->Natom, sizeof(double*));
+    s->aU = (double**)calloc(p->Natom, sizeof(double*));
+    s->aChi = (double**)calloc(p->Natom, sizeof(double*));
+    for (int a = 0; a < p->Natom; ++a)
+    {
+        const LwB200Atom* at = &p->atoms[a];
+        s->gij[a] = q; q += (size_t)at->Ntrans * K;
+        s->wla[a] = q; q += (size_t)at->Ntrans * K;
+        s->aEta[a] = q; q += K;
+        s->aU[a] = q; q += (size_t)at->Nlevel * K;
+        s->aChi[a] = q; q += (size_t)at->Nlevel * K;
+    }
+    return s;
+}
+
+static void scratch_free(Scratch* s)
+{
+    free(s->gij); free(s->wla); free(s->aEta); free(s->aU); free(s->aChi);
+    free(s->pool);
+    free(s);
+}
+
+static inline int is_active(const LwB200Transition* t, int la) { return la >= t->Nblue && la < t->Nred; }
+
+/* Atom::setup_wavelength, LwAtom.hpp:82-128 */
+static void setup_wavelength(const LwB200Problem* p, int col, int a, int la, Scratch* s)
+{
+    const LwB200Atom* at = &p->atoms[a];
+    const int K = p->Nspace;
+    const double pi4_h = 4.0 * C_PI / C_HPLANCK;
+    const double hc_4pi = 0.25 * C_HC / C_PI;
+    const double pi4_hc = 1.0 / hc_4pi;
+    const double hc_k = C_HC / (C_KBOLTZMANN * C_NM_TO_M);
+    const double* nStar = at->nStar + (size_t)col * at->Nlevel * K;
+    const double* T = p->temperature + (size_t)col * K;
+    for (int kr = 0; kr < at->Ntrans; ++kr)
+    {
+        const LwB200Transition* t = &at->trans[kr];
+        if (!is_active(t, la))
+            continue;
+        double* g = s->gij[a] + (size_t)kr * K;
+        double* w = s->wla[a] + (size_t)kr * K;
+        const int lt = la - t->Nblue;
+        const int Nl = t->Nred - t->Nblue;
+        const double wlam = wlambda(t, lt);
+        if (t->type == LWB200_LINE)
+        {
+            const double* wphi = t->wphi + (size_t)col * K;
+            for (int k = 0; k < K; ++k)
+            {
+                g[k] = t->Bji / t->Bij;
+                w[k] = wlam * wphi[k] * pi4_hc;
+            }
+            if (t->rhoPrd)
+            {
+                const double* rho = t->rhoPrd + ((size_t)col * Nl + lt) * K;
+                for (int k = 0; k < K; ++k)
+                    g[k] *= rho[k];
+            }
+        }
+        else
+        {
+            const double hc_kl = hc_k / t->wavelength[lt];
+            const double wlambda_lambda = wlam / t->wavelength[lt];
+            for (int k = 0; k < K; ++k)
+            {
+                g[k] = nStar[(size_t)t->i * K + k] / nStar[(size_t)t->j * K + k] * exp(-hc_kl / T[k]);
+                w[k] = wlambda_lambda * pi4_h;
+            }
+        }
+    }
+}
+
+/* Transition::uv, LwTransition.hpp:93-144 */
+static void uv(const LwB200Problem* p, int col, int a, int kr, int la, int mu, int toObs, Scratch* s)
+{
+    const LwB200Transition* t = &p->atoms[a].trans[kr];
+    const int K = p->Nspace, M = p->Nrays;
+    const int lt = la - t->Nblue;
+    const int Nl = t->Nred - t->Nblue;
+    const double* g = s->gij[a] + (size_t)kr * K;
+    if (t->type == LWB200_LINE)
+    {
+        const double hc_4pi = 0.25 * C_HC / C_PI;
+        const double hnu_4pi = hc_4pi * (t->lambda0 / t->wavelength[lt]);
+        const double* ph = t->phi + ((((size_t)col * Nl + lt) * M + mu) * 2 + toObs) * K;
+        for (int k = 0; k < K; ++k)
+        {
+            s->Vij[k] = hnu_4pi * t->Bij * ph[k];
+            s->Vji[k] = g[k] * s->Vij[k];
+        }
+        for (int k = 0; k < K; ++k)
+            s->Uji[k] = t->Aji / t->Bji * s->Vji[k];
+    }
+    else
+    {
+        const double twoHc = 2.0 * C_HC / cb(C_NM_TO_M);
+        const double hcl = twoHc / cb(t->wavelength[lt]);
+        const double al = t->alpha[lt];
+        for (int k = 0; k < K; ++k)
+        {
+            s->Vij[k] = al;
+            s->Vji[k] = g[k] * s->Vij[k];
+            s->Uji[k] = hcl * s->Vji[k];
+        }
+    }
+}
+
+/* gather_opacity_emissivity_opt + chi_eta_aux_accum,
+ * SimdFullIterationTemplates.hpp:59-167.  Per-atom aux arrays are zeroed per
+ * call instead of using the reference's "first write stores" flags (:124-147);
+ * the values read afterwards are identical. */
+static void gather(const LwB200Problem* p, int col, int la, int mu, int toObs, Scratch* s)
+{
+    const int K = p->Nspace;
+    for (int a = 0; a < p->Natom; ++a)
+    {
+        const LwB200Atom* at = &p->atoms[a];
+        const double* n = at->n + (size_t)col * at->Nlevel * K;
+        double* aChi = s->aChi[a];
+        double* aU = s->aU[a];
+        double* aEta = s->aEta[a];
+        if (!at->detailedStatic)
+        {
+            memset(aChi, 0, sizeof(double) * at->Nlevel * K);
+            memset(aU, 0, sizeof(double) * at->Nlevel * K);
+            memset(aEta, 0, sizeof(double) * K);
+        }
+        for (int kr = 0; kr < at->Ntrans; ++kr)
+        {
+            const LwB200Transition* t = &at->trans[kr];
+            if (!is_active(t, la))
+                continue;
+            uv(p, col, a, kr, la, mu, toObs, s);
+            for (int k = 0; k < K; ++k)
+            {
+                double chi = n[(size_t)t->i * K + k] * s->Vij[k] - n[(size_t)t->j * K + k] * s->Vji[k];
+                double eta = n[(size_t)t->j * K + k] * s->Uji[k];
+                if (!at->detailedStatic)
+                {
+                    aChi[(size_t)t->i * K + k] += chi;
+                    aChi[(size_t)t->j * K + k] -= chi;
+                    aU[(size_t)t->j * K + k] += s->Uji[k];
+                    aEta[k] += eta;
+                }
+                s->chiTot[k] += chi;
+                s->etaTot[k] += eta;
+            }
+        }
+    }
+}
+
+/* continua_only, SimdFullIterationTemplates.hpp:30-57 */
+static int continua_only(const LwB200Problem* p, int la)
+{
+    for (int a = 0; a < p->Natom; ++a)
+        for (int kr = 0; kr < p->atoms[a].Ntrans; ++kr)
+        {
+            const LwB200Transition* t = &p->atoms[a].trans[kr];
+            if (is_active(t, la) && t->type != LWB200_CONTINUUM)
+                return 0;
+        }
+    return 1;
+}
+
+static double bc_value(const LwB200Problem* p, int col, int la, int mu, int toObs)
+{
+    if (toObs && p->lowerBc == LWB200_BC_CALLABLE)
+    {
+        int idx = p->lowerBcIdx[mu * 2 + toObs];
+        return p->lowerBcData[((size_t)col * p->Nspect + la) * p->NlowerBcMu + idx];
+    }
+    if (!toObs && p->upperBc == LWB200_BC_CALLABLE)
+    {
+        int idx = p->upperBcIdx[mu * 2 + toObs];
+        return p->upperBcData[((size_t)col * p->Nspect + la) * p->NupperBcMu + idx];
+    }
+    return 0.0;
+}
+
+/* intensity_core_opt, SimdFullIterationTemplates.hpp:238-487.
+ * updateRates/computeOperator both on for the Gamma iteration, both off for
+ * formal_sol. */
+static double intensity_core(const LwB200Problem* p, int col, int la, Scratch* s, int fullIter,
+                             int lambdaIterate, int upOnly, int storeDepth)
+{
+    const int K = p->Nspace, M = p->Nrays, L = p->Nspect;
+    const double* h = p->height + (size_t)col * K;
+    const double* T = p->temperature + (size_t)col * K;
+    double* J = p->J + ((size_t)col * L + la) * K;
+    const double* bgChi = p->chiBg + ((size_t)col * L + la) * K;
+    const double* bgEta = p->etaBg + ((size_t)col * L + la) * K;
+    const double* bgSca = p->scaBg + ((size_t)col * L + la) * K;
+    const double wav = p->wavelength[la];
+
+    memcpy(s->JDag, J, sizeof(double) * K);
+    if (fullIter)
+        memset(J, 0, sizeof(double) * K);
+
+    for (int a = 0; a < p->Natom; ++a)
+        setup_wavelength(p, col, a, la, s);
+
+    const int contOnly = continua_only(p, la);
+    const int toObsStart = upOnly ? 1 : 0;
+
+    for (int mu = 0; mu < M; ++mu)
+    {
+        for (int toObs = toObsStart; toObs < 2; ++toObs)
+        {
+            if (!contOnly || (mu == 0 && toObs == toObsStart))
+            {
+                memcpy(s->chiTot, bgChi, sizeof(double) * K);
+                memcpy(s->etaTot, bgEta, sizeof(double) * K);
+                gather(p, col, la, mu, toObs, s);
+                for (int k = 0; k < K; ++k)
+                    s->S[k] = (s->etaTot[k] + bgSca[k] * s->JDag[k]) / s->chiTot[k];
+                if (storeDepth)
+                {
+                    if (!contOnly)
+                    {
+                        size_t off = ((((size_t)col * L + la) * M + mu) * 2 + toObs) * K;
+                        memcpy(p->depthChi + off, s->chiTot, sizeof(double) * K);
+                        memcpy(p->depthEta + off, s->etaTot, sizeof(double) * K);
+                    }
+                    else
+                    {
+                        for (int m2 = 0; m2 < M; ++m2)
+                            for (int d2 = 0; d2 < 2; ++d2)
+                            {
+                                size_t off = ((((size_t)col * L + la) * M + m2) * 2 + d2) * K;
+                                memcpy(p->depthChi + off, s->chiTot, sizeof(double) * K);
+                                memcpy(p->depthEta + off, s->etaTot, sizeof(double) * K);
+                            }
+                    }
+                }
+            }
+
+            lwo_solve_ray(p->formalSolver, K, h, T, s->chiTot, s->S, p->muz[mu], toObs, wav,
+                          p->lowerBc, p->upperBc, bc_value(p, col, la, mu, toObs), s->I,
+                          fullIter ? s->Psi : NULL);
+            p->I[((size_t)col * L + la) * M + mu] = s->I[0];
+
+            if (fullIter)
+            {
+                const double halfwmu = 0.5 * p->wmu[mu];
+                for (int k = 0; k < K; ++k)
+                    J[k] += halfwmu * s->I[k];
+
+                for (int a = 0; a < p->Natom; ++a)
+                {
+                    const LwB200Atom* at = &p->atoms[a];
+                    const int N = at->Nlevel;
+                    if (!at->detailedStatic)
+                    {
+                        if (lambdaIterate)
+                            memset(s->Psi, 0, sizeof(double) * K);
+                        for (int k = 0; k < K; ++k)
+                            s->Ieff[k] = s->I[k] - s->Psi[k] * s->aEta[a][k];
+                    }
+                    double* Gamma = at->detailedStatic ? NULL : at->Gamma + (size_t)col * N * N * K;
+                    for (int kr = 0; kr < at->Ntrans; ++kr)
+                    {
+                        const LwB200Transition* t = &at->trans[kr];
+                        if (!is_active(t, la))
+                            continue;
+                        uv(p, col, a, kr, la, mu, toObs, s);
+                        const double* wla = s->wla[a] + (size_t)kr * K;
+                        double* Rij = t->Rij + (size_t)col * K;
+                        double* Rji = t->Rji + (size_t)col * K;
+                        /* compute_full_operator_rates, :206-234 */
+                        for (int k = 0; k < K; ++k)
+                        {
+                            const double wlamu = wla[k] * halfwmu;
+                            if (Gamma)
+                            {
+                                double integrand = (s->Uji[k] + s->Vji[k] * s->Ieff[k])
+                                    - (s->Psi[k] * s->aChi[a][(size_t)t->i * K + k] * s->aU[a][(size_t)t->j * K + k]);
+                                Gamma[((size_t)t->i * N + t->j) * K + k] += integrand * wlamu;
+                                integrand = (s->Vij[k] * s->Ieff[k])
+                                    - (s->Psi[k] * s->aChi[a][(size_t)t->j * K + k] * s->aU[a][(size_t)t->i * K + k]);
+                                Gamma[((size_t)t->j * N + t->i) * K + k] += integrand * wlamu;
+                            }
+                            Rij[k] += s->I[k] * s->Vij[k] * wlamu;
+                            Rji[k] += (s->Uji[k] + s->I[k] * s->Vji[k]) * wlamu;
+                        }
+                    }
+                }
+                if (storeDepth)
+                {
+                    size_t off = ((((size_t)col * L + la) * M + mu) * 2 + toObs) * K;
+                    memcpy(p->depthI + off, s->I, sizeof(double) * K);
+                }
+            }
+        }
+    }
+
+    double dJMax = 0.0;
+    if (fullIter)
+        for (int k = 0; k < K; ++k)
+        {
+            double dJ = fabs(1.0 - s->JDag[k] / J[k]);
+            dJMax = dmax(dJ, dJMax);
+        }
+    return dJMax;
+}
+
+/* formal_sol_iteration_matrices_impl, Nthreads <= 1 branch (:597-637), then
+ * finalise_Gamma (:491-508).  With a sub-range [laStart, laEnd) the Gamma
+ * diagonal is still finalised, which is only meaningful for the full range. */
+int lwo_fs_iter(const LwB200Problem* p, int col, unsigned flags, int laStart, int laEnd,
+                double* dJMaxOut, int64_t* dJMaxIdx, int64_t* dJMaxIdxSerial)
+{
+    const int K = p->Nspace;
+    if (laStart < 0) laStart = 0;
+    if (laEnd < 0 || laEnd > p->Nspect) laEnd = p->Nspect;
+    Scratch* s = scratch_new(p);
+    for (int a = 0; a < p->Natom; ++a)
+        for (int kr = 0; kr < p->atoms[a].Ntrans; ++kr)
+        {
+            memset(p->atoms[a].trans[kr].Rij + (size_t)col * K, 0, sizeof(double) * K);
+            memset(p->atoms[a].trans[kr].Rji + (size_t)col * K, 0, sizeof(double) * K);
+        }
+    double dJMax = 0.0, dJSerial = 0.0;
+    int64_t idx = 0, idxSerial = 0;
+    const int storeDepth = (flags & LWB200_STORE_DEPTH) && p->depthChi && p->depthEta && p->depthI;
+    for (int la = laStart; la < laEnd; ++la)
+    {
+        double dJ = intensity_core(p, col, la, s, 1, (flags & LWB200_LAMBDA_ITERATE) != 0, 0, storeDepth);
+        /* threaded branch: td.dJ = max_idx(td.dJ, dJ, td.dJIdx, la)  (:688) */
+        if (dJMax < dJ) { dJMax = dJ; idx = la; }
+        /* serial branch: dJMax = max_idx(dJ, dJMax, maxIdx, la)  (:627; Constants.hpp:114-125) */
+        if (dJ < dJSerial) { idxSerial = la; } else { dJSerial = dJ; }
+    }
+    for (int a = 0; a < p->Natom; ++a)
+    {
+        const LwB200Atom* at = &p->atoms[a];
+        if (at->detailedStatic)
+            continue;
+        const int N = at->Nlevel;
+        double* G = at->Gamma + (size_t)col * N * N * K;
+        for (int k = 0; k < K; ++k)
+            for (int i = 0; i < N; ++i)
+            {
+                G[((size_t)i * N + i) * K + k] = 0.0;
+                double diag = 0.0;
+                for (int j = 0; j < N; ++j)
+                    diag += G[((size_t)j * N + i) * K + k];
+                G[((size_t)i * N + i) * K + k] = -diag;
+            }
+    }
+    scratch_free(s);
+    if (dJMaxOut) *dJMaxOut = dJMax;
+    if (dJMaxIdx) *dJMaxIdx = idx;
+    if (dJMaxIdxSerial) *dJMaxIdxSerial = idxSerial;
+    return 0;
+}
+
+/* formal_sol_impl, SimdFullIterationTemplates.hpp:721-737 */
+int lwo_formal_sol(const LwB200Problem* p, int col, int upOnly)
+{
+    Scratch* s = scratch_new(p);
+    for (int la = 0; la < p->Nspect; ++la)
+        intensity_core(p, col, la, s, 0, 0, upOnly, 0);
+    scratch_free(s);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* lu_decompose, LuSolve.cpp:8-70.  Returns 1 for the "Singular Matrix" throw. */
+static int lu_decompose(int N, double* A, int* index)
+{
+    const double Tiny = 1e-20;
+    double vv[64];
+    for (int i = 0; i < N; ++i)
+    {
+        double big = 0.0;
+        for (int j = 0; j < N; ++j)
+            big = dmax(big, fabs(A[i * N + j]));
+        if (big == 0.0)
+            return 1;
+        vv[i] = 1.0 / big;
+    }
+    for (int j = 0; j < N; ++j)
+    {
+        for (int i = 0; i < j; ++i)
+        {
+            double sum = A[i * N + j];
+            for (int k = 0; k < i; ++k)
+                sum -= A[i * N + k] * A[k * N + j];
+            A[i * N + j] = sum;
+        }
+        int iMax = 0;
+        double big = 0.0;
+        for (int i = j; i < N; ++i)
+        {
+            double sum = A[i * N + j];
+            for (int k = 0; k < j; ++k)
+                sum -= A[i * N + k] * A[k * N + j];
+            A[i * N + j] = sum;
+            double cand = vv[i] * fabs(sum);
+            if (big < cand) { big = cand; iMax = i; } /* max_idx(big, cand, iMax, i) */
+        }
+        if (j != iMax)
+        {
+            for (int k = 0; k < N; ++k)
+            {
+                double temp = A[iMax * N + k];
+                A[iMax * N + k] = A[j * N + k];
+                A[j * N + k] = temp;
+            }
+            vv[iMax] = vv[j];
+        }
+        index[j] = iMax;
+        if (A[j * N + j] == 0.0)
+            A[j * N + j] = Tiny;
+        double temp = 1.0 / A[j * N + j];
+        for (int i = j + 1; i < N; ++i)
+            A[i * N + j] *= temp;
+    }
+    return 0;
+}
+
+/* lu_backsub, LuSolve.cpp:72-101 */
+static void lu_backsub(int N, const double* A, const int* index, double* b)
+{
+    int ii = -1;
+    for (int i = 0; i < N; ++i)
+    {
+        int ip = index[i];
+        double sum = b[ip];
+        b[ip] = b[i];
+        if (ii >= 0)
+        {
+            for (int j = ii; j < i; ++j)
+                sum -= A[i * N + j] * b[j];
+        }
+        else if (sum != 0.0)
+            ii = i;
+        b[i] = sum;
+    }
+    for (int i = N - 1; i >= 0; --i)
+    {
+        double sum = b[i];
+        for (int j = i + 1; j < N; ++j)
+            sum -= A[i * N + j] * b[j];
+        b[i] = sum / A[i * N + i];
+    }
+}
+
+/* solve_lin_eq, LuSolve.cpp:103-133 */
+int lwo_solve_lin_eq(int N, double* A, double* b, int improve)
+{
+    if (N > 64)
+        return 2;
+    double ACopy[64 * 64], bCopy[64], residual[64];
+    int index[64];
+    if (improve)
+    {
+        memcpy(ACopy, A, sizeof(double) * N * N);
+        memcpy(bCopy, b, sizeof(double) * N);
+    }
+    if (lu_decompose(N, A, index))
+        return 1;
+    lu_backsub(N, A, index, b);
+    if (improve)
+    {
+        memcpy(residual, bCopy, sizeof(double) * N);
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j)
+                residual[i] -= ACopy[i * N + j] * b[j];
+        lu_backsub(N, A, index, residual);
+        for (int i = 0; i < N; ++i)
+            b[i] += residual[i];
+    }
+    return 0;
+}
+
+/* stat_eq_impl, UpdatePopulations.cpp:7-47 */
+int lwo_stat_eq(const LwB200Problem* p, int col, int atom, int kStart, int kEnd, int* nSingular)
+{
+    const int K = p->Nspace;
+    if (kStart < 0 && kEnd < 0) { kStart = 0; kEnd = K; }
+    int singular = 0;
+    for (int a = 0; a < p->Natom; ++a)
+    {
+        if (atom >= 0 && a != atom)
+            continue;
+        const LwB200Atom* at = &p->atoms[a];
+        if (at->detailedStatic)
+            continue;
+        const int N = at->Nlevel;
+        if (N > 64)
+            return 2;
+        double* n = at->n + (size_t)col * N * K;
+        const double* G = at->Gamma + (size_t)col * N * N * K;
+        const double* nTotal = at->nTotal + (size_t)col * K;
+        double nk[64], Gam[64 * 64];
+        for (int k = kStart; k < kEnd; ++k)
+        {
+            for (int i = 0; i < N; ++i)
+            {
+                nk[i] = n[(size_t)i * K + k];
+                for (int j = 0; j < N; ++j)
+                    Gam[i * N + j] = G[((size_t)i * N + j) * K + k];
+            }
+            int iEliminate = 0;
+            double nMax = 0.0;
+            for (int i = 0; i < N; ++i)
+                if (nMax < nk[i]) { nMax = nk[i]; iEliminate = i; } /* max_idx(nMax, nk(i), ...) */
+            for (int i = 0; i < N; ++i)
+            {
+                Gam[iEliminate * N + i] = 1.0;
+                nk[i] = 0.0;
+            }
+            nk[iEliminate] = nTotal[k];
+            if (lwo_solve_lin_eq(N, Gam, nk, 1))
+            {
+                singular += 1;
+                continue;
+            }
+            for (int i = 0; i < N; ++i)
+                n[(size_t)i * K + k] = nk[i];
+        }
+    }
+    if (nSingular) *nSingular = singular;
+    return singular ? 1 : 0;
+}
+
+typedef struct
+{
+    const LwB200Problem* p;
+    int colEnd, withStatEq;
+    unsigned flags;
+    atomic_int next;
+    atomic_int rc;
+} ColumnJob;
+
+static void* column_worker(void* arg)
+{
+    ColumnJob* job = (ColumnJob*)arg;
+    for (;;)
+    {
+        int c = atomic_fetch_add(&job->next, 1);
+        if (c >= job->colEnd)
+            break;
+        int rc = lwo_fs_iter(job->p, c, job->flags, 0, -1, NULL, NULL, NULL);
+        if (job->withStatEq)
+        {
+            int ns = 0;
+            rc |= lwo_stat_eq(job->p, c, -1, -1, -1, &ns);
+        }
+        if (rc)
+            atomic_fetch_or(&job->rc, rc);
+    }
+    return NULL;
+}
+
+/* Columns are independent: one worker per host thread pulls columns off a
+ * shared counter (the user-level ProcessPool/MPI pattern the reference's docs
+ * describe for 1.5D, docs/index.rst:37-40). */
+int lwo_fs_iter_columns(const LwB200Problem* p, int col0, int ncol, unsigned flags, int withStatEq,
+                        int nthreads)
+{
+    ColumnJob job;
+    job.p = p;
+    job.colEnd = col0 + ncol;
+    job.withStatEq = withStatEq;
+    job.flags = flags;
+    atomic_init(&job.next, col0);
+    atomic_init(&job.rc, 0);
+    if (nthreads < 1)
+        nthreads = 1;
+    if (nthreads > 256)
+        nthreads = 256;
+    pthread_t th[256];
+    for (int t = 1; t < nthreads; ++t)
+        pthread_create(&th[t], NULL, column_worker, &job);
+    column_worker(&job);
+    for (int t = 1; t < nthreads; ++t)
+        pthread_join(th[t], NULL);
+    return atomic_load(&job.rc);
+}

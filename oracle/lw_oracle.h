@@ -1,0 +1,57 @@
+/* lw_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C CPU restatement of the reference's formal-solution / Gamma-iteration /
+ * stat-eq hot path, operating on the same LwB200Problem the CUDA library takes.
+ * Parity is PINNED: tests/test_oracle_vs_ref.py checks it against the
+ * reference's own compiled C++ (oracle/_ref, scalar scheme) and
+ * tests/golden/*.npz holds outputs of that reference for use where
+ * /root/reference does not exist (the GPU box).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may link or load this.
+ */
+#ifndef LW_ORACLE_H
+#define LW_ORACLE_H
+#include "../include/lwb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One ray through one of the three 1D solvers (FormalScalar.cpp:136-666).
+ * Psi may be NULL.  lowerBc/upperBc: LWB200_BC_ZERO or _THERMALISED, or
+ * _CALLABLE with the boundary intensity in bcValue. */
+void lwo_solve_ray(int solver, int Nspace, const double* height, const double* temperature,
+                   const double* chi, const double* S, double muz, int toObs, double wavelength,
+                   int lowerBc, int upperBc, double bcValue, double* I, double* Psi);
+
+/* formal_sol_gamma_matrices on column `col` (SimdFullIterationTemplates.hpp:588-637,
+ * Nthreads <= 1 branch).  flags: LWB200_LAMBDA_ITERATE | LWB200_STORE_DEPTH.
+ * dJMaxIdx is the argmax wavelength (what the reference's threaded branch
+ * returns, :688,:703); dJMaxIdxSerial reproduces the single-threaded branch's
+ * index (:627, argument order of max_idx). */
+int lwo_fs_iter(const LwB200Problem* p, int col, unsigned flags, int laStart, int laEnd,
+                double* dJMax, int64_t* dJMaxIdx, int64_t* dJMaxIdxSerial);
+
+/* formal_sol (SimdFullIterationTemplates.hpp:721-737). */
+int lwo_formal_sol(const LwB200Problem* p, int col, int upOnly);
+
+/* stat_eq_impl (UpdatePopulations.cpp:7-47); atom < 0: all active atoms.
+ * Returns 0, or 1 with *nSingular > 0 when lu_decompose would have thrown. */
+int lwo_stat_eq(const LwB200Problem* p, int col, int atom, int kStart, int kEnd, int* nSingular);
+
+/* solve_lin_eq (LuSolve.cpp:103-133); returns 1 for "Singular Matrix". */
+int lwo_solve_lin_eq(int N, double* A, double* b, int improve);
+
+/* Gamma iteration (+ optional stat_eq) over columns [col0, col0+ncol) on
+ * nthreads OpenMP threads -- the "port" CPU baseline for column stacks. */
+int lwo_fs_iter_columns(const LwB200Problem* p, int col0, int ncol, unsigned flags,
+                        int withStatEq, int nthreads);
+
+/* Transition::compute_phi / compute_wphi are NOT restated here (they need
+ * Faddeeva); the tests use scipy.special.wofz (the same Faddeeva package). */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,96 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes wrapper of oracle/liblw_oracle.so (the
+plain-C restatement, oracle/lw_oracle.c)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, 'liblw_oracle.so')
+    src = os.path.join(_HERE, 'lw_oracle.c')
+    deps = [src, os.path.join(_HERE, 'lw_oracle.h'), os.path.join(_HERE, '..', 'include', 'lwb200.h')]
+    if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(['make', '-C', _HERE, 'oracle'], stdout=subprocess.DEVNULL)
+    return so
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    so = os.path.join(_HERE, 'liblw_oracle.so')
+    if not os.path.exists(so):
+        build()
+    lib = C.CDLL(so)
+    vp, dp = C.c_void_p, C.POINTER(C.c_double)
+    i64p = C.POINTER(C.c_int64)
+    lib.lwo_solve_ray.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_int, C.c_double,
+                                  C.c_int, C.c_int, C.c_double, dp, dp]
+    lib.lwo_solve_ray.restype = None
+    lib.lwo_fs_iter.argtypes = [vp, C.c_int, C.c_uint, C.c_int, C.c_int, dp, i64p, i64p]
+    lib.lwo_formal_sol.argtypes = [vp, C.c_int, C.c_int]
+    lib.lwo_stat_eq.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.lwo_solve_lin_eq.argtypes = [C.c_int, dp, dp, C.c_int]
+    lib.lwo_fs_iter_columns.argtypes = [vp, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int]
+    _lib = lib
+    return lib
+
+
+class OracleContext:
+    """Same call surface as reflib.RefContext, results in place in the Problem."""
+
+    def __init__(self, problem, col=0):
+        self.lib = load()
+        self.problem = problem
+        self.col = col
+        self._cs = problem.c_struct()
+
+    def fs_iter(self, lambdaIterate=False, storeDepth=False, laStart=0, laEnd=-1, serial_idx=False):
+        dJ, idx, idxS = C.c_double(), C.c_int64(), C.c_int64()
+        flags = (1 if lambdaIterate else 0) | (2 if storeDepth else 0)
+        rc = self.lib.lwo_fs_iter(C.byref(self._cs), self.col, flags, laStart, laEnd,
+                                  C.byref(dJ), C.byref(idx), C.byref(idxS))
+        assert rc == 0
+        return dJ.value, (idxS.value if serial_idx else idx.value)
+
+    def formal_sol(self, upOnly=True):
+        assert self.lib.lwo_formal_sol(C.byref(self._cs), self.col, int(upOnly)) == 0
+
+    def stat_eq(self, atom=-1, kStart=-1, kEnd=-1):
+        ns = C.c_int(0)
+        rc = self.lib.lwo_stat_eq(C.byref(self._cs), self.col, atom, kStart, kEnd, C.byref(ns))
+        if rc != 0:
+            raise RuntimeError('Singular Matrix')
+
+    def fs_iter_columns(self, col0, ncol, withStatEq=False, nthreads=0):
+        rc = self.lib.lwo_fs_iter_columns(C.byref(self._cs), col0, ncol, 0, int(withStatEq), nthreads)
+        assert rc == 0
+
+
+def solve_ray(solver, height, temperature, chi, S, muz, toObs, wavelength, lowerBc, upperBc,
+              bcValue=0.0, want_psi=True):
+    lib = load()
+    K = len(height)
+    dp = C.POINTER(C.c_double)
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (height, temperature, chi, S)]
+    I, Psi = np.zeros(K), np.zeros(K)
+    lib.lwo_solve_ray(solver, K, *[a.ctypes.data_as(dp) for a in arrs], float(muz), int(toObs),
+                      float(wavelength), lowerBc, upperBc, float(bcValue), I.ctypes.data_as(dp),
+                      Psi.ctypes.data_as(dp) if want_psi else dp())
+    return I, Psi
+
+
+def solve_lin_eq(A, b, improve=True):
+    lib = load()
+    A = np.array(A, dtype=np.float64, order='C')
+    b = np.array(b, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    rc = lib.lwo_solve_lin_eq(A.shape[0], A.ctypes.data_as(dp), b.ctypes.data_as(dp), int(improve))
+    if rc:
+        raise RuntimeError('Singular Matrix')
+    return b

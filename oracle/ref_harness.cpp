@@ -1,0 +1,465 @@
+// ref_harness.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// Drives the UNMODIFIED reference C++ (compiled from /root/reference/Source where
+// it lies, see oracle/Makefile) on the flat LwB200Problem that the CUDA library
+// consumes, so that the reference, the C restatement (oracle/lw_oracle.c) and
+// the GPU path all see bit-identical inputs.  Built into oracle/_ref/
+// (git-ignored); only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load it.
+//
+// It fills the reference's POD structs with non-owning views the way the Cython
+// middle layer does (reference: Source/LwMiddleLayer.pyx LwAtmosphere.__init__
+// :620-715, LwSpectrum :2724-2732, LwBackground :1571-1597, LwTransition
+// :1772-1825, LwAtom :2346-2424, LwContext :2946-2973) and then calls the
+// reference's own entry points formal_sol_gamma_matrices / formal_sol / stat_eq
+// (Source/Lightweaver.hpp:21-32).  Iteration schemes: the built-in scalar one
+// (the parity oracle), the reference's SIMD plugins (timing baseline), or any
+// plugin path -- which is how tests load OUR plugin through the reference's own
+// FsIterationFnsManager::load_fns_from_path (Source/FormalInterface.cpp:62-81).
+
+#include "Lightweaver.hpp"
+#include "../include/lwb200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <deque>
+#include <dlfcn.h>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace
+{
+thread_local std::string g_err;
+
+struct LwRef
+{
+    const LwB200Problem* prob = nullptr;
+    int col = 0;
+    Atmosphere atmos{};
+    Spectrum spect{};
+    Background background{};
+    DepthData depth{};
+    std::deque<Atom> atoms;
+    std::deque<Transition> trans;
+    std::deque<std::vector<int8_t>> activeMasks;
+    std::vector<f64> stagesDummy;
+    std::vector<f64> vzDummy;
+    std::vector<std::vector<f64>> gammaPrefill;
+    FormalSolverManager fsManager;
+    FsIterationFnsManager iterManager;
+    std::unique_ptr<Context> ctx;
+};
+
+std::string harness_dir()
+{
+    Dl_info info;
+    if (dladdr((void*)&harness_dir, &info) && info.dli_fname)
+    {
+        std::string p(info.dli_fname);
+        auto pos = p.find_last_of('/');
+        if (pos != std::string::npos)
+            return p.substr(0, pos);
+    }
+    return ".";
+}
+}
+
+extern "C"
+{
+struct LwRefHandle;
+
+const char* lwref_last_error() { return g_err.c_str(); }
+
+// scheme: "scalar" | "SSE2" | "AVX2FMA" | "AVX512" | path of an iteration-scheme plugin.
+int lwref_create(const LwB200Problem* p, int col, const char* scheme, int Nthreads, LwRefHandle** out)
+{
+    try
+    {
+        if (!p || p->abiVersion != LWB200_ABI_VERSION)
+            throw std::runtime_error("lwref_create: bad problem / ABI version");
+        if (col < 0 || col >= p->Ncol)
+            throw std::runtime_error("lwref_create: column out of range");
+
+        auto h = std::make_unique<LwRef>();
+        h->prob = p;
+        h->col = col;
+        const i64 K = p->Nspace;
+        const i64 M = p->Nrays;
+        const i64 L = p->Nspect;
+        const i64 c = col;
+
+        auto& a = h->atmos;
+        a.Nspace = K; a.Nrays = M; a.Ndim = 1;
+        a.Nx = 0; a.Ny = 0; a.Nz = K; a.Noutgoing = 1;
+        a.height = F64View(const_cast<f64*>(p->height) + c * K, K);
+        a.z = a.height;
+        a.temperature = F64View(const_cast<f64*>(p->temperature) + c * K, K);
+        h->vzDummy.assign(K, 0.0);
+        a.vz = F64View(h->vzDummy.data(), K);
+        if (p->vlosMu)
+            a.vlosMu = F64View2D(const_cast<f64*>(p->vlosMu) + c * M * K, M, K);
+        a.muz = F64View(const_cast<f64*>(p->muz), M);
+        a.wmu = F64View(const_cast<f64*>(p->wmu), M);
+
+        auto set_bc = [&](AtmosphericBoundaryCondition& bc, int type, int Nmu,
+                          const f64* data, const int32_t* idx)
+        {
+            BcIdxs idxs;
+            if (idx)
+                idxs = BcIdxs(const_cast<i32*>(idx), M, 2);
+            bc = AtmosphericBoundaryCondition((RadiationBc)type, L, Nmu, 1, idxs);
+            if (type == CALLABLE)
+            {
+                if (!data || !idx)
+                    throw std::runtime_error("CALLABLE boundary without data/idxs");
+                for (i64 la = 0; la < L; ++la)
+                    for (int mu = 0; mu < Nmu; ++mu)
+                        bc.bcData(la, mu, 0) = data[(c * L + la) * Nmu + mu];
+            }
+        };
+        set_bc(a.zLowerBc, p->lowerBc, p->NlowerBcMu, p->lowerBcData, p->lowerBcIdx);
+        set_bc(a.zUpperBc, p->upperBc, p->NupperBcMu, p->upperBcData, p->upperBcIdx);
+
+        auto& s = h->spect;
+        s.wavelength = F64View(const_cast<f64*>(p->wavelength), L);
+        s.I = F64View3D(p->I + c * L * M, L, M, 1);
+        s.J = F64View2D(p->J + c * L * K, L, K);
+
+        auto& bg = h->background;
+        bg.chi = F64View2D(const_cast<f64*>(p->chiBg) + c * L * K, L, K);
+        bg.eta = F64View2D(const_cast<f64*>(p->etaBg) + c * L * K, L, K);
+        bg.sca = F64View2D(const_cast<f64*>(p->scaBg) + c * L * K, L, K);
+
+        h->ctx = std::make_unique<Context>();
+        auto& ctx = *h->ctx;
+        ctx.atmos = &h->atmos;
+        ctx.spect = &h->spect;
+        ctx.background = &h->background;
+        ctx.depthData = nullptr;
+        if (p->depthChi && p->depthEta && p->depthI)
+        {
+            const i64 n = L * M * 2 * K;
+            h->depth.fill = false;
+            h->depth.chi = F64View4D(p->depthChi + c * n, L, M, 2, K);
+            h->depth.eta = F64View4D(p->depthEta + c * n, L, M, 2, K);
+            h->depth.I = F64View4D(p->depthI + c * n, L, M, 2, K);
+            ctx.depthData = &h->depth;
+        }
+        ctx.methodScratch = nullptr;
+
+        i64 maxLevel = 1;
+        for (int ia = 0; ia < p->Natom; ++ia)
+            maxLevel = std::max<i64>(maxLevel, p->atoms[ia].Nlevel);
+        h->stagesDummy.assign(maxLevel, 0.0);
+
+        for (int ia = 0; ia < p->Natom; ++ia)
+        {
+            const LwB200Atom& pa = p->atoms[ia];
+            h->atoms.emplace_back();
+            Atom& atom = h->atoms.back();
+            const i64 N = pa.Nlevel;
+            atom.Nlevel = N;
+            atom.Ntrans = pa.Ntrans;
+            atom.atmos = &h->atmos;
+            atom.n = F64View2D(pa.n + c * N * K, N, K);
+            atom.nStar = F64View2D(const_cast<f64*>(pa.nStar) + c * N * K, N, K);
+            atom.nTotal = F64View(const_cast<f64*>(pa.nTotal) + c * K, K);
+            if (pa.vBroad)
+                atom.vBroad = F64View(const_cast<f64*>(pa.vBroad) + c * K, K);
+            atom.stages = F64View(h->stagesDummy.data(), N);
+            if (!pa.detailedStatic)
+            {
+                if (!pa.Gamma)
+                    throw std::runtime_error("active atom without Gamma");
+                atom.Gamma = F64View3D(pa.Gamma + c * N * N * K, N, N, K);
+            }
+            atom.methodScratch = nullptr;
+
+            for (int kr = 0; kr < pa.Ntrans; ++kr)
+            {
+                const LwB200Transition& pt = pa.trans[kr];
+                h->trans.emplace_back();
+                Transition& t = h->trans.back();
+                const i64 Nl = pt.Nred - pt.Nblue;
+                t.Nblue = pt.Nblue;
+                t.Nred = pt.Nred;
+                t.type = pt.type == LWB200_LINE ? LINE : CONTINUUM;
+                t.i = pt.i;
+                t.j = pt.j;
+                t.Aji = pt.Aji; t.Bji = pt.Bji; t.Bij = pt.Bij;
+                t.lambda0 = pt.lambda0;
+                t.dopplerWidth = pt.dopplerWidth;
+                t.polarised = false;
+                t.wavelength = F64View(const_cast<f64*>(pt.wavelength), Nl);
+                if (t.type == LINE)
+                {
+                    t.phi = F64View4D(pt.phi + c * Nl * M * 2 * K, Nl, M, 2, K);
+                    t.wphi = F64View(pt.wphi + c * K, K);
+                    if (pt.aDamp)
+                        t.aDamp = F64View(const_cast<f64*>(pt.aDamp) + c * K, K);
+                    if (pt.rhoPrd)
+                        t.rhoPrd = F64View2D(const_cast<f64*>(pt.rhoPrd) + c * Nl * K, Nl, K);
+                }
+                else
+                {
+                    t.alpha = F64View(const_cast<f64*>(pt.alpha), Nl);
+                }
+                h->activeMasks.emplace_back(L, 0);
+                auto& mask = h->activeMasks.back();
+                for (i64 la = pt.Nblue; la < pt.Nred; ++la)
+                    mask[la] = 1;
+                t.active = BoolView((bool*)mask.data(), L);
+                t.Rij = F64View(pt.Rij + c * K, K);
+                t.Rji = F64View(pt.Rji + c * K, K);
+                t.methodScratch = nullptr;
+                atom.trans.push_back(&t);
+            }
+            atom.init_scratch(K, pa.detailedStatic != 0, true, true);
+            if (pa.detailedStatic)
+                ctx.detailedAtoms.push_back(&atom);
+            else
+                ctx.activeAtoms.push_back(&atom);
+        }
+
+        ctx.Nthreads = std::max(Nthreads, 1);
+        if (p->formalSolver < 0 || p->formalSolver > 2)
+            throw std::runtime_error("formalSolver must be 0 (linear), 1 (besser) or 2 (bezier3)");
+        ctx.formalSolver = h->fsManager.formalSolvers[p->formalSolver];
+
+        std::string sch(scheme ? scheme : "scalar");
+        if (sch == "scalar")
+        {
+            ctx.iterFns = h->iterManager.fns[0];
+        }
+        else
+        {
+            std::string path = sch;
+            if (sch == "SSE2" || sch == "AVX2FMA" || sch == "AVX512")
+                path = harness_dir() + "/SimdImpl_" + sch + ".so";
+            if (!h->iterManager.load_fns_from_path(path.c_str()))
+            {
+                const char* why = dlerror();
+                throw std::runtime_error("could not load iteration scheme from " + path
+                                         + (why ? std::string(": ") + why : std::string()));
+            }
+            ctx.iterFns = h->iterManager.fns.back();
+        }
+        ctx.initialise_threads();
+
+        *out = (LwRefHandle*)h.release();
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+void lwref_destroy(LwRefHandle* hh)
+{
+    auto* h = (LwRef*)hh;
+    if (!h)
+        return;
+    if (h->ctx)
+        h->ctx->threading.clear(h->ctx.get());
+    delete h;
+}
+
+const char* lwref_scheme_name(LwRefHandle* hh)
+{
+    return ((LwRef*)hh)->ctx->iterFns.name;
+}
+
+int lwref_set_depth_fill(LwRefHandle* hh, int fill)
+{
+    auto* h = (LwRef*)hh;
+    if (!h->ctx->depthData)
+    {
+        g_err = "no depthData arrays in the problem";
+        return 1;
+    }
+    h->depth.fill = fill != 0;
+    return 0;
+}
+
+// One Gamma iteration.  The caller pre-fills Gamma with crsw*C, as
+// LwContext.formal_sol_gamma_matrices does (LwMiddleLayer.pyx:3198-3203).
+int lwref_fs_iter(LwRefHandle* hh, int lambdaIterate, double* dJMax, int64_t* dJMaxIdx)
+{
+    auto* h = (LwRef*)hh;
+    try
+    {
+        IterationResult r = formal_sol_gamma_matrices(*h->ctx, lambdaIterate != 0, ExtraParams{});
+        if (dJMax) *dJMax = r.dJMax;
+        if (dJMaxIdx) *dJMaxIdx = r.dJMaxIdx;
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+int lwref_formal_sol(LwRefHandle* hh, int upOnly)
+{
+    auto* h = (LwRef*)hh;
+    try
+    {
+        formal_sol(*h->ctx, upOnly != 0, ExtraParams{});
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// stat_eq over every active atom (LwContext.stat_equil, LwMiddleLayer.pyx:3509-3514).
+int lwref_stat_eq(LwRefHandle* hh)
+{
+    auto* h = (LwRef*)hh;
+    try
+    {
+        for (Atom* a : h->ctx->activeAtoms)
+            stat_eq(*h->ctx, a, ExtraParams{}, -1, -1);
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// Transition::compute_phi + compute_wphi for every line from aDamp / vBroad /
+// vlosMu (LwContext.compute_profiles; Source/FormalScalar.cpp:28-134).
+int lwref_compute_profiles(LwRefHandle* hh)
+{
+    auto* h = (LwRef*)hh;
+    try
+    {
+        auto do_atoms = [&](std::vector<Atom*>& atoms)
+        {
+            for (Atom* a : atoms)
+                for (Transition* t : a->trans)
+                {
+                    if (t->type != LINE)
+                        continue;
+                    if (!t->aDamp || !a->vBroad || !h->atmos.vlosMu)
+                        throw std::runtime_error("compute_profiles needs aDamp, vBroad and vlosMu");
+                    t->compute_phi(h->atmos, t->aDamp, a->vBroad);
+                    t->compute_wphi(h->atmos);
+                }
+        };
+        do_atoms(h->ctx->activeAtoms);
+        do_atoms(h->ctx->detailedAtoms);
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// Timing protocol of lightweaver/benchmark.py:84-89 / BASELINE.md section 3:
+// nWarm + nTimed calls, Gamma re-filled from its value at entry before each
+// call, steady_clock around the C++ call only.  seconds[] receives nTimed
+// samples.  withStatEq != 0 adds stat_eq to the timed region (populations are
+// restored afterwards so every call sees the same inputs).
+int lwref_time_fs_iter(LwRefHandle* hh, int nWarm, int nTimed, int withStatEq, double* seconds)
+{
+    auto* h = (LwRef*)hh;
+    try
+    {
+        auto& atoms = h->ctx->activeAtoms;
+        std::vector<std::vector<f64>> prefill, pops;
+        for (Atom* a : atoms)
+        {
+            const i64 n3 = a->Gamma.shape(0) * a->Gamma.shape(1) * a->Gamma.shape(2);
+            prefill.emplace_back(a->Gamma.data, a->Gamma.data + n3);
+            const i64 n2 = a->n.shape(0) * a->n.shape(1);
+            pops.emplace_back(a->n.data, a->n.data + n2);
+        }
+        for (int it = 0; it < nWarm + nTimed; ++it)
+        {
+            for (size_t ia = 0; ia < atoms.size(); ++ia)
+            {
+                std::memcpy(atoms[ia]->Gamma.data, prefill[ia].data(), prefill[ia].size() * sizeof(f64));
+                if (withStatEq)
+                    std::memcpy(atoms[ia]->n.data, pops[ia].data(), pops[ia].size() * sizeof(f64));
+            }
+            auto t0 = std::chrono::steady_clock::now();
+            formal_sol_gamma_matrices(*h->ctx, false, ExtraParams{});
+            if (withStatEq)
+                for (Atom* a : atoms)
+                    stat_eq(*h->ctx, a, ExtraParams{}, -1, -1);
+            auto t1 = std::chrono::steady_clock::now();
+            if (it >= nWarm)
+                seconds[it - nWarm] = std::chrono::duration<double>(t1 - t0).count();
+        }
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// One ray through the reference's own 1D solvers (FormalSolverManager order:
+// 0 linear, 1 besser, 2 bezier3), for solver-level golden vectors.
+int lwref_solve_ray(int solver, int Nspace, const double* height, const double* temperature,
+                    const double* chi, const double* S, double muz, int toObs, double wavelength,
+                    int lowerBc, int upperBc, double* I, double* Psi)
+{
+    try
+    {
+        FormalSolverManager man;
+        if (solver < 0 || solver > 2)
+            throw std::runtime_error("bad solver index");
+        Atmosphere atmos{};
+        atmos.Nspace = Nspace; atmos.Nrays = 1; atmos.Ndim = 1; atmos.Nz = Nspace;
+        atmos.height = F64View(const_cast<f64*>(height), Nspace);
+        atmos.temperature = F64View(const_cast<f64*>(temperature), Nspace);
+        atmos.muz = F64View(&muz, 1);
+        atmos.zLowerBc.type = (RadiationBc)lowerBc;
+        atmos.zUpperBc.type = (RadiationBc)upperBc;
+        LwInternal::FormalData fd;
+        fd.atmos = &atmos;
+        fd.chi = F64View(const_cast<f64*>(chi), Nspace);
+        fd.S = F64View(const_cast<f64*>(S), Nspace);
+        fd.I = F64View(I, Nspace);
+        if (Psi)
+            fd.Psi = F64View(Psi, Nspace);
+        F64View1D wave(&wavelength, 1);
+        man.formalSolvers[solver].solver(&fd, 0, 0, toObs != 0, wave);
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// solve_lin_eq (Source/LuSolve.cpp:103-133) on a caller-owned N x N system.
+int lwref_solve_lin_eq(int N, double* A, double* b, int improve)
+{
+    try
+    {
+        solve_lin_eq(F64View2D(A, N, N), F64View(b, N), improve != 0);
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+}

@@ -1,0 +1,148 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes wrapper of oracle/_ref/liblwref.so, the
+UNMODIFIED reference C++ (built by oracle/Makefile) driven through
+oracle/ref_harness.cpp on an LwB200Problem."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(_HERE, '_ref')
+_lib = None
+
+
+def available():
+    return os.path.exists(os.path.join(REF_DIR, 'liblwref.so'))
+
+
+def cpu_flags():
+    try:
+        with open('/proc/cpuinfo') as f:
+            for line in f:
+                if line.startswith('flags'):
+                    return set(line.split(':', 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def usable_schemes():
+    """Reference iteration schemes this host CPU can run (cf. the reference's
+    lightweaver/simd_management.py:27-42)."""
+    flags = cpu_flags()
+    out = ['scalar']
+    if 'sse2' in flags and os.path.exists(os.path.join(REF_DIR, 'SimdImpl_SSE2.so')):
+        out.append('SSE2')
+    if {'avx2', 'fma'} <= flags and os.path.exists(os.path.join(REF_DIR, 'SimdImpl_AVX2FMA.so')):
+        out.append('AVX2FMA')
+    if {'avx512f', 'avx512dq'} <= flags and os.path.exists(os.path.join(REF_DIR, 'SimdImpl_AVX512.so')):
+        out.append('AVX512')
+    return out
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = os.path.join(REF_DIR, 'liblwref.so')
+    if not os.path.exists(path):
+        raise RuntimeError(f'{path} not built: run `make -C oracle ref` where /root/reference exists')
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    dp = C.POINTER(C.c_double)
+    lib.lwref_last_error.restype = C.c_char_p
+    lib.lwref_create.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(vp)]
+    lib.lwref_destroy.argtypes = [vp]
+    lib.lwref_destroy.restype = None
+    lib.lwref_scheme_name.argtypes = [vp]
+    lib.lwref_scheme_name.restype = C.c_char_p
+    lib.lwref_set_depth_fill.argtypes = [vp, C.c_int]
+    lib.lwref_fs_iter.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int64)]
+    lib.lwref_formal_sol.argtypes = [vp, C.c_int]
+    lib.lwref_stat_eq.argtypes = [vp]
+    lib.lwref_compute_profiles.argtypes = [vp]
+    lib.lwref_time_fs_iter.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
+    lib.lwref_solve_ray.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_int,
+                                    C.c_double, C.c_int, C.c_int, dp, dp]
+    lib.lwref_solve_lin_eq.argtypes = [C.c_int, dp, dp, C.c_int]
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(load().lwref_last_error().decode())
+
+
+class RefContext:
+    """The reference's Context over column ``col`` of a Problem.  Results are
+    written in place into the Problem's numpy buffers, as the reference does."""
+
+    def __init__(self, problem, col=0, scheme='scalar', Nthreads=1):
+        self.lib = load()
+        self.problem = problem
+        self._cs = problem.c_struct()
+        self.h = C.c_void_p()
+        _check(self.lib.lwref_create(C.byref(self._cs), col, scheme.encode(), Nthreads, C.byref(self.h)))
+
+    @property
+    def scheme_name(self):
+        return self.lib.lwref_scheme_name(self.h).decode()
+
+    def fs_iter(self, lambdaIterate=False):
+        dJ = C.c_double()
+        idx = C.c_int64()
+        _check(self.lib.lwref_fs_iter(self.h, int(lambdaIterate), C.byref(dJ), C.byref(idx)))
+        return dJ.value, idx.value
+
+    def formal_sol(self, upOnly=True):
+        _check(self.lib.lwref_formal_sol(self.h, int(upOnly)))
+
+    def stat_eq(self):
+        _check(self.lib.lwref_stat_eq(self.h))
+
+    def compute_profiles(self):
+        _check(self.lib.lwref_compute_profiles(self.h))
+
+    def set_depth_fill(self, fill):
+        _check(self.lib.lwref_set_depth_fill(self.h, int(fill)))
+
+    def time_fs_iter(self, nWarm=3, nTimed=20, withStatEq=False):
+        out = np.zeros(nTimed)
+        _check(self.lib.lwref_time_fs_iter(self.h, nWarm, nTimed, int(withStatEq),
+                                           out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.lwref_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def solve_ray(solver, height, temperature, chi, S, muz, toObs, wavelength, lowerBc, upperBc,
+              want_psi=True):
+    lib = load()
+    K = len(height)
+    dp = C.POINTER(C.c_double)
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (height, temperature, chi, S)]
+    I = np.zeros(K)
+    Psi = np.zeros(K)
+    _check(lib.lwref_solve_ray(solver, K, *[a.ctypes.data_as(dp) for a in arrs], float(muz),
+                               int(toObs), float(wavelength), lowerBc, upperBc,
+                               I.ctypes.data_as(dp), Psi.ctypes.data_as(dp) if want_psi else dp()))
+    return I, Psi
+
+
+def solve_lin_eq(A, b, improve=True):
+    lib = load()
+    A = np.array(A, dtype=np.float64, order='C')
+    b = np.array(b, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    _check(lib.lwref_solve_lin_eq(A.shape[0], A.ctypes.data_as(dp), b.ctypes.data_as(dp), int(improve)))
+    return b
