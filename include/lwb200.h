@@ -128,6 +128,8 @@ enum {
     LWB200_INTENS  = 1u << 7, /* down only: I */
     LWB200_RATES   = 1u << 8, /* down only: Rij, Rji */
     LWB200_DEPTH   = 1u << 9, /* down only: depthChi/Eta/I */
+    LWB200_ADAMP   = 1u << 10, /* up only: aDamp alone (profiles are then made by lwb200_compute_profiles) */
+    LWB200_GAMMA_FINAL = 1u << 11, /* up only: host Gamma taken as the finalised matrix stat_eq reads */
     LWB200_ALL_INPUTS  = 0x7fu,
     LWB200_ITER_INPUTS = LWB200_POPS | LWB200_NSTAR | LWB200_GAMMA,
     LWB200_ITER_OUTPUTS = LWB200_GAMMA | LWB200_JBAR | LWB200_INTENS | LWB200_RATES

@@ -18,7 +18,8 @@ FS_LINEAR, FS_BESSER, FS_BEZIER3 = 0, 1, 2
 FS_NAMES = {'piecewise_linear_1d': FS_LINEAR, 'piecewise_besser_1d': FS_BESSER,
             'piecewise_bezier3_1d': FS_BEZIER3}
 
-ATMOS, BACKGR, POPS, NSTAR, GAMMA, JBAR, PROFILE, INTENS, RATES, DEPTH = (1 << i for i in range(10))
+(ATMOS, BACKGR, POPS, NSTAR, GAMMA, JBAR, PROFILE, INTENS, RATES, DEPTH, ADAMP,
+ GAMMA_FINAL) = (1 << i for i in range(12))
 ALL_INPUTS = 0x7f
 ITER_INPUTS = POPS | NSTAR | GAMMA
 ITER_OUTPUTS = GAMMA | JBAR | INTENS | RATES

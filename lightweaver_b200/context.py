@@ -1,0 +1,198 @@
+"""Host-side mirror of ``lw.Context`` for the hot path, over the C-ABI.
+
+Same method names, argument meaning and error behaviour as the reference's
+``LwContext`` (``Source/LwMiddleLayer.pyx``): ``formal_sol_gamma_matrices``
+(:3152-3210), ``formal_sol`` (:3212-3241), ``stat_equil`` (:3461-3531),
+``update_deps`` (:3244-3288).  The numpy buffers of the ``Problem`` are the
+source of truth, exactly as the reference's Cython objects own theirs; every
+call moves what the reference's caller may have mutated to the device and what
+it reads afterwards back.  There is no CPU path:
+without the CUDA library or a GPU every call raises.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import capi
+from .problem import Problem
+
+
+class ExplodingMatrixError(Exception):
+    """Same name as the reference's exception for a singular stat-eq system
+    (Source/LwMiddleLayer.pyx:3509-3514)."""
+
+
+@dataclass
+class IterationUpdate:
+    """Subset of lightweaver.iteration_update.IterationUpdate this path fills
+    (iteration_update.py:64-85)."""
+    updatedJ: bool = False
+    dJMax: float = 0.0
+    dJMaxIdx: int = 0
+    updatedPops: bool = False
+    dPops: List[float] = field(default_factory=list)
+    dPopsMaxIdx: List[int] = field(default_factory=list)
+    crsw: float = 1.0
+
+
+class Context:
+    """A Lightweaver-style context whose formal solution, Gamma accumulation and
+    statistical-equilibrium solve run on one B200.
+
+    ``problem`` may hold one column (a classic 1D Context) or a 1.5D stack.
+    ``laRange`` restricts the wavelength sweep to ``[laStart, laEnd)`` (one
+    lambda-shard of a multi-GPU run, see ``sharding.py``).
+    """
+
+    def __init__(self, problem: Problem, device: int = 0, stream=None, laRange=None,
+                 upload: bool = True):
+        self.lib = capi.load()
+        self.problem = problem
+        self.device = device
+        self._cs = problem.c_struct()
+        self._h = C.c_void_p()
+        capi.check(self.lib.lwb200_create(C.byref(self._cs), device, C.byref(self._h)))
+        if stream is not None:
+            self.set_stream(stream)
+        if laRange is not None:
+            self.set_lambda_range(*laRange)
+        self.crsw = 1.0
+        if upload:
+            self.upload(capi.ALL_INPUTS)
+
+    # --------------------------------------------------------------- plumbing
+    def close(self):
+        if self._h:
+            self.lib.lwb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream):
+        """``stream``: a raw cudaStream_t (int) or a torch.cuda.Stream."""
+        ptr = getattr(stream, 'cuda_stream', stream)
+        capi.check(self.lib.lwb200_set_stream(self._h, C.c_void_p(int(ptr))))
+
+    def set_lambda_range(self, laStart, laEnd):
+        capi.check(self.lib.lwb200_set_lambda_range(self._h, int(laStart), int(laEnd)))
+
+    def upload(self, mask):
+        capi.check(self.lib.lwb200_upload(self._h, mask))
+
+    def download(self, mask, sync=True):
+        capi.check(self.lib.lwb200_download(self._h, mask))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        capi.check(self.lib.lwb200_sync(self._h))
+
+    def device_buffer(self, which):
+        """(device pointer, nbytes) of one of the capi.BUF_* buffers."""
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        capi.check(self.lib.lwb200_device_buffer(self._h, which, C.byref(ptr), C.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def work_stats(self):
+        pts, byts, launches = C.c_double(), C.c_double(), C.c_int64()
+        capi.check(self.lib.lwb200_work_stats(self._h, C.byref(pts), C.byref(byts), C.byref(launches)))
+        return pts.value, byts.value, launches.value
+
+    # ------------------------------------------------- device-resident calls
+    def fs_iter_device(self, lambdaIterate=False, storeDepth=False, deferFinalise=False,
+                       want_dJ=True):
+        """One Gamma iteration on device-resident data (no host copies)."""
+        flags = ((capi.LAMBDA_ITERATE if lambdaIterate else 0) | (capi.STORE_DEPTH if storeDepth else 0)
+                 | (capi.DEFER_FINALISE if deferFinalise else 0))
+        if want_dJ:
+            dJ, idx = C.c_double(), C.c_int64()
+            capi.check(self.lib.lwb200_fs_iter(self._h, flags, C.byref(dJ), C.byref(idx)))
+            return dJ.value, idx.value
+        capi.check(self.lib.lwb200_fs_iter(self._h, flags, None, None))
+        return None
+
+    def finalise(self):
+        capi.check(self.lib.lwb200_finalise(self._h))
+
+    def dj_max(self):
+        dJ, idx = C.c_double(), C.c_int64()
+        capi.check(self.lib.lwb200_dj_max(self._h, C.byref(dJ), C.byref(idx)))
+        return dJ.value, idx.value
+
+    def stat_eq_device(self, atom=-1, kStart=-1, kEnd=-1):
+        ns = C.c_int32(0)
+        rc = self.lib.lwb200_stat_eq(self._h, atom, kStart, kEnd, C.byref(ns))
+        if rc != 0:
+            if ns.value > 0:
+                raise ExplodingMatrixError('Singular Matrix')
+            capi.check(rc)
+
+    def compute_profiles_device(self):
+        capi.check(self.lib.lwb200_compute_profiles(self._h))
+
+    # ------------------------------------------- the reference's call surface
+    def formal_sol_gamma_matrices(self, fixCollisionalRates=True, lambdaIterate=False,
+                                  extraParams=None, crsw=None):
+        """lw.Context.formal_sol_gamma_matrices: Gamma = crsw*C (host prologue,
+        LwMiddleLayer.pyx:3198-3203), then the device Gamma iteration; I, J,
+        Gamma and the rates are back in the numpy buffers on return.  The
+        collisional rates C are an input of this path (computed by the
+        reference's Python layer), so fixCollisionalRates is always honoured as
+        True."""
+        storeDepth = bool(extraParams and extraParams.get('storeDepthData', False))
+        if crsw is not None:
+            self.crsw = crsw
+        self.problem.prefill_gamma(self.crsw)
+        self.upload(capi.ITER_INPUTS)
+        dJ, idx = self.fs_iter_device(lambdaIterate=lambdaIterate, storeDepth=storeDepth)
+        self.download(capi.ITER_OUTPUTS | (capi.DEPTH if storeDepth else 0))
+        return IterationUpdate(updatedJ=True, dJMax=dJ, dJMaxIdx=idx % self.problem.Nspect,
+                               crsw=self.crsw)
+
+    def formal_sol(self, upOnly=True, extraParams=None):
+        """lw.Context.formal_sol: intensity only (LwMiddleLayer.pyx:3212-3241)."""
+        self.upload(capi.POPS | capi.NSTAR | capi.JBAR)
+        capi.check(self.lib.lwb200_formal_sol(self._h, int(upOnly)))
+        self.download(capi.INTENS)
+        return IterationUpdate()
+
+    def stat_equil(self, extraParams=None):
+        """lw.Context.stat_equil: per-depth statistical equilibrium from the
+        current Gamma (LwMiddleLayer.pyx:3461-3531); raises ExplodingMatrixError
+        on a singular system.  Returns the relative population change per atom
+        (what rel_diff_ng_accelerate reports without Ng acceleration)."""
+        prev = [a.n.copy() for a in self.problem.active_atoms()]
+        self.upload(capi.POPS | capi.GAMMA_FINAL)
+        self.stat_eq_device()
+        self.download(capi.POPS)
+        upd = IterationUpdate(updatedPops=True)
+        for p, a in zip(prev, self.problem.active_atoms()):
+            with np.errstate(divide='ignore', invalid='ignore'):
+                d = np.abs(1.0 - p / a.n)
+            d = np.where(np.isfinite(d), d, 0.0)
+            upd.dPops.append(float(d.max()))
+            upd.dPopsMaxIdx.append(int(d.argmax()))
+        return upd
+
+    def update_deps(self, temperature=True, ne=True, vturb=True, vlos=True, B=True,
+                    background=True, hprd=True, quiet=True, profiles_on_device=False):
+        """lw.Context.update_deps (LwMiddleLayer.pyx:3244-3288) as seen from the
+        back end: whatever the host recomputed (projections, profiles, LTE
+        populations, background) is re-mirrored.  With profiles_on_device the
+        Voigt profiles are regenerated on the GPU from aDamp/vBroad/vlosMu
+        instead of being uploaded."""
+        mask = capi.ATMOS | capi.NSTAR | capi.POPS
+        if background:
+            mask |= capi.BACKGR
+        if not profiles_on_device:
+            mask |= capi.PROFILE
+        self.upload(mask)
+        if profiles_on_device:
+            self.upload(capi.ADAMP)
+            self.compute_profiles_device()

@@ -1,0 +1,938 @@
+// lwb200_api.cu -- implementation of the C-ABI in include/lwb200.h: problem
+// marshalling, the wavelength work plan (what TaskScheduler/ThreadStorage did on
+// the CPU), device memory, host<->device copies and kernel launches.
+#include "../../include/lwb200.h"
+#include "lwb200_kernels.cuh"
+#include "lwb200_profiles.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace lwb200;
+
+namespace
+{
+thread_local std::string g_err;
+
+int fail(const std::string& msg)
+{
+    g_err = msg;
+    return 1;
+}
+
+#define CU(call)                                                                                   \
+    do                                                                                             \
+    {                                                                                              \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                       \
+    } while (0)
+
+struct HostTrans
+{
+    LwB200Transition t;
+    int atom, kr, global;
+};
+
+template <typename T>
+struct DevBuf
+{
+    T* p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count)
+    {
+        n = count;
+        if (count == 0)
+            return 0;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e != cudaSuccess)
+        {
+            g_err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+            return 1;
+        }
+        return 0;
+    }
+    int upload(const std::vector<T>& h)
+    {
+        if (alloc(h.size()))
+            return 1;
+        if (h.empty())
+            return 0;
+        cudaError_t e = cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess)
+        {
+            g_err = std::string("cudaMemcpy: ") + cudaGetErrorString(e);
+            return 1;
+        }
+        return 0;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+} // namespace
+
+struct LwB200Context
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    LwB200Problem prob{};
+    std::vector<LwB200Atom> atoms;
+    std::vector<std::vector<LwB200Transition>> atomTrans;
+    std::vector<HostTrans> trans; // flattened, global order
+    std::vector<DevTrans> devTrans;
+    std::vector<int> atomNlevel, atomLevOff, atomGammaOff, atomDetailed;
+    std::vector<int> tileLa, tileSlotOff, tileSlotTrans;
+    int Ntile = 0;
+    int nwarps = 4;
+    int laLo = 0, laHi = 0;
+    int NCH = 0;
+    size_t smemBytes = 0;
+    int64_t lastLaunches = 0;
+    bool nstarUploaded = false;
+
+    DevProblem P{};
+    DevBuf<double> height, temperature, vlosMu, muz, wmu, wavelength, chiBg, etaBg, scaBg;
+    DevBuf<double> J, I, n, nStar, nTotal, vBroad, gRatio, phi, wphi, rhoPrd, aDamp;
+    DevBuf<double> wlambdaTab, alphaTab, transWave, lowerBcData, upperBcData, accum, prefill, gamma, dJ;
+    DevBuf<double> depthChi, depthEta, depthI, djOut;
+    DevBuf<int> lowerBcIdx, upperBcIdx, dLaOff, dLaHasLine, dTileLa, dTileSlotOff, dTileSlotTrans;
+    DevBuf<int> dAtomNlevel, dAtomLevOff, dAtomGammaOff, dAtomDetailed, dSingular;
+    DevBuf<long long> djIdx;
+    DevBuf<DevTrans> dTrans;
+    DevBuf<DevEntry> dEntries;
+    std::vector<DevLine> devLines;
+    DevBuf<DevLine> dLines;
+};
+
+namespace
+{
+// ---------------------------------------------------------------- planning
+int build_plan(LwB200Context* c)
+{
+    const LwB200Problem& p = c->prob;
+    const int K = p.Nspace, L = p.Nspect, M = p.Nrays;
+    int levOff = 0, gammaOff = 0, nline = 0, ncont = 0, tabOff = 0;
+    long long phiOff = 0, rhoOff = 0;
+    for (int a = 0; a < p.Natom; ++a)
+    {
+        const LwB200Atom& at = c->atoms[a];
+        c->atomNlevel.push_back(at.Nlevel);
+        c->atomLevOff.push_back(levOff);
+        c->atomGammaOff.push_back(gammaOff);
+        c->atomDetailed.push_back(at.detailedStatic);
+        for (int kr = 0; kr < at.Ntrans; ++kr)
+        {
+            const LwB200Transition& t = c->atomTrans[a][kr];
+            if (t.Nblue < 0 || t.Nred > L || t.Nred - t.Nblue < 2)
+                return fail("transition wavelength range invalid");
+            if (t.i < 0 || t.j < 0 || t.i >= at.Nlevel || t.j >= at.Nlevel)
+                return fail("transition level index out of range");
+            HostTrans ht{t, a, kr, (int)c->trans.size()};
+            c->trans.push_back(ht);
+        }
+        levOff += at.Nlevel;
+        if (!at.detailedStatic)
+            gammaOff += at.Nlevel * at.Nlevel;
+    }
+    const int NlevTot = levOff, GammaTot = gammaOff, NT = (int)c->trans.size();
+    const int AccTot = GammaTot + 2 * NT;
+    for (int g = 0; g < NT; ++g)
+    {
+        const HostTrans& ht = c->trans[g];
+        const LwB200Transition& t = ht.t;
+        const LwB200Atom& at = c->atoms[ht.atom];
+        DevTrans d{};
+        d.type = t.type;
+        d.i = t.i;
+        d.j = t.j;
+        d.atom = ht.atom;
+        d.Nblue = t.Nblue;
+        d.Nred = t.Nred;
+        d.levI = c->atomLevOff[ht.atom] + t.i;
+        d.levJ = c->atomLevOff[ht.atom] + t.j;
+        d.detailed = at.detailedStatic;
+        if (at.detailedStatic)
+        {
+            d.accIJ = d.accJI = -1;
+        }
+        else
+        {
+            d.accIJ = c->atomGammaOff[ht.atom] + t.i * at.Nlevel + t.j;
+            d.accJI = c->atomGammaOff[ht.atom] + t.j * at.Nlevel + t.i;
+        }
+        d.accRij = GammaTot + 2 * g;
+        d.accRji = GammaTot + 2 * g + 1;
+        d.tabOff = tabOff;
+        const int Nl = t.Nred - t.Nblue;
+        tabOff += Nl;
+        d.lineIdx = d.contIdx = -1;
+        d.rhoOff = -1;
+        if (t.type == LWB200_LINE)
+        {
+            if (!t.phi || !t.wphi)
+                return fail("line without phi / wphi buffers");
+            d.lineIdx = nline++;
+            d.phiOff = phiOff;
+            d.phiColStride = (long long)Nl * M * 2 * K;
+            phiOff += d.phiColStride * p.Ncol;
+            if (t.rhoPrd)
+            {
+                d.rhoOff = rhoOff;
+                rhoOff += (long long)p.Ncol * Nl * K;
+            }
+            d.Aji_Bji = t.Aji / t.Bji;
+            d.Bji_Bij = t.Bji / t.Bij;
+            d.Bij = t.Bij;
+        }
+        else
+        {
+            if (!t.alpha)
+                return fail("continuum without alpha");
+            d.contIdx = ncont++;
+        }
+        d.lambda0 = t.lambda0;
+        c->devTrans.push_back(d);
+    }
+
+    // per-wavelength active lists in the reference's (atom, kr) order
+    std::vector<int> laOff(L + 1, 0), laHasLine(L, 0);
+    std::vector<std::vector<int>> active(L);
+    for (int g = 0; g < NT; ++g)
+        for (int la = c->devTrans[g].Nblue; la < c->devTrans[g].Nred; ++la)
+        {
+            active[la].push_back(g);
+            if (c->devTrans[g].type == 0)
+                laHasLine[la] = 1;
+        }
+
+    // tiles: runs of wavelengths whose union of active transitions fits the
+    // shared-memory accumulator; sized so that the grid fills the GPU
+    const int KP = ((K + 31) / 32) * 32;
+    int maxNlevel = 1;
+    for (int a = 0; a < p.Natom; ++a)
+        maxNlevel = std::max(maxNlevel, c->atoms[a].Nlevel);
+    const size_t scratchBytes = (size_t)c->nwarps * 2 * maxNlevel * 32 * sizeof(double);
+    const size_t smemLimit = 200 * 1024;
+    if (scratchBytes + 4 * KP * sizeof(double) > smemLimit)
+        return fail("atom too large for the shared-memory scratch");
+    const int slotCap = (int)std::min<size_t>((smemLimit - scratchBytes) / (4 * KP * sizeof(double)), 48);
+    const long long targetCtas = 148LL * 16;
+    long long want = ((long long)L * p.Ncol + targetCtas - 1) / targetCtas;
+    int tileLen = (int)std::max<long long>(c->nwarps, std::min<long long>(want, 16 * c->nwarps));
+    tileLen = ((tileLen + c->nwarps - 1) / c->nwarps) * c->nwarps;
+
+    std::vector<DevEntry> entries;
+    int maxSlots = 1;
+    c->tileLa.push_back(0);
+    c->tileSlotOff.push_back(0);
+    int la = 0;
+    while (la < L)
+    {
+        std::vector<int> slots; // transitions of this tile
+        int start = la;
+        while (la < L && la - start < tileLen)
+        {
+            std::vector<int> add;
+            for (int g : active[la])
+                if (std::find(slots.begin(), slots.end(), g) == slots.end())
+                    add.push_back(g);
+            if ((int)(slots.size() + add.size()) > slotCap)
+            {
+                if (la == start)
+                    return fail("too many transitions active at one wavelength for shared memory");
+                break;
+            }
+            slots.insert(slots.end(), add.begin(), add.end());
+            ++la;
+        }
+        for (int l2 = start; l2 < la; ++l2)
+        {
+            laOff[l2] = (int)entries.size();
+            for (int g : active[l2])
+            {
+                int s = (int)(std::find(slots.begin(), slots.end(), g) - slots.begin());
+                entries.push_back(DevEntry{g, s});
+            }
+        }
+        c->tileLa.push_back(la);
+        for (int g : slots)
+            c->tileSlotTrans.push_back(g);
+        c->tileSlotOff.push_back((int)c->tileSlotTrans.size());
+        maxSlots = std::max(maxSlots, (int)slots.size());
+    }
+    laOff[L] = (int)entries.size();
+    c->Ntile = (int)c->tileLa.size() - 1;
+    c->smemBytes = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchBytes;
+    c->NCH = (K + 31) / 32;
+
+    // per-transition wavelength tables
+    std::vector<double> wlambdaTab(tabOff), alphaTab(tabOff, 0.0);
+    for (int g = 0; g < NT; ++g)
+    {
+        const LwB200Transition& t = c->trans[g].t;
+        const int Nl = t.Nred - t.Nblue;
+        const int off = c->devTrans[g].tabOff;
+        for (int lt = 0; lt < Nl; ++lt)
+        {
+            // Transition::wlambda, LwTransition.hpp:71-81
+            double w;
+            if (lt == 0)
+                w = 0.5 * (t.wavelength[1] - t.wavelength[0]) * t.dopplerWidth;
+            else if (lt == Nl - 1)
+                w = 0.5 * (t.wavelength[Nl - 1] - t.wavelength[Nl - 2]) * t.dopplerWidth;
+            else
+                w = 0.5 * (t.wavelength[lt + 1] - t.wavelength[lt - 1]) * t.dopplerWidth;
+            wlambdaTab[off + lt] = w;
+            if (t.type == LWB200_CONTINUUM)
+                alphaTab[off + lt] = t.alpha[lt];
+        }
+    }
+
+    // ---- device allocations
+    const size_t ncol = p.Ncol;
+    if (c->height.alloc(ncol * K) || c->temperature.alloc(ncol * K) || c->muz.alloc(M) || c->wmu.alloc(M)
+        || c->wavelength.alloc(L) || c->chiBg.alloc(ncol * L * K) || c->etaBg.alloc(ncol * L * K)
+        || c->scaBg.alloc(ncol * L * K) || c->J.alloc(ncol * L * K) || c->I.alloc(ncol * L * M)
+        || c->n.alloc(ncol * NlevTot * K) || c->nStar.alloc(ncol * NlevTot * K)
+        || c->nTotal.alloc(ncol * p.Natom * K) || c->vBroad.alloc(ncol * p.Natom * K)
+        || c->gRatio.alloc((size_t)std::max(ncont, 1) * ncol * K) || c->phi.alloc((size_t)std::max<long long>(phiOff, 1))
+        || c->wphi.alloc((size_t)std::max(nline, 1) * ncol * K) || c->aDamp.alloc((size_t)std::max(nline, 1) * ncol * K)
+        || c->rhoPrd.alloc((size_t)std::max<long long>(rhoOff, 1))
+        || c->accum.alloc(ncol * AccTot * K) || c->prefill.alloc(ncol * std::max(GammaTot, 1) * K)
+        || c->gamma.alloc(ncol * std::max(GammaTot, 1) * K) || c->dJ.alloc(ncol * L) || c->djOut.alloc(1)
+        || c->djIdx.alloc(1) || c->dSingular.alloc(1))
+        return 1;
+    if (p.vlosMu && c->vlosMu.alloc(ncol * M * K))
+        return 1;
+    CU(cudaMemset(c->J.p, 0, c->J.n * sizeof(double)));
+    CU(cudaMemset(c->I.p, 0, c->I.n * sizeof(double)));
+    CU(cudaMemset(c->accum.p, 0, c->accum.n * sizeof(double)));
+    CU(cudaMemset(c->prefill.p, 0, c->prefill.n * sizeof(double)));
+    CU(cudaMemset(c->gamma.p, 0, c->gamma.n * sizeof(double)));
+    CU(cudaMemset(c->dJ.p, 0, c->dJ.n * sizeof(double)));
+    CU(cudaMemset(c->rhoPrd.p, 0, c->rhoPrd.n * sizeof(double)));
+    if (p.depthChi && p.depthEta && p.depthI)
+    {
+        const size_t nd = ncol * L * M * 2 * K;
+        if (c->depthChi.alloc(nd) || c->depthEta.alloc(nd) || c->depthI.alloc(nd))
+            return 1;
+    }
+    if (p.lowerBc == LWB200_BC_CALLABLE)
+    {
+        if (!p.lowerBcData || !p.lowerBcIdx || p.NlowerBcMu < 1)
+            return fail("CALLABLE lower boundary without data");
+        if (c->lowerBcData.alloc(ncol * L * p.NlowerBcMu) || c->lowerBcIdx.alloc(M * 2))
+            return 1;
+        CU(cudaMemcpy(c->lowerBcIdx.p, p.lowerBcIdx, M * 2 * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (p.upperBc == LWB200_BC_CALLABLE)
+    {
+        if (!p.upperBcData || !p.upperBcIdx || p.NupperBcMu < 1)
+            return fail("CALLABLE upper boundary without data");
+        if (c->upperBcData.alloc(ncol * L * p.NupperBcMu) || c->upperBcIdx.alloc(M * 2))
+            return 1;
+        CU(cudaMemcpy(c->upperBcIdx.p, p.upperBcIdx, M * 2 * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (c->wlambdaTab.upload(wlambdaTab) || c->alphaTab.upload(alphaTab) || c->dTrans.upload(c->devTrans)
+        || c->dEntries.upload(entries) || c->dLaOff.upload(laOff) || c->dLaHasLine.upload(laHasLine)
+        || c->dTileLa.upload(c->tileLa) || c->dTileSlotOff.upload(c->tileSlotOff)
+        || c->dTileSlotTrans.upload(c->tileSlotTrans) || c->dAtomNlevel.upload(c->atomNlevel)
+        || c->dAtomLevOff.upload(c->atomLevOff) || c->dAtomGammaOff.upload(c->atomGammaOff)
+        || c->dAtomDetailed.upload(c->atomDetailed))
+        return 1;
+    CU(cudaMemcpy(c->muz.p, p.muz, M * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->wmu.p, p.wmu, M * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->wavelength.p, p.wavelength, L * sizeof(double), cudaMemcpyHostToDevice));
+
+    // line descriptors for the device profile kernel
+    {
+        std::vector<double> transWave(tabOff);
+        for (int g = 0; g < NT; ++g)
+        {
+            const LwB200Transition& t = c->trans[g].t;
+            for (int lt = 0; lt < t.Nred - t.Nblue; ++lt)
+                transWave[c->devTrans[g].tabOff + lt] = t.wavelength[lt];
+        }
+        if (c->transWave.upload(transWave))
+            return 1;
+        for (int g = 0; g < NT; ++g)
+        {
+            const DevTrans& d = c->devTrans[g];
+            if (d.type != 0)
+                continue;
+            DevLine dl{};
+            dl.Nl = d.Nred - d.Nblue;
+            dl.tabOff = d.tabOff;
+            dl.lineIdx = d.lineIdx;
+            dl.atom = d.atom;
+            dl.phiOff = d.phiOff;
+            dl.phiColStride = d.phiColStride;
+            dl.lambda0 = d.lambda0;
+            c->devLines.push_back(dl);
+        }
+        if (c->dLines.upload(c->devLines))
+            return 1;
+    }
+
+    DevProblem& P = c->P;
+    P.Ncol = p.Ncol; P.K = K; P.M = M; P.L = L;
+    P.NlevTot = NlevTot; P.GammaTot = GammaTot; P.AccTot = AccTot; P.Natom = p.Natom;
+    P.NtransTot = NT; P.Nline = nline; P.Ncont = ncont;
+    P.lowerBc = p.lowerBc; P.upperBc = p.upperBc;
+    P.NlowerBcMu = p.NlowerBcMu; P.NupperBcMu = p.NupperBcMu;
+    P.maxNlevel = maxNlevel; P.maxSlots = maxSlots; P.KP = KP;
+    P.height = c->height.p; P.temperature = c->temperature.p; P.muz = c->muz.p; P.wmu = c->wmu.p;
+    P.wavelength = c->wavelength.p; P.chiBg = c->chiBg.p; P.etaBg = c->etaBg.p; P.scaBg = c->scaBg.p;
+    P.J = c->J.p; P.I = c->I.p; P.n = c->n.p; P.nStar = c->nStar.p; P.gRatio = c->gRatio.p;
+    P.phi = c->phi.p; P.wphi = c->wphi.p; P.rhoPrd = c->rhoPrd.p;
+    P.wlambdaTab = c->wlambdaTab.p; P.alphaTab = c->alphaTab.p;
+    P.lowerBcData = c->lowerBcData.p; P.upperBcData = c->upperBcData.p;
+    P.lowerBcIdx = c->lowerBcIdx.p; P.upperBcIdx = c->upperBcIdx.p;
+    P.accum = c->accum.p; P.dJ = c->dJ.p;
+    P.depthChi = c->depthChi.p; P.depthEta = c->depthEta.p; P.depthI = c->depthI.p;
+    P.trans = c->dTrans.p; P.entries = c->dEntries.p; P.laOff = c->dLaOff.p; P.laHasLine = c->dLaHasLine.p;
+    P.tileLa = c->dTileLa.p; P.tileSlotOff = c->dTileSlotOff.p; P.tileSlotTrans = c->dTileSlotTrans.p;
+    P.atomNlevel = c->dAtomNlevel.p; P.atomLevOff = c->dAtomLevOff.p;
+    P.atomGammaOff = c->dAtomGammaOff.p; P.atomDetailed = c->dAtomDetailed.p;
+    return 0;
+}
+
+template <int NCH, int SOLVER, int MODE>
+int launch_fs_t(LwB200Context* c, int tile0, int ntile, int lambdaIterate, int upOnly, int storeDepth)
+{
+    auto kern = fs_kernel<NCH, SOLVER, MODE>;
+    static bool attrSet[16] = {false};
+    if (!attrSet[c->device & 15])
+    {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attrSet[c->device & 15] = true;
+    }
+    dim3 grid(ntile, c->prob.Ncol);
+    kern<<<grid, c->nwarps * 32, c->smemBytes, c->stream>>>(c->P, tile0, c->laLo, c->laHi, lambdaIterate,
+                                                            upOnly, storeDepth);
+    CU(cudaGetLastError());
+    c->lastLaunches += 1;
+    return 0;
+}
+
+template <int NCH, int MODE>
+int launch_fs_s(LwB200Context* c, int tile0, int ntile, int li, int uo, int sd)
+{
+    switch (c->prob.formalSolver)
+    {
+    case LWB200_FS_LINEAR: return launch_fs_t<NCH, 0, MODE>(c, tile0, ntile, li, uo, sd);
+    case LWB200_FS_BESSER: return launch_fs_t<NCH, 1, MODE>(c, tile0, ntile, li, uo, sd);
+    case LWB200_FS_BEZIER3: return launch_fs_t<NCH, 2, MODE>(c, tile0, ntile, li, uo, sd);
+    }
+    return fail("unknown formal solver");
+}
+
+template <int MODE>
+int launch_fs(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
+{
+    // tiles overlapping [laLo, laHi)
+    int t0 = 0, t1 = c->Ntile;
+    while (t0 < c->Ntile && c->tileLa[t0 + 1] <= c->laLo)
+        ++t0;
+    while (t1 > t0 && c->tileLa[t1 - 1] >= c->laHi)
+        --t1;
+    if (t1 <= t0)
+        return 0;
+    switch (c->NCH)
+    {
+    case 1: return launch_fs_s<1, MODE>(c, t0, t1 - t0, lambdaIterate, upOnly, storeDepth);
+    case 2: return launch_fs_s<2, MODE>(c, t0, t1 - t0, lambdaIterate, upOnly, storeDepth);
+    case 3: return launch_fs_s<3, MODE>(c, t0, t1 - t0, lambdaIterate, upOnly, storeDepth);
+    case 4: return launch_fs_s<4, MODE>(c, t0, t1 - t0, lambdaIterate, upOnly, storeDepth);
+    }
+    return fail("Nspace > 128 is not supported yet by the register-resident depth layout");
+}
+
+int copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+           cudaMemcpyKind kind, cudaStream_t s)
+{
+    if (width == 0 || height == 0)
+        return 0;
+    if (height == 1 || (dpitch == width && spitch == width))
+    {
+        CU(cudaMemcpyAsync(dst, src, width * height, kind, s));
+        return 0;
+    }
+    CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s));
+    return 0;
+}
+
+int grid_for(size_t total, int block = 256)
+{
+    size_t g = (total + block - 1) / block;
+    return (int)std::max<size_t>(1, std::min<size_t>(g, 148 * 32));
+}
+} // namespace
+
+extern "C"
+{
+const char* lwb200_last_error(void) { return g_err.c_str(); }
+int lwb200_abi_version(void) { return LWB200_ABI_VERSION; }
+
+int lwb200_device_count(int* count)
+{
+    CU(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int lwb200_create(const LwB200Problem* problem, int device, LwB200Context** out)
+{
+    if (!problem || !out)
+        return fail("lwb200_create: null argument");
+    if (problem->abiVersion != LWB200_ABI_VERSION)
+        return fail("lwb200_create: ABI version mismatch");
+    if (problem->Nspace < 3 || problem->Nrays < 1 || problem->Nspect < 1 || problem->Ncol < 1 || problem->Natom < 1)
+        return fail("lwb200_create: bad dimensions");
+    if (problem->Nspace > 128)
+        return fail("lwb200_create: Nspace > 128 is not supported yet");
+    if (problem->formalSolver < 0 || problem->formalSolver > 2)
+        return fail("lwb200_create: formalSolver must be 0 (linear), 1 (besser) or 2 (bezier3)");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev < 1)
+        return fail("lwb200_create: no CUDA device (this back end has no CPU fallback)");
+    if (device < 0 || device >= ndev)
+        return fail("lwb200_create: device index out of range");
+    CU(cudaSetDevice(device));
+    auto* c = new LwB200Context();
+    c->device = device;
+    c->prob = *problem;
+    c->atoms.assign(problem->atoms, problem->atoms + problem->Natom);
+    c->atomTrans.resize(problem->Natom);
+    for (int a = 0; a < problem->Natom; ++a)
+    {
+        const LwB200Atom& at = problem->atoms[a];
+        if (at.Nlevel < 1 || at.Nlevel > 32)
+        {
+            delete c;
+            return fail("lwb200_create: Nlevel must be in [1, 32]");
+        }
+        c->atomTrans[a].assign(at.trans, at.trans + at.Ntrans);
+        c->atoms[a].trans = c->atomTrans[a].data();
+    }
+    c->prob.atoms = c->atoms.data();
+    c->laLo = 0;
+    c->laHi = problem->Nspect;
+    if (build_plan(c))
+    {
+        lwb200_destroy(c);
+        return 1;
+    }
+    *out = c;
+    return 0;
+}
+
+int lwb200_destroy(LwB200Context* c)
+{
+    if (!c)
+        return 0;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    DevBuf<double>* dbl[] = {&c->height, &c->temperature, &c->vlosMu, &c->muz, &c->wmu, &c->wavelength,
+                             &c->chiBg, &c->etaBg, &c->scaBg, &c->J, &c->I, &c->n, &c->nStar, &c->nTotal,
+                             &c->vBroad, &c->gRatio, &c->phi, &c->wphi, &c->rhoPrd, &c->aDamp, &c->wlambdaTab,
+                             &c->alphaTab, &c->transWave, &c->lowerBcData, &c->upperBcData, &c->accum,
+                             &c->prefill, &c->gamma, &c->dJ, &c->depthChi, &c->depthEta, &c->depthI, &c->djOut};
+    for (auto* b : dbl)
+        b->release();
+    DevBuf<int>* ints[] = {&c->lowerBcIdx, &c->upperBcIdx, &c->dLaOff, &c->dLaHasLine, &c->dTileLa,
+                           &c->dTileSlotOff, &c->dTileSlotTrans, &c->dAtomNlevel, &c->dAtomLevOff,
+                           &c->dAtomGammaOff, &c->dAtomDetailed, &c->dSingular};
+    for (auto* b : ints)
+        b->release();
+    c->djIdx.release();
+    c->dTrans.release();
+    c->dEntries.release();
+    c->dLines.release();
+    delete c;
+    return 0;
+}
+
+int lwb200_set_stream(LwB200Context* c, void* stream)
+{
+    c->stream = (cudaStream_t)stream;
+    return 0;
+}
+
+int lwb200_set_lambda_range(LwB200Context* c, int32_t laStart, int32_t laEnd)
+{
+    if (laStart < 0 || laEnd > c->prob.Nspect || laStart > laEnd)
+        return fail("lwb200_set_lambda_range: bad range");
+    c->laLo = laStart;
+    c->laHi = laEnd;
+    return 0;
+}
+
+int lwb200_sync(LwB200Context* c)
+{
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lwb200_upload(LwB200Context* c, uint32_t mask)
+{
+    CU(cudaSetDevice(c->device));
+    const LwB200Problem& p = c->prob;
+    const size_t K = p.Nspace, L = p.Nspect, M = p.Nrays, ncol = p.Ncol;
+    const size_t D = sizeof(double);
+    cudaStream_t s = c->stream;
+    const auto H2D = cudaMemcpyHostToDevice;
+    c->lastLaunches = 0;
+    if (mask & LWB200_ATMOS)
+    {
+        CU(cudaMemcpyAsync(c->height.p, p.height, ncol * K * D, H2D, s));
+        CU(cudaMemcpyAsync(c->temperature.p, p.temperature, ncol * K * D, H2D, s));
+        if (p.vlosMu)
+            CU(cudaMemcpyAsync(c->vlosMu.p, p.vlosMu, ncol * M * K * D, H2D, s));
+        if (p.lowerBc == LWB200_BC_CALLABLE)
+            CU(cudaMemcpyAsync(c->lowerBcData.p, p.lowerBcData, ncol * L * p.NlowerBcMu * D, H2D, s));
+        if (p.upperBc == LWB200_BC_CALLABLE)
+            CU(cudaMemcpyAsync(c->upperBcData.p, p.upperBcData, ncol * L * p.NupperBcMu * D, H2D, s));
+    }
+    if (mask & LWB200_BACKGR)
+    {
+        CU(cudaMemcpyAsync(c->chiBg.p, p.chiBg, ncol * L * K * D, H2D, s));
+        CU(cudaMemcpyAsync(c->etaBg.p, p.etaBg, ncol * L * K * D, H2D, s));
+        CU(cudaMemcpyAsync(c->scaBg.p, p.scaBg, ncol * L * K * D, H2D, s));
+    }
+    if (mask & LWB200_JBAR)
+        CU(cudaMemcpyAsync(c->J.p, p.J, ncol * L * K * D, H2D, s));
+    for (int a = 0; a < p.Natom; ++a)
+    {
+        const LwB200Atom& at = c->atoms[a];
+        const size_t N = at.Nlevel;
+        const size_t rowN = (size_t)c->P.NlevTot * K * D;
+        if (mask & LWB200_POPS)
+            if (copy2d(c->n.p + (size_t)c->atomLevOff[a] * K, rowN, at.n, N * K * D, N * K * D, ncol, H2D, s))
+                return 1;
+        if (mask & LWB200_NSTAR)
+        {
+            if (copy2d(c->nStar.p + (size_t)c->atomLevOff[a] * K, rowN, at.nStar, N * K * D, N * K * D, ncol, H2D, s))
+                return 1;
+            if (copy2d(c->nTotal.p + (size_t)a * K, (size_t)p.Natom * K * D, at.nTotal, K * D, K * D, ncol, H2D, s))
+                return 1;
+            if (at.vBroad
+                && copy2d(c->vBroad.p + (size_t)a * K, (size_t)p.Natom * K * D, at.vBroad, K * D, K * D, ncol, H2D, s))
+                return 1;
+        }
+        if ((mask & LWB200_GAMMA) && !at.detailedStatic)
+        {
+            if (!at.Gamma)
+                return fail("active atom without Gamma buffer");
+            if (copy2d(c->prefill.p + (size_t)c->atomGammaOff[a] * K, (size_t)c->P.GammaTot * K * D, at.Gamma,
+                       N * N * K * D, N * N * K * D, ncol, H2D, s))
+                return 1;
+        }
+    }
+    if (mask & LWB200_NSTAR)
+    {
+        if (c->P.Ncont > 0)
+        {
+            const size_t total = (size_t)c->P.Ncont * ncol * K;
+            ratio_kernel<<<grid_for(total), 256, 0, s>>>(c->P, c->gRatio.p);
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
+        }
+        c->nstarUploaded = true;
+    }
+    if (mask & LWB200_GAMMA_FINAL)
+    {
+        for (int a = 0; a < p.Natom; ++a)
+        {
+            const LwB200Atom& at = c->atoms[a];
+            const size_t N = at.Nlevel;
+            if (at.detailedStatic)
+                continue;
+            if (copy2d(c->gamma.p + (size_t)c->atomGammaOff[a] * K, (size_t)c->P.GammaTot * K * D, at.Gamma,
+                       N * N * K * D, N * N * K * D, ncol, H2D, s))
+                return 1;
+        }
+    }
+    if ((mask & LWB200_ADAMP) && !(mask & LWB200_PROFILE))
+    {
+        for (size_t g = 0; g < c->trans.size(); ++g)
+        {
+            const DevTrans& d = c->devTrans[g];
+            const LwB200Transition& t = c->trans[g].t;
+            if (d.type != 0)
+                continue;
+            if (!t.aDamp)
+                return fail("line without aDamp");
+            CU(cudaMemcpyAsync(c->aDamp.p + (size_t)d.lineIdx * ncol * K, t.aDamp, ncol * K * D, H2D, s));
+        }
+    }
+    if (mask & LWB200_PROFILE)
+    {
+        for (size_t g = 0; g < c->trans.size(); ++g)
+        {
+            const DevTrans& d = c->devTrans[g];
+            const LwB200Transition& t = c->trans[g].t;
+            if (d.type != 0)
+                continue;
+            const size_t Nl = d.Nred - d.Nblue;
+            CU(cudaMemcpyAsync(c->phi.p + d.phiOff, t.phi, ncol * Nl * M * 2 * K * D, H2D, s));
+            CU(cudaMemcpyAsync(c->wphi.p + (size_t)d.lineIdx * ncol * K, t.wphi, ncol * K * D, H2D, s));
+            if (t.aDamp)
+                CU(cudaMemcpyAsync(c->aDamp.p + (size_t)d.lineIdx * ncol * K, t.aDamp, ncol * K * D, H2D, s));
+            if (d.rhoOff >= 0)
+                CU(cudaMemcpyAsync(c->rhoPrd.p + d.rhoOff, t.rhoPrd, ncol * Nl * K * D, H2D, s));
+        }
+    }
+    return 0;
+}
+
+int lwb200_download(LwB200Context* c, uint32_t mask)
+{
+    CU(cudaSetDevice(c->device));
+    const LwB200Problem& p = c->prob;
+    const size_t K = p.Nspace, L = p.Nspect, M = p.Nrays, ncol = p.Ncol;
+    const size_t D = sizeof(double);
+    cudaStream_t s = c->stream;
+    const auto D2H = cudaMemcpyDeviceToHost;
+    if (mask & LWB200_JBAR)
+        CU(cudaMemcpyAsync(p.J, c->J.p, ncol * L * K * D, D2H, s));
+    if (mask & LWB200_INTENS)
+        CU(cudaMemcpyAsync(p.I, c->I.p, ncol * L * M * D, D2H, s));
+    for (int a = 0; a < p.Natom; ++a)
+    {
+        const LwB200Atom& at = c->atoms[a];
+        const size_t N = at.Nlevel;
+        if (mask & LWB200_POPS)
+            if (copy2d(at.n, N * K * D, c->n.p + (size_t)c->atomLevOff[a] * K, (size_t)c->P.NlevTot * K * D,
+                       N * K * D, ncol, D2H, s))
+                return 1;
+        if ((mask & LWB200_GAMMA) && !at.detailedStatic)
+            if (copy2d(at.Gamma, N * N * K * D, c->gamma.p + (size_t)c->atomGammaOff[a] * K,
+                       (size_t)c->P.GammaTot * K * D, N * N * K * D, ncol, D2H, s))
+                return 1;
+    }
+    if (mask & LWB200_RATES)
+    {
+        const size_t pitch = (size_t)c->P.AccTot * K * D;
+        for (size_t g = 0; g < c->trans.size(); ++g)
+        {
+            const DevTrans& d = c->devTrans[g];
+            const LwB200Transition& t = c->trans[g].t;
+            if (copy2d(t.Rij, K * D, c->accum.p + (size_t)d.accRij * K, pitch, K * D, ncol, D2H, s))
+                return 1;
+            if (copy2d(t.Rji, K * D, c->accum.p + (size_t)d.accRji * K, pitch, K * D, ncol, D2H, s))
+                return 1;
+        }
+    }
+    if ((mask & LWB200_DEPTH) && c->depthChi.p)
+    {
+        const size_t nd = ncol * L * M * 2 * K * D;
+        CU(cudaMemcpyAsync(p.depthChi, c->depthChi.p, nd, D2H, s));
+        CU(cudaMemcpyAsync(p.depthEta, c->depthEta.p, nd, D2H, s));
+        CU(cudaMemcpyAsync(p.depthI, c->depthI.p, nd, D2H, s));
+    }
+    if (mask & LWB200_PROFILE)
+    {
+        for (size_t g = 0; g < c->trans.size(); ++g)
+        {
+            const DevTrans& d = c->devTrans[g];
+            const LwB200Transition& t = c->trans[g].t;
+            if (d.type != 0)
+                continue;
+            const size_t Nl = d.Nred - d.Nblue;
+            CU(cudaMemcpyAsync(t.phi, c->phi.p + d.phiOff, ncol * Nl * M * 2 * K * D, D2H, s));
+            CU(cudaMemcpyAsync(t.wphi, c->wphi.p + (size_t)d.lineIdx * ncol * K, ncol * K * D, D2H, s));
+        }
+    }
+    return 0;
+}
+
+int lwb200_compute_profiles(LwB200Context* c)
+{
+    CU(cudaSetDevice(c->device));
+    if (!c->vlosMu.p)
+        return fail("lwb200_compute_profiles: the problem has no vlosMu");
+    if (c->devLines.empty())
+        return 0;
+    c->lastLaunches = 0;
+    int rc = launch_profiles(c->P, c->dLines.p, (int)c->devLines.size(), c->devLines.data(), c->transWave.p,
+                             c->wlambdaTab.p, c->aDamp.p, c->vBroad.p, c->vlosMu.p, c->phi.p, c->wphi.p,
+                             c->stream, &c->lastLaunches);
+    if (rc)
+        return fail(std::string("lwb200_compute_profiles: ") + cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
+int lwb200_finalise(LwB200Context* c)
+{
+    CU(cudaSetDevice(c->device));
+    if (c->P.GammaTot > 0)
+    {
+        const size_t total = (size_t)c->P.Ncol * c->P.Natom * c->P.K;
+        finalise_kernel<<<grid_for(total), 256, 0, c->stream>>>(c->P, c->prefill.p, c->gamma.p);
+        CU(cudaGetLastError());
+        c->lastLaunches += 1;
+    }
+    return 0;
+}
+
+int lwb200_dj_max(LwB200Context* c, double* dJMax, int64_t* dJMaxIdx)
+{
+    CU(cudaSetDevice(c->device));
+    dj_reduce_kernel<<<1, 256, 0, c->stream>>>(c->dJ.p, c->P.Ncol, c->P.L, c->laLo, c->laHi, c->djOut.p,
+                                               c->djIdx.p);
+    CU(cudaGetLastError());
+    c->lastLaunches += 1;
+    double m = 0.0;
+    long long idx = 0;
+    CU(cudaMemcpyAsync(&m, c->djOut.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&idx, c->djIdx.p, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (dJMax)
+        *dJMax = m;
+    if (dJMaxIdx)
+        *dJMaxIdx = idx;
+    return 0;
+}
+
+int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJMaxIdx)
+{
+    CU(cudaSetDevice(c->device));
+    if (!c->nstarUploaded)
+        return fail("lwb200_fs_iter: inputs have not been uploaded (lwb200_upload)");
+    const int storeDepth = (flags & LWB200_STORE_DEPTH) ? 1 : 0;
+    if (storeDepth && !c->depthChi.p)
+        return fail("lwb200_fs_iter: STORE_DEPTH without depth arrays in the problem");
+    c->lastLaunches = 0;
+    // zero_rates + fresh partial sums (:605-612, :643)
+    CU(cudaMemsetAsync(c->accum.p, 0, c->accum.n * sizeof(double), c->stream));
+    if (launch_fs<MODE_ITER>(c, (flags & LWB200_LAMBDA_ITERATE) ? 1 : 0, 0, storeDepth))
+        return 1;
+    if (!(flags & LWB200_DEFER_FINALISE))
+        if (lwb200_finalise(c))
+            return 1;
+    if (dJMax || dJMaxIdx)
+        return lwb200_dj_max(c, dJMax, dJMaxIdx);
+    return 0;
+}
+
+int lwb200_formal_sol(LwB200Context* c, int upOnly)
+{
+    CU(cudaSetDevice(c->device));
+    if (!c->nstarUploaded)
+        return fail("lwb200_formal_sol: inputs have not been uploaded (lwb200_upload)");
+    c->lastLaunches = 0;
+    return launch_fs<MODE_FS>(c, 0, upOnly ? 1 : 0, 0);
+}
+
+int lwb200_stat_eq(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd, int32_t* nSingular)
+{
+    CU(cudaSetDevice(c->device));
+    const int K = c->prob.Nspace;
+    if (kStart < 0 && kEnd < 0)
+    {
+        kStart = 0;
+        kEnd = K;
+    }
+    if (kStart < 0 || kEnd > K || kStart >= kEnd)
+        return fail("lwb200_stat_eq: bad depth range");
+    if (atom >= c->prob.Natom)
+        return fail("lwb200_stat_eq: atom index out of range");
+    c->lastLaunches = 0;
+    CU(cudaMemsetAsync(c->dSingular.p, 0, sizeof(int), c->stream));
+    for (int a = 0; a < c->prob.Natom; ++a)
+    {
+        if (atom >= 0 && a != atom)
+            continue;
+        if (c->atoms[a].detailedStatic)
+            continue;
+        const size_t total = (size_t)c->prob.Ncol * (kEnd - kStart);
+        const int N = c->atoms[a].Nlevel;
+        if (N <= 8)
+            stat_eq_kernel<8><<<grid_for(total, 64), 64, 0, c->stream>>>(c->P, a, kStart, kEnd, c->gamma.p, c->n.p,
+                                                                           c->nTotal.p, c->dSingular.p);
+        else if (N <= 16)
+            stat_eq_kernel<16><<<grid_for(total, 64), 64, 0, c->stream>>>(c->P, a, kStart, kEnd, c->gamma.p, c->n.p,
+                                                                            c->nTotal.p, c->dSingular.p);
+        else
+            stat_eq_kernel<32><<<grid_for(total, 64), 64, 0, c->stream>>>(c->P, a, kStart, kEnd, c->gamma.p, c->n.p,
+                                                                            c->nTotal.p, c->dSingular.p);
+        CU(cudaGetLastError());
+        c->lastLaunches += 1;
+    }
+    int ns = 0;
+    CU(cudaMemcpyAsync(&ns, c->dSingular.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (nSingular)
+        *nSingular = ns;
+    if (ns > 0)
+        return fail("Singular Matrix");
+    return 0;
+}
+
+int lwb200_device_buffer(LwB200Context* c, int32_t which, void** ptr, size_t* nbytes)
+{
+    DevBuf<double>* b = nullptr;
+    switch (which)
+    {
+    case LWB200_BUF_ACCUM: b = &c->accum; break;
+    case LWB200_BUF_J: b = &c->J; break;
+    case LWB200_BUF_I: b = &c->I; break;
+    case LWB200_BUF_POPS: b = &c->n; break;
+    case LWB200_BUF_GAMMA: b = &c->gamma; break;
+    case LWB200_BUF_DJ: b = &c->dJ; break;
+    default: return fail("lwb200_device_buffer: unknown buffer");
+    }
+    if (ptr)
+        *ptr = b->p;
+    if (nbytes)
+        *nbytes = b->n * sizeof(double);
+    return 0;
+}
+
+int lwb200_work_stats(LwB200Context* c, double* points, double* algBytes, int64_t* lastLaunches)
+{
+    const LwB200Problem& p = c->prob;
+    const double K = p.Nspace, M = p.Nrays, ncol = p.Ncol;
+    const double Lr = c->laHi - c->laLo;
+    if (points)
+        *points = ncol * K * Lr * M * 2.0;
+    if (algBytes)
+    {
+        // every array once
+        double Pr = 0.0, nlines = 0.0, b = 0.0;
+        for (const DevTrans& d : c->devTrans)
+        {
+            if (d.type != 0)
+                continue;
+            const int lo = std::max(d.Nblue, c->laLo), hi = std::min(d.Nred, c->laHi);
+            if (hi > lo)
+            {
+                Pr += hi - lo;
+                nlines += 1;
+            }
+        }
+        b = Pr * M * 2 * K + 5.0 * Lr * K + Lr * M + nlines * K + 2 * K;
+        for (int a = 0; a < p.Natom; ++a)
+        {
+            const LwB200Atom& at = c->atoms[a];
+            b += 2.0 * at.Nlevel * K + 2.0 * at.Ntrans * K;
+            if (!at.detailedStatic)
+                b += 2.0 * at.Nlevel * at.Nlevel * K;
+        }
+        *algBytes = 8.0 * b * ncol;
+    }
+    if (lastLaunches)
+        *lastLaunches = c->lastLaunches;
+    return 0;
+}
+} // extern "C"

@@ -1,0 +1,732 @@
+// lwb200_kernels.cuh -- the hot-path kernels.
+//
+//   fs_kernel<NCH, SOLVER, MODE>   gather + source function + formal solution
+//                                  (+ J, Gamma, Rij/Rji for MODE_ITER)
+//                                  replaces intensity_core_opt and everything it
+//                                  calls (SimdFullIterationTemplates.hpp:59-487)
+//   finalise_kernel                Gamma = prefill + partial sums, diagonal
+//                                  (finalise_Gamma, :491-508)
+//   stat_eq_kernel                 per-depth N x N solve (UpdatePopulations.cpp:7-47,
+//                                  LuSolve.cpp:8-133)
+//   ratio_kernel, dj_reduce_kernel small helpers
+//
+// Work decomposition (replaces TaskScheduler/ThreadStorage): the host planner
+// cuts the wavelength axis into tiles; one CTA owns (tile, column); its warps
+// take wavelengths round-robin; per-transition Gamma/R partial sums live in
+// shared memory for the whole tile and are flushed once with fp64 atomics.
+#pragma once
+#include "lwb200_device.cuh"
+
+namespace lwb200
+{
+enum { MODE_FS = 0, MODE_ITER = 1 };
+
+struct DevTrans
+{
+    int type; // 0 line, 1 continuum
+    int i, j; // levels within the atom
+    int atom;
+    int Nblue, Nred;
+    int levI, levJ;       // rows in the packed population arrays
+    int accIJ, accJI;     // rows in the packed accumulator for Gamma(i,j), Gamma(j,i); -1: none
+    int accRij, accRji;   // rows for Rij, Rji
+    int tabOff;           // offset into wlambdaTab / alphaTab
+    int lineIdx;          // index among lines, -1 for continua
+    int contIdx;          // index among continua, -1 for lines
+    int detailed;         // belongs to a detailed-static atom
+    long long phiOff;     // element offset of phi[col = 0] in the phi pool
+    long long phiColStride;
+    long long rhoOff;     // -1: no rhoPrd
+    double Aji_Bji;       // Aji / Bji
+    double Bji_Bij;       // Bji / Bij
+    double Bij;
+    double lambda0;
+};
+
+struct DevEntry
+{
+    int trans;
+    int slot;
+};
+
+struct DevProblem
+{
+    int Ncol, K, M, L;
+    int NlevTot, GammaTot, AccTot, Natom, NtransTot, Nline, Ncont;
+    int lowerBc, upperBc, NlowerBcMu, NupperBcMu;
+    int maxNlevel, maxSlots, KP;
+    const double *height, *temperature, *muz, *wmu, *wavelength;
+    const double *chiBg, *etaBg, *scaBg;
+    double *J, *I;
+    const double *n, *nStar, *gRatio;
+    const double *phi, *wphi, *rhoPrd;
+    const double *wlambdaTab, *alphaTab;
+    const double *lowerBcData, *upperBcData;
+    const int *lowerBcIdx, *upperBcIdx;
+    double* accum;
+    double* dJ;
+    double *depthChi, *depthEta, *depthI;
+    const DevTrans* trans;
+    const DevEntry* entries;
+    const int* laOff;
+    const int* laHasLine;
+    const int* tileLa;       // [Ntile + 1]
+    const int* tileSlotOff;  // [Ntile + 1]
+    const int* tileSlotTrans;
+    const int* atomNlevel;
+    const int* atomLevOff;
+    const int* atomGammaOff;
+    const int* atomDetailed;
+};
+
+// U, V for one transition at one (wavelength, ray, depth): Transition::uv
+// (LwTransition.hpp:93-144) with gij from Atom::setup_wavelength
+// (LwAtom.hpp:82-128), same operation order.
+struct UV
+{
+    double Vij, Vji, Uji;
+};
+
+__device__ __forceinline__ UV trans_uv(const DevProblem& P, const DevTrans& t, int col, int lt,
+                                       int mu, int dir, int k, double lambda, double expfac)
+{
+    UV r;
+    if (t.type == 0)
+    {
+        constexpr double hc_4pi = 0.25 * kHC / kPi;
+        const double hnu_4pi = hc_4pi * (t.lambda0 / lambda);
+        const double p = __ldg(P.phi + t.phiOff + (long long)col * t.phiColStride
+                               + ((long long)(lt * P.M + mu) * 2 + dir) * P.K + k);
+        double g = t.Bji_Bij;
+        if (t.rhoOff >= 0)
+            g *= __ldg(P.rhoPrd + t.rhoOff + ((long long)col * (t.Nred - t.Nblue) + lt) * P.K + k);
+        r.Vij = hnu_4pi * t.Bij * p;
+        r.Vji = g * r.Vij;
+        r.Uji = t.Aji_Bji * r.Vji;
+    }
+    else
+    {
+        constexpr double twoHc = 2.0 * kHC / (kNmToM * kNmToM * kNmToM);
+        const double hcl = twoHc / (lambda * lambda * lambda);
+        const double g = __ldg(P.gRatio + ((long long)t.contIdx * P.Ncol + col) * P.K + k) * expfac;
+        r.Vij = __ldg(P.alphaTab + t.tabOff + lt);
+        r.Vji = g * r.Vij;
+        r.Uji = hcl * r.Vji;
+    }
+    return r;
+}
+
+// wla(kr, k) of Atom::setup_wavelength (LwAtom.hpp:100-118)
+__device__ __forceinline__ double trans_wla(const DevProblem& P, const DevTrans& t, int col, int lt,
+                                            int k, double lambda)
+{
+    constexpr double pi4_h = 4.0 * kPi / kHPlanck;
+    constexpr double hc_4pi = 0.25 * kHC / kPi;
+    constexpr double pi4_hc = 1.0 / hc_4pi;
+    const double wlam = __ldg(P.wlambdaTab + t.tabOff + lt);
+    if (t.type == 0)
+        return wlam * __ldg(P.wphi + ((long long)t.lineIdx * P.Ncol + col) * P.K + k) * pi4_hc;
+    return (wlam / lambda) * pi4_h;
+}
+
+__device__ __forceinline__ void smem_add(double* addr, double v) { atomicAdd(addr, v); }
+
+// ---------------------------------------------------------------------------
+template <int NCH, int SOLVER, int MODE>
+__global__ void __launch_bounds__(128)
+fs_kernel(const DevProblem P, int tile0, int laLo, int laHi, int lambdaIterate, int upOnly,
+          int storeDepth)
+{
+    extern __shared__ double smem[];
+    const int K = P.K, M = P.M, L = P.L, KP = P.KP;
+    const int tile = tile0 + blockIdx.x;
+    const int col = blockIdx.y;
+    const int warp = threadIdx.x >> 5;
+    const int nwarp = blockDim.x >> 5;
+    const int lane = lane_id();
+
+    const int slot0 = P.tileSlotOff[tile];
+    const int nslot = P.tileSlotOff[tile + 1] - slot0;
+    double* acc = smem;                                   // [nslot][4][KP]
+    double* scratch = smem + (size_t)P.maxSlots * 4 * KP  // per warp [2][maxNlevel][32]
+        + (size_t)warp * 2 * P.maxNlevel * 32;
+
+    if (MODE == MODE_ITER)
+    {
+        for (int idx = threadIdx.x; idx < nslot * 4 * KP; idx += blockDim.x)
+            acc[idx] = 0.0;
+        __syncthreads();
+    }
+
+    Geometry<NCH> g;
+    load_geometry<NCH>(g, P.height + (size_t)col * K, K);
+    double T[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+    {
+        const int k = g.k(j);
+        T[j] = (k < K) ? __ldg(P.temperature + (size_t)col * K + k) : 1.0;
+    }
+    const double Ttop0 = __ldg(P.temperature + (size_t)col * K + 0);
+    const double Ttop1 = __ldg(P.temperature + (size_t)col * K + 1);
+    const double Tbot0 = __ldg(P.temperature + (size_t)col * K + K - 1);
+    const double Tbot1 = __ldg(P.temperature + (size_t)col * K + K - 2);
+
+    int laBeg = max(P.tileLa[tile], laLo);
+    int laEnd = min(P.tileLa[tile + 1], laHi);
+
+    for (int la = laBeg + warp; la < laEnd; la += nwarp)
+    {
+        const double lambda = __ldg(P.wavelength + la);
+        const size_t rowLK = ((size_t)col * L + la) * K;
+        const int eBeg = P.laOff[la], eEnd = P.laOff[la + 1];
+        const bool hasLine = P.laHasLine[la] != 0;
+
+        // --- ray-independent part: background + continua (the reference's
+        //     continuaOnly shortcut, :295-307, generalised: continua are
+        //     angle-independent at every wavelength)
+        double chiC[NCH], etaC[NCH], scaJ[NCH], JDag[NCH], expfac[NCH];
+        constexpr double hc_k = kHC / (kKBoltzmann * kNmToM);
+        const double hc_kl = hc_k / lambda;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            const int k = g.k(j);
+            const bool v = k < K;
+            chiC[j] = v ? __ldg(P.chiBg + rowLK + k) : 1.0;
+            etaC[j] = v ? __ldg(P.etaBg + rowLK + k) : 0.0;
+            const double sca = v ? __ldg(P.scaBg + rowLK + k) : 0.0;
+            JDag[j] = v ? P.J[rowLK + k] : 0.0;
+            scaJ[j] = sca * JDag[j];
+            expfac[j] = exp(-hc_kl / T[j]);
+        }
+        for (int e = eBeg; e < eEnd; ++e)
+        {
+            const DevTrans& t = P.trans[P.entries[e].trans];
+            if (t.type == 0)
+                continue;
+            const int lt = la - t.Nblue;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+            {
+                const int k = g.k(j);
+                if (k < K)
+                {
+                    const UV uv = trans_uv(P, t, col, lt, 0, 0, k, lambda, expfac[j]);
+                    const double ni = __ldg(P.n + ((size_t)col * P.NlevTot + t.levI) * K + k);
+                    const double nj = __ldg(P.n + ((size_t)col * P.NlevTot + t.levJ) * K + k);
+                    chiC[j] += ni * uv.Vij - nj * uv.Vji;
+                    etaC[j] += nj * uv.Uji;
+                }
+            }
+        }
+
+        double Jnew[NCH];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+            Jnew[j] = 0.0;
+
+        for (int mu = 0; mu < M; ++mu)
+        {
+            const double muz = __ldg(P.muz + mu);
+            const double halfwmu = 0.5 * __ldg(P.wmu + mu);
+            for (int dir = upOnly ? 1 : 0; dir < 2; ++dir)
+            {
+                // --- opacity, emissivity, source function for this ray
+                double chi[NCH], S[NCH];
+                {
+                    double eta[NCH];
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+                    {
+                        chi[j] = chiC[j];
+                        eta[j] = etaC[j];
+                    }
+                    if (hasLine)
+                    {
+                        for (int e = eBeg; e < eEnd; ++e)
+                        {
+                            const DevTrans& t = P.trans[P.entries[e].trans];
+                            if (t.type != 0)
+                                continue;
+                            const int lt = la - t.Nblue;
+#pragma unroll
+                            for (int j = 0; j < NCH; ++j)
+                            {
+                                const int k = g.k(j);
+                                if (k < K)
+                                {
+                                    const UV uv = trans_uv(P, t, col, lt, mu, dir, k, lambda, 0.0);
+                                    const double ni = __ldg(P.n + ((size_t)col * P.NlevTot + t.levI) * K + k);
+                                    const double nj = __ldg(P.n + ((size_t)col * P.NlevTot + t.levJ) * K + k);
+                                    chi[j] += ni * uv.Vij - nj * uv.Vji;
+                                    eta[j] += nj * uv.Uji;
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+                        S[j] = (eta[j] + scaJ[j]) / chi[j]; // compute_source_fn (:169-179)
+                    if (MODE == MODE_ITER && storeDepth)
+                    {
+                        const size_t off = ((((size_t)col * L + la) * M + mu) * 2 + dir) * K;
+#pragma unroll
+                        for (int j = 0; j < NCH; ++j)
+                        {
+                            const int k = g.k(j);
+                            if (k < K)
+                            {
+                                P.depthChi[off + k] = chi[j];
+                                P.depthEta[off + k] = eta[j];
+                            }
+                        }
+                    }
+                }
+
+                // --- boundary condition + formal solution (:344-349)
+                RayBc bc;
+                bc.value = 0.0;
+                bc.B0 = bc.B1 = 0.0;
+                if (dir == 1)
+                {
+                    bc.type = P.lowerBc;
+                    if (bc.type == 2)
+                    {
+                        bc.B0 = planck_nu(Tbot0, lambda);
+                        bc.B1 = planck_nu(Tbot1, lambda);
+                    }
+                    else if (bc.type == 4)
+                    {
+                        const int idx = P.lowerBcIdx[mu * 2 + 1];
+                        bc.value = P.lowerBcData[((size_t)col * L + la) * P.NlowerBcMu + idx];
+                    }
+                }
+                else
+                {
+                    bc.type = P.upperBc;
+                    if (bc.type == 2)
+                    {
+                        bc.B0 = planck_nu(Ttop0, lambda);
+                        bc.B1 = planck_nu(Ttop1, lambda);
+                    }
+                    else if (bc.type == 4)
+                    {
+                        const int idx = P.upperBcIdx[mu * 2 + 0];
+                        bc.value = P.upperBcData[((size_t)col * L + la) * P.NupperBcMu + idx];
+                    }
+                }
+                double I[NCH], psi[NCH];
+                if (dir == 1)
+                    solve_ray<NCH, SOLVER, false, MODE == MODE_ITER>(g, chi, S, muz, bc, I, psi);
+                else
+                    solve_ray<NCH, SOLVER, true, MODE == MODE_ITER>(g, chi, S, muz, bc, I, psi);
+
+                if (lane == 0)
+                    P.I[((size_t)col * L + la) * M + mu] = I[0]; // spect.I(la, mu, 0) = I(0)
+
+                if (MODE != MODE_ITER)
+                    continue;
+
+                if (storeDepth)
+                {
+                    const size_t off = ((((size_t)col * L + la) * M + mu) * 2 + dir) * K;
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+                    {
+                        const int k = g.k(j);
+                        if (k < K)
+                            P.depthI[off + k] = I[j];
+                    }
+                }
+
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+                    Jnew[j] += halfwmu * I[j]; // accumulate_J (:181-190)
+
+                if (lambdaIterate)
+                {
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+                        psi[j] = 0.0;
+                }
+
+                // --- Gamma and rates, atom by atom (:411-467), one depth chunk
+                //     at a time through a per-warp shared scratch that holds
+                //     the per-level chi_atom / U_atom of chi_eta_aux_accum (:59-109)
+                int e0 = eBeg;
+                while (e0 < eEnd)
+                {
+                    const int atom = P.trans[P.entries[e0].trans].atom;
+                    int e1 = e0 + 1;
+                    while (e1 < eEnd && P.trans[P.entries[e1].trans].atom == atom)
+                        ++e1;
+                    const bool detailed = P.atomDetailed[atom] != 0;
+                    const int N = P.atomNlevel[atom];
+                    double* Xs = scratch;                      // chi_atom[level][lane]
+                    double* Us = scratch + P.maxNlevel * 32;   // U_atom[level][lane]
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+                    {
+                        const int k = g.k(j);
+                        if (k < K)
+                        {
+                            double Ieff = I[j];
+                            if (!detailed)
+                            {
+                                for (int m = 0; m < N; ++m)
+                                {
+                                    Xs[m * 32 + lane] = 0.0;
+                                    Us[m * 32 + lane] = 0.0;
+                                }
+                                double etaA = 0.0;
+                                for (int e = e0; e < e1; ++e)
+                                {
+                                    const DevTrans& t = P.trans[P.entries[e].trans];
+                                    const UV uv = trans_uv(P, t, col, la - t.Nblue, mu, dir, k, lambda, expfac[j]);
+                                    const double ni = __ldg(P.n + ((size_t)col * P.NlevTot + t.levI) * K + k);
+                                    const double nj = __ldg(P.n + ((size_t)col * P.NlevTot + t.levJ) * K + k);
+                                    const double x = ni * uv.Vij - nj * uv.Vji;
+                                    Xs[t.i * 32 + lane] += x;
+                                    Xs[t.j * 32 + lane] -= x;
+                                    Us[t.j * 32 + lane] += uv.Uji;
+                                    etaA += nj * uv.Uji;
+                                }
+                                Ieff = I[j] - psi[j] * etaA; // compute_full_Ieff (:192-204)
+                            }
+                            for (int e = e0; e < e1; ++e)
+                            {
+                                const DevEntry en = P.entries[e];
+                                const DevTrans& t = P.trans[en.trans];
+                                const int lt = la - t.Nblue;
+                                const UV uv = trans_uv(P, t, col, lt, mu, dir, k, lambda, expfac[j]);
+                                const double wlamu = trans_wla(P, t, col, lt, k, lambda) * halfwmu;
+                                double* a4 = acc + (size_t)en.slot * 4 * KP + k;
+                                if (!detailed)
+                                {
+                                    // compute_full_operator_rates (:218-226)
+                                    double integrand = (uv.Uji + uv.Vji * Ieff)
+                                        - (psi[j] * Xs[t.i * 32 + lane] * Us[t.j * 32 + lane]);
+                                    smem_add(a4, integrand * wlamu);
+                                    integrand = (uv.Vij * Ieff)
+                                        - (psi[j] * Xs[t.j * 32 + lane] * Us[t.i * 32 + lane]);
+                                    smem_add(a4 + KP, integrand * wlamu);
+                                }
+                                smem_add(a4 + 2 * KP, I[j] * uv.Vij * wlamu);              // Rij (:230)
+                                smem_add(a4 + 3 * KP, (uv.Uji + I[j] * uv.Vji) * wlamu);   // Rji (:231)
+                            }
+                        }
+                    }
+                    e0 = e1;
+                }
+            }
+        }
+
+        if (MODE == MODE_ITER)
+        {
+            // J row and dJ = max_k |1 - Jdag/J|  (:477-485)
+            double dJ = 0.0;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+            {
+                const int k = g.k(j);
+                if (k < K)
+                {
+                    P.J[rowLK + k] = Jnew[j];
+                    const double d = fabs(1.0 - JDag[j] / Jnew[j]);
+                    dJ = (d < dJ) ? dJ : d;
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1)
+            {
+                const double o = __shfl_xor_sync(kFull, dJ, d);
+                dJ = (o < dJ) ? dJ : o;
+            }
+            if (lane == 0)
+                P.dJ[(size_t)col * L + la] = dJ;
+        }
+    }
+
+    if (MODE == MODE_ITER)
+    {
+        __syncthreads();
+        // flush this tile's partial sums (one fp64 RED per element per tile)
+        for (int idx = threadIdx.x; idx < nslot * 4 * KP; idx += blockDim.x)
+        {
+            const int k = idx % KP;
+            const int q = (idx / KP) & 3;
+            const int s = idx / (4 * KP);
+            if (k >= K)
+                continue;
+            const DevTrans& t = P.trans[P.tileSlotTrans[slot0 + s]];
+            const int row = q == 0 ? t.accIJ : q == 1 ? t.accJI : q == 2 ? t.accRij : t.accRji;
+            if (row < 0)
+                continue;
+            const double v = acc[idx];
+            if (v != 0.0)
+                atomicAdd(P.accum + ((size_t)col * P.AccTot + row) * K + k, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// gRatio[cont][col][k] = nStar(i,k) / nStar(j,k): the ray- and wavelength-
+// independent factor of gij for continua (LwAtom.hpp:112)
+__global__ void ratio_kernel(const DevProblem P, double* gRatio)
+{
+    const size_t total = (size_t)P.Ncont * P.Ncol * P.K;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x)
+    {
+        const int k = idx % P.K;
+        const int col = (idx / P.K) % P.Ncol;
+        const int c = idx / ((size_t)P.K * P.Ncol);
+        // find the c-th continuum
+        int tIdx = -1;
+        for (int t = 0; t < P.NtransTot; ++t)
+            if (P.trans[t].contIdx == c)
+            {
+                tIdx = t;
+                break;
+            }
+        const DevTrans& t = P.trans[tIdx];
+        const double ni = P.nStar[((size_t)col * P.NlevTot + t.levI) * P.K + k];
+        const double nj = P.nStar[((size_t)col * P.NlevTot + t.levJ) * P.K + k];
+        gRatio[idx] = ni / nj;
+    }
+}
+
+// finalise_Gamma (:491-508): Gamma = prefill (crsw*C) + radiative partial sums,
+// then diagonal = -(column sum).  One thread per (column, atom, depth).
+__global__ void finalise_kernel(const DevProblem P, const double* __restrict__ prefill,
+                                double* __restrict__ gamma)
+{
+    const size_t total = (size_t)P.Ncol * P.Natom * P.K;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x)
+    {
+        const int k = idx % P.K;
+        const int atom = (idx / P.K) % P.Natom;
+        const int col = idx / ((size_t)P.K * P.Natom);
+        if (P.atomDetailed[atom])
+            continue;
+        const int N = P.atomNlevel[atom];
+        const size_t gOff = ((size_t)col * P.GammaTot + P.atomGammaOff[atom]) * P.K + k;
+        const size_t aOff = ((size_t)col * P.AccTot + P.atomGammaOff[atom]) * P.K + k;
+        for (int i = 0; i < N; ++i)
+        {
+            double diag = 0.0;
+            for (int j = 0; j < N; ++j)
+            {
+                if (j == i)
+                    continue;
+                // Gamma(j, i): rate from i to j
+                const size_t r = (size_t)(j * N + i) * P.K;
+                const double v = prefill[gOff + r] + P.accum[aOff + r];
+                gamma[gOff + r] = v;
+                diag += v;
+            }
+            gamma[gOff + (size_t)(i * N + i) * P.K] = -diag;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// stat_eq_impl + solve_lin_eq (UpdatePopulations.cpp:7-47; LuSolve.cpp:8-133):
+// Crout LU with implicit scaled partial pivoting, Tiny = 1e-20 pivots, one
+// step of iterative refinement.  One thread per (column, depth) system of one
+// atom; MAXN bounds the local arrays.
+template <int MAXN>
+__device__ bool lu_decompose_dev(int N, double* A, int* index)
+{
+    constexpr double Tiny = 1e-20;
+    double vv[MAXN];
+    for (int i = 0; i < N; ++i)
+    {
+        double big = 0.0;
+        for (int j = 0; j < N; ++j)
+        {
+            const double v = fabs(A[i * N + j]);
+            big = (big < v) ? v : big;
+        }
+        if (big == 0.0)
+            return false;
+        vv[i] = 1.0 / big;
+    }
+    for (int j = 0; j < N; ++j)
+    {
+        for (int i = 0; i < j; ++i)
+        {
+            double sum = A[i * N + j];
+            for (int k = 0; k < i; ++k)
+                sum -= A[i * N + k] * A[k * N + j];
+            A[i * N + j] = sum;
+        }
+        int iMax = 0;
+        double big = 0.0;
+        for (int i = j; i < N; ++i)
+        {
+            double sum = A[i * N + j];
+            for (int k = 0; k < j; ++k)
+                sum -= A[i * N + k] * A[k * N + j];
+            A[i * N + j] = sum;
+            const double cand = vv[i] * fabs(sum);
+            if (big < cand)
+            {
+                big = cand;
+                iMax = i;
+            }
+        }
+        if (j != iMax)
+        {
+            for (int k = 0; k < N; ++k)
+            {
+                const double temp = A[iMax * N + k];
+                A[iMax * N + k] = A[j * N + k];
+                A[j * N + k] = temp;
+            }
+            vv[iMax] = vv[j];
+        }
+        index[j] = iMax;
+        if (A[j * N + j] == 0.0)
+            A[j * N + j] = Tiny;
+        const double temp = 1.0 / A[j * N + j];
+        for (int i = j + 1; i < N; ++i)
+            A[i * N + j] *= temp;
+    }
+    return true;
+}
+
+__device__ inline void lu_backsub_dev(int N, const double* A, const int* index, double* b)
+{
+    int ii = -1;
+    for (int i = 0; i < N; ++i)
+    {
+        const int ip = index[i];
+        double sum = b[ip];
+        b[ip] = b[i];
+        if (ii >= 0)
+        {
+            for (int j = ii; j < i; ++j)
+                sum -= A[i * N + j] * b[j];
+        }
+        else if (sum != 0.0)
+            ii = i;
+        b[i] = sum;
+    }
+    for (int i = N - 1; i >= 0; --i)
+    {
+        double sum = b[i];
+        for (int j = i + 1; j < N; ++j)
+            sum -= A[i * N + j] * b[j];
+        b[i] = sum / A[i * N + i];
+    }
+}
+
+template <int MAXN>
+__global__ void stat_eq_kernel(const DevProblem P, int atom, int kStart, int kEnd,
+                               const double* __restrict__ gamma, double* __restrict__ n,
+                               const double* __restrict__ nTotal, int* __restrict__ nSingular)
+{
+    const int nk = kEnd - kStart;
+    const size_t total = (size_t)P.Ncol * nk;
+    const int N = P.atomNlevel[atom];
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x)
+    {
+        const int k = kStart + idx % nk;
+        const int col = idx / nk;
+        double A[MAXN * MAXN], ACopy[MAXN * MAXN], b[MAXN], bCopy[MAXN], res[MAXN];
+        int index[MAXN];
+        const size_t gOff = ((size_t)col * P.GammaTot + P.atomGammaOff[atom]) * P.K + k;
+        const size_t nOff = ((size_t)col * P.NlevTot + P.atomLevOff[atom]) * P.K + k;
+        int iElim = 0;
+        double nMax = 0.0;
+        for (int i = 0; i < N; ++i)
+        {
+            const double ni = n[nOff + (size_t)i * P.K];
+            if (nMax < ni)
+            {
+                nMax = ni;
+                iElim = i;
+            }
+            for (int j = 0; j < N; ++j)
+                A[i * N + j] = gamma[gOff + (size_t)(i * N + j) * P.K];
+        }
+        for (int i = 0; i < N; ++i)
+        {
+            A[iElim * N + i] = 1.0;
+            b[i] = 0.0;
+        }
+        b[iElim] = nTotal[((size_t)col * P.Natom + atom) * P.K + k];
+        for (int i = 0; i < N * N; ++i)
+            ACopy[i] = A[i];
+        for (int i = 0; i < N; ++i)
+            bCopy[i] = b[i];
+        if (!lu_decompose_dev<MAXN>(N, A, index))
+        {
+            atomicAdd(nSingular, 1);
+            continue;
+        }
+        lu_backsub_dev(N, A, index, b);
+        for (int i = 0; i < N; ++i)
+        {
+            double r = bCopy[i];
+            for (int j = 0; j < N; ++j)
+                r -= ACopy[i * N + j] * b[j];
+            res[i] = r;
+        }
+        lu_backsub_dev(N, A, index, res);
+        for (int i = 0; i < N; ++i)
+            n[nOff + (size_t)i * P.K] = b[i] + res[i];
+    }
+}
+
+// (max, first index) over dJ[Ncol][L] restricted to [laLo, laHi): what the
+// reference's threaded branch returns (:688, :700-703).  Single block.
+__global__ void dj_reduce_kernel(const double* __restrict__ dJ, int Ncol, int L, int laLo, int laHi,
+                                 double* outMax, long long* outIdx)
+{
+    __shared__ double sMax[256];
+    __shared__ long long sIdx[256];
+    double best = -1.0;
+    long long bestIdx = 0;
+    const long long span = laHi - laLo;
+    const long long total = (long long)Ncol * span;
+    for (long long q = threadIdx.x; q < total; q += blockDim.x)
+    {
+        const long long col = q / span;
+        const long long la = laLo + q % span;
+        const double v = dJ[col * L + la];
+        if (best < v)
+        {
+            best = v;
+            bestIdx = col * L + la;
+        }
+    }
+    sMax[threadIdx.x] = best;
+    sIdx[threadIdx.x] = bestIdx;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1)
+    {
+        if (threadIdx.x < s)
+        {
+            const double o = sMax[threadIdx.x + s];
+            const long long oi = sIdx[threadIdx.x + s];
+            if (sMax[threadIdx.x] < o || (sMax[threadIdx.x] == o && oi < sIdx[threadIdx.x]))
+            {
+                sMax[threadIdx.x] = o;
+                sIdx[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        *outMax = sMax[0] < 0.0 ? 0.0 : sMax[0];
+        *outIdx = sIdx[0];
+    }
+}
+
+} // namespace lwb200
