@@ -1,0 +1,104 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED
+reference C++ (oracle/_ref, scalar scheme `mali_full_precond_scalar`, 1 thread,
+g++ -O2 x86-64 without FMA contraction) on the seeded synthetic problems of
+lightweaver_b200.synth.  Run where /root/reference exists:
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+The .npz files are committed; the GPU box (no /root/reference) checks the CUDA
+path and the C oracle against them.  Inputs are regenerated from the seeds at
+test time; `input_digest` guards against generator drift.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from lightweaver_b200 import capi, synth  # noqa: E402
+from oracle import reflib  # noqa: E402
+
+
+def input_digest(p):
+    h = hashlib.sha256()
+    for arr in (p.height, p.temperature, p.wavelength, p.chiBg, p.etaBg, p.scaBg, p.muz, p.wmu):
+        h.update(np.ascontiguousarray(arr).tobytes())
+    for a in p.atoms:
+        h.update(a.nStar.tobytes())
+        if a.C is not None:
+            h.update(a.C.tobytes())
+        for t in a.trans:
+            h.update(t.wavelength.tobytes())
+            if t.phi is not None:
+                h.update(t.phi.tobytes())
+                h.update(t.wphi.tobytes())
+            if t.alpha is not None:
+                h.update(t.alpha.tobytes())
+    return h.hexdigest()
+
+
+CASES = {
+    # name: (builder, kwargs, number of iterations, which J rows to keep (None = all))
+    'tiny_bezier3': (synth.tiny_problem, dict(formal_solver=capi.FS_BEZIER3), 3, None),
+    'tiny_besser': (synth.tiny_problem, dict(formal_solver=capi.FS_BESSER), 3, None),
+    'tiny_linear': (synth.tiny_problem, dict(formal_solver=capi.FS_LINEAR), 3, None),
+    'tiny_k40_2col': (synth.tiny_problem, dict(ncol=2, ndepth=40, perturb=True), 2, None),
+    'tiny_k100': (synth.tiny_problem, dict(ndepth=100, nrays=2), 2, None),
+    'c1_bezier3': (synth.config_c1, dict(), 3, 16),
+}
+
+
+def build_case(name):
+    fn, kw, niter, jstride = CASES[name]
+    return fn(**kw), niter, jstride
+
+
+def run_reference(p, niter):
+    """iterate_ctx_se-style: first iteration pure Lambda, then MALI, stat_eq
+    after each (lightweaver/iterate_ctx.py:157-176).  Returns per-iteration
+    snapshots."""
+    snaps = []
+    ctxs = [reflib.RefContext(p, col=c) for c in range(p.Ncol)]
+    for it in range(niter):
+        p.prefill_gamma()
+        dJ = [c.fs_iter(lambdaIterate=(it == 0)) for c in ctxs]
+        snap = {'dJMax': np.array([d[0] for d in dJ]), 'I': p.I.copy(), 'J': p.J.copy()}
+        for ia, a in enumerate(p.atoms):
+            if not a.detailedStatic:
+                snap[f'Gamma{ia}'] = a.Gamma.copy()
+            for it_, t in enumerate(a.trans):
+                snap[f'Rij{ia}_{it_}'] = t.Rij.copy()
+                snap[f'Rji{ia}_{it_}'] = t.Rji.copy()
+        for c in ctxs:
+            c.stat_eq()
+        for ia, a in enumerate(p.atoms):
+            snap[f'n{ia}'] = a.n.copy()
+        snaps.append(snap)
+    for c in ctxs:
+        c.close()
+    return snaps
+
+
+def main():
+    for name in CASES:
+        p, niter, jstride = build_case(name)
+        digest = input_digest(p)
+        snaps = run_reference(p, niter)
+        out = {'input_digest': np.array(digest), 'niter': np.array(niter),
+               'jstride': np.array(0 if jstride is None else jstride)}
+        for it, s in enumerate(snaps):
+            for k, v in s.items():
+                if k == 'J' and jstride is not None:
+                    v = v[:, ::jstride]
+                out[f'it{it}_{k}'] = v
+        path = os.path.join(HERE, name + '.npz')
+        np.savez_compressed(path, **out)
+        print(name, 'L', p.Nspect, 'K', p.Nspace, 'size %.0f KB' % (os.path.getsize(path) / 1024))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,332 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the
+C-ABI, against (a) the golden vectors produced by the reference's own C++ and
+(b) the C oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): per-iteration I, J, Gamma <= 1e-9
+relative; populations after stat-eq <= 1e-8 per iteration here (they inherit
+the conditioning of the rate matrix), converged populations / spectra <= 1e-6.
+"""
+import numpy as np
+import pytest
+
+from lightweaver_b200 import capi, synth
+from lightweaver_b200.context import Context, ExplodingMatrixError
+from oracle import oraclelib
+from tests.golden.make_golden import CASES, build_case, input_digest
+from tests.test_oracle import check_snapshot, load_golden
+from tests.util import compare_problems, gamma_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+TOL_N = 1e-8
+
+
+def oracle_iter(q, lambdaIterate=False, storeDepth=False, stat_eq=True):
+    q.prefill_gamma()
+    out = []
+    for c in range(q.Ncol):
+        o = oraclelib.OracleContext(q, col=c)
+        out.append(o.fs_iter(lambdaIterate=lambdaIterate, storeDepth=storeDepth))
+        if stat_eq:
+            o.stat_eq()
+    return out
+
+
+def assert_close(p, q, tol=TOL, tol_n=TOL_N):
+    e = compare_problems(p, q)
+    assert e['I'] <= tol and e['J'] <= tol and e['Gamma'] <= tol and e['R'] <= tol, e
+    assert e['n'] <= tol_n, e
+    return e
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_cuda_matches_reference_golden(name):
+    p, niter, jstride = build_case(name)
+    g = load_golden(name)
+    assert input_digest(p) == str(g['input_digest'])
+    ctx = Context(p)
+    for it in range(niter):
+        upd = ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+        assert abs(upd.dJMax - g[f'it{it}_dJMax'].max()) <= 1e-9 * max(upd.dJMax, 1.0)
+        check_snapshot(p, g, it, jstride, TOL)
+        ctx.stat_equil()
+        for ia, a in enumerate(p.atoms):
+            assert rel_err(a.n, g[f'it{it}_n{ia}']) <= TOL_N
+    ctx.close()
+
+
+@pytest.mark.parametrize('solver', [capi.FS_BEZIER3, capi.FS_BESSER, capi.FS_LINEAR])
+def test_cuda_vs_oracle_multicolumn_c1(solver):
+    """Config-3-shaped: perturbed FAL C columns with velocity fields, H + Ca II."""
+    p = synth.config_c1(ncol=3, perturb=True, formal_solver=solver, nl=0.4)
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(3):
+        upd = ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+        ctx.stat_equil()
+        ref = oracle_iter(q, lambdaIterate=(it == 0))
+        assert_close(p, q)
+        dJ = max(r[0] for r in ref)
+        assert abs(upd.dJMax - dJ) <= 1e-9 * max(dJ, 1.0)
+    ctx.close()
+
+
+def test_dj_index_is_argmax_wavelength():
+    p = synth.tiny_problem()
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(3):
+        upd = ctx.formal_sol_gamma_matrices()
+        ctx.stat_equil()
+        (dJ, idx), = oracle_iter(q)
+        assert upd.dJMaxIdx == idx
+    ctx.close()
+
+
+def test_formal_sol_up_only_and_full():
+    p = synth.tiny_problem(ncol=2, perturb=True)
+    q = p.clone()
+    ctx = Context(p)
+    ctx.formal_sol_gamma_matrices()
+    oracle_iter(q, stat_eq=False)
+    for upOnly in (True, False):
+        p.I[:] = -1.0
+        ctx.formal_sol(upOnly=upOnly)
+        for c in range(q.Ncol):
+            oraclelib.OracleContext(q, col=c).formal_sol(upOnly=upOnly)
+        assert rel_err(p.I, q.I) <= TOL
+    ctx.close()
+
+
+def test_depth_data_store():
+    p = synth.tiny_problem(nrays=2)
+    p.alloc_depth_data()
+    q = p.clone()
+    ctx = Context(p)
+    ctx.formal_sol_gamma_matrices(extraParams={'storeDepthData': True})
+    oracle_iter(q, storeDepth=True, stat_eq=False)
+    assert rel_err(p.depthChi, q.depthChi) <= TOL
+    assert rel_err(p.depthEta, q.depthEta) <= TOL
+    assert rel_err(p.depthI, q.depthI) <= TOL
+    ctx.close()
+
+
+@pytest.mark.parametrize('ndepth', [3, 4, 5, 31, 32, 33, 64, 65, 96, 97, 128])
+def test_depth_counts_across_lane_layouts(ndepth):
+    """Every register layout (NCH = 1..4), lane-boundary and end-point cases."""
+    p = synth.tiny_problem(ndepth=ndepth, nrays=2)
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices()
+        ctx.stat_equil()
+        oracle_iter(q)
+        assert_close(p, q)
+    ctx.close()
+
+
+def test_too_many_depths_fails_loudly():
+    p = synth.tiny_problem(ndepth=200, nrays=2, with_profiles=False)
+    with pytest.raises(capi.LwB200Error):
+        Context(p)
+
+
+def test_thermalised_upper_and_zero_lower_boundaries():
+    p = synth.tiny_problem()
+    p.lowerBc, p.upperBc = capi.BC_ZERO, capi.BC_THERMALISED
+    q = p.clone()
+    ctx = Context(p)
+    ctx.formal_sol_gamma_matrices()
+    oracle_iter(q, stat_eq=False)
+    assert_close(p, q)
+    ctx.close()
+
+
+def test_callable_boundaries():
+    p = synth.tiny_problem(nrays=3)
+    rng = np.random.default_rng(5)
+    L, M = p.Nspect, p.Nrays
+    p.lowerBc = p.upperBc = capi.BC_CALLABLE
+    p.lowerBcData = 1e-8 * rng.random((1, L, M))
+    p.upperBcData = 1e-10 * rng.random((1, L, M))
+    idx = np.full((M, 2), -1, dtype=np.int32)
+    idx[:, 1] = np.arange(M)
+    p.lowerBcIdx = idx.copy()
+    idx2 = np.full((M, 2), -1, dtype=np.int32)
+    idx2[:, 0] = np.arange(M)[::-1]
+    p.upperBcIdx = idx2
+    q = p.clone()
+    ctx = Context(p)
+    ctx.formal_sol_gamma_matrices()
+    oracle_iter(q, stat_eq=False)
+    assert_close(p, q)
+    ctx.close()
+
+
+def test_detailed_static_atom_gets_rates_but_no_gamma():
+    p = synth.build_problem([synth.h6_atom(0.3), synth.ca2_atom(0.3)], nrays=2, detailed=('Ca',))
+    assert p.atoms[1].detailedStatic and p.atoms[1].Gamma is None
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices()
+        ctx.stat_equil()
+        oracle_iter(q)
+        assert_close(p, q)
+    ctx.close()
+
+
+def test_angle_averaged_prd_rho_scales_gij():
+    p = synth.tiny_problem()
+    rng = np.random.default_rng(11)
+    t = p.atoms[0].trans[0]
+    t.rhoPrd = np.ascontiguousarray(1.0 + 0.3 * rng.random((1, t.Nlambda, p.Nspace)))
+    q = p.clone()
+    ctx = Context(p)
+    ctx.formal_sol_gamma_matrices()
+    oracle_iter(q, stat_eq=False)
+    assert_close(p, q)
+    ctx.close()
+
+
+def test_lambda_shards_sum_to_full_iteration():
+    """Two wavelength shards with deferred finalise, summed on the host, equal
+    the single-context result (the data path of the NCCL all-reduce)."""
+    import ctypes as C
+    import torch
+    p = synth.tiny_problem()
+    full = p.clone()
+    cf = Context(full)
+    cf.formal_sol_gamma_matrices()
+    L = p.Nspect
+    split = L // 3
+    parts = [p.clone(), p.clone()]
+    ctxs = [Context(parts[0], laRange=(0, split)), Context(parts[1], laRange=(split, L))]
+    bufs = []
+    for c, pp in zip(ctxs, parts):
+        pp.prefill_gamma()
+        c.upload(capi.ITER_INPUTS)
+        c.fs_iter_device(deferFinalise=True, want_dJ=False)
+        ptr, nbytes = c.device_buffer(capi.BUF_ACCUM)
+        host = np.empty(nbytes // 8)
+        torch.cuda.synchronize()
+        from lightweaver_b200.sharding import copy_device_to_host
+        copy_device_to_host(host, ptr, nbytes)
+        bufs.append(host)
+    total = bufs[0] + bufs[1]
+    from lightweaver_b200.sharding import copy_host_to_device
+    ptr, nbytes = ctxs[0].device_buffer(capi.BUF_ACCUM)
+    copy_host_to_device(ptr, total, nbytes)
+    ctxs[0].finalise()
+    ctxs[0].download(capi.GAMMA | capi.RATES)
+    for a, b in zip(parts[0].atoms, full.atoms):
+        assert gamma_err(a.Gamma, b.Gamma) <= 1e-12
+        for t, u in zip(a.trans, b.trans):
+            assert rel_err(t.Rij, u.Rij, floor=1e-30) <= 1e-12
+    # J rows are disjoint per shard
+    ctxs[0].download(capi.JBAR)
+    ctxs[1].download(capi.JBAR)
+    assert rel_err(parts[0].J[:, :split], full.J[:, :split]) <= 1e-14
+    assert rel_err(parts[1].J[:, split:], full.J[:, split:]) <= 1e-14
+    d0, i0 = ctxs[0].dj_max()
+    d1, i1 = ctxs[1].dj_max()
+    df, idf = cf.dj_max()
+    assert max(d0, d1) == df
+    for c in ctxs + [cf]:
+        c.close()
+
+
+def test_singular_matrix_raises():
+    p = synth.tiny_problem()
+    ctx = Context(p)
+    ctx.formal_sol_gamma_matrices()
+    p.atoms[0].Gamma[0, 2, :, 10] = 0.0  # an all-zero row that is not the eliminated one
+    p.atoms[0].Gamma[0, 1, :, 10] = 0.0
+    p.atoms[0].Gamma[0, 3, :, 10] = 0.0
+    with pytest.raises(ExplodingMatrixError):
+        ctx.stat_equil()
+    ctx.close()
+
+
+def test_device_profiles_match_host_voigt():
+    """lwb200_compute_profiles (device Voigt) vs the Faddeeva-based host profiles."""
+    p = synth.config_c1(ncol=2, perturb=True, nl=0.3)
+    q = p.clone()
+    for a in p.atoms:
+        for t in a.trans:
+            if t.phi is not None:
+                t.phi[:] = 0.0
+                t.wphi[:] = 0.0
+    ctx = Context(p)
+    ctx.update_deps(profiles_on_device=True)
+    ctx.download(capi.PROFILE)
+    for a, b in zip(p.atoms, q.atoms):
+        for t, u in zip(a.trans, b.trans):
+            if t.phi is not None:
+                assert rel_err(t.phi, u.phi) <= 1e-12, t.name
+                assert rel_err(t.wphi, u.wphi) <= 1e-12, t.name
+    # and the iteration run on device-made profiles agrees with the oracle on host-made ones
+    ctx.formal_sol_gamma_matrices()
+    oracle_iter(q, stat_eq=False)
+    assert_close(p, q)
+    ctx.close()
+
+
+def test_converged_populations_and_spectrum():
+    """Run the Gamma iteration to convergence on both sides (iterate_ctx_se
+    semantics, lightweaver/iterate_ctx.py:85-88,157-176)."""
+    p = synth.tiny_problem()
+    q = p.clone()
+    ctx = Context(p)
+    o = oraclelib.OracleContext(q)
+    for it in range(200):
+        upd = ctx.formal_sol_gamma_matrices(lambdaIterate=(it < 3))
+        pops = ctx.stat_equil()
+        q.prefill_gamma()
+        o.fs_iter(lambdaIterate=(it < 3))
+        o.stat_eq()
+        if it > 3 and upd.dJMax < 1e-5 and max(pops.dPops) < 1e-5:
+            break
+    assert it < 199, 'did not converge'
+    assert rel_err(p.atoms[0].n, q.atoms[0].n) <= 1e-6
+    assert rel_err(p.I, q.I) <= 1e-6
+    ctx.close()
+
+
+def test_column_stack_properties_at_scale():
+    """Size-independent properties on a larger column stack: identical columns
+    give identical results, Gamma columns sum to zero, populations are conserved,
+    and sampled columns match the oracle."""
+    base = synth.config_c1(ncol=4, perturb=True, nl=0.3)
+    reps = 16
+    big = synth.config_c1(ncol=4 * reps, perturb=False, nl=0.3, with_profiles=False)
+
+    def tile(dst, src):
+        dst[...] = np.tile(src, (reps,) + (1,) * (src.ndim - 1))
+    for name in ('height', 'temperature', 'chiBg', 'etaBg', 'scaBg', 'vlosMu'):
+        tile(getattr(big, name), getattr(base, name))
+    for a, b in zip(big.atoms, base.atoms):
+        for name in ('n', 'nStar', 'nTotal', 'vBroad', 'C'):
+            tile(getattr(a, name), getattr(b, name))
+        for t, u in zip(a.trans, b.trans):
+            if t.phi is not None:
+                tile(t.phi, u.phi)
+                tile(t.wphi, u.wphi)
+    ctx = Context(big)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices()
+        ctx.stat_equil()
+    q = base.clone()
+    for it in range(2):
+        oracle_iter(q)
+    for a, b in zip(big.atoms, q.atoms):
+        n = a.n.reshape(reps, 4, *a.n.shape[1:])
+        assert rel_err(n, np.broadcast_to(b.n, n.shape)) <= TOL_N
+        assert rel_err(n, np.broadcast_to(n[0], n.shape)) <= 1e-11  # replicas agree (atomics reorder sums)
+        G = a.Gamma
+        assert np.abs(G.sum(axis=1)).max() <= 1e-9 * np.abs(G).max()
+        assert rel_err(a.n.sum(axis=1), a.nTotal) <= 1e-12
+    I = big.I.reshape(reps, 4, *big.I.shape[1:])
+    assert rel_err(I, np.broadcast_to(q.I, I.shape)) <= TOL
+    ctx.close()

@@ -1,0 +1,193 @@
+"""CPU tests (no GPU): the C oracle against the golden vectors produced by the
+reference's own C++ (tests/golden/make_golden.py) and, where oracle/_ref exists,
+against the reference live; plus the C-ABI surface."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from lightweaver_b200 import capi, synth
+from oracle import oraclelib, reflib
+from tests.golden.make_golden import CASES, build_case, input_digest
+from tests.util import compare_problems, rel_err
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name + '.npz'))
+
+
+def check_snapshot(p, g, it, jstride, tol, what=('I', 'J', 'Gamma', 'R')):
+    errs = {}
+    if 'I' in what:
+        errs['I'] = rel_err(p.I, g[f'it{it}_I'])
+    if 'J' in what:
+        J = p.J if not jstride else p.J[:, ::jstride]
+        errs['J'] = rel_err(J, g[f'it{it}_J'])
+    for ia, a in enumerate(p.atoms):
+        if 'Gamma' in what and not a.detailedStatic:
+            G, Gr = a.Gamma, g[f'it{it}_Gamma{ia}']
+            d = np.abs(G - Gr).max(axis=(-3, -2)) / np.abs(Gr).max(axis=(-3, -2))
+            errs[f'Gamma{ia}'] = float(d.max())
+        if 'R' in what:
+            for it_, t in enumerate(a.trans):
+                errs[f'R{ia}_{it_}'] = max(rel_err(t.Rij, g[f'it{it}_Rij{ia}_{it_}'], floor=1e-30),
+                                          rel_err(t.Rji, g[f'it{it}_Rji{ia}_{it_}'], floor=1e-30))
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, f'iteration {it}: {bad}'
+    return errs
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_oracle_matches_reference_golden(name):
+    """The plain-C restatement reproduces the reference's outputs (pins the oracle)."""
+    p, niter, jstride = build_case(name)
+    g = load_golden(name)
+    assert input_digest(p) == str(g['input_digest']), 'synthetic input generator drifted; regenerate goldens'
+    for it in range(niter):
+        p.prefill_gamma()
+        for c in range(p.Ncol):
+            o = oraclelib.OracleContext(p, col=c)
+            dJ, _ = o.fs_iter(lambdaIterate=(it == 0))
+            assert abs(dJ - g[f'it{it}_dJMax'][c]) <= 1e-12 * max(dJ, 1.0)
+        check_snapshot(p, g, it, jstride, 1e-12)
+        for c in range(p.Ncol):
+            oraclelib.OracleContext(p, col=c).stat_eq()
+        for ia, a in enumerate(p.atoms):
+            assert rel_err(a.n, g[f'it{it}_n{ia}']) <= 1e-11
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize('solver', [0, 1, 2])
+def test_oracle_solvers_vs_reference_rays(solver):
+    """Solver-level known answers: random rays through the reference's own
+    LwFsFn solvers vs the restatement, both directions, both boundary types."""
+    rng = np.random.default_rng(7 + solver)
+    atm = synth.falc_columns(1)
+    h, T = atm['height'][0], atm['temperature'][0]
+    K = h.shape[0]
+    for trial in range(20):
+        chi = 10.0**(np.linspace(-9, -1, K) + 0.3 * rng.standard_normal(K))
+        S = 1e-8 * (1.0 + np.linspace(0, 3, K) + 0.2 * rng.random(K))
+        mu = rng.uniform(0.05, 1.0)
+        for toObs in (0, 1):
+            for lbc, ubc in ((capi.BC_THERMALISED, capi.BC_ZERO), (capi.BC_ZERO, capi.BC_THERMALISED)):
+                Ir, Pr = reflib.solve_ray(solver, h, T, chi, S, mu, toObs, 500.0, lbc, ubc)
+                Io, Po = oraclelib.solve_ray(solver, h, T, chi, S, mu, toObs, 500.0, lbc, ubc)
+                assert rel_err(Io, Ir) <= 1e-14 and rel_err(Po, Pr) <= 1e-14
+
+
+@pytest.mark.ref
+def test_oracle_lu_vs_reference():
+    rng = np.random.default_rng(3)
+    for N in (2, 3, 6, 11):
+        for trial in range(20):
+            A = rng.standard_normal((N, N)) * 10.0**rng.uniform(-6, 6, (N, 1))
+            b = rng.standard_normal(N)
+            xr = reflib.solve_lin_eq(A, b)
+            xo = oraclelib.solve_lin_eq(A, b)
+            assert np.array_equal(xr, xo)
+    A = np.ones((3, 3))
+    A[1] = 0.0
+    with pytest.raises(RuntimeError):
+        oraclelib.solve_lin_eq(A, np.ones(3))
+    with pytest.raises(RuntimeError):
+        reflib.solve_lin_eq(A, np.ones(3))
+
+
+@pytest.mark.ref
+def test_oracle_vs_reference_live_full_iteration():
+    """Bit-level agreement on a multi-column perturbed problem, incl. depth data."""
+    p = synth.tiny_problem(ncol=2, perturb=True, nrays=2)
+    p.alloc_depth_data()
+    q = p.clone()
+    for it in range(2):
+        p.prefill_gamma()
+        q.prefill_gamma()
+        for c in range(2):
+            r = reflib.RefContext(p, col=c)
+            r.set_depth_fill(True)
+            a = r.fs_iter(lambdaIterate=(it == 0))
+            r.stat_eq()
+            r.close()
+            o = oraclelib.OracleContext(q, col=c)
+            b = o.fs_iter(lambdaIterate=(it == 0), storeDepth=True, serial_idx=True)
+            o.stat_eq()
+            assert a == b
+        e = compare_problems(q, p)
+        assert max(e.values()) <= 1e-14, e
+        assert rel_err(q.depthI, p.depthI) <= 1e-14 and rel_err(q.depthChi, p.depthChi) <= 1e-14
+        assert rel_err(q.depthEta, p.depthEta) <= 1e-14
+
+
+@pytest.mark.ref
+def test_reference_simd_schemes_load_and_agree_away_from_tail():
+    """The reference's SIMD plugins (the timing baseline) load through its own
+    plugin manager; they agree with scalar except at the last Nspace % stride
+    depths -- which is why scalar is the oracle."""
+    schemes = [s for s in reflib.usable_schemes() if s != 'scalar']
+    if not schemes:
+        pytest.skip('no SIMD scheme usable on this CPU')
+    p = synth.tiny_problem()
+    q = p.clone()
+    reflib.RefContext(p).fs_iter()
+    r = reflib.RefContext(q, scheme=schemes[-1])
+    assert schemes[-1] in r.scheme_name
+    r.fs_iter()
+    # the tail mismatch changes chi at the deepest points, which feeds back into J
+    # everywhere along up-going rays: only loose agreement can be expected
+    assert rel_err(q.J, p.J) <= 1e-4
+    assert rel_err(q.J, p.J) > 1e-12, 'SIMD scheme unexpectedly identical to scalar'
+
+
+def test_profiles_match_reference_voigt():
+    """scipy's wofz (used by the synthetic generator) is the Faddeeva package the
+    reference vendors: phi/wphi from the reference's compute_phi agree."""
+    if not reflib.available():
+        pytest.skip('oracle/_ref not built')
+    p = synth.tiny_problem(ncol=1, perturb=True)
+    q = p.clone()
+    for a in q.atoms:
+        for t in a.trans:
+            if t.phi is not None:
+                t.phi[:] = 0.0
+                t.wphi[:] = 0.0
+    r = reflib.RefContext(q)
+    r.compute_profiles()
+    for a, b in zip(p.atoms, q.atoms):
+        for t, u in zip(a.trans, b.trans):
+            if t.phi is not None:
+                assert rel_err(t.phi, u.phi) <= 1e-13
+                assert rel_err(t.wphi, u.wphi) <= 1e-13
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """liblwb200.so loads without a GPU and exports what include/lwb200.h declares."""
+    hdr = open(os.path.join(ROOT, 'include', 'lwb200.h')).read()
+    declared = sorted(set(re.findall(r'\b(lwb200_[a-z_0-9]+)\s*\(', hdr)))
+    assert declared == sorted(capi.EXPORTED_SYMBOLS)
+    lib = capi.load()
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.lwb200_abi_version() == capi.ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors of the POD structs have the C sizes (LP64)."""
+    import ctypes as C
+    assert C.sizeof(capi.LwB200Transition) == 6 * 4 + 5 * 8 + 8 * 8
+    assert C.sizeof(capi.LwB200Atom) == 4 * 4 + 6 * 8
+    assert C.sizeof(capi.LwB200Problem) == 12 * 4 + 19 * 8
+
+
+def test_create_fails_loudly_without_gpu():
+    """No CPU fallback: without a device the product path raises."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from lightweaver_b200.context import Context
+    with pytest.raises(capi.LwB200Error):
+        Context(synth.tiny_problem())
