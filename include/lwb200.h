@@ -58,8 +58,9 @@ typedef struct LwB200Transition {
     double dopplerWidth;   /* c/lambda0 for lines, 1 for continua (LwMiddleLayer.pyx:1799,1815) */
     const double* wavelength; /* [Nlambda = Nred - Nblue] */
     const double* alpha;      /* [Nlambda] continua, else NULL */
-    double* phi;              /* [Ncol][Nlambda][Nrays][2][Nspace] lines, else NULL */
-    double* wphi;             /* [Ncol][Nspace] lines */
+    double* phi;              /* [Ncol][Nlambda][Nrays][2][Nspace] lines, else NULL; may also be NULL for a
+                                 line whose profile is only ever made on the device (lwb200_compute_profiles) */
+    double* wphi;             /* [Ncol][Nspace] lines (NULL together with phi) */
     const double* rhoPrd;     /* [Ncol][Nlambda][Nspace] angle-averaged PRD lines, else NULL */
     const double* aDamp;      /* [Ncol][Nspace] lines; only read by *_compute_profiles */
     double* Rij;              /* [Ncol][Nspace] out */
@@ -139,8 +140,11 @@ enum {
 enum {
     LWB200_LAMBDA_ITERATE = 1u << 0, /* FsMode::PureLambdaIteration */
     LWB200_STORE_DEPTH    = 1u << 1, /* depthData.fill */
-    LWB200_DEFER_FINALISE = 1u << 2  /* leave [Gamma|R] partial sums un-finalised (lambda-sharded
+    LWB200_DEFER_FINALISE = 1u << 2, /* leave [Gamma|R] partial sums un-finalised (lambda-sharded
                                         ranks all-reduce them, then call lwb200_finalise) */
+    LWB200_GENERAL_KERNEL = 1u << 3  /* run every wavelength through the general per-ray accumulation
+                                        kernel (normally only wavelengths with > 2 overlapping lines);
+                                        a cross-check of the moment kernel, not a fast path */
 };
 
 /* Device buffers a caller may need to hand to a collective. */
@@ -211,6 +215,11 @@ int lwb200_formal_sol(LwB200Context* ctx, int upOnly);
  * receives the number of (column, depth) systems with an all-zero row; the
  * call then fails like the reference's throw ("Singular Matrix"). */
 int lwb200_stat_eq(LwB200Context* ctx, int32_t atom, int32_t kStart, int32_t kEnd, int32_t* nSingular);
+
+/* Device time (ms, CUDA events on the context's stream) of the most recent
+ * formal-solution kernel launched by lwb200_fs_iter / lwb200_formal_sol: the
+ * dominant kernel of the path, for the roofline. */
+int lwb200_kernel_time(LwB200Context* ctx, double* ms);
 
 /* Device pointer + byte size of one of the LWB200_BUF_* buffers. */
 int lwb200_device_buffer(LwB200Context* ctx, int32_t which, void** ptr, size_t* nbytes);

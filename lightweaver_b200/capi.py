@@ -24,7 +24,7 @@ ALL_INPUTS = 0x7f
 ITER_INPUTS = POPS | NSTAR | GAMMA
 ITER_OUTPUTS = GAMMA | JBAR | INTENS | RATES
 
-LAMBDA_ITERATE, STORE_DEPTH, DEFER_FINALISE = 1, 2, 4
+LAMBDA_ITERATE, STORE_DEPTH, DEFER_FINALISE, GENERAL_KERNEL = 1, 2, 4, 8
 
 BUF_ACCUM, BUF_J, BUF_I, BUF_POPS, BUF_GAMMA, BUF_DJ = range(6)
 
@@ -121,12 +121,13 @@ def load():
     lib.lwb200_dj_max.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.lwb200_formal_sol.argtypes = [vp, C.c_int]
     lib.lwb200_stat_eq.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    lib.lwb200_kernel_time.argtypes = [vp, C.POINTER(C.c_double)]
     lib.lwb200_device_buffer.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.lwb200_work_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.POINTER(C.c_int64)]
     for name in ('device_count', 'create', 'destroy', 'set_stream', 'set_lambda_range', 'upload',
                  'download', 'sync', 'compute_profiles', 'fs_iter', 'finalise', 'dj_max',
-                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats'):
+                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time'):
         getattr(lib, 'lwb200_' + name).restype = C.c_int
     if lib.lwb200_abi_version() != ABI_VERSION:
         raise LwB200Error('liblwb200.so ABI version mismatch; rebuild')
@@ -145,5 +146,5 @@ EXPORTED_SYMBOLS = [
     'lwb200_destroy', 'lwb200_set_stream', 'lwb200_set_lambda_range', 'lwb200_upload',
     'lwb200_download', 'lwb200_sync', 'lwb200_compute_profiles', 'lwb200_fs_iter',
     'lwb200_finalise', 'lwb200_dj_max', 'lwb200_formal_sol', 'lwb200_stat_eq',
-    'lwb200_device_buffer', 'lwb200_work_stats',
+    'lwb200_device_buffer', 'lwb200_work_stats', 'lwb200_kernel_time',
 ]

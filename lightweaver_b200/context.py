@@ -104,12 +104,19 @@ class Context:
         capi.check(self.lib.lwb200_work_stats(self._h, C.byref(pts), C.byref(byts), C.byref(launches)))
         return pts.value, byts.value, launches.value
 
+    def kernel_time_ms(self):
+        """Device time of the most recent formal-solution kernel (CUDA events)."""
+        ms = C.c_double()
+        capi.check(self.lib.lwb200_kernel_time(self._h, C.byref(ms)))
+        return ms.value
+
     # ------------------------------------------------- device-resident calls
     def fs_iter_device(self, lambdaIterate=False, storeDepth=False, deferFinalise=False,
-                       want_dJ=True):
+                       want_dJ=True, generalKernel=False):
         """One Gamma iteration on device-resident data (no host copies)."""
         flags = ((capi.LAMBDA_ITERATE if lambdaIterate else 0) | (capi.STORE_DEPTH if storeDepth else 0)
-                 | (capi.DEFER_FINALISE if deferFinalise else 0))
+                 | (capi.DEFER_FINALISE if deferFinalise else 0)
+                 | (capi.GENERAL_KERNEL if generalKernel else 0))
         if want_dJ:
             dJ, idx = C.c_double(), C.c_int64()
             capi.check(self.lib.lwb200_fs_iter(self._h, flags, C.byref(dJ), C.byref(idx)))
@@ -146,11 +153,13 @@ class Context:
         reference's Python layer), so fixCollisionalRates is always honoured as
         True."""
         storeDepth = bool(extraParams and extraParams.get('storeDepthData', False))
+        general = bool(extraParams and extraParams.get('generalKernel', False))
         if crsw is not None:
             self.crsw = crsw
         self.problem.prefill_gamma(self.crsw)
         self.upload(capi.ITER_INPUTS)
-        dJ, idx = self.fs_iter_device(lambdaIterate=lambdaIterate, storeDepth=storeDepth)
+        dJ, idx = self.fs_iter_device(lambdaIterate=lambdaIterate, storeDepth=storeDepth,
+                                      generalKernel=general)
         self.download(capi.ITER_OUTPUTS | (capi.DEPTH if storeDepth else 0))
         return IterationUpdate(updatedJ=True, dJMax=dJ, dJMaxIdx=idx % self.problem.Nspect,
                                crsw=self.crsw)

@@ -4,6 +4,7 @@
 #include "../../include/lwb200.h"
 #include "lwb200_kernels.cuh"
 #include "lwb200_profiles.cuh"
+#include "lwb200_fsm.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -79,8 +80,39 @@ struct DevBuf
 };
 } // namespace
 
+struct Pinned
+{
+    double* p = nullptr;
+    size_t n = 0;
+    cudaEvent_t ev = nullptr;
+    bool inFlight = false;
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        if (ev)
+            cudaEventDestroy(ev);
+        p = nullptr;
+        ev = nullptr;
+        n = 0;
+    }
+};
+
+struct Pending
+{
+    void* dst;
+    const void* src;
+    size_t bytes;
+};
+
 struct LwB200Context
 {
+    Pinned stN, stNStar, stNTotal, stVBroad, stPrefill, stGamma, stNOut, stGammaOut, stRates;
+    std::vector<Pending> pending;
+    std::vector<void*> registered;
+    cudaEvent_t evK0 = nullptr, evK1 = nullptr;
+    bool kernelTimed = false;
+    bool forceDirect = false;
     int device = 0;
     cudaStream_t stream = nullptr;
     LwB200Problem prob{};
@@ -89,7 +121,9 @@ struct LwB200Context
     std::vector<HostTrans> trans; // flattened, global order
     std::vector<DevTrans> devTrans;
     std::vector<int> atomNlevel, atomLevOff, atomGammaOff, atomDetailed;
-    std::vector<int> tileLa, tileSlotOff, tileSlotTrans;
+    std::vector<int> tileLa, tileSlotOff, tileSlotTrans, tileKind;
+    DevBuf<int> dListMoments, dListDirect, dListAll;
+    int nListMoments = 0, nListDirect = 0, nListAll = 0, listLo = -1, listHi = -1;
     int Ntile = 0;
     int nwarps = 4;
     int laLo = 0, laHi = 0;
@@ -177,8 +211,6 @@ int build_plan(LwB200Context* c)
         d.rhoOff = -1;
         if (t.type == LWB200_LINE)
         {
-            if (!t.phi || !t.wphi)
-                return fail("line without phi / wphi buffers");
             d.lineIdx = nline++;
             d.phiOff = phiOff;
             d.phiColStride = (long long)Nl * M * 2 * K;
@@ -203,15 +235,20 @@ int build_plan(LwB200Context* c)
     }
 
     // per-wavelength active lists in the reference's (atom, kr) order
-    std::vector<int> laOff(L + 1, 0), laHasLine(L, 0);
+    std::vector<int> laOff(L + 1, 0), laHasLine(L, 0), laNLines(L, 0);
     std::vector<std::vector<int>> active(L);
     for (int g = 0; g < NT; ++g)
         for (int la = c->devTrans[g].Nblue; la < c->devTrans[g].Nred; ++la)
         {
             active[la].push_back(g);
             if (c->devTrans[g].type == 0)
+            {
                 laHasLine[la] = 1;
+                laNLines[la] += 1;
+            }
         }
+    // wavelengths with more than two overlapping lines go to the general kernel
+    auto kind_of = [&](int la) { return laNLines[la] > 2 ? 1 : 0; };
 
     // tiles: runs of wavelengths whose union of active transitions fits the
     // shared-memory accumulator; sized so that the grid fills the GPU
@@ -238,7 +275,7 @@ int build_plan(LwB200Context* c)
     {
         std::vector<int> slots; // transitions of this tile
         int start = la;
-        while (la < L && la - start < tileLen)
+        while (la < L && la - start < tileLen && kind_of(la) == kind_of(start))
         {
             std::vector<int> add;
             for (int g : active[la])
@@ -263,6 +300,7 @@ int build_plan(LwB200Context* c)
             }
         }
         c->tileLa.push_back(la);
+        c->tileKind.push_back(kind_of(start));
         for (int g : slots)
             c->tileSlotTrans.push_back(g);
         c->tileSlotOff.push_back((int)c->tileSlotTrans.size());
@@ -405,32 +443,102 @@ int build_plan(LwB200Context* c)
     return 0;
 }
 
-template <int NCH, int SOLVER, int MODE>
-int launch_fs_t(LwB200Context* c, int tile0, int ntile, int lambdaIterate, int upOnly, int storeDepth)
+int refresh_tile_lists(LwB200Context* c)
 {
-    auto kern = fs_kernel<NCH, SOLVER, MODE>;
+    if (c->listLo == c->laLo && c->listHi == c->laHi)
+        return 0;
+    std::vector<int> mom, dir, all;
+    for (int t = 0; t < c->Ntile; ++t)
+    {
+        if (c->tileLa[t + 1] <= c->laLo || c->tileLa[t] >= c->laHi)
+            continue;
+        all.push_back(t);
+        (c->tileKind[t] == 0 ? mom : dir).push_back(t);
+    }
+    c->dListMoments.release();
+    c->dListDirect.release();
+    c->dListAll.release();
+    if (c->dListMoments.upload(mom) || c->dListDirect.upload(dir) || c->dListAll.upload(all))
+        return 1;
+    c->nListMoments = (int)mom.size();
+    c->nListDirect = (int)dir.size();
+    c->nListAll = (int)all.size();
+    c->listLo = c->laLo;
+    c->listHi = c->laHi;
+    return 0;
+}
+
+template <typename Kern>
+int set_smem_attr(Kern kern, int device)
+{
     static bool attrSet[16] = {false};
-    if (!attrSet[c->device & 15])
+    if (!attrSet[device & 15])
     {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attrSet[c->device & 15] = true;
+        attrSet[device & 15] = true;
     }
-    dim3 grid(ntile, c->prob.Ncol);
-    kern<<<grid, c->nwarps * 32, c->smemBytes, c->stream>>>(c->P, tile0, c->laLo, c->laHi, lambdaIterate,
-                                                            upOnly, storeDepth);
-    CU(cudaGetLastError());
-    c->lastLaunches += 1;
+    return 0;
+}
+
+template <int NCH, int SOLVER, int MODE>
+int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
+{
+    if (!c->evK0)
+    {
+        CU(cudaEventCreate(&c->evK0));
+        CU(cudaEventCreate(&c->evK1));
+    }
+    CU(cudaEventRecord(c->evK0, c->stream));
+    const int threads = c->nwarps * 32;
+    if (MODE == MODE_ITER && !c->forceDirect)
+    {
+        if (c->nListMoments > 0)
+        {
+            auto kern = fsm_kernel<NCH, SOLVER>;
+            if (set_smem_attr(kern, c->device))
+                return 1;
+            dim3 grid(c->nListMoments, c->prob.Ncol);
+            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListMoments.p, c->laLo, c->laHi,
+                                                             lambdaIterate, storeDepth);
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
+        }
+        if (c->nListDirect > 0)
+        {
+            auto kern = fs_kernel<NCH, SOLVER, MODE_ITER>;
+            if (set_smem_attr(kern, c->device))
+                return 1;
+            dim3 grid(c->nListDirect, c->prob.Ncol);
+            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListDirect.p, c->laLo, c->laHi,
+                                                             lambdaIterate, 0, storeDepth);
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
+        }
+    }
+    else if (c->nListAll > 0)
+    {
+        auto kern = fs_kernel<NCH, SOLVER, MODE>;
+        if (set_smem_attr(kern, c->device))
+            return 1;
+        dim3 grid(c->nListAll, c->prob.Ncol);
+        kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListAll.p, c->laLo, c->laHi, lambdaIterate,
+                                                         upOnly, storeDepth);
+        CU(cudaGetLastError());
+        c->lastLaunches += 1;
+    }
+    CU(cudaEventRecord(c->evK1, c->stream));
+    c->kernelTimed = true;
     return 0;
 }
 
 template <int NCH, int MODE>
-int launch_fs_s(LwB200Context* c, int tile0, int ntile, int li, int uo, int sd)
+int launch_fs_s(LwB200Context* c, int li, int uo, int sd)
 {
     switch (c->prob.formalSolver)
     {
-    case LWB200_FS_LINEAR: return launch_fs_t<NCH, 0, MODE>(c, tile0, ntile, li, uo, sd);
-    case LWB200_FS_BESSER: return launch_fs_t<NCH, 1, MODE>(c, tile0, ntile, li, uo, sd);
-    case LWB200_FS_BEZIER3: return launch_fs_t<NCH, 2, MODE>(c, tile0, ntile, li, uo, sd);
+    case LWB200_FS_LINEAR: return launch_fs_t<NCH, 0, MODE>(c, li, uo, sd);
+    case LWB200_FS_BESSER: return launch_fs_t<NCH, 1, MODE>(c, li, uo, sd);
+    case LWB200_FS_BEZIER3: return launch_fs_t<NCH, 2, MODE>(c, li, uo, sd);
     }
     return fail("unknown formal solver");
 }
@@ -438,20 +546,14 @@ int launch_fs_s(LwB200Context* c, int tile0, int ntile, int li, int uo, int sd)
 template <int MODE>
 int launch_fs(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
 {
-    // tiles overlapping [laLo, laHi)
-    int t0 = 0, t1 = c->Ntile;
-    while (t0 < c->Ntile && c->tileLa[t0 + 1] <= c->laLo)
-        ++t0;
-    while (t1 > t0 && c->tileLa[t1 - 1] >= c->laHi)
-        --t1;
-    if (t1 <= t0)
-        return 0;
+    if (refresh_tile_lists(c))
+        return 1;
     switch (c->NCH)
     {
-    case 1: return launch_fs_s<1, MODE>(c, t0, t1 - t0, lambdaIterate, upOnly, storeDepth);
-    case 2: return launch_fs_s<2, MODE>(c, t0, t1 - t0, lambdaIterate, upOnly, storeDepth);
-    case 3: return launch_fs_s<3, MODE>(c, t0, t1 - t0, lambdaIterate, upOnly, storeDepth);
-    case 4: return launch_fs_s<4, MODE>(c, t0, t1 - t0, lambdaIterate, upOnly, storeDepth);
+    case 1: return launch_fs_s<1, MODE>(c, lambdaIterate, upOnly, storeDepth);
+    case 2: return launch_fs_s<2, MODE>(c, lambdaIterate, upOnly, storeDepth);
+    case 3: return launch_fs_s<3, MODE>(c, lambdaIterate, upOnly, storeDepth);
+    case 4: return launch_fs_s<4, MODE>(c, lambdaIterate, upOnly, storeDepth);
     }
     return fail("Nspace > 128 is not supported yet by the register-resident depth layout");
 }
@@ -531,6 +633,17 @@ int lwb200_create(const LwB200Problem* problem, int device, LwB200Context** out)
         lwb200_destroy(c);
         return 1;
     }
+    // pin the two large per-iteration outputs in place (J, I) so that their
+    // device->host copies are true async DMA; failure to pin is not an error
+    {
+        const size_t nJ = (size_t)problem->Ncol * problem->Nspect * problem->Nspace * sizeof(double);
+        const size_t nI = (size_t)problem->Ncol * problem->Nspect * problem->Nrays * sizeof(double);
+        if (nJ >= (1u << 20) && cudaHostRegister(problem->J, nJ, cudaHostRegisterDefault) == cudaSuccess)
+            c->registered.push_back(problem->J);
+        if (nI >= (1u << 20) && cudaHostRegister(problem->I, nI, cudaHostRegisterDefault) == cudaSuccess)
+            c->registered.push_back(problem->I);
+        cudaGetLastError();
+    }
     *out = c;
     return 0;
 }
@@ -553,6 +666,19 @@ int lwb200_destroy(LwB200Context* c)
                            &c->dAtomGammaOff, &c->dAtomDetailed, &c->dSingular};
     for (auto* b : ints)
         b->release();
+    for (void* r : c->registered)
+        cudaHostUnregister(r);
+    Pinned* pins[] = {&c->stN, &c->stNStar, &c->stNTotal, &c->stVBroad, &c->stPrefill, &c->stGamma,
+                      &c->stNOut, &c->stGammaOut, &c->stRates};
+    for (auto* q : pins)
+        q->release();
+    if (c->evK0)
+        cudaEventDestroy(c->evK0);
+    if (c->evK1)
+        cudaEventDestroy(c->evK1);
+    c->dListMoments.release();
+    c->dListDirect.release();
+    c->dListAll.release();
     c->djIdx.release();
     c->dTrans.release();
     c->dEntries.release();
@@ -580,9 +706,65 @@ int lwb200_sync(LwB200Context* c)
 {
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    for (const Pending& q : c->pending)
+        std::memcpy(q.dst, q.src, q.bytes);
+    c->pending.clear();
     return 0;
 }
 
+} // extern "C"
+
+// Per-iteration arrays (populations, Gamma, rates) are many small per-atom /
+// per-transition host buffers.  They cross PCIe as ONE packed copy per group
+// through pinned staging buffers that mirror the packed device layouts; the
+// host-side scatter of downloads runs in lwb200_sync once the stream is done.
+static int stage_ready(Pinned& st, size_t count)
+{
+    if (st.n < count)
+    {
+        if (st.p)
+            cudaFreeHost(st.p);
+        st.p = nullptr;
+        cudaError_t e = cudaMallocHost((void**)&st.p, count * sizeof(double));
+        if (e != cudaSuccess)
+            return fail(std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+        st.n = count;
+    }
+    if (!st.ev)
+        CU(cudaEventCreateWithFlags(&st.ev, cudaEventDisableTiming));
+    if (st.inFlight)
+    {
+        CU(cudaEventSynchronize(st.ev));
+        st.inFlight = false;
+    }
+    return 0;
+}
+
+template <typename RowsFn, typename OffFn, typename PtrFn>
+static int upload_packed(LwB200Context* c, Pinned& st, double* dev, int totalRows, RowsFn rows, OffFn off,
+                         PtrFn ptr)
+{
+    const size_t K = c->prob.Nspace, ncol = c->prob.Ncol;
+    const size_t total = ncol * (size_t)totalRows * K;
+    if (stage_ready(st, total))
+        return 1;
+    for (int a = 0; a < c->prob.Natom; ++a)
+    {
+        const double* src = ptr(a);
+        const size_t r = rows(a);
+        if (!src || r == 0)
+            continue;
+        for (size_t col = 0; col < ncol; ++col)
+            std::memcpy(st.p + (col * totalRows + off(a)) * K, src + col * r * K, r * K * sizeof(double));
+    }
+    CU(cudaMemcpyAsync(dev, st.p, total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(st.ev, c->stream));
+    st.inFlight = true;
+    return 0;
+}
+
+extern "C"
+{
 int lwb200_upload(LwB200Context* c, uint32_t mask)
 {
     CU(cudaSetDevice(c->device));
@@ -611,35 +793,29 @@ int lwb200_upload(LwB200Context* c, uint32_t mask)
     }
     if (mask & LWB200_JBAR)
         CU(cudaMemcpyAsync(c->J.p, p.J, ncol * L * K * D, H2D, s));
-    for (int a = 0; a < p.Natom; ++a)
-    {
-        const LwB200Atom& at = c->atoms[a];
-        const size_t N = at.Nlevel;
-        const size_t rowN = (size_t)c->P.NlevTot * K * D;
-        if (mask & LWB200_POPS)
-            if (copy2d(c->n.p + (size_t)c->atomLevOff[a] * K, rowN, at.n, N * K * D, N * K * D, ncol, H2D, s))
-                return 1;
-        if (mask & LWB200_NSTAR)
-        {
-            if (copy2d(c->nStar.p + (size_t)c->atomLevOff[a] * K, rowN, at.nStar, N * K * D, N * K * D, ncol, H2D, s))
-                return 1;
-            if (copy2d(c->nTotal.p + (size_t)a * K, (size_t)p.Natom * K * D, at.nTotal, K * D, K * D, ncol, H2D, s))
-                return 1;
-            if (at.vBroad
-                && copy2d(c->vBroad.p + (size_t)a * K, (size_t)p.Natom * K * D, at.vBroad, K * D, K * D, ncol, H2D, s))
-                return 1;
-        }
-        if ((mask & LWB200_GAMMA) && !at.detailedStatic)
-        {
-            if (!at.Gamma)
-                return fail("active atom without Gamma buffer");
-            if (copy2d(c->prefill.p + (size_t)c->atomGammaOff[a] * K, (size_t)c->P.GammaTot * K * D, at.Gamma,
-                       N * N * K * D, N * N * K * D, ncol, H2D, s))
-                return 1;
-        }
-    }
+    auto levRows = [&](int a) { return (size_t)c->atoms[a].Nlevel; };
+    auto levOff = [&](int a) { return (size_t)c->atomLevOff[a]; };
+    auto one = [&](int) { return (size_t)1; };
+    auto atomIdx = [&](int a) { return (size_t)a; };
+    auto gamRows = [&](int a) {
+        return c->atoms[a].detailedStatic ? (size_t)0 : (size_t)c->atoms[a].Nlevel * c->atoms[a].Nlevel;
+    };
+    auto gamOff = [&](int a) { return (size_t)c->atomGammaOff[a]; };
+    if (mask & LWB200_POPS)
+        if (upload_packed(c, c->stN, c->n.p, c->P.NlevTot, levRows, levOff,
+                          [&](int a) { return (const double*)c->atoms[a].n; }))
+            return 1;
     if (mask & LWB200_NSTAR)
     {
+        if (upload_packed(c, c->stNStar, c->nStar.p, c->P.NlevTot, levRows, levOff,
+                          [&](int a) { return c->atoms[a].nStar; }))
+            return 1;
+        if (upload_packed(c, c->stNTotal, c->nTotal.p, p.Natom, one, atomIdx,
+                          [&](int a) { return c->atoms[a].nTotal; }))
+            return 1;
+        if (upload_packed(c, c->stVBroad, c->vBroad.p, p.Natom, one, atomIdx,
+                          [&](int a) { return c->atoms[a].vBroad; }))
+            return 1;
         if (c->P.Ncont > 0)
         {
             const size_t total = (size_t)c->P.Ncont * ncol * K;
@@ -649,18 +825,20 @@ int lwb200_upload(LwB200Context* c, uint32_t mask)
         }
         c->nstarUploaded = true;
     }
-    if (mask & LWB200_GAMMA_FINAL)
+    if ((mask & LWB200_GAMMA) && c->P.GammaTot > 0)
     {
         for (int a = 0; a < p.Natom; ++a)
-        {
-            const LwB200Atom& at = c->atoms[a];
-            const size_t N = at.Nlevel;
-            if (at.detailedStatic)
-                continue;
-            if (copy2d(c->gamma.p + (size_t)c->atomGammaOff[a] * K, (size_t)c->P.GammaTot * K * D, at.Gamma,
-                       N * N * K * D, N * N * K * D, ncol, H2D, s))
-                return 1;
-        }
+            if (!c->atoms[a].detailedStatic && !c->atoms[a].Gamma)
+                return fail("active atom without Gamma buffer");
+        if (upload_packed(c, c->stPrefill, c->prefill.p, c->P.GammaTot, gamRows, gamOff,
+                          [&](int a) { return (const double*)c->atoms[a].Gamma; }))
+            return 1;
+    }
+    if ((mask & LWB200_GAMMA_FINAL) && c->P.GammaTot > 0)
+    {
+        if (upload_packed(c, c->stGamma, c->gamma.p, c->P.GammaTot, gamRows, gamOff,
+                          [&](int a) { return (const double*)c->atoms[a].Gamma; }))
+            return 1;
     }
     if ((mask & LWB200_ADAMP) && !(mask & LWB200_PROFILE))
     {
@@ -683,6 +861,8 @@ int lwb200_upload(LwB200Context* c, uint32_t mask)
             const LwB200Transition& t = c->trans[g].t;
             if (d.type != 0)
                 continue;
+            if (!t.phi || !t.wphi)
+                return fail("LWB200_PROFILE upload of a line without host phi/wphi (use lwb200_compute_profiles)");
             const size_t Nl = d.Nred - d.Nblue;
             CU(cudaMemcpyAsync(c->phi.p + d.phiOff, t.phi, ncol * Nl * M * 2 * K * D, H2D, s));
             CU(cudaMemcpyAsync(c->wphi.p + (size_t)d.lineIdx * ncol * K, t.wphi, ncol * K * D, H2D, s));
@@ -707,30 +887,53 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
         CU(cudaMemcpyAsync(p.J, c->J.p, ncol * L * K * D, D2H, s));
     if (mask & LWB200_INTENS)
         CU(cudaMemcpyAsync(p.I, c->I.p, ncol * L * M * D, D2H, s));
-    for (int a = 0; a < p.Natom; ++a)
+    if (mask & LWB200_POPS)
     {
-        const LwB200Atom& at = c->atoms[a];
-        const size_t N = at.Nlevel;
-        if (mask & LWB200_POPS)
-            if (copy2d(at.n, N * K * D, c->n.p + (size_t)c->atomLevOff[a] * K, (size_t)c->P.NlevTot * K * D,
-                       N * K * D, ncol, D2H, s))
-                return 1;
-        if ((mask & LWB200_GAMMA) && !at.detailedStatic)
-            if (copy2d(at.Gamma, N * N * K * D, c->gamma.p + (size_t)c->atomGammaOff[a] * K,
-                       (size_t)c->P.GammaTot * K * D, N * N * K * D, ncol, D2H, s))
-                return 1;
+        const size_t rows = c->P.NlevTot;
+        if (stage_ready(c->stNOut, ncol * rows * K))
+            return 1;
+        CU(cudaMemcpyAsync(c->stNOut.p, c->n.p, ncol * rows * K * D, D2H, s));
+        for (int a = 0; a < p.Natom; ++a)
+        {
+            const size_t N = c->atoms[a].Nlevel;
+            for (size_t col = 0; col < ncol; ++col)
+                c->pending.push_back({c->atoms[a].n + col * N * K,
+                                      c->stNOut.p + (col * rows + c->atomLevOff[a]) * K, N * K * D});
+        }
+    }
+    if ((mask & LWB200_GAMMA) && c->P.GammaTot > 0)
+    {
+        const size_t rows = c->P.GammaTot;
+        if (stage_ready(c->stGammaOut, ncol * rows * K))
+            return 1;
+        CU(cudaMemcpyAsync(c->stGammaOut.p, c->gamma.p, ncol * rows * K * D, D2H, s));
+        for (int a = 0; a < p.Natom; ++a)
+        {
+            if (c->atoms[a].detailedStatic)
+                continue;
+            const size_t N2 = (size_t)c->atoms[a].Nlevel * c->atoms[a].Nlevel;
+            for (size_t col = 0; col < ncol; ++col)
+                c->pending.push_back({c->atoms[a].Gamma + col * N2 * K,
+                                      c->stGammaOut.p + (col * rows + c->atomGammaOff[a]) * K, N2 * K * D});
+        }
     }
     if (mask & LWB200_RATES)
     {
-        const size_t pitch = (size_t)c->P.AccTot * K * D;
+        // the R rows are the tail of each column's accumulator block
+        const size_t rows = 2 * c->trans.size();
+        if (stage_ready(c->stRates, ncol * rows * K))
+            return 1;
+        if (copy2d(c->stRates.p, rows * K * D, c->accum.p + (size_t)c->P.GammaTot * K, (size_t)c->P.AccTot * K * D,
+                   rows * K * D, ncol, D2H, s))
+            return 1;
         for (size_t g = 0; g < c->trans.size(); ++g)
         {
-            const DevTrans& d = c->devTrans[g];
             const LwB200Transition& t = c->trans[g].t;
-            if (copy2d(t.Rij, K * D, c->accum.p + (size_t)d.accRij * K, pitch, K * D, ncol, D2H, s))
-                return 1;
-            if (copy2d(t.Rji, K * D, c->accum.p + (size_t)d.accRji * K, pitch, K * D, ncol, D2H, s))
-                return 1;
+            for (size_t col = 0; col < ncol; ++col)
+            {
+                c->pending.push_back({t.Rij + col * K, c->stRates.p + (col * rows + 2 * g) * K, K * D});
+                c->pending.push_back({t.Rji + col * K, c->stRates.p + (col * rows + 2 * g + 1) * K, K * D});
+            }
         }
     }
     if ((mask & LWB200_DEPTH) && c->depthChi.p)
@@ -746,7 +949,7 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
         {
             const DevTrans& d = c->devTrans[g];
             const LwB200Transition& t = c->trans[g].t;
-            if (d.type != 0)
+            if (d.type != 0 || !t.phi)
                 continue;
             const size_t Nl = d.Nred - d.Nblue;
             CU(cudaMemcpyAsync(t.phi, c->phi.p + d.phiOff, ncol * Nl * M * 2 * K * D, D2H, s));
@@ -810,6 +1013,7 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
     if (!c->nstarUploaded)
         return fail("lwb200_fs_iter: inputs have not been uploaded (lwb200_upload)");
     const int storeDepth = (flags & LWB200_STORE_DEPTH) ? 1 : 0;
+    c->forceDirect = (flags & LWB200_GENERAL_KERNEL) != 0;
     if (storeDepth && !c->depthChi.p)
         return fail("lwb200_fs_iter: STORE_DEPTH without depth arrays in the problem");
     c->lastLaunches = 0;
@@ -876,6 +1080,19 @@ int lwb200_stat_eq(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd,
         *nSingular = ns;
     if (ns > 0)
         return fail("Singular Matrix");
+    return 0;
+}
+
+int lwb200_kernel_time(LwB200Context* c, double* ms)
+{
+    CU(cudaSetDevice(c->device));
+    if (!c->kernelTimed)
+        return fail("lwb200_kernel_time: no formal-solution kernel has been launched yet");
+    CU(cudaEventSynchronize(c->evK1));
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, c->evK0, c->evK1));
+    if (ms)
+        *ms = t;
     return 0;
 }
 

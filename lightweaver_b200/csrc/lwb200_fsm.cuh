@@ -1,0 +1,834 @@
+// lwb200_fsm.cuh -- the production Gamma-iteration kernel ("moments" form).
+//
+// Same ownership as fs_kernel (one warp = one wavelength of one column, lanes
+// over depth), but the Gamma / rate accumulation of
+// compute_full_operator_rates (SimdFullIterationTemplates.hpp:206-234) is
+// re-associated.  Every quantity that the reference sums over the rays of one
+// wavelength is a polynomial in (I_r, Psi*_r, phi_r) with ray-independent
+// coefficients:
+//
+//   Vij = v p,  Vji = g v p,  Uji = u g v p          (p = phi for a line, 1 for a continuum)
+//   chi_atom(m) = sum_q p_q X_q(m),  U_atom(m) = sum_q p_q U_q(m),  eta_atom = sum_q p_q E_q
+//
+// so per ray only the MOMENTS  sum_r w_r {I, Psi*, p, p I, p Psi*, p p' Psi*}
+// are accumulated (in registers, private to the lane that owns depth k), and
+// the per-transition work (Gamma(i,j), Gamma(j,i), Rij, Rji) runs once per
+// wavelength instead of once per ray.  Up to two lines may overlap at a
+// wavelength in this kernel (the planner routes the rare wavelengths with
+// three or more overlapping lines to the general fs_kernel).
+//
+// The formal solver is the same arithmetic as lwb200_device.cuh, restructured
+// for instruction-cache footprint and fp64-pipe cost: one code copy for both
+// ray directions, divisions by ray-independent geometry replaced by
+// precomputed reciprocals, the remaining ones by a Newton reciprocal, and a
+// branch-light exp.  Differences from the reference are at rounding level.
+#pragma once
+#include "lwb200_kernels.cuh"
+
+namespace lwb200
+{
+// 1/x to ~1 ulp: hardware seed + two Newton steps (no IEEE corner cases needed:
+// every argument here is a finite positive opacity, path length or optical depth)
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// exp(x) for |x| < 700, ~1 ulp: Cody-Waite reduction, degree-13 Taylor on |r| <= ln2/2
+__device__ __forceinline__ double exp_fast(double x)
+{
+    const double magic = 6755399441055744.0; // 1.5 * 2^52
+    double t = fma(x, 1.4426950408889634074, magic);
+    const int n = __double2loint(t);
+    t -= magic;
+    double r = fma(t, -6.93147180369123816490e-01, x);
+    r = fma(t, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;           // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);         // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);        // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);        // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);       // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);         // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);        // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);        // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);        // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);       // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);       // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+template <int NCH>
+struct GeometryR
+{
+    int K;
+    double dsf[NCH];   // |h_k - h_{k+1}|
+    double dsfP[NCH];  // |h_{k-1} - h_k|
+    double rdsf[NCH];  // 1 / dsf
+    double rsum[NCH];  // 1 / (dsf + dsfP)
+};
+
+template <int NCH>
+__device__ __forceinline__ void load_geometry_r(GeometryR<NCH>& g, const double* __restrict__ height, int K)
+{
+    const int lane = lane_id();
+    g.K = K;
+    double h[NCH], hN[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+    {
+        const int k = lane * NCH + j;
+        h[j] = (k < K) ? __ldg(height + k) : 0.0;
+    }
+    shift_next<NCH>(h, hN);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+    {
+        const int k = lane * NCH + j;
+        g.dsf[j] = (k + 1 < K) ? fabs(h[j] - hN[j]) : 1.0;
+    }
+    shift_prev<NCH>(g.dsf, g.dsfP);
+    if (lane == 0)
+        g.dsfP[0] = 1.0;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+    {
+        g.rdsf[j] = 1.0 / g.dsf[j];
+        g.rsum[j] = 1.0 / (g.dsf[j] + g.dsfP[j]);
+    }
+}
+
+__device__ __forceinline__ double steffen_r(double wUw, double wDw, double Suw, double S0)
+{
+    // wUw = dsdw/(dsdw+dsuw) multiplies Suw, wDw = dsuw/(dsdw+dsuw) multiplies S0 (Bezier.hpp:58-65)
+    const double P0 = fabs(Suw * wUw + S0 * wDw);
+    return (copysign(1.0, S0) + copysign(1.0, Suw)) * fmin(fabs(Suw), fmin(fabs(S0), 0.5 * P0));
+}
+
+// One ray of piecewise_bezier3_1d / piecewise_besser_1d / piecewise_linear_1d,
+// both directions through one code path.  Outputs I and psi = Psi*/chi.
+template <int NCH, int SOLVER>
+__device__ __forceinline__ void solve_ray_r(const GeometryR<NCH>& g, const double (&chi)[NCH],
+                                            const double (&S)[NCH], const double (&rchi)[NCH],
+                                            double muz, bool down, int bcType, double bcB0,
+                                            double bcB1, double bcValue, double (&I)[NCH],
+                                            double (&psi)[NCH])
+{
+    const int lane = lane_id();
+    const int K = g.K;
+    const int ks = down ? 0 : K - 1;
+    const int ke = down ? K - 1 : 0;
+    double a[NCH], b[NCH];
+    double chiN[NCH], chiP[NCH], SN[NCH], SP[NCH];
+    shift_next<NCH>(chi, chiN);
+    shift_prev<NCH>(chi, chiP);
+    shift_next<NCH>(S, SN);
+    shift_prev<NCH>(S, SP);
+
+    if (SOLVER == 2)
+    {
+        const double zmu = 1.0 / muz;
+        // chi slopes on forward intervals and Steffen derivatives (geometry reciprocals are static)
+        double sl[NCH], slP[NCH], Df[NCH], DfN[NCH];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+            sl[j] = (chiN[j] - chi[j]) * (g.rdsf[j] * muz);
+        shift_prev<NCH>(sl, slP);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            const int k = lane * NCH + j;
+            double d = steffen_r(g.dsf[j] * g.rsum[j], g.dsfP[j] * g.rsum[j], slP[j], sl[j]);
+            d = (k == 0) ? sl[j] : d;
+            d = (k == K - 1) ? slP[j] : d;
+            Df[j] = d;
+        }
+        shift_next<NCH>(Df, DfN);
+        double dtf[NCH], dtfP[NCH], rdtf[NCH], rdtfP[NCH];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            const double ds = g.dsf[j] * zmu;
+            const double ds3 = ds * (1.0 / 3.0);
+            const double cA = fma(ds3, Df[j], chi[j]);
+            const double cB = fma(-ds3, DfN[j], chiN[j]);
+            const double t1 = chi[j] + chiN[j];
+            const double x = down ? cA : cB, y = down ? cB : cA;
+            dtf[j] = ds * ((t1 + x) + y) * 0.25;
+            rdtf[j] = rcp_fast(dtf[j]);
+        }
+        shift_prev<NCH>(dtf, dtfP);
+        shift_prev<NCH>(rdtf, rdtfP);
+        double slS[NCH], slSP[NCH], DSf[NCH], DSuw[NCH];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+            slS[j] = (SN[j] - S[j]) * rdtf[j];
+        shift_prev<NCH>(slS, slSP);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            const int k = lane * NCH + j;
+            const double rs = rcp_fast(dtf[j] + dtfP[j]);
+            double d = steffen_r(dtf[j] * rs, dtfP[j] * rs, slSP[j], slS[j]);
+            d = (k == 0) ? slS[j] : d;
+            d = (k == K - 1) ? slSP[j] : d;
+            DSf[j] = d;
+        }
+        {
+            double tP[NCH], tN[NCH];
+            shift_prev<NCH>(DSf, tP);
+            shift_next<NCH>(DSf, tN);
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+                DSuw[j] = down ? tP[j] : -tN[j];
+        }
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            const int k = lane * NCH + j;
+            const bool isEnd = (k == ke);
+            const double chiUw = down ? chiP[j] : chiN[j];
+            const double Suw = down ? SP[j] : SN[j];
+            const double dsfUw = down ? g.dsfP[j] : g.dsf[j];
+            const double dtEnd = 0.5 * zmu * (chi[j] + chiUw) * dsfUw;
+            const double dt = isEnd ? dtEnd : (down ? dtfP[j] : dtf[j]);
+            const double rdt = isEnd ? rcp_fast(dtEnd) : (down ? rdtfP[j] : rdtf[j]);
+            const bool taylor = dt < (isEnd ? 5.0E-4 : 5e-2);
+            const bool thick = dt > (isEnd ? 50.0 : 30.0);
+            double edt = (taylor || thick) ? 0.0 : exp_fast(-dt);
+            const double dt2 = dt * dt, dt3 = dt2 * dt;
+            double aa, bb, pp;
+            if (taylor && !isEnd)
+            {
+                edt = 1.0 - dt + 0.5 * dt2 - dt3 * (1.0 / 6.0);
+                const double alpha = 0.25 * dt - 0.2 * dt2 + dt3 * (1.0 / 12.0);
+                const double beta = 0.25 * dt - 0.05 * dt2 + dt3 * (1.0 / 120.0);
+                const double gamma = 0.25 * dt - 0.15 * dt2 + 0.05 * dt3;
+                const double delta = 0.25 * dt - 0.1 * dt2 + 0.025 * dt3;
+                const double dt3rd = dt * (1.0 / 3.0);
+                const double Cuw = fma(dt3rd, DSuw[j], Suw);
+                const double C0 = down ? fma(-dt3rd, DSf[j], S[j]) : fma(dt3rd, DSf[j], S[j]);
+                aa = edt;
+                bb = alpha * Suw + beta * S[j] + gamma * Cuw + delta * C0;
+                pp = beta + delta;
+            }
+            else if (!isEnd)
+            {
+                const double rdt3 = rdt * rdt * rdt;
+                const double alpha = (6.0 - edt * (6.0 + 6.0 * dt + 3.0 * dt2 + dt3)) * rdt3;
+                const double beta = (6.0 * edt - 6.0 + 6.0 * dt - 3.0 * dt2 + dt3) * rdt3;
+                const double gamma = 3.0 * (2.0 * dt - 6.0 + edt * (6.0 + 4.0 * dt + dt2)) * rdt3;
+                const double delta = 3.0 * (6.0 - 4.0 * dt + dt2 - 2.0 * edt * (3.0 + dt)) * rdt3;
+                const double dt3rd = dt * (1.0 / 3.0);
+                const double Cuw = fma(dt3rd, DSuw[j], Suw);
+                const double C0 = down ? fma(-dt3rd, DSf[j], S[j]) : fma(dt3rd, DSf[j], S[j]);
+                aa = edt;
+                bb = alpha * Suw + beta * S[j] + gamma * Cuw + delta * C0;
+                pp = beta + delta;
+            }
+            else
+            {
+                double w0, w1; // w2(), LwInternal.hpp:90-110
+                if (taylor)
+                {
+                    w0 = dt * (1.0 - 0.5 * dt);
+                    w1 = dt2 * (0.5 - dt * (1.0 / 3.0));
+                }
+                else if (thick)
+                {
+                    w0 = w1 = 1.0;
+                }
+                else
+                {
+                    w0 = 1.0 - edt;
+                    w1 = w0 - dt * edt;
+                }
+                const double dS = (S[j] - Suw) * rdt;
+                aa = 1.0 - w0;
+                bb = w0 * S[j] - w1 * dS;
+                pp = w0 - w1 * rdt;
+            }
+            if (k == ks)
+            {
+                double Iupw = 0.0;
+                if (bcType == 2)
+                {
+                    const double chiDw = down ? chiN[j] : chiP[j];
+                    const double dsfDw = down ? g.dsf[j] : g.dsfP[j];
+                    const double dtau_b = 0.5 * zmu * (chi[j] + chiDw) * dsfDw;
+                    Iupw = bcB0 - (bcB1 - bcB0) / dtau_b;
+                }
+                else if (bcType == 4)
+                    Iupw = bcValue;
+                aa = 0.0;
+                bb = Iupw;
+                pp = 0.0;
+            }
+            if (k >= K)
+            {
+                aa = 1.0;
+                bb = 0.0;
+                pp = 0.0;
+            }
+            a[j] = aa;
+            b[j] = bb;
+            psi[j] = pp * rchi[j];
+        }
+    }
+    else
+    {
+        // linear (SOLVER 0) and besser (SOLVER 1): local stencils only
+        const double zmu = (SOLVER == 0 ? 0.5 : 1.0) / muz;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            const int k = lane * NCH + j;
+            const bool isEnd = (k == ke);
+            const double chiUw = down ? chiP[j] : chiN[j];
+            const double chiDw = down ? chiN[j] : chiP[j];
+            const double Suw = down ? SP[j] : SN[j];
+            const double Sdw = down ? SN[j] : SP[j];
+            const double dsfUw = down ? g.dsfP[j] : g.dsf[j];
+            const double dsfDw = down ? g.dsf[j] : g.dsfP[j];
+            double aa, bb, pp;
+            if (SOLVER == 0 || isEnd)
+            {
+                const double dt = (SOLVER == 0 ? zmu : 0.5 * zmu) * (chi[j] + chiUw) * dsfUw;
+                const double rdt = 1.0 / dt;
+                double w0, w1;
+                if (dt < 5.0E-4)
+                {
+                    w0 = dt * (1.0 - 0.5 * dt);
+                    w1 = (dt * dt) * (0.5 - dt * (1.0 / 3.0));
+                }
+                else if (dt > 50.0)
+                {
+                    w0 = w1 = 1.0;
+                }
+                else
+                {
+                    const double e = exp(-dt);
+                    w0 = 1.0 - e;
+                    w1 = w0 - dt * e;
+                }
+                aa = 1.0 - w0;
+                if (SOLVER == 0)
+                {
+                    bb = w0 * S[j] + w1 * ((Suw - S[j]) * rdt);
+                    pp = w0 - w1 * rdt;
+                }
+                else
+                {
+                    bb = w0 * S[j] - w1 * ((S[j] - Suw) / dt);
+                    pp = w0 - w1 / dt;
+                }
+            }
+            else
+            {
+                const double ds_uw = dsfUw * zmu, ds_dw = dsfDw * zmu;
+                const double chiC = besser_control_point(ds_uw, ds_dw, chiUw, chi[j], chiDw);
+                const double dtauUw = (1.0 / 3.0) * (chiUw + chiC + chi[j]) * ds_uw;
+                const double dtauDw = 0.5 * (chi[j] + chiDw) * ds_dw;
+                const double SC = besser_control_point(dtauUw, dtauDw, Suw, S[j], Sdw);
+                const double t = dtauUw;
+                double M, O, C, edt;
+                if (t < 0.14)
+                {
+                    M = (t * (t * (t * (t * (t * (t * ((140.0 - 18.0 * t) * t - 945.0) + 5400.0) - 25200.0) + 90720.0) - 226800.0) + 302400.0)) / 907200.0;
+                    O = (t * (t * (t * (t * (t * (t * ((10.0 - t) * t - 90.0) + 720.0) - 5040.0) + 30240.0) - 151200.0) + 604800.0)) / 1814400.0;
+                    C = (t * (t * (t * (t * (t * (t * ((35.0 - 4.0 * t) * t - 270.0) + 1800.0) - 10080.0) + 45360.0) - 151200.0) + 302400.0)) / 907200.0;
+                    const double t2 = t * t, t3 = t2 * t;
+                    edt = 1.0 - t + 0.5 * t2 - t3 / 6.0 + t * t3 / 24.0 - t2 * t3 / 120.0 + t3 * t3 / 720.0 - t3 * t3 * t / 5040.0;
+                }
+                else
+                {
+                    const double t2 = t * t;
+                    edt = exp(-t);
+                    M = (2.0 - edt * (t2 + 2.0 * t + 2.0)) / t2;
+                    O = 1.0 - 2.0 * (edt + t - 1.0) / t2;
+                    C = 2.0 * (t - 2.0 + edt * (t + 2.0)) / t2;
+                }
+                aa = edt;
+                bb = M * Suw + O * S[j] + C * SC;
+                pp = O + C;
+            }
+            if (k == ks)
+            {
+                double Iupw = 0.0;
+                if (bcType == 2)
+                {
+                    const double dtau_b = (SOLVER == 0 ? zmu : 0.5 * zmu) * (chi[j] + chiDw) * dsfDw;
+                    Iupw = bcB0 - (bcB1 - bcB0) / dtau_b;
+                }
+                else if (bcType == 4)
+                    Iupw = bcValue;
+                aa = 0.0;
+                bb = Iupw;
+                pp = 0.0;
+            }
+            if (k >= K)
+            {
+                aa = 1.0;
+                bb = 0.0;
+                pp = 0.0;
+            }
+            a[j] = aa;
+            b[j] = bb;
+            psi[j] = pp * rchi[j];
+        }
+    }
+    if (down)
+        affine_scan<NCH, true>(a, b, I);
+    else
+        affine_scan<NCH, false>(a, b, I);
+}
+
+// per-wavelength line slot (at most two lines overlap on this kernel's wavelengths)
+struct LineSlot
+{
+    int trans;   // index into P.trans, -1: unused
+    int atom, li, lj;
+    double v;    // hnu/4pi * Bij
+    double gv;   // g * v   (without rhoPrd)
+    double ugv;  // Aji/Bji * g * v
+    const double* phi; // phi(lt, 0, 0, 0) of this column
+    const double* rho; // rhoPrd(lt, 0) or nullptr
+};
+
+template <int NCH, int SOLVER>
+__global__ void __launch_bounds__(128)
+fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi, int lambdaIterate,
+           int storeDepth)
+{
+    extern __shared__ double smem[];
+    const int K = P.K, M = P.M, L = P.L, KP = P.KP;
+    const int tile = tileList[blockIdx.x];
+    const int col = blockIdx.y;
+    const int warp = threadIdx.x >> 5;
+    const int nwarp = blockDim.x >> 5;
+    const int lane = lane_id();
+
+    const int slot0 = P.tileSlotOff[tile];
+    const int nslot = P.tileSlotOff[tile + 1] - slot0;
+    double* acc = smem;
+    double* Xs = smem + (size_t)P.maxSlots * 4 * KP + (size_t)warp * 2 * P.maxNlevel * 32;
+    double* Us = Xs + P.maxNlevel * 32;
+
+    for (int idx = threadIdx.x; idx < nslot * 4 * KP; idx += blockDim.x)
+        acc[idx] = 0.0;
+    __syncthreads();
+
+    GeometryR<NCH> g;
+    load_geometry_r<NCH>(g, P.height + (size_t)col * K, K);
+    double rT[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+    {
+        const int k = lane * NCH + j;
+        rT[j] = (k < K) ? 1.0 / __ldg(P.temperature + (size_t)col * K + k) : 1.0;
+    }
+    const double* Tcol = P.temperature + (size_t)col * K;
+    const double* ncol = P.n + (size_t)col * P.NlevTot * K;
+
+    const int laBeg = max(P.tileLa[tile], laLo);
+    const int laEnd = min(P.tileLa[tile + 1], laHi);
+
+    for (int la = laBeg + warp; la < laEnd; la += nwarp)
+    {
+        const double lambda = __ldg(P.wavelength + la);
+        const size_t rowLK = ((size_t)col * L + la) * K;
+        const int eBeg = P.laOff[la], eEnd = P.laOff[la + 1];
+        constexpr double hc_k = kHC / (kKBoltzmann * kNmToM);
+        constexpr double twoHc = 2.0 * kHC / (kNmToM * kNmToM * kNmToM);
+        constexpr double hc_4pi = 0.25 * kHC / kPi;
+        const double hc_kl = hc_k / lambda;
+        const double hcl = twoHc / (lambda * lambda * lambda);
+
+        // ---- ray-independent: background + continua
+        double chiC[NCH], etaC[NCH], scaJ[NCH], expfac[NCH];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            const int k = lane * NCH + j;
+            const bool v = k < K;
+            chiC[j] = v ? __ldg(P.chiBg + rowLK + k) : 1.0;
+            etaC[j] = v ? __ldg(P.etaBg + rowLK + k) : 0.0;
+            const double sca = v ? __ldg(P.scaBg + rowLK + k) : 0.0;
+            const double JDag = v ? P.J[rowLK + k] : 0.0;
+            scaJ[j] = sca * JDag;
+            expfac[j] = exp_fast(-hc_kl * rT[j]);
+        }
+        LineSlot ls[2];
+        ls[0].trans = ls[1].trans = -1;
+        ls[0].phi = ls[1].phi = nullptr;
+        ls[0].rho = ls[1].rho = nullptr;
+        ls[0].atom = ls[1].atom = -1;
+        int nL = 0;
+        double cX[2][NCH], cE[2][NCH];
+#pragma unroll
+        for (int l = 0; l < 2; ++l)
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+                cX[l][j] = cE[l][j] = 0.0;
+
+        for (int e = eBeg; e < eEnd; ++e)
+        {
+            const int ti = P.entries[e].trans;
+            const DevTrans& t = P.trans[ti];
+            const int lt = la - t.Nblue;
+            if (t.type == 0)
+            {
+                // line: constants of Transition::uv (LwTransition.hpp:93-130)
+                const double vB = hc_4pi * (t.lambda0 / lambda) * t.Bij;
+                const double gS = t.Bji_Bij;
+                const double* rho = (t.rhoOff >= 0)
+                    ? P.rhoPrd + t.rhoOff + ((size_t)col * (t.Nred - t.Nblue) + lt) * K : nullptr;
+                const int l = nL++;
+                // nL <= 2 guaranteed by the planner for this kernel
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                {
+                    if (q == l)
+                    {
+                        ls[q].trans = ti;
+                        ls[q].atom = t.atom;
+                        ls[q].li = t.i;
+                        ls[q].lj = t.j;
+                        ls[q].v = vB;
+                        ls[q].gv = gS * vB;
+                        ls[q].ugv = t.Aji_Bji * (gS * vB);
+                        ls[q].phi = P.phi + t.phiOff + (size_t)col * t.phiColStride + (size_t)lt * M * 2 * K;
+                        ls[q].rho = rho;
+#pragma unroll
+                        for (int j = 0; j < NCH; ++j)
+                        {
+                            const int k = lane * NCH + j;
+                            if (k < K)
+                            {
+                                const double ni = __ldg(ncol + (size_t)t.levI * K + k);
+                                const double nj = __ldg(ncol + (size_t)t.levJ * K + k);
+                                const double gk = rho ? gS * __ldg(rho + k) : gS;
+                                cX[q][j] = vB * (ni - nj * gk);
+                                cE[q][j] = nj * (t.Aji_Bji * (gk * vB));
+                            }
+                        }
+                    }
+                }
+            }
+            else
+            {
+                const double al = __ldg(P.alphaTab + t.tabOff + lt);
+                const double* gr = P.gRatio + ((size_t)t.contIdx * P.Ncol + col) * K;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+                {
+                    const int k = lane * NCH + j;
+                    if (k < K)
+                    {
+                        const double gk = __ldg(gr + k) * expfac[j];
+                        const double Vji = gk * al;
+                        const double ni = __ldg(ncol + (size_t)t.levI * K + k);
+                        const double nj = __ldg(ncol + (size_t)t.levJ * K + k);
+                        chiC[j] += ni * al - nj * Vji;
+                        etaC[j] += nj * (hcl * Vji);
+                    }
+                }
+            }
+        }
+
+        // thermalised boundaries: Planck function at the two boundary pairs (once per wavelength)
+        double Btop0 = 0.0, Btop1 = 0.0, Bbot0 = 0.0, Bbot1 = 0.0;
+        if (P.upperBc == 2)
+        {
+            Btop0 = planck_nu(__ldg(Tcol + 0), lambda);
+            Btop1 = planck_nu(__ldg(Tcol + 1), lambda);
+        }
+        if (P.lowerBc == 2)
+        {
+            Bbot0 = planck_nu(__ldg(Tcol + K - 1), lambda);
+            Bbot1 = planck_nu(__ldg(Tcol + K - 2), lambda);
+        }
+
+        // ---- moments over the rays of this wavelength
+        double mJ[NCH], mP[NCH], mW[2][NCH], mA[2][NCH], mB0[2][NCH], mB[2][NCH], mB01[NCH];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            mJ[j] = mP[j] = mB01[j] = 0.0;
+#pragma unroll
+            for (int l = 0; l < 2; ++l)
+                mW[l][j] = mA[l][j] = mB0[l][j] = mB[l][j] = 0.0;
+        }
+        double W0 = 0.0;
+
+        for (int ray = 0; ray < 2 * M; ++ray)
+        {
+            const int mu = ray >> 1, dir = ray & 1;
+            const double muz = __ldg(P.muz + mu);
+            const double w = 0.5 * __ldg(P.wmu + mu);
+            double chi[NCH], S[NCH], rchi[NCH], p0[NCH], p1[NCH];
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+            {
+                const int k = lane * NCH + j;
+                double c = chiC[j], e = etaC[j];
+                p0[j] = p1[j] = 0.0;
+                if (nL > 0 && k < K)
+                {
+                    p0[j] = __ldg(ls[0].phi + (size_t)(mu * 2 + dir) * K + k);
+                    c = fma(cX[0][j], p0[j], c);
+                    e = fma(cE[0][j], p0[j], e);
+                }
+                if (nL > 1 && k < K)
+                {
+                    p1[j] = __ldg(ls[1].phi + (size_t)(mu * 2 + dir) * K + k);
+                    c = fma(cX[1][j], p1[j], c);
+                    e = fma(cE[1][j], p1[j], e);
+                }
+                chi[j] = c;
+                rchi[j] = rcp_fast(c);
+                S[j] = (e + scaJ[j]) * rchi[j];
+                if (storeDepth && k < K)
+                {
+                    const size_t off = ((((size_t)col * L + la) * M + mu) * 2 + dir) * K + k;
+                    P.depthChi[off] = c;
+                    P.depthEta[off] = e;
+                }
+            }
+            int bcType;
+            double bcB0, bcB1, bcValue = 0.0;
+            if (dir == 1)
+            {
+                bcType = P.lowerBc;
+                bcB0 = Bbot0;
+                bcB1 = Bbot1;
+                if (bcType == 4)
+                    bcValue = P.lowerBcData[((size_t)col * L + la) * P.NlowerBcMu + P.lowerBcIdx[mu * 2 + 1]];
+            }
+            else
+            {
+                bcType = P.upperBc;
+                bcB0 = Btop0;
+                bcB1 = Btop1;
+                if (bcType == 4)
+                    bcValue = P.upperBcData[((size_t)col * L + la) * P.NupperBcMu + P.upperBcIdx[mu * 2 + 0]];
+            }
+            double I[NCH], psi[NCH];
+            solve_ray_r<NCH, SOLVER>(g, chi, S, rchi, muz, dir == 0, bcType, bcB0, bcB1, bcValue, I, psi);
+
+            if (lane == 0)
+                P.I[((size_t)col * L + la) * M + mu] = I[0];
+            W0 += w;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+            {
+                const int k = lane * NCH + j;
+                if (storeDepth && k < K)
+                    P.depthI[((((size_t)col * L + la) * M + mu) * 2 + dir) * K + k] = I[j];
+                const double wI = w * I[j];
+                const double wP = lambdaIterate ? 0.0 : w * psi[j];
+                mJ[j] += wI;
+                mP[j] += wP;
+                const double t0 = wP * p0[j];
+                mW[0][j] = fma(w, p0[j], mW[0][j]);
+                mA[0][j] = fma(wI, p0[j], mA[0][j]);
+                mB0[0][j] += t0;
+                mB[0][j] = fma(t0, p0[j], mB[0][j]);
+                const double t1 = wP * p1[j];
+                mW[1][j] = fma(w, p1[j], mW[1][j]);
+                mA[1][j] = fma(wI, p1[j], mA[1][j]);
+                mB0[1][j] += t1;
+                mB[1][j] = fma(t1, p1[j], mB[1][j]);
+                mB01[j] = fma(t0, p1[j], mB01[j]);
+            }
+        }
+
+        // ---- J row and dJ (:477-485)
+        double dJ = 0.0;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            const int k = lane * NCH + j;
+            if (k < K)
+            {
+                const double JDag = P.J[rowLK + k];
+                P.J[rowLK + k] = mJ[j];
+                const double d = fabs(1.0 - JDag / mJ[j]);
+                dJ = (d < dJ) ? dJ : d;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+        {
+            const double o = __shfl_xor_sync(kFull, dJ, d);
+            dJ = (o < dJ) ? dJ : o;
+        }
+        if (lane == 0)
+            P.dJ[(size_t)col * L + la] = dJ;
+
+        // ---- epilogue: Gamma and rates from the moments, atom by atom
+        int e0 = eBeg;
+        while (e0 < eEnd)
+        {
+            const int atom = P.trans[P.entries[e0].trans].atom;
+            int e1 = e0 + 1;
+            while (e1 < eEnd && P.trans[P.entries[e1].trans].atom == atom)
+                ++e1;
+            const bool detailed = P.atomDetailed[atom] != 0;
+            const int N = P.atomNlevel[atom];
+            const bool own0 = (nL > 0) && ls[0].atom == atom;
+            const bool own1 = (nL > 1) && ls[1].atom == atom;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+            {
+                const int k = lane * NCH + j;
+                if (k >= K)
+                    continue;
+                double E0 = 0.0;
+                if (!detailed)
+                {
+                    // continuum aggregates per level: chi_atom / U_atom of chi_eta_aux_accum (:59-109)
+                    for (int m = 0; m < N; ++m)
+                    {
+                        Xs[m * 32 + lane] = 0.0;
+                        Us[m * 32 + lane] = 0.0;
+                    }
+                    for (int e = e0; e < e1; ++e)
+                    {
+                        const DevTrans& t = P.trans[P.entries[e].trans];
+                        if (t.type == 0)
+                            continue;
+                        const double al = __ldg(P.alphaTab + t.tabOff + (la - t.Nblue));
+                        const double gk = __ldg(P.gRatio + ((size_t)t.contIdx * P.Ncol + col) * K + k) * expfac[j];
+                        const double Vji = gk * al;
+                        const double Uji = hcl * Vji;
+                        const double ni = __ldg(ncol + (size_t)t.levI * K + k);
+                        const double nj = __ldg(ncol + (size_t)t.levJ * K + k);
+                        const double x = ni * al - nj * Vji;
+                        Xs[t.i * 32 + lane] += x;
+                        Xs[t.j * 32 + lane] -= x;
+                        Us[t.j * 32 + lane] += Uji;
+                        E0 += nj * Uji;
+                    }
+                }
+                // line profile members of this atom: per-unit-phi coefficients
+                double gv0 = 0.0, ugv0 = 0.0, gv1 = 0.0, ugv1 = 0.0;
+                if (own0)
+                {
+                    const double r = ls[0].rho ? __ldg(ls[0].rho + k) : 1.0;
+                    gv0 = ls[0].gv * r;
+                    ugv0 = ls[0].ugv * r;
+                }
+                if (own1)
+                {
+                    const double r = ls[1].rho ? __ldg(ls[1].rho + k) : 1.0;
+                    gv1 = ls[1].gv * r;
+                    ugv1 = ls[1].ugv * r;
+                }
+                const double X0l = own0 ? cX[0][j] : 0.0, E0l = own0 ? cE[0][j] : 0.0;
+                const double X1l = own1 ? cX[1][j] : 0.0, E1l = own1 ? cE[1][j] : 0.0;
+                // sum_q' E_q' M(q, q') for q = continuum, line0, line1
+                const double EBc = E0 * mP[j] + E0l * mB0[0][j] + E1l * mB0[1][j];
+                const double EB0 = E0 * mB0[0][j] + E0l * mB[0][j] + E1l * mB01[j];
+                const double EB1 = E0 * mB0[1][j] + E0l * mB01[j] + E1l * mB[1][j];
+
+                for (int e = e0; e < e1; ++e)
+                {
+                    const DevEntry en = P.entries[e];
+                    const DevTrans& t = P.trans[en.trans];
+                    const int lt = la - t.Nblue;
+                    // profile member of this transition: 0 continuum, 1 line slot 0, 2 line slot 1
+                    const int q = (t.type != 0) ? 0 : (en.trans == ls[0].trans ? 1 : 2);
+                    double v, gv, ugv, Wq, Aq, EBq;
+                    if (q == 0)
+                    {
+                        const double al = __ldg(P.alphaTab + t.tabOff + lt);
+                        const double gk = __ldg(P.gRatio + ((size_t)t.contIdx * P.Ncol + col) * K + k) * expfac[j];
+                        v = al;
+                        gv = gk * al;
+                        ugv = hcl * gv;
+                        Wq = W0;
+                        Aq = mJ[j];
+                        EBq = EBc;
+                    }
+                    else if (q == 1)
+                    {
+                        v = ls[0].v;
+                        gv = gv0;
+                        ugv = ugv0;
+                        Wq = mW[0][j];
+                        Aq = mA[0][j];
+                        EBq = EB0;
+                    }
+                    else
+                    {
+                        v = ls[1].v;
+                        gv = gv1;
+                        ugv = ugv1;
+                        Wq = mW[1][j];
+                        Aq = mA[1][j];
+                        EBq = EB1;
+                    }
+                    const double wla = trans_wla(P, t, col, lt, k, lambda);
+                    double* a4 = acc + (size_t)en.slot * 4 * KP + k;
+                    if (!detailed)
+                    {
+                        // chi_atom(m) = Xc(m) + p0 X0l s0(m) + p1 X1l s1(m);  U_atom(m) = Uc(m) + p0 ugv0 [m==lj0] + ...
+                        const double Xci = Xs[t.i * 32 + lane], Xcj = Xs[t.j * 32 + lane];
+                        const double Uci = Us[t.i * 32 + lane], Ucj = Us[t.j * 32 + lane];
+                        const double X0i = own0 ? (t.i == ls[0].li ? X0l : (t.i == ls[0].lj ? -X0l : 0.0)) : 0.0;
+                        const double X0j = own0 ? (t.j == ls[0].li ? X0l : (t.j == ls[0].lj ? -X0l : 0.0)) : 0.0;
+                        const double X1i = own1 ? (t.i == ls[1].li ? X1l : (t.i == ls[1].lj ? -X1l : 0.0)) : 0.0;
+                        const double X1j = own1 ? (t.j == ls[1].li ? X1l : (t.j == ls[1].lj ? -X1l : 0.0)) : 0.0;
+                        const double U0i = (own0 && t.i == ls[0].lj) ? ugv0 : 0.0;
+                        const double U0j = (own0 && t.j == ls[0].lj) ? ugv0 : 0.0;
+                        const double U1i = (own1 && t.i == ls[1].lj) ? ugv1 : 0.0;
+                        const double U1j = (own1 && t.j == ls[1].lj) ? ugv1 : 0.0;
+                        // sum_r w Psi chi_atom(a) U_atom(b) = sum_{q',q''} X_q'(a) U_q''(b) M(q',q'')
+                        const double XUij =
+                            Xci * (Ucj * mP[j] + U0j * mB0[0][j] + U1j * mB0[1][j])
+                            + X0i * (Ucj * mB0[0][j] + U0j * mB[0][j] + U1j * mB01[j])
+                            + X1i * (Ucj * mB0[1][j] + U0j * mB01[j] + U1j * mB[1][j]);
+                        const double XUji =
+                            Xcj * (Uci * mP[j] + U0i * mB0[0][j] + U1i * mB0[1][j])
+                            + X0j * (Uci * mB0[0][j] + U0i * mB[0][j] + U1i * mB01[j])
+                            + X1j * (Uci * mB0[1][j] + U0i * mB01[j] + U1i * mB[1][j]);
+                        // sum_r w [(Uji + Vji Ieff) - Psi chi(i) U(j)],  Ieff = I - Psi eta_atom
+                        smem_add(a4, (ugv * Wq + gv * (Aq - EBq) - XUij) * wla);
+                        smem_add(a4 + KP, (v * (Aq - EBq) - XUji) * wla);
+                    }
+                    smem_add(a4 + 2 * KP, (v * Aq) * wla);
+                    smem_add(a4 + 3 * KP, (ugv * Wq + gv * Aq) * wla);
+                }
+            }
+            e0 = e1;
+        }
+    }
+
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nslot * 4 * KP; idx += blockDim.x)
+    {
+        const int k = idx % KP;
+        const int q = (idx / KP) & 3;
+        const int s = idx / (4 * KP);
+        if (k >= K)
+            continue;
+        const DevTrans& t = P.trans[P.tileSlotTrans[slot0 + s]];
+        const int row = q == 0 ? t.accIJ : q == 1 ? t.accJI : q == 2 ? t.accRij : t.accRji;
+        if (row < 0)
+            continue;
+        const double v = acc[idx];
+        if (v != 0.0)
+            atomicAdd(P.accum + ((size_t)col * P.AccTot + row) * K + k, v);
+    }
+}
+
+} // namespace lwb200

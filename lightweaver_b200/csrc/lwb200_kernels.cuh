@@ -134,12 +134,12 @@ __device__ __forceinline__ void smem_add(double* addr, double v) { atomicAdd(add
 // ---------------------------------------------------------------------------
 template <int NCH, int SOLVER, int MODE>
 __global__ void __launch_bounds__(128)
-fs_kernel(const DevProblem P, int tile0, int laLo, int laHi, int lambdaIterate, int upOnly,
-          int storeDepth)
+fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi, int lambdaIterate,
+          int upOnly, int storeDepth)
 {
     extern __shared__ double smem[];
     const int K = P.K, M = P.M, L = P.L, KP = P.KP;
-    const int tile = tile0 + blockIdx.x;
+    const int tile = tileList[blockIdx.x];
     const int col = blockIdx.y;
     const int warp = threadIdx.x >> 5;
     const int nwarp = blockDim.x >> 5;

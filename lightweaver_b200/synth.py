@@ -285,9 +285,18 @@ def planck_nu(wavelength_nm, T):
         return np.where(x <= 150.0, twohnu3_c2 / np.expm1(np.minimum(x, 150.0)), 0.0)
 
 
-def background(wavelength, temperature, ne, nHTot, metal_scale=1.0):
+def background(wavelength, temperature, ne, nHTot, metal_scale=1.0, chunk=64):
     """Smooth H-minus-like continuous absorption + Thomson/Rayleigh scattering.
     Returns chi (absorption + scattering), eta (thermal), sca, each [ncol, L, K]."""
+    ncol = temperature.shape[0]
+    if ncol > chunk:
+        shape = (ncol, wavelength.shape[0], temperature.shape[1])
+        chi, eta, sca = np.empty(shape), np.empty(shape), np.empty(shape)
+        for c0 in range(0, ncol, chunk):
+            sl = slice(c0, min(c0 + chunk, ncol))
+            chi[sl], eta[sl], sca[sl] = background(wavelength, temperature[sl], ne[sl], nHTot[sl],
+                                                   metal_scale, chunk)
+        return chi, eta, sca
     lam = wavelength[None, :, None]
     T = temperature[:, None, :]
     theta = 5040.0 / T
@@ -322,10 +331,18 @@ def collision_matrix(atom: ModelAtom, temperature, ne, nStar, rng):
 # ------------------------------------------------------------- the generator
 def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, seed=SEED,
                   formal_solver=capi.FS_BEZIER3, ndepth=None, detailed: Sequence[str] = (),
-                  with_profiles=True, lambda_reference=500.0) -> Problem:
-    """Assemble a Problem for ``atoms`` in ``ncol`` FAL C columns."""
+                  with_profiles=True, lambda_reference=500.0, col_range=None,
+                  alloc_phi=True) -> Problem:
+    """Assemble a Problem for ``atoms`` in ``ncol`` FAL C columns.  ``col_range``
+    = (c0, c1) keeps only that slice of the ``ncol`` columns (one column shard of
+    a multi-GPU run; every rank sees the same seeded stack).  ``with_profiles``
+    False leaves phi/wphi zero (to be made on the device); ``alloc_phi`` False
+    does not even allocate host phi."""
     rng = np.random.default_rng(seed + 1)
     atm = falc_columns(ncol, perturb=perturb, seed=seed, ndepth=ndepth)
+    if col_range is not None:
+        atm = {k: np.ascontiguousarray(v[col_range[0]:col_range[1]]) for k, v in atm.items()}
+        ncol = col_range[1] - col_range[0]
     T, ne, nHTot, vturb = atm['temperature'], atm['ne'], atm['nHTot'], atm['vturb']
     K = T.shape[1]
     muz, wmu = gauss_legendre_mu(nrays)
@@ -388,8 +405,10 @@ def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, se
                 wlam = t.wlambda()
                 s = np.einsum('clmdk,l,m->ck', t.phi, wlam, 0.5 * wmu)
                 t.wphi = np.ascontiguousarray(1.0 / s)
-            else:
+            elif alloc_phi:
                 t.phi = np.zeros((ncol, t.Nlambda, nrays, 2, K))
+            else:
+                t.wphi = None
         is_detailed = atom.name in detailed
         atom_data[ia] = AtomData(name=atom.name, Nlevel=len(atom.levels), trans=trans_lists[ia],
                                  n=nStar.copy(), nStar=nStar, nTotal=nTotal, vBroad=vBroad,
@@ -411,7 +430,7 @@ def config_c1(ncol=1, nrays=5, perturb=False, seed=SEED, nl=1.0, **kw) -> Proble
                          seed=seed, **kw)
 
 
-def config_c2(nrays=10, nl=3.0, seed=SEED, **kw) -> Problem:
+def config_c2(nrays=10, nl=4.8, seed=SEED, **kw) -> Problem:
     """Config 2: FAL C, H + Ca II + Mg II + Na I + He I active (Fe only through
     the background), ~1e4 wavelengths, 10 rays."""
     atoms = [h6_atom(nl), ca2_atom(nl), mg2_atom(nl), na1_atom(nl), he1_atom(nl)]
