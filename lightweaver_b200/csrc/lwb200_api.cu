@@ -9,7 +9,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <set>
 #include <string>
+#include <utility>
 #include <vector>
 
 using namespace lwb200;
@@ -122,8 +124,8 @@ struct LwB200Context
     std::vector<DevTrans> devTrans;
     std::vector<int> atomNlevel, atomLevOff, atomGammaOff, atomDetailed;
     std::vector<int> tileLa, tileSlotOff, tileSlotTrans, tileKind;
-    DevBuf<int> dListMoments, dListDirect, dListAll;
-    int nListMoments = 0, nListDirect = 0, nListAll = 0, listLo = -1, listHi = -1;
+    DevBuf<int> dListNL[3], dListDirect, dListAll;
+    int nListNL[3] = {0, 0, 0}, nListDirect = 0, nListAll = 0, listLo = -1, listHi = -1;
     int Ntile = 0;
     int nwarps = 4;
     int laLo = 0, laHi = 0;
@@ -248,7 +250,7 @@ int build_plan(LwB200Context* c)
             }
         }
     // wavelengths with more than two overlapping lines go to the general kernel
-    auto kind_of = [&](int la) { return laNLines[la] > 2 ? 1 : 0; };
+    auto kind_of = [&](int la) { return laNLines[la] > 2 ? 3 : laNLines[la]; };
 
     // tiles: runs of wavelengths whose union of active transitions fits the
     // shared-memory accumulator; sized so that the grid fills the GPU
@@ -447,20 +449,25 @@ int refresh_tile_lists(LwB200Context* c)
 {
     if (c->listLo == c->laLo && c->listHi == c->laHi)
         return 0;
-    std::vector<int> mom, dir, all;
+    std::vector<int> mom[3], dir, all;
     for (int t = 0; t < c->Ntile; ++t)
     {
         if (c->tileLa[t + 1] <= c->laLo || c->tileLa[t] >= c->laHi)
             continue;
         all.push_back(t);
-        (c->tileKind[t] == 0 ? mom : dir).push_back(t);
+        (c->tileKind[t] < 3 ? mom[c->tileKind[t]] : dir).push_back(t);
     }
-    c->dListMoments.release();
     c->dListDirect.release();
     c->dListAll.release();
-    if (c->dListMoments.upload(mom) || c->dListDirect.upload(dir) || c->dListAll.upload(all))
+    for (int q = 0; q < 3; ++q)
+    {
+        c->dListNL[q].release();
+        if (c->dListNL[q].upload(mom[q]))
+            return 1;
+        c->nListNL[q] = (int)mom[q].size();
+    }
+    if (c->dListDirect.upload(dir) || c->dListAll.upload(all))
         return 1;
-    c->nListMoments = (int)mom.size();
     c->nListDirect = (int)dir.size();
     c->nListAll = (int)all.size();
     c->listLo = c->laLo;
@@ -471,12 +478,13 @@ int refresh_tile_lists(LwB200Context* c)
 template <typename Kern>
 int set_smem_attr(Kern kern, int device)
 {
-    static bool attrSet[16] = {false};
-    if (!attrSet[device & 15])
-    {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attrSet[device & 15] = true;
-    }
+    // per (kernel, device): opt in to > 48 KB of dynamic shared memory
+    static std::set<std::pair<const void*, int>> done;
+    const auto key = std::make_pair((const void*)kern, device);
+    if (done.count(key))
+        return 0;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    done.insert(key);
     return 0;
 }
 
@@ -492,13 +500,36 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
     const int threads = c->nwarps * 32;
     if (MODE == MODE_ITER && !c->forceDirect)
     {
-        if (c->nListMoments > 0)
+        // largest tiles first: the NL = 1 (single line) wavelengths dominate
+        if (c->nListNL[1] > 0)
         {
-            auto kern = fsm_kernel<NCH, SOLVER>;
+            auto kern = fsm_kernel<NCH, SOLVER, 1>;
             if (set_smem_attr(kern, c->device))
                 return 1;
-            dim3 grid(c->nListMoments, c->prob.Ncol);
-            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListMoments.p, c->laLo, c->laHi,
+            dim3 grid(c->nListNL[1], c->prob.Ncol);
+            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListNL[1].p, c->laLo, c->laHi,
+                                                             lambdaIterate, storeDepth);
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
+        }
+        if (c->nListNL[2] > 0)
+        {
+            auto kern = fsm_kernel<NCH, SOLVER, 2>;
+            if (set_smem_attr(kern, c->device))
+                return 1;
+            dim3 grid(c->nListNL[2], c->prob.Ncol);
+            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListNL[2].p, c->laLo, c->laHi,
+                                                             lambdaIterate, storeDepth);
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
+        }
+        if (c->nListNL[0] > 0)
+        {
+            auto kern = fsm_kernel<NCH, SOLVER, 0>;
+            if (set_smem_attr(kern, c->device))
+                return 1;
+            dim3 grid(c->nListNL[0], c->prob.Ncol);
+            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListNL[0].p, c->laLo, c->laHi,
                                                              lambdaIterate, storeDepth);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
@@ -676,7 +707,8 @@ int lwb200_destroy(LwB200Context* c)
         cudaEventDestroy(c->evK0);
     if (c->evK1)
         cudaEventDestroy(c->evK1);
-    c->dListMoments.release();
+    for (int q = 0; q < 3; ++q)
+        c->dListNL[q].release();
     c->dListDirect.release();
     c->dListAll.release();
     c->djIdx.release();

@@ -13,15 +13,18 @@
 // so per ray only the MOMENTS  sum_r w_r {I, Psi*, p, p I, p Psi*, p p' Psi*}
 // are accumulated (in registers, private to the lane that owns depth k), and
 // the per-transition work (Gamma(i,j), Gamma(j,i), Rij, Rji) runs once per
-// wavelength instead of once per ray.  Up to two lines may overlap at a
-// wavelength in this kernel (the planner routes the rare wavelengths with
-// three or more overlapping lines to the general fs_kernel).
+// wavelength instead of once per ray.  The kernel is specialised on the number
+// NL of lines overlapping at a wavelength (0, 1 or 2; the planner cuts tiles so
+// that NL is constant inside a tile and routes the rare wavelengths with three
+// or more overlapping lines to the general fs_kernel).
 //
 // The formal solver is the same arithmetic as lwb200_device.cuh, restructured
-// for instruction-cache footprint and fp64-pipe cost: one code copy for both
-// ray directions, divisions by ray-independent geometry replaced by
-// precomputed reciprocals, the remaining ones by a Newton reciprocal, and a
-// branch-light exp.  Differences from the reference are at rounding level.
+// for the B200 issue/fp64 pipes: one straight-line, branch-free code path for
+// both ray directions and all optical-depth regimes (selects instead of
+// divergent branches, so the three depth chunks of a lane interleave and no
+// shuffle needs re-convergence), divisions by ray-independent geometry replaced
+// by precomputed reciprocals, the rest by a Newton reciprocal, and a
+// table-free exp.  Differences from the reference are at rounding level.
 #pragma once
 #include "lwb200_kernels.cuh"
 
@@ -66,6 +69,13 @@ __device__ __forceinline__ double exp_fast(double x)
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
+// one 64-bit value from the neighbouring lane: lane-1 if `fromPrev`, else lane+1
+__device__ __forceinline__ double shfl_neighbour(double v, bool fromPrev)
+{
+    const int src = lane_id() + (fromPrev ? -1 : 1);
+    return __shfl_sync(kFull, v, src & 31);
+}
+
 template <int NCH>
 struct GeometryR
 {
@@ -74,6 +84,7 @@ struct GeometryR
     double dsfP[NCH];  // |h_{k-1} - h_k|
     double rdsf[NCH];  // 1 / dsf
     double rsum[NCH];  // 1 / (dsf + dsfP)
+    double rdsfP0;     // 1 / dsfP[0]
 };
 
 template <int NCH>
@@ -104,23 +115,177 @@ __device__ __forceinline__ void load_geometry_r(GeometryR<NCH>& g, const double*
         g.rdsf[j] = 1.0 / g.dsf[j];
         g.rsum[j] = 1.0 / (g.dsf[j] + g.dsfP[j]);
     }
+    g.rdsfP0 = 1.0 / g.dsfP[0];
 }
 
 __device__ __forceinline__ double steffen_r(double wUw, double wDw, double Suw, double S0)
 {
     // wUw = dsdw/(dsdw+dsuw) multiplies Suw, wDw = dsuw/(dsdw+dsuw) multiplies S0 (Bezier.hpp:58-65)
-    const double P0 = fabs(Suw * wUw + S0 * wDw);
+    const double P0 = fabs(fma(Suw, wUw, S0 * wDw));
     return (copysign(1.0, S0) + copysign(1.0, Suw)) * fmin(fabs(Suw), fmin(fabs(S0), 0.5 * P0));
 }
 
-// One ray of piecewise_bezier3_1d / piecewise_besser_1d / piecewise_linear_1d,
-// both directions through one code path.  Outputs I and psi = Psi*/chi.
-template <int NCH, int SOLVER>
-__device__ __forceinline__ void solve_ray_r(const GeometryR<NCH>& g, const double (&chi)[NCH],
+__device__ __forceinline__ double sel(bool c, double a, double b) { return c ? a : b; }
+
+// One ray of piecewise_bezier3_1d (FormalScalar.cpp:209-325, :535-600), both
+// directions and every optical-depth regime through one straight-line path.
+// Outputs I and psi = Psi*/chi.
+template <int NCH>
+__device__ __forceinline__ void bezier3_ray(const GeometryR<NCH>& g, const double (&chi)[NCH],
                                             const double (&S)[NCH], const double (&rchi)[NCH],
                                             double muz, bool down, int bcType, double bcB0,
                                             double bcB1, double bcValue, double (&I)[NCH],
                                             double (&psi)[NCH])
+{
+    const int lane = lane_id();
+    const int K = g.K;
+    const int ks = down ? 0 : K - 1;
+    const int ke = down ? K - 1 : 0;
+    const double zmu = rcp_fast(muz);
+    const double sgn = down ? 1.0 : -1.0;
+    double chiN[NCH], chiP[NCH], SN[NCH], SP[NCH];
+    shift_next<NCH>(chi, chiN);
+    shift_prev<NCH>(chi, chiP);
+    shift_next<NCH>(S, SN);
+    shift_prev<NCH>(S, SP);
+
+    // chi slopes on forward intervals, Steffen derivatives (array-forward orientation; the
+    // derivative along an up-going ray is exactly the negative)
+    double sl[NCH], Df[NCH], DfN[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+        sl[j] = (chiN[j] - chi[j]) * (g.rdsf[j] * muz);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+    {
+        const int k = lane * NCH + j;
+        const double slPj = (j == 0) ? (chi[0] - chiP[0]) * (g.rdsfP0 * muz) : sl[j > 0 ? j - 1 : 0];
+        double d = steffen_r(g.dsf[j] * g.rsum[j], g.dsfP[j] * g.rsum[j], slPj, sl[j]);
+        d = sel(k == 0, sl[j], d);       // one-sided at the top    (:239 / :288)
+        d = sel(k == K - 1, slPj, d);    // one-sided at the bottom
+        Df[j] = d;
+    }
+    shift_next<NCH>(Df, DfN);
+
+    // Bezier-interpolated optical depth of the forward interval (k, k+1) (:242-246, :261-263)
+    double dtf[NCH], dtfP[NCH], rdtf[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+    {
+        const double ds = g.dsf[j] * zmu;
+        const double ds3 = ds * (1.0 / 3.0);
+        const double cA = fma(ds3, Df[j], chi[j]);
+        const double cB = fma(-ds3, DfN[j], chiN[j]);
+        const double t1 = chi[j] + chiN[j];
+        dtf[j] = ds * ((t1 + sel(down, cA, cB)) + sel(down, cB, cA)) * 0.25;
+        rdtf[j] = rcp_fast(dtf[j]);
+    }
+    shift_prev<NCH>(dtf, dtfP);
+
+    // source-function slopes and derivatives with respect to optical depth
+    double slS[NCH], DSf[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+        slS[j] = (SN[j] - S[j]) * rdtf[j];
+    const double rdtfP0 = rcp_fast(dtfP[0]);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+    {
+        const int k = lane * NCH + j;
+        const double slSPj = (j == 0) ? (S[0] - SP[0]) * rdtfP0 : slS[j > 0 ? j - 1 : 0];
+        const double rs = rcp_fast(dtf[j] + dtfP[j]);
+        double d = steffen_r(dtf[j] * rs, dtfP[j] * rs, slSPj, slS[j]);
+        d = sel(k == 0, slS[j], d);      // (:247)
+        d = sel(k == K - 1, slSPj, d);
+        DSf[j] = d;
+    }
+    // derivative at the upwind point, signed along the ray: one shuffle whose source lane
+    // depends on the direction
+    const double DSedge = shfl_neighbour(sel(down, DSf[NCH - 1], DSf[0]), down);
+
+    double a[NCH], b[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+    {
+        const int k = lane * NCH + j;
+        const bool isEnd = (k == ke);
+        const double chiUw = sel(down, chiP[j], chiN[j]);
+        const double Suw = sel(down, SP[j], SN[j]);
+        const double dsfUw = sel(down, g.dsfP[j], g.dsf[j]);
+        // upwind derivative along the ray
+        const double DSprev = (j == 0) ? DSedge : DSf[j > 0 ? j - 1 : 0];
+        const double DSnext = (j == NCH - 1) ? DSedge : DSf[j < NCH - 1 ? j + 1 : j];
+        const double DSuw = sel(down, DSprev, -DSnext);
+        // piecewise linear on the end (:307-321), Bezier elsewhere: one optical depth, one exp
+        const double dtEnd = 0.5 * zmu * (chi[j] + chiUw) * dsfUw;
+        const double dt = sel(isEnd, dtEnd, sel(down, dtfP[j], dtf[j]));
+        const double rdt = rcp_fast(dt);
+        const double ex = exp_fast(-fmin(fmax(dt, 0.0), 700.0));
+        const double dt2 = dt * dt, dt3 = dt2 * dt;
+
+        // Bezier3_coeffs (Bezier.hpp:81-127); dt > 30 is the closed form with edt = 0, term for term
+        const double edtC = sel(dt > 30.0, 0.0, ex);
+        const double rdt3 = rdt * rdt * rdt;
+        const double alphaC = (6.0 - edtC * (6.0 + 6.0 * dt + 3.0 * dt2 + dt3)) * rdt3;
+        const double betaC = (6.0 * edtC - 6.0 + 6.0 * dt - 3.0 * dt2 + dt3) * rdt3;
+        const double gammaC = 3.0 * (2.0 * dt - 6.0 + edtC * (6.0 + 4.0 * dt + dt2)) * rdt3;
+        const double deltaC = 3.0 * (6.0 - 4.0 * dt + dt2 - 2.0 * edtC * (3.0 + dt)) * rdt3;
+        const double edtT = 1.0 - dt + 0.5 * dt2 - dt3 * (1.0 / 6.0);
+        const double alphaT = 0.25 * dt - 0.2 * dt2 + dt3 * (1.0 / 12.0);
+        const double betaT = 0.25 * dt - 0.05 * dt2 + dt3 * (1.0 / 120.0);
+        const double gammaT = 0.25 * dt - 0.15 * dt2 + 0.05 * dt3;
+        const double deltaT = 0.25 * dt - 0.1 * dt2 + 0.025 * dt3;
+        const bool tay = dt < 5e-2;
+        const double alpha = sel(tay, alphaT, alphaC), beta = sel(tay, betaT, betaC);
+        const double gamma = sel(tay, gammaT, gammaC), delta = sel(tay, deltaT, deltaC);
+        const double dt3rd = dt * (1.0 / 3.0);
+        const double Cuw = fma(dt3rd, DSuw, Suw);
+        const double C0 = fma(-sgn * dt3rd, DSf[j], S[j]);
+        double aa = sel(tay, edtT, edtC);
+        double bb = alpha * Suw + beta * S[j] + gamma * Cuw + delta * C0;
+        double pp = beta + delta;
+
+        // w2() (LwInternal.hpp:90-110) for the end point
+        const bool tayE = dt < 5.0E-4, thickE = dt > 50.0;
+        const double w0m = 1.0 - ex;
+        const double w0 = sel(tayE, dt * (1.0 - 0.5 * dt), sel(thickE, 1.0, w0m));
+        const double w1 = sel(tayE, dt2 * (0.5 - dt * (1.0 / 3.0)), sel(thickE, 1.0, w0m - dt * ex));
+        const double dS = (S[j] - Suw) * rdt;
+        aa = sel(isEnd, 1.0 - w0, aa);
+        bb = sel(isEnd, w0 * S[j] - w1 * dS, bb);
+        pp = sel(isEnd, w0 - w1 * rdt, pp);
+
+        // boundary intensity (:551-597)
+        double Iupw = bcValue;
+        if (bcType == 2)
+        {
+            const double chiDw = sel(down, chiN[j], chiP[j]);
+            const double dsfDw = sel(down, g.dsf[j], g.dsfP[j]);
+            const double dtau_b = 0.5 * zmu * (chi[j] + chiDw) * dsfDw;
+            Iupw = bcB0 - (bcB1 - bcB0) * rcp_fast(dtau_b);
+        }
+        const bool isStart = (k == ks);
+        aa = sel(isStart, 0.0, aa);
+        bb = sel(isStart, Iupw, bb);
+        pp = sel(isStart, 0.0, pp);
+        const bool valid = k < K;
+        a[j] = sel(valid, aa, 1.0);
+        b[j] = sel(valid, bb, 0.0);
+        psi[j] = sel(valid, pp * rchi[j], 0.0);
+    }
+    if (down)
+        affine_scan<NCH, true>(a, b, I);
+    else
+        affine_scan<NCH, false>(a, b, I);
+}
+
+// linear (SOLVER 0) and besser (SOLVER 1): local stencils only
+template <int NCH, int SOLVER>
+__device__ __forceinline__ void local_stencil_ray(const GeometryR<NCH>& g, const double (&chi)[NCH],
+                                                  const double (&S)[NCH], const double (&rchi)[NCH],
+                                                  double muz, bool down, int bcType, double bcB0,
+                                                  double bcB1, double bcValue, double (&I)[NCH],
+                                                  double (&psi)[NCH])
 {
     const int lane = lane_id();
     const int K = g.K;
@@ -132,287 +297,137 @@ __device__ __forceinline__ void solve_ray_r(const GeometryR<NCH>& g, const doubl
     shift_prev<NCH>(chi, chiP);
     shift_next<NCH>(S, SN);
     shift_prev<NCH>(S, SP);
-
-    if (SOLVER == 2)
+    const double zmu = (SOLVER == 0 ? 0.5 : 1.0) / muz;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
     {
-        const double zmu = 1.0 / muz;
-        // chi slopes on forward intervals and Steffen derivatives (geometry reciprocals are static)
-        double sl[NCH], slP[NCH], Df[NCH], DfN[NCH];
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
-            sl[j] = (chiN[j] - chi[j]) * (g.rdsf[j] * muz);
-        shift_prev<NCH>(sl, slP);
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
+        const int k = lane * NCH + j;
+        const bool isEnd = (k == ke);
+        const double chiUw = down ? chiP[j] : chiN[j];
+        const double chiDw = down ? chiN[j] : chiP[j];
+        const double Suw = down ? SP[j] : SN[j];
+        const double Sdw = down ? SN[j] : SP[j];
+        const double dsfUw = down ? g.dsfP[j] : g.dsf[j];
+        const double dsfDw = down ? g.dsf[j] : g.dsfP[j];
+        double aa, bb, pp;
+        if (SOLVER == 0 || isEnd)
         {
-            const int k = lane * NCH + j;
-            double d = steffen_r(g.dsf[j] * g.rsum[j], g.dsfP[j] * g.rsum[j], slP[j], sl[j]);
-            d = (k == 0) ? sl[j] : d;
-            d = (k == K - 1) ? slP[j] : d;
-            Df[j] = d;
-        }
-        shift_next<NCH>(Df, DfN);
-        double dtf[NCH], dtfP[NCH], rdtf[NCH], rdtfP[NCH];
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
-        {
-            const double ds = g.dsf[j] * zmu;
-            const double ds3 = ds * (1.0 / 3.0);
-            const double cA = fma(ds3, Df[j], chi[j]);
-            const double cB = fma(-ds3, DfN[j], chiN[j]);
-            const double t1 = chi[j] + chiN[j];
-            const double x = down ? cA : cB, y = down ? cB : cA;
-            dtf[j] = ds * ((t1 + x) + y) * 0.25;
-            rdtf[j] = rcp_fast(dtf[j]);
-        }
-        shift_prev<NCH>(dtf, dtfP);
-        shift_prev<NCH>(rdtf, rdtfP);
-        double slS[NCH], slSP[NCH], DSf[NCH], DSuw[NCH];
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
-            slS[j] = (SN[j] - S[j]) * rdtf[j];
-        shift_prev<NCH>(slS, slSP);
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
-        {
-            const int k = lane * NCH + j;
-            const double rs = rcp_fast(dtf[j] + dtfP[j]);
-            double d = steffen_r(dtf[j] * rs, dtfP[j] * rs, slSP[j], slS[j]);
-            d = (k == 0) ? slS[j] : d;
-            d = (k == K - 1) ? slSP[j] : d;
-            DSf[j] = d;
-        }
-        {
-            double tP[NCH], tN[NCH];
-            shift_prev<NCH>(DSf, tP);
-            shift_next<NCH>(DSf, tN);
-#pragma unroll
-            for (int j = 0; j < NCH; ++j)
-                DSuw[j] = down ? tP[j] : -tN[j];
-        }
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
-        {
-            const int k = lane * NCH + j;
-            const bool isEnd = (k == ke);
-            const double chiUw = down ? chiP[j] : chiN[j];
-            const double Suw = down ? SP[j] : SN[j];
-            const double dsfUw = down ? g.dsfP[j] : g.dsf[j];
-            const double dtEnd = 0.5 * zmu * (chi[j] + chiUw) * dsfUw;
-            const double dt = isEnd ? dtEnd : (down ? dtfP[j] : dtf[j]);
-            const double rdt = isEnd ? rcp_fast(dtEnd) : (down ? rdtfP[j] : rdtf[j]);
-            const bool taylor = dt < (isEnd ? 5.0E-4 : 5e-2);
-            const bool thick = dt > (isEnd ? 50.0 : 30.0);
-            double edt = (taylor || thick) ? 0.0 : exp_fast(-dt);
-            const double dt2 = dt * dt, dt3 = dt2 * dt;
-            double aa, bb, pp;
-            if (taylor && !isEnd)
+            const double dt = (SOLVER == 0 ? zmu : 0.5 * zmu) * (chi[j] + chiUw) * dsfUw;
+            const double rdt = 1.0 / dt;
+            double w0, w1;
+            if (dt < 5.0E-4)
             {
-                edt = 1.0 - dt + 0.5 * dt2 - dt3 * (1.0 / 6.0);
-                const double alpha = 0.25 * dt - 0.2 * dt2 + dt3 * (1.0 / 12.0);
-                const double beta = 0.25 * dt - 0.05 * dt2 + dt3 * (1.0 / 120.0);
-                const double gamma = 0.25 * dt - 0.15 * dt2 + 0.05 * dt3;
-                const double delta = 0.25 * dt - 0.1 * dt2 + 0.025 * dt3;
-                const double dt3rd = dt * (1.0 / 3.0);
-                const double Cuw = fma(dt3rd, DSuw[j], Suw);
-                const double C0 = down ? fma(-dt3rd, DSf[j], S[j]) : fma(dt3rd, DSf[j], S[j]);
-                aa = edt;
-                bb = alpha * Suw + beta * S[j] + gamma * Cuw + delta * C0;
-                pp = beta + delta;
+                w0 = dt * (1.0 - 0.5 * dt);
+                w1 = (dt * dt) * (0.5 - dt * (1.0 / 3.0));
             }
-            else if (!isEnd)
+            else if (dt > 50.0)
             {
-                const double rdt3 = rdt * rdt * rdt;
-                const double alpha = (6.0 - edt * (6.0 + 6.0 * dt + 3.0 * dt2 + dt3)) * rdt3;
-                const double beta = (6.0 * edt - 6.0 + 6.0 * dt - 3.0 * dt2 + dt3) * rdt3;
-                const double gamma = 3.0 * (2.0 * dt - 6.0 + edt * (6.0 + 4.0 * dt + dt2)) * rdt3;
-                const double delta = 3.0 * (6.0 - 4.0 * dt + dt2 - 2.0 * edt * (3.0 + dt)) * rdt3;
-                const double dt3rd = dt * (1.0 / 3.0);
-                const double Cuw = fma(dt3rd, DSuw[j], Suw);
-                const double C0 = down ? fma(-dt3rd, DSf[j], S[j]) : fma(dt3rd, DSf[j], S[j]);
-                aa = edt;
-                bb = alpha * Suw + beta * S[j] + gamma * Cuw + delta * C0;
-                pp = beta + delta;
+                w0 = w1 = 1.0;
             }
             else
             {
-                double w0, w1; // w2(), LwInternal.hpp:90-110
-                if (taylor)
-                {
-                    w0 = dt * (1.0 - 0.5 * dt);
-                    w1 = dt2 * (0.5 - dt * (1.0 / 3.0));
-                }
-                else if (thick)
-                {
-                    w0 = w1 = 1.0;
-                }
-                else
-                {
-                    w0 = 1.0 - edt;
-                    w1 = w0 - dt * edt;
-                }
-                const double dS = (S[j] - Suw) * rdt;
-                aa = 1.0 - w0;
-                bb = w0 * S[j] - w1 * dS;
+                const double e = exp(-dt);
+                w0 = 1.0 - e;
+                w1 = w0 - dt * e;
+            }
+            aa = 1.0 - w0;
+            if (SOLVER == 0)
+            {
+                bb = w0 * S[j] + w1 * ((Suw - S[j]) * rdt);
                 pp = w0 - w1 * rdt;
             }
-            if (k == ks)
+            else
             {
-                double Iupw = 0.0;
-                if (bcType == 2)
-                {
-                    const double chiDw = down ? chiN[j] : chiP[j];
-                    const double dsfDw = down ? g.dsf[j] : g.dsfP[j];
-                    const double dtau_b = 0.5 * zmu * (chi[j] + chiDw) * dsfDw;
-                    Iupw = bcB0 - (bcB1 - bcB0) / dtau_b;
-                }
-                else if (bcType == 4)
-                    Iupw = bcValue;
-                aa = 0.0;
-                bb = Iupw;
-                pp = 0.0;
+                bb = w0 * S[j] - w1 * ((S[j] - Suw) / dt);
+                pp = w0 - w1 / dt;
             }
-            if (k >= K)
-            {
-                aa = 1.0;
-                bb = 0.0;
-                pp = 0.0;
-            }
-            a[j] = aa;
-            b[j] = bb;
-            psi[j] = pp * rchi[j];
         }
-    }
-    else
-    {
-        // linear (SOLVER 0) and besser (SOLVER 1): local stencils only
-        const double zmu = (SOLVER == 0 ? 0.5 : 1.0) / muz;
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
+        else
         {
-            const int k = lane * NCH + j;
-            const bool isEnd = (k == ke);
-            const double chiUw = down ? chiP[j] : chiN[j];
-            const double chiDw = down ? chiN[j] : chiP[j];
-            const double Suw = down ? SP[j] : SN[j];
-            const double Sdw = down ? SN[j] : SP[j];
-            const double dsfUw = down ? g.dsfP[j] : g.dsf[j];
-            const double dsfDw = down ? g.dsf[j] : g.dsfP[j];
-            double aa, bb, pp;
-            if (SOLVER == 0 || isEnd)
+            const double ds_uw = dsfUw * zmu, ds_dw = dsfDw * zmu;
+            const double chiC = besser_control_point(ds_uw, ds_dw, chiUw, chi[j], chiDw);
+            const double dtauUw = (1.0 / 3.0) * (chiUw + chiC + chi[j]) * ds_uw;
+            const double dtauDw = 0.5 * (chi[j] + chiDw) * ds_dw;
+            const double SC = besser_control_point(dtauUw, dtauDw, Suw, S[j], Sdw);
+            const double t = dtauUw;
+            double Mc, Oc, Cc, edt;
+            if (t < 0.14)
             {
-                const double dt = (SOLVER == 0 ? zmu : 0.5 * zmu) * (chi[j] + chiUw) * dsfUw;
-                const double rdt = 1.0 / dt;
-                double w0, w1;
-                if (dt < 5.0E-4)
-                {
-                    w0 = dt * (1.0 - 0.5 * dt);
-                    w1 = (dt * dt) * (0.5 - dt * (1.0 / 3.0));
-                }
-                else if (dt > 50.0)
-                {
-                    w0 = w1 = 1.0;
-                }
-                else
-                {
-                    const double e = exp(-dt);
-                    w0 = 1.0 - e;
-                    w1 = w0 - dt * e;
-                }
-                aa = 1.0 - w0;
-                if (SOLVER == 0)
-                {
-                    bb = w0 * S[j] + w1 * ((Suw - S[j]) * rdt);
-                    pp = w0 - w1 * rdt;
-                }
-                else
-                {
-                    bb = w0 * S[j] - w1 * ((S[j] - Suw) / dt);
-                    pp = w0 - w1 / dt;
-                }
+                Mc = (t * (t * (t * (t * (t * (t * ((140.0 - 18.0 * t) * t - 945.0) + 5400.0) - 25200.0) + 90720.0) - 226800.0) + 302400.0)) / 907200.0;
+                Oc = (t * (t * (t * (t * (t * (t * ((10.0 - t) * t - 90.0) + 720.0) - 5040.0) + 30240.0) - 151200.0) + 604800.0)) / 1814400.0;
+                Cc = (t * (t * (t * (t * (t * (t * ((35.0 - 4.0 * t) * t - 270.0) + 1800.0) - 10080.0) + 45360.0) - 151200.0) + 302400.0)) / 907200.0;
+                const double t2 = t * t, t3 = t2 * t;
+                edt = 1.0 - t + 0.5 * t2 - t3 / 6.0 + t * t3 / 24.0 - t2 * t3 / 120.0 + t3 * t3 / 720.0 - t3 * t3 * t / 5040.0;
             }
             else
             {
-                const double ds_uw = dsfUw * zmu, ds_dw = dsfDw * zmu;
-                const double chiC = besser_control_point(ds_uw, ds_dw, chiUw, chi[j], chiDw);
-                const double dtauUw = (1.0 / 3.0) * (chiUw + chiC + chi[j]) * ds_uw;
-                const double dtauDw = 0.5 * (chi[j] + chiDw) * ds_dw;
-                const double SC = besser_control_point(dtauUw, dtauDw, Suw, S[j], Sdw);
-                const double t = dtauUw;
-                double M, O, C, edt;
-                if (t < 0.14)
-                {
-                    M = (t * (t * (t * (t * (t * (t * ((140.0 - 18.0 * t) * t - 945.0) + 5400.0) - 25200.0) + 90720.0) - 226800.0) + 302400.0)) / 907200.0;
-                    O = (t * (t * (t * (t * (t * (t * ((10.0 - t) * t - 90.0) + 720.0) - 5040.0) + 30240.0) - 151200.0) + 604800.0)) / 1814400.0;
-                    C = (t * (t * (t * (t * (t * (t * ((35.0 - 4.0 * t) * t - 270.0) + 1800.0) - 10080.0) + 45360.0) - 151200.0) + 302400.0)) / 907200.0;
-                    const double t2 = t * t, t3 = t2 * t;
-                    edt = 1.0 - t + 0.5 * t2 - t3 / 6.0 + t * t3 / 24.0 - t2 * t3 / 120.0 + t3 * t3 / 720.0 - t3 * t3 * t / 5040.0;
-                }
-                else
-                {
-                    const double t2 = t * t;
-                    edt = exp(-t);
-                    M = (2.0 - edt * (t2 + 2.0 * t + 2.0)) / t2;
-                    O = 1.0 - 2.0 * (edt + t - 1.0) / t2;
-                    C = 2.0 * (t - 2.0 + edt * (t + 2.0)) / t2;
-                }
-                aa = edt;
-                bb = M * Suw + O * S[j] + C * SC;
-                pp = O + C;
+                const double t2 = t * t;
+                edt = exp(-t);
+                Mc = (2.0 - edt * (t2 + 2.0 * t + 2.0)) / t2;
+                Oc = 1.0 - 2.0 * (edt + t - 1.0) / t2;
+                Cc = 2.0 * (t - 2.0 + edt * (t + 2.0)) / t2;
             }
-            if (k == ks)
-            {
-                double Iupw = 0.0;
-                if (bcType == 2)
-                {
-                    const double dtau_b = (SOLVER == 0 ? zmu : 0.5 * zmu) * (chi[j] + chiDw) * dsfDw;
-                    Iupw = bcB0 - (bcB1 - bcB0) / dtau_b;
-                }
-                else if (bcType == 4)
-                    Iupw = bcValue;
-                aa = 0.0;
-                bb = Iupw;
-                pp = 0.0;
-            }
-            if (k >= K)
-            {
-                aa = 1.0;
-                bb = 0.0;
-                pp = 0.0;
-            }
-            a[j] = aa;
-            b[j] = bb;
-            psi[j] = pp * rchi[j];
+            aa = edt;
+            bb = Mc * Suw + Oc * S[j] + Cc * SC;
+            pp = Oc + Cc;
         }
+        if (k == ks)
+        {
+            double Iupw = 0.0;
+            if (bcType == 2)
+            {
+                const double dtau_b = (SOLVER == 0 ? zmu : 0.5 * zmu) * (chi[j] + chiDw) * dsfDw;
+                Iupw = bcB0 - (bcB1 - bcB0) / dtau_b;
+            }
+            else if (bcType == 4)
+                Iupw = bcValue;
+            aa = 0.0;
+            bb = Iupw;
+            pp = 0.0;
+        }
+        if (k >= K)
+        {
+            aa = 1.0;
+            bb = 0.0;
+            pp = 0.0;
+        }
+        a[j] = aa;
+        b[j] = bb;
+        psi[j] = pp * rchi[j];
     }
+    __syncwarp();
     if (down)
         affine_scan<NCH, true>(a, b, I);
     else
         affine_scan<NCH, false>(a, b, I);
 }
 
-// per-wavelength line slot (at most two lines overlap on this kernel's wavelengths)
+// per-wavelength line slot
 struct LineSlot
 {
-    int trans;   // index into P.trans, -1: unused
+    int trans;   // index into P.trans
     int atom, li, lj;
     double v;    // hnu/4pi * Bij
     double gv;   // g * v   (without rhoPrd)
     double ugv;  // Aji/Bji * g * v
-    const double* phi; // phi(lt, 0, 0, 0) of this column
-    const double* rho; // rhoPrd(lt, 0) or nullptr
+    double wlaS; // wlambda * 4 pi / (h c)   (times wphi(k) gives wla)
+    const double* phi;  // phi(lt, 0, 0, 0) of this column
+    const double* rho;  // rhoPrd(lt, 0) or nullptr
+    const double* wphi; // wphi(0) of this column
 };
 
-template <int NCH, int SOLVER>
+template <int NCH, int SOLVER, int NL>
 __global__ void __launch_bounds__(128)
 fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi, int lambdaIterate,
            int storeDepth)
 {
     extern __shared__ double smem[];
+    constexpr int NLA = NL > 0 ? NL : 1;
     const int K = P.K, M = P.M, L = P.L, KP = P.KP;
     const int tile = tileList[blockIdx.x];
     const int col = blockIdx.y;
-    const int warp = threadIdx.x >> 5;
+    // warp index made provably warp-uniform: every loop below stays convergent
+    const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0);
     const int nwarp = blockDim.x >> 5;
     const int lane = lane_id();
 
@@ -428,13 +443,6 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
 
     GeometryR<NCH> g;
     load_geometry_r<NCH>(g, P.height + (size_t)col * K, K);
-    double rT[NCH];
-#pragma unroll
-    for (int j = 0; j < NCH; ++j)
-    {
-        const int k = lane * NCH + j;
-        rT[j] = (k < K) ? 1.0 / __ldg(P.temperature + (size_t)col * K + k) : 1.0;
-    }
     const double* Tcol = P.temperature + (size_t)col * K;
     const double* ncol = P.n + (size_t)col * P.NlevTot * K;
 
@@ -444,15 +452,19 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
     for (int la = laBeg + warp; la < laEnd; la += nwarp)
     {
         const double lambda = __ldg(P.wavelength + la);
+        const double rlambda = 1.0 / lambda;
         const size_t rowLK = ((size_t)col * L + la) * K;
         const int eBeg = P.laOff[la], eEnd = P.laOff[la + 1];
         constexpr double hc_k = kHC / (kKBoltzmann * kNmToM);
         constexpr double twoHc = 2.0 * kHC / (kNmToM * kNmToM * kNmToM);
         constexpr double hc_4pi = 0.25 * kHC / kPi;
-        const double hc_kl = hc_k / lambda;
-        const double hcl = twoHc / (lambda * lambda * lambda);
+        constexpr double pi4_h = 4.0 * kPi / kHPlanck;
+        constexpr double pi4_hc = 1.0 / hc_4pi;
+        const double hc_kl = hc_k * rlambda;
+        const double hcl = twoHc * (rlambda * rlambda * rlambda);
 
-        // ---- ray-independent: background + continua
+        // ---- ray-independent: background + continua (generalises the reference's
+        //      continuaOnly shortcut, :295-307)
         double chiC[NCH], etaC[NCH], scaJ[NCH], expfac[NCH];
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
@@ -464,20 +476,26 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
             const double sca = v ? __ldg(P.scaBg + rowLK + k) : 0.0;
             const double JDag = v ? P.J[rowLK + k] : 0.0;
             scaJ[j] = sca * JDag;
-            expfac[j] = exp_fast(-hc_kl * rT[j]);
+            const double Tk = v ? __ldg(Tcol + k) : 1.0e4;
+            expfac[j] = exp_fast(-hc_kl / Tk);
         }
-        LineSlot ls[2];
-        ls[0].trans = ls[1].trans = -1;
-        ls[0].phi = ls[1].phi = nullptr;
-        ls[0].rho = ls[1].rho = nullptr;
-        ls[0].atom = ls[1].atom = -1;
-        int nL = 0;
-        double cX[2][NCH], cE[2][NCH];
+        LineSlot ls[NLA];
+        double cX[NLA][NCH], cE[NLA][NCH];
 #pragma unroll
-        for (int l = 0; l < 2; ++l)
+        for (int l = 0; l < NLA; ++l)
+        {
+            ls[l].trans = -1;
+            ls[l].atom = -1;
+            ls[l].li = ls[l].lj = 0;
+            ls[l].v = ls[l].gv = ls[l].ugv = ls[l].wlaS = 0.0;
+            ls[l].phi = P.phi;
+            ls[l].rho = nullptr;
+            ls[l].wphi = P.wphi;
 #pragma unroll
             for (int j = 0; j < NCH; ++j)
                 cX[l][j] = cE[l][j] = 0.0;
+        }
+        int nLseen = 0;
 
         for (int e = eBeg; e < eEnd; ++e)
         {
@@ -486,38 +504,42 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
             const int lt = la - t.Nblue;
             if (t.type == 0)
             {
-                // line: constants of Transition::uv (LwTransition.hpp:93-130)
-                const double vB = hc_4pi * (t.lambda0 / lambda) * t.Bij;
-                const double gS = t.Bji_Bij;
-                const double* rho = (t.rhoOff >= 0)
-                    ? P.rhoPrd + t.rhoOff + ((size_t)col * (t.Nred - t.Nblue) + lt) * K : nullptr;
-                const int l = nL++;
-                // nL <= 2 guaranteed by the planner for this kernel
-#pragma unroll
-                for (int q = 0; q < 2; ++q)
+                if (NL > 0)
                 {
-                    if (q == l)
-                    {
-                        ls[q].trans = ti;
-                        ls[q].atom = t.atom;
-                        ls[q].li = t.i;
-                        ls[q].lj = t.j;
-                        ls[q].v = vB;
-                        ls[q].gv = gS * vB;
-                        ls[q].ugv = t.Aji_Bji * (gS * vB);
-                        ls[q].phi = P.phi + t.phiOff + (size_t)col * t.phiColStride + (size_t)lt * M * 2 * K;
-                        ls[q].rho = rho;
+                    // line: constants of Transition::uv (LwTransition.hpp:93-130)
+                    const double vB = hc_4pi * (t.lambda0 * rlambda) * t.Bij;
+                    const double gS = t.Bji_Bij;
+                    const double* rho = (t.rhoOff >= 0)
+                        ? P.rhoPrd + t.rhoOff + ((size_t)col * (t.Nred - t.Nblue) + lt) * K : nullptr;
+                    const int l = nLseen++;
 #pragma unroll
-                        for (int j = 0; j < NCH; ++j)
+                    for (int q = 0; q < NLA; ++q)
+                    {
+                        if (q == l)
                         {
-                            const int k = lane * NCH + j;
-                            if (k < K)
+                            ls[q].trans = ti;
+                            ls[q].atom = t.atom;
+                            ls[q].li = t.i;
+                            ls[q].lj = t.j;
+                            ls[q].v = vB;
+                            ls[q].gv = gS * vB;
+                            ls[q].ugv = t.Aji_Bji * (gS * vB);
+                            ls[q].wlaS = __ldg(P.wlambdaTab + t.tabOff + lt) * pi4_hc;
+                            ls[q].phi = P.phi + t.phiOff + (size_t)col * t.phiColStride + (size_t)lt * M * 2 * K;
+                            ls[q].rho = rho;
+                            ls[q].wphi = P.wphi + ((size_t)t.lineIdx * P.Ncol + col) * K;
+#pragma unroll
+                            for (int j = 0; j < NCH; ++j)
                             {
-                                const double ni = __ldg(ncol + (size_t)t.levI * K + k);
-                                const double nj = __ldg(ncol + (size_t)t.levJ * K + k);
-                                const double gk = rho ? gS * __ldg(rho + k) : gS;
-                                cX[q][j] = vB * (ni - nj * gk);
-                                cE[q][j] = nj * (t.Aji_Bji * (gk * vB));
+                                const int k = lane * NCH + j;
+                                if (k < K)
+                                {
+                                    const double ni = __ldg(ncol + (size_t)t.levI * K + k);
+                                    const double nj = __ldg(ncol + (size_t)t.levJ * K + k);
+                                    const double gk = rho ? gS * __ldg(rho + k) : gS;
+                                    cX[q][j] = vB * (ni - nj * gk);
+                                    cE[q][j] = nj * (t.Aji_Bji * (gk * vB));
+                                }
                             }
                         }
                     }
@@ -558,49 +580,72 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
         }
 
         // ---- moments over the rays of this wavelength
-        double mJ[NCH], mP[NCH], mW[2][NCH], mA[2][NCH], mB0[2][NCH], mB[2][NCH], mB01[NCH];
+        double mJ[NCH], mP[NCH], mW[NLA][NCH], mA[NLA][NCH], mB0[NLA][NCH], mB[NLA][NCH], mB01[NCH];
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
         {
             mJ[j] = mP[j] = mB01[j] = 0.0;
 #pragma unroll
-            for (int l = 0; l < 2; ++l)
+            for (int l = 0; l < NLA; ++l)
                 mW[l][j] = mA[l][j] = mB0[l][j] = mB[l][j] = 0.0;
         }
         double W0 = 0.0;
+        double chi[NCH], S[NCH], rchi[NCH];
+        const double* ph[NLA];
+#pragma unroll
+        for (int l = 0; l < NLA; ++l)
+            ph[l] = ls[l].phi + lane * NCH;
 
         for (int ray = 0; ray < 2 * M; ++ray)
         {
             const int mu = ray >> 1, dir = ray & 1;
             const double muz = __ldg(P.muz + mu);
             const double w = 0.5 * __ldg(P.wmu + mu);
-            double chi[NCH], S[NCH], rchi[NCH], p0[NCH], p1[NCH];
-#pragma unroll
-            for (int j = 0; j < NCH; ++j)
+            double p[NLA][NCH];
+            if (NL > 0 || ray == 0)
             {
-                const int k = lane * NCH + j;
-                double c = chiC[j], e = etaC[j];
-                p0[j] = p1[j] = 0.0;
-                if (nL > 0 && k < K)
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
                 {
-                    p0[j] = __ldg(ls[0].phi + (size_t)(mu * 2 + dir) * K + k);
-                    c = fma(cX[0][j], p0[j], c);
-                    e = fma(cE[0][j], p0[j], e);
+                    const int k = lane * NCH + j;
+                    double c = chiC[j], e = etaC[j];
+#pragma unroll
+                    for (int l = 0; l < NLA; ++l)
+                    {
+                        p[l][j] = 0.0;
+                        if (NL > 0)
+                        {
+                            p[l][j] = (k < K) ? __ldg(ph[l] + j) : 0.0;
+                            c = fma(cX[l][j], p[l][j], c);
+                            e = fma(cE[l][j], p[l][j], e);
+                        }
+                    }
+                    chi[j] = c;
+                    rchi[j] = rcp_fast(c);
+                    S[j] = (e + scaJ[j]) * rchi[j]; // compute_source_fn (:169-179)
+                    if (storeDepth && k < K)
+                    {
+                        const size_t off = ((((size_t)col * L + la) * M + mu) * 2 + dir) * K + k;
+                        P.depthChi[off] = c;
+                        P.depthEta[off] = e;
+                    }
                 }
-                if (nL > 1 && k < K)
+#pragma unroll
+                for (int l = 0; l < NLA; ++l)
+                    ph[l] += K;
+            }
+            else if (storeDepth)
+            {
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
                 {
-                    p1[j] = __ldg(ls[1].phi + (size_t)(mu * 2 + dir) * K + k);
-                    c = fma(cX[1][j], p1[j], c);
-                    e = fma(cE[1][j], p1[j], e);
-                }
-                chi[j] = c;
-                rchi[j] = rcp_fast(c);
-                S[j] = (e + scaJ[j]) * rchi[j];
-                if (storeDepth && k < K)
-                {
-                    const size_t off = ((((size_t)col * L + la) * M + mu) * 2 + dir) * K + k;
-                    P.depthChi[off] = c;
-                    P.depthEta[off] = e;
+                    const int k = lane * NCH + j;
+                    if (k < K)
+                    {
+                        const size_t off = ((((size_t)col * L + la) * M + mu) * 2 + dir) * K + k;
+                        P.depthChi[off] = chiC[j];
+                        P.depthEta[off] = etaC[j];
+                    }
                 }
             }
             int bcType;
@@ -622,7 +667,10 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
                     bcValue = P.upperBcData[((size_t)col * L + la) * P.NupperBcMu + P.upperBcIdx[mu * 2 + 0]];
             }
             double I[NCH], psi[NCH];
-            solve_ray_r<NCH, SOLVER>(g, chi, S, rchi, muz, dir == 0, bcType, bcB0, bcB1, bcValue, I, psi);
+            if (SOLVER == 2)
+                bezier3_ray<NCH>(g, chi, S, rchi, muz, dir == 0, bcType, bcB0, bcB1, bcValue, I, psi);
+            else
+                local_stencil_ray<NCH, SOLVER>(g, chi, S, rchi, muz, dir == 0, bcType, bcB0, bcB1, bcValue, I, psi);
 
             if (lane == 0)
                 P.I[((size_t)col * L + la) * M + mu] = I[0];
@@ -637,17 +685,21 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
                 const double wP = lambdaIterate ? 0.0 : w * psi[j];
                 mJ[j] += wI;
                 mP[j] += wP;
-                const double t0 = wP * p0[j];
-                mW[0][j] = fma(w, p0[j], mW[0][j]);
-                mA[0][j] = fma(wI, p0[j], mA[0][j]);
-                mB0[0][j] += t0;
-                mB[0][j] = fma(t0, p0[j], mB[0][j]);
-                const double t1 = wP * p1[j];
-                mW[1][j] = fma(w, p1[j], mW[1][j]);
-                mA[1][j] = fma(wI, p1[j], mA[1][j]);
-                mB0[1][j] += t1;
-                mB[1][j] = fma(t1, p1[j], mB[1][j]);
-                mB01[j] = fma(t0, p1[j], mB01[j]);
+                if (NL > 0)
+                {
+                    double tq[NLA];
+#pragma unroll
+                    for (int l = 0; l < NLA; ++l)
+                    {
+                        tq[l] = wP * p[l][j];
+                        mW[l][j] = fma(w, p[l][j], mW[l][j]);
+                        mA[l][j] = fma(wI, p[l][j], mA[l][j]);
+                        mB0[l][j] += tq[l];
+                        mB[l][j] = fma(tq[l], p[l][j], mB[l][j]);
+                    }
+                    if (NL > 1)
+                        mB01[j] = fma(tq[0], p[NLA - 1][j], mB01[j]);
+                }
             }
         }
 
@@ -684,129 +736,158 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
                 ++e1;
             const bool detailed = P.atomDetailed[atom] != 0;
             const int N = P.atomNlevel[atom];
-            const bool own0 = (nL > 0) && ls[0].atom == atom;
-            const bool own1 = (nL > 1) && ls[1].atom == atom;
+            const bool own0 = (NL > 0) && ls[0].atom == atom;
+            const bool own1 = (NL > 1) && ls[NLA - 1].atom == atom;
 #pragma unroll
             for (int j = 0; j < NCH; ++j)
             {
                 const int k = lane * NCH + j;
-                if (k >= K)
-                    continue;
-                double E0 = 0.0;
-                if (!detailed)
+                if (k < K)
                 {
-                    // continuum aggregates per level: chi_atom / U_atom of chi_eta_aux_accum (:59-109)
-                    for (int m = 0; m < N; ++m)
-                    {
-                        Xs[m * 32 + lane] = 0.0;
-                        Us[m * 32 + lane] = 0.0;
-                    }
-                    for (int e = e0; e < e1; ++e)
-                    {
-                        const DevTrans& t = P.trans[P.entries[e].trans];
-                        if (t.type == 0)
-                            continue;
-                        const double al = __ldg(P.alphaTab + t.tabOff + (la - t.Nblue));
-                        const double gk = __ldg(P.gRatio + ((size_t)t.contIdx * P.Ncol + col) * K + k) * expfac[j];
-                        const double Vji = gk * al;
-                        const double Uji = hcl * Vji;
-                        const double ni = __ldg(ncol + (size_t)t.levI * K + k);
-                        const double nj = __ldg(ncol + (size_t)t.levJ * K + k);
-                        const double x = ni * al - nj * Vji;
-                        Xs[t.i * 32 + lane] += x;
-                        Xs[t.j * 32 + lane] -= x;
-                        Us[t.j * 32 + lane] += Uji;
-                        E0 += nj * Uji;
-                    }
-                }
-                // line profile members of this atom: per-unit-phi coefficients
-                double gv0 = 0.0, ugv0 = 0.0, gv1 = 0.0, ugv1 = 0.0;
-                if (own0)
-                {
-                    const double r = ls[0].rho ? __ldg(ls[0].rho + k) : 1.0;
-                    gv0 = ls[0].gv * r;
-                    ugv0 = ls[0].ugv * r;
-                }
-                if (own1)
-                {
-                    const double r = ls[1].rho ? __ldg(ls[1].rho + k) : 1.0;
-                    gv1 = ls[1].gv * r;
-                    ugv1 = ls[1].ugv * r;
-                }
-                const double X0l = own0 ? cX[0][j] : 0.0, E0l = own0 ? cE[0][j] : 0.0;
-                const double X1l = own1 ? cX[1][j] : 0.0, E1l = own1 ? cE[1][j] : 0.0;
-                // sum_q' E_q' M(q, q') for q = continuum, line0, line1
-                const double EBc = E0 * mP[j] + E0l * mB0[0][j] + E1l * mB0[1][j];
-                const double EB0 = E0 * mB0[0][j] + E0l * mB[0][j] + E1l * mB01[j];
-                const double EB1 = E0 * mB0[1][j] + E0l * mB01[j] + E1l * mB[1][j];
-
-                for (int e = e0; e < e1; ++e)
-                {
-                    const DevEntry en = P.entries[e];
-                    const DevTrans& t = P.trans[en.trans];
-                    const int lt = la - t.Nblue;
-                    // profile member of this transition: 0 continuum, 1 line slot 0, 2 line slot 1
-                    const int q = (t.type != 0) ? 0 : (en.trans == ls[0].trans ? 1 : 2);
-                    double v, gv, ugv, Wq, Aq, EBq;
-                    if (q == 0)
-                    {
-                        const double al = __ldg(P.alphaTab + t.tabOff + lt);
-                        const double gk = __ldg(P.gRatio + ((size_t)t.contIdx * P.Ncol + col) * K + k) * expfac[j];
-                        v = al;
-                        gv = gk * al;
-                        ugv = hcl * gv;
-                        Wq = W0;
-                        Aq = mJ[j];
-                        EBq = EBc;
-                    }
-                    else if (q == 1)
-                    {
-                        v = ls[0].v;
-                        gv = gv0;
-                        ugv = ugv0;
-                        Wq = mW[0][j];
-                        Aq = mA[0][j];
-                        EBq = EB0;
-                    }
-                    else
-                    {
-                        v = ls[1].v;
-                        gv = gv1;
-                        ugv = ugv1;
-                        Wq = mW[1][j];
-                        Aq = mA[1][j];
-                        EBq = EB1;
-                    }
-                    const double wla = trans_wla(P, t, col, lt, k, lambda);
-                    double* a4 = acc + (size_t)en.slot * 4 * KP + k;
+                    double E0 = 0.0;
                     if (!detailed)
                     {
-                        // chi_atom(m) = Xc(m) + p0 X0l s0(m) + p1 X1l s1(m);  U_atom(m) = Uc(m) + p0 ugv0 [m==lj0] + ...
-                        const double Xci = Xs[t.i * 32 + lane], Xcj = Xs[t.j * 32 + lane];
-                        const double Uci = Us[t.i * 32 + lane], Ucj = Us[t.j * 32 + lane];
-                        const double X0i = own0 ? (t.i == ls[0].li ? X0l : (t.i == ls[0].lj ? -X0l : 0.0)) : 0.0;
-                        const double X0j = own0 ? (t.j == ls[0].li ? X0l : (t.j == ls[0].lj ? -X0l : 0.0)) : 0.0;
-                        const double X1i = own1 ? (t.i == ls[1].li ? X1l : (t.i == ls[1].lj ? -X1l : 0.0)) : 0.0;
-                        const double X1j = own1 ? (t.j == ls[1].li ? X1l : (t.j == ls[1].lj ? -X1l : 0.0)) : 0.0;
-                        const double U0i = (own0 && t.i == ls[0].lj) ? ugv0 : 0.0;
-                        const double U0j = (own0 && t.j == ls[0].lj) ? ugv0 : 0.0;
-                        const double U1i = (own1 && t.i == ls[1].lj) ? ugv1 : 0.0;
-                        const double U1j = (own1 && t.j == ls[1].lj) ? ugv1 : 0.0;
-                        // sum_r w Psi chi_atom(a) U_atom(b) = sum_{q',q''} X_q'(a) U_q''(b) M(q',q'')
-                        const double XUij =
-                            Xci * (Ucj * mP[j] + U0j * mB0[0][j] + U1j * mB0[1][j])
-                            + X0i * (Ucj * mB0[0][j] + U0j * mB[0][j] + U1j * mB01[j])
-                            + X1i * (Ucj * mB0[1][j] + U0j * mB01[j] + U1j * mB[1][j]);
-                        const double XUji =
-                            Xcj * (Uci * mP[j] + U0i * mB0[0][j] + U1i * mB0[1][j])
-                            + X0j * (Uci * mB0[0][j] + U0i * mB[0][j] + U1i * mB01[j])
-                            + X1j * (Uci * mB0[1][j] + U0i * mB01[j] + U1i * mB[1][j]);
-                        // sum_r w [(Uji + Vji Ieff) - Psi chi(i) U(j)],  Ieff = I - Psi eta_atom
-                        smem_add(a4, (ugv * Wq + gv * (Aq - EBq) - XUij) * wla);
-                        smem_add(a4 + KP, (v * (Aq - EBq) - XUji) * wla);
+                        // continuum aggregates per level: chi_atom / U_atom of chi_eta_aux_accum (:59-109)
+                        for (int m = 0; m < N; ++m)
+                        {
+                            Xs[m * 32 + lane] = 0.0;
+                            Us[m * 32 + lane] = 0.0;
+                        }
+                        for (int e = e0; e < e1; ++e)
+                        {
+                            const DevTrans& t = P.trans[P.entries[e].trans];
+                            if (t.type == 0)
+                                continue;
+                            const double al = __ldg(P.alphaTab + t.tabOff + (la - t.Nblue));
+                            const double gk = __ldg(P.gRatio + ((size_t)t.contIdx * P.Ncol + col) * K + k) * expfac[j];
+                            const double Vji = gk * al;
+                            const double Uji = hcl * Vji;
+                            const double ni = __ldg(ncol + (size_t)t.levI * K + k);
+                            const double nj = __ldg(ncol + (size_t)t.levJ * K + k);
+                            const double x = ni * al - nj * Vji;
+                            Xs[t.i * 32 + lane] += x;
+                            Xs[t.j * 32 + lane] -= x;
+                            Us[t.j * 32 + lane] += Uji;
+                            E0 += nj * Uji;
+                        }
                     }
-                    smem_add(a4 + 2 * KP, (v * Aq) * wla);
-                    smem_add(a4 + 3 * KP, (ugv * Wq + gv * Aq) * wla);
+                    // line members of this atom: per-unit-phi coefficients
+                    double gv0 = 0.0, ugv0 = 0.0, gv1 = 0.0, ugv1 = 0.0;
+                    double X0l = 0.0, E0l = 0.0, X1l = 0.0, E1l = 0.0;
+                    double B00 = 0.0, Bs0 = 0.0, B11 = 0.0, Bs1 = 0.0, B01 = 0.0;
+                    if (NL > 0)
+                    {
+                        Bs0 = mB0[0][j];
+                        B00 = mB[0][j];
+                        if (own0)
+                        {
+                            const double r = ls[0].rho ? __ldg(ls[0].rho + k) : 1.0;
+                            gv0 = ls[0].gv * r;
+                            ugv0 = ls[0].ugv * r;
+                            X0l = cX[0][j];
+                            E0l = cE[0][j];
+                        }
+                    }
+                    if (NL > 1)
+                    {
+                        Bs1 = mB0[NLA - 1][j];
+                        B11 = mB[NLA - 1][j];
+                        B01 = mB01[j];
+                        if (own1)
+                        {
+                            const double r = ls[NLA - 1].rho ? __ldg(ls[NLA - 1].rho + k) : 1.0;
+                            gv1 = ls[NLA - 1].gv * r;
+                            ugv1 = ls[NLA - 1].ugv * r;
+                            X1l = cX[NLA - 1][j];
+                            E1l = cE[NLA - 1][j];
+                        }
+                    }
+                    // sum_q' E_q' M(q, q') for q = continuum, line0, line1
+                    const double EBc = E0 * mP[j] + E0l * Bs0 + E1l * Bs1;
+                    const double EB0 = E0 * Bs0 + E0l * B00 + E1l * B01;
+                    const double EB1 = E0 * Bs1 + E0l * B01 + E1l * B11;
+
+                    for (int e = e0; e < e1; ++e)
+                    {
+                        const DevEntry en = P.entries[e];
+                        const DevTrans& t = P.trans[en.trans];
+                        const int lt = la - t.Nblue;
+                        // profile member of this transition: 0 continuum, 1 line slot 0, 2 line slot 1
+                        const int q = (t.type != 0) ? 0 : ((NL < 2 || en.trans == ls[0].trans) ? 1 : 2);
+                        double v, gv, ugv, Wq, Aq, EBq, wla;
+                        if (q == 0)
+                        {
+                            const double al = __ldg(P.alphaTab + t.tabOff + lt);
+                            const double gk = __ldg(P.gRatio + ((size_t)t.contIdx * P.Ncol + col) * K + k) * expfac[j];
+                            v = al;
+                            gv = gk * al;
+                            ugv = hcl * gv;
+                            Wq = W0;
+                            Aq = mJ[j];
+                            EBq = EBc;
+                            wla = (__ldg(P.wlambdaTab + t.tabOff + lt) * rlambda) * pi4_h;
+                        }
+                        else if (q == 1)
+                        {
+                            v = ls[0].v;
+                            gv = gv0;
+                            ugv = ugv0;
+                            Wq = mW[0][j];
+                            Aq = mA[0][j];
+                            EBq = EB0;
+                            wla = ls[0].wlaS * __ldg(ls[0].wphi + k);
+                        }
+                        else
+                        {
+                            v = ls[NLA - 1].v;
+                            gv = gv1;
+                            ugv = ugv1;
+                            Wq = mW[NLA - 1][j];
+                            Aq = mA[NLA - 1][j];
+                            EBq = EB1;
+                            wla = ls[NLA - 1].wlaS * __ldg(ls[NLA - 1].wphi + k);
+                        }
+                        double* a4 = acc + (size_t)en.slot * 4 * KP + k;
+                        if (!detailed)
+                        {
+                            const double Xci = Xs[t.i * 32 + lane], Xcj = Xs[t.j * 32 + lane];
+                            const double Uci = Us[t.i * 32 + lane], Ucj = Us[t.j * 32 + lane];
+                            double XUij = Xci * Ucj * mP[j];
+                            double XUji = Xcj * Uci * mP[j];
+                            if (NL > 0 && own0)
+                            {
+                                const double X0i = t.i == ls[0].li ? X0l : (t.i == ls[0].lj ? -X0l : 0.0);
+                                const double X0j = t.j == ls[0].li ? X0l : (t.j == ls[0].lj ? -X0l : 0.0);
+                                const double U0i = t.i == ls[0].lj ? ugv0 : 0.0;
+                                const double U0j = t.j == ls[0].lj ? ugv0 : 0.0;
+                                XUij += Xci * U0j * Bs0 + X0i * (Ucj * Bs0 + U0j * B00);
+                                XUji += Xcj * U0i * Bs0 + X0j * (Uci * Bs0 + U0i * B00);
+                                if (NL > 1 && own1)
+                                {
+                                    const double X1i = t.i == ls[NLA - 1].li ? X1l : (t.i == ls[NLA - 1].lj ? -X1l : 0.0);
+                                    const double X1j = t.j == ls[NLA - 1].li ? X1l : (t.j == ls[NLA - 1].lj ? -X1l : 0.0);
+                                    const double U1i = t.i == ls[NLA - 1].lj ? ugv1 : 0.0;
+                                    const double U1j = t.j == ls[NLA - 1].lj ? ugv1 : 0.0;
+                                    XUij += X0i * U1j * B01 + X1i * U0j * B01;
+                                    XUji += X0j * U1i * B01 + X1j * U0i * B01;
+                                }
+                            }
+                            if (NL > 1 && own1)
+                            {
+                                const double X1i = t.i == ls[NLA - 1].li ? X1l : (t.i == ls[NLA - 1].lj ? -X1l : 0.0);
+                                const double X1j = t.j == ls[NLA - 1].li ? X1l : (t.j == ls[NLA - 1].lj ? -X1l : 0.0);
+                                const double U1i = t.i == ls[NLA - 1].lj ? ugv1 : 0.0;
+                                const double U1j = t.j == ls[NLA - 1].lj ? ugv1 : 0.0;
+                                XUij += Xci * U1j * Bs1 + X1i * (Ucj * Bs1 + U1j * B11);
+                                XUji += Xcj * U1i * Bs1 + X1j * (Uci * Bs1 + U1i * B11);
+                            }
+                            // sum_r w [(Uji + Vji Ieff) - Psi chi(i) U(j)],  Ieff = I - Psi eta_atom
+                            smem_add(a4, (ugv * Wq + gv * (Aq - EBq) - XUij) * wla);
+                            smem_add(a4 + KP, (v * (Aq - EBq) - XUji) * wla);
+                        }
+                        smem_add(a4 + 2 * KP, (v * Aq) * wla);
+                        smem_add(a4 + 3 * KP, (ugv * Wq + gv * Aq) * wla);
+                    }
                 }
             }
             e0 = e1;
