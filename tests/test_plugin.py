@@ -1,0 +1,121 @@
+"""The Lightweaver plugin shim (liblwb200_plugin.so): the drop-in boundary.
+
+The reference's own compiled core (oracle/_ref, driven by oracle/ref_harness.cpp)
+loads the shim through ITS plugin manager
+(FsIterationFnsManager::load_fns_from_path, Source/FormalInterface.cpp:62-81) and
+calls ITS entry points formal_sol_gamma_matrices / formal_sol / stat_eq
+(Source/Lightweaver.hpp:21-32) -- once with the built-in scalar scheme, once with
+`mali_full_precond_B200`.  Results must agree to the parity bar."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from lightweaver_b200 import capi, synth
+from oracle import reflib
+from tests.util import compare_problems, rel_err
+
+PLUGIN = os.path.join(os.path.dirname(capi.lib_path()), 'liblwb200_plugin.so')
+needs_plugin = pytest.mark.skipif(not os.path.exists(PLUGIN), reason='plugin shim not built (needs /root/reference)')
+
+
+@needs_plugin
+def test_plugin_exports_provider_symbols():
+    lib = ctypes.CDLL(PLUGIN)
+    assert hasattr(lib, 'fs_iteration_fns_provider')
+    assert hasattr(lib, 'fs_provider')
+
+
+@needs_plugin
+@pytest.mark.ref
+def test_reference_plugin_manager_loads_the_scheme():
+    import torch
+    p = synth.tiny_problem()
+    if torch.cuda.is_available():
+        r = reflib.RefContext(p, scheme=PLUGIN)
+        assert r.scheme_name == 'mali_full_precond_B200'
+        r.close()
+    else:
+        # no GPU: loading works, the first device call raises (no CPU fallback)
+        r = reflib.RefContext(p, scheme=PLUGIN)
+        assert r.scheme_name == 'mali_full_precond_B200'
+        with pytest.raises(RuntimeError):
+            r.fs_iter()
+        r.close()
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.gpu
+@pytest.mark.parametrize('solver', [capi.FS_BEZIER3, capi.FS_BESSER, capi.FS_LINEAR])
+def test_reference_core_with_b200_scheme_matches_scalar_scheme(solver):
+    p = synth.config_c1(formal_solver=solver, nl=0.5)
+    q = p.clone()
+    gpu = reflib.RefContext(p, scheme=PLUGIN)
+    cpu = reflib.RefContext(q, scheme='scalar')
+    for it in range(3):
+        p.prefill_gamma()
+        q.prefill_gamma()
+        a = gpu.fs_iter(lambdaIterate=(it == 0))
+        b = cpu.fs_iter(lambdaIterate=(it == 0))
+        assert abs(a[0] - b[0]) <= 1e-9 * max(b[0], 1.0)
+        e = compare_problems(p, q)
+        assert e['I'] <= 1e-9 and e['J'] <= 1e-9 and e['Gamma'] <= 1e-9 and e['R'] <= 1e-9, e
+        gpu.stat_eq()
+        cpu.stat_eq()
+        assert compare_problems(p, q)['n'] <= 1e-8
+    # formal_sol (compute_rays path) through the plugin's simple_fs
+    p.I[:] = 0.0
+    gpu.formal_sol(upOnly=True)
+    cpu.formal_sol(upOnly=True)
+    assert rel_err(p.I, q.I) <= 1e-9
+    gpu.close()
+    cpu.close()
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.gpu
+def test_plugin_sees_in_place_host_mutations():
+    """Python mutates buffers in place between calls without telling the plugin
+    (update_deps, Ng acceleration): the shim's fingerprints must notice."""
+    p = synth.tiny_problem()
+    q = p.clone()
+    gpu = reflib.RefContext(p, scheme=PLUGIN)
+    cpu = reflib.RefContext(q, scheme='scalar')
+    for prob, ctx in ((p, gpu), (q, cpu)):
+        prob.prefill_gamma()
+        ctx.fs_iter()
+        ctx.stat_eq()
+    # "update_deps": new temperature-dependent background and profiles, populations nudged
+    for prob in (p, q):
+        prob.chiBg *= 1.07
+        prob.etaBg *= 0.93
+        t = prob.atoms[0].trans[0]
+        t.phi *= 1.01
+        t.wphi /= 1.01
+        prob.atoms[0].n *= 1.0 + 0.01 * np.linspace(-1, 1, prob.Nspace)
+        prob.J *= 1.02
+    for prob, ctx in ((p, gpu), (q, cpu)):
+        prob.prefill_gamma()
+        ctx.fs_iter()
+    e = compare_problems(p, q)
+    assert e['I'] <= 1e-9 and e['J'] <= 1e-9 and e['Gamma'] <= 1e-9, e
+    gpu.close()
+    cpu.close()
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.gpu
+def test_plugin_singular_matrix_is_a_runtime_error():
+    p = synth.tiny_problem()
+    gpu = reflib.RefContext(p, scheme=PLUGIN)
+    p.prefill_gamma()
+    gpu.fs_iter()
+    p.atoms[0].Gamma[0, 1:, :, 10] = 0.0
+    p.atoms[0].n[0, :, 10] = [4.0, 3.0, 2.0, 1.0]  # eliminated row is level 0; rows 1..3 all zero
+    with pytest.raises(RuntimeError, match='Singular Matrix'):
+        gpu.stat_eq()
+    gpu.close()
