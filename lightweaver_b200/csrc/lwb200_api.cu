@@ -124,8 +124,8 @@ struct LwB200Context
     std::vector<DevTrans> devTrans;
     std::vector<int> atomNlevel, atomLevOff, atomGammaOff, atomDetailed;
     std::vector<int> tileLa, tileSlotOff, tileSlotTrans, tileKind;
-    DevBuf<int> dListNL[3], dListDirect, dListAll;
-    int nListNL[3] = {0, 0, 0}, nListDirect = 0, nListAll = 0, listLo = -1, listHi = -1;
+    DevBuf<int> dListNL[4], dListDirect, dListAll;
+    int nListNL[4] = {0, 0, 0, 0}, nListDirect = 0, nListAll = 0, listLo = -1, listHi = -1;
     int Ntile = 0;
     int nwarps = 4;
     int laLo = 0, laHi = 0;
@@ -250,7 +250,8 @@ int build_plan(LwB200Context* c)
             }
         }
     // wavelengths with more than two overlapping lines go to the general kernel
-    auto kind_of = [&](int la) { return laNLines[la] > 2 ? 3 : laNLines[la]; };
+    // kinds 0..3: that many overlapping lines, moment kernel; 4: more, general kernel
+    auto kind_of = [&](int la) { return laNLines[la] > 3 ? 4 : laNLines[la]; };
 
     // tiles: runs of wavelengths whose union of active transitions fits the
     // shared-memory accumulator; sized so that the grid fills the GPU
@@ -449,17 +450,17 @@ int refresh_tile_lists(LwB200Context* c)
 {
     if (c->listLo == c->laLo && c->listHi == c->laHi)
         return 0;
-    std::vector<int> mom[3], dir, all;
+    std::vector<int> mom[4], dir, all;
     for (int t = 0; t < c->Ntile; ++t)
     {
         if (c->tileLa[t + 1] <= c->laLo || c->tileLa[t] >= c->laHi)
             continue;
         all.push_back(t);
-        (c->tileKind[t] < 3 ? mom[c->tileKind[t]] : dir).push_back(t);
+        (c->tileKind[t] < 4 ? mom[c->tileKind[t]] : dir).push_back(t);
     }
     c->dListDirect.release();
     c->dListAll.release();
-    for (int q = 0; q < 3; ++q)
+    for (int q = 0; q < 4; ++q)
     {
         c->dListNL[q].release();
         if (c->dListNL[q].upload(mom[q]))
@@ -519,6 +520,17 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
                 return 1;
             dim3 grid(c->nListNL[2], c->prob.Ncol);
             kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListNL[2].p, c->laLo, c->laHi,
+                                                             lambdaIterate, storeDepth);
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
+        }
+        if (c->nListNL[3] > 0)
+        {
+            auto kern = fsm_kernel<NCH, SOLVER, 3>;
+            if (set_smem_attr(kern, c->device))
+                return 1;
+            dim3 grid(c->nListNL[3], c->prob.Ncol);
+            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListNL[3].p, c->laLo, c->laHi,
                                                              lambdaIterate, storeDepth);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
@@ -707,7 +719,7 @@ int lwb200_destroy(LwB200Context* c)
         cudaEventDestroy(c->evK0);
     if (c->evK1)
         cudaEventDestroy(c->evK1);
-    for (int q = 0; q < 3; ++q)
+    for (int q = 0; q < 4; ++q)
         c->dListNL[q].release();
     c->dListDirect.release();
     c->dListAll.release();

@@ -580,14 +580,20 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
         }
 
         // ---- moments over the rays of this wavelength
-        double mJ[NCH], mP[NCH], mW[NLA][NCH], mA[NLA][NCH], mB0[NLA][NCH], mB[NLA][NCH], mB01[NCH];
+        //   mJ = sum w I, mP = sum w Psi*, mW[l] = sum w p_l, mA[l] = sum w p_l I,
+        //   mB0[l] = sum w Psi* p_l, mB[l] = sum w Psi* p_l^2, mBx[(a,b)] = sum w Psi* p_a p_b (a < b)
+        constexpr int NPAIR = NL > 1 ? NL * (NL - 1) / 2 : 1;
+        double mJ[NCH], mP[NCH], mW[NLA][NCH], mA[NLA][NCH], mB0[NLA][NCH], mB[NLA][NCH], mBx[NPAIR][NCH];
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
         {
-            mJ[j] = mP[j] = mB01[j] = 0.0;
+            mJ[j] = mP[j] = 0.0;
 #pragma unroll
             for (int l = 0; l < NLA; ++l)
                 mW[l][j] = mA[l][j] = mB0[l][j] = mB[l][j] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q)
+                mBx[q][j] = 0.0;
         }
         double W0 = 0.0;
         double chi[NCH], S[NCH], rchi[NCH];
@@ -698,7 +704,17 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
                         mB[l][j] = fma(tq[l], p[l][j], mB[l][j]);
                     }
                     if (NL > 1)
-                        mB01[j] = fma(tq[0], p[NLA - 1][j], mB01[j]);
+                    {
+                        int pr = 0;
+#pragma unroll
+                        for (int a = 0; a < NLA; ++a)
+#pragma unroll
+                            for (int b = a + 1; b < NLA; ++b)
+                            {
+                                mBx[pr][j] = fma(tq[a], p[b][j], mBx[pr][j]);
+                                ++pr;
+                            }
+                    }
                 }
             }
         }
@@ -726,7 +742,9 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
         if (lane == 0)
             P.dJ[(size_t)col * L + la] = dJ;
 
-        // ---- epilogue: Gamma and rates from the moments, atom by atom
+        // ---- epilogue: Gamma and rates from the moments, atom by atom.
+        // Profile members of an atom: q = 0 the continua (p = 1), q = l + 1 line slot l.
+        // M(q, q') = sum_r w Psi* p_q p_q'.
         int e0 = eBeg;
         while (e0 < eEnd)
         {
@@ -736,14 +754,34 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
                 ++e1;
             const bool detailed = P.atomDetailed[atom] != 0;
             const int N = P.atomNlevel[atom];
-            const bool own0 = (NL > 0) && ls[0].atom == atom;
-            const bool own1 = (NL > 1) && ls[NLA - 1].atom == atom;
+            bool own[NLA];
+#pragma unroll
+            for (int l = 0; l < NLA; ++l)
+                own[l] = (NL > 0) && ls[l].atom == atom;
 #pragma unroll
             for (int j = 0; j < NCH; ++j)
             {
                 const int k = lane * NCH + j;
                 if (k < K)
                 {
+                    constexpr int NQ = NL + 1;
+                    double Mq[NQ][NQ], Eq[NQ];
+                    Mq[0][0] = mP[j];
+                    {
+                        int pr = 0;
+#pragma unroll
+                        for (int a = 0; a < NL; ++a)
+                        {
+                            Mq[0][a + 1] = Mq[a + 1][0] = mB0[a][j];
+                            Mq[a + 1][a + 1] = mB[a][j];
+#pragma unroll
+                            for (int b = a + 1; b < NL; ++b)
+                            {
+                                Mq[a + 1][b + 1] = Mq[b + 1][a + 1] = mBx[pr][j];
+                                ++pr;
+                            }
+                        }
+                    }
                     double E0 = 0.0;
                     if (!detailed)
                     {
@@ -771,117 +809,100 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
                             E0 += nj * Uji;
                         }
                     }
-                    // line members of this atom: per-unit-phi coefficients
-                    double gv0 = 0.0, ugv0 = 0.0, gv1 = 0.0, ugv1 = 0.0;
-                    double X0l = 0.0, E0l = 0.0, X1l = 0.0, E1l = 0.0;
-                    double B00 = 0.0, Bs0 = 0.0, B11 = 0.0, Bs1 = 0.0, B01 = 0.0;
-                    if (NL > 0)
+                    // line members of this atom: per-unit-phi coefficients (0 for other atoms' lines)
+                    double Xl[NLA], gvl[NLA], ugvl[NLA];
+                    Eq[0] = E0;
+#pragma unroll
+                    for (int l = 0; l < NLA; ++l)
                     {
-                        Bs0 = mB0[0][j];
-                        B00 = mB[0][j];
-                        if (own0)
+                        Xl[l] = gvl[l] = ugvl[l] = 0.0;
+                        if (NL > 0)
                         {
-                            const double r = ls[0].rho ? __ldg(ls[0].rho + k) : 1.0;
-                            gv0 = ls[0].gv * r;
-                            ugv0 = ls[0].ugv * r;
-                            X0l = cX[0][j];
-                            E0l = cE[0][j];
+                            Eq[l + (NL > 0 ? 1 : 0)] = 0.0;
+                            if (own[l])
+                            {
+                                const double r = ls[l].rho ? __ldg(ls[l].rho + k) : 1.0;
+                                gvl[l] = ls[l].gv * r;
+                                ugvl[l] = ls[l].ugv * r;
+                                Xl[l] = cX[l][j];
+                                Eq[l + (NL > 0 ? 1 : 0)] = cE[l][j];
+                            }
                         }
                     }
-                    if (NL > 1)
+                    // EB[q] = sum_q' E_q' M(q, q')
+                    double EB[NQ];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
                     {
-                        Bs1 = mB0[NLA - 1][j];
-                        B11 = mB[NLA - 1][j];
-                        B01 = mB01[j];
-                        if (own1)
-                        {
-                            const double r = ls[NLA - 1].rho ? __ldg(ls[NLA - 1].rho + k) : 1.0;
-                            gv1 = ls[NLA - 1].gv * r;
-                            ugv1 = ls[NLA - 1].ugv * r;
-                            X1l = cX[NLA - 1][j];
-                            E1l = cE[NLA - 1][j];
-                        }
+                        double s = 0.0;
+#pragma unroll
+                        for (int q2 = 0; q2 < NQ; ++q2)
+                            s = fma(Eq[q2], Mq[q][q2], s);
+                        EB[q] = s;
                     }
-                    // sum_q' E_q' M(q, q') for q = continuum, line0, line1
-                    const double EBc = E0 * mP[j] + E0l * Bs0 + E1l * Bs1;
-                    const double EB0 = E0 * Bs0 + E0l * B00 + E1l * B01;
-                    const double EB1 = E0 * Bs1 + E0l * B01 + E1l * B11;
 
                     for (int e = e0; e < e1; ++e)
                     {
                         const DevEntry en = P.entries[e];
                         const DevTrans& t = P.trans[en.trans];
                         const int lt = la - t.Nblue;
-                        // profile member of this transition: 0 continuum, 1 line slot 0, 2 line slot 1
-                        const int q = (t.type != 0) ? 0 : ((NL < 2 || en.trans == ls[0].trans) ? 1 : 2);
-                        double v, gv, ugv, Wq, Aq, EBq, wla;
-                        if (q == 0)
+                        double v = 0.0, gv = 0.0, ugv = 0.0, Wq = W0, Aq = mJ[j], EBq = EB[0], wla = 0.0;
+                        if (t.type != 0)
                         {
                             const double al = __ldg(P.alphaTab + t.tabOff + lt);
                             const double gk = __ldg(P.gRatio + ((size_t)t.contIdx * P.Ncol + col) * K + k) * expfac[j];
                             v = al;
                             gv = gk * al;
                             ugv = hcl * gv;
-                            Wq = W0;
-                            Aq = mJ[j];
-                            EBq = EBc;
                             wla = (__ldg(P.wlambdaTab + t.tabOff + lt) * rlambda) * pi4_h;
                         }
-                        else if (q == 1)
+#pragma unroll
+                        for (int l = 0; l < NL; ++l)
                         {
-                            v = ls[0].v;
-                            gv = gv0;
-                            ugv = ugv0;
-                            Wq = mW[0][j];
-                            Aq = mA[0][j];
-                            EBq = EB0;
-                            wla = ls[0].wlaS * __ldg(ls[0].wphi + k);
-                        }
-                        else
-                        {
-                            v = ls[NLA - 1].v;
-                            gv = gv1;
-                            ugv = ugv1;
-                            Wq = mW[NLA - 1][j];
-                            Aq = mA[NLA - 1][j];
-                            EBq = EB1;
-                            wla = ls[NLA - 1].wlaS * __ldg(ls[NLA - 1].wphi + k);
+                            if (t.type == 0 && en.trans == ls[l].trans)
+                            {
+                                v = ls[l].v;
+                                gv = gvl[l];
+                                ugv = ugvl[l];
+                                Wq = mW[l][j];
+                                Aq = mA[l][j];
+                                EBq = EB[l + 1];
+                                wla = ls[l].wlaS * __ldg(ls[l].wphi + k);
+                            }
                         }
                         double* a4 = acc + (size_t)en.slot * 4 * KP + k;
                         if (!detailed)
                         {
-                            const double Xci = Xs[t.i * 32 + lane], Xcj = Xs[t.j * 32 + lane];
-                            const double Uci = Us[t.i * 32 + lane], Ucj = Us[t.j * 32 + lane];
-                            double XUij = Xci * Ucj * mP[j];
-                            double XUji = Xcj * Uci * mP[j];
-                            if (NL > 0 && own0)
+                            // chi_atom(m) = sum_q p_q X_q(m), U_atom(m) = sum_q p_q U_q(m)
+                            double Xi[NQ], Xj[NQ], Ui[NQ], Uj[NQ];
+                            Xi[0] = Xs[t.i * 32 + lane];
+                            Xj[0] = Xs[t.j * 32 + lane];
+                            Ui[0] = Us[t.i * 32 + lane];
+                            Uj[0] = Us[t.j * 32 + lane];
+#pragma unroll
+                            for (int l = 0; l < NL; ++l)
                             {
-                                const double X0i = t.i == ls[0].li ? X0l : (t.i == ls[0].lj ? -X0l : 0.0);
-                                const double X0j = t.j == ls[0].li ? X0l : (t.j == ls[0].lj ? -X0l : 0.0);
-                                const double U0i = t.i == ls[0].lj ? ugv0 : 0.0;
-                                const double U0j = t.j == ls[0].lj ? ugv0 : 0.0;
-                                XUij += Xci * U0j * Bs0 + X0i * (Ucj * Bs0 + U0j * B00);
-                                XUji += Xcj * U0i * Bs0 + X0j * (Uci * Bs0 + U0i * B00);
-                                if (NL > 1 && own1)
+                                Xi[l + 1] = t.i == ls[l].li ? Xl[l] : (t.i == ls[l].lj ? -Xl[l] : 0.0);
+                                Xj[l + 1] = t.j == ls[l].li ? Xl[l] : (t.j == ls[l].lj ? -Xl[l] : 0.0);
+                                Ui[l + 1] = t.i == ls[l].lj ? ugvl[l] : 0.0;
+                                Uj[l + 1] = t.j == ls[l].lj ? ugvl[l] : 0.0;
+                            }
+                            // sum_r w Psi* chi_atom(a) U_atom(b) = sum_{q,q'} X_q(a) M(q,q') U_q'(b)
+                            double XUij = 0.0, XUji = 0.0;
+#pragma unroll
+                            for (int q = 0; q < NQ; ++q)
+                            {
+                                double mj = 0.0, mi = 0.0;
+#pragma unroll
+                                for (int q2 = 0; q2 < NQ; ++q2)
                                 {
-                                    const double X1i = t.i == ls[NLA - 1].li ? X1l : (t.i == ls[NLA - 1].lj ? -X1l : 0.0);
-                                    const double X1j = t.j == ls[NLA - 1].li ? X1l : (t.j == ls[NLA - 1].lj ? -X1l : 0.0);
-                                    const double U1i = t.i == ls[NLA - 1].lj ? ugv1 : 0.0;
-                                    const double U1j = t.j == ls[NLA - 1].lj ? ugv1 : 0.0;
-                                    XUij += X0i * U1j * B01 + X1i * U0j * B01;
-                                    XUji += X0j * U1i * B01 + X1j * U0i * B01;
+                                    mj = fma(Mq[q][q2], Uj[q2], mj);
+                                    mi = fma(Mq[q][q2], Ui[q2], mi);
                                 }
+                                XUij = fma(Xi[q], mj, XUij);
+                                XUji = fma(Xj[q], mi, XUji);
                             }
-                            if (NL > 1 && own1)
-                            {
-                                const double X1i = t.i == ls[NLA - 1].li ? X1l : (t.i == ls[NLA - 1].lj ? -X1l : 0.0);
-                                const double X1j = t.j == ls[NLA - 1].li ? X1l : (t.j == ls[NLA - 1].lj ? -X1l : 0.0);
-                                const double U1i = t.i == ls[NLA - 1].lj ? ugv1 : 0.0;
-                                const double U1j = t.j == ls[NLA - 1].lj ? ugv1 : 0.0;
-                                XUij += Xci * U1j * Bs1 + X1i * (Ucj * Bs1 + U1j * B11);
-                                XUji += Xcj * U1i * Bs1 + X1j * (Uci * Bs1 + U1i * B11);
-                            }
-                            // sum_r w [(Uji + Vji Ieff) - Psi chi(i) U(j)],  Ieff = I - Psi eta_atom
+                            // sum_r w [(Uji + Vji Ieff) - Psi* chi(i) U(j)],  Ieff = I - Psi* eta_atom
                             smem_add(a4, (ugv * Wq + gv * (Aq - EBq) - XUij) * wla);
                             smem_add(a4 + KP, (v * (Aq - EBq) - XUji) * wla);
                         }

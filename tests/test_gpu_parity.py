@@ -330,3 +330,38 @@ def test_column_stack_properties_at_scale():
     I = big.I.reshape(reps, 4, *big.I.shape[1:])
     assert rel_err(I, np.broadcast_to(q.I, I.shape)) <= TOL
     ctx.close()
+
+
+def _overlap_problem(nlines):
+    """A toy atom whose `nlines` lines all overlap (same-atom cross moments), plus a
+    second atom with an overlapping line (cross-atom case)."""
+    lev = [synth.Level(0.0, 2, 0)] + [synth.Level(60000.0 + 18.0 * i, 4 + 2 * i, 0) for i in range(nlines)]
+    lev.append(synth.Level(100000.0, 1, 1))
+    top = len(lev) - 1
+    lines = [synth.LineSpec(i + 1, 0, 2.0e8 / (i + 1), 21, 5.0, 80.0) for i in range(nlines)]
+    cont = [synth.ContSpec(top, i, 5.0e-22, 8, 50.0) for i in range(top)]
+    a = synth.ModelAtom('Ovl', 12.0, 1e-4, lev, lines, cont)
+    lev2 = [synth.Level(0.0, 2, 0), synth.Level(60010.0, 6, 0), synth.Level(90000.0, 1, 1)]
+    b = synth.ModelAtom('Oth', 20.0, 3e-5, lev2, [synth.LineSpec(1, 0, 1.0e8, 21, 5.0, 80.0)],
+                        [synth.ContSpec(2, 0, 5.0e-22, 8, 50.0), synth.ContSpec(2, 1, 8.0e-22, 8, 80.0)])
+    return synth.build_problem([a, b], nrays=3, perturb=True, ncol=2)
+
+
+@pytest.mark.parametrize('nlines', [1, 2, 3, 4])
+def test_overlapping_lines_moment_and_general_kernels(nlines):
+    """Up to 3 overlapping lines go through the moment kernel, more through the general
+    kernel; both must match the oracle, and each other."""
+    p = _overlap_problem(nlines)
+    q = p.clone()
+    g = p.clone()
+    ctx, ctg = Context(p), Context(g)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices()
+        ctg.formal_sol_gamma_matrices(extraParams={'generalKernel': True})
+        ctx.stat_equil()
+        ctg.stat_equil()
+        oracle_iter(q)
+        assert_close(p, q)
+        assert_close(g, q)
+    ctx.close()
+    ctg.close()
