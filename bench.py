@@ -316,7 +316,10 @@ def run_ours(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload)
+            tj = json.load(open(tpath))
+            traffic = tj.get(args.workload)
+            if args.workload == 'c3' and tj.get('c3_per_column'):
+                traffic = tj['c3_per_column'] * problem.Ncol
         except Exception:
             traffic = None
     line = {
