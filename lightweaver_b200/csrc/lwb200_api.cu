@@ -123,7 +123,7 @@ struct LwB200Context
     std::vector<HostTrans> trans; // flattened, global order
     std::vector<DevTrans> devTrans;
     std::vector<int> atomNlevel, atomLevOff, atomGammaOff, atomDetailed;
-    std::vector<int> tileLa, tileSlotOff, tileSlotTrans, tileKind;
+    std::vector<int> tileLa, tileLambda, tileSlotOff, tileSlotTrans, tileKind;
     DevBuf<int> dListNL[4], dListDirect, dListAll;
     int nListNL[4] = {0, 0, 0, 0}, nListDirect = 0, nListAll = 0, listLo = -1, listHi = -1;
     int Ntile = 0;
@@ -139,7 +139,7 @@ struct LwB200Context
     DevBuf<double> J, I, n, nStar, nTotal, vBroad, gRatio, phi, wphi, rhoPrd, aDamp;
     DevBuf<double> wlambdaTab, alphaTab, transWave, lowerBcData, upperBcData, accum, prefill, gamma, dJ;
     DevBuf<double> depthChi, depthEta, depthI, djOut;
-    DevBuf<int> lowerBcIdx, upperBcIdx, dLaOff, dLaHasLine, dTileLa, dTileSlotOff, dTileSlotTrans;
+    DevBuf<int> lowerBcIdx, upperBcIdx, dLaOff, dLaCnt, dTileLambda, dLaHasLine, dTileLa, dTileSlotOff, dTileSlotTrans;
     DevBuf<int> dAtomNlevel, dAtomLevOff, dAtomGammaOff, dAtomDetailed, dSingular;
     DevBuf<long long> djIdx;
     DevBuf<DevTrans> dTrans;
@@ -269,45 +269,61 @@ int build_plan(LwB200Context* c)
     int tileLen = (int)std::max<long long>(c->nwarps, std::min<long long>(want, 16 * c->nwarps));
     tileLen = ((tileLen + c->nwarps - 1) / c->nwarps) * c->nwarps;
 
+    // Tiles are lists of wavelengths of ONE kind (same number of overlapping lines), in
+    // ascending order but not necessarily contiguous: continuum-only grid points are
+    // scattered between the lines, and contiguous runs would fragment into 1-2 wavelength
+    // tiles.  A tile ends when it is full or its union of active transitions would
+    // outgrow the shared-memory accumulator.
     std::vector<DevEntry> entries;
+    std::vector<int> laCnt(L, 0);
     int maxSlots = 1;
     c->tileLa.push_back(0);
     c->tileSlotOff.push_back(0);
-    int la = 0;
-    while (la < L)
+    for (int kind = 0; kind <= 4; ++kind)
     {
-        std::vector<int> slots; // transitions of this tile
-        int start = la;
-        while (la < L && la - start < tileLen && kind_of(la) == kind_of(start))
+        std::vector<int> las;
+        for (int la = 0; la < L; ++la)
+            if (kind_of(la) == kind)
+                las.push_back(la);
+        size_t pos = 0;
+        while (pos < las.size())
         {
-            std::vector<int> add;
-            for (int g : active[la])
-                if (std::find(slots.begin(), slots.end(), g) == slots.end())
-                    add.push_back(g);
-            if ((int)(slots.size() + add.size()) > slotCap)
+            std::vector<int> slots; // transitions of this tile
+            const size_t start = pos;
+            while (pos < las.size() && (int)(pos - start) < tileLen)
             {
-                if (la == start)
-                    return fail("too many transitions active at one wavelength for shared memory");
-                break;
+                std::vector<int> add;
+                for (int g : active[las[pos]])
+                    if (std::find(slots.begin(), slots.end(), g) == slots.end())
+                        add.push_back(g);
+                if ((int)(slots.size() + add.size()) > slotCap)
+                {
+                    if (pos == start)
+                        return fail("too many transitions active at one wavelength for shared memory");
+                    break;
+                }
+                slots.insert(slots.end(), add.begin(), add.end());
+                ++pos;
             }
-            slots.insert(slots.end(), add.begin(), add.end());
-            ++la;
-        }
-        for (int l2 = start; l2 < la; ++l2)
-        {
-            laOff[l2] = (int)entries.size();
-            for (int g : active[l2])
+            for (size_t q = start; q < pos; ++q)
             {
-                int s = (int)(std::find(slots.begin(), slots.end(), g) - slots.begin());
-                entries.push_back(DevEntry{g, s});
+                const int l2 = las[q];
+                laOff[l2] = (int)entries.size();
+                laCnt[l2] = (int)active[l2].size();
+                for (int g : active[l2])
+                {
+                    int sl = (int)(std::find(slots.begin(), slots.end(), g) - slots.begin());
+                    entries.push_back(DevEntry{g, sl});
+                }
+                c->tileLambda.push_back(l2);
             }
+            c->tileLa.push_back((int)c->tileLambda.size());
+            c->tileKind.push_back(kind);
+            for (int g : slots)
+                c->tileSlotTrans.push_back(g);
+            c->tileSlotOff.push_back((int)c->tileSlotTrans.size());
+            maxSlots = std::max(maxSlots, (int)slots.size());
         }
-        c->tileLa.push_back(la);
-        c->tileKind.push_back(kind_of(start));
-        for (int g : slots)
-            c->tileSlotTrans.push_back(g);
-        c->tileSlotOff.push_back((int)c->tileSlotTrans.size());
-        maxSlots = std::max(maxSlots, (int)slots.size());
     }
     laOff[L] = (int)entries.size();
     c->Ntile = (int)c->tileLa.size() - 1;
@@ -384,7 +400,7 @@ int build_plan(LwB200Context* c)
     }
     if (c->wlambdaTab.upload(wlambdaTab) || c->alphaTab.upload(alphaTab) || c->dTrans.upload(c->devTrans)
         || c->dEntries.upload(entries) || c->dLaOff.upload(laOff) || c->dLaHasLine.upload(laHasLine)
-        || c->dTileLa.upload(c->tileLa) || c->dTileSlotOff.upload(c->tileSlotOff)
+        || c->dLaCnt.upload(laCnt) || c->dTileLambda.upload(c->tileLambda) || c->dTileLa.upload(c->tileLa) || c->dTileSlotOff.upload(c->tileSlotOff)
         || c->dTileSlotTrans.upload(c->tileSlotTrans) || c->dAtomNlevel.upload(c->atomNlevel)
         || c->dAtomLevOff.upload(c->atomLevOff) || c->dAtomGammaOff.upload(c->atomGammaOff)
         || c->dAtomDetailed.upload(c->atomDetailed))
@@ -440,6 +456,7 @@ int build_plan(LwB200Context* c)
     P.accum = c->accum.p; P.dJ = c->dJ.p;
     P.depthChi = c->depthChi.p; P.depthEta = c->depthEta.p; P.depthI = c->depthI.p;
     P.trans = c->dTrans.p; P.entries = c->dEntries.p; P.laOff = c->dLaOff.p; P.laHasLine = c->dLaHasLine.p;
+    P.laCnt = c->dLaCnt.p; P.tileLambda = c->dTileLambda.p;
     P.tileLa = c->dTileLa.p; P.tileSlotOff = c->dTileSlotOff.p; P.tileSlotTrans = c->dTileSlotTrans.p;
     P.atomNlevel = c->dAtomNlevel.p; P.atomLevOff = c->dAtomLevOff.p;
     P.atomGammaOff = c->dAtomGammaOff.p; P.atomDetailed = c->dAtomDetailed.p;
@@ -453,7 +470,8 @@ int refresh_tile_lists(LwB200Context* c)
     std::vector<int> mom[4], dir, all;
     for (int t = 0; t < c->Ntile; ++t)
     {
-        if (c->tileLa[t + 1] <= c->laLo || c->tileLa[t] >= c->laHi)
+        // tile wavelength lists are ascending: overlap test on first / last
+        if (c->tileLambda[c->tileLa[t + 1] - 1] < c->laLo || c->tileLambda[c->tileLa[t]] >= c->laHi)
             continue;
         all.push_back(t);
         (c->tileKind[t] < 4 ? mom[c->tileKind[t]] : dir).push_back(t);
@@ -704,7 +722,7 @@ int lwb200_destroy(LwB200Context* c)
                              &c->prefill, &c->gamma, &c->dJ, &c->depthChi, &c->depthEta, &c->depthI, &c->djOut};
     for (auto* b : dbl)
         b->release();
-    DevBuf<int>* ints[] = {&c->lowerBcIdx, &c->upperBcIdx, &c->dLaOff, &c->dLaHasLine, &c->dTileLa,
+    DevBuf<int>* ints[] = {&c->lowerBcIdx, &c->upperBcIdx, &c->dLaOff, &c->dLaCnt, &c->dTileLambda, &c->dLaHasLine, &c->dTileLa,
                            &c->dTileSlotOff, &c->dTileSlotTrans, &c->dAtomNlevel, &c->dAtomLevOff,
                            &c->dAtomGammaOff, &c->dAtomDetailed, &c->dSingular};
     for (auto* b : ints)
@@ -1097,25 +1115,30 @@ int lwb200_stat_eq(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd,
         return fail("lwb200_stat_eq: atom index out of range");
     c->lastLaunches = 0;
     CU(cudaMemsetAsync(c->dSingular.p, 0, sizeof(int), c->stream));
-    for (int a = 0; a < c->prob.Natom; ++a)
     {
-        if (atom >= 0 && a != atom)
-            continue;
-        if (c->atoms[a].detailedStatic)
-            continue;
-        const size_t total = (size_t)c->prob.Ncol * (kEnd - kStart);
-        const int N = c->atoms[a].Nlevel;
-        if (N <= 8)
-            stat_eq_kernel<8><<<grid_for(total, 64), 64, 0, c->stream>>>(c->P, a, kStart, kEnd, c->gamma.p, c->n.p,
-                                                                           c->nTotal.p, c->dSingular.p);
-        else if (N <= 16)
-            stat_eq_kernel<16><<<grid_for(total, 64), 64, 0, c->stream>>>(c->P, a, kStart, kEnd, c->gamma.p, c->n.p,
-                                                                            c->nTotal.p, c->dSingular.p);
-        else
-            stat_eq_kernel<32><<<grid_for(total, 64), 64, 0, c->stream>>>(c->P, a, kStart, kEnd, c->gamma.p, c->n.p,
-                                                                            c->nTotal.p, c->dSingular.p);
-        CU(cudaGetLastError());
-        c->lastLaunches += 1;
+        int maxN = 1, nActive = 0;
+        for (int a = 0; a < c->prob.Natom; ++a)
+        {
+            if ((atom >= 0 && a != atom) || c->atoms[a].detailedStatic)
+                continue;
+            maxN = std::max(maxN, c->atoms[a].Nlevel);
+            ++nActive;
+        }
+        if (nActive > 0)
+        {
+            const size_t total = (size_t)(atom >= 0 ? 1 : c->prob.Natom) * c->prob.Ncol * (kEnd - kStart);
+            if (maxN <= 8)
+                stat_eq_kernel<8><<<grid_for(total, 64), 64, 0, c->stream>>>(c->P, atom, kStart, kEnd, c->gamma.p,
+                                                                               c->n.p, c->nTotal.p, c->dSingular.p);
+            else if (maxN <= 16)
+                stat_eq_kernel<16><<<grid_for(total, 64), 64, 0, c->stream>>>(c->P, atom, kStart, kEnd, c->gamma.p,
+                                                                                c->n.p, c->nTotal.p, c->dSingular.p);
+            else
+                stat_eq_kernel<32><<<grid_for(total, 64), 64, 0, c->stream>>>(c->P, atom, kStart, kEnd, c->gamma.p,
+                                                                                c->n.p, c->nTotal.p, c->dSingular.p);
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
+        }
     }
     int ns = 0;
     CU(cudaMemcpyAsync(&ns, c->dSingular.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

@@ -446,15 +446,17 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
     const double* Tcol = P.temperature + (size_t)col * K;
     const double* ncol = P.n + (size_t)col * P.NlevTot * K;
 
-    const int laBeg = max(P.tileLa[tile], laLo);
-    const int laEnd = min(P.tileLa[tile + 1], laHi);
+    const int tlBeg = P.tileLa[tile], tlEnd = P.tileLa[tile + 1];
 
-    for (int la = laBeg + warp; la < laEnd; la += nwarp)
+    for (int tl = tlBeg + warp; tl < tlEnd; tl += nwarp)
     {
+        const int la = P.tileLambda[tl];
+        if (la < laLo || la >= laHi)
+            continue;
         const double lambda = __ldg(P.wavelength + la);
         const double rlambda = 1.0 / lambda;
         const size_t rowLK = ((size_t)col * L + la) * K;
-        const int eBeg = P.laOff[la], eEnd = P.laOff[la + 1];
+        const int eBeg = P.laOff[la], eEnd = eBeg + P.laCnt[la];
         constexpr double hc_k = kHC / (kKBoltzmann * kNmToM);
         constexpr double twoHc = 2.0 * kHC / (kNmToM * kNmToM * kNmToM);
         constexpr double hc_4pi = 0.25 * kHC / kPi;

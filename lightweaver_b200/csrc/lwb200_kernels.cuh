@@ -68,9 +68,11 @@ struct DevProblem
     double *depthChi, *depthEta, *depthI;
     const DevTrans* trans;
     const DevEntry* entries;
-    const int* laOff;
+    const int* laOff;        // [L] first entry of a wavelength's active-transition list
+    const int* laCnt;        // [L] its length
     const int* laHasLine;
-    const int* tileLa;       // [Ntile + 1]
+    const int* tileLambda;   // wavelength indices of every tile, ascending within a tile
+    const int* tileLa;       // [Ntile + 1] offsets into tileLambda
     const int* tileSlotOff;  // [Ntile + 1]
     const int* tileSlotTrans;
     const int* atomNlevel;
@@ -172,14 +174,16 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
     const double Tbot0 = __ldg(P.temperature + (size_t)col * K + K - 1);
     const double Tbot1 = __ldg(P.temperature + (size_t)col * K + K - 2);
 
-    int laBeg = max(P.tileLa[tile], laLo);
-    int laEnd = min(P.tileLa[tile + 1], laHi);
+    const int tlBeg = P.tileLa[tile], tlEnd = P.tileLa[tile + 1];
 
-    for (int la = laBeg + warp; la < laEnd; la += nwarp)
+    for (int tl = tlBeg + warp; tl < tlEnd; tl += nwarp)
     {
+        const int la = P.tileLambda[tl];
+        if (la < laLo || la >= laHi)
+            continue;
         const double lambda = __ldg(P.wavelength + la);
         const size_t rowLK = ((size_t)col * L + la) * K;
-        const int eBeg = P.laOff[la], eEnd = P.laOff[la + 1];
+        const int eBeg = P.laOff[la], eEnd = eBeg + P.laCnt[la];
         const bool hasLine = P.laHasLine[la] != 0;
 
         // --- ray-independent part: background + continua (the reference's
@@ -625,18 +629,24 @@ __device__ inline void lu_backsub_dev(int N, const double* A, const int* index, 
 }
 
 template <int MAXN>
-__global__ void stat_eq_kernel(const DevProblem P, int atom, int kStart, int kEnd,
+__global__ void stat_eq_kernel(const DevProblem P, int atomSel, int kStart, int kEnd,
                                const double* __restrict__ gamma, double* __restrict__ n,
                                const double* __restrict__ nTotal, int* __restrict__ nSingular)
 {
+    // atomSel >= 0: that atom; atomSel < 0: every active atom in ONE launch (the systems of
+    // different atoms are independent; in 1D there are only Nspace of them per atom)
     const int nk = kEnd - kStart;
-    const size_t total = (size_t)P.Ncol * nk;
-    const int N = P.atomNlevel[atom];
+    const int nAtomLoop = atomSel >= 0 ? 1 : P.Natom;
+    const size_t total = (size_t)nAtomLoop * P.Ncol * nk;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x)
     {
         const int k = kStart + idx % nk;
-        const int col = idx / nk;
+        const int col = (idx / nk) % P.Ncol;
+        const int atom = atomSel >= 0 ? atomSel : (int)(idx / ((size_t)nk * P.Ncol));
+        if (P.atomDetailed[atom])
+            continue;
+        const int N = P.atomNlevel[atom];
         double A[MAXN * MAXN], ACopy[MAXN * MAXN], b[MAXN], bCopy[MAXN], res[MAXN];
         int index[MAXN];
         const size_t gOff = ((size_t)col * P.GammaTot + P.atomGammaOff[atom]) * P.K + k;
