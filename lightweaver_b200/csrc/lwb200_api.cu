@@ -264,10 +264,19 @@ int build_plan(LwB200Context* c)
     if (scratchBytes + 4 * KP * sizeof(double) > smemLimit)
         return fail("atom too large for the shared-memory scratch");
     const int slotCap = (int)std::min<size_t>((smemLimit - scratchBytes) / (4 * KP * sizeof(double)), 48);
-    const long long targetCtas = 148LL * 16;
-    long long want = ((long long)L * p.Ncol + targetCtas - 1) / targetCtas;
-    int tileLen = (int)std::max<long long>(c->nwarps, std::min<long long>(want, 16 * c->nwarps));
-    tileLen = ((tileLen + c->nwarps - 1) / c->nwarps) * c->nwarps;
+    // tile length per kind: enough CTAs of every kind for several full waves (2-3 CTAs of
+    // 4 warps per SM), at least one wavelength per warp, at most 16 per warp
+    int kindCount[5] = {0, 0, 0, 0, 0};
+    for (int la = 0; la < L; ++la)
+        kindCount[kind_of(la)] += 1;
+    int tileLenKind[5];
+    for (int q = 0; q < 5; ++q)
+    {
+        const long long targetCtas = 148LL * 3 * 6; // ~6 waves
+        long long want = ((long long)kindCount[q] * p.Ncol + targetCtas - 1) / targetCtas;
+        int tl = (int)std::max<long long>(c->nwarps, std::min<long long>(want, 16 * c->nwarps));
+        tileLenKind[q] = ((tl + c->nwarps - 1) / c->nwarps) * c->nwarps;
+    }
 
     // Tiles are lists of wavelengths of ONE kind (same number of overlapping lines), in
     // ascending order but not necessarily contiguous: continuum-only grid points are
@@ -290,7 +299,7 @@ int build_plan(LwB200Context* c)
         {
             std::vector<int> slots; // transitions of this tile
             const size_t start = pos;
-            while (pos < las.size() && (int)(pos - start) < tileLen)
+            while (pos < las.size() && (int)(pos - start) < tileLenKind[kind])
             {
                 std::vector<int> add;
                 for (int g : active[las[pos]])
