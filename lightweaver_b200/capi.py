@@ -90,6 +90,11 @@ _lib = None
 
 
 def lib_path():
+    # LWB200_LIB: development aid for timing kernel variants built side by side
+    # (tools/variants.py); it changes which build of the same C-ABI is loaded, nothing else
+    override = os.environ.get('LWB200_LIB')
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'liblwb200.so')
 
 

@@ -113,6 +113,8 @@ struct LwB200Context
     std::vector<Pending> pending;
     std::vector<void*> registered;
     cudaEvent_t evK0 = nullptr, evK1 = nullptr;
+    cudaStream_t sideStream[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evFork = nullptr, evJoin[4] = {nullptr, nullptr, nullptr, nullptr};
     bool kernelTimed = false;
     bool forceDirect = false;
     int device = 0;
@@ -516,6 +518,23 @@ int set_smem_attr(Kern kern, int device)
     return 0;
 }
 
+int ensure_side_streams(LwB200Context* c)
+{
+    if (c->evFork)
+        return 0;
+    int prLow = 0, prHigh = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh)); // numerically lower = more urgent
+    for (int q = 0; q < 4; ++q)
+    {
+        // earlier side streams carry the more expensive kinds: give their CTAs precedence
+        const int pr = std::max(prHigh, std::min(prLow, prLow - (3 - q)));
+        CU(cudaStreamCreateWithPriority(&c->sideStream[q], cudaStreamNonBlocking, pr));
+        CU(cudaEventCreateWithFlags(&c->evJoin[q], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    return 0;
+}
+
 template <int NCH, int SOLVER, int MODE>
 int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
 {
@@ -528,48 +547,53 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
     const int threads = c->nwarps * 32;
     if (MODE == MODE_ITER && !c->forceDirect)
     {
-        // largest tiles first: the NL = 1 (single line) wavelengths dominate
-        if (c->nListNL[1] > 0)
+        // The kinds run CONCURRENTLY: most expensive per wavelength first (3, 2, 1, 0
+        // overlapping lines, then the general kernel), each on its own side stream forked
+        // from / joined to the caller's stream, so that they share one tail instead of
+        // each paying its own (a 1D atmosphere is only a few waves of CTAs in total).
+        if (ensure_side_streams(c))
+            return 1;
+        int nside = 0;
+        auto side = [&]() -> cudaStream_t {
+            if (nside == 0)
+                cudaEventRecord(c->evFork, c->stream);
+            cudaStream_t s = c->sideStream[nside];
+            cudaStreamWaitEvent(s, c->evFork, 0);
+            ++nside;
+            return s;
+        };
+        const int order[4] = {3, 2, 1, 0};
+        int nkinds = (c->nListDirect > 0 ? 1 : 0);
+        for (int q = 0; q < 4; ++q)
+            nkinds += c->nListNL[q] > 0 ? 1 : 0;
+        int launched = 0;
+        for (int oi = 0; oi < 4; ++oi)
         {
-            auto kern = fsm_kernel<NCH, SOLVER, 1>;
-            if (set_smem_attr(kern, c->device))
-                return 1;
-            dim3 grid(c->nListNL[1], c->prob.Ncol);
-            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListNL[1].p, c->laLo, c->laHi,
-                                                             lambdaIterate, storeDepth);
-            CU(cudaGetLastError());
-            c->lastLaunches += 1;
-        }
-        if (c->nListNL[2] > 0)
-        {
-            auto kern = fsm_kernel<NCH, SOLVER, 2>;
-            if (set_smem_attr(kern, c->device))
-                return 1;
-            dim3 grid(c->nListNL[2], c->prob.Ncol);
-            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListNL[2].p, c->laLo, c->laHi,
-                                                             lambdaIterate, storeDepth);
-            CU(cudaGetLastError());
-            c->lastLaunches += 1;
-        }
-        if (c->nListNL[3] > 0)
-        {
-            auto kern = fsm_kernel<NCH, SOLVER, 3>;
-            if (set_smem_attr(kern, c->device))
-                return 1;
-            dim3 grid(c->nListNL[3], c->prob.Ncol);
-            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListNL[3].p, c->laLo, c->laHi,
-                                                             lambdaIterate, storeDepth);
-            CU(cudaGetLastError());
-            c->lastLaunches += 1;
-        }
-        if (c->nListNL[0] > 0)
-        {
-            auto kern = fsm_kernel<NCH, SOLVER, 0>;
-            if (set_smem_attr(kern, c->device))
-                return 1;
-            dim3 grid(c->nListNL[0], c->prob.Ncol);
-            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListNL[0].p, c->laLo, c->laHi,
-                                                             lambdaIterate, storeDepth);
+            const int q = order[oi];
+            if (c->nListNL[q] == 0)
+                continue;
+            // the last kind runs on the caller's stream itself
+            cudaStream_t s = (++launched == nkinds) ? c->stream : side();
+            dim3 grid(c->nListNL[q], c->prob.Ncol);
+            switch (q)
+            {
+            case 0:
+                if (set_smem_attr(fsm_kernel<NCH, SOLVER, 0>, c->device)) return 1;
+                fsm_kernel<NCH, SOLVER, 0><<<grid, threads, c->smemBytes, s>>>(c->P, c->dListNL[q].p, c->laLo, c->laHi, lambdaIterate, storeDepth);
+                break;
+            case 1:
+                if (set_smem_attr(fsm_kernel<NCH, SOLVER, 1>, c->device)) return 1;
+                fsm_kernel<NCH, SOLVER, 1><<<grid, threads, c->smemBytes, s>>>(c->P, c->dListNL[q].p, c->laLo, c->laHi, lambdaIterate, storeDepth);
+                break;
+            case 2:
+                if (set_smem_attr(fsm_kernel<NCH, SOLVER, 2>, c->device)) return 1;
+                fsm_kernel<NCH, SOLVER, 2><<<grid, threads, c->smemBytes, s>>>(c->P, c->dListNL[q].p, c->laLo, c->laHi, lambdaIterate, storeDepth);
+                break;
+            default:
+                if (set_smem_attr(fsm_kernel<NCH, SOLVER, 3>, c->device)) return 1;
+                fsm_kernel<NCH, SOLVER, 3><<<grid, threads, c->smemBytes, s>>>(c->P, c->dListNL[q].p, c->laLo, c->laHi, lambdaIterate, storeDepth);
+                break;
+            }
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }
@@ -583,6 +607,11 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
                                                              lambdaIterate, 0, storeDepth);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
+        }
+        for (int q = 0; q < nside; ++q)
+        {
+            CU(cudaEventRecord(c->evJoin[q], c->sideStream[q]));
+            CU(cudaStreamWaitEvent(c->stream, c->evJoin[q], 0));
         }
     }
     else if (c->nListAll > 0)
@@ -606,8 +635,10 @@ int launch_fs_s(LwB200Context* c, int li, int uo, int sd)
 {
     switch (c->prob.formalSolver)
     {
+#ifndef LWB200_DEV_FAST_BUILD // (variant timing builds instantiate NCH = 3 / bezier3 only)
     case LWB200_FS_LINEAR: return launch_fs_t<NCH, 0, MODE>(c, li, uo, sd);
     case LWB200_FS_BESSER: return launch_fs_t<NCH, 1, MODE>(c, li, uo, sd);
+#endif
     case LWB200_FS_BEZIER3: return launch_fs_t<NCH, 2, MODE>(c, li, uo, sd);
     }
     return fail("unknown formal solver");
@@ -620,10 +651,14 @@ int launch_fs(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
         return 1;
     switch (c->NCH)
     {
+#ifndef LWB200_DEV_FAST_BUILD
     case 1: return launch_fs_s<1, MODE>(c, lambdaIterate, upOnly, storeDepth);
     case 2: return launch_fs_s<2, MODE>(c, lambdaIterate, upOnly, storeDepth);
+#endif
     case 3: return launch_fs_s<3, MODE>(c, lambdaIterate, upOnly, storeDepth);
+#ifndef LWB200_DEV_FAST_BUILD
     case 4: return launch_fs_s<4, MODE>(c, lambdaIterate, upOnly, storeDepth);
+#endif
     }
     return fail("Nspace > 128 is not supported yet by the register-resident depth layout");
 }
@@ -742,6 +777,15 @@ int lwb200_destroy(LwB200Context* c)
                       &c->stNOut, &c->stGammaOut, &c->stRates};
     for (auto* q : pins)
         q->release();
+    if (c->evFork)
+    {
+        cudaEventDestroy(c->evFork);
+        for (int q = 0; q < 4; ++q)
+        {
+            cudaEventDestroy(c->evJoin[q]);
+            cudaStreamDestroy(c->sideStream[q]);
+        }
+    }
     if (c->evK0)
         cudaEventDestroy(c->evK0);
     if (c->evK1)

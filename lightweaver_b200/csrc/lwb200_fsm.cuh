@@ -416,8 +416,12 @@ struct LineSlot
     const double* wphi; // wphi(0) of this column
 };
 
+#ifndef LWB200_FSM_MINBLOCKS
+#define LWB200_FSM_MINBLOCKS 2
+#endif
+
 template <int NCH, int SOLVER, int NL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, LWB200_FSM_MINBLOCKS)
 fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi, int lambdaIterate,
            int storeDepth)
 {
@@ -604,7 +608,11 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
         for (int l = 0; l < NLA; ++l)
             ph[l] = ls[l].phi + lane * NCH;
 
+#ifdef LWB200_EXP_NRAYS
+        for (int ray = 0; ray < LWB200_EXP_NRAYS; ++ray)
+#else
         for (int ray = 0; ray < 2 * M; ++ray)
+#endif
         {
             const int mu = ray >> 1, dir = ray & 1;
             const double muz = __ldg(P.muz + mu);
@@ -748,6 +756,9 @@ fsm_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int l
         // Profile members of an atom: q = 0 the continua (p = 1), q = l + 1 line slot l.
         // M(q, q') = sum_r w Psi* p_q p_q'.
         int e0 = eBeg;
+#ifdef LWB200_EXP_NOEPI
+        e0 = eEnd;
+#endif
         while (e0 < eEnd)
         {
             const int atom = P.trans[P.entries[e0].trans].atom;
