@@ -4,7 +4,7 @@
 #include "../../include/lwb200.h"
 #include "lwb200_kernels.cuh"
 #include "lwb200_profiles.cuh"
-#include "lwb200_fsm.cuh"
+#include "lwb200_pipeline.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -126,8 +126,15 @@ struct LwB200Context
     std::vector<DevTrans> devTrans;
     std::vector<int> atomNlevel, atomLevOff, atomGammaOff, atomDetailed;
     std::vector<int> tileLa, tileLambda, tileSlotOff, tileSlotTrans, tileKind;
-    DevBuf<int> dListNL[4], dListDirect, dListAll;
-    int nListNL[4] = {0, 0, 0, 0}, nListDirect = 0, nListAll = 0, listLo = -1, listHi = -1;
+    // pipeline work lists: wavelengths per kind (0..3 overlapping lines) for ray_kernel, tiles
+    // for continuum_kernel / gamma_kernel (moment tiles) and for the general fs_kernel
+    std::vector<int> laKind;
+    DevBuf<int> dKindLam[4], dListMoment, dListDirect, dListAll, dMomOff, dLaNLines;
+    DevBuf<LambdaLine> dLamLine;
+    DevBuf<double> chiC, etaC, mom;
+    int nKindLam[4] = {0, 0, 0, 0}, nListMoment = 0, nListDirect = 0, nListAll = 0, listLo = -1, listHi = -1;
+    int batchCols = 1, momRows = 0;
+    size_t smemGamma = 0;
     int Ntile = 0;
     int nwarps = 4;
     int laLo = 0, laHi = 0;
@@ -142,7 +149,7 @@ struct LwB200Context
     DevBuf<double> wlambdaTab, alphaTab, transWave, lowerBcData, upperBcData, accum, prefill, gamma, dJ;
     DevBuf<double> depthChi, depthEta, depthI, djOut;
     DevBuf<int> lowerBcIdx, upperBcIdx, dLaOff, dLaCnt, dTileLambda, dLaHasLine, dTileLa, dTileSlotOff, dTileSlotTrans;
-    DevBuf<int> dAtomNlevel, dAtomLevOff, dAtomGammaOff, dAtomDetailed, dSingular;
+    DevBuf<int> dAtomNlevel, dAtomLevOff, dAtomGammaOff, dAtomDetailed, dSingular, dPhiAsym;
     DevBuf<long long> djIdx;
     DevBuf<DevTrans> dTrans;
     DevBuf<DevEntry> dEntries;
@@ -255,92 +262,6 @@ int build_plan(LwB200Context* c)
     // kinds 0..3: that many overlapping lines, moment kernel; 4: more, general kernel
     auto kind_of = [&](int la) { return laNLines[la] > 3 ? 4 : laNLines[la]; };
 
-    // tiles: runs of wavelengths whose union of active transitions fits the
-    // shared-memory accumulator; sized so that the grid fills the GPU
-    const int KP = ((K + 31) / 32) * 32;
-    int maxNlevel = 1;
-    for (int a = 0; a < p.Natom; ++a)
-        maxNlevel = std::max(maxNlevel, c->atoms[a].Nlevel);
-    const size_t scratchBytes = (size_t)c->nwarps * 2 * maxNlevel * 32 * sizeof(double);
-    const size_t smemLimit = 200 * 1024;
-    if (scratchBytes + 4 * KP * sizeof(double) > smemLimit)
-        return fail("atom too large for the shared-memory scratch");
-    const int slotCap = (int)std::min<size_t>((smemLimit - scratchBytes) / (4 * KP * sizeof(double)), 48);
-    // tile length per kind: enough CTAs of every kind for several full waves (2-3 CTAs of
-    // 4 warps per SM), at least one wavelength per warp, at most 16 per warp
-    int kindCount[5] = {0, 0, 0, 0, 0};
-    for (int la = 0; la < L; ++la)
-        kindCount[kind_of(la)] += 1;
-    int tileLenKind[5];
-    for (int q = 0; q < 5; ++q)
-    {
-        const long long targetCtas = 148LL * 3 * 6; // ~6 waves
-        long long want = ((long long)kindCount[q] * p.Ncol + targetCtas - 1) / targetCtas;
-        int tl = (int)std::max<long long>(c->nwarps, std::min<long long>(want, 16 * c->nwarps));
-        tileLenKind[q] = ((tl + c->nwarps - 1) / c->nwarps) * c->nwarps;
-    }
-
-    // Tiles are lists of wavelengths of ONE kind (same number of overlapping lines), in
-    // ascending order but not necessarily contiguous: continuum-only grid points are
-    // scattered between the lines, and contiguous runs would fragment into 1-2 wavelength
-    // tiles.  A tile ends when it is full or its union of active transitions would
-    // outgrow the shared-memory accumulator.
-    std::vector<DevEntry> entries;
-    std::vector<int> laCnt(L, 0);
-    int maxSlots = 1;
-    c->tileLa.push_back(0);
-    c->tileSlotOff.push_back(0);
-    for (int kind = 0; kind <= 4; ++kind)
-    {
-        std::vector<int> las;
-        for (int la = 0; la < L; ++la)
-            if (kind_of(la) == kind)
-                las.push_back(la);
-        size_t pos = 0;
-        while (pos < las.size())
-        {
-            std::vector<int> slots; // transitions of this tile
-            const size_t start = pos;
-            while (pos < las.size() && (int)(pos - start) < tileLenKind[kind])
-            {
-                std::vector<int> add;
-                for (int g : active[las[pos]])
-                    if (std::find(slots.begin(), slots.end(), g) == slots.end())
-                        add.push_back(g);
-                if ((int)(slots.size() + add.size()) > slotCap)
-                {
-                    if (pos == start)
-                        return fail("too many transitions active at one wavelength for shared memory");
-                    break;
-                }
-                slots.insert(slots.end(), add.begin(), add.end());
-                ++pos;
-            }
-            for (size_t q = start; q < pos; ++q)
-            {
-                const int l2 = las[q];
-                laOff[l2] = (int)entries.size();
-                laCnt[l2] = (int)active[l2].size();
-                for (int g : active[l2])
-                {
-                    int sl = (int)(std::find(slots.begin(), slots.end(), g) - slots.begin());
-                    entries.push_back(DevEntry{g, sl});
-                }
-                c->tileLambda.push_back(l2);
-            }
-            c->tileLa.push_back((int)c->tileLambda.size());
-            c->tileKind.push_back(kind);
-            for (int g : slots)
-                c->tileSlotTrans.push_back(g);
-            c->tileSlotOff.push_back((int)c->tileSlotTrans.size());
-            maxSlots = std::max(maxSlots, (int)slots.size());
-        }
-    }
-    laOff[L] = (int)entries.size();
-    c->Ntile = (int)c->tileLa.size() - 1;
-    c->smemBytes = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchBytes;
-    c->NCH = (K + 31) / 32;
-
     // per-transition wavelength tables
     std::vector<double> wlambdaTab(tabOff), alphaTab(tabOff, 0.0);
     for (int g = 0; g < NT; ++g)
@@ -364,6 +285,161 @@ int build_plan(LwB200Context* c)
         }
     }
 
+    // tiles: contiguous runs of wavelengths, homogeneous in "needs the general kernel",
+    // whose union of active transitions fits the shared-memory accumulator; sized so that
+    // (tiles x columns) fills the GPU several times over
+    const int KP = ((K + 31) / 32) * 32;
+    int maxNlevel = 1;
+    for (int a = 0; a < p.Natom; ++a)
+        maxNlevel = std::max(maxNlevel, c->atoms[a].Nlevel);
+    const size_t scratchFs = (size_t)c->nwarps * 2 * maxNlevel * 32 * sizeof(double);
+    const size_t scratchGamma = (size_t)2 * maxNlevel * KP * sizeof(double);
+    const size_t scratchBytes = std::max(scratchFs, scratchGamma);
+    const size_t smemLimit = 200 * 1024;
+    if (scratchBytes + 4 * KP * sizeof(double) > smemLimit)
+        return fail("atom too large for the shared-memory scratch");
+    // keep the accumulator <= ~48 KB so that several CTAs share an SM
+    const size_t accBudget = std::min<size_t>(smemLimit - scratchBytes, 30 * 1024);
+    const int slotCap = (int)std::max<size_t>(accBudget / (4 * KP * sizeof(double)), 1);
+    const long long targetCtas = 148LL * 16;
+    const int tileLen = (int)std::max<long long>(4, std::min<long long>(32, ((long long)L * p.Ncol) / targetCtas));
+
+    std::vector<DevEntry> entries;
+    std::vector<int> laCnt(L, 0);
+    c->laKind.resize(L);
+    for (int la = 0; la < L; ++la)
+        c->laKind[la] = kind_of(la);
+    int maxSlots = 1;
+    c->tileLa.push_back(0);
+    c->tileSlotOff.push_back(0);
+    {
+        int pos = 0;
+        while (pos < L)
+        {
+            std::vector<int> slots; // transitions of this tile
+            const int start = pos;
+            const bool general = c->laKind[start] == 4;
+            while (pos < L && pos - start < tileLen && (c->laKind[pos] == 4) == general)
+            {
+                std::vector<int> add;
+                for (int g : active[pos])
+                    if (std::find(slots.begin(), slots.end(), g) == slots.end())
+                        add.push_back(g);
+                if ((int)(slots.size() + add.size()) > slotCap && pos > start)
+                    break;
+                if ((int)(slots.size() + add.size()) * 4 * KP * sizeof(double) + scratchBytes > smemLimit)
+                    return fail("too many transitions active at one wavelength for shared memory");
+                slots.insert(slots.end(), add.begin(), add.end());
+                ++pos;
+            }
+            for (int l2 = start; l2 < pos; ++l2)
+            {
+                laOff[l2] = (int)entries.size();
+                laCnt[l2] = (int)active[l2].size();
+                const size_t eFirst = entries.size();
+                for (int g : active[l2])
+                {
+                    int sl = (int)(std::find(slots.begin(), slots.end(), g) - slots.begin());
+                    const DevTrans& d = c->devTrans[g];
+                    const int lt = l2 - d.Nblue;
+                    DevEntry en{};
+                    en.trans = g;
+                    en.slot = sl;
+                    en.type = d.type;
+                    en.i = d.i;
+                    en.j = d.j;
+                    en.levI = d.levI;
+                    en.levJ = d.levJ;
+                    en.contIdx = d.contIdx;
+                    en.Nlevel = c->atoms[d.atom].Nlevel;
+                    en.detailed = d.detailed;
+                    en.atom = d.atom;
+                    constexpr double pi4_h = 4.0 * kPi / kHPlanck;
+                    constexpr double pi4_hc = 1.0 / (0.25 * kHC / kPi);
+                    if (d.type == 0)
+                    {
+                        en.al = 0.0;
+                        en.wlaF = wlambdaTab[d.tabOff + lt] * pi4_hc;
+                    }
+                    else
+                    {
+                        en.al = alphaTab[d.tabOff + lt];
+                        en.wlaF = (wlambdaTab[d.tabOff + lt] * (1.0 / p.wavelength[l2])) * pi4_h;
+                    }
+                    entries.push_back(en);
+                }
+                // atom groups (entries are in (atom, kr) order)
+                for (size_t e = eFirst; e < entries.size();)
+                {
+                    size_t e1 = e + 1;
+                    while (e1 < entries.size()
+                           && c->devTrans[entries[e1].trans].atom == c->devTrans[entries[e].trans].atom)
+                        ++e1;
+                    for (size_t q = e; q < e1; ++q)
+                        entries[q].groupEnd = (int)e1;
+                    e = e1;
+                }
+                c->tileLambda.push_back(l2);
+            }
+            c->tileLa.push_back((int)c->tileLambda.size());
+            c->tileKind.push_back(general ? 4 : 0);
+            for (int g : slots)
+                c->tileSlotTrans.push_back(g);
+            c->tileSlotOff.push_back((int)c->tileSlotTrans.size());
+            maxSlots = std::max(maxSlots, (int)slots.size());
+        }
+    }
+    laOff[L] = (int)entries.size();
+    c->Ntile = (int)c->tileLa.size() - 1;
+    c->smemBytes = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchFs;
+    c->smemGamma = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchGamma;
+    c->NCH = (K + 31) / 32;
+
+    // per-wavelength line slots and moment rows of the pipeline
+    std::vector<LambdaLine> lamLine((size_t)L * 3);
+    std::vector<int> momOff(L, 0);
+    int momRows = 0;
+    for (int la = 0; la < L; ++la)
+    {
+        momOff[la] = momRows;
+        if (c->laKind[la] == 4)
+            continue;
+        momRows += moment_rows(c->laKind[la]);
+        int l = 0;
+        for (int g : active[la])
+        {
+            const DevTrans& d = c->devTrans[g];
+            if (d.type != 0)
+                continue;
+            const int Nl = d.Nred - d.Nblue, lt = la - d.Nblue;
+            LambdaLine ll{};
+            ll.phiOff = d.phiOff + (long long)lt * M * 2 * K;
+            ll.phiColStride = d.phiColStride;
+            ll.rhoOff = d.rhoOff >= 0 ? d.rhoOff + (long long)lt * K : -1;
+            ll.rhoColStride = (long long)Nl * K;
+            ll.trans = g;
+            ll.levI = d.levI;
+            ll.levJ = d.levJ;
+            ll.lineIdx = d.lineIdx;
+            ll.atom = d.atom;
+            ll.i = d.i;
+            ll.j = d.j;
+            ll.wlaS = wlambdaTab[d.tabOff + lt] * (1.0 / (0.25 * kHC / kPi));
+            ll.lambda0 = d.lambda0;
+            ll.Bij = d.Bij;
+            ll.Bji_Bij = d.Bji_Bij;
+            ll.Aji_Bji = d.Aji_Bji;
+            lamLine[(size_t)la * 3 + l++] = ll;
+        }
+    }
+    c->momRows = std::max(momRows, 1);
+    {
+        // columns per pipeline batch: chiC + etaC + moments of one batch stay under ~3 GB
+        const size_t perCol = ((size_t)2 * L + c->momRows) * K * sizeof(double);
+        const size_t cap = (size_t)3 << 30;
+        c->batchCols = (int)std::max<size_t>(1, std::min<size_t>(p.Ncol, std::min<size_t>(512, cap / perCol)));
+    }
+
     // ---- device allocations
     const size_t ncol = p.Ncol;
     if (c->height.alloc(ncol * K) || c->temperature.alloc(ncol * K) || c->muz.alloc(M) || c->wmu.alloc(M)
@@ -376,8 +452,12 @@ int build_plan(LwB200Context* c)
         || c->rhoPrd.alloc((size_t)std::max<long long>(rhoOff, 1))
         || c->accum.alloc(ncol * AccTot * K) || c->prefill.alloc(ncol * std::max(GammaTot, 1) * K)
         || c->gamma.alloc(ncol * std::max(GammaTot, 1) * K) || c->dJ.alloc(ncol * L) || c->djOut.alloc(1)
-        || c->djIdx.alloc(1) || c->dSingular.alloc(1))
+        || c->djIdx.alloc(1) || c->dSingular.alloc(1) || c->dPhiAsym.alloc(1))
         return 1;
+    {
+        const int one = 1; // until the profiles have been looked at, assume nothing
+        CU(cudaMemcpy(c->dPhiAsym.p, &one, sizeof(int), cudaMemcpyHostToDevice));
+    }
     if (p.vlosMu && c->vlosMu.alloc(ncol * M * K))
         return 1;
     CU(cudaMemset(c->J.p, 0, c->J.n * sizeof(double)));
@@ -414,8 +494,14 @@ int build_plan(LwB200Context* c)
         || c->dLaCnt.upload(laCnt) || c->dTileLambda.upload(c->tileLambda) || c->dTileLa.upload(c->tileLa) || c->dTileSlotOff.upload(c->tileSlotOff)
         || c->dTileSlotTrans.upload(c->tileSlotTrans) || c->dAtomNlevel.upload(c->atomNlevel)
         || c->dAtomLevOff.upload(c->atomLevOff) || c->dAtomGammaOff.upload(c->atomGammaOff)
-        || c->dAtomDetailed.upload(c->atomDetailed))
+        || c->dAtomDetailed.upload(c->atomDetailed) || c->dMomOff.upload(momOff) || c->dLaNLines.upload(laNLines)
+        || c->dLamLine.upload(lamLine))
         return 1;
+    {
+        const size_t bc = (size_t)c->batchCols;
+        if (c->chiC.alloc(bc * L * K) || c->etaC.alloc(bc * L * K) || c->mom.alloc(bc * c->momRows * K))
+            return 1;
+    }
     CU(cudaMemcpy(c->muz.p, p.muz, M * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->wmu.p, p.wmu, M * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->wavelength.p, p.wavelength, L * sizeof(double), cudaMemcpyHostToDevice));
@@ -471,6 +557,9 @@ int build_plan(LwB200Context* c)
     P.tileLa = c->dTileLa.p; P.tileSlotOff = c->dTileSlotOff.p; P.tileSlotTrans = c->dTileSlotTrans.p;
     P.atomNlevel = c->dAtomNlevel.p; P.atomLevOff = c->dAtomLevOff.p;
     P.atomGammaOff = c->dAtomGammaOff.p; P.atomDetailed = c->dAtomDetailed.p;
+    P.chiC = c->chiC.p; P.etaC = c->etaC.p; P.mom = c->mom.p; P.momOff = c->dMomOff.p;
+    P.laNLines = c->dLaNLines.p; P.lamLine = c->dLamLine.p; P.momRows = c->momRows;
+    P.phiAsym = c->dPhiAsym.p;
     return 0;
 }
 
@@ -478,23 +567,30 @@ int refresh_tile_lists(LwB200Context* c)
 {
     if (c->listLo == c->laLo && c->listHi == c->laHi)
         return 0;
-    std::vector<int> mom[4], dir, all;
+    std::vector<int> mom, dir, all, kindLam[4];
     for (int t = 0; t < c->Ntile; ++t)
     {
         // tile wavelength lists are ascending: overlap test on first / last
         if (c->tileLambda[c->tileLa[t + 1] - 1] < c->laLo || c->tileLambda[c->tileLa[t]] >= c->laHi)
             continue;
         all.push_back(t);
-        (c->tileKind[t] < 4 ? mom[c->tileKind[t]] : dir).push_back(t);
+        (c->tileKind[t] < 4 ? mom : dir).push_back(t);
     }
+    for (int la = c->laLo; la < c->laHi; ++la)
+        if (c->laKind[la] < 4)
+            kindLam[c->laKind[la]].push_back(la);
     c->dListDirect.release();
     c->dListAll.release();
+    c->dListMoment.release();
+    if (c->dListMoment.upload(mom))
+        return 1;
+    c->nListMoment = (int)mom.size();
     for (int q = 0; q < 4; ++q)
     {
-        c->dListNL[q].release();
-        if (c->dListNL[q].upload(mom[q]))
+        c->dKindLam[q].release();
+        if (c->dKindLam[q].upload(kindLam[q]))
             return 1;
-        c->nListNL[q] = (int)mom[q].size();
+        c->nKindLam[q] = (int)kindLam[q].size();
     }
     if (c->dListDirect.upload(dir) || c->dListAll.upload(all))
         return 1;
@@ -515,6 +611,17 @@ int set_smem_attr(Kern kern, int device)
         return 0;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     done.insert(key);
+    return 0;
+}
+
+int check_phi_symmetry(LwB200Context* c)
+{
+    if (c->P.Nline == 0)
+        return 0;
+    CU(cudaMemsetAsync(c->dPhiAsym.p, 0, sizeof(int), c->stream));
+    const size_t nPairs = c->phi.n / ((size_t)2 * c->P.K);
+    phi_symmetry_kernel<<<148 * 8, 256, 0, c->stream>>>(c->phi.p, nPairs, c->P.K, c->dPhiAsym.p);
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -547,55 +654,79 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
     const int threads = c->nwarps * 32;
     if (MODE == MODE_ITER && !c->forceDirect)
     {
-        // The kinds run CONCURRENTLY: most expensive per wavelength first (3, 2, 1, 0
-        // overlapping lines, then the general kernel), each on its own side stream forked
-        // from / joined to the caller's stream, so that they share one tail instead of
-        // each paying its own (a 1D atmosphere is only a few waves of CTAs in total).
+        // Three-stage pipeline per batch of columns (lwb200_pipeline.cuh):
+        //   continuum_kernel -> ray_kernel<NL> for NL = 3, 2, 1, 0 -> gamma_kernel
+        // The ray kernels of the four kinds run CONCURRENTLY, most expensive per wavelength
+        // first, on prioritised side streams forked from / joined to the caller's stream, so
+        // that they share one tail (a 1D atmosphere is only a few waves of warps in total).
+        // Wavelengths with more than three overlapping lines go through the general kernel.
         if (ensure_side_streams(c))
             return 1;
-        int nside = 0;
-        auto side = [&]() -> cudaStream_t {
-            if (nside == 0)
-                cudaEventRecord(c->evFork, c->stream);
-            cudaStream_t s = c->sideStream[nside];
-            cudaStreamWaitEvent(s, c->evFork, 0);
-            ++nside;
-            return s;
-        };
-        const int order[4] = {3, 2, 1, 0};
-        int nkinds = (c->nListDirect > 0 ? 1 : 0);
-        for (int q = 0; q < 4; ++q)
-            nkinds += c->nListNL[q] > 0 ? 1 : 0;
-        int launched = 0;
-        for (int oi = 0; oi < 4; ++oi)
+        if (set_smem_attr(gamma_kernel, c->device))
+            return 1;
+        const int Ncol = c->prob.Ncol, KP = c->P.KP;
+        for (int colBase = 0; colBase < Ncol; colBase += c->batchCols)
         {
-            const int q = order[oi];
-            if (c->nListNL[q] == 0)
-                continue;
-            // the last kind runs on the caller's stream itself
-            cudaStream_t s = (++launched == nkinds) ? c->stream : side();
-            dim3 grid(c->nListNL[q], c->prob.Ncol);
-            switch (q)
+            const int nb = std::min(c->batchCols, Ncol - colBase);
+            if (c->nListMoment > 0)
             {
-            case 0:
-                if (set_smem_attr(fsm_kernel<NCH, SOLVER, 0>, c->device)) return 1;
-                fsm_kernel<NCH, SOLVER, 0><<<grid, threads, c->smemBytes, s>>>(c->P, c->dListNL[q].p, c->laLo, c->laHi, lambdaIterate, storeDepth);
-                break;
-            case 1:
-                if (set_smem_attr(fsm_kernel<NCH, SOLVER, 1>, c->device)) return 1;
-                fsm_kernel<NCH, SOLVER, 1><<<grid, threads, c->smemBytes, s>>>(c->P, c->dListNL[q].p, c->laLo, c->laHi, lambdaIterate, storeDepth);
-                break;
-            case 2:
-                if (set_smem_attr(fsm_kernel<NCH, SOLVER, 2>, c->device)) return 1;
-                fsm_kernel<NCH, SOLVER, 2><<<grid, threads, c->smemBytes, s>>>(c->P, c->dListNL[q].p, c->laLo, c->laHi, lambdaIterate, storeDepth);
-                break;
-            default:
-                if (set_smem_attr(fsm_kernel<NCH, SOLVER, 3>, c->device)) return 1;
-                fsm_kernel<NCH, SOLVER, 3><<<grid, threads, c->smemBytes, s>>>(c->P, c->dListNL[q].p, c->laLo, c->laHi, lambdaIterate, storeDepth);
-                break;
+                continuum_kernel<<<dim3(c->nListMoment, nb), KP, 0, c->stream>>>(c->P, c->dListMoment.p, c->laLo,
+                                                                                c->laHi, colBase);
+                CU(cudaGetLastError());
+                c->lastLaunches += 1;
             }
-            CU(cudaGetLastError());
-            c->lastLaunches += 1;
+            int nkinds = 0;
+            for (int q = 0; q < 4; ++q)
+                nkinds += c->nKindLam[q] > 0 ? 1 : 0;
+            int nside = 0, launched = 0;
+            for (int q = 3; q >= 0; --q)
+            {
+                const int nLam = c->nKindLam[q];
+                if (nLam == 0)
+                    continue;
+                // the last kind runs on the caller's stream itself
+                cudaStream_t s = c->stream;
+                if (++launched != nkinds)
+                {
+                    if (nside == 0)
+                        CU(cudaEventRecord(c->evFork, c->stream));
+                    s = c->sideStream[nside++];
+                    CU(cudaStreamWaitEvent(s, c->evFork, 0));
+                }
+                const long long warps = (long long)nLam * nb;
+                const int perWarp = (int)std::max<long long>(1, std::min<long long>(4, warps / (148LL * 8 * 8)));
+                const int nw = c->nwarps;
+                dim3 grid((nLam + nw * perWarp - 1) / (nw * perWarp), nb);
+                switch (q)
+                {
+                case 0:
+                    ray_kernel<NCH, SOLVER, 0><<<grid, threads, 0, s>>>(c->P, c->dKindLam[q].p, nLam, perWarp, colBase, lambdaIterate, storeDepth);
+                    break;
+                case 1:
+                    ray_kernel<NCH, SOLVER, 1><<<grid, threads, 0, s>>>(c->P, c->dKindLam[q].p, nLam, perWarp, colBase, lambdaIterate, storeDepth);
+                    break;
+                case 2:
+                    ray_kernel<NCH, SOLVER, 2><<<grid, threads, 0, s>>>(c->P, c->dKindLam[q].p, nLam, perWarp, colBase, lambdaIterate, storeDepth);
+                    break;
+                default:
+                    ray_kernel<NCH, SOLVER, 3><<<grid, threads, 0, s>>>(c->P, c->dKindLam[q].p, nLam, perWarp, colBase, lambdaIterate, storeDepth);
+                    break;
+                }
+                CU(cudaGetLastError());
+                c->lastLaunches += 1;
+            }
+            for (int q = 0; q < nside; ++q)
+            {
+                CU(cudaEventRecord(c->evJoin[q], c->sideStream[q]));
+                CU(cudaStreamWaitEvent(c->stream, c->evJoin[q], 0));
+            }
+            if (c->nListMoment > 0)
+            {
+                gamma_kernel<<<dim3(c->nListMoment, nb), KP, c->smemGamma, c->stream>>>(c->P, c->dListMoment.p,
+                                                                                        c->laLo, c->laHi, colBase);
+                CU(cudaGetLastError());
+                c->lastLaunches += 1;
+            }
         }
         if (c->nListDirect > 0)
         {
@@ -607,11 +738,6 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
                                                              lambdaIterate, 0, storeDepth);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
-        }
-        for (int q = 0; q < nside; ++q)
-        {
-            CU(cudaEventRecord(c->evJoin[q], c->sideStream[q]));
-            CU(cudaStreamWaitEvent(c->stream, c->evJoin[q], 0));
         }
     }
     else if (c->nListAll > 0)
@@ -768,7 +894,7 @@ int lwb200_destroy(LwB200Context* c)
         b->release();
     DevBuf<int>* ints[] = {&c->lowerBcIdx, &c->upperBcIdx, &c->dLaOff, &c->dLaCnt, &c->dTileLambda, &c->dLaHasLine, &c->dTileLa,
                            &c->dTileSlotOff, &c->dTileSlotTrans, &c->dAtomNlevel, &c->dAtomLevOff,
-                           &c->dAtomGammaOff, &c->dAtomDetailed, &c->dSingular};
+                           &c->dAtomGammaOff, &c->dAtomDetailed, &c->dSingular, &c->dPhiAsym};
     for (auto* b : ints)
         b->release();
     for (void* r : c->registered)
@@ -791,7 +917,14 @@ int lwb200_destroy(LwB200Context* c)
     if (c->evK1)
         cudaEventDestroy(c->evK1);
     for (int q = 0; q < 4; ++q)
-        c->dListNL[q].release();
+        c->dKindLam[q].release();
+    c->dListMoment.release();
+    c->dMomOff.release();
+    c->dLaNLines.release();
+    c->dLamLine.release();
+    c->chiC.release();
+    c->etaC.release();
+    c->mom.release();
     c->dListDirect.release();
     c->dListAll.release();
     c->djIdx.release();
@@ -986,6 +1119,8 @@ int lwb200_upload(LwB200Context* c, uint32_t mask)
             if (d.rhoOff >= 0)
                 CU(cudaMemcpyAsync(c->rhoPrd.p + d.rhoOff, t.rhoPrd, ncol * Nl * K * D, H2D, s));
         }
+        if (check_phi_symmetry(c))
+            return 1;
     }
     return 0;
 }
@@ -1087,7 +1222,7 @@ int lwb200_compute_profiles(LwB200Context* c)
                              c->stream, &c->lastLaunches);
     if (rc)
         return fail(std::string("lwb200_compute_profiles: ") + cudaGetErrorString((cudaError_t)rc));
-    return 0;
+    return check_phi_symmetry(c);
 }
 
 int lwb200_finalise(LwB200Context* c)

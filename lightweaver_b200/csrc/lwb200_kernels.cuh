@@ -43,10 +43,36 @@ struct DevTrans
     double lambda0;
 };
 
+// One active transition at one wavelength.  Self-contained: the pipeline kernels read
+// nothing else to know what to do with it (no second indirection through DevTrans).
 struct DevEntry
 {
     int trans;
-    int slot;
+    int slot;          // accumulator slot within the wavelength's tile
+    int type, i, j;    // 0 line / 1 continuum; levels within the atom
+    int levI, levJ;    // rows in the packed population arrays
+    int contIdx;       // continuum index (gRatio row), -1 for lines
+    int groupEnd;      // one past the last entry of the same atom at this wavelength
+    int Nlevel;        // of the atom
+    int detailed;      // atom is detailed-static (rates only, no Gamma)
+    int atom;
+    double al;         // continuum: alpha(lambda); line: 0
+    double wlaF;       // continuum: wlambda / lambda * 4 pi / h;  line: wlambda * 4 pi / (h c)
+};
+
+// Per (wavelength, overlapping-line slot) descriptor built by the planner (<= 3 slots).
+struct LambdaLine
+{
+    long long phiOff;       // element offset of phi(lt, 0, 0, 0) of column 0 in the phi pool
+    long long phiColStride;
+    long long rhoOff;       // element offset of rhoPrd(lt, 0) of column 0; -1: none
+    long long rhoColStride;
+    int trans;              // global transition index
+    int levI, levJ;         // rows in the packed population arrays
+    int lineIdx;
+    int atom, i, j, pad;
+    double lambda0, Bij, Bji_Bij, Aji_Bji;
+    double wlaS;            // wlambda * 4 pi / (h c)  (times wphi(k) gives wla)
 };
 
 struct DevProblem
@@ -79,6 +105,14 @@ struct DevProblem
     const int* atomLevOff;
     const int* atomGammaOff;
     const int* atomDetailed;
+    // three-stage pipeline (lwb200_pipeline.cuh); chiC/etaC/mom hold one batch of columns
+    double *chiC, *etaC;      // [batch][L][K]
+    double* mom;              // [batch][momRows][K]
+    const int* momOff;        // [L] first moment row of a wavelength
+    const int* laNLines;      // [L] number of overlapping lines
+    const LambdaLine* lamLine; // [L][3]
+    int momRows;
+    const int* phiAsym;       // 0: phi(.., dir 0, .) == phi(.., dir 1, .) everywhere (static atmosphere)
 };
 
 // U, V for one transition at one (wavelength, ray, depth): Transition::uv

@@ -1,0 +1,730 @@
+// lwb200_pipeline.cuh -- the production Gamma iteration as a three-stage pipeline.
+//
+//   continuum_kernel   per (column, wavelength, depth): background + every active
+//                      continuum -> chiC, etaC  (the ray-independent part of
+//                      chi_eta_aux_accum, SimdFullIterationTemplates.hpp:59-109,
+//                      with gij of Atom::setup_wavelength, LwAtom.hpp:82-128)
+//   ray_kernel         one warp = one wavelength of one column, lanes over depth:
+//                      line opacities, source function, formal solution of the
+//                      2*Nrays rays, J, dJ, emergent I, and the RAY MOMENTS
+//                      sum_r w {Psi*, p, p I, p Psi*, p p' Psi*} written to HBM
+//   gamma_kernel       per (column, wavelength tile), one thread per depth: Gamma
+//                      and Rij/Rji from J and the moments
+//                      (compute_full_Ieff / compute_full_operator_rates, :192-234)
+//
+// Why three kernels.  The formal solution is a latency-bound fp64 recurrence that
+// runs at 8 warps/SM; every dependent global load issued from inside it (transition
+// tables, populations, shared-memory atomics of the rate accumulation) stalls a
+// whole wavelength.  Measured on B200 (differential builds, tools/variants.py): in
+// the fused kernel the per-wavelength set-up was 14 % and the Gamma/rate epilogue
+// 31 % of the time although together they are < 15 % of the flops.  Split off, both
+// become plain streaming kernels at high occupancy, and the rate accumulation needs
+// no atomics at all inside a CTA (one thread owns one depth).  The price is HBM
+// traffic for chiC/etaC and the moments (~1.2x the algorithmic bytes on top), which
+// is free here: the path uses < 10 % of the HBM bandwidth.
+//
+// Moment form (unchanged from round 1): with p = phi for a line and 1 for a
+// continuum, Vij = v p, Vji = g v p, Uji = u g v p and chi_atom(m), U_atom(m),
+// eta_atom are linear in the p's, so every sum over the rays of one wavelength in
+// compute_full_operator_rates reduces to the moments above and the per-transition
+// work runs once per wavelength instead of once per ray.
+#pragma once
+#include "lwb200_fsm.cuh"
+
+namespace lwb200
+{
+// number of moment rows of a wavelength with NL overlapping lines:
+//   Psi*, then per line {p, p I, p Psi*, p^2 Psi*}, then the cross terms p_a p_b Psi* (a < b)
+__host__ __device__ constexpr int moment_rows(int NL) { return 1 + 4 * NL + NL * (NL - 1) / 2; }
+
+// ---------------------------------------------------------------------------
+// Are the profiles of the two directions of every (line wavelength, mu) bitwise identical?
+// (They are whenever vlos = 0 and the profile is the default Voigt; a line model that
+// overrides compute_phi may break it, which is why the data is checked, not the flags.)
+// The phi pool is a sequence of [2][K] blocks.  Runs after every profile upload / generation.
+__global__ void phi_symmetry_kernel(const double* __restrict__ phi, size_t nPairs, int K, int* __restrict__ asym)
+{
+    bool diff = false;
+    const size_t total = nPairs * (size_t)K;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x)
+    {
+        const size_t pair = idx / K;
+        const int k = (int)(idx % K);
+        const double a = phi[pair * 2 * K + k], b = phi[(pair * 2 + 1) * K + k];
+        diff |= (__double_as_longlong(a) != __double_as_longlong(b));
+    }
+    if (__any_sync(kFull, diff) && lane_id() == 0)
+        atomicOr(asym, 1);
+}
+
+// ---------------------------------------------------------------------------
+// Stage 1: chiC, etaC.  Grid (tiles, columns of the batch), one thread per depth.
+__global__ void continuum_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi,
+                                 int colBase)
+{
+    const int K = P.K, L = P.L;
+    const int tile = tileList[blockIdx.x];
+    const int cb = blockIdx.y, col = colBase + cb;
+    const int k = threadIdx.x;
+    if (k >= K)
+        return;
+    const double Tk = __ldg(P.temperature + (size_t)col * K + k);
+    const double* ncol = P.n + (size_t)col * P.NlevTot * K + k;
+    const double* gcol = P.gRatio + (size_t)col * K + k;
+    const int tlBeg = P.tileLa[tile], tlEnd = P.tileLa[tile + 1];
+    for (int tl = tlBeg; tl < tlEnd; ++tl)
+    {
+        const int la = P.tileLambda[tl];
+        if (la < laLo || la >= laHi)
+            continue;
+        const double lambda = __ldg(P.wavelength + la);
+        const double rlambda = 1.0 / lambda;
+        constexpr double hc_k = kHC / (kKBoltzmann * kNmToM);
+        constexpr double twoHc = 2.0 * kHC / (kNmToM * kNmToM * kNmToM);
+        const double hc_kl = hc_k * rlambda;
+        const double hcl = twoHc * (rlambda * rlambda * rlambda);
+        const size_t rowLK = ((size_t)col * L + la) * K + k;
+        double chiC = __ldg(P.chiBg + rowLK);
+        double etaC = __ldg(P.etaBg + rowLK);
+        const double expfac = exp_fast(-hc_kl / Tk);
+        const int eBeg = P.laOff[la], eEnd = eBeg + P.laCnt[la];
+        for (int e = eBeg; e < eEnd; ++e)
+        {
+            const DevEntry& t = P.entries[e];
+            if (t.type == 0)
+                continue;
+            const double al = t.al;
+            const double gk = __ldg(gcol + (size_t)t.contIdx * P.Ncol * K) * expfac;
+            const double Vji = gk * al;
+            const double ni = __ldg(ncol + (size_t)t.levI * K);
+            const double nj = __ldg(ncol + (size_t)t.levJ * K);
+            chiC += ni * al - nj * Vji;
+            etaC += nj * (hcl * Vji);
+        }
+        const size_t o = ((size_t)cb * L + la) * K + k;
+        P.chiC[o] = chiC;
+        P.etaC[o] = etaC;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Stage 2: the rays.
+#ifndef LWB200_RAY_MINBLOCKS
+#define LWB200_RAY_MINBLOCKS 2
+#endif
+
+template <int NCH, int SOLVER, int NL>
+__global__ void __launch_bounds__(128, LWB200_RAY_MINBLOCKS)
+ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int perWarp, int colBase,
+           int lambdaIterate, int storeDepth)
+{
+    constexpr int NLA = NL > 0 ? NL : 1;
+    constexpr int NPAIR = NL > 1 ? NL * (NL - 1) / 2 : 1;
+    const int K = P.K, M = P.M, L = P.L;
+    const int cb = blockIdx.y, col = colBase + cb;
+    // warp index made provably warp-uniform: every loop below stays convergent
+    const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0);
+    const int lane = lane_id();
+    const int first = (blockIdx.x * (blockDim.x >> 5) + warp) * perWarp;
+    if (first >= nLam)
+        return;
+
+    GeometryR<NCH> g;
+    load_geometry_r<NCH>(g, P.height + (size_t)col * K, K);
+    const double* Tcol = P.temperature + (size_t)col * K;
+    const double* ncol = P.n + (size_t)col * P.NlevTot * K;
+
+    for (int q = first; q < min(first + perWarp, nLam); ++q)
+    {
+        const int la = lamList[q];
+        const double lambda = __ldg(P.wavelength + la);
+        const double rlambda = 1.0 / lambda;
+        const size_t rowLK = ((size_t)col * L + la) * K;
+        const size_t rowB = ((size_t)cb * L + la) * K;
+        constexpr double hc_4pi = 0.25 * kHC / kPi;
+
+        double chiC[NCH], etaC[NCH], scaJ[NCH];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            const int k = lane * NCH + j;
+            const bool v = k < K;
+            chiC[j] = v ? __ldg(P.chiC + rowB + k) : 1.0;
+            etaC[j] = v ? __ldg(P.etaC + rowB + k) : 0.0;
+            const double sca = v ? __ldg(P.scaBg + rowLK + k) : 0.0;
+            const double JDag = v ? P.J[rowLK + k] : 0.0;
+            scaJ[j] = sca * JDag;
+        }
+        // line slots: chi = chiC + sum_l cX_l phi_l, eta = etaC + sum_l cE_l phi_l
+        double cX[NLA][NCH], cE[NLA][NCH];
+        const double* ph[NLA];
+#pragma unroll
+        for (int l = 0; l < NLA; ++l)
+        {
+            ph[l] = P.phi;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+                cX[l][j] = cE[l][j] = 0.0;
+            if (NL > 0)
+            {
+                const LambdaLine& ll = P.lamLine[(size_t)la * 3 + l];
+                // constants of Transition::uv (LwTransition.hpp:93-130)
+                const double vB = hc_4pi * (ll.lambda0 * rlambda) * ll.Bij;
+                const double gS = ll.Bji_Bij;
+                const double* rho = (ll.rhoOff >= 0) ? P.rhoPrd + ll.rhoOff + (size_t)col * ll.rhoColStride : nullptr;
+                ph[l] = P.phi + ll.phiOff + (size_t)col * ll.phiColStride + lane * NCH;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+                {
+                    const int k = lane * NCH + j;
+                    if (k < K)
+                    {
+                        const double ni = __ldg(ncol + (size_t)ll.levI * K + k);
+                        const double nj = __ldg(ncol + (size_t)ll.levJ * K + k);
+                        const double gk = rho ? gS * __ldg(rho + k) : gS;
+                        cX[l][j] = vB * (ni - nj * gk);
+                        cE[l][j] = nj * (ll.Aji_Bji * (gk * vB));
+                    }
+                }
+            }
+        }
+
+        // thermalised boundaries: Planck function at the two boundary pairs (once per wavelength)
+        double Btop0 = 0.0, Btop1 = 0.0, Bbot0 = 0.0, Bbot1 = 0.0;
+        if (P.upperBc == 2)
+        {
+            Btop0 = planck_nu(__ldg(Tcol + 0), lambda);
+            Btop1 = planck_nu(__ldg(Tcol + 1), lambda);
+        }
+        if (P.lowerBc == 2)
+        {
+            Bbot0 = planck_nu(__ldg(Tcol + K - 1), lambda);
+            Bbot1 = planck_nu(__ldg(Tcol + K - 2), lambda);
+        }
+
+        // ---- moments over the rays of this wavelength
+        //   mJ = sum w I, mP = sum w Psi*, mW[l] = sum w p_l, mA[l] = sum w p_l I,
+        //   mB0[l] = sum w Psi* p_l, mB[l] = sum w Psi* p_l^2, mBx[(a,b)] = sum w Psi* p_a p_b (a < b)
+        double mJ[NCH], mP[NCH], mW[NLA][NCH], mA[NLA][NCH], mB0[NLA][NCH], mB[NLA][NCH], mBx[NPAIR][NCH];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            mJ[j] = mP[j] = 0.0;
+#pragma unroll
+            for (int l = 0; l < NLA; ++l)
+                mW[l][j] = mA[l][j] = mB0[l][j] = mB[l][j] = 0.0;
+#pragma unroll
+            for (int pq = 0; pq < NPAIR; ++pq)
+                mBx[pq][j] = 0.0;
+        }
+        double chi[NCH], S[NCH], rchi[NCH], p[NLA][NCH];
+        RayPre<NCH> pre;
+        // the up and down rays of one mu share opacities, source function and the whole
+        // direction-independent phase of the solver when their profiles are identical
+        const bool shareDir = (SOLVER == 2) && !storeDepth && (__ldg(P.phiAsym) == 0);
+
+        // line-free wavelengths: chi and S are the same for every ray; interpolation data once at mu = 1
+        RayPre<NCH> pre1;
+        if (NL == 0)
+        {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+            {
+                chi[j] = chiC[j];
+                rchi[j] = rcp_fast(chiC[j]);
+                S[j] = (etaC[j] + scaJ[j]) * rchi[j]; // compute_source_fn (:169-179)
+                p[0][j] = 0.0;
+            }
+            if (SOLVER == 2)
+                bezier3_prepare<NCH>(g, chi, S, 1.0, 1.0, pre1);
+        }
+        // profiles are fetched one ray ahead (NL <= 2; three lines leave no registers for it)
+#ifdef LWB200_NO_PREFETCH
+        constexpr bool PREFETCH = false;
+#else
+        constexpr bool PREFETCH = (NL == 1 || NL == 2);
+#endif
+        double pn[NLA][NCH];
+        if (PREFETCH)
+        {
+#pragma unroll
+            for (int l = 0; l < NLA; ++l)
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+                    pn[l][j] = (lane * NCH + j < K) ? __ldg(ph[l] + j) : 0.0;
+        }
+
+        for (int mu = 0; mu < M; ++mu)
+        {
+            const double muz = __ldg(P.muz + mu);
+            const double zmu = rcp_fast(muz);
+            const double w = 0.5 * __ldg(P.wmu + mu);
+            if (NL == 0 && SOLVER == 2)
+            {
+                const RayPre<NCH>& q1 = pre1;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+                {
+                    pre.SN[j] = q1.SN[j];
+                    pre.dtf[j] = q1.dtf[j] * zmu;
+                    pre.rdtf[j] = q1.rdtf[j] * muz;
+                    pre.DSf[j] = q1.DSf[j] * muz;
+                }
+            }
+#pragma unroll
+            for (int dir = 0; dir < 2; ++dir)
+            {
+                if (NL > 0 && (dir == 0 || !shareDir))
+                {
+                    const int row = 2 * mu + dir;
+                    if (PREFETCH)
+                    {
+                        const int nextRow = shareDir ? row + 2 : row + 1;
+#pragma unroll
+                        for (int l = 0; l < NLA; ++l)
+#pragma unroll
+                            for (int j = 0; j < NCH; ++j)
+                            {
+                                p[l][j] = pn[l][j];
+                                if (nextRow < 2 * M)
+                                    pn[l][j]
+                                        = (lane * NCH + j < K) ? __ldg(ph[l] + (size_t)nextRow * K + j) : 0.0;
+                            }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int l = 0; l < NLA; ++l)
+#pragma unroll
+                            for (int j = 0; j < NCH; ++j)
+                                p[l][j] = (lane * NCH + j < K) ? __ldg(ph[l] + (size_t)row * K + j) : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+                    {
+                        const int k = lane * NCH + j;
+                        double c = chiC[j], e = etaC[j];
+#pragma unroll
+                        for (int l = 0; l < NLA; ++l)
+                        {
+                            c = fma(cX[l][j], p[l][j], c);
+                            e = fma(cE[l][j], p[l][j], e);
+                        }
+                        chi[j] = c;
+                        rchi[j] = rcp_fast(c);
+                        S[j] = (e + scaJ[j]) * rchi[j]; // compute_source_fn (:169-179)
+                        if (storeDepth && k < K)
+                        {
+                            const size_t off = ((((size_t)col * L + la) * M + mu) * 2 + dir) * K + k;
+                            P.depthChi[off] = c;
+                            P.depthEta[off] = e;
+                        }
+                    }
+                    if (SOLVER == 2)
+                        bezier3_prepare<NCH>(g, chi, S, muz, zmu, pre);
+                }
+                else if (NL == 0 && storeDepth)
+                {
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+                    {
+                        const int k = lane * NCH + j;
+                        if (k < K)
+                        {
+                            const size_t off = ((((size_t)col * L + la) * M + mu) * 2 + dir) * K + k;
+                            P.depthChi[off] = chiC[j];
+                            P.depthEta[off] = etaC[j];
+                        }
+                    }
+                }
+                int bcType;
+                double bcB0, bcB1, bcValue = 0.0;
+                if (dir == 1)
+                {
+                    bcType = P.lowerBc;
+                    bcB0 = Bbot0;
+                    bcB1 = Bbot1;
+                    if (bcType == 4)
+                        bcValue = P.lowerBcData[((size_t)col * L + la) * P.NlowerBcMu + P.lowerBcIdx[mu * 2 + 1]];
+                }
+                else
+                {
+                    bcType = P.upperBc;
+                    bcB0 = Btop0;
+                    bcB1 = Btop1;
+                    if (bcType == 4)
+                        bcValue = P.upperBcData[((size_t)col * L + la) * P.NupperBcMu + P.upperBcIdx[mu * 2 + 0]];
+                }
+                double I[NCH], psi[NCH];
+                if (SOLVER == 2)
+                {
+                    if (dir == 0)
+                        bezier3_sweep<NCH, true>(g, chi, S, rchi, pre, zmu, bcType, bcB0, bcB1, bcValue, I, psi);
+                    else
+                        bezier3_sweep<NCH, false>(g, chi, S, rchi, pre, zmu, bcType, bcB0, bcB1, bcValue, I, psi);
+                }
+                else
+                    local_stencil_ray<NCH, SOLVER>(g, chi, S, rchi, muz, dir == 0, bcType, bcB0, bcB1, bcValue, I,
+                                                   psi);
+
+                if (lane == 0)
+                    P.I[((size_t)col * L + la) * M + mu] = I[0];
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+                {
+                    const int k = lane * NCH + j;
+                    if (storeDepth && k < K)
+                        P.depthI[((((size_t)col * L + la) * M + mu) * 2 + dir) * K + k] = I[j];
+                    const double wI = w * I[j];
+                    const double wP = lambdaIterate ? 0.0 : w * psi[j];
+                    mJ[j] += wI;
+                    mP[j] += wP;
+                    if (NL > 0)
+                    {
+                        double tq[NLA];
+#pragma unroll
+                        for (int l = 0; l < NLA; ++l)
+                        {
+                            tq[l] = wP * p[l][j];
+                            mW[l][j] = fma(w, p[l][j], mW[l][j]);
+                            mA[l][j] = fma(wI, p[l][j], mA[l][j]);
+                            mB0[l][j] += tq[l];
+                            mB[l][j] = fma(tq[l], p[l][j], mB[l][j]);
+                        }
+                        if (NL > 1)
+                        {
+                            int pr = 0;
+#pragma unroll
+                            for (int a = 0; a < NLA; ++a)
+#pragma unroll
+                                for (int b = a + 1; b < NLA; ++b)
+                                {
+                                    mBx[pr][j] = fma(tq[a], p[b][j], mBx[pr][j]);
+                                    ++pr;
+                                }
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- J row, dJ (:477-485) and the moment rows
+        double dJ = 0.0;
+        double* mom = P.mom + ((size_t)cb * P.momRows + P.momOff[la]) * K;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            const int k = lane * NCH + j;
+            if (k < K)
+            {
+                const double JDag = P.J[rowLK + k];
+                P.J[rowLK + k] = mJ[j];
+                const double d = fabs(1.0 - JDag / mJ[j]);
+                dJ = (d < dJ) ? dJ : d;
+                mom[k] = mP[j];
+                if (NL > 0)
+                {
+#pragma unroll
+                    for (int l = 0; l < NLA; ++l)
+                    {
+                        mom[(size_t)(1 + 4 * l) * K + k] = mW[l][j];
+                        mom[(size_t)(2 + 4 * l) * K + k] = mA[l][j];
+                        mom[(size_t)(3 + 4 * l) * K + k] = mB0[l][j];
+                        mom[(size_t)(4 + 4 * l) * K + k] = mB[l][j];
+                    }
+                    if (NL > 1)
+                    {
+#pragma unroll
+                        for (int pr = 0; pr < NPAIR; ++pr)
+                            mom[(size_t)(1 + 4 * NL + pr) * K + k] = mBx[pr][j];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+        {
+            const double o = __shfl_xor_sync(kFull, dJ, d);
+            dJ = (o < dJ) ? dJ : o;
+        }
+        if (lane == 0)
+            P.dJ[(size_t)col * L + la] = dJ;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Stage 3: Gamma and rates from J and the moments.  Grid (tiles, columns of the batch),
+// one thread per depth; the tile's per-transition partial sums live in shared memory with
+// a single writer per element (no atomics) and are flushed once with fp64 RED.
+//
+// Profile members of an atom at one wavelength: q = 0 the continua (p = 1), q = l + 1 the
+// line in slot l.  M(q, q') = sum_r w Psi* p_q p_q'.
+template <int NL>
+__device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int col, int cb, int k, double Tk,
+                                             double W0, double* __restrict__ acc, double* __restrict__ Xs,
+                                             double* __restrict__ Us, int KP)
+{
+    constexpr int NLA = NL > 0 ? NL : 1;
+    constexpr int NQ = NL + 1;
+    const int K = P.K;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const double lambda = __ldg(P.wavelength + la);
+    const double rlambda = 1.0 / lambda;
+    constexpr double hc_k = kHC / (kKBoltzmann * kNmToM);
+    constexpr double twoHc = 2.0 * kHC / (kNmToM * kNmToM * kNmToM);
+    constexpr double hc_4pi = 0.25 * kHC / kPi;
+    const double hc_kl = hc_k * rlambda;
+    const double hcl = twoHc * (rlambda * rlambda * rlambda);
+    const double* ncol = P.n + (size_t)col * P.NlevTot * K + k;
+    const double* gcol = P.gRatio + (size_t)col * K + k;
+
+    // moments of this wavelength at depth k (independent loads, issued together)
+    const double* mom = P.mom + ((size_t)cb * P.momRows + P.momOff[la]) * K + k;
+    const double mJ = P.J[((size_t)col * P.L + la) * K + k];
+    double Mq[NQ][NQ], mW[NLA], mA[NLA];
+    Mq[0][0] = mom[0];
+    {
+        int pr = 0;
+#pragma unroll
+        for (int a = 0; a < NL; ++a)
+        {
+            mW[a] = mom[(size_t)(1 + 4 * a) * K];
+            mA[a] = mom[(size_t)(2 + 4 * a) * K];
+            Mq[0][a + 1] = Mq[a + 1][0] = mom[(size_t)(3 + 4 * a) * K];
+            Mq[a + 1][a + 1] = mom[(size_t)(4 + 4 * a) * K];
+#pragma unroll
+            for (int b = a + 1; b < NL; ++b)
+            {
+                Mq[a + 1][b + 1] = Mq[b + 1][a + 1] = mom[(size_t)(1 + 4 * NL + pr) * K];
+                ++pr;
+            }
+        }
+    }
+    const double expfac = exp_fast(-hc_kl / Tk);
+
+    // line slots of this wavelength
+    int lsTrans[NLA], lsAtom[NLA], lsI[NLA], lsJ[NLA];
+    double lsV[NLA], lsGv[NLA], lsUgv[NLA], lsX[NLA], lsE[NLA], lsWla[NLA];
+#pragma unroll
+    for (int l = 0; l < NLA; ++l)
+    {
+        lsTrans[l] = lsAtom[l] = -1;
+        lsI[l] = lsJ[l] = 0;
+        lsV[l] = lsGv[l] = lsUgv[l] = lsX[l] = lsE[l] = lsWla[l] = 0.0;
+        if (NL > 0)
+        {
+            const LambdaLine& ll = P.lamLine[(size_t)la * 3 + l];
+            const double vB = hc_4pi * (ll.lambda0 * rlambda) * ll.Bij;
+            const double gS = ll.Bji_Bij;
+            const double r = (ll.rhoOff >= 0) ? __ldg(P.rhoPrd + ll.rhoOff + (size_t)col * ll.rhoColStride + k) : 1.0;
+            const double gk = (ll.rhoOff >= 0) ? gS * r : gS;
+            const double ni = __ldg(ncol + (size_t)ll.levI * K);
+            const double nj = __ldg(ncol + (size_t)ll.levJ * K);
+            lsTrans[l] = ll.trans;
+            lsAtom[l] = ll.atom;
+            lsI[l] = ll.i;
+            lsJ[l] = ll.j;
+            lsV[l] = vB;
+            lsGv[l] = (gS * vB) * r;
+            lsUgv[l] = (ll.Aji_Bji * (gS * vB)) * r;
+            lsX[l] = vB * (ni - nj * gk);
+            lsE[l] = nj * (ll.Aji_Bji * (gk * vB));
+            lsWla[l] = ll.wlaS * __ldg(P.wphi + ((size_t)ll.lineIdx * P.Ncol + col) * K + k);
+        }
+    }
+
+    const int eBeg = P.laOff[la], eEnd = eBeg + P.laCnt[la];
+    int e0 = eBeg;
+    while (e0 < eEnd)
+    {
+        const DevEntry& first = P.entries[e0];
+        const int e1 = first.groupEnd;
+        const bool detailed = first.detailed != 0;
+        const int N = first.Nlevel;
+        const int atom = first.atom;
+        double E0 = 0.0;
+        if (!detailed)
+        {
+            // continuum aggregates per level: chi_atom / U_atom of chi_eta_aux_accum (:59-109)
+            for (int m = 0; m < N; ++m)
+            {
+                Xs[m * nthr + tid] = 0.0;
+                Us[m * nthr + tid] = 0.0;
+            }
+            for (int e = e0; e < e1; ++e)
+            {
+                const DevEntry& t = P.entries[e];
+                if (t.type == 0)
+                    continue;
+                const double al = t.al;
+                const double gk = __ldg(gcol + (size_t)t.contIdx * P.Ncol * K) * expfac;
+                const double Vji = gk * al;
+                const double Uji = hcl * Vji;
+                const double ni = __ldg(ncol + (size_t)t.levI * K);
+                const double nj = __ldg(ncol + (size_t)t.levJ * K);
+                const double x = ni * al - nj * Vji;
+                Xs[t.i * nthr + tid] += x;
+                Xs[t.j * nthr + tid] -= x;
+                Us[t.j * nthr + tid] += Uji;
+                E0 += nj * Uji;
+            }
+        }
+        // line members of this atom: per-unit-phi coefficients (0 for other atoms' lines)
+        double Xl[NLA], ugvl[NLA], Eq[NQ];
+        Eq[0] = E0;
+#pragma unroll
+        for (int l = 0; l < NLA; ++l)
+        {
+            Xl[l] = ugvl[l] = 0.0;
+            if (NL > 0)
+            {
+                const bool own = lsAtom[l] == atom;
+                Xl[l] = own ? lsX[l] : 0.0;
+                ugvl[l] = own ? lsUgv[l] : 0.0;
+                Eq[l + (NL > 0 ? 1 : 0)] = own ? lsE[l] : 0.0;
+            }
+        }
+        // EB[q] = sum_q' E_q' M(q, q')
+        double EB[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+        {
+            double s = 0.0;
+#pragma unroll
+            for (int q2 = 0; q2 < NQ; ++q2)
+                s = fma(Eq[q2], Mq[q][q2], s);
+            EB[q] = s;
+        }
+
+        for (int e = e0; e < e1; ++e)
+        {
+            const DevEntry& t = P.entries[e];
+            double v = 0.0, gv = 0.0, ugv = 0.0, Wq = W0, Aq = mJ, EBq = EB[0], wla = 0.0;
+            if (t.type != 0)
+            {
+                const double gk = __ldg(gcol + (size_t)t.contIdx * P.Ncol * K) * expfac;
+                v = t.al;
+                gv = gk * t.al;
+                ugv = hcl * gv;
+                wla = t.wlaF;
+            }
+#pragma unroll
+            for (int l = 0; l < NL; ++l)
+            {
+                if (t.type == 0 && t.trans == lsTrans[l])
+                {
+                    v = lsV[l];
+                    gv = lsGv[l];
+                    ugv = lsUgv[l];
+                    Wq = mW[l];
+                    Aq = mA[l];
+                    EBq = EB[l + 1];
+                    wla = lsWla[l];
+                }
+            }
+            double* a4 = acc + (size_t)t.slot * 4 * KP + k;
+            if (!detailed)
+            {
+                // chi_atom(m) = sum_q p_q X_q(m), U_atom(m) = sum_q p_q U_q(m)
+                double Xi[NQ], Xj[NQ], Ui[NQ], Uj[NQ];
+                Xi[0] = Xs[t.i * nthr + tid];
+                Xj[0] = Xs[t.j * nthr + tid];
+                Ui[0] = Us[t.i * nthr + tid];
+                Uj[0] = Us[t.j * nthr + tid];
+#pragma unroll
+                for (int l = 0; l < NL; ++l)
+                {
+                    Xi[l + 1] = t.i == lsI[l] ? Xl[l] : (t.i == lsJ[l] ? -Xl[l] : 0.0);
+                    Xj[l + 1] = t.j == lsI[l] ? Xl[l] : (t.j == lsJ[l] ? -Xl[l] : 0.0);
+                    Ui[l + 1] = t.i == lsJ[l] ? ugvl[l] : 0.0;
+                    Uj[l + 1] = t.j == lsJ[l] ? ugvl[l] : 0.0;
+                }
+                // sum_r w Psi* chi_atom(a) U_atom(b) = sum_{q,q'} X_q(a) M(q,q') U_q'(b)
+                double XUij = 0.0, XUji = 0.0;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                {
+                    double mj = 0.0, mi = 0.0;
+#pragma unroll
+                    for (int q2 = 0; q2 < NQ; ++q2)
+                    {
+                        mj = fma(Mq[q][q2], Uj[q2], mj);
+                        mi = fma(Mq[q][q2], Ui[q2], mi);
+                    }
+                    XUij = fma(Xi[q], mj, XUij);
+                    XUji = fma(Xj[q], mi, XUji);
+                }
+                // sum_r w [(Uji + Vji Ieff) - Psi* chi(i) U(j)],  Ieff = I - Psi* eta_atom
+                a4[0] += (ugv * Wq + gv * (Aq - EBq) - XUij) * wla;
+                a4[KP] += (v * (Aq - EBq) - XUji) * wla;
+            }
+            a4[2 * KP] += (v * Aq) * wla;
+            a4[3 * KP] += (ugv * Wq + gv * Aq) * wla;
+        }
+        e0 = e1;
+    }
+}
+
+__global__ void __launch_bounds__(128, 5) gamma_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi,
+                             int colBase)
+{
+    extern __shared__ double smem[];
+    const int K = P.K, KP = P.KP;
+    const int tile = tileList[blockIdx.x];
+    const int cb = blockIdx.y, col = colBase + cb;
+    const int k = threadIdx.x;
+    const int slot0 = P.tileSlotOff[tile];
+    const int nslot = P.tileSlotOff[tile + 1] - slot0;
+    double* acc = smem;                                   // [nslot][4][KP]
+    double* Xs = smem + (size_t)P.maxSlots * 4 * KP;      // [maxNlevel][blockDim]
+    double* Us = Xs + (size_t)P.maxNlevel * blockDim.x;
+    for (int idx = threadIdx.x; idx < nslot * 4 * KP; idx += blockDim.x)
+        acc[idx] = 0.0;
+    __syncthreads();
+    if (k < K)
+    {
+        const double Tk = __ldg(P.temperature + (size_t)col * K + k);
+        // W0 = sum_r w over both directions of every mu, in the ray order of ray_kernel
+        double W0 = 0.0;
+        for (int mu = 0; mu < P.M; ++mu)
+        {
+            const double w = 0.5 * __ldg(P.wmu + mu);
+            W0 += w;
+            W0 += w;
+        }
+        const int tlBeg = P.tileLa[tile], tlEnd = P.tileLa[tile + 1];
+        for (int tl = tlBeg; tl < tlEnd; ++tl)
+        {
+            const int la = P.tileLambda[tl];
+            if (la < laLo || la >= laHi)
+                continue;
+            switch (P.laNLines[la])
+            {
+            case 0: gamma_lambda<0>(P, la, col, cb, k, Tk, W0, acc, Xs, Us, KP); break;
+            case 1: gamma_lambda<1>(P, la, col, cb, k, Tk, W0, acc, Xs, Us, KP); break;
+            case 2: gamma_lambda<2>(P, la, col, cb, k, Tk, W0, acc, Xs, Us, KP); break;
+            case 3: gamma_lambda<3>(P, la, col, cb, k, Tk, W0, acc, Xs, Us, KP); break;
+            default: break; // > 3 overlapping lines: handled by the general kernel
+            }
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nslot * 4 * KP; idx += blockDim.x)
+    {
+        const int kk = idx % KP;
+        const int q = (idx / KP) & 3;
+        const int s = idx / (4 * KP);
+        if (kk >= K)
+            continue;
+        const DevTrans& t = P.trans[P.tileSlotTrans[slot0 + s]];
+        const int row = q == 0 ? t.accIJ : q == 1 ? t.accJI : q == 2 ? t.accRij : t.accRji;
+        if (row < 0)
+            continue;
+        const double v = acc[idx];
+        if (v != 0.0)
+            atomicAdd(P.accum + ((size_t)col * P.AccTot + row) * K + kk, v);
+    }
+}
+
+} // namespace lwb200

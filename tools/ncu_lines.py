@@ -5,7 +5,7 @@ import csv, re, subprocess, sys, os, tempfile, glob
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 45
 tmp = tempfile.mkdtemp()
-so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'lightweaver_b200', 'liblwb200.so')
+so = os.environ.get('LWB200_LIB') or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'lightweaver_b200', 'liblwb200.so')
 subprocess.run(['cuobjdump', '-xelf', 'all', so], cwd=tmp, capture_output=True)
 dis = subprocess.run(['nvdisasm', '-g', '-c'] + glob.glob(tmp + '/*.cubin'), capture_output=True, text=True).stdout.splitlines()
 # locate function
@@ -23,7 +23,9 @@ for l in dis[start + 1:]:
         continue
     if re.match(r'\s+/\*[0-9a-f]{4,}\*/', l):
         lines.append(cur)
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+kid = os.environ.get('NCU_KERNEL_ID')  # e.g. ::regex:ray_kernel:1 when the report holds several kernels
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'] + (['--kernel-id', kid] if kid else []),
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = next(i for i, r in enumerate(rows) if 'Instructions Executed' in r)
 hdr = rows[hi]

@@ -29,7 +29,7 @@ def build(specs):
         out, _ = pr.communicate()
         lines = out.splitlines()
         for i, ln in enumerate(lines):
-            if 'fsm_kernel' in ln and 'Compiling' in ln:
+            if ('ray_kernel' in ln or 'gamma_kernel' in ln) and 'Compiling' in ln:
                 print(name, ln.split("'")[1][:60], '|', lines[i + 1].strip(), '|', lines[i + 2].strip())
         if pr.returncode:
             print(name, 'FAILED\n', out[-3000:])
