@@ -142,9 +142,12 @@ enum {
     LWB200_STORE_DEPTH    = 1u << 1, /* depthData.fill */
     LWB200_DEFER_FINALISE = 1u << 2, /* leave [Gamma|R] partial sums un-finalised (lambda-sharded
                                         ranks all-reduce them, then call lwb200_finalise) */
-    LWB200_GENERAL_KERNEL = 1u << 3  /* run every wavelength through the general per-ray accumulation
-                                        kernel (normally only wavelengths with > 2 overlapping lines);
-                                        a cross-check of the moment kernel, not a fast path */
+    LWB200_GENERAL_KERNEL = 1u << 3, /* run every wavelength through the general per-ray accumulation
+                                        kernel (normally only wavelengths with > 3 overlapping lines);
+                                        a cross-check of the moment pipeline, not a fast path */
+    LWB200_FETCH_EARLY    = 1u << 4  /* start copying J and I back to the host buffers as soon as the rays
+                                        are done, overlapped with the Gamma accumulation; a following
+                                        lwb200_download(JBAR | INTENS) then only waits for that copy */
 };
 
 /* Device buffers a caller may need to hand to a collective. */

@@ -24,7 +24,7 @@ ALL_INPUTS = 0x7f
 ITER_INPUTS = POPS | NSTAR | GAMMA
 ITER_OUTPUTS = GAMMA | JBAR | INTENS | RATES
 
-LAMBDA_ITERATE, STORE_DEPTH, DEFER_FINALISE, GENERAL_KERNEL = 1, 2, 4, 8
+LAMBDA_ITERATE, STORE_DEPTH, DEFER_FINALISE, GENERAL_KERNEL, FETCH_EARLY = 1, 2, 4, 8, 16
 
 BUF_ACCUM, BUF_J, BUF_I, BUF_POPS, BUF_GAMMA, BUF_DJ = range(6)
 

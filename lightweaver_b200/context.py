@@ -112,11 +112,12 @@ class Context:
 
     # ------------------------------------------------- device-resident calls
     def fs_iter_device(self, lambdaIterate=False, storeDepth=False, deferFinalise=False,
-                       want_dJ=True, generalKernel=False):
+                       want_dJ=True, generalKernel=False, fetchEarly=False):
         """One Gamma iteration on device-resident data (no host copies)."""
         flags = ((capi.LAMBDA_ITERATE if lambdaIterate else 0) | (capi.STORE_DEPTH if storeDepth else 0)
                  | (capi.DEFER_FINALISE if deferFinalise else 0)
-                 | (capi.GENERAL_KERNEL if generalKernel else 0))
+                 | (capi.GENERAL_KERNEL if generalKernel else 0)
+                 | (capi.FETCH_EARLY if fetchEarly else 0))
         if want_dJ:
             dJ, idx = C.c_double(), C.c_int64()
             capi.check(self.lib.lwb200_fs_iter(self._h, flags, C.byref(dJ), C.byref(idx)))
@@ -159,7 +160,7 @@ class Context:
         self.problem.prefill_gamma(self.crsw)
         self.upload(capi.ITER_INPUTS)
         dJ, idx = self.fs_iter_device(lambdaIterate=lambdaIterate, storeDepth=storeDepth,
-                                      generalKernel=general)
+                                      generalKernel=general, fetchEarly=True)
         self.download(capi.ITER_OUTPUTS | (capi.DEPTH if storeDepth else 0))
         return IterationUpdate(updatedJ=True, dJMax=dJ, dJMaxIdx=idx % self.problem.Nspect,
                                crsw=self.crsw)

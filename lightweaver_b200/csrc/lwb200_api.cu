@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 #include <string>
@@ -113,6 +114,9 @@ struct LwB200Context
     std::vector<Pending> pending;
     std::vector<void*> registered;
     cudaEvent_t evK0 = nullptr, evK1 = nullptr;
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evRays = nullptr, evCopy = nullptr;
+    bool fetchEarly = false, fetched = false;
     cudaStream_t sideStream[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t evFork = nullptr, evJoin[4] = {nullptr, nullptr, nullptr, nullptr};
     bool kernelTimed = false;
@@ -299,10 +303,16 @@ int build_plan(LwB200Context* c)
     if (scratchBytes + 4 * KP * sizeof(double) > smemLimit)
         return fail("atom too large for the shared-memory scratch");
     // keep the accumulator <= ~48 KB so that several CTAs share an SM
-    const size_t accBudget = std::min<size_t>(smemLimit - scratchBytes, 30 * 1024);
-    const int slotCap = (int)std::max<size_t>(accBudget / (4 * KP * sizeof(double)), 1);
+    // per slot: 4 accumulator rows (+ 3 rows of staged per-depth data in gamma_kernel); keep a
+    // CTA under ~48 KB so that several share an SM and the L1 keeps some room
+    const size_t accBudget = std::min<size_t>(smemLimit - scratchBytes, 40 * 1024);
+    const int slotCap = (int)std::max<size_t>(accBudget / (7 * KP * sizeof(double)), 1);
+    if ((long long)std::max(ncont, 1) * p.Ncol * K > 0x7fffffffLL)
+        return fail("gRatio block exceeds 2^31 elements");
     const long long targetCtas = 148LL * 16;
-    const int tileLen = (int)std::max<long long>(4, std::min<long long>(32, ((long long)L * p.Ncol) / targetCtas));
+    int tileLen = (int)std::max<long long>(4, std::min<long long>(32, ((long long)L * p.Ncol) / targetCtas));
+    if (const char* ev = getenv("LWB200_EXP_TILELEN"))
+        tileLen = std::max(1, atoi(ev));
 
     std::vector<DevEntry> entries;
     std::vector<int> laCnt(L, 0);
@@ -310,6 +320,7 @@ int build_plan(LwB200Context* c)
     for (int la = 0; la < L; ++la)
         c->laKind[la] = kind_of(la);
     int maxSlots = 1;
+    size_t maxTileEntries = 1;
     c->tileLa.push_back(0);
     c->tileSlotOff.push_back(0);
     {
@@ -318,6 +329,7 @@ int build_plan(LwB200Context* c)
         {
             std::vector<int> slots; // transitions of this tile
             const int start = pos;
+            const size_t tileEntry0 = entries.size();
             const bool general = c->laKind[start] == 4;
             while (pos < L && pos - start < tileLen && (c->laKind[pos] == 4) == general)
             {
@@ -327,7 +339,7 @@ int build_plan(LwB200Context* c)
                         add.push_back(g);
                 if ((int)(slots.size() + add.size()) > slotCap && pos > start)
                     break;
-                if ((int)(slots.size() + add.size()) * 4 * KP * sizeof(double) + scratchBytes > smemLimit)
+                if ((int)(slots.size() + add.size()) * 7 * KP * sizeof(double) + scratchBytes > smemLimit)
                     return fail("too many transitions active at one wavelength for shared memory");
                 slots.insert(slots.end(), add.begin(), add.end());
                 ++pos;
@@ -354,6 +366,9 @@ int build_plan(LwB200Context* c)
                     en.Nlevel = c->atoms[d.atom].Nlevel;
                     en.detailed = d.detailed;
                     en.atom = d.atom;
+                    en.nOffI = d.levI * K;
+                    en.nOffJ = d.levJ * K;
+                    en.gOff = d.type == 0 ? 0 : (int)((long long)d.contIdx * p.Ncol * K);
                     constexpr double pi4_h = 4.0 * kPi / kHPlanck;
                     constexpr double pi4_hc = 1.0 / (0.25 * kHC / kPi);
                     if (d.type == 0)
@@ -381,6 +396,7 @@ int build_plan(LwB200Context* c)
                 }
                 c->tileLambda.push_back(l2);
             }
+            maxTileEntries = std::max(maxTileEntries, entries.size() - tileEntry0);
             c->tileLa.push_back((int)c->tileLambda.size());
             c->tileKind.push_back(general ? 4 : 0);
             for (int g : slots)
@@ -392,7 +408,9 @@ int build_plan(LwB200Context* c)
     laOff[L] = (int)entries.size();
     c->Ntile = (int)c->tileLa.size() - 1;
     c->smemBytes = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchFs;
-    c->smemGamma = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchGamma;
+    c->smemGamma = (size_t)maxSlots * 7 * K * sizeof(double) + scratchGamma;
+    if (c->smemGamma > smemLimit)
+        return fail("wavelength tile too large for shared memory");
     c->NCH = (K + 31) / 32;
 
     // per-wavelength line slots and moment rows of the pipeline
@@ -421,6 +439,10 @@ int build_plan(LwB200Context* c)
             ll.levI = d.levI;
             ll.levJ = d.levJ;
             ll.lineIdx = d.lineIdx;
+            ll.slot = -1;
+            for (int e = laOff[la]; e < laOff[la] + laCnt[la]; ++e)
+                if (entries[e].trans == g)
+                    ll.slot = entries[e].slot;
             ll.atom = d.atom;
             ll.i = d.i;
             ll.j = d.j;
@@ -638,6 +660,9 @@ int ensure_side_streams(LwB200Context* c)
         CU(cudaStreamCreateWithPriority(&c->sideStream[q], cudaStreamNonBlocking, pr));
         CU(cudaEventCreateWithFlags(&c->evJoin[q], cudaEventDisableTiming));
     }
+    CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->evRays, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->evCopy, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
     return 0;
 }
@@ -719,6 +744,18 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
             {
                 CU(cudaEventRecord(c->evJoin[q], c->sideStream[q]));
                 CU(cudaStreamWaitEvent(c->stream, c->evJoin[q], 0));
+            }
+            if (c->fetchEarly && c->nListDirect == 0 && colBase + nb >= Ncol)
+            {
+                // J and I are final: send them home on the copy stream while Gamma is accumulated
+                const LwB200Problem& p = c->prob;
+                const size_t nJ = (size_t)p.Ncol * p.Nspect * p.Nspace, nI = (size_t)p.Ncol * p.Nspect * p.Nrays;
+                CU(cudaEventRecord(c->evRays, c->stream));
+                CU(cudaStreamWaitEvent(c->copyStream, c->evRays, 0));
+                CU(cudaMemcpyAsync(p.J, c->J.p, nJ * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
+                CU(cudaMemcpyAsync(p.I, c->I.p, nI * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
+                CU(cudaEventRecord(c->evCopy, c->copyStream));
+                c->fetched = true;
             }
             if (c->nListMoment > 0)
             {
@@ -906,6 +943,9 @@ int lwb200_destroy(LwB200Context* c)
     if (c->evFork)
     {
         cudaEventDestroy(c->evFork);
+        cudaEventDestroy(c->evRays);
+        cudaEventDestroy(c->evCopy);
+        cudaStreamDestroy(c->copyStream);
         for (int q = 0; q < 4; ++q)
         {
             cudaEventDestroy(c->evJoin[q]);
@@ -1133,6 +1173,13 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
     const size_t D = sizeof(double);
     cudaStream_t s = c->stream;
     const auto D2H = cudaMemcpyDeviceToHost;
+    if (c->fetched && (mask & (LWB200_JBAR | LWB200_INTENS)))
+    {
+        // already on their way (LWB200_FETCH_EARLY): order the stream after that copy
+        CU(cudaStreamWaitEvent(s, c->evCopy, 0));
+        c->fetched = false;
+        mask &= ~(uint32_t)(LWB200_JBAR | LWB200_INTENS);
+    }
     if (mask & LWB200_JBAR)
         CU(cudaMemcpyAsync(p.J, c->J.p, ncol * L * K * D, D2H, s));
     if (mask & LWB200_INTENS)
@@ -1264,6 +1311,13 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
         return fail("lwb200_fs_iter: inputs have not been uploaded (lwb200_upload)");
     const int storeDepth = (flags & LWB200_STORE_DEPTH) ? 1 : 0;
     c->forceDirect = (flags & LWB200_GENERAL_KERNEL) != 0;
+    c->fetchEarly = (flags & LWB200_FETCH_EARLY) != 0 && !c->forceDirect;
+    if (c->fetched)
+    {
+        // an early copy nobody collected: it must not race with this iteration's writes of J
+        CU(cudaStreamWaitEvent(c->stream, c->evCopy, 0));
+        c->fetched = false;
+    }
     if (storeDepth && !c->depthChi.p)
         return fail("lwb200_fs_iter: STORE_DEPTH without depth arrays in the problem");
     c->lastLaunches = 0;

@@ -58,6 +58,9 @@ struct DevEntry
     int atom;
     double al;         // continuum: alpha(lambda); line: 0
     double wlaF;       // continuum: wlambda / lambda * 4 pi / h;  line: wlambda * 4 pi / (h c)
+    int nOffI, nOffJ;  // levI * K, levJ * K: element offsets into one column of n
+    int gOff;          // contIdx * Ncol * K: element offset of the continuum's gRatio block
+    int pad;
 };
 
 // Per (wavelength, overlapping-line slot) descriptor built by the planner (<= 3 slots).
@@ -70,7 +73,8 @@ struct LambdaLine
     int trans;              // global transition index
     int levI, levJ;         // rows in the packed population arrays
     int lineIdx;
-    int atom, i, j, pad;
+    int atom, i, j;
+    int slot;               // accumulator slot of the line within the wavelength's tile
     double lambda0, Bij, Bji_Bij, Aji_Bji;
     double wlaS;            // wlambda * 4 pi / (h c)  (times wphi(k) gives wla)
 };

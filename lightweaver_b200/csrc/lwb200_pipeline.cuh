@@ -95,10 +95,10 @@ __global__ void continuum_kernel(const DevProblem P, const int* __restrict__ til
             if (t.type == 0)
                 continue;
             const double al = t.al;
-            const double gk = __ldg(gcol + (size_t)t.contIdx * P.Ncol * K) * expfac;
+            const double gk = __ldg(gcol + t.gOff) * expfac;
             const double Vji = gk * al;
-            const double ni = __ldg(ncol + (size_t)t.levI * K);
-            const double nj = __ldg(ncol + (size_t)t.levJ * K);
+            const double ni = __ldg(ncol + t.nOffI);
+            const double nj = __ldg(ncol + t.nOffJ);
             chiC += ni * al - nj * Vji;
             etaC += nj * (hcl * Vji);
         }
@@ -460,10 +460,14 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
 //
 // Profile members of an atom at one wavelength: q = 0 the continua (p = 1), q = l + 1 the
 // line in slot l.  M(q, q') = sum_r w Psi* p_q p_q'.
+#ifndef LWB200_GAMMA_MINBLOCKS
+#define LWB200_GAMMA_MINBLOCKS 4
+#endif
+
 template <int NL>
 __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int col, int cb, int k, double Tk,
-                                             double W0, double* __restrict__ acc, double* __restrict__ Xs,
-                                             double* __restrict__ Us, int KP)
+                                             double W0, double* __restrict__ acc, const double* __restrict__ sd,
+                                             double* __restrict__ Xs, double* __restrict__ Us)
 {
     constexpr int NLA = NL > 0 ? NL : 1;
     constexpr int NQ = NL + 1;
@@ -476,8 +480,8 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
     constexpr double hc_4pi = 0.25 * kHC / kPi;
     const double hc_kl = hc_k * rlambda;
     const double hcl = twoHc * (rlambda * rlambda * rlambda);
-    const double* ncol = P.n + (size_t)col * P.NlevTot * K + k;
-    const double* gcol = P.gRatio + (size_t)col * K + k;
+    // sd: this thread's column of the tile's staged per-depth data, [slot][3][K]:
+    //     n(levI), n(levJ), and gRatio (continuum) or wphi (line)
 
     // moments of this wavelength at depth k (independent loads, issued together)
     const double* mom = P.mom + ((size_t)cb * P.momRows + P.momOff[la]) * K + k;
@@ -519,8 +523,8 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
             const double gS = ll.Bji_Bij;
             const double r = (ll.rhoOff >= 0) ? __ldg(P.rhoPrd + ll.rhoOff + (size_t)col * ll.rhoColStride + k) : 1.0;
             const double gk = (ll.rhoOff >= 0) ? gS * r : gS;
-            const double ni = __ldg(ncol + (size_t)ll.levI * K);
-            const double nj = __ldg(ncol + (size_t)ll.levJ * K);
+            const double ni = sd[(ll.slot * 3 + 0) * K];
+            const double nj = sd[(ll.slot * 3 + 1) * K];
             lsTrans[l] = ll.trans;
             lsAtom[l] = ll.atom;
             lsI[l] = ll.i;
@@ -530,7 +534,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
             lsUgv[l] = (ll.Aji_Bji * (gS * vB)) * r;
             lsX[l] = vB * (ni - nj * gk);
             lsE[l] = nj * (ll.Aji_Bji * (gk * vB));
-            lsWla[l] = ll.wlaS * __ldg(P.wphi + ((size_t)ll.lineIdx * P.Ncol + col) * K + k);
+            lsWla[l] = ll.wlaS * sd[(ll.slot * 3 + 2) * K];
         }
     }
 
@@ -558,11 +562,12 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
                 if (t.type == 0)
                     continue;
                 const double al = t.al;
-                const double gk = __ldg(gcol + (size_t)t.contIdx * P.Ncol * K) * expfac;
+                const double* sds = sd + t.slot * 3 * K;
+                const double gk = sds[2 * K] * expfac;
                 const double Vji = gk * al;
                 const double Uji = hcl * Vji;
-                const double ni = __ldg(ncol + (size_t)t.levI * K);
-                const double nj = __ldg(ncol + (size_t)t.levJ * K);
+                const double ni = sds[0];
+                const double nj = sds[K];
                 const double x = ni * al - nj * Vji;
                 Xs[t.i * nthr + tid] += x;
                 Xs[t.j * nthr + tid] -= x;
@@ -603,7 +608,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
             double v = 0.0, gv = 0.0, ugv = 0.0, Wq = W0, Aq = mJ, EBq = EB[0], wla = 0.0;
             if (t.type != 0)
             {
-                const double gk = __ldg(gcol + (size_t)t.contIdx * P.Ncol * K) * expfac;
+                const double gk = sd[(t.slot * 3 + 2) * K] * expfac;
                 v = t.al;
                 gv = gk * t.al;
                 ugv = hcl * gv;
@@ -623,7 +628,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
                     wla = lsWla[l];
                 }
             }
-            double* a4 = acc + (size_t)t.slot * 4 * KP + k;
+            double* a4 = acc + t.slot * 4 * K;
             if (!detailed)
             {
                 // chi_atom(m) = sum_q p_q X_q(m), U_atom(m) = sum_q p_q U_q(m)
@@ -657,33 +662,49 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
                 }
                 // sum_r w [(Uji + Vji Ieff) - Psi* chi(i) U(j)],  Ieff = I - Psi* eta_atom
                 a4[0] += (ugv * Wq + gv * (Aq - EBq) - XUij) * wla;
-                a4[KP] += (v * (Aq - EBq) - XUji) * wla;
+                a4[K] += (v * (Aq - EBq) - XUji) * wla;
             }
-            a4[2 * KP] += (v * Aq) * wla;
-            a4[3 * KP] += (ugv * Wq + gv * Aq) * wla;
+            a4[2 * K] += (v * Aq) * wla;
+            a4[3 * K] += (ugv * Wq + gv * Aq) * wla;
         }
         e0 = e1;
     }
 }
 
-__global__ void __launch_bounds__(128, 5) gamma_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi,
+__global__ void __launch_bounds__(128, LWB200_GAMMA_MINBLOCKS) gamma_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi,
                              int colBase)
 {
     extern __shared__ double smem[];
-    const int K = P.K, KP = P.KP;
+    const int K = P.K;
     const int tile = tileList[blockIdx.x];
     const int cb = blockIdx.y, col = colBase + cb;
     const int k = threadIdx.x;
     const int slot0 = P.tileSlotOff[tile];
     const int nslot = P.tileSlotOff[tile + 1] - slot0;
-    double* acc = smem;                                   // [nslot][4][KP]
-    double* Xs = smem + (size_t)P.maxSlots * 4 * KP;      // [maxNlevel][blockDim]
+    double* acc = smem;                                   // [nslot][4][K]   partial sums, one writer each
+    double* slotD = smem + (size_t)P.maxSlots * 4 * K;    // [nslot][3][K]   staged per-depth data
+    double* Xs = slotD + (size_t)P.maxSlots * 3 * K;      // [maxNlevel][blockDim]
     double* Us = Xs + (size_t)P.maxNlevel * blockDim.x;
-    for (int idx = threadIdx.x; idx < nslot * 4 * KP; idx += blockDim.x)
-        acc[idx] = 0.0;
-    __syncthreads();
     if (k < K)
     {
+        // Everything the wavelength loop needs per depth that does not depend on the wavelength is
+        // read ONCE per CTA (independent loads, one memory latency): the populations of each
+        // slot's two levels and its gRatio / wphi.  Inside the loop only J and the moments come
+        // from global memory.
+        for (int s = 0; s < nslot; ++s)
+        {
+            const DevTrans& t = P.trans[P.tileSlotTrans[slot0 + s]];
+            acc[(s * 4 + 0) * K + k] = 0.0;
+            acc[(s * 4 + 1) * K + k] = 0.0;
+            acc[(s * 4 + 2) * K + k] = 0.0;
+            acc[(s * 4 + 3) * K + k] = 0.0;
+            const double* ncol = P.n + (size_t)col * P.NlevTot * K + k;
+            slotD[(s * 3 + 0) * K + k] = __ldg(ncol + (size_t)t.levI * K);
+            slotD[(s * 3 + 1) * K + k] = __ldg(ncol + (size_t)t.levJ * K);
+            slotD[(s * 3 + 2) * K + k] = (t.type == 0)
+                ? __ldg(P.wphi + ((size_t)t.lineIdx * P.Ncol + col) * K + k)
+                : __ldg(P.gRatio + ((size_t)t.contIdx * P.Ncol + col) * K + k);
+        }
         const double Tk = __ldg(P.temperature + (size_t)col * K + k);
         // W0 = sum_r w over both directions of every mu, in the ray order of ray_kernel
         double W0 = 0.0;
@@ -701,29 +722,26 @@ __global__ void __launch_bounds__(128, 5) gamma_kernel(const DevProblem P, const
                 continue;
             switch (P.laNLines[la])
             {
-            case 0: gamma_lambda<0>(P, la, col, cb, k, Tk, W0, acc, Xs, Us, KP); break;
-            case 1: gamma_lambda<1>(P, la, col, cb, k, Tk, W0, acc, Xs, Us, KP); break;
-            case 2: gamma_lambda<2>(P, la, col, cb, k, Tk, W0, acc, Xs, Us, KP); break;
-            case 3: gamma_lambda<3>(P, la, col, cb, k, Tk, W0, acc, Xs, Us, KP); break;
+            case 0: gamma_lambda<0>(P, la, col, cb, k, Tk, W0, acc + k, slotD + k, Xs, Us); break;
+            case 1: gamma_lambda<1>(P, la, col, cb, k, Tk, W0, acc + k, slotD + k, Xs, Us); break;
+            case 2: gamma_lambda<2>(P, la, col, cb, k, Tk, W0, acc + k, slotD + k, Xs, Us); break;
+            case 3: gamma_lambda<3>(P, la, col, cb, k, Tk, W0, acc + k, slotD + k, Xs, Us); break;
             default: break; // > 3 overlapping lines: handled by the general kernel
             }
         }
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < nslot * 4 * KP; idx += blockDim.x)
-    {
-        const int kk = idx % KP;
-        const int q = (idx / KP) & 3;
-        const int s = idx / (4 * KP);
-        if (kk >= K)
-            continue;
-        const DevTrans& t = P.trans[P.tileSlotTrans[slot0 + s]];
-        const int row = q == 0 ? t.accIJ : q == 1 ? t.accJI : q == 2 ? t.accRij : t.accRji;
-        if (row < 0)
-            continue;
-        const double v = acc[idx];
-        if (v != 0.0)
-            atomicAdd(P.accum + ((size_t)col * P.AccTot + row) * K + kk, v);
+        // flush: this thread's own column of partial sums (one fp64 RED per element per tile)
+        for (int s = 0; s < nslot; ++s)
+        {
+            const DevTrans& t = P.trans[P.tileSlotTrans[slot0 + s]];
+            const int rows[4] = {t.accIJ, t.accJI, t.accRij, t.accRji};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+            {
+                const double v = acc[(s * 4 + q) * K + k];
+                if (rows[q] >= 0 && v != 0.0)
+                    atomicAdd(P.accum + ((size_t)col * P.AccTot + rows[q]) * K + k, v);
+            }
+        }
     }
 }
 

@@ -312,7 +312,7 @@ IterationResult b200_fs_iter(Context& ctx, bool lambdaIterate, ExtraParams param
 {
     Mirror& m = mirror_for(ctx);
     sync_inputs(ctx, m, true);
-    uint32_t flags = lambdaIterate ? LWB200_LAMBDA_ITERATE : 0;
+    uint32_t flags = (lambdaIterate ? LWB200_LAMBDA_ITERATE : 0) | LWB200_FETCH_EARLY;
     const bool storeDepth = ctx.depthData && ctx.depthData->fill;
     if (storeDepth)
         flags |= LWB200_STORE_DEPTH;
