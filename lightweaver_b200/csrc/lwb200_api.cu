@@ -139,6 +139,7 @@ struct LwB200Context
     int nKindLam[4] = {0, 0, 0, 0}, nListMoment = 0, nListDirect = 0, nListAll = 0, listLo = -1, listHi = -1;
     int batchCols = 1, momRows = 0;
     size_t smemGamma = 0;
+    int KC = 0;
     int Ntile = 0;
     int nwarps = 4;
     int laLo = 0, laHi = 0;
@@ -297,16 +298,17 @@ int build_plan(LwB200Context* c)
     for (int a = 0; a < p.Natom; ++a)
         maxNlevel = std::max(maxNlevel, c->atoms[a].Nlevel);
     const size_t scratchFs = (size_t)c->nwarps * 2 * maxNlevel * 32 * sizeof(double);
-    const size_t scratchGamma = (size_t)2 * maxNlevel * KP * sizeof(double);
+    const int KC = std::min(KP, 128); // depths per gamma_kernel CTA
+    const size_t scratchGamma = (size_t)2 * maxNlevel * KC * sizeof(double);
     const size_t scratchBytes = std::max(scratchFs, scratchGamma);
     const size_t smemLimit = 200 * 1024;
-    if (scratchBytes + 4 * KP * sizeof(double) > smemLimit)
+    if (scratchBytes + 7 * KC * sizeof(double) > smemLimit)
         return fail("atom too large for the shared-memory scratch");
     // keep the accumulator <= ~48 KB so that several CTAs share an SM
     // per slot: 4 accumulator rows (+ 3 rows of staged per-depth data in gamma_kernel); keep a
     // CTA under ~48 KB so that several share an SM and the L1 keeps some room
     const size_t accBudget = std::min<size_t>(smemLimit - scratchBytes, 40 * 1024);
-    const int slotCap = (int)std::max<size_t>(accBudget / (7 * KP * sizeof(double)), 1);
+    const int slotCap = (int)std::max<size_t>(accBudget / (7 * KC * sizeof(double)), 1);
     if ((long long)std::max(ncont, 1) * p.Ncol * K > 0x7fffffffLL)
         return fail("gRatio block exceeds 2^31 elements");
     const long long targetCtas = 148LL * 16;
@@ -339,7 +341,7 @@ int build_plan(LwB200Context* c)
                         add.push_back(g);
                 if ((int)(slots.size() + add.size()) > slotCap && pos > start)
                     break;
-                if ((int)(slots.size() + add.size()) * 7 * KP * sizeof(double) + scratchBytes > smemLimit)
+                if ((int)(slots.size() + add.size()) * 7 * KC * sizeof(double) + scratchBytes > smemLimit)
                     return fail("too many transitions active at one wavelength for shared memory");
                 slots.insert(slots.end(), add.begin(), add.end());
                 ++pos;
@@ -408,10 +410,21 @@ int build_plan(LwB200Context* c)
     laOff[L] = (int)entries.size();
     c->Ntile = (int)c->tileLa.size() - 1;
     c->smemBytes = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchFs;
-    c->smemGamma = (size_t)maxSlots * 7 * K * sizeof(double) + scratchGamma;
+    c->smemGamma = (size_t)maxSlots * 7 * KC * sizeof(double) + scratchGamma;
+    c->KC = KC;
     if (c->smemGamma > smemLimit)
         return fail("wavelength tile too large for shared memory");
     c->NCH = (K + 31) / 32;
+    if (K > 128)
+    {
+        // beyond one warp per column: ray_kernel in multi-warp mode (4 depths per lane, up to 8 warps)
+        if (K > 1024)
+            return fail("Nspace > 1024 is not supported");
+        for (int la = 0; la < L; ++la)
+            if (c->laKind[la] == 4)
+                return fail("more than three overlapping lines at one wavelength with Nspace > 128 is not supported");
+        c->NCH = 4;
+    }
 
     // per-wavelength line slots and moment rows of the pipeline
     std::vector<LambdaLine> lamLine((size_t)L * 3);
@@ -667,6 +680,103 @@ int ensure_side_streams(LwB200Context* c)
     return 0;
 }
 
+// Three-stage pipeline per batch of columns (lwb200_pipeline.cuh):
+//   continuum_kernel -> ray_kernel<NL> for NL = 3, 2, 1, 0 -> gamma_kernel
+// The ray kernels of the four kinds run CONCURRENTLY, most expensive per wavelength first, on
+// prioritised side streams forked from / joined to the caller's stream, so that they share one
+// tail (a 1D atmosphere is only a few waves of warps in total).  fsMode != 0: formal solution
+// only (no J, no moments, no Gamma stage).
+template <int NCH, int SOLVER, bool MULTI>
+int launch_pipeline(LwB200Context* c, int lambdaIterate, int storeDepth, int fsMode)
+{
+    if (ensure_side_streams(c))
+        return 1;
+    if (set_smem_attr(gamma_kernel, c->device))
+        return 1;
+    const int Ncol = c->prob.Ncol, KP = c->P.KP, K = c->P.K;
+    const int threads = MULTI ? 32 * ((K + 32 * NCH - 1) / (32 * NCH)) : c->nwarps * 32;
+    for (int colBase = 0; colBase < Ncol; colBase += c->batchCols)
+    {
+        const int nb = std::min(c->batchCols, Ncol - colBase);
+        if (c->nListMoment > 0)
+        {
+            continuum_kernel<<<dim3(c->nListMoment, nb), KP, 0, c->stream>>>(c->P, c->dListMoment.p, c->laLo,
+                                                                            c->laHi, colBase);
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
+        }
+        int nkinds = 0;
+        for (int q = 0; q < 4; ++q)
+            nkinds += c->nKindLam[q] > 0 ? 1 : 0;
+        int nside = 0, launched = 0;
+        for (int q = 3; q >= 0; --q)
+        {
+            const int nLam = c->nKindLam[q];
+            if (nLam == 0)
+                continue;
+            // the last kind runs on the caller's stream itself
+            cudaStream_t s = c->stream;
+            if (++launched != nkinds)
+            {
+                if (nside == 0)
+                    CU(cudaEventRecord(c->evFork, c->stream));
+                s = c->sideStream[nside++];
+                CU(cudaStreamWaitEvent(s, c->evFork, 0));
+            }
+            const long long warps = (long long)nLam * nb;
+            const int perWarp = MULTI ? 1 : (int)std::max<long long>(1, std::min<long long>(4, warps / (148LL * 8 * 8)));
+            const int nw = c->nwarps;
+            dim3 grid(MULTI ? nLam : (nLam + nw * perWarp - 1) / (nw * perWarp), nb);
+            const int* list = c->dKindLam[q].p;
+            switch (q)
+            {
+            case 0:
+                ray_kernel<NCH, SOLVER, 0, MULTI><<<grid, threads, 0, s>>>(c->P, list, nLam, perWarp, colBase, lambdaIterate, storeDepth, fsMode);
+                break;
+            case 1:
+                ray_kernel<NCH, SOLVER, 1, MULTI><<<grid, threads, 0, s>>>(c->P, list, nLam, perWarp, colBase, lambdaIterate, storeDepth, fsMode);
+                break;
+            case 2:
+                ray_kernel<NCH, SOLVER, 2, MULTI><<<grid, threads, 0, s>>>(c->P, list, nLam, perWarp, colBase, lambdaIterate, storeDepth, fsMode);
+                break;
+            default:
+                ray_kernel<NCH, SOLVER, 3, MULTI><<<grid, threads, 0, s>>>(c->P, list, nLam, perWarp, colBase, lambdaIterate, storeDepth, fsMode);
+                break;
+            }
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
+        }
+        for (int q = 0; q < nside; ++q)
+        {
+            CU(cudaEventRecord(c->evJoin[q], c->sideStream[q]));
+            CU(cudaStreamWaitEvent(c->stream, c->evJoin[q], 0));
+        }
+        if (fsMode != 0)
+            continue;
+        if (c->fetchEarly && c->nListDirect == 0 && colBase + nb >= Ncol)
+        {
+            // J and I are final: send them home on the copy stream while Gamma is accumulated
+            const LwB200Problem& p = c->prob;
+            const size_t nJ = (size_t)p.Ncol * p.Nspect * p.Nspace, nI = (size_t)p.Ncol * p.Nspect * p.Nrays;
+            CU(cudaEventRecord(c->evRays, c->stream));
+            CU(cudaStreamWaitEvent(c->copyStream, c->evRays, 0));
+            CU(cudaMemcpyAsync(p.J, c->J.p, nJ * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
+            CU(cudaMemcpyAsync(p.I, c->I.p, nI * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
+            CU(cudaEventRecord(c->evCopy, c->copyStream));
+            c->fetched = true;
+        }
+        if (c->nListMoment > 0)
+        {
+            const int KC = c->KC;
+            gamma_kernel<<<dim3(c->nListMoment, nb, (K + KC - 1) / KC), KC, c->smemGamma, c->stream>>>(
+                c->P, c->dListMoment.p, c->laLo, c->laHi, colBase);
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
+        }
+    }
+    return 0;
+}
+
 template <int NCH, int SOLVER, int MODE>
 int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
 {
@@ -679,92 +789,9 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
     const int threads = c->nwarps * 32;
     if (MODE == MODE_ITER && !c->forceDirect)
     {
-        // Three-stage pipeline per batch of columns (lwb200_pipeline.cuh):
-        //   continuum_kernel -> ray_kernel<NL> for NL = 3, 2, 1, 0 -> gamma_kernel
-        // The ray kernels of the four kinds run CONCURRENTLY, most expensive per wavelength
-        // first, on prioritised side streams forked from / joined to the caller's stream, so
-        // that they share one tail (a 1D atmosphere is only a few waves of warps in total).
-        // Wavelengths with more than three overlapping lines go through the general kernel.
-        if (ensure_side_streams(c))
+        // wavelengths with more than three overlapping lines go through the general kernel
+        if (launch_pipeline<NCH, SOLVER, false>(c, lambdaIterate, storeDepth, 0))
             return 1;
-        if (set_smem_attr(gamma_kernel, c->device))
-            return 1;
-        const int Ncol = c->prob.Ncol, KP = c->P.KP;
-        for (int colBase = 0; colBase < Ncol; colBase += c->batchCols)
-        {
-            const int nb = std::min(c->batchCols, Ncol - colBase);
-            if (c->nListMoment > 0)
-            {
-                continuum_kernel<<<dim3(c->nListMoment, nb), KP, 0, c->stream>>>(c->P, c->dListMoment.p, c->laLo,
-                                                                                c->laHi, colBase);
-                CU(cudaGetLastError());
-                c->lastLaunches += 1;
-            }
-            int nkinds = 0;
-            for (int q = 0; q < 4; ++q)
-                nkinds += c->nKindLam[q] > 0 ? 1 : 0;
-            int nside = 0, launched = 0;
-            for (int q = 3; q >= 0; --q)
-            {
-                const int nLam = c->nKindLam[q];
-                if (nLam == 0)
-                    continue;
-                // the last kind runs on the caller's stream itself
-                cudaStream_t s = c->stream;
-                if (++launched != nkinds)
-                {
-                    if (nside == 0)
-                        CU(cudaEventRecord(c->evFork, c->stream));
-                    s = c->sideStream[nside++];
-                    CU(cudaStreamWaitEvent(s, c->evFork, 0));
-                }
-                const long long warps = (long long)nLam * nb;
-                const int perWarp = (int)std::max<long long>(1, std::min<long long>(4, warps / (148LL * 8 * 8)));
-                const int nw = c->nwarps;
-                dim3 grid((nLam + nw * perWarp - 1) / (nw * perWarp), nb);
-                switch (q)
-                {
-                case 0:
-                    ray_kernel<NCH, SOLVER, 0><<<grid, threads, 0, s>>>(c->P, c->dKindLam[q].p, nLam, perWarp, colBase, lambdaIterate, storeDepth);
-                    break;
-                case 1:
-                    ray_kernel<NCH, SOLVER, 1><<<grid, threads, 0, s>>>(c->P, c->dKindLam[q].p, nLam, perWarp, colBase, lambdaIterate, storeDepth);
-                    break;
-                case 2:
-                    ray_kernel<NCH, SOLVER, 2><<<grid, threads, 0, s>>>(c->P, c->dKindLam[q].p, nLam, perWarp, colBase, lambdaIterate, storeDepth);
-                    break;
-                default:
-                    ray_kernel<NCH, SOLVER, 3><<<grid, threads, 0, s>>>(c->P, c->dKindLam[q].p, nLam, perWarp, colBase, lambdaIterate, storeDepth);
-                    break;
-                }
-                CU(cudaGetLastError());
-                c->lastLaunches += 1;
-            }
-            for (int q = 0; q < nside; ++q)
-            {
-                CU(cudaEventRecord(c->evJoin[q], c->sideStream[q]));
-                CU(cudaStreamWaitEvent(c->stream, c->evJoin[q], 0));
-            }
-            if (c->fetchEarly && c->nListDirect == 0 && colBase + nb >= Ncol)
-            {
-                // J and I are final: send them home on the copy stream while Gamma is accumulated
-                const LwB200Problem& p = c->prob;
-                const size_t nJ = (size_t)p.Ncol * p.Nspect * p.Nspace, nI = (size_t)p.Ncol * p.Nspect * p.Nrays;
-                CU(cudaEventRecord(c->evRays, c->stream));
-                CU(cudaStreamWaitEvent(c->copyStream, c->evRays, 0));
-                CU(cudaMemcpyAsync(p.J, c->J.p, nJ * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
-                CU(cudaMemcpyAsync(p.I, c->I.p, nI * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
-                CU(cudaEventRecord(c->evCopy, c->copyStream));
-                c->fetched = true;
-            }
-            if (c->nListMoment > 0)
-            {
-                gamma_kernel<<<dim3(c->nListMoment, nb), KP, c->smemGamma, c->stream>>>(c->P, c->dListMoment.p,
-                                                                                        c->laLo, c->laHi, colBase);
-                CU(cudaGetLastError());
-                c->lastLaunches += 1;
-            }
-        }
         if (c->nListDirect > 0)
         {
             auto kern = fs_kernel<NCH, SOLVER, MODE_ITER>;
@@ -793,6 +820,26 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
     return 0;
 }
 
+// Nspace > 128: the multi-warp ray kernel for everything (Gamma iteration and formal solution)
+template <int SOLVER, int MODE>
+int launch_fs_long(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
+{
+    if (!c->evK0)
+    {
+        CU(cudaEventCreate(&c->evK0));
+        CU(cudaEventCreate(&c->evK1));
+    }
+    if (c->forceDirect)
+        return fail("the general per-ray kernel is limited to Nspace <= 128");
+    CU(cudaEventRecord(c->evK0, c->stream));
+    const int fsMode = MODE == MODE_ITER ? 0 : (upOnly ? 3 : 1);
+    if (launch_pipeline<4, SOLVER, true>(c, lambdaIterate, storeDepth, fsMode))
+        return 1;
+    CU(cudaEventRecord(c->evK1, c->stream));
+    c->kernelTimed = true;
+    return 0;
+}
+
 template <int NCH, int MODE>
 int launch_fs_s(LwB200Context* c, int li, int uo, int sd)
 {
@@ -812,6 +859,18 @@ int launch_fs(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
 {
     if (refresh_tile_lists(c))
         return 1;
+    if (c->prob.Nspace > 128)
+    {
+        switch (c->prob.formalSolver)
+        {
+#ifndef LWB200_DEV_FAST_BUILD
+        case LWB200_FS_LINEAR: return launch_fs_long<0, MODE>(c, lambdaIterate, upOnly, storeDepth);
+        case LWB200_FS_BESSER: return launch_fs_long<1, MODE>(c, lambdaIterate, upOnly, storeDepth);
+#endif
+        case LWB200_FS_BEZIER3: return launch_fs_long<2, MODE>(c, lambdaIterate, upOnly, storeDepth);
+        }
+        return fail("unknown formal solver");
+    }
     switch (c->NCH)
     {
 #ifndef LWB200_DEV_FAST_BUILD
@@ -823,7 +882,7 @@ int launch_fs(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
     case 4: return launch_fs_s<4, MODE>(c, lambdaIterate, upOnly, storeDepth);
 #endif
     }
-    return fail("Nspace > 128 is not supported yet by the register-resident depth layout");
+    return fail("unexpected depth layout");
 }
 
 int copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
@@ -866,8 +925,8 @@ int lwb200_create(const LwB200Problem* problem, int device, LwB200Context** out)
         return fail("lwb200_create: ABI version mismatch");
     if (problem->Nspace < 3 || problem->Nrays < 1 || problem->Nspect < 1 || problem->Ncol < 1 || problem->Natom < 1)
         return fail("lwb200_create: bad dimensions");
-    if (problem->Nspace > 128)
-        return fail("lwb200_create: Nspace > 128 is not supported yet");
+    if (problem->Nspace > 1024)
+        return fail("lwb200_create: Nspace > 1024 is not supported");
     if (problem->formalSolver < 0 || problem->formalSolver > 2)
         return fail("lwb200_create: formalSolver must be 0 (linear), 1 (besser) or 2 (bezier3)");
     int ndev = 0;

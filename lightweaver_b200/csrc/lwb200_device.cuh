@@ -134,6 +134,199 @@ __device__ __forceinline__ void affine_scan(const double (&a)[NCH], const double
 }
 
 // ---------------------------------------------------------------------------
+// Depth ownership beyond one warp.  MULTI = false: one warp covers the whole column
+// (Nspace <= 32 * NCH) and everything below is plain warp shuffles.  MULTI = true: the
+// warps of a CTA cover consecutive blocks of 32 * NCH depths of ONE wavelength; a lane's
+// depth neighbour may live in the adjacent warp, so edge values and the scan carry cross
+// warps through a few doubles of shared memory (double-buffered: one barrier per exchange).
+// Every warp of the CTA must make the same sequence of calls.
+template <bool MULTI>
+struct DepthComm
+{
+    double* buf;  // MULTI: [2][nwarp] edge exchange, then [2][nwarp][2] scan composites, then [nwarp]
+    int warp;     // position of this warp along depth
+    int nwarp;
+    int parity;
+
+    __device__ __forceinline__ int lane_global() const { return MULTI ? warp * 32 + lane_id() : lane_id(); }
+
+    // `v` of the previous lane along depth (the first lane of the column gets its own value back)
+    __device__ __forceinline__ double from_prev(double v)
+    {
+        double r = __shfl_up_sync(kFull, v, 1);
+        if (MULTI)
+        {
+            const int lane = lane_id();
+            if (lane == 31)
+                buf[parity * nwarp + warp] = v;
+            __syncthreads();
+            if (lane == 0 && warp > 0)
+                r = buf[parity * nwarp + warp - 1];
+            parity ^= 1;
+        }
+        return r;
+    }
+    // `v` of the next lane along depth (the last lane gets its own value back)
+    __device__ __forceinline__ double from_next(double v)
+    {
+        double r = __shfl_down_sync(kFull, v, 1);
+        if (MULTI)
+        {
+            const int lane = lane_id();
+            if (lane == 0)
+                buf[parity * nwarp + warp] = v;
+            __syncthreads();
+            if (lane == 31 && warp < nwarp - 1)
+                r = buf[parity * nwarp + warp + 1];
+            parity ^= 1;
+        }
+        return r;
+    }
+    // max over all lanes of all warps, valid in every thread
+    __device__ __forceinline__ double max_all(double v)
+    {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+        {
+            const double o = __shfl_xor_sync(kFull, v, d);
+            v = (o < v) ? v : o;
+        }
+        if (MULTI)
+        {
+            double* mx = buf + 6 * nwarp;
+            if (lane_id() == 0)
+                mx[warp] = v;
+            __syncthreads();
+            for (int w = 0; w < nwarp; ++w)
+                v = (mx[w] < v) ? v : mx[w];
+            __syncthreads();
+        }
+        return v;
+    }
+};
+
+template <int NCH, bool MULTI>
+__device__ __forceinline__ void shift_prev(DepthComm<MULTI>& cm, const double (&v)[NCH], double (&out)[NCH])
+{
+    const double up = cm.from_prev(v[NCH - 1]);
+    out[0] = up;
+#pragma unroll
+    for (int j = 1; j < NCH; ++j)
+        out[j] = v[j - 1];
+}
+
+template <int NCH, bool MULTI>
+__device__ __forceinline__ void shift_next(DepthComm<MULTI>& cm, const double (&v)[NCH], double (&out)[NCH])
+{
+    const double dn = cm.from_next(v[0]);
+#pragma unroll
+    for (int j = 0; j < NCH - 1; ++j)
+        out[j] = v[j + 1];
+    out[NCH - 1] = dn;
+}
+
+// affine_scan across the warps of a CTA: in-warp scan as above, then the composite of every
+// warp goes through shared memory and each warp folds the ones before it into its carry.
+template <int NCH, bool DOWN, bool MULTI>
+__device__ __forceinline__ void affine_scan(DepthComm<MULTI>& cm, const double (&a)[NCH], const double (&b)[NCH],
+                                            double (&I)[NCH])
+{
+    if (!MULTI)
+    {
+        affine_scan<NCH, DOWN>(a, b, I);
+        return;
+    }
+    const int lane = lane_id();
+    double A, B;
+    if (DOWN)
+    {
+        A = a[0];
+        B = b[0];
+#pragma unroll
+        for (int j = 1; j < NCH; ++j)
+        {
+            B = fma(a[j], B, b[j]);
+            A = a[j] * A;
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const double Ap = __shfl_up_sync(kFull, A, d);
+            const double Bp = __shfl_up_sync(kFull, B, d);
+            if (lane >= d)
+            {
+                B = fma(A, Bp, B);
+                A = A * Ap;
+            }
+        }
+    }
+    else
+    {
+        A = a[NCH - 1];
+        B = b[NCH - 1];
+#pragma unroll
+        for (int j = NCH - 2; j >= 0; --j)
+        {
+            B = fma(a[j], B, b[j]);
+            A = a[j] * A;
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const double Ap = __shfl_down_sync(kFull, A, d);
+            const double Bp = __shfl_down_sync(kFull, B, d);
+            if (lane + d < 32)
+            {
+                B = fma(A, Bp, B);
+                A = A * Ap;
+            }
+        }
+    }
+    // warp composites -> carry into this warp
+    double* sc = cm.buf + 2 * cm.nwarp + cm.parity * 2 * cm.nwarp;
+    if (lane == (DOWN ? 31 : 0))
+    {
+        sc[2 * cm.warp] = A;
+        sc[2 * cm.warp + 1] = B;
+    }
+    __syncthreads();
+    double c = 0.0;
+    if (DOWN)
+    {
+        for (int w = 0; w < cm.warp; ++w)
+            c = fma(sc[2 * w], c, sc[2 * w + 1]);
+    }
+    else
+    {
+        for (int w = cm.nwarp - 1; w > cm.warp; --w)
+            c = fma(sc[2 * w], c, sc[2 * w + 1]);
+    }
+    cm.parity ^= 1;
+    // intensity entering this lane: composite of the lanes before it applied to the carry
+    const double Ap = DOWN ? __shfl_up_sync(kFull, A, 1) : __shfl_down_sync(kFull, A, 1);
+    const double Bp = DOWN ? __shfl_up_sync(kFull, B, 1) : __shfl_down_sync(kFull, B, 1);
+    double x = (lane == (DOWN ? 0 : 31)) ? c : fma(Ap, c, Bp);
+    if (DOWN)
+    {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+        {
+            x = fma(a[j], x, b[j]);
+            I[j] = x;
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int j = NCH - 1; j >= 0; --j)
+        {
+            x = fma(a[j], x, b[j]);
+            I[j] = x;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Steffen (1990) derivative from the two adjacent slopes (Bezier.hpp:58-65).
 // Written for the array-forward ("DOWN") orientation; the derivative along an
 // up-going ray is exactly its negative (all products commute bitwise).

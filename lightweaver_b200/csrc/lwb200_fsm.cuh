@@ -52,13 +52,6 @@ __device__ __forceinline__ double exp_fast(double x)
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
-// one 64-bit value from the neighbouring lane: lane-1 if `fromPrev`, else lane+1
-__device__ __forceinline__ double shfl_neighbour(double v, bool fromPrev)
-{
-    const int src = lane_id() + (fromPrev ? -1 : 1);
-    return __shfl_sync(kFull, v, src & 31);
-}
-
 template <int NCH>
 struct GeometryR
 {
@@ -70,10 +63,11 @@ struct GeometryR
     double rdsfP0;     // 1 / dsfP[0]
 };
 
-template <int NCH>
-__device__ __forceinline__ void load_geometry_r(GeometryR<NCH>& g, const double* __restrict__ height, int K)
+template <int NCH, bool MULTI>
+__device__ __forceinline__ void load_geometry_r(DepthComm<MULTI>& cm, GeometryR<NCH>& g,
+                                                const double* __restrict__ height, int K)
 {
-    const int lane = lane_id();
+    const int lane = cm.lane_global();
     g.K = K;
     double h[NCH], hN[NCH];
 #pragma unroll
@@ -82,14 +76,14 @@ __device__ __forceinline__ void load_geometry_r(GeometryR<NCH>& g, const double*
         const int k = lane * NCH + j;
         h[j] = (k < K) ? __ldg(height + k) : 0.0;
     }
-    shift_next<NCH>(h, hN);
+    shift_next<NCH>(cm, h, hN);
 #pragma unroll
     for (int j = 0; j < NCH; ++j)
     {
         const int k = lane * NCH + j;
         g.dsf[j] = (k + 1 < K) ? fabs(h[j] - hN[j]) : 1.0;
     }
-    shift_prev<NCH>(g.dsf, g.dsfP);
+    shift_prev<NCH>(cm, g.dsf, g.dsfP);
     if (lane == 0)
         g.dsfP[0] = 1.0;
 #pragma unroll
@@ -129,23 +123,23 @@ struct RayPre
     double DSf[NCH];  // dS/dtau at k, forward orientation
 };
 
-template <int NCH>
-__device__ __forceinline__ void bezier3_prepare(const GeometryR<NCH>& g, const double (&chi)[NCH],
-                                                const double (&S)[NCH], double muz, double zmu,
-                                                RayPre<NCH>& r)
+template <int NCH, bool MULTI>
+__device__ __forceinline__ void bezier3_prepare(DepthComm<MULTI>& cm, const GeometryR<NCH>& g,
+                                                const double (&chi)[NCH], const double (&S)[NCH], double muz,
+                                                double zmu, RayPre<NCH>& r)
 {
-    const int lane = lane_id();
+    const int lane = cm.lane_global();
     const int K = g.K;
     double chiN[NCH];
-    shift_next<NCH>(chi, chiN);
-    shift_next<NCH>(S, r.SN);
+    shift_next<NCH>(cm, chi, chiN);
+    shift_next<NCH>(cm, S, r.SN);
 
     // chi slopes on forward intervals and Steffen derivatives
     double sl[NCH], Df[NCH], DfN[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j)
         sl[j] = (chiN[j] - chi[j]) * (g.rdsf[j] * muz);
-    const double slUp = __shfl_up_sync(kFull, sl[NCH - 1], 1);
+    const double slUp = cm.from_prev(sl[NCH - 1]);
 #pragma unroll
     for (int j = 0; j < NCH; ++j)
     {
@@ -156,7 +150,7 @@ __device__ __forceinline__ void bezier3_prepare(const GeometryR<NCH>& g, const d
         d = sel(k == K - 1, slPj, d);    // one-sided at the bottom
         Df[j] = d;
     }
-    shift_next<NCH>(Df, DfN);
+    shift_next<NCH>(cm, Df, DfN);
 
     double dtfP[NCH];
 #pragma unroll
@@ -170,13 +164,13 @@ __device__ __forceinline__ void bezier3_prepare(const GeometryR<NCH>& g, const d
         r.dtf[j] = ds * ((t1 + cA) + cB) * 0.25;
         r.rdtf[j] = rcp_fast(r.dtf[j]);
     }
-    shift_prev<NCH>(r.dtf, dtfP);
+    shift_prev<NCH>(cm, r.dtf, dtfP);
 
     double slS[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j)
         slS[j] = (r.SN[j] - S[j]) * r.rdtf[j];
-    const double slSUp = __shfl_up_sync(kFull, slS[NCH - 1], 1);
+    const double slSUp = cm.from_prev(slS[NCH - 1]);
 #pragma unroll
     for (int j = 0; j < NCH; ++j)
     {
@@ -207,31 +201,31 @@ __device__ __forceinline__ double pick(const double (&v)[NCH], int jx)
 // fix-ups computed once per ray instead of once per point: the last point is piecewise
 // linear through w2() (:307-321, LwInternal.hpp:90-110), the first carries the boundary
 // intensity (:551-597).  Outputs I and psi = Psi*/chi.
-template <int NCH, bool DOWN>
-__device__ __forceinline__ void bezier3_sweep(const GeometryR<NCH>& g, const double (&chi)[NCH],
+template <int NCH, bool DOWN, bool MULTI>
+__device__ __forceinline__ void bezier3_sweep(DepthComm<MULTI>& cm, const GeometryR<NCH>& g, const double (&chi)[NCH],
                                               const double (&S)[NCH], const double (&rchi)[NCH],
                                               const RayPre<NCH>& r, double zmu, int bcType, double bcB0,
                                               double bcB1, double bcValue, double (&I)[NCH],
                                               double (&psi)[NCH])
 {
-    const int lane = lane_id();
+    const int lane = cm.lane_global();
     const int K = g.K;
     const int kS = DOWN ? 0 : K - 1;
     const int kE = DOWN ? K - 1 : 0;
     // upwind neighbours along the ray
     double SU[NCH], dtU[NCH], rdtU[NCH], DSU[NCH], chiP[NCH], chiN[NCH];
-    shift_prev<NCH>(chi, chiP);
-    shift_next<NCH>(chi, chiN);
+    shift_prev<NCH>(cm, chi, chiP);
+    shift_next<NCH>(cm, chi, chiN);
     if (DOWN)
     {
-        shift_prev<NCH>(S, SU);
-        shift_prev<NCH>(r.dtf, dtU);
-        shift_prev<NCH>(r.rdtf, rdtU);
-        shift_prev<NCH>(r.DSf, DSU);
+        shift_prev<NCH>(cm, S, SU);
+        shift_prev<NCH>(cm, r.dtf, dtU);
+        shift_prev<NCH>(cm, r.rdtf, rdtU);
+        shift_prev<NCH>(cm, r.DSf, DSU);
     }
     else
     {
-        shift_next<NCH>(r.DSf, DSU);
+        shift_next<NCH>(cm, r.DSf, DSU);
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
         {
@@ -322,7 +316,7 @@ __device__ __forceinline__ void bezier3_sweep(const GeometryR<NCH>& g, const dou
     if (DOWN)
     {
         // padding lanes (k >= K) come after every real point: whatever they hold is never used
-        affine_scan<NCH, true>(a, b, I);
+        affine_scan<NCH, true>(cm, a, b, I);
     }
     else
     {
@@ -334,28 +328,28 @@ __device__ __forceinline__ void bezier3_sweep(const GeometryR<NCH>& g, const dou
             a[j] = sel(valid, a[j], 1.0);
             b[j] = sel(valid, b[j], 0.0);
         }
-        affine_scan<NCH, false>(a, b, I);
+        affine_scan<NCH, false>(cm, a, b, I);
     }
 }
 
 // linear (SOLVER 0) and besser (SOLVER 1): local stencils only
-template <int NCH, int SOLVER>
-__device__ __forceinline__ void local_stencil_ray(const GeometryR<NCH>& g, const double (&chi)[NCH],
+template <int NCH, int SOLVER, bool MULTI>
+__device__ __forceinline__ void local_stencil_ray(DepthComm<MULTI>& cm, const GeometryR<NCH>& g, const double (&chi)[NCH],
                                                   const double (&S)[NCH], const double (&rchi)[NCH],
                                                   double muz, bool down, int bcType, double bcB0,
                                                   double bcB1, double bcValue, double (&I)[NCH],
                                                   double (&psi)[NCH])
 {
-    const int lane = lane_id();
+    const int lane = cm.lane_global();
     const int K = g.K;
     const int ks = down ? 0 : K - 1;
     const int ke = down ? K - 1 : 0;
     double a[NCH], b[NCH];
     double chiN[NCH], chiP[NCH], SN[NCH], SP[NCH];
-    shift_next<NCH>(chi, chiN);
-    shift_prev<NCH>(chi, chiP);
-    shift_next<NCH>(S, SN);
-    shift_prev<NCH>(S, SP);
+    shift_next<NCH>(cm, chi, chiN);
+    shift_prev<NCH>(cm, chi, chiP);
+    shift_next<NCH>(cm, S, SN);
+    shift_prev<NCH>(cm, S, SP);
     const double zmu = (SOLVER == 0 ? 0.5 : 1.0) / muz;
 #pragma unroll
     for (int j = 0; j < NCH; ++j)
@@ -454,11 +448,10 @@ __device__ __forceinline__ void local_stencil_ray(const GeometryR<NCH>& g, const
         b[j] = bb;
         psi[j] = pp * rchi[j];
     }
-    __syncwarp();
     if (down)
-        affine_scan<NCH, true>(a, b, I);
+        affine_scan<NCH, true>(cm, a, b, I);
     else
-        affine_scan<NCH, false>(a, b, I);
+        affine_scan<NCH, false>(cm, a, b, I);
 }
 
 } // namespace lwb200

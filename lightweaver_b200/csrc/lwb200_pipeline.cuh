@@ -114,24 +114,40 @@ __global__ void continuum_kernel(const DevProblem P, const int* __restrict__ til
 #define LWB200_RAY_MINBLOCKS 2
 #endif
 
-template <int NCH, int SOLVER, int NL>
-__global__ void __launch_bounds__(128, LWB200_RAY_MINBLOCKS)
+// MULTI = false: one warp per wavelength (Nspace <= 32 * NCH), `perWarp` wavelengths per warp.
+// MULTI = true:  one CTA per wavelength, its warps laid over consecutive blocks of 32 * NCH
+//                depths (Nspace <= blockDim.x * NCH); neighbours and the scan carry cross
+//                warps through DepthComm.
+template <int NCH, int SOLVER, int NL, bool MULTI>
+__global__ void __launch_bounds__(MULTI ? 256 : 128, MULTI ? 1 : LWB200_RAY_MINBLOCKS)
 ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int perWarp, int colBase,
-           int lambdaIterate, int storeDepth)
+           int lambdaIterate, int storeDepth, int fsMode)
 {
+    // fsMode: 0 Gamma iteration; 1 formal solution only (formal_sol_impl, :721-781: emergent I,
+    // nothing else written); 3 the same with up-going rays only (upOnly)
+    const bool fsOnly = (fsMode & 1) != 0;
+    const int dirFirst = (fsMode & 2) ? 1 : 0;
     constexpr int NLA = NL > 0 ? NL : 1;
     constexpr int NPAIR = NL > 1 ? NL * (NL - 1) / 2 : 1;
+    __shared__ double commBuf[MULTI ? 7 * 8 : 1];
     const int K = P.K, M = P.M, L = P.L;
     const int cb = blockIdx.y, col = colBase + cb;
     // warp index made provably warp-uniform: every loop below stays convergent
     const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0);
-    const int lane = lane_id();
-    const int first = (blockIdx.x * (blockDim.x >> 5) + warp) * perWarp;
+    DepthComm<MULTI> cm;
+    cm.buf = commBuf;
+    cm.warp = MULTI ? warp : 0;
+    cm.nwarp = MULTI ? (int)(blockDim.x >> 5) : 1;
+    cm.parity = 0;
+    const int lane = cm.lane_global(); // position along depth in units of NCH points
+    const int first = MULTI ? (int)blockIdx.x : (int)(blockIdx.x * (blockDim.x >> 5) + warp) * perWarp;
+    if (MULTI)
+        perWarp = 1;
     if (first >= nLam)
         return;
 
     GeometryR<NCH> g;
-    load_geometry_r<NCH>(g, P.height + (size_t)col * K, K);
+    load_geometry_r<NCH>(cm, g, P.height + (size_t)col * K, K);
     const double* Tcol = P.temperature + (size_t)col * K;
     const double* ncol = P.n + (size_t)col * P.NlevTot * K;
 
@@ -222,7 +238,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
         RayPre<NCH> pre;
         // the up and down rays of one mu share opacities, source function and the whole
         // direction-independent phase of the solver when their profiles are identical
-        const bool shareDir = (SOLVER == 2) && !storeDepth && (__ldg(P.phiAsym) == 0);
+        const bool shareDir = (SOLVER == 2) && !storeDepth && dirFirst == 0 && (__ldg(P.phiAsym) == 0);
 
         // line-free wavelengths: chi and S are the same for every ray; interpolation data once at mu = 1
         RayPre<NCH> pre1;
@@ -237,7 +253,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
                 p[0][j] = 0.0;
             }
             if (SOLVER == 2)
-                bezier3_prepare<NCH>(g, chi, S, 1.0, 1.0, pre1);
+                bezier3_prepare<NCH>(cm, g, chi, S, 1.0, 1.0, pre1);
         }
         // profiles are fetched one ray ahead (NL <= 2; three lines leave no registers for it)
 #ifdef LWB200_NO_PREFETCH
@@ -252,7 +268,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
             for (int l = 0; l < NLA; ++l)
 #pragma unroll
                 for (int j = 0; j < NCH; ++j)
-                    pn[l][j] = (lane * NCH + j < K) ? __ldg(ph[l] + j) : 0.0;
+                    pn[l][j] = (lane * NCH + j < K) ? __ldg(ph[l] + (size_t)dirFirst * K + j) : 0.0;
         }
 
         for (int mu = 0; mu < M; ++mu)
@@ -275,12 +291,14 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
 #pragma unroll
             for (int dir = 0; dir < 2; ++dir)
             {
+                if (dir < dirFirst)
+                    continue;
                 if (NL > 0 && (dir == 0 || !shareDir))
                 {
                     const int row = 2 * mu + dir;
                     if (PREFETCH)
                     {
-                        const int nextRow = shareDir ? row + 2 : row + 1;
+                        const int nextRow = (shareDir || dirFirst) ? row + 2 : row + 1;
 #pragma unroll
                         for (int l = 0; l < NLA; ++l)
 #pragma unroll
@@ -322,7 +340,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
                         }
                     }
                     if (SOLVER == 2)
-                        bezier3_prepare<NCH>(g, chi, S, muz, zmu, pre);
+                        bezier3_prepare<NCH>(cm, g, chi, S, muz, zmu, pre);
                 }
                 else if (NL == 0 && storeDepth)
                 {
@@ -360,12 +378,12 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
                 if (SOLVER == 2)
                 {
                     if (dir == 0)
-                        bezier3_sweep<NCH, true>(g, chi, S, rchi, pre, zmu, bcType, bcB0, bcB1, bcValue, I, psi);
+                        bezier3_sweep<NCH, true>(cm, g, chi, S, rchi, pre, zmu, bcType, bcB0, bcB1, bcValue, I, psi);
                     else
-                        bezier3_sweep<NCH, false>(g, chi, S, rchi, pre, zmu, bcType, bcB0, bcB1, bcValue, I, psi);
+                        bezier3_sweep<NCH, false>(cm, g, chi, S, rchi, pre, zmu, bcType, bcB0, bcB1, bcValue, I, psi);
                 }
                 else
-                    local_stencil_ray<NCH, SOLVER>(g, chi, S, rchi, muz, dir == 0, bcType, bcB0, bcB1, bcValue, I,
+                    local_stencil_ray<NCH, SOLVER>(cm, g, chi, S, rchi, muz, dir == 0, bcType, bcB0, bcB1, bcValue, I,
                                                    psi);
 
                 if (lane == 0)
@@ -409,6 +427,8 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
             }
         }
 
+        if (fsOnly)
+            continue;
         // ---- J row, dJ (:477-485) and the moment rows
         double dJ = 0.0;
         double* mom = P.mom + ((size_t)cb * P.momRows + P.momOff[la]) * K;
@@ -442,12 +462,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
                 }
             }
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1)
-        {
-            const double o = __shfl_xor_sync(kFull, dJ, d);
-            dJ = (o < dJ) ? dJ : o;
-        }
+        dJ = cm.max_all(dJ);
         if (lane == 0)
             P.dJ[(size_t)col * L + la] = dJ;
     }
@@ -472,7 +487,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
     constexpr int NLA = NL > 0 ? NL : 1;
     constexpr int NQ = NL + 1;
     const int K = P.K;
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x, nthr = blockDim.x, KC = blockDim.x; // shared-memory row stride
     const double lambda = __ldg(P.wavelength + la);
     const double rlambda = 1.0 / lambda;
     constexpr double hc_k = kHC / (kKBoltzmann * kNmToM);
@@ -523,8 +538,8 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
             const double gS = ll.Bji_Bij;
             const double r = (ll.rhoOff >= 0) ? __ldg(P.rhoPrd + ll.rhoOff + (size_t)col * ll.rhoColStride + k) : 1.0;
             const double gk = (ll.rhoOff >= 0) ? gS * r : gS;
-            const double ni = sd[(ll.slot * 3 + 0) * K];
-            const double nj = sd[(ll.slot * 3 + 1) * K];
+            const double ni = sd[(ll.slot * 3 + 0) * KC];
+            const double nj = sd[(ll.slot * 3 + 1) * KC];
             lsTrans[l] = ll.trans;
             lsAtom[l] = ll.atom;
             lsI[l] = ll.i;
@@ -534,7 +549,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
             lsUgv[l] = (ll.Aji_Bji * (gS * vB)) * r;
             lsX[l] = vB * (ni - nj * gk);
             lsE[l] = nj * (ll.Aji_Bji * (gk * vB));
-            lsWla[l] = ll.wlaS * sd[(ll.slot * 3 + 2) * K];
+            lsWla[l] = ll.wlaS * sd[(ll.slot * 3 + 2) * KC];
         }
     }
 
@@ -562,12 +577,12 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
                 if (t.type == 0)
                     continue;
                 const double al = t.al;
-                const double* sds = sd + t.slot * 3 * K;
-                const double gk = sds[2 * K] * expfac;
+                const double* sds = sd + t.slot * 3 * KC;
+                const double gk = sds[2 * KC] * expfac;
                 const double Vji = gk * al;
                 const double Uji = hcl * Vji;
                 const double ni = sds[0];
-                const double nj = sds[K];
+                const double nj = sds[KC];
                 const double x = ni * al - nj * Vji;
                 Xs[t.i * nthr + tid] += x;
                 Xs[t.j * nthr + tid] -= x;
@@ -608,7 +623,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
             double v = 0.0, gv = 0.0, ugv = 0.0, Wq = W0, Aq = mJ, EBq = EB[0], wla = 0.0;
             if (t.type != 0)
             {
-                const double gk = sd[(t.slot * 3 + 2) * K] * expfac;
+                const double gk = sd[(t.slot * 3 + 2) * KC] * expfac;
                 v = t.al;
                 gv = gk * t.al;
                 ugv = hcl * gv;
@@ -628,7 +643,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
                     wla = lsWla[l];
                 }
             }
-            double* a4 = acc + t.slot * 4 * K;
+            double* a4 = acc + t.slot * 4 * KC;
             if (!detailed)
             {
                 // chi_atom(m) = sum_q p_q X_q(m), U_atom(m) = sum_q p_q U_q(m)
@@ -662,10 +677,10 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
                 }
                 // sum_r w [(Uji + Vji Ieff) - Psi* chi(i) U(j)],  Ieff = I - Psi* eta_atom
                 a4[0] += (ugv * Wq + gv * (Aq - EBq) - XUij) * wla;
-                a4[K] += (v * (Aq - EBq) - XUji) * wla;
+                a4[KC] += (v * (Aq - EBq) - XUji) * wla;
             }
-            a4[2 * K] += (v * Aq) * wla;
-            a4[3 * K] += (ugv * Wq + gv * Aq) * wla;
+            a4[2 * KC] += (v * Aq) * wla;
+            a4[3 * KC] += (ugv * Wq + gv * Aq) * wla;
         }
         e0 = e1;
     }
@@ -675,15 +690,16 @@ __global__ void __launch_bounds__(128, LWB200_GAMMA_MINBLOCKS) gamma_kernel(cons
                              int colBase)
 {
     extern __shared__ double smem[];
-    const int K = P.K;
+    // depth chunk of this CTA: blockDim.x consecutive depths (one chunk covers Nspace <= 128)
+    const int K = P.K, KC = blockDim.x;
     const int tile = tileList[blockIdx.x];
     const int cb = blockIdx.y, col = colBase + cb;
-    const int k = threadIdx.x;
+    const int kk = threadIdx.x, k = blockIdx.z * KC + kk;
     const int slot0 = P.tileSlotOff[tile];
     const int nslot = P.tileSlotOff[tile + 1] - slot0;
-    double* acc = smem;                                   // [nslot][4][K]   partial sums, one writer each
-    double* slotD = smem + (size_t)P.maxSlots * 4 * K;    // [nslot][3][K]   staged per-depth data
-    double* Xs = slotD + (size_t)P.maxSlots * 3 * K;      // [maxNlevel][blockDim]
+    double* acc = smem;                                   // [nslot][4][KC]  partial sums, one writer each
+    double* slotD = smem + (size_t)P.maxSlots * 4 * KC;   // [nslot][3][KC]  staged per-depth data
+    double* Xs = slotD + (size_t)P.maxSlots * 3 * KC;     // [maxNlevel][KC]
     double* Us = Xs + (size_t)P.maxNlevel * blockDim.x;
     if (k < K)
     {
@@ -694,14 +710,14 @@ __global__ void __launch_bounds__(128, LWB200_GAMMA_MINBLOCKS) gamma_kernel(cons
         for (int s = 0; s < nslot; ++s)
         {
             const DevTrans& t = P.trans[P.tileSlotTrans[slot0 + s]];
-            acc[(s * 4 + 0) * K + k] = 0.0;
-            acc[(s * 4 + 1) * K + k] = 0.0;
-            acc[(s * 4 + 2) * K + k] = 0.0;
-            acc[(s * 4 + 3) * K + k] = 0.0;
+            acc[(s * 4 + 0) * KC + kk] = 0.0;
+            acc[(s * 4 + 1) * KC + kk] = 0.0;
+            acc[(s * 4 + 2) * KC + kk] = 0.0;
+            acc[(s * 4 + 3) * KC + kk] = 0.0;
             const double* ncol = P.n + (size_t)col * P.NlevTot * K + k;
-            slotD[(s * 3 + 0) * K + k] = __ldg(ncol + (size_t)t.levI * K);
-            slotD[(s * 3 + 1) * K + k] = __ldg(ncol + (size_t)t.levJ * K);
-            slotD[(s * 3 + 2) * K + k] = (t.type == 0)
+            slotD[(s * 3 + 0) * KC + kk] = __ldg(ncol + (size_t)t.levI * K);
+            slotD[(s * 3 + 1) * KC + kk] = __ldg(ncol + (size_t)t.levJ * K);
+            slotD[(s * 3 + 2) * KC + kk] = (t.type == 0)
                 ? __ldg(P.wphi + ((size_t)t.lineIdx * P.Ncol + col) * K + k)
                 : __ldg(P.gRatio + ((size_t)t.contIdx * P.Ncol + col) * K + k);
         }
@@ -722,10 +738,10 @@ __global__ void __launch_bounds__(128, LWB200_GAMMA_MINBLOCKS) gamma_kernel(cons
                 continue;
             switch (P.laNLines[la])
             {
-            case 0: gamma_lambda<0>(P, la, col, cb, k, Tk, W0, acc + k, slotD + k, Xs, Us); break;
-            case 1: gamma_lambda<1>(P, la, col, cb, k, Tk, W0, acc + k, slotD + k, Xs, Us); break;
-            case 2: gamma_lambda<2>(P, la, col, cb, k, Tk, W0, acc + k, slotD + k, Xs, Us); break;
-            case 3: gamma_lambda<3>(P, la, col, cb, k, Tk, W0, acc + k, slotD + k, Xs, Us); break;
+            case 0: gamma_lambda<0>(P, la, col, cb, k, Tk, W0, acc + kk, slotD + kk, Xs, Us); break;
+            case 1: gamma_lambda<1>(P, la, col, cb, k, Tk, W0, acc + kk, slotD + kk, Xs, Us); break;
+            case 2: gamma_lambda<2>(P, la, col, cb, k, Tk, W0, acc + kk, slotD + kk, Xs, Us); break;
+            case 3: gamma_lambda<3>(P, la, col, cb, k, Tk, W0, acc + kk, slotD + kk, Xs, Us); break;
             default: break; // > 3 overlapping lines: handled by the general kernel
             }
         }
@@ -737,7 +753,7 @@ __global__ void __launch_bounds__(128, LWB200_GAMMA_MINBLOCKS) gamma_kernel(cons
 #pragma unroll
             for (int q = 0; q < 4; ++q)
             {
-                const double v = acc[(s * 4 + q) * K + k];
+                const double v = acc[(s * 4 + q) * KC + kk];
                 if (rows[q] >= 0 && v != 0.0)
                     atomicAdd(P.accum + ((size_t)col * P.AccTot + rows[q]) * K + k, v);
             }

@@ -126,8 +126,45 @@ def test_depth_counts_across_lane_layouts(ndepth):
     ctx.close()
 
 
+@pytest.mark.parametrize('ndepth,solver', [(129, capi.FS_BEZIER3), (200, capi.FS_BEZIER3), (256, capi.FS_BEZIER3),
+                                           (257, capi.FS_BESSER), (500, capi.FS_BEZIER3), (500, capi.FS_LINEAR),
+                                           (1000, capi.FS_BEZIER3)])
+def test_deep_atmospheres_multi_warp_columns(ndepth, solver):
+    """Nspace > 128: several warps per wavelength (4 depths per lane), neighbours and the
+    scan carry exchanged between warps; warp-boundary and partially filled last warps."""
+    p = synth.tiny_problem(ndepth=ndepth, nrays=2, ncol=2, perturb=True, formal_solver=solver)
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+        ctx.stat_equil()
+        oracle_iter(q, lambdaIterate=(it == 0))
+        assert_close(p, q)
+    for upOnly in (True, False):
+        p.I[:] = -1.0
+        ctx.formal_sol(upOnly=upOnly)
+        for c in range(q.Ncol):
+            oraclelib.OracleContext(q, col=c).formal_sol(upOnly=upOnly)
+        assert rel_err(p.I, q.I) <= TOL
+    ctx.close()
+
+
+def test_deep_static_atmosphere_shares_directions():
+    """Nspace > 128 without velocities: the up/down rays of one mu share the direction-independent
+    phase of the solver (identical profiles), also across warps."""
+    p = synth.tiny_problem(ndepth=300, nrays=3)
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices()
+        ctx.stat_equil()
+        oracle_iter(q)
+        assert_close(p, q)
+    ctx.close()
+
+
 def test_too_many_depths_fails_loudly():
-    p = synth.tiny_problem(ndepth=200, nrays=2, with_profiles=False)
+    p = synth.tiny_problem(ndepth=1100, nrays=2, with_profiles=False)
     with pytest.raises(capi.LwB200Error):
         Context(p)
 
