@@ -409,6 +409,20 @@ def run_reference(args, rank, world):
 
 
 def main():
+    # only the JSON line may reach stdout (NCCL and torch.distributed print banners there)
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -423,10 +437,7 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
 
     if args.impl == 'reference':
-        line = run_reference(args, rank, world)
-        if line is not None:
-            print(json.dumps(line), flush=True)
-        return
+        return run_reference(args, rank, world)
 
     import torch
     import torch.distributed as dist
@@ -441,8 +452,7 @@ def main():
     finally:
         if world > 1:
             dist.destroy_process_group()
-    if line is not None:
-        print(json.dumps(line), flush=True)
+    return line
 
 
 if __name__ == '__main__':

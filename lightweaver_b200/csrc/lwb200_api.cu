@@ -302,13 +302,13 @@ int build_plan(LwB200Context* c)
     const size_t scratchGamma = (size_t)2 * maxNlevel * KC * sizeof(double);
     const size_t scratchBytes = std::max(scratchFs, scratchGamma);
     const size_t smemLimit = 200 * 1024;
-    if (scratchBytes + 7 * KC * sizeof(double) > smemLimit)
+    if (scratchBytes + 4 * KC * sizeof(double) > smemLimit)
         return fail("atom too large for the shared-memory scratch");
     // keep the accumulator <= ~48 KB so that several CTAs share an SM
     // per slot: 4 accumulator rows (+ 3 rows of staged per-depth data in gamma_kernel); keep a
     // CTA under ~48 KB so that several share an SM and the L1 keeps some room
-    const size_t accBudget = std::min<size_t>(smemLimit - scratchBytes, 40 * 1024);
-    const int slotCap = (int)std::max<size_t>(accBudget / (7 * KC * sizeof(double)), 1);
+    const size_t accBudget = std::min<size_t>(smemLimit - scratchBytes, 32 * 1024);
+    const int slotCap = (int)std::max<size_t>(accBudget / (4 * KC * sizeof(double)), 1);
     if ((long long)std::max(ncont, 1) * p.Ncol * K > 0x7fffffffLL)
         return fail("gRatio block exceeds 2^31 elements");
     const long long targetCtas = 148LL * 16;
@@ -341,7 +341,7 @@ int build_plan(LwB200Context* c)
                         add.push_back(g);
                 if ((int)(slots.size() + add.size()) > slotCap && pos > start)
                     break;
-                if ((int)(slots.size() + add.size()) * 7 * KC * sizeof(double) + scratchBytes > smemLimit)
+                if ((int)(slots.size() + add.size()) * 4 * KC * sizeof(double) + scratchBytes > smemLimit)
                     return fail("too many transitions active at one wavelength for shared memory");
                 slots.insert(slots.end(), add.begin(), add.end());
                 ++pos;
@@ -410,7 +410,7 @@ int build_plan(LwB200Context* c)
     laOff[L] = (int)entries.size();
     c->Ntile = (int)c->tileLa.size() - 1;
     c->smemBytes = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchFs;
-    c->smemGamma = (size_t)maxSlots * 7 * KC * sizeof(double) + scratchGamma;
+    c->smemGamma = (size_t)maxSlots * 4 * KC * sizeof(double) + scratchGamma;
     c->KC = KC;
     if (c->smemGamma > smemLimit)
         return fail("wavelength tile too large for shared memory");

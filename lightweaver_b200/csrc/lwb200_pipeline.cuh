@@ -481,8 +481,8 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
 
 template <int NL>
 __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int col, int cb, int k, double Tk,
-                                             double W0, double* __restrict__ acc, const double* __restrict__ sd,
-                                             double* __restrict__ Xs, double* __restrict__ Us)
+                                             double W0, double* __restrict__ acc, double* __restrict__ Xs,
+                                             double* __restrict__ Us)
 {
     constexpr int NLA = NL > 0 ? NL : 1;
     constexpr int NQ = NL + 1;
@@ -495,8 +495,8 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
     constexpr double hc_4pi = 0.25 * kHC / kPi;
     const double hc_kl = hc_k * rlambda;
     const double hcl = twoHc * (rlambda * rlambda * rlambda);
-    // sd: this thread's column of the tile's staged per-depth data, [slot][3][K]:
-    //     n(levI), n(levJ), and gRatio (continuum) or wphi (line)
+    const double* ncol = P.n + (size_t)col * P.NlevTot * K + k;
+    const double* gcol = P.gRatio + (size_t)col * K + k;
 
     // moments of this wavelength at depth k (independent loads, issued together)
     const double* mom = P.mom + ((size_t)cb * P.momRows + P.momOff[la]) * K + k;
@@ -538,8 +538,8 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
             const double gS = ll.Bji_Bij;
             const double r = (ll.rhoOff >= 0) ? __ldg(P.rhoPrd + ll.rhoOff + (size_t)col * ll.rhoColStride + k) : 1.0;
             const double gk = (ll.rhoOff >= 0) ? gS * r : gS;
-            const double ni = sd[(ll.slot * 3 + 0) * KC];
-            const double nj = sd[(ll.slot * 3 + 1) * KC];
+            const double ni = __ldg(ncol + (size_t)ll.levI * K);
+            const double nj = __ldg(ncol + (size_t)ll.levJ * K);
             lsTrans[l] = ll.trans;
             lsAtom[l] = ll.atom;
             lsI[l] = ll.i;
@@ -549,7 +549,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
             lsUgv[l] = (ll.Aji_Bji * (gS * vB)) * r;
             lsX[l] = vB * (ni - nj * gk);
             lsE[l] = nj * (ll.Aji_Bji * (gk * vB));
-            lsWla[l] = ll.wlaS * sd[(ll.slot * 3 + 2) * KC];
+            lsWla[l] = ll.wlaS * __ldg(P.wphi + ((size_t)ll.lineIdx * P.Ncol + col) * K + k);
         }
     }
 
@@ -577,12 +577,11 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
                 if (t.type == 0)
                     continue;
                 const double al = t.al;
-                const double* sds = sd + t.slot * 3 * KC;
-                const double gk = sds[2 * KC] * expfac;
+                const double gk = __ldg(gcol + t.gOff) * expfac;
                 const double Vji = gk * al;
                 const double Uji = hcl * Vji;
-                const double ni = sds[0];
-                const double nj = sds[KC];
+                const double ni = __ldg(ncol + t.nOffI);
+                const double nj = __ldg(ncol + t.nOffJ);
                 const double x = ni * al - nj * Vji;
                 Xs[t.i * nthr + tid] += x;
                 Xs[t.j * nthr + tid] -= x;
@@ -623,7 +622,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
             double v = 0.0, gv = 0.0, ugv = 0.0, Wq = W0, Aq = mJ, EBq = EB[0], wla = 0.0;
             if (t.type != 0)
             {
-                const double gk = sd[(t.slot * 3 + 2) * KC] * expfac;
+                const double gk = __ldg(gcol + t.gOff) * expfac;
                 v = t.al;
                 gv = gk * t.al;
                 ugv = hcl * gv;
@@ -698,28 +697,19 @@ __global__ void __launch_bounds__(128, LWB200_GAMMA_MINBLOCKS) gamma_kernel(cons
     const int slot0 = P.tileSlotOff[tile];
     const int nslot = P.tileSlotOff[tile + 1] - slot0;
     double* acc = smem;                                   // [nslot][4][KC]  partial sums, one writer each
-    double* slotD = smem + (size_t)P.maxSlots * 4 * KC;   // [nslot][3][KC]  staged per-depth data
-    double* Xs = slotD + (size_t)P.maxSlots * 3 * KC;     // [maxNlevel][KC]
+    double* Xs = smem + (size_t)P.maxSlots * 4 * KC;      // [maxNlevel][KC]
     double* Us = Xs + (size_t)P.maxNlevel * blockDim.x;
     if (k < K)
     {
-        // Everything the wavelength loop needs per depth that does not depend on the wavelength is
-        // read ONCE per CTA (independent loads, one memory latency): the populations of each
-        // slot's two levels and its gRatio / wphi.  Inside the loop only J and the moments come
-        // from global memory.
+        // Shared memory is private per thread here (its own depth column of every row): the
+        // kernel needs no barrier and no shared-memory atomic.  What limits it is latency, i.e.
+        // resident CTAs per SM, i.e. shared memory per CTA: only the accumulators live there.
         for (int s = 0; s < nslot; ++s)
         {
-            const DevTrans& t = P.trans[P.tileSlotTrans[slot0 + s]];
             acc[(s * 4 + 0) * KC + kk] = 0.0;
             acc[(s * 4 + 1) * KC + kk] = 0.0;
             acc[(s * 4 + 2) * KC + kk] = 0.0;
             acc[(s * 4 + 3) * KC + kk] = 0.0;
-            const double* ncol = P.n + (size_t)col * P.NlevTot * K + k;
-            slotD[(s * 3 + 0) * KC + kk] = __ldg(ncol + (size_t)t.levI * K);
-            slotD[(s * 3 + 1) * KC + kk] = __ldg(ncol + (size_t)t.levJ * K);
-            slotD[(s * 3 + 2) * KC + kk] = (t.type == 0)
-                ? __ldg(P.wphi + ((size_t)t.lineIdx * P.Ncol + col) * K + k)
-                : __ldg(P.gRatio + ((size_t)t.contIdx * P.Ncol + col) * K + k);
         }
         const double Tk = __ldg(P.temperature + (size_t)col * K + k);
         // W0 = sum_r w over both directions of every mu, in the ray order of ray_kernel
@@ -738,10 +728,10 @@ __global__ void __launch_bounds__(128, LWB200_GAMMA_MINBLOCKS) gamma_kernel(cons
                 continue;
             switch (P.laNLines[la])
             {
-            case 0: gamma_lambda<0>(P, la, col, cb, k, Tk, W0, acc + kk, slotD + kk, Xs, Us); break;
-            case 1: gamma_lambda<1>(P, la, col, cb, k, Tk, W0, acc + kk, slotD + kk, Xs, Us); break;
-            case 2: gamma_lambda<2>(P, la, col, cb, k, Tk, W0, acc + kk, slotD + kk, Xs, Us); break;
-            case 3: gamma_lambda<3>(P, la, col, cb, k, Tk, W0, acc + kk, slotD + kk, Xs, Us); break;
+            case 0: gamma_lambda<0>(P, la, col, cb, k, Tk, W0, acc + kk, Xs, Us); break;
+            case 1: gamma_lambda<1>(P, la, col, cb, k, Tk, W0, acc + kk, Xs, Us); break;
+            case 2: gamma_lambda<2>(P, la, col, cb, k, Tk, W0, acc + kk, Xs, Us); break;
+            case 3: gamma_lambda<3>(P, la, col, cb, k, Tk, W0, acc + kk, Xs, Us); break;
             default: break; // > 3 overlapping lines: handled by the general kernel
             }
         }
