@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LWB200_ABI_VERSION 1
+#define LWB200_ABI_VERSION 2
 
 /* TransitionType, Source/LwTransition.hpp:10-14 */
 enum { LWB200_LINE = 0, LWB200_CONTINUUM = 1 };
@@ -61,10 +61,13 @@ typedef struct LwB200Transition {
     double* phi;              /* [Ncol][Nlambda][Nrays][2][Nspace] lines, else NULL; may also be NULL for a
                                  line whose profile is only ever made on the device (lwb200_compute_profiles) */
     double* wphi;             /* [Ncol][Nspace] lines (NULL together with phi) */
-    const double* rhoPrd;     /* [Ncol][Nlambda][Nspace] angle-averaged PRD lines, else NULL */
+    double* rhoPrd;           /* [Ncol][Nlambda][Nspace] angle-averaged PRD lines (in; out of
+                                 lwb200_redistribute_prd), else NULL */
     const double* aDamp;      /* [Ncol][Nspace] lines; only read by *_compute_profiles */
     double* Rij;              /* [Ncol][Nspace] out */
     double* Rji;              /* [Ncol][Nspace] out */
+    const double* Qelast;     /* [Ncol][Nspace] elastic collision rate of a PRD line (Transition::Qelast,
+                                 LwTransition.hpp:51); only read by lwb200_redistribute_prd */
 } LwB200Transition;
 
 /* One atom (Source/LwAtom.hpp:42-80).  detailedStatic atoms contribute
@@ -80,6 +83,8 @@ typedef struct LwB200Atom {
     const double* nTotal;    /* [Ncol][Nspace] */
     const double* vBroad;    /* [Ncol][Nspace]; only read by *_compute_profiles */
     double* Gamma;           /* [Ncol][Nlevel][Nlevel][Nspace] in (crsw*C prefill) / out; NULL if detailedStatic */
+    const double* C;         /* [Ncol][Nlevel][Nlevel][Nspace] collisional rates (Atom::C); only read by
+                                lwb200_redistribute_prd, may be NULL otherwise */
 } LwB200Atom;
 
 /* What the hot path reads from / writes to a Context (Source/LwContext.hpp:20-45). */
@@ -127,10 +132,13 @@ enum {
     LWB200_JBAR    = 1u << 5, /* J */
     LWB200_PROFILE = 1u << 6, /* phi, wphi, rhoPrd, aDamp */
     LWB200_INTENS  = 1u << 7, /* down only: I */
-    LWB200_RATES   = 1u << 8, /* down only: Rij, Rji */
+    LWB200_RATES   = 1u << 8, /* down: Rij, Rji; up: host Rij, Rji into the device accumulator rows (only
+                                 lwb200_redistribute_prd reads rates on the device) */
     LWB200_DEPTH   = 1u << 9, /* down only: depthChi/Eta/I */
     LWB200_ADAMP   = 1u << 10, /* up only: aDamp alone (profiles are then made by lwb200_compute_profiles) */
     LWB200_GAMMA_FINAL = 1u << 11, /* up only: host Gamma taken as the finalised matrix stat_eq reads */
+    LWB200_PRD     = 1u << 12, /* up: rhoPrd, Qelast, C, aDamp (inputs of lwb200_redistribute_prd);
+                                  down: rhoPrd */
     LWB200_ALL_INPUTS  = 0x7fu,
     LWB200_ITER_INPUTS = LWB200_POPS | LWB200_NSTAR | LWB200_GAMMA,
     LWB200_ITER_OUTPUTS = LWB200_GAMMA | LWB200_JBAR | LWB200_INTENS | LWB200_RATES
@@ -218,6 +226,24 @@ int lwb200_formal_sol(LwB200Context* ctx, int upOnly);
  * receives the number of (column, depth) systems with an all-zero row; the
  * call then fails like the reference's throw ("Singular Matrix"). */
 int lwb200_stat_eq(LwB200Context* ctx, int32_t atom, int32_t kStart, int32_t kEnd, int32_t* nSingular);
+
+/* Replaces redistribute_prd_lines (Source/Prd.cpp:648-658, PrdTemplates.hpp:164-351;
+ * FsIterationFns::redistribute_prd, LwFormalInterface.hpp:118) for angle-averaged PRD lines:
+ * up to maxIter sub-iterations of
+ *   (1) per PRD line and depth the scattering integral of J against Gouttebroze's GII on the
+ *       fixed-step fine grid, rho = 1 + gamma (scatInt / gNorm - Jbar)   (Prd.cpp:9-124, :468-575),
+ *   (2) a formal solution over the wavelengths touched by a PRD line that updates J, I and the
+ *       rates of the PRD lines only (formal_sol_prd_update_rates, PrdTemplates.hpp:18-155),
+ * until the largest relative change of rho falls below tol.  Works on the device-resident state
+ * (populations, J, rates of the last lwb200_fs_iter); inputs that only this call reads are
+ * uploaded with LWB200_PRD.  includeDetailed: also redistribute the PRD lines of detailed-static
+ * atoms (extraParams["include_detailed_atoms"]).
+ * Outputs (any may be NULL): *nIter sub-iterations taken; dRho / dRhoIdx [maxIter * NprdLines]
+ * in (iteration, line) order; dJPrdMax / dJPrdMaxIdx [maxIter].  Hybrid PRD (hPrdCoeffs, JRest)
+ * is not handled here: the plugin shim leaves such Contexts to the reference's own function. */
+int lwb200_redistribute_prd(LwB200Context* ctx, int32_t maxIter, double tol, int32_t includeDetailed,
+                            int32_t* nIter, double* dRho, int32_t* dRhoIdx, double* dJPrdMax,
+                            int64_t* dJPrdMaxIdx);
 
 /* Device time (ms, CUDA events on the context's stream) of the most recent
  * formal-solution kernel launched by lwb200_fs_iter / lwb200_formal_sol: the

@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 LINE, CONTINUUM = 0, 1
 BC_UNINITIALISED, BC_ZERO, BC_THERMALISED, BC_PERIODIC, BC_CALLABLE = range(5)
@@ -19,7 +19,7 @@ FS_NAMES = {'piecewise_linear_1d': FS_LINEAR, 'piecewise_besser_1d': FS_BESSER,
             'piecewise_bezier3_1d': FS_BEZIER3}
 
 (ATMOS, BACKGR, POPS, NSTAR, GAMMA, JBAR, PROFILE, INTENS, RATES, DEPTH, ADAMP,
- GAMMA_FINAL) = (1 << i for i in range(12))
+ GAMMA_FINAL, PRD) = (1 << i for i in range(13))
 ALL_INPUTS = 0x7f
 ITER_INPUTS = POPS | NSTAR | GAMMA
 ITER_OUTPUTS = GAMMA | JBAR | INTENS | RATES
@@ -39,7 +39,7 @@ class LwB200Transition(C.Structure):
         ('Aji', C.c_double), ('Bji', C.c_double), ('Bij', C.c_double),
         ('lambda0', C.c_double), ('dopplerWidth', C.c_double),
         ('wavelength', _dp), ('alpha', _dp), ('phi', _dp), ('wphi', _dp),
-        ('rhoPrd', _dp), ('aDamp', _dp), ('Rij', _dp), ('Rji', _dp),
+        ('rhoPrd', _dp), ('aDamp', _dp), ('Rij', _dp), ('Rji', _dp), ('Qelast', _dp),
     ]
 
 
@@ -48,7 +48,7 @@ class LwB200Atom(C.Structure):
         ('Nlevel', C.c_int32), ('Ntrans', C.c_int32),
         ('detailedStatic', C.c_int32), ('reserved', C.c_int32),
         ('trans', C.POINTER(LwB200Transition)),
-        ('n', _dp), ('nStar', _dp), ('nTotal', _dp), ('vBroad', _dp), ('Gamma', _dp),
+        ('n', _dp), ('nStar', _dp), ('nTotal', _dp), ('vBroad', _dp), ('Gamma', _dp), ('C', _dp),
     ]
 
 
@@ -126,13 +126,15 @@ def load():
     lib.lwb200_dj_max.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.lwb200_formal_sol.argtypes = [vp, C.c_int]
     lib.lwb200_stat_eq.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    lib.lwb200_redistribute_prd.argtypes = [vp, C.c_int32, C.c_double, C.c_int32, C.POINTER(C.c_int32), _dp,
+                                            _ip, _dp, C.POINTER(C.c_int64)]
     lib.lwb200_kernel_time.argtypes = [vp, C.POINTER(C.c_double)]
     lib.lwb200_device_buffer.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.lwb200_work_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.POINTER(C.c_int64)]
     for name in ('device_count', 'create', 'destroy', 'set_stream', 'set_lambda_range', 'upload',
                  'download', 'sync', 'compute_profiles', 'fs_iter', 'finalise', 'dj_max',
-                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time'):
+                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd'):
         getattr(lib, 'lwb200_' + name).restype = C.c_int
     if lib.lwb200_abi_version() != ABI_VERSION:
         raise LwB200Error('liblwb200.so ABI version mismatch; rebuild')
@@ -151,5 +153,5 @@ EXPORTED_SYMBOLS = [
     'lwb200_destroy', 'lwb200_set_stream', 'lwb200_set_lambda_range', 'lwb200_upload',
     'lwb200_download', 'lwb200_sync', 'lwb200_compute_profiles', 'lwb200_fs_iter',
     'lwb200_finalise', 'lwb200_dj_max', 'lwb200_formal_sol', 'lwb200_stat_eq',
-    'lwb200_device_buffer', 'lwb200_work_stats', 'lwb200_kernel_time',
+    'lwb200_device_buffer', 'lwb200_work_stats', 'lwb200_kernel_time', 'lwb200_redistribute_prd',
 ]

@@ -35,6 +35,13 @@ class IterationUpdate:
     dPops: List[float] = field(default_factory=list)
     dPopsMaxIdx: List[int] = field(default_factory=list)
     crsw: float = 1.0
+    updatedRho: bool = False
+    NprdSubIter: int = 0
+    dRho: List[float] = field(default_factory=list)
+    dRhoMaxIdx: List[int] = field(default_factory=list)
+    updatedJPrd: bool = False
+    dJPrdMax: List[float] = field(default_factory=list)
+    dJPrdMaxIdx: List[int] = field(default_factory=list)
 
 
 class Context:
@@ -171,6 +178,35 @@ class Context:
         capi.check(self.lib.lwb200_formal_sol(self._h, int(upOnly)))
         self.download(capi.INTENS)
         return IterationUpdate()
+
+    def prd_redistribute(self, maxIter=3, tol=1e-2, extraParams=None):
+        """lw.Context.prd_redistribute (LwMiddleLayer.pyx:3647-3684): update the emission-profile
+        ratio rho of every angle-averaged PRD line from the current J, populations and rates, then
+        J, I and the PRD lines' rates from the new rho; up to maxIter sub-iterations."""
+        include = bool(extraParams and extraParams.get('include_detailed_atoms', False))
+        lines = [t for a in self.problem.atoms for t in a.trans
+                 if t.rhoPrd is not None and (include or not a.detailedStatic)]
+        upd = IterationUpdate()
+        if not lines:
+            return upd
+        self.upload(capi.PRD | capi.POPS | capi.RATES | capi.JBAR)
+        n = C.c_int32(0)
+        dRho = np.zeros(maxIter * len(lines))
+        dRhoIdx = np.zeros(maxIter * len(lines), dtype=np.int32)
+        dJ = np.zeros(maxIter)
+        dJIdx = np.zeros(maxIter, dtype=np.int64)
+        capi.check(self.lib.lwb200_redistribute_prd(
+            self._h, maxIter, tol, int(include), C.byref(n), capi.dptr(dRho), capi.iptr(dRhoIdx),
+            capi.dptr(dJ), dJIdx.ctypes.data_as(C.POINTER(C.c_int64))))
+        self.download(capi.PRD | capi.JBAR | capi.INTENS | capi.RATES)
+        k = n.value
+        upd.updatedRho = upd.updatedJPrd = True
+        upd.NprdSubIter = k
+        upd.dRho = list(dRho[:k * len(lines)])
+        upd.dRhoMaxIdx = list(dRhoIdx[:k * len(lines)])
+        upd.dJPrdMax = list(dJ[:k])
+        upd.dJPrdMaxIdx = list(dJIdx[:k])
+        return upd
 
     def stat_equil(self, extraParams=None):
         """lw.Context.stat_equil: per-depth statistical equilibrium from the

@@ -5,6 +5,7 @@
 #include "lwb200_kernels.cuh"
 #include "lwb200_profiles.cuh"
 #include "lwb200_pipeline.cuh"
+#include "lwb200_prd.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -108,8 +109,22 @@ struct Pending
     size_t bytes;
 };
 
+// What one pass of the pipeline covers: every wavelength of the context's range (the Gamma
+// iteration) or the wavelengths touched by the redistributed PRD lines (rates-only pass).
+struct PipelineLists
+{
+    const int* moment;
+    int nMoment;
+    const int* kindLam[4];
+    int nKindLam[4];
+    const unsigned char* laMask;
+    int prdOnly;
+};
+
 struct LwB200Context
 {
+    bool prdPass = false;
+    PipelineLists prdPl{};
     Pinned stN, stNStar, stNTotal, stVBroad, stPrefill, stGamma, stNOut, stGammaOut, stRates;
     std::vector<Pending> pending;
     std::vector<void*> registered;
@@ -138,6 +153,17 @@ struct LwB200Context
     DevBuf<double> chiC, etaC, mom;
     int nKindLam[4] = {0, 0, 0, 0}, nListMoment = 0, nListDirect = 0, nListAll = 0, listLo = -1, listHi = -1;
     int batchCols = 1, momRows = 0;
+    // angle-averaged PRD (lwb200_redistribute_prd): lines with rhoPrd, active atoms first
+    std::vector<DevPrdLine> prdLines;
+    std::vector<int> prdLineDetailed;
+    DevBuf<DevPrdLine> dPrdLines;
+    DevBuf<double> qelast, cmat, rhoPrev, prdMax;
+    DevBuf<int> prdIdx, dKindLamPrd[4], dListMomentPrd;
+    DevBuf<unsigned char> dPrdMask;
+    std::vector<long long> atomCOff;
+    long long cTot = 0;
+    int nKindLamPrd[4] = {0, 0, 0, 0}, nListMomentPrd = 0, prdListsFor = -1;
+    bool prdUploaded = false;
     size_t smemGamma = 0;
     int KC = 0;
     int Ntile = 0;
@@ -368,6 +394,7 @@ int build_plan(LwB200Context* c)
                     en.Nlevel = c->atoms[d.atom].Nlevel;
                     en.detailed = d.detailed;
                     en.atom = d.atom;
+                    en.prd = d.rhoOff >= 0 ? 1 : 0;
                     en.nOffI = d.levI * K;
                     en.nOffJ = d.levJ * K;
                     en.gOff = d.type == 0 ? 0 : (int)((long long)d.contIdx * p.Ncol * K);
@@ -468,6 +495,43 @@ int build_plan(LwB200Context* c)
         }
     }
     c->momRows = std::max(momRows, 1);
+
+    // PRD lines (PrdTemplates.hpp:186-211: active atoms first, then detailed ones) and the packed
+    // layouts of the inputs only lwb200_redistribute_prd reads
+    c->atomCOff.assign(p.Natom, -1);
+    for (int a = 0; a < p.Natom; ++a)
+        if (c->atoms[a].C)
+        {
+            c->atomCOff[a] = c->cTot;
+            c->cTot += (long long)c->atoms[a].Nlevel * c->atoms[a].Nlevel * K;
+        }
+    for (int pass = 0; pass < 2; ++pass)
+        for (int g = 0; g < NT; ++g)
+        {
+            const DevTrans& d = c->devTrans[g];
+            if (d.type != 0 || d.rhoOff < 0 || (d.detailed != 0) != (pass == 1))
+                continue;
+            DevPrdLine ln{};
+            ln.trans = g;
+            ln.atom = d.atom;
+            ln.j = d.j;
+            ln.levI = d.levI;
+            ln.levJ = d.levJ;
+            ln.Nblue = d.Nblue;
+            ln.Nl = d.Nred - d.Nblue;
+            ln.tabOff = d.tabOff;
+            ln.lineIdx = d.lineIdx;
+            ln.Nlevel = c->atoms[d.atom].Nlevel;
+            ln.transBeg = g - c->trans[g].kr;
+            ln.transEnd = ln.transBeg + c->atoms[d.atom].Ntrans;
+            ln.qelRow = (int)c->prdLines.size();
+            ln.cOff = c->atomCOff[d.atom];
+            ln.rhoOff = d.rhoOff;
+            ln.Bij = d.Bij;
+            ln.lambda0 = d.lambda0;
+            c->prdLines.push_back(ln);
+            c->prdLineDetailed.push_back(d.detailed);
+        }
     {
         // columns per pipeline batch: chiC + etaC + moments of one batch stay under ~3 GB
         const size_t perCol = ((size_t)2 * L + c->momRows) * K * sizeof(double);
@@ -495,6 +559,14 @@ int build_plan(LwB200Context* c)
     }
     if (p.vlosMu && c->vlosMu.alloc(ncol * M * K))
         return 1;
+    if (!c->prdLines.empty())
+    {
+        const size_t np = c->prdLines.size();
+        if (c->qelast.alloc(np * ncol * K) || c->cmat.alloc((size_t)std::max<long long>(c->cTot, 1) * ncol)
+            || c->rhoPrev.alloc(c->rhoPrd.n) || c->prdMax.alloc(np) || c->prdIdx.alloc(np)
+            || c->dPrdLines.upload(c->prdLines))
+            return 1;
+    }
     CU(cudaMemset(c->J.p, 0, c->J.n * sizeof(double)));
     CU(cudaMemset(c->I.p, 0, c->I.n * sizeof(double)));
     CU(cudaMemset(c->accum.p, 0, c->accum.n * sizeof(double)));
@@ -686,8 +758,23 @@ int ensure_side_streams(LwB200Context* c)
 // prioritised side streams forked from / joined to the caller's stream, so that they share one
 // tail (a 1D atmosphere is only a few waves of warps in total).  fsMode != 0: formal solution
 // only (no J, no moments, no Gamma stage).
+PipelineLists full_lists(LwB200Context* c)
+{
+    PipelineLists pl{};
+    pl.moment = c->dListMoment.p;
+    pl.nMoment = c->nListMoment;
+    for (int q = 0; q < 4; ++q)
+    {
+        pl.kindLam[q] = c->dKindLam[q].p;
+        pl.nKindLam[q] = c->nKindLam[q];
+    }
+    pl.laMask = nullptr;
+    pl.prdOnly = 0;
+    return pl;
+}
+
 template <int NCH, int SOLVER, bool MULTI>
-int launch_pipeline(LwB200Context* c, int lambdaIterate, int storeDepth, int fsMode)
+int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate, int storeDepth, int fsMode)
 {
     if (ensure_side_streams(c))
         return 1;
@@ -698,20 +785,20 @@ int launch_pipeline(LwB200Context* c, int lambdaIterate, int storeDepth, int fsM
     for (int colBase = 0; colBase < Ncol; colBase += c->batchCols)
     {
         const int nb = std::min(c->batchCols, Ncol - colBase);
-        if (c->nListMoment > 0)
+        if (pl.nMoment > 0)
         {
-            continuum_kernel<<<dim3(c->nListMoment, nb), KP, 0, c->stream>>>(c->P, c->dListMoment.p, c->laLo,
-                                                                            c->laHi, colBase);
+            continuum_kernel<<<dim3(pl.nMoment, nb), KP, 0, c->stream>>>(c->P, pl.moment, c->laLo, c->laHi,
+                                                                        colBase, pl.laMask);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }
         int nkinds = 0;
         for (int q = 0; q < 4; ++q)
-            nkinds += c->nKindLam[q] > 0 ? 1 : 0;
+            nkinds += pl.nKindLam[q] > 0 ? 1 : 0;
         int nside = 0, launched = 0;
         for (int q = 3; q >= 0; --q)
         {
-            const int nLam = c->nKindLam[q];
+            const int nLam = pl.nKindLam[q];
             if (nLam == 0)
                 continue;
             // the last kind runs on the caller's stream itself
@@ -727,7 +814,7 @@ int launch_pipeline(LwB200Context* c, int lambdaIterate, int storeDepth, int fsM
             const int perWarp = MULTI ? 1 : (int)std::max<long long>(1, std::min<long long>(4, warps / (148LL * 8 * 8)));
             const int nw = c->nwarps;
             dim3 grid(MULTI ? nLam : (nLam + nw * perWarp - 1) / (nw * perWarp), nb);
-            const int* list = c->dKindLam[q].p;
+            const int* list = pl.kindLam[q];
             switch (q)
             {
             case 0:
@@ -753,7 +840,7 @@ int launch_pipeline(LwB200Context* c, int lambdaIterate, int storeDepth, int fsM
         }
         if (fsMode != 0)
             continue;
-        if (c->fetchEarly && c->nListDirect == 0 && colBase + nb >= Ncol)
+        if (c->fetchEarly && !pl.prdOnly && c->nListDirect == 0 && colBase + nb >= Ncol)
         {
             // J and I are final: send them home on the copy stream while Gamma is accumulated
             const LwB200Problem& p = c->prob;
@@ -765,11 +852,11 @@ int launch_pipeline(LwB200Context* c, int lambdaIterate, int storeDepth, int fsM
             CU(cudaEventRecord(c->evCopy, c->copyStream));
             c->fetched = true;
         }
-        if (c->nListMoment > 0)
+        if (pl.nMoment > 0)
         {
             const int KC = c->KC;
-            gamma_kernel<<<dim3(c->nListMoment, nb, (K + KC - 1) / KC), KC, c->smemGamma, c->stream>>>(
-                c->P, c->dListMoment.p, c->laLo, c->laHi, colBase);
+            gamma_kernel<<<dim3(pl.nMoment, nb, (K + KC - 1) / KC), KC, c->smemGamma, c->stream>>>(
+                c->P, pl.moment, c->laLo, c->laHi, colBase, pl.laMask, pl.prdOnly);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }
@@ -790,9 +877,9 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
     if (MODE == MODE_ITER && !c->forceDirect)
     {
         // wavelengths with more than three overlapping lines go through the general kernel
-        if (launch_pipeline<NCH, SOLVER, false>(c, lambdaIterate, storeDepth, 0))
+        if (launch_pipeline<NCH, SOLVER, false>(c, c->prdPass ? c->prdPl : full_lists(c), lambdaIterate, storeDepth, 0))
             return 1;
-        if (c->nListDirect > 0)
+        if (c->nListDirect > 0 && !c->prdPass)
         {
             auto kern = fs_kernel<NCH, SOLVER, MODE_ITER>;
             if (set_smem_attr(kern, c->device))
@@ -833,7 +920,7 @@ int launch_fs_long(LwB200Context* c, int lambdaIterate, int upOnly, int storeDep
         return fail("the general per-ray kernel is limited to Nspace <= 128");
     CU(cudaEventRecord(c->evK0, c->stream));
     const int fsMode = MODE == MODE_ITER ? 0 : (upOnly ? 3 : 1);
-    if (launch_pipeline<4, SOLVER, true>(c, lambdaIterate, storeDepth, fsMode))
+    if (launch_pipeline<4, SOLVER, true>(c, c->prdPass ? c->prdPl : full_lists(c), lambdaIterate, storeDepth, fsMode))
         return 1;
     CU(cudaEventRecord(c->evK1, c->stream));
     c->kernelTimed = true;
@@ -1018,6 +1105,16 @@ int lwb200_destroy(LwB200Context* c)
     for (int q = 0; q < 4; ++q)
         c->dKindLam[q].release();
     c->dListMoment.release();
+    c->dListMomentPrd.release();
+    c->dPrdMask.release();
+    c->dPrdLines.release();
+    c->qelast.release();
+    c->cmat.release();
+    c->rhoPrev.release();
+    c->prdMax.release();
+    c->prdIdx.release();
+    for (int q = 0; q < 4; ++q)
+        c->dKindLamPrd[q].release();
     c->dMomOff.release();
     c->dLaNLines.release();
     c->dLamLine.release();
@@ -1221,6 +1318,43 @@ int lwb200_upload(LwB200Context* c, uint32_t mask)
         if (check_phi_symmetry(c))
             return 1;
     }
+    if (mask & LWB200_RATES)
+    {
+        // host Rij / Rji -> the rate rows of the accumulator (only lwb200_redistribute_prd reads
+        // rates on the device; a caller that changed them on the host sends them back with this)
+        for (size_t g = 0; g < c->trans.size(); ++g)
+        {
+            const DevTrans& d = c->devTrans[g];
+            const LwB200Transition& t = c->trans[g].t;
+            if (copy2d(c->accum.p + (size_t)d.accRij * K, (size_t)c->P.AccTot * K * D, t.Rij, K * D, K * D, ncol, H2D, s)
+                || copy2d(c->accum.p + (size_t)d.accRji * K, (size_t)c->P.AccTot * K * D, t.Rji, K * D, K * D, ncol, H2D, s))
+                return 1;
+        }
+    }
+    if ((mask & LWB200_PRD) && !c->prdLines.empty())
+    {
+        for (size_t q = 0; q < c->prdLines.size(); ++q)
+        {
+            const DevPrdLine& ln = c->prdLines[q];
+            const DevTrans& d = c->devTrans[ln.trans];
+            const LwB200Transition& t = c->trans[ln.trans].t;
+            if (!t.Qelast || !t.aDamp || !t.rhoPrd)
+                return fail("LWB200_PRD upload: PRD line without Qelast / aDamp / rhoPrd");
+            CU(cudaMemcpyAsync(c->qelast.p + q * ncol * K, t.Qelast, ncol * K * D, H2D, s));
+            CU(cudaMemcpyAsync(c->aDamp.p + (size_t)d.lineIdx * ncol * K, t.aDamp, ncol * K * D, H2D, s));
+            CU(cudaMemcpyAsync(c->rhoPrd.p + d.rhoOff, t.rhoPrd, ncol * (size_t)ln.Nl * K * D, H2D, s));
+        }
+        for (int a = 0; a < p.Natom; ++a)
+        {
+            if (c->atomCOff[a] < 0)
+                continue;
+            const size_t n2k = (size_t)c->atoms[a].Nlevel * c->atoms[a].Nlevel * K;
+            if (copy2d(c->cmat.p + c->atomCOff[a], (size_t)c->cTot * D, c->atoms[a].C, n2k * D, n2k * D, ncol,
+                       H2D, s))
+                return 1;
+        }
+        c->prdUploaded = true;
+    }
     return 0;
 }
 
@@ -1239,6 +1373,12 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
         c->fetched = false;
         mask &= ~(uint32_t)(LWB200_JBAR | LWB200_INTENS);
     }
+    if (mask & LWB200_PRD)
+        for (const DevPrdLine& ln : c->prdLines)
+        {
+            const LwB200Transition& t = c->trans[ln.trans].t;
+            CU(cudaMemcpyAsync(t.rhoPrd, c->rhoPrd.p + ln.rhoOff, ncol * (size_t)ln.Nl * K * D, D2H, s));
+        }
     if (mask & LWB200_JBAR)
         CU(cudaMemcpyAsync(p.J, c->J.p, ncol * L * K * D, D2H, s));
     if (mask & LWB200_INTENS)
@@ -1450,6 +1590,145 @@ int lwb200_stat_eq(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd,
         return fail("Singular Matrix");
     return 0;
 }
+
+// redistribute_prd_lines_template (PrdTemplates.hpp:164-291) on the device-resident state.
+int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32_t includeDetailed,
+                            int32_t* nIterOut, double* dRho, int32_t* dRhoIdx, double* dJPrdMax,
+                            int64_t* dJPrdMaxIdx)
+{
+    CU(cudaSetDevice(c->device));
+    if (nIterOut)
+        *nIterOut = 0;
+    // the lines taking part: active atoms' always, detailed ones on request
+    int nLines = 0;
+    for (size_t q = 0; q < c->prdLines.size(); ++q)
+        if (!c->prdLineDetailed[q] || includeDetailed)
+            nLines = (int)q + 1; // (active lines come first, so this is a prefix)
+    if (nLines == 0)
+        return 0;
+    if (!c->nstarUploaded || !c->prdUploaded)
+        return fail("lwb200_redistribute_prd: inputs have not been uploaded (lwb200_upload with LWB200_PRD)");
+    for (int q = 0; q < nLines; ++q)
+        if (c->prdLines[q].cOff < 0)
+            return fail("lwb200_redistribute_prd: atom of a PRD line without collisional rates C");
+    if (c->laLo != 0 || c->laHi != c->prob.Nspect)
+        return fail("lwb200_redistribute_prd: not available on a wavelength shard");
+    if (refresh_tile_lists(c))
+        return 1;
+    const LwB200Problem& p = c->prob;
+    const int K = p.Nspace, L = p.Nspect;
+    cudaStream_t s = c->stream;
+    c->forceDirect = false;
+    c->fetchEarly = false;
+
+    // wavelengths touched by a redistributed line (:225-240) and the work lists over them
+    if (c->prdListsFor != nLines)
+    {
+        std::vector<unsigned char> mask(L, 0);
+        for (int q = 0; q < nLines; ++q)
+            for (int la = c->prdLines[q].Nblue; la < c->prdLines[q].Nblue + c->prdLines[q].Nl; ++la)
+                mask[la] = 1;
+        std::vector<int> kindLam[4], tiles;
+        for (int la = 0; la < L; ++la)
+            if (mask[la])
+            {
+                if (c->laKind[la] >= 4)
+                    return fail("lwb200_redistribute_prd: a PRD line overlaps more than two other lines");
+                kindLam[c->laKind[la]].push_back(la);
+            }
+        for (int t = 0; t < c->Ntile; ++t)
+        {
+            bool any = false;
+            for (int q = c->tileLa[t]; q < c->tileLa[t + 1]; ++q)
+                any = any || mask[c->tileLambda[q]];
+            if (any && c->tileKind[t] < 4)
+                tiles.push_back(t);
+        }
+        c->dPrdMask.release();
+        c->dListMomentPrd.release();
+        if (c->dPrdMask.upload(mask) || c->dListMomentPrd.upload(tiles))
+            return 1;
+        c->nListMomentPrd = (int)tiles.size();
+        for (int q = 0; q < 4; ++q)
+        {
+            c->dKindLamPrd[q].release();
+            if (c->dKindLamPrd[q].upload(kindLam[q]))
+                return 1;
+            c->nKindLamPrd[q] = (int)kindLam[q].size();
+        }
+        c->prdListsFor = nLines;
+    }
+    PipelineLists pl{};
+    pl.moment = c->dListMomentPrd.p;
+    pl.nMoment = c->nListMomentPrd;
+    for (int q = 0; q < 4; ++q)
+    {
+        pl.kindLam[q] = c->dKindLamPrd[q].p;
+        pl.nKindLam[q] = c->nKindLamPrd[q];
+    }
+    pl.laMask = c->dPrdMask.p;
+    pl.prdOnly = 1;
+
+    // Ng(0, 0, 0, rho): the change of the first redistribution is measured against the rho we start from
+    CU(cudaMemcpyAsync(c->rhoPrev.p, c->rhoPrd.p, c->rhoPrd.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    int maxNl = 1;
+    for (int q = 0; q < nLines; ++q)
+        maxNl = std::max(maxNl, c->prdLines[q].Nl);
+    std::vector<double> hMax(nLines);
+    std::vector<int> hIdx(nLines);
+    int iter = 0;
+    c->lastLaunches = 0;
+    while (iter < maxIter)
+    {
+        ++iter;
+        prd_scatter_kernel<<<dim3((maxNl * K + 127) / 128, p.Ncol, nLines), 128, 0, s>>>(
+            c->P, c->dPrdLines.p, c->transWave.p, c->qelast.p, c->cmat.p, c->cTot, c->vBroad.p, c->aDamp.p,
+            c->rhoPrd.p);
+        CU(cudaGetLastError());
+        prd_change_kernel<<<nLines, 256, 0, s>>>(c->dPrdLines.p, p.Ncol, K, c->rhoPrd.p, c->rhoPrev.p,
+                                                 c->prdMax.p, c->prdIdx.p);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(hMax.data(), c->prdMax.p, nLines * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(hIdx.data(), c->prdIdx.p, nLines * sizeof(int), cudaMemcpyDeviceToHost, s));
+        // formal_sol_prd_update_rates (PrdTemplates.hpp:18-76)
+        prd_zero_rates_kernel<<<grid_for((size_t)nLines * p.Ncol * K), 256, 0, s>>>(c->P, c->dPrdLines.p, nLines);
+        CU(cudaGetLastError());
+        c->lastLaunches += 3;
+        c->prdPass = true;
+        c->prdPl = pl;
+        const int rc = launch_fs<MODE_ITER>(c, 0, 0, 0);
+        c->prdPass = false;
+        if (rc)
+            return 1;
+        dj_reduce_kernel<<<1, 256, 0, s>>>(c->dJ.p, p.Ncol, L, 0, L, c->djOut.p, c->djIdx.p, c->dPrdMask.p);
+        CU(cudaGetLastError());
+        c->lastLaunches += 1;
+        double m = 0.0;
+        long long idx = 0;
+        CU(cudaMemcpyAsync(&m, c->djOut.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(&idx, c->djIdx.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        double dRhoMax = 0.0;
+        for (int q = 0; q < nLines; ++q)
+        {
+            dRhoMax = std::max(dRhoMax, hMax[q]);
+            if (dRho)
+                dRho[(size_t)(iter - 1) * nLines + q] = hMax[q];
+            if (dRhoIdx)
+                dRhoIdx[(size_t)(iter - 1) * nLines + q] = hIdx[q];
+        }
+        if (dJPrdMax)
+            dJPrdMax[iter - 1] = m;
+        if (dJPrdMaxIdx)
+            dJPrdMaxIdx[iter - 1] = idx % L;
+        if (dRhoMax < tol)
+            break;
+    }
+    if (nIterOut)
+        *nIterOut = iter;
+    return 0;
+}
+
 
 int lwb200_kernel_time(LwB200Context* c, double* ms)
 {

@@ -60,7 +60,7 @@ struct DevEntry
     double wlaF;       // continuum: wlambda / lambda * 4 pi / h;  line: wlambda * 4 pi / (h c)
     int nOffI, nOffJ;  // levI * K, levJ * K: element offsets into one column of n
     int gOff;          // contIdx * Ncol * K: element offset of the continuum's gRatio block
-    int pad;
+    int prd;           // line with rhoPrd (angle-averaged PRD)
 };
 
 // Per (wavelength, overlapping-line slot) descriptor built by the planner (<= 3 slots).
@@ -734,7 +734,7 @@ __global__ void stat_eq_kernel(const DevProblem P, int atomSel, int kStart, int 
 // (max, first index) over dJ[Ncol][L] restricted to [laLo, laHi): what the
 // reference's threaded branch returns (:688, :700-703).  Single block.
 __global__ void dj_reduce_kernel(const double* __restrict__ dJ, int Ncol, int L, int laLo, int laHi,
-                                 double* outMax, long long* outIdx)
+                                 double* outMax, long long* outIdx, const unsigned char* __restrict__ laMask = nullptr)
 {
     __shared__ double sMax[256];
     __shared__ long long sIdx[256];
@@ -746,6 +746,8 @@ __global__ void dj_reduce_kernel(const double* __restrict__ dJ, int Ncol, int L,
     {
         const long long col = q / span;
         const long long la = laLo + q % span;
+        if (laMask && !laMask[la])
+            continue;
         const double v = dJ[col * L + la];
         if (best < v)
         {

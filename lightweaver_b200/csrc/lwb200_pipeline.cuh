@@ -61,7 +61,7 @@ __global__ void phi_symmetry_kernel(const double* __restrict__ phi, size_t nPair
 // ---------------------------------------------------------------------------
 // Stage 1: chiC, etaC.  Grid (tiles, columns of the batch), one thread per depth.
 __global__ void continuum_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi,
-                                 int colBase)
+                                 int colBase, const unsigned char* __restrict__ laMask)
 {
     const int K = P.K, L = P.L;
     const int tile = tileList[blockIdx.x];
@@ -76,7 +76,7 @@ __global__ void continuum_kernel(const DevProblem P, const int* __restrict__ til
     for (int tl = tlBeg; tl < tlEnd; ++tl)
     {
         const int la = P.tileLambda[tl];
-        if (la < laLo || la >= laHi)
+        if (la < laLo || la >= laHi || (laMask && !laMask[la]))
             continue;
         const double lambda = __ldg(P.wavelength + la);
         const double rlambda = 1.0 / lambda;
@@ -482,7 +482,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
 template <int NL>
 __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int col, int cb, int k, double Tk,
                                              double W0, double* __restrict__ acc, double* __restrict__ Xs,
-                                             double* __restrict__ Us)
+                                             double* __restrict__ Us, const bool prdOnly)
 {
     constexpr int NLA = NL > 0 ? NL : 1;
     constexpr int NQ = NL + 1;
@@ -563,7 +563,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
         const int N = first.Nlevel;
         const int atom = first.atom;
         double E0 = 0.0;
-        if (!detailed)
+        if (!detailed && !prdOnly)
         {
             // continuum aggregates per level: chi_atom / U_atom of chi_eta_aux_accum (:59-109)
             for (int m = 0; m < N; ++m)
@@ -619,6 +619,8 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
         for (int e = e0; e < e1; ++e)
         {
             const DevEntry& t = P.entries[e];
+            if (prdOnly && !t.prd)
+                continue; // formal_sol_prd_update_rates: rates of the PRD lines only (:433-434)
             double v = 0.0, gv = 0.0, ugv = 0.0, Wq = W0, Aq = mJ, EBq = EB[0], wla = 0.0;
             if (t.type != 0)
             {
@@ -643,7 +645,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
                 }
             }
             double* a4 = acc + t.slot * 4 * KC;
-            if (!detailed)
+            if (!detailed && !prdOnly)
             {
                 // chi_atom(m) = sum_q p_q X_q(m), U_atom(m) = sum_q p_q U_q(m)
                 double Xi[NQ], Xj[NQ], Ui[NQ], Uj[NQ];
@@ -685,8 +687,10 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
     }
 }
 
-__global__ void __launch_bounds__(128, LWB200_GAMMA_MINBLOCKS) gamma_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi,
-                             int colBase)
+// laMask / prdOnly: the rates-only pass of the PRD sub-iterations over the masked wavelengths.
+__global__ void __launch_bounds__(128, LWB200_GAMMA_MINBLOCKS)
+gamma_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi, int colBase,
+             const unsigned char* __restrict__ laMask, int prdOnly)
 {
     extern __shared__ double smem[];
     // depth chunk of this CTA: blockDim.x consecutive depths (one chunk covers Nspace <= 128)
@@ -724,14 +728,14 @@ __global__ void __launch_bounds__(128, LWB200_GAMMA_MINBLOCKS) gamma_kernel(cons
         for (int tl = tlBeg; tl < tlEnd; ++tl)
         {
             const int la = P.tileLambda[tl];
-            if (la < laLo || la >= laHi)
+            if (la < laLo || la >= laHi || (laMask && !laMask[la]))
                 continue;
             switch (P.laNLines[la])
             {
-            case 0: gamma_lambda<0>(P, la, col, cb, k, Tk, W0, acc + kk, Xs, Us); break;
-            case 1: gamma_lambda<1>(P, la, col, cb, k, Tk, W0, acc + kk, Xs, Us); break;
-            case 2: gamma_lambda<2>(P, la, col, cb, k, Tk, W0, acc + kk, Xs, Us); break;
-            case 3: gamma_lambda<3>(P, la, col, cb, k, Tk, W0, acc + kk, Xs, Us); break;
+            case 0: gamma_lambda<0>(P, la, col, cb, k, Tk, W0, acc + kk, Xs, Us, prdOnly != 0); break;
+            case 1: gamma_lambda<1>(P, la, col, cb, k, Tk, W0, acc + kk, Xs, Us, prdOnly != 0); break;
+            case 2: gamma_lambda<2>(P, la, col, cb, k, Tk, W0, acc + kk, Xs, Us, prdOnly != 0); break;
+            case 3: gamma_lambda<3>(P, la, col, cb, k, Tk, W0, acc + kk, Xs, Us, prdOnly != 0); break;
             default: break; // > 3 overlapping lines: handled by the general kernel
             }
         }

@@ -188,6 +188,7 @@ void build_mirror(Context& ctx, Mirror& m)
             fa.nTotal = a->nTotal.data;
             fa.vBroad = a->vBroad.data;
             fa.Gamma = detailed ? nullptr : a->Gamma.data;
+            fa.C = a->C ? a->C.data : nullptr;
             m.trans.emplace_back();
             auto& tv = m.trans.back();
             for (Transition* t : a->trans)
@@ -213,6 +214,7 @@ void build_mirror(Context& ctx, Mirror& m)
                 ft.aDamp = t->aDamp.data;
                 ft.Rij = t->Rij.data;
                 ft.Rji = t->Rji.data;
+                ft.Qelast = t->Qelast ? t->Qelast.data : nullptr;
                 tv.push_back(ft);
             }
             fa.trans = tv.data();
@@ -331,6 +333,55 @@ IterationResult b200_fs_iter(Context& ctx, bool lambdaIterate, ExtraParams param
     return result;
 }
 
+// FsIterationFns::redistribute_prd (LwFormalInterface.hpp:118; called from
+// redistribute_prd_lines, Prd.cpp:648-653): angle-averaged PRD on the device.  The rates of
+// the last fs_iter are taken from the host (they may have been touched since).
+IterationResult b200_redistribute_prd(Context& ctx, int maxIter, f64 tol, ExtraParams params)
+{
+    Mirror& m = mirror_for(ctx);
+    bool includeDetailed = false;
+    if (params.contains("include_detailed_atoms"))
+        includeDetailed = params.get_as<bool>("include_detailed_atoms");
+    int nLines = 0;
+    for (const LwB200Atom& a : m.atoms)
+        for (int kr = 0; kr < a.Ntrans; ++kr)
+            if (a.trans[kr].rhoPrd && (!a.detailedStatic || includeDetailed))
+            {
+                if (!a.trans[kr].Qelast || !a.C)
+                    return redistribute_prd_lines_scalar(ctx, maxIter, tol, params); // not ours to guess
+                ++nLines;
+            }
+    if (nLines == 0)
+        return IterationResult{};
+    sync_inputs(ctx, m, false);
+    check(lwb200_upload(m.dev, LWB200_PRD | LWB200_RATES), "lwb200_upload");
+    std::vector<f64> dRho((size_t)maxIter * nLines, 0.0), dJ(maxIter, 0.0);
+    std::vector<int32_t> dRhoIdx((size_t)maxIter * nLines, 0);
+    std::vector<int64_t> dJIdx(maxIter, 0);
+    int32_t nIter = 0;
+    check(lwb200_redistribute_prd(m.dev, maxIter, tol, includeDetailed ? 1 : 0, &nIter, dRho.data(),
+                                  dRhoIdx.data(), dJ.data(), dJIdx.data()),
+          "lwb200_redistribute_prd");
+    check(lwb200_download(m.dev, LWB200_PRD | LWB200_JBAR | LWB200_INTENS | LWB200_RATES), "lwb200_download");
+    check(lwb200_sync(m.dev), "lwb200_sync");
+    m.fpJ = fingerprint(1469598103934665603ULL, m.prob.J, (size_t)m.prob.Nspect * m.prob.Nspace);
+    IterationResult result{};
+    result.updatedRho = true;
+    result.updatedJPrd = true;
+    result.NprdSubIter = nIter;
+    for (int it = 0; it < nIter; ++it)
+    {
+        for (int q = 0; q < nLines; ++q)
+        {
+            result.dRho.push_back(dRho[(size_t)it * nLines + q]);
+            result.dRhoMaxIdx.push_back(dRhoIdx[(size_t)it * nLines + q]);
+        }
+        result.dJPrdMax.push_back(dJ[it]);
+        result.dJPrdMaxIdx.push_back((int)dJIdx[it]);
+    }
+    return result;
+}
+
 IterationResult b200_simple_fs(Context& ctx, bool upOnly, ExtraParams params)
 {
     (void)params;
@@ -416,7 +467,7 @@ FsIterationFns fs_iteration_fns_provider()
         b200_fs_iter,
         b200_simple_fs,
         formal_sol_full_stokes_impl,
-        redistribute_prd_lines_scalar,
+        b200_redistribute_prd,
         b200_stat_eq,
         time_dependent_update_impl,
         nr_post_update_impl,

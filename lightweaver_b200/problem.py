@@ -40,6 +40,7 @@ class TransitionData:
     wphi: Optional[np.ndarray] = None      # [Ncol, Nspace]
     rhoPrd: Optional[np.ndarray] = None    # [Ncol, Nlambda, Nspace]
     aDamp: Optional[np.ndarray] = None     # [Ncol, Nspace]
+    Qelast: Optional[np.ndarray] = None    # [Ncol, Nspace] PRD lines
     Rij: Optional[np.ndarray] = None       # [Ncol, Nspace]
     Rji: Optional[np.ndarray] = None
     name: str = ''
@@ -177,7 +178,7 @@ class Problem:
                                     lambda0=t.lambda0, wavelength=t.wavelength, Aji=t.Aji,
                                     Bji=t.Bji, Bij=t.Bij, dopplerWidth=t.dopplerWidth,
                                     alpha=t.alpha, phi=sl(t.phi), wphi=sl(t.wphi),
-                                    rhoPrd=sl(t.rhoPrd), aDamp=sl(t.aDamp), Rij=sl(t.Rij),
+                                    rhoPrd=sl(t.rhoPrd), aDamp=sl(t.aDamp), Qelast=sl(t.Qelast), Rij=sl(t.Rij),
                                     Rji=sl(t.Rji), name=t.name) for t in a.trans]
             atoms.append(AtomData(name=a.name, Nlevel=a.Nlevel, trans=trans, n=sl(a.n),
                                   nStar=sl(a.nStar), nTotal=sl(a.nTotal), vBroad=sl(a.vBroad),
@@ -228,10 +229,12 @@ class Problem:
                 ct.wavelength, ct.alpha = d(t.wavelength), d(t.alpha)
                 ct.phi, ct.wphi, ct.rhoPrd, ct.aDamp = d(t.phi), d(t.wphi), d(t.rhoPrd), d(t.aDamp)
                 ct.Rij, ct.Rji = d(t.Rij), d(t.Rji)
+                ct.Qelast = d(t.Qelast)
             keep.append(trans)
             ca.trans = C.cast(trans, C.POINTER(capi.LwB200Transition))
             ca.n, ca.nStar, ca.nTotal = d(a.n), d(a.nStar), d(a.nTotal)
             ca.vBroad, ca.Gamma = d(a.vBroad), d(a.Gamma)
+            ca.C = d(a.C)
         keep.append(atoms)
         p.atoms = C.cast(atoms, C.POINTER(capi.LwB200Atom))
         self._keepalive.append((p, keep))

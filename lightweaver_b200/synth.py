@@ -332,12 +332,13 @@ def collision_matrix(atom: ModelAtom, temperature, ne, nStar, rng):
 def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, seed=SEED,
                   formal_solver=capi.FS_BEZIER3, ndepth=None, detailed: Sequence[str] = (),
                   with_profiles=True, lambda_reference=500.0, col_range=None,
-                  alloc_phi=True) -> Problem:
+                  alloc_phi=True, prd=None) -> Problem:
     """Assemble a Problem for ``atoms`` in ``ncol`` FAL C columns.  ``col_range``
     = (c0, c1) keeps only that slice of the ``ncol`` columns (one column shard of
     a multi-GPU run; every rank sees the same seeded stack).  ``with_profiles``
     False leaves phi/wphi zero (to be made on the device); ``alloc_phi`` False
-    does not even allocate host phi."""
+    does not even allocate host phi.  ``prd``: {atom name: [line indices]} treated with
+    angle-averaged PRD (rhoPrd = 1 to start with, Qelast = the collisional part of the damping)."""
     rng = np.random.default_rng(seed + 1)
     atm = falc_columns(ncol, perturb=perturb, seed=seed, ndepth=ndepth)
     if col_range is not None:
@@ -399,6 +400,10 @@ def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, se
             gamma = gRad + 1.0e-14 * nHTot * (T / 5000.0)**0.38 + 4.0e-13 * ne
             dnuD = vBroad / (t.lambda0 * NM_TO_M)
             t.aDamp = np.ascontiguousarray(np.clip(gamma / (4.0 * np.pi * dnuD), 1e-4, 1e-1))
+            line_idx = [x for x in trans_lists[ia] if x.type == capi.LINE].index(t)
+            if prd and line_idx in prd.get(atom.name, ()):
+                t.rhoPrd = np.ones((ncol, t.Nlambda, K))
+                t.Qelast = np.ascontiguousarray(gamma - gRad)
             t.wphi = np.zeros((ncol, K))
             if with_profiles:
                 t.phi = voigt_profile(t.wavelength, t.lambda0, t.aDamp, vBroad, vlosMu)
@@ -437,6 +442,12 @@ def config_c2(nrays=10, nl=4.8, seed=SEED, **kw) -> Problem:
     return build_problem(atoms, ncol=1, nrays=nrays, seed=seed, **kw)
 
 
+def config_c4(nrays=5, nl=1.0, seed=SEED, **kw) -> Problem:
+    """Config 4: FAL C, H + Ca II + Mg II with the Mg II h and k lines in angle-averaged PRD."""
+    atoms = [h6_atom(nl), ca2_atom(nl), mg2_atom(nl)]
+    return build_problem(atoms, ncol=1, nrays=nrays, seed=seed, prd={'Mg': [0, 1]}, **kw)
+
+
 def config_c3(ncol=4096, nrays=5, seed=SEED, **kw) -> Problem:
     """Config 3: stack of perturbed FAL C columns, H + Ca II."""
     return config_c1(ncol=ncol, nrays=nrays, perturb=True, seed=seed, **kw)
@@ -452,3 +463,8 @@ def tiny_problem(ncol=1, nrays=3, seed=SEED, ndepth=None, perturb=False, **kw) -
     toy = ModelAtom('Toy', 12.0, 1e-4, lev, lines, cont)
     return build_problem([toy], ncol=ncol, nrays=nrays, seed=seed, ndepth=ndepth,
                          perturb=perturb, **kw)
+
+
+def tiny_prd_problem(ncol=1, nrays=3, **kw) -> Problem:
+    """tiny_problem with its two resonance lines in angle-averaged PRD."""
+    return tiny_problem(ncol=ncol, nrays=nrays, prd={'Toy': [0, 1]}, **kw)

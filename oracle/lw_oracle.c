@@ -562,8 +562,21 @@ static double bc_value(const LwB200Problem* p, int col, int la, int mu, int toOb
 /* intensity_core_opt, SimdFullIterationTemplates.hpp:238-487.
  * updateRates/computeOperator both on for the Gamma iteration, both off for
  * formal_sol. */
+static double intensity_core_mode(const LwB200Problem* p, int col, int la, Scratch* s, int fullIter,
+                                  int lambdaIterate, int upOnly, int storeDepth, int prdOnly);
+
 static double intensity_core(const LwB200Problem* p, int col, int la, Scratch* s, int fullIter,
                              int lambdaIterate, int upOnly, int storeDepth)
+{
+    return intensity_core_mode(p, col, la, s, fullIter, lambdaIterate, upOnly, storeDepth, 0);
+}
+
+/* prdOnly: the instantiation <UpdateRates = true, PrdRatesOnly = true, ComputeOperator = false>
+ * with FsMode UpdateJ | UpdateRates | PrdOnly that formal_sol_prd_update_rates uses
+ * (PrdTemplates.hpp:64-66): J and I as in the full iteration, rates only for transitions
+ * with rhoPrd (:433-434, :455-456), no Gamma. */
+static double intensity_core_mode(const LwB200Problem* p, int col, int la, Scratch* s, int fullIter,
+                                  int lambdaIterate, int upOnly, int storeDepth, int prdOnly)
 {
     const int K = p->Nspace, M = p->Nrays, L = p->Nspect;
     const double* h = p->height + (size_t)col * K;
@@ -618,7 +631,7 @@ static double intensity_core(const LwB200Problem* p, int col, int la, Scratch* s
 
             lwo_solve_ray(p->formalSolver, K, h, T, s->chiTot, s->S, p->muz[mu], toObs, wav,
                           p->lowerBc, p->upperBc, bc_value(p, col, la, mu, toObs), s->I,
-                          fullIter ? s->Psi : NULL);
+                          (fullIter && !prdOnly) ? s->Psi : NULL);
             p->I[((size_t)col * L + la) * M + mu] = s->I[0];
 
             if (fullIter)
@@ -631,18 +644,20 @@ static double intensity_core(const LwB200Problem* p, int col, int la, Scratch* s
                 {
                     const LwB200Atom* at = &p->atoms[a];
                     const int N = at->Nlevel;
-                    if (!at->detailedStatic)
+                    if (!at->detailedStatic && !prdOnly)
                     {
                         if (lambdaIterate)
                             memset(s->Psi, 0, sizeof(double) * K);
                         for (int k = 0; k < K; ++k)
                             s->Ieff[k] = s->I[k] - s->Psi[k] * s->aEta[a][k];
                     }
-                    double* Gamma = at->detailedStatic ? NULL : at->Gamma + (size_t)col * N * N * K;
+                    double* Gamma = (at->detailedStatic || prdOnly) ? NULL : at->Gamma + (size_t)col * N * N * K;
                     for (int kr = 0; kr < at->Ntrans; ++kr)
                     {
                         const LwB200Transition* t = &at->trans[kr];
                         if (!is_active(t, la))
+                            continue;
+                        if (prdOnly && !t->rhoPrd)
                             continue;
                         uv(p, col, a, kr, la, mu, toObs, s);
                         const double* wla = s->wla[a] + (size_t)kr * K;
@@ -961,3 +976,314 @@ int lwo_fs_iter_columns(const LwB200Problem* p, int col0, int ncol, unsigned fla
         pthread_join(th[t], NULL);
     return atomic_load(&job.rc);
 }
+
+/* ------------------------------------------------------------------------ */
+/* Angle-averaged PRD: redistribute_prd_lines (Prd.cpp:648-658 ->
+ * redistribute_prd_lines_template, PrdTemplates.hpp:164-351, Nthreads <= 1 branch). */
+
+/* Prd.cpp:33-36 */
+#define PRD_QWING 4.0
+#define PRD_QCORE 2.0
+#define PRD_QSPREAD 5.0
+#define PRD_DQ 0.15
+
+/* Prd.cpp:46-49 */
+static double G_zero(double x) { return 1.0 / (fabs(x) + sqrt(sq(x) + 1.273239545)); }
+
+/* Gouttebroze's GII, Prd.cpp:51-124 (waveratio = 1) */
+static double GII(double aDamp, double qEmit, double qAbs)
+{
+    const double waveratio = 1.0;
+    if (qEmit < 0.0)
+    {
+        qEmit = -qEmit;
+        qAbs = -qAbs;
+    }
+    double giiCore = 0.0, coreFactor = 0.0;
+    if (qEmit < PRD_QWING)
+    {
+        if ((qAbs < -PRD_QWING) || (qAbs > qEmit + waveratio * PRD_QSPREAD))
+            return 0.0;
+        if (fabs(qAbs) <= qEmit)
+            giiCore = G_zero(qEmit);
+        else
+            giiCore = exp(sq(qEmit) - sq(qAbs)) * G_zero(qAbs);
+        if (qEmit >= PRD_QCORE && qEmit <= PRD_QWING)
+        {
+            double phiCore = exp(-sq(qEmit));
+            double phiWing = aDamp / (sqrt(C_PI) * (sq(aDamp) + sq(qEmit)));
+            coreFactor = phiCore / (phiCore + phiWing);
+        }
+        else
+            return giiCore;
+    }
+    double gii = 0.0;
+    if (qEmit >= PRD_QCORE)
+    {
+        double aqEmit = waveratio * qEmit;
+        if ((qEmit >= PRD_QWING) && (fabs(qAbs - aqEmit) > waveratio * PRD_QSPREAD))
+            return 0.0;
+        double uMin = fabs((qAbs - aqEmit) / (1.0 + waveratio));
+        double giiWing = (1.0 + waveratio) * (1.0 - 2.0 * uMin * G_zero(uMin)) * exp(-sq(uMin))
+            / (2.0 * waveratio * sqrt(C_PI));
+        double ratio = qAbs / qEmit;
+        giiWing *= (2.75 - (2.5 - 0.75 * ratio) * ratio);
+        gii = coreFactor * giiCore + (1.0 - coreFactor) * giiWing;
+    }
+    return gii;
+}
+
+/* scattering_int_range, Prd.cpp:231-259 */
+static void scattering_int_range(double qEmit, double* q0, double* qN)
+{
+    if (fabs(qEmit) < PRD_QCORE)
+    {
+        *q0 = -PRD_QWING;
+        *qN = PRD_QWING;
+    }
+    else if (fabs(qEmit) < PRD_QWING)
+    {
+        if (qEmit > 0.0)
+        {
+            *q0 = -PRD_QWING;
+            *qN = qEmit + PRD_QSPREAD;
+        }
+        else
+        {
+            *q0 = qEmit - PRD_QSPREAD;
+            *qN = PRD_QWING;
+        }
+    }
+    else
+    {
+        *q0 = qEmit - PRD_QSPREAD;
+        *qN = qEmit + PRD_QSPREAD;
+    }
+}
+
+/* optimised_fine_linear_fixed_spacing, Prd.cpp:180-228 */
+static void fine_linear_fixed_spacing(int Ntable, const double* xTable, const double* yTable, double xStart,
+                                      double xStep, int N, double* y)
+{
+    if (N < 1)
+        return;
+    int iter; /* index of the first table entry > x (std::upper_bound) */
+    double x = xStart;
+    if (x <= xTable[0])
+        iter = 0;
+    else if (x >= xTable[Ntable - 1])
+        iter = Ntable - 1;
+    else
+    {
+        iter = 0;
+        while (iter < Ntable && !(x < xTable[iter]))
+            ++iter;
+    }
+    for (int i = 0; i < N; ++i)
+    {
+        x = xStart + i * xStep;
+        while (iter < Ntable && xTable[iter] <= x)
+            ++iter;
+        if (iter == Ntable)
+        {
+            y[i] = yTable[Ntable - 1];
+            continue;
+        }
+        else if (iter == 0)
+        {
+            y[i] = yTable[0];
+            continue;
+        }
+        double xp = xTable[iter - 1], xn = xTable[iter];
+        double t = (x - xp) / (xn - xp);
+        y[i] = (1.0 - t) * yTable[iter - 1] + t * yTable[iter];
+    }
+}
+
+#define PRD_MAX_FINE 128 /* max_fine_grid_size() = 87, Prd.cpp:126-129 */
+
+/* total_depop_elastic_scattering_rate (Prd.cpp:9-30) + prd_scatter / scattering_int
+ * (Prd.cpp:468-645) for one PRD line of column col.  gII is recomputed on every call: the
+ * reference caches it per (depth, wavelength) until aDamp / vBroad change, the values are the same. */
+static int prd_scatter_line(const LwB200Problem* p, int col, int a, int kr)
+{
+    const int K = p->Nspace, L = p->Nspect;
+    const LwB200Atom* at = &p->atoms[a];
+    const LwB200Transition* t = &at->trans[kr];
+    const int N = at->Nlevel, Nl = t->Nred - t->Nblue;
+    if (!t->Qelast || !at->C || !t->aDamp || !at->vBroad)
+        return 1;
+    double* rho = t->rhoPrd + (size_t)col * Nl * K;
+    double* Jk = (double*)malloc(sizeof(double) * Nl);
+    double* qWave = (double*)malloc(sizeof(double) * Nl);
+    double JFine[PRD_MAX_FINE], gII[PRD_MAX_FINE];
+    for (size_t q = 0; q < (size_t)Nl * K; ++q)
+        rho[q] = 1.0;
+    for (int k = 0; k < K; ++k)
+    {
+        double PjQj = t->Qelast[(size_t)col * K + k];
+        for (int i = 0; i < N; ++i)
+            PjQj += at->C[(((size_t)col * N + i) * N + t->j) * K + k];
+        for (int kr2 = 0; kr2 < at->Ntrans; ++kr2)
+        {
+            const LwB200Transition* t2 = &at->trans[kr2];
+            if (t2->j == t->j)
+                PjQj += t2->Rji[(size_t)col * K + k];
+            if (t2->i == t->j)
+                PjQj += t2->Rij[(size_t)col * K + k];
+        }
+        const double* n = at->n + (size_t)col * N * K;
+        double gammaPrefactor = n[(size_t)t->i * K + k] / n[(size_t)t->j * K + k] * t->Bij / PjQj;
+        double Jbar = t->Rij[(size_t)col * K + k] / t->Bij;
+        for (int la = 0; la < Nl; ++la)
+        {
+            Jk[la] = p->J[((size_t)col * L + la + t->Nblue) * K + k];
+            qWave[la] = (t->wavelength[la] - t->lambda0) * C_CLIGHT / (t->lambda0 * at->vBroad[(size_t)col * K + k]);
+        }
+        const double aDamp = t->aDamp[(size_t)col * K + k];
+        for (int la = 0; la < Nl; ++la)
+        {
+            const double qEmit = qWave[la];
+            double q0, qN;
+            scattering_int_range(qEmit, &q0, &qN);
+            const int Np = (int)((double)(qN - q0) / PRD_DQ) + 1;
+            fine_linear_fixed_spacing(Nl, qWave, Jk, q0, PRD_DQ, Np, JFine);
+            double qPrime = q0;
+            gII[0] = GII(aDamp, qEmit, qPrime) * 5.0 / 12.0 * PRD_DQ;
+            qPrime += PRD_DQ;
+            gII[1] = GII(aDamp, qEmit, qPrime) * 13.0 / 12.0 * PRD_DQ;
+            for (int laFine = 2; laFine < Np - 2; ++laFine)
+            {
+                qPrime += PRD_DQ;
+                gII[laFine] = GII(aDamp, qEmit, qPrime) * PRD_DQ;
+            }
+            qPrime += PRD_DQ;
+            gII[Np - 2] = GII(aDamp, qEmit, qPrime) * 13.0 / 12.0 * PRD_DQ;
+            qPrime += PRD_DQ;
+            gII[Np - 1] = GII(aDamp, qEmit, qPrime) * 5.0 / 12.0 * PRD_DQ;
+            double gNorm = 0.0, scatInt = 0.0;
+            for (int laF = 0; laF < Np; ++laF)
+            {
+                gNorm += gII[laF];
+                scatInt += JFine[laF] * gII[laF];
+            }
+            rho[(size_t)la * K + k] += gammaPrefactor * (scatInt / gNorm - Jbar);
+        }
+    }
+    free(Jk);
+    free(qWave);
+    return 0;
+}
+
+int lwo_redistribute_prd(const LwB200Problem* p, int col, int maxIter, double tol, int includeDetailed,
+                         int* nIterOut, double* dRho, int* dRhoIdx, double* dJPrdMax, int64_t* dJPrdMaxIdx)
+{
+    const int K = p->Nspace, L = p->Nspect;
+    /* the PRD lines, active atoms first then (optionally) detailed ones (PrdTemplates.hpp:186-211) */
+    int nLines = 0;
+    int (*lines)[2] = (int (*)[2])malloc(sizeof(int[2]) * 256);
+    for (int pass = 0; pass < (includeDetailed ? 2 : 1); ++pass)
+        for (int a = 0; a < p->Natom; ++a)
+        {
+            if ((p->atoms[a].detailedStatic != 0) != (pass == 1))
+                continue;
+            for (int kr = 0; kr < p->atoms[a].Ntrans; ++kr)
+                if (p->atoms[a].trans[kr].rhoPrd && nLines < 256)
+                {
+                    lines[nLines][0] = a;
+                    lines[nLines][1] = kr;
+                    ++nLines;
+                }
+        }
+    if (nIterOut) *nIterOut = 0;
+    if (nLines == 0)
+    {
+        free(lines);
+        return 0;
+    }
+    /* Ng(0, 0, 0, rho): change tracking only (Ng.hpp:30-40, :52-62, :137-155) */
+    double** prev = (double**)malloc(sizeof(double*) * nLines);
+    for (int q = 0; q < nLines; ++q)
+    {
+        const LwB200Transition* t = &p->atoms[lines[q][0]].trans[lines[q][1]];
+        const size_t n = (size_t)(t->Nred - t->Nblue) * K;
+        prev[q] = (double*)malloc(sizeof(double) * n);
+        memcpy(prev[q], t->rhoPrd + (size_t)col * n, sizeof(double) * n);
+    }
+    /* wavelengths touched by a PRD line (:225-240) */
+    char* prdLa = (char*)calloc(L, 1);
+    for (int q = 0; q < nLines; ++q)
+    {
+        const LwB200Transition* t = &p->atoms[lines[q][0]].trans[lines[q][1]];
+        for (int la = t->Nblue; la < t->Nred; ++la)
+            prdLa[la] = 1;
+    }
+    Scratch* s = scratch_new(p);
+    int iter = 0, rc = 0;
+    while (iter < maxIter)
+    {
+        ++iter;
+        double dRhoMax = 0.0;
+        for (int q = 0; q < nLines; ++q)
+        {
+            const LwB200Transition* t = &p->atoms[lines[q][0]].trans[lines[q][1]];
+            const int Nl = t->Nred - t->Nblue;
+            if (prd_scatter_line(p, col, lines[q][0], lines[q][1]))
+            {
+                rc = 1;
+                goto done;
+            }
+            const double* cur = t->rhoPrd + (size_t)col * Nl * K;
+            double dMax = 0.0;
+            int maxIdx = 0;
+            for (size_t e = 0; e < (size_t)Nl * K; ++e)
+                if (cur[e] != 0.0)
+                {
+                    double change = fabs((cur[e] - prev[q][e]) / cur[e]);
+                    if (dMax < change)
+                    {
+                        dMax = change;
+                        maxIdx = (int)e;
+                    }
+                }
+            memcpy(prev[q], cur, sizeof(double) * (size_t)Nl * K);
+            dRhoMax = dmax(dRhoMax, dMax);
+            if (dRho) dRho[(size_t)(iter - 1) * nLines + q] = dMax;
+            if (dRhoIdx) dRhoIdx[(size_t)(iter - 1) * nLines + q] = maxIdx % Nl;
+        }
+        /* formal_sol_prd_update_rates (PrdTemplates.hpp:18-76) */
+        for (int q = 0; q < nLines; ++q)
+        {
+            const LwB200Transition* t = &p->atoms[lines[q][0]].trans[lines[q][1]];
+            memset(t->Rij + (size_t)col * K, 0, sizeof(double) * K);
+            memset(t->Rji + (size_t)col * K, 0, sizeof(double) * K);
+        }
+        double dJMax = 0.0;
+        int64_t dJIdx = 0;
+        for (int la = 0; la < L; ++la)
+        {
+            if (!prdLa[la])
+                continue;
+            double dJ = intensity_core_mode(p, col, la, s, 1, 0, 0, 0, 1);
+            if (dJMax < dJ)
+            {
+                dJMax = dJ;
+                dJIdx = la;
+            }
+        }
+        if (dJPrdMax) dJPrdMax[iter - 1] = dJMax;
+        if (dJPrdMaxIdx) dJPrdMaxIdx[iter - 1] = dJIdx;
+        if (dRhoMax < tol)
+            break;
+    }
+done:
+    if (nIterOut) *nIterOut = iter;
+    scratch_free(s);
+    free(prdLa);
+    for (int q = 0; q < nLines; ++q)
+        free(prev[q]);
+    free(prev);
+    free(lines);
+    return rc;
+}
+

@@ -48,6 +48,14 @@ int lwo_solve_lin_eq(int N, double* A, double* b, int improve);
 int lwo_fs_iter_columns(const LwB200Problem* p, int col0, int ncol, unsigned flags,
                         int withStatEq, int nthreads);
 
+/* redistribute_prd_lines for angle-averaged PRD lines (Prd.cpp:9-124, :468-658;
+ * PrdTemplates.hpp:18-76, :164-291), Nthreads <= 1 branch, on column `col`.  dRho / dRhoIdx
+ * [maxIter * NprdLines] in (iteration, line) order, dJPrdMax / dJPrdMaxIdx [maxIter];
+ * dJPrdMaxIdx is the argmax wavelength (the reference's serial branch returns the index quirk
+ * described at lwo_fs_iter).  Returns 1 if a PRD line lacks Qelast / C / aDamp / vBroad. */
+int lwo_redistribute_prd(const LwB200Problem* p, int col, int maxIter, double tol, int includeDetailed,
+                         int* nIter, double* dRho, int* dRhoIdx, double* dJPrdMax, int64_t* dJPrdMaxIdx);
+
 /* Transition::compute_phi / compute_wphi are NOT restated here (they need
  * Faddeeva); the tests use scipy.special.wofz (the same Faddeeva package). */
 

@@ -37,6 +37,8 @@ def load():
     lib.lwo_stat_eq.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.lwo_solve_lin_eq.argtypes = [C.c_int, dp, dp, C.c_int]
     lib.lwo_fs_iter_columns.argtypes = [vp, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int]
+    lib.lwo_redistribute_prd.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp,
+                                         C.POINTER(C.c_int), dp, i64p]
     _lib = lib
     return lib
 
@@ -66,6 +68,21 @@ class OracleContext:
         rc = self.lib.lwo_stat_eq(C.byref(self._cs), self.col, atom, kStart, kEnd, C.byref(ns))
         if rc != 0:
             raise RuntimeError('Singular Matrix')
+
+    def redistribute_prd(self, maxIter=3, tol=1e-2, includeDetailed=False, nlines=16):
+        """-> dict(nIter, dRho, dRhoIdx, dJPrdMax, dJPrdMaxIdx) like reflib.RefContext.redistribute_prd"""
+        n = C.c_int(0)
+        dRho = np.zeros(maxIter * nlines)
+        dRhoIdx = np.zeros(maxIter * nlines, dtype=np.int32)
+        dJ = np.zeros(maxIter)
+        dJIdx = np.zeros(maxIter, dtype=np.int64)
+        dp = C.POINTER(C.c_double)
+        rc = self.lib.lwo_redistribute_prd(C.byref(self._cs), self.col, maxIter, tol, int(includeDetailed),
+                                           C.byref(n), dRho.ctypes.data_as(dp),
+                                           dRhoIdx.ctypes.data_as(C.POINTER(C.c_int)), dJ.ctypes.data_as(dp),
+                                           dJIdx.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert rc == 0
+        return dict(nIter=n.value, dRho=dRho, dRhoIdx=dRhoIdx, dJPrdMax=dJ[:n.value], dJPrdMaxIdx=dJIdx[:n.value])
 
     def fs_iter_columns(self, col0, ncol, withStatEq=False, nthreads=0):
         rc = self.lib.lwo_fs_iter_columns(C.byref(self._cs), col0, ncol, 0, int(withStatEq), nthreads)

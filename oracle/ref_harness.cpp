@@ -175,6 +175,8 @@ int lwref_create(const LwB200Problem* p, int col, const char* scheme, int Nthrea
                     throw std::runtime_error("active atom without Gamma");
                 atom.Gamma = F64View3D(pa.Gamma + c * N * N * K, N, N, K);
             }
+            if (pa.C)
+                atom.C = F64View3D(const_cast<f64*>(pa.C) + c * N * N * K, N, N, K);
             atom.methodScratch = nullptr;
 
             for (int kr = 0; kr < pa.Ntrans; ++kr)
@@ -201,6 +203,8 @@ int lwref_create(const LwB200Problem* p, int col, const char* scheme, int Nthrea
                         t.aDamp = F64View(const_cast<f64*>(pt.aDamp) + c * K, K);
                     if (pt.rhoPrd)
                         t.rhoPrd = F64View2D(const_cast<f64*>(pt.rhoPrd) + c * Nl * K, Nl, K);
+                    if (pt.Qelast)
+                        t.Qelast = F64View(const_cast<f64*>(pt.Qelast) + c * K, K);
                 }
                 else
                 {
@@ -310,6 +314,36 @@ int lwref_formal_sol(LwRefHandle* hh, int upOnly)
     try
     {
         formal_sol(*h->ctx, upOnly != 0, ExtraParams{});
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// redistribute_prd_lines (LwContext.prd_redistribute, LwMiddleLayer.pyx:3647-3684).
+int lwref_redistribute_prd(LwRefHandle* hh, int maxIter, double tol, int includeDetailed, int* nIter,
+                           double* dRho, int* dRhoIdx, double* dJPrdMax, int64_t* dJPrdMaxIdx)
+{
+    auto* h = (LwRef*)hh;
+    try
+    {
+        ExtraParams params{};
+        params.insert("include_detailed_atoms", includeDetailed != 0);
+        IterationResult r = redistribute_prd_lines(*h->ctx, maxIter, tol, params);
+        if (nIter) *nIter = r.NprdSubIter;
+        for (size_t q = 0; q < r.dRho.size(); ++q)
+        {
+            if (dRho) dRho[q] = r.dRho[q];
+            if (dRhoIdx) dRhoIdx[q] = r.dRhoMaxIdx[q];
+        }
+        for (size_t q = 0; q < r.dJPrdMax.size(); ++q)
+        {
+            if (dJPrdMax) dJPrdMax[q] = r.dJPrdMax[q];
+            if (dJPrdMaxIdx) dJPrdMaxIdx[q] = r.dJPrdMaxIdx[q];
+        }
         return 0;
     }
     catch (const std::exception& e)

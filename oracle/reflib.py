@@ -60,6 +60,8 @@ def load():
     lib.lwref_fs_iter.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int64)]
     lib.lwref_formal_sol.argtypes = [vp, C.c_int]
     lib.lwref_stat_eq.argtypes = [vp]
+    lib.lwref_redistribute_prd.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp,
+                                           C.POINTER(C.c_int), dp, C.POINTER(C.c_int64)]
     lib.lwref_compute_profiles.argtypes = [vp]
     lib.lwref_time_fs_iter.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
     lib.lwref_solve_ray.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_int,
@@ -100,6 +102,20 @@ class RefContext:
 
     def stat_eq(self):
         _check(self.lib.lwref_stat_eq(self.h))
+
+    def redistribute_prd(self, maxIter=3, tol=1e-2, includeDetailed=False, nlines=16):
+        """-> dict(nIter, dRho [nIter, nlines'], dJPrdMax [nIter])"""
+        import numpy as np
+        n = C.c_int(0)
+        dRho = np.zeros(maxIter * nlines)
+        dRhoIdx = np.zeros(maxIter * nlines, dtype=np.int32)
+        dJ = np.zeros(maxIter)
+        dJIdx = np.zeros(maxIter, dtype=np.int64)
+        dp = C.POINTER(C.c_double)
+        _check(self.lib.lwref_redistribute_prd(self.h, maxIter, tol, int(includeDetailed), C.byref(n),
+                                               dRho.ctypes.data_as(dp), dRhoIdx.ctypes.data_as(C.POINTER(C.c_int)),
+                                               dJ.ctypes.data_as(dp), dJIdx.ctypes.data_as(C.POINTER(C.c_int64))))
+        return dict(nIter=n.value, dRho=dRho, dRhoIdx=dRhoIdx, dJPrdMax=dJ[:n.value], dJPrdMaxIdx=dJIdx[:n.value])
 
     def compute_profiles(self):
         _check(self.lib.lwref_compute_profiles(self.h))

@@ -38,6 +38,9 @@ def input_digest(p):
                 h.update(t.wphi.tobytes())
             if t.alpha is not None:
                 h.update(t.alpha.tobytes())
+            if t.Qelast is not None:
+                h.update(t.Qelast.tobytes())
+                h.update(t.aDamp.tobytes())
     return h.hexdigest()
 
 
@@ -51,13 +54,35 @@ CASES = {
     'c1_bezier3': (synth.config_c1, dict(), 3, 16),
 }
 
+# angle-averaged PRD: every iteration is formal_sol_gamma_matrices, prd_redistribute(maxIter, tol),
+# stat_equil (the order of lightweaver/iterate_ctx.py)
+PRD_CASES = {
+    'tiny_prd': (synth.tiny_prd_problem, dict(perturb=True), 3, None, dict(maxIter=3, tol=1e-3)),
+    'c4_prd': (synth.config_c4, dict(), 2, 16, dict(maxIter=3, tol=1e-2)),
+}
+
 
 def build_case(name):
-    fn, kw, niter, jstride = CASES[name]
+    if name in PRD_CASES:
+        fn, kw, niter, jstride, _ = PRD_CASES[name]
+    else:
+        fn, kw, niter, jstride = CASES[name]
     return fn(**kw), niter, jstride
 
 
-def run_reference(p, niter):
+def prd_snapshot(p, res):
+    snap = {'prd_nIter': np.array(res['nIter']), 'prd_dRho': np.array(res['dRho']),
+            'prd_dJ': np.array(res['dJPrdMax']), 'prd_I': p.I.copy(), 'prd_J': p.J.copy()}
+    for ia, a in enumerate(p.atoms):
+        for it_, t in enumerate(a.trans):
+            if t.rhoPrd is not None:
+                snap[f'prd_rho{ia}_{it_}'] = t.rhoPrd.copy()
+                snap[f'prd_Rij{ia}_{it_}'] = t.Rij.copy()
+                snap[f'prd_Rji{ia}_{it_}'] = t.Rji.copy()
+    return snap
+
+
+def run_reference(p, niter, prd=None):
     """iterate_ctx_se-style: first iteration pure Lambda, then MALI, stat_eq
     after each (lightweaver/iterate_ctx.py:157-176).  Returns per-iteration
     snapshots."""
@@ -73,6 +98,10 @@ def run_reference(p, niter):
             for it_, t in enumerate(a.trans):
                 snap[f'Rij{ia}_{it_}'] = t.Rij.copy()
                 snap[f'Rji{ia}_{it_}'] = t.Rji.copy()
+        if prd is not None:
+            assert p.Ncol == 1
+            nl = sum(1 for a in p.atoms for t in a.trans if t.rhoPrd is not None)
+            snap.update(prd_snapshot(p, ctxs[0].redistribute_prd(nlines=nl, **prd)))
         for c in ctxs:
             c.stat_eq()
         for ia, a in enumerate(p.atoms):
@@ -84,15 +113,18 @@ def run_reference(p, niter):
 
 
 def main():
-    for name in CASES:
+    only = sys.argv[1:]
+    for name in list(CASES) + list(PRD_CASES):
+        if only and name not in only:
+            continue
         p, niter, jstride = build_case(name)
         digest = input_digest(p)
-        snaps = run_reference(p, niter)
+        snaps = run_reference(p, niter, PRD_CASES[name][4] if name in PRD_CASES else None)
         out = {'input_digest': np.array(digest), 'niter': np.array(niter),
                'jstride': np.array(0 if jstride is None else jstride)}
         for it, s in enumerate(snaps):
             for k, v in s.items():
-                if k == 'J' and jstride is not None:
+                if k in ('J', 'prd_J') and jstride is not None:
                     v = v[:, ::jstride]
                 out[f'it{it}_{k}'] = v
         path = os.path.join(HERE, name + '.npz')

@@ -12,8 +12,8 @@ import pytest
 from lightweaver_b200 import capi, synth
 from lightweaver_b200.context import Context, ExplodingMatrixError
 from oracle import oraclelib
-from tests.golden.make_golden import CASES, build_case, input_digest
-from tests.test_oracle import check_snapshot, load_golden
+from tests.golden.make_golden import CASES, PRD_CASES, build_case, input_digest
+from tests.test_oracle import check_prd_snapshot, check_snapshot, load_golden
 from tests.util import compare_problems, gamma_err, rel_err
 
 pytestmark = pytest.mark.gpu
@@ -224,6 +224,55 @@ def test_angle_averaged_prd_rho_scales_gij():
     ctx.formal_sol_gamma_matrices()
     oracle_iter(q, stat_eq=False)
     assert_close(p, q)
+    ctx.close()
+
+
+@pytest.mark.parametrize('name', list(PRD_CASES))
+def test_cuda_prd_matches_reference_golden(name):
+    """formal_sol_gamma_matrices -> prd_redistribute -> stat_equil against the reference's outputs."""
+    p, niter, jstride = build_case(name)
+    prd = PRD_CASES[name][4]
+    g = load_golden(name)
+    assert input_digest(p) == str(g['input_digest'])
+    ctx = Context(p)
+    for it in range(niter):
+        ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+        check_snapshot(p, g, it, jstride, TOL)
+        upd = ctx.prd_redistribute(**prd)
+        res = dict(nIter=upd.NprdSubIter, dRho=upd.dRho, dJPrdMax=upd.dJPrdMax)
+        check_prd_snapshot(p, g, it, jstride, res, TOL)
+        ctx.stat_equil()
+        for ia, a in enumerate(p.atoms):
+            assert rel_err(a.n, g[f'it{it}_n{ia}']) <= TOL_N
+    ctx.close()
+
+
+@pytest.mark.parametrize('ndepth', [None, 200])
+def test_cuda_prd_vs_oracle_columns(ndepth):
+    """Angle-averaged PRD on a perturbed two-column stack (also with several warps per column)."""
+    p = synth.tiny_prd_problem(ncol=2, perturb=True, ndepth=ndepth)
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices()
+        upd = ctx.prd_redistribute(maxIter=2, tol=1e-6)
+        q.prefill_gamma()
+        dRho = []
+        for c in range(q.Ncol):
+            o = oraclelib.OracleContext(q, col=c)
+            o.fs_iter()
+            dRho.append(o.redistribute_prd(maxIter=2, tol=1e-6, nlines=2)['dRho'][:4])
+        assert upd.NprdSubIter == 2
+        assert rel_err(np.asarray(upd.dRho), np.max(dRho, axis=0)) <= TOL
+        for tp, tq in zip(p.atoms[0].trans, q.atoms[0].trans):
+            if tp.rhoPrd is not None:
+                assert rel_err(tp.rhoPrd, tq.rhoPrd) <= TOL
+        e = compare_problems(p, q)
+        assert e['I'] <= TOL and e['J'] <= TOL and e['R'] <= TOL, e
+        ctx.stat_equil()
+        for c in range(q.Ncol):
+            oraclelib.OracleContext(q, col=c).stat_eq()
+        assert compare_problems(p, q)['n'] <= TOL_N
     ctx.close()
 
 

@@ -9,7 +9,7 @@ import pytest
 
 from lightweaver_b200 import capi, synth
 from oracle import oraclelib, reflib
-from tests.golden.make_golden import CASES, build_case, input_digest
+from tests.golden.make_golden import CASES, PRD_CASES, build_case, input_digest
 from tests.util import compare_problems, rel_err
 
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
@@ -58,6 +58,70 @@ def test_oracle_matches_reference_golden(name):
             oraclelib.OracleContext(p, col=c).stat_eq()
         for ia, a in enumerate(p.atoms):
             assert rel_err(a.n, g[f'it{it}_n{ia}']) <= 1e-11
+
+
+def check_prd_snapshot(p, g, it, jstride, res, tol):
+    """State after prd_redistribute against the reference's (tests/golden, PRD cases)."""
+    assert res['nIter'] == int(g[f'it{it}_prd_nIter'])
+    n = res['nIter']
+    nl = len(g[f'it{it}_prd_dRho']) // max(len(g[f'it{it}_prd_dJ']), 1) if n else 0
+    errs = {'dRho': rel_err(np.asarray(res['dRho'][:n * nl]), g[f'it{it}_prd_dRho'][:n * nl], floor=1e-30),
+            'dJ': rel_err(np.asarray(res['dJPrdMax'][:n]), g[f'it{it}_prd_dJ'][:n], floor=1e-30),
+            'I': rel_err(p.I, g[f'it{it}_prd_I'])}
+    J = p.J if not jstride else p.J[:, ::jstride]
+    errs['J'] = rel_err(J, g[f'it{it}_prd_J'])
+    for ia, a in enumerate(p.atoms):
+        for it_, t in enumerate(a.trans):
+            if t.rhoPrd is not None:
+                errs[f'rho{ia}_{it_}'] = rel_err(t.rhoPrd, g[f'it{it}_prd_rho{ia}_{it_}'])
+                errs[f'R{ia}_{it_}'] = max(rel_err(t.Rij, g[f'it{it}_prd_Rij{ia}_{it_}'], floor=1e-30),
+                                          rel_err(t.Rji, g[f'it{it}_prd_Rji{ia}_{it_}'], floor=1e-30))
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, f'iteration {it} (PRD): {bad}'
+    return errs
+
+
+@pytest.mark.parametrize('name', list(PRD_CASES))
+def test_oracle_prd_matches_reference_golden(name):
+    """redistribute_prd_lines: the C restatement against the reference's own outputs."""
+    p, niter, jstride = build_case(name)
+    prd = PRD_CASES[name][4]
+    g = load_golden(name)
+    assert input_digest(p) == str(g['input_digest']), 'synthetic input generator drifted; regenerate goldens'
+    nl = sum(1 for a in p.atoms for t in a.trans if t.rhoPrd is not None)
+    o = oraclelib.OracleContext(p)
+    for it in range(niter):
+        p.prefill_gamma()
+        o.fs_iter(lambdaIterate=(it == 0))
+        check_snapshot(p, g, it, jstride, 1e-12)
+        res = o.redistribute_prd(nlines=nl, **prd)
+        check_prd_snapshot(p, g, it, jstride, res, 1e-12)
+        o.stat_eq()
+        for ia, a in enumerate(p.atoms):
+            assert rel_err(a.n, g[f'it{it}_n{ia}']) <= 1e-11
+
+
+@pytest.mark.ref
+def test_oracle_prd_vs_reference_live():
+    """Bit-level agreement of the PRD restatement with the compiled reference."""
+    p = synth.tiny_prd_problem(nrays=2, ndepth=50)
+    q = p.clone()
+    r, o = reflib.RefContext(p), oraclelib.OracleContext(q)
+    for it in range(2):
+        p.prefill_gamma()
+        q.prefill_gamma()
+        r.fs_iter()
+        o.fs_iter()
+        a, b = r.redistribute_prd(maxIter=4, tol=1e-4, nlines=2), o.redistribute_prd(maxIter=4, tol=1e-4, nlines=2)
+        assert a['nIter'] == b['nIter']
+        assert np.array_equal(a['dRho'], b['dRho']) and np.array_equal(a['dJPrdMax'], b['dJPrdMax'])
+        for ta, tb in zip(p.atoms[0].trans, q.atoms[0].trans):
+            if ta.rhoPrd is not None:
+                assert np.array_equal(ta.rhoPrd, tb.rhoPrd)
+        assert max(compare_problems(q, p).values()) <= 1e-14
+        r.stat_eq()
+        o.stat_eq()
+    r.close()
 
 
 @pytest.mark.ref
@@ -178,8 +242,8 @@ def test_cabi_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     """ctypes mirrors of the POD structs have the C sizes (LP64)."""
     import ctypes as C
-    assert C.sizeof(capi.LwB200Transition) == 6 * 4 + 5 * 8 + 8 * 8
-    assert C.sizeof(capi.LwB200Atom) == 4 * 4 + 6 * 8
+    assert C.sizeof(capi.LwB200Transition) == 6 * 4 + 5 * 8 + 9 * 8
+    assert C.sizeof(capi.LwB200Atom) == 4 * 4 + 7 * 8
     assert C.sizeof(capi.LwB200Problem) == 12 * 4 + 19 * 8
 
 
