@@ -77,6 +77,39 @@ def test_reference_core_with_b200_scheme_matches_scalar_scheme(solver):
 @needs_plugin
 @pytest.mark.ref
 @pytest.mark.gpu
+def test_reference_core_redistributes_prd_through_the_b200_scheme():
+    """redistribute_prd_lines (Prd.cpp:648-653) dispatches to the scheme's redistribute_prd slot:
+    the reference core with our plugin against the reference core with its scalar scheme."""
+    p = synth.tiny_prd_problem(perturb=True)
+    q = p.clone()
+    gpu = reflib.RefContext(p, scheme=PLUGIN)
+    cpu = reflib.RefContext(q, scheme='scalar')
+    for it in range(2):
+        p.prefill_gamma()
+        q.prefill_gamma()
+        gpu.fs_iter()
+        cpu.fs_iter()
+        a = gpu.redistribute_prd(maxIter=3, tol=1e-3, nlines=2)
+        b = cpu.redistribute_prd(maxIter=3, tol=1e-3, nlines=2)
+        assert a['nIter'] == b['nIter']
+        n = a['nIter']
+        assert rel_err(a['dRho'][:2 * n], b['dRho'][:2 * n]) <= 1e-9
+        assert rel_err(a['dJPrdMax'], b['dJPrdMax']) <= 1e-9
+        for tp, tq in zip(p.atoms[0].trans, q.atoms[0].trans):
+            if tp.rhoPrd is not None:
+                assert rel_err(tp.rhoPrd, tq.rhoPrd) <= 1e-9
+        e = compare_problems(p, q)
+        assert e['I'] <= 1e-9 and e['J'] <= 1e-9 and e['R'] <= 1e-9, e
+        gpu.stat_eq()
+        cpu.stat_eq()
+        assert compare_problems(p, q)['n'] <= 1e-8
+    gpu.close()
+    cpu.close()
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.gpu
 def test_plugin_sees_in_place_host_mutations():
     """Python mutates buffers in place between calls without telling the plugin
     (update_deps, Ng acceleration): the shim's fingerprints must notice."""
