@@ -66,6 +66,11 @@ def build_workload(name, columns, rank=0, world=1, for_gpu=True):
     if name == 'c2':
         return synth.config_c2(), ('FAL C 1D, H + Ca II + Mg II + Na I + He I active, 10 rays '
                                    '(configs[1], synthetic atomic data)')
+    if name == 'c4':
+        return synth.config_c4(nl=2.0), ('FAL C 1D, H + Ca II + Mg II, Mg II h&k in angle-averaged PRD, 5 rays '
+                                         '(configs[3]; each step = Gamma iteration + up to 3 PRD sub-iterations on '
+                                         'fixed LTE populations -- no stat-eq, the synthetic atom is not meant to be '
+                                         'iterated to convergence with PRD; points counted for the Gamma iteration only)')
     if name == 'c3':
         from lightweaver_b200.sharding import partition_columns
         c0, c1 = partition_columns(columns, world)[rank]
@@ -138,6 +143,27 @@ def time_reference(problem, steps, warmup, budget_s=120.0):
     if reflib.available():
         schemes = reflib.usable_schemes()
         scheme = 'AVX2FMA' if 'AVX2FMA' in schemes else schemes[-1]
+        nprd = sum(1 for a in problem.atoms for t_ in a.trans if t_.rhoPrd is not None)
+        if problem.Ncol == 1 and nprd:
+            # PRD workload: Gamma iteration + prd_redistribute + stat_eq, timed around the three calls
+            ctx = reflib.RefContext(problem, scheme=scheme, Nthreads=cores)
+
+            def one():
+                problem.prefill_gamma()
+                t0 = time.perf_counter()
+                ctx.fs_iter()
+                ctx.redistribute_prd(maxIter=3, tol=1e-2, nlines=nprd)
+                return time.perf_counter() - t0
+            probe = one()
+            steps = max(1, min(steps, int(budget_s / max(probe, 1e-6)) - warmup))
+            for _ in range(warmup):
+                one()
+            sec = float(np.median([one() for _ in range(steps)]))
+            ctx.close()
+            return {'kind': 'reference', 'cores': cores, 'scheme': f'mali_full_precond_{scheme}',
+                    'sec_per_step': sec, 'value': pts_col / sec, 'steps': steps,
+                    'sample': f'full workload, {steps} timed (Gamma iteration + prd_redistribute(3)), '
+                              f'Nthreads={cores}'}
         if problem.Ncol == 1:
             problem.prefill_gamma()
             ctx = reflib.RefContext(problem, scheme=scheme, Nthreads=cores)
@@ -209,8 +235,11 @@ def run_ours(args, rank, world, local_rank):
         ctx.upload(capi.ALL_INPUTS & ~capi.PROFILE)
         ctx.update_deps(background=False, profiles_on_device=True)
     else:
-        ctx.upload(capi.ALL_INPUTS)
+        ctx.upload(capi.ALL_INPUTS | (capi.PRD if args.workload == 'c4' else 0))
     ctx.sync()
+    with_prd = args.workload == 'c4'
+    if with_prd and world > 1:
+        raise SystemExit('bench.py: the PRD workload (c4) runs on one GPU')
     shard = sharding.GpuLambdaShard(ctx)
     pts_local, alg_bytes, _ = ctx.work_stats()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -220,7 +249,10 @@ def run_ours(args, rank, world, local_rank):
             sharding.sharded_gamma_iteration(shard, group=None, want_dJ=False)
         else:
             ctx.fs_iter_device(want_dJ=False)
-        ctx.stat_eq_device()
+        if with_prd:
+            ctx.prd_redistribute_device(maxIter=3, tol=1e-2)
+        else:
+            ctx.stat_eq_device()
 
     def barrier():
         if world > 1:
@@ -239,7 +271,10 @@ def run_ours(args, rank, world, local_rank):
     else:
         ctx.fs_iter_device(want_dJ=False)
     per_step += ctx.work_stats()[2]
-    ctx.stat_eq_device()
+    if with_prd:
+        ctx.prd_redistribute_device(maxIter=3, tol=1e-2)
+    else:
+        ctx.stat_eq_device()
     per_step += ctx.work_stats()[2]
     barrier()
     clocks = ClockSampler(local_rank)
@@ -294,14 +329,18 @@ def run_ours(args, rank, world, local_rank):
     d2h += sum(t_.Rij.nbytes + t_.Rji.nbytes for a in problem.atoms for t_ in a.trans)
     e2e = None
     if world == 1 or column_sharded:
-        for _ in range(2):
+        def api_step():
             ctx.formal_sol_gamma_matrices()
-            ctx.stat_equil()
+            if with_prd:
+                ctx.prd_redistribute(maxIter=3, tol=1e-2)
+            else:
+                ctx.stat_equil()
+        for _ in range(2):
+            api_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            ctx.formal_sol_gamma_matrices()
-            ctx.stat_equil()
+            api_step()
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / args.steps
         te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -428,7 +467,7 @@ def _main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c3'])
+    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c3', 'c4'])
     ap.add_argument('--columns', type=int, default=4096)
     args = ap.parse_args()
 

@@ -227,6 +227,14 @@ int lwb200_formal_sol(LwB200Context* ctx, int upOnly);
  * call then fails like the reference's throw ("Singular Matrix"). */
 int lwb200_stat_eq(LwB200Context* ctx, int32_t atom, int32_t kStart, int32_t kEnd, int32_t* nSingular);
 
+/* Replaces time_dependent_update_impl (Source/UpdatePopulations.cpp:120-151;
+ * FsIterationFns::time_dep_update, LwFormalInterface.hpp:120): backward-Euler population update
+ * (1 - Gamma dt) n = nOld of atom `atom`, per depth, through the same LU solve as lwb200_stat_eq.
+ * nOld: host [Ncol][Nlevel][Nspace].  Gamma is the finalised matrix on the device (the last
+ * lwb200_fs_iter, or an LWB200_GAMMA_FINAL upload). */
+int lwb200_time_dep_update(LwB200Context* ctx, int32_t atom, const double* nOld, double dt, int32_t kStart,
+                           int32_t kEnd, int32_t* nSingular);
+
 /* Replaces redistribute_prd_lines (Source/Prd.cpp:648-658, PrdTemplates.hpp:164-351;
  * FsIterationFns::redistribute_prd, LwFormalInterface.hpp:118) for angle-averaged PRD lines:
  * up to maxIter sub-iterations of

@@ -148,6 +148,13 @@ class Context:
                 raise ExplodingMatrixError('Singular Matrix')
             capi.check(rc)
 
+    def prd_redistribute_device(self, maxIter=3, tol=1e-2, includeDetailed=False):
+        """PRD sub-iterations on device-resident data (inputs uploaded with capi.PRD)."""
+        n = C.c_int32(0)
+        capi.check(self.lib.lwb200_redistribute_prd(self._h, maxIter, tol, int(includeDetailed), C.byref(n),
+                                                    None, None, None, None))
+        return n.value
+
     def compute_profiles_device(self):
         capi.check(self.lib.lwb200_compute_profiles(self._h))
 
@@ -225,6 +232,35 @@ class Context:
             upd.dPops.append(float(d.max()))
             upd.dPopsMaxIdx.append(int(d.argmax()))
         return upd
+
+    def time_dep_update(self, dt, prevTimePops=None, extraParams=None):
+        """lw.Context.time_dep_update (LwMiddleLayer.pyx:3348-3432) without Ng: one backward-Euler
+        step of every active atom's populations from the current Gamma.  Returns (update,
+        prevTimePops) like the reference; pass the returned prevTimePops back in on the
+        following sub-iterations of the same time step."""
+        atoms = self.problem.active_atoms()
+        if prevTimePops is None:
+            prevTimePops = [np.copy(a.n) for a in atoms]
+        before = [a.n.copy() for a in atoms]
+        self.upload(capi.GAMMA_FINAL)
+        for a, nOld in zip(atoms, prevTimePops):
+            idx = self.problem.atoms.index(a)
+            ns = C.c_int32(0)
+            rc = self.lib.lwb200_time_dep_update(self._h, idx, capi.dptr(np.ascontiguousarray(nOld)), float(dt),
+                                                 -1, -1, C.byref(ns))
+            if rc != 0:
+                if ns.value > 0:
+                    raise ExplodingMatrixError('Singular Matrix')
+                capi.check(rc)
+        self.download(capi.POPS)
+        upd = IterationUpdate(updatedPops=True)
+        for p, a in zip(before, atoms):
+            with np.errstate(divide='ignore', invalid='ignore'):
+                d = np.abs(1.0 - p / a.n)
+            d = np.where(np.isfinite(d), d, 0.0)
+            upd.dPops.append(float(d.max()))
+            upd.dPopsMaxIdx.append(int(d.argmax()))
+        return upd, prevTimePops
 
     def update_deps(self, temperature=True, ne=True, vturb=True, vlos=True, B=True,
                     background=True, hprd=True, quiet=True, profiles_on_device=False):

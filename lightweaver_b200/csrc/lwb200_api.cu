@@ -157,7 +157,7 @@ struct LwB200Context
     std::vector<DevPrdLine> prdLines;
     std::vector<int> prdLineDetailed;
     DevBuf<DevPrdLine> dPrdLines;
-    DevBuf<double> qelast, cmat, rhoPrev, prdMax;
+    DevBuf<double> qelast, cmat, rhoPrev, prdMax, nOld;
     DevBuf<int> prdIdx, dKindLamPrd[4], dListMomentPrd;
     DevBuf<unsigned char> dPrdMask;
     std::vector<long long> atomCOff;
@@ -1111,6 +1111,7 @@ int lwb200_destroy(LwB200Context* c)
     c->qelast.release();
     c->cmat.release();
     c->rhoPrev.release();
+    c->nOld.release();
     c->prdMax.release();
     c->prdIdx.release();
     for (int q = 0; q < 4; ++q)
@@ -1541,7 +1542,8 @@ int lwb200_formal_sol(LwB200Context* c, int upOnly)
     return launch_fs<MODE_FS>(c, 0, upOnly ? 1 : 0, 0);
 }
 
-int lwb200_stat_eq(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd, int32_t* nSingular)
+static int population_update(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd, int32_t* nSingular,
+                             const double* nOldHost, double dt, const char* who)
 {
     CU(cudaSetDevice(c->device));
     const int K = c->prob.Nspace;
@@ -1551,11 +1553,26 @@ int lwb200_stat_eq(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd,
         kEnd = K;
     }
     if (kStart < 0 || kEnd > K || kStart >= kEnd)
-        return fail("lwb200_stat_eq: bad depth range");
+        return fail(std::string(who) + ": bad depth range");
     if (atom >= c->prob.Natom)
-        return fail("lwb200_stat_eq: atom index out of range");
+        return fail(std::string(who) + ": atom index out of range");
     c->lastLaunches = 0;
     CU(cudaMemsetAsync(c->dSingular.p, 0, sizeof(int), c->stream));
+    const double* nOldDev = nullptr;
+    if (nOldHost)
+    {
+        if (atom < 0 || c->atoms[atom].detailedStatic)
+            return fail(std::string(who) + ": needs one active atom");
+        const size_t count = (size_t)c->prob.Ncol * c->atoms[atom].Nlevel * K;
+        if (c->nOld.n < count)
+        {
+            c->nOld.release();
+            if (c->nOld.alloc(count))
+                return 1;
+        }
+        CU(cudaMemcpyAsync(c->nOld.p, nOldHost, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        nOldDev = c->nOld.p;
+    }
     {
         int maxN = 1, nActive = 0;
         for (int a = 0; a < c->prob.Natom; ++a)
@@ -1569,14 +1586,14 @@ int lwb200_stat_eq(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd,
         {
             const size_t total = (size_t)(atom >= 0 ? 1 : c->prob.Natom) * c->prob.Ncol * (kEnd - kStart);
             if (maxN <= 8)
-                stat_eq_kernel<8><<<grid_for(total, 64), 64, 0, c->stream>>>(c->P, atom, kStart, kEnd, c->gamma.p,
-                                                                               c->n.p, c->nTotal.p, c->dSingular.p);
+                stat_eq_kernel<8><<<grid_for(total, 64), 64, 0, c->stream>>>(
+                    c->P, atom, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, c->dSingular.p, nOldDev, dt);
             else if (maxN <= 16)
-                stat_eq_kernel<16><<<grid_for(total, 64), 64, 0, c->stream>>>(c->P, atom, kStart, kEnd, c->gamma.p,
-                                                                                c->n.p, c->nTotal.p, c->dSingular.p);
+                stat_eq_kernel<16><<<grid_for(total, 64), 64, 0, c->stream>>>(
+                    c->P, atom, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, c->dSingular.p, nOldDev, dt);
             else
-                stat_eq_kernel<32><<<grid_for(total, 64), 64, 0, c->stream>>>(c->P, atom, kStart, kEnd, c->gamma.p,
-                                                                                c->n.p, c->nTotal.p, c->dSingular.p);
+                stat_eq_kernel<32><<<grid_for(total, 64), 64, 0, c->stream>>>(
+                    c->P, atom, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, c->dSingular.p, nOldDev, dt);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }
@@ -1589,6 +1606,19 @@ int lwb200_stat_eq(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd,
     if (ns > 0)
         return fail("Singular Matrix");
     return 0;
+}
+
+int lwb200_stat_eq(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd, int32_t* nSingular)
+{
+    return population_update(c, atom, kStart, kEnd, nSingular, nullptr, 0.0, "lwb200_stat_eq");
+}
+
+int lwb200_time_dep_update(LwB200Context* c, int32_t atom, const double* nOld, double dt, int32_t kStart,
+                           int32_t kEnd, int32_t* nSingular)
+{
+    if (!nOld)
+        return fail("lwb200_time_dep_update: nOld is NULL");
+    return population_update(c, atom, kStart, kEnd, nSingular, nOld, dt, "lwb200_time_dep_update");
 }
 
 // redistribute_prd_lines_template (PrdTemplates.hpp:164-291) on the device-resident state.

@@ -666,10 +666,14 @@ __device__ inline void lu_backsub_dev(int N, const double* A, const int* index, 
     }
 }
 
+// nOld != nullptr: time_dependent_update_impl (UpdatePopulations.cpp:120-151) instead -- the
+// backward-Euler system (1 - Gamma dt) n = nOld of the same atom, depth by depth, through the
+// same solve_lin_eq.  nOld is [Ncol][Nlevel][K] of atom atomSel.
 template <int MAXN>
 __global__ void stat_eq_kernel(const DevProblem P, int atomSel, int kStart, int kEnd,
                                const double* __restrict__ gamma, double* __restrict__ n,
-                               const double* __restrict__ nTotal, int* __restrict__ nSingular)
+                               const double* __restrict__ nTotal, int* __restrict__ nSingular,
+                               const double* __restrict__ nOld, double dt)
 {
     // atomSel >= 0: that atom; atomSel < 0: every active atom in ONE launch (the systems of
     // different atoms are independent; in 1D there are only Nspace of them per atom)
@@ -702,12 +706,25 @@ __global__ void stat_eq_kernel(const DevProblem P, int atomSel, int kStart, int 
             for (int j = 0; j < N; ++j)
                 A[i * N + j] = gamma[gOff + (size_t)(i * N + j) * P.K];
         }
-        for (int i = 0; i < N; ++i)
+        if (nOld)
         {
-            A[iElim * N + i] = 1.0;
-            b[i] = 0.0;
+            for (int i = 0; i < N; ++i)
+            {
+                b[i] = nOld[((size_t)col * N + i) * P.K + k];
+                for (int j = 0; j < N; ++j)
+                    A[i * N + j] = -A[i * N + j] * dt;
+                A[i * N + i] = 1.0 - gamma[gOff + (size_t)(i * N + i) * P.K] * dt;
+            }
         }
-        b[iElim] = nTotal[((size_t)col * P.Natom + atom) * P.K + k];
+        else
+        {
+            for (int i = 0; i < N; ++i)
+            {
+                A[iElim * N + i] = 1.0;
+                b[i] = 0.0;
+            }
+            b[iElim] = nTotal[((size_t)col * P.Natom + atom) * P.K + k];
+        }
         for (int i = 0; i < N * N; ++i)
             ACopy[i] = A[i];
         for (int i = 0; i < N; ++i)

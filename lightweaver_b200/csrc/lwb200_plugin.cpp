@@ -424,6 +424,37 @@ void b200_stat_eq(Atom* atom, ExtraParams params, int spaceStart, int spaceEnd)
     check(lwb200_sync(m->dev), "lwb200_sync");
 }
 
+// FsIterationFns::time_dep_update (LwFormalInterface.hpp:120): backward-Euler step of one atom.
+void b200_time_dep_update(Atom* atom, F64View2D nOld, f64 dt, ExtraParams params, int spaceStart, int spaceEnd)
+{
+    Mirror* m = nullptr;
+    int idx = -1;
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        auto it = g_atoms.find(atom);
+        if (it != g_atoms.end())
+        {
+            m = it->second.first;
+            idx = it->second.second;
+        }
+    }
+    if (!m || !m->dev)
+    {
+        time_dependent_update_impl(atom, nOld, dt, params, spaceStart, spaceEnd);
+        return;
+    }
+    check(lwb200_upload(m->dev, LWB200_GAMMA_FINAL), "lwb200_upload");
+    int32_t nSingular = 0;
+    if (lwb200_time_dep_update(m->dev, idx, nOld.data, dt, spaceStart, spaceEnd, &nSingular) != 0)
+    {
+        if (nSingular > 0)
+            throw std::runtime_error("Singular Matrix");
+        raise("lwb200_time_dep_update");
+    }
+    check(lwb200_download(m->dev, LWB200_POPS), "lwb200_download");
+    check(lwb200_sync(m->dev), "lwb200_sync");
+}
+
 void b200_alloc_global_scratch(Context* ctx)
 {
     // Called from ThreadData::initialise (ThreadStorage.cpp:484-493), i.e. BEFORE
@@ -469,7 +500,7 @@ FsIterationFns fs_iteration_fns_provider()
         formal_sol_full_stokes_impl,
         b200_redistribute_prd,
         b200_stat_eq,
-        time_dependent_update_impl,
+        b200_time_dep_update,
         nr_post_update_impl,
         nullptr, // alloc_per_atom
         nullptr, // free_per_atom

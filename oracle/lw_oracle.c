@@ -977,6 +977,39 @@ int lwo_fs_iter_columns(const LwB200Problem* p, int col0, int ncol, unsigned fla
     return atomic_load(&job.rc);
 }
 
+/* time_dependent_update_impl, UpdatePopulations.cpp:120-151.  nOld: [Ncol][Nlevel][K] of the atom. */
+int lwo_time_dep_update(const LwB200Problem* p, int col, int atom, const double* nOld, double dt)
+{
+    const int K = p->Nspace;
+    const LwB200Atom* at = &p->atoms[atom];
+    const int N = at->Nlevel;
+    double* nk = (double*)malloc(sizeof(double) * N);
+    double* G = (double*)malloc(sizeof(double) * N * N);
+    const double* Gamma = at->Gamma + (size_t)col * N * N * K;
+    double* n = at->n + (size_t)col * N * K;
+    int rc = 0;
+    for (int k = 0; k < K; ++k)
+    {
+        for (int i = 0; i < N; ++i)
+        {
+            nk[i] = nOld[((size_t)col * N + i) * K + k];
+            for (int j = 0; j < N; ++j)
+                G[i * N + j] = -Gamma[((size_t)i * N + j) * K + k] * dt;
+            G[i * N + i] = 1.0 - Gamma[((size_t)i * N + i) * K + k] * dt;
+        }
+        if (lwo_solve_lin_eq(N, G, nk, 1))
+        {
+            rc = 1;
+            break;
+        }
+        for (int i = 0; i < N; ++i)
+            n[(size_t)i * K + k] = nk[i];
+    }
+    free(nk);
+    free(G);
+    return rc;
+}
+
 /* ------------------------------------------------------------------------ */
 /* Angle-averaged PRD: redistribute_prd_lines (Prd.cpp:648-658 ->
  * redistribute_prd_lines_template, PrdTemplates.hpp:164-351, Nthreads <= 1 branch). */

@@ -48,6 +48,10 @@ int lwo_solve_lin_eq(int N, double* A, double* b, int improve);
 int lwo_fs_iter_columns(const LwB200Problem* p, int col0, int ncol, unsigned flags,
                         int withStatEq, int nthreads);
 
+/* time_dependent_update_impl (UpdatePopulations.cpp:120-151) of atom `atom` on column `col`;
+ * nOld is [Ncol][Nlevel][Nspace].  Returns 1 for "Singular Matrix". */
+int lwo_time_dep_update(const LwB200Problem* p, int col, int atom, const double* nOld, double dt);
+
 /* redistribute_prd_lines for angle-averaged PRD lines (Prd.cpp:9-124, :468-658;
  * PrdTemplates.hpp:18-76, :164-291), Nthreads <= 1 branch, on column `col`.  dRho / dRhoIdx
  * [maxIter * NprdLines] in (iteration, line) order, dJPrdMax / dJPrdMaxIdx [maxIter];

@@ -37,6 +37,7 @@ def load():
     lib.lwo_stat_eq.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.lwo_solve_lin_eq.argtypes = [C.c_int, dp, dp, C.c_int]
     lib.lwo_fs_iter_columns.argtypes = [vp, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int]
+    lib.lwo_time_dep_update.argtypes = [vp, C.c_int, C.c_int, dp, C.c_double]
     lib.lwo_redistribute_prd.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp,
                                          C.POINTER(C.c_int), dp, i64p]
     _lib = lib
@@ -66,6 +67,12 @@ class OracleContext:
     def stat_eq(self, atom=-1, kStart=-1, kEnd=-1):
         ns = C.c_int(0)
         rc = self.lib.lwo_stat_eq(C.byref(self._cs), self.col, atom, kStart, kEnd, C.byref(ns))
+        if rc != 0:
+            raise RuntimeError('Singular Matrix')
+
+    def time_dep_update(self, atom, nOld, dt):
+        nOld = np.ascontiguousarray(nOld, dtype=np.float64)
+        rc = self.lib.lwo_time_dep_update(C.byref(self._cs), self.col, atom, nOld.ctypes.data_as(C.POINTER(C.c_double)), dt)
         if rc != 0:
             raise RuntimeError('Singular Matrix')
 

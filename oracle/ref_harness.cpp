@@ -323,6 +323,24 @@ int lwref_formal_sol(LwRefHandle* hh, int upOnly)
     }
 }
 
+// time_dependent_update of active atom number `activeIdx` (LwContext.time_dep_update,
+// LwMiddleLayer.pyx:3420-3424).  nOld: [Nlevel][Nspace] of this column.
+int lwref_time_dep_update(LwRefHandle* hh, int activeIdx, double* nOld, double dt)
+{
+    auto* h = (LwRef*)hh;
+    try
+    {
+        Atom* a = h->ctx->activeAtoms.at(activeIdx);
+        time_dependent_update(*h->ctx, a, F64View2D(nOld, a->Nlevel, h->atmos.Nspace), dt, ExtraParams{}, -1, -1);
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
 // redistribute_prd_lines (LwContext.prd_redistribute, LwMiddleLayer.pyx:3647-3684).
 int lwref_redistribute_prd(LwRefHandle* hh, int maxIter, double tol, int includeDetailed, int* nIter,
                            double* dRho, int* dRhoIdx, double* dJPrdMax, int64_t* dJPrdMaxIdx)

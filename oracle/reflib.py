@@ -60,6 +60,7 @@ def load():
     lib.lwref_fs_iter.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int64)]
     lib.lwref_formal_sol.argtypes = [vp, C.c_int]
     lib.lwref_stat_eq.argtypes = [vp]
+    lib.lwref_time_dep_update.argtypes = [vp, C.c_int, dp, C.c_double]
     lib.lwref_redistribute_prd.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp,
                                            C.POINTER(C.c_int), dp, C.POINTER(C.c_int64)]
     lib.lwref_compute_profiles.argtypes = [vp]
@@ -102,6 +103,12 @@ class RefContext:
 
     def stat_eq(self):
         _check(self.lib.lwref_stat_eq(self.h))
+
+    def time_dep_update(self, activeIdx, nOld, dt):
+        """nOld: [Nlevel, Nspace] of this context's column"""
+        import numpy as np
+        nOld = np.ascontiguousarray(nOld, dtype=np.float64)
+        _check(self.lib.lwref_time_dep_update(self.h, activeIdx, nOld.ctypes.data_as(C.POINTER(C.c_double)), dt))
 
     def redistribute_prd(self, maxIter=3, tol=1e-2, includeDetailed=False, nlines=16):
         """-> dict(nIter, dRho [nIter, nlines'], dJPrdMax [nIter])"""

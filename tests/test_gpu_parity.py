@@ -276,6 +276,25 @@ def test_cuda_prd_vs_oracle_columns(ndepth):
     ctx.close()
 
 
+def test_time_dependent_update_matches_oracle():
+    """Backward-Euler population step (time_dependent_update_impl) on a perturbed two-column stack."""
+    p = synth.tiny_problem(ncol=2, perturb=True)
+    q = p.clone()
+    ctx = Context(p)
+    ctx.formal_sol_gamma_matrices()
+    oracle_iter(q, stat_eq=False)
+    prev = None
+    nOld = q.atoms[0].n.copy()
+    for dt in (1e-3, 0.05):
+        upd, prev = ctx.time_dep_update(dt, prev)
+        for c in range(q.Ncol):
+            oraclelib.OracleContext(q, col=c).time_dep_update(0, nOld, dt)
+        assert rel_err(p.atoms[0].n, q.atoms[0].n) <= TOL_N
+        assert upd.updatedPops and len(upd.dPops) == 1
+    assert np.array_equal(prev[0], nOld)
+    ctx.close()
+
+
 def test_lambda_shards_sum_to_full_iteration():
     """Two wavelength shards with deferred finalise, summed on the host, equal
     the single-context result (the data path of the NCCL all-reduce)."""

@@ -102,6 +102,25 @@ def test_oracle_prd_matches_reference_golden(name):
 
 
 @pytest.mark.ref
+def test_oracle_time_dep_update_vs_reference():
+    """time_dependent_update_impl: restatement against the compiled reference (bit level)."""
+    p = synth.tiny_problem(perturb=True)
+    q = p.clone()
+    r, o = reflib.RefContext(p), oraclelib.OracleContext(q)
+    p.prefill_gamma()
+    q.prefill_gamma()
+    r.fs_iter()
+    o.fs_iter()
+    nOld = p.atoms[0].n.copy()
+    for dt in (1e-3, 0.1):
+        r.time_dep_update(0, nOld[0], dt)
+        o.time_dep_update(0, nOld, dt)
+        assert np.array_equal(p.atoms[0].n, q.atoms[0].n)
+        assert np.all(np.isfinite(p.atoms[0].n)) and not np.array_equal(p.atoms[0].n, nOld)
+    r.close()
+
+
+@pytest.mark.ref
 def test_oracle_prd_vs_reference_live():
     """Bit-level agreement of the PRD restatement with the compiled reference."""
     p = synth.tiny_prd_problem(nrays=2, ndepth=50)

@@ -110,6 +110,26 @@ def test_reference_core_redistributes_prd_through_the_b200_scheme():
 @needs_plugin
 @pytest.mark.ref
 @pytest.mark.gpu
+def test_reference_core_time_dep_update_through_the_b200_scheme():
+    p = synth.tiny_problem(perturb=True)
+    q = p.clone()
+    gpu = reflib.RefContext(p, scheme=PLUGIN)
+    cpu = reflib.RefContext(q, scheme='scalar')
+    for prob, ctx in ((p, gpu), (q, cpu)):
+        prob.prefill_gamma()
+        ctx.fs_iter()
+    nOld = q.atoms[0].n.copy()
+    gpu.time_dep_update(0, nOld[0], 0.01)
+    cpu.time_dep_update(0, nOld[0], 0.01)
+    assert rel_err(p.atoms[0].n, q.atoms[0].n) <= 1e-8
+    assert not np.array_equal(q.atoms[0].n, nOld)
+    gpu.close()
+    cpu.close()
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.gpu
 def test_plugin_sees_in_place_host_mutations():
     """Python mutates buffers in place between calls without telling the plugin
     (update_deps, Ng acceleration): the shim's fingerprints must notice."""
