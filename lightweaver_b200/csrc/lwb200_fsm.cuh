@@ -35,6 +35,7 @@ __device__ __forceinline__ double exp_fast(double x)
     t -= magic;
     double r = fma(t, -6.93147180369123816490e-01, x);
     r = fma(t, -1.90821492927058770002e-10, r);
+#ifdef LWB200_EXP_HORNER
     double p = 1.6059043836821613e-10;           // 1/13!
     p = fma(p, r, 2.08767569878681e-09);         // 1/12!
     p = fma(p, r, 2.505210838544172e-08);        // 1/11!
@@ -49,6 +50,24 @@ __device__ __forceinline__ double exp_fast(double x)
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
+#else
+    // Estrin's scheme: the same degree-13 Taylor polynomial with a dependency depth of 5
+    // instead of 14 (the kernel is bound by dependent-issue latency, not by fp64 throughput)
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double q01 = fma(r, 1.0, 1.0);
+    const double q23 = fma(r, 1.6666666666666666e-01, 0.5);
+    const double q45 = fma(r, 8.333333333333333e-03, 4.1666666666666664e-02);
+    const double q67 = fma(r, 1.984126984126984e-04, 1.388888888888889e-03);
+    const double q89 = fma(r, 2.7557319223985893e-06, 2.48015873015873e-05);
+    const double qab = fma(r, 2.505210838544172e-08, 2.755731922398589e-07);
+    const double qcd = fma(r, 1.6059043836821613e-10, 2.08767569878681e-09);
+    const double s03 = fma(r2, q23, q01);
+    const double s47 = fma(r2, q67, q45);
+    const double s8b = fma(r2, qab, q89);
+    const double t07 = fma(r4, s47, s03);
+    const double t8d = fma(r4, qcd, s8b);
+    double p = fma(r8, t8d, t07);
+#endif
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
@@ -97,12 +116,30 @@ __device__ __forceinline__ void load_geometry_r(DepthComm<MULTI>& cm, GeometryR<
 
 __device__ __forceinline__ double steffen_r(double wUw, double wDw, double Suw, double S0)
 {
-    // wUw = dsdw/(dsdw+dsuw) multiplies Suw, wDw = dsuw/(dsdw+dsuw) multiplies S0 (Bezier.hpp:58-65)
-    const double P0 = fabs(fma(Suw, wUw, S0 * wDw));
-    return (copysign(1.0, S0) + copysign(1.0, Suw)) * fmin(fabs(Suw), fmin(fabs(S0), 0.5 * P0));
+    // wUw = dsdw/(dsdw+dsuw) multiplies Suw, wDw = dsuw/(dsdw+dsuw) multiplies S0 (Bezier.hpp:58-65):
+    //   (sign(S0) + sign(Suw)) * min(|Suw|, |S0|, P0/2)
+    // = 0 if the slopes differ in sign, else 2 min(...) with their common sign.  The sign test and
+    // the sign transfer are integer operations on the high words (no fp64 issue slots), the
+    // minima plain compare/selects (no NaN path: the inputs are finite).
+    const double P0h = 0.5 * fabs(fma(Suw, wUw, S0 * wDw));
+    const double aU = fabs(Suw), a0 = fabs(S0);
+    double m = (a0 < P0h) ? a0 : P0h;
+    m = (aU < m) ? aU : m;
+    m += m;
+    const int h0 = __double2hiint(S0), hU = __double2hiint(Suw);
+    const int hm = __double2hiint(m) | (h0 & 0x80000000);
+    const double r = __hiloint2double(hm, __double2loint(m));
+    return ((h0 ^ hU) < 0) ? 0.0 : r;
 }
 
 __device__ __forceinline__ double sel(bool c, double a, double b) { return c ? a : b; }
+
+// optical depth clamped to [0, 700] for exp_fast (plain compare/selects)
+__device__ __forceinline__ double clamp_dt(double dt)
+{
+    dt = (dt < 0.0) ? 0.0 : dt;
+    return (dt > 700.0) ? 700.0 : dt;
+}
 
 // piecewise_bezier3_1d (FormalScalar.cpp:209-325, :535-600) in two phases.
 //
@@ -241,7 +278,7 @@ __device__ __forceinline__ void bezier3_sweep(DepthComm<MULTI>& cm, const Geomet
     for (int j = 0; j < NCH; ++j)
     {
         const double dt = dtU[j], rdt = rdtU[j];
-        const double ex = exp_fast(-fmin(fmax(dt, 0.0), 700.0));
+        const double ex = exp_fast(-clamp_dt(dt));
         const double dt2 = dt * dt, dt3 = dt2 * dt;
         const double edtC = sel(dt > 30.0, 0.0, ex);
         const double rdt3 = rdt * rdt * rdt;
@@ -273,7 +310,7 @@ __device__ __forceinline__ void bezier3_sweep(DepthComm<MULTI>& cm, const Geomet
         const double dsUE = DOWN ? pick<NCH>(g.dsfP, jE) : pick<NCH>(g.dsf, jE);
         const double dt = 0.5 * zmu * (chiE + chiUE) * dsUE;
         const double rdt = rcp_fast(dt);
-        const double ex = exp_fast(-fmin(fmax(dt, 0.0), 700.0));
+        const double ex = exp_fast(-clamp_dt(dt));
         const bool tayE = dt < 5.0E-4, thickE = dt > 50.0;
         const double w0m = 1.0 - ex;
         const double w0 = sel(tayE, dt * (1.0 - 0.5 * dt), sel(thickE, 1.0, w0m));

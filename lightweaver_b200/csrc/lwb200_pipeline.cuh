@@ -256,11 +256,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
                 bezier3_prepare<NCH>(cm, g, chi, S, 1.0, 1.0, pre1);
         }
         // profiles are fetched one ray ahead (NL <= 2; three lines leave no registers for it)
-#ifdef LWB200_NO_PREFETCH
-        constexpr bool PREFETCH = false;
-#else
         constexpr bool PREFETCH = (NL == 1 || NL == 2);
-#endif
         double pn[NLA][NCH];
         if (PREFETCH)
         {
