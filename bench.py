@@ -388,6 +388,18 @@ def run_ours(args, rank, world, local_rank):
                 traffic = tj['c3_per_column'] * problem.Ncol
         except Exception:
             traffic = None
+    # secondary, fp64-pipe view of the same launch set (F_alg ~ W (110 + 23 tbar) flop,
+    # tbar = mean number of active transitions per wavelength), against the DFMA peak measured on
+    # this pool's B200 by tools/fp64_peak.cu (profiles/*_fp64_peak.json)
+    tbar = sum(t_.Nlambda for a in problem.atoms for t_ in a.trans) / float(problem.Nspect)
+    flop_pt = 110.0 + 23.0 * tbar
+    fp64_peak = 36.0
+    try:
+        cands = sorted(f for f in os.listdir(os.path.join(ROOT, 'profiles')) if f.endswith('fp64_peak.json'))
+        fp64_peak = float(json.load(open(os.path.join(ROOT, 'profiles', cands[-1])))['fp64_tflops'])
+    except Exception:
+        pass
+    fp64_ach = flop_pt * pts_local / (kms * 1e-3) / 1e12
     line = {
         'metric': 'depth*lambda*mu*column ray-depth points/s, fp64 Gamma iteration (formal solution + Gamma/rates + stat-eq)',
         'value': value, 'unit': 'points/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -407,7 +419,10 @@ def run_ours(args, rank, world, local_rank):
                      'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                      'alg_bytes_per_launch': alg_bytes, 'kernel_ms': kms,
                      'kernel_share_of_step': kms / ms_per_step,
-                     'note': 'fp64-pipe bound, not HBM bound: see DESIGN.md section 5'},
+                     'note': 'fp64-pipe / dependent-issue bound, not HBM bound: see DESIGN.md section 5',
+                     'fp64': {'alg_flop_per_point': flop_pt, 'achieved': fp64_ach, 'peak': fp64_peak,
+                              'unit': 'TFLOP/s', 'frac': fp64_ach / fp64_peak,
+                              'peak_source': 'tools/fp64_peak.cu on this pool (profiles/*_fp64_peak.json)'}},
         'clocks': clk,
     }
     if world == 1:
