@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LWB200_ABI_VERSION 2
+#define LWB200_ABI_VERSION 3
 
 /* TransitionType, Source/LwTransition.hpp:10-14 */
 enum { LWB200_LINE = 0, LWB200_CONTINUUM = 1 };
@@ -68,6 +68,9 @@ typedef struct LwB200Transition {
     double* Rji;              /* [Ncol][Nspace] out */
     const double* Qelast;     /* [Ncol][Nspace] elastic collision rate of a PRD line (Transition::Qelast,
                                  LwTransition.hpp:51); only read by lwb200_redistribute_prd */
+    const double* polProfiles; /* polarised lines (Transition::polarised, LwTransition.hpp:44-50), else NULL:
+                                 [6][Ncol][Nlambda][Nrays][2][Nspace] = phiQ, phiU, phiV, psiQ, psiU, psiV;
+                                 only read by lwb200_formal_sol_full_stokes */
 } LwB200Transition;
 
 /* One atom (Source/LwAtom.hpp:42-80).  detailedStatic atoms contribute
@@ -120,6 +123,8 @@ typedef struct LwB200Problem {
     double* depthEta;
     double* depthI;
     LwB200Atom* atoms;         /* [Natom] */
+    double* Quv;               /* [Ncol][3][Nspect][Nrays] out of lwb200_formal_sol_full_stokes: spect.Quv(s, la, mu, 0)
+                                  (LwMisc.hpp:94), or NULL */
 } LwB200Problem;
 
 /* Input/output groups for lwb200_upload / lwb200_download. */
@@ -139,6 +144,7 @@ enum {
     LWB200_GAMMA_FINAL = 1u << 11, /* up only: host Gamma taken as the finalised matrix stat_eq reads */
     LWB200_PRD     = 1u << 12, /* up: rhoPrd, Qelast, C, aDamp (inputs of lwb200_redistribute_prd);
                                   down: rhoPrd */
+    LWB200_STOKES  = 1u << 13, /* up: the polarised profiles of every polarised line; down: Quv */
     LWB200_ALL_INPUTS  = 0x7fu,
     LWB200_ITER_INPUTS = LWB200_POPS | LWB200_NSTAR | LWB200_GAMMA,
     LWB200_ITER_OUTPUTS = LWB200_GAMMA | LWB200_JBAR | LWB200_INTENS | LWB200_RATES
@@ -226,6 +232,14 @@ int lwb200_formal_sol(LwB200Context* ctx, int upOnly);
  * receives the number of (column, depth) systems with an all-zero row; the
  * call then fails like the reference's throw ("Singular Matrix"). */
 int lwb200_stat_eq(LwB200Context* ctx, int32_t atom, int32_t kStart, int32_t kEnd, int32_t* nSingular);
+
+/* Replaces formal_sol_full_stokes_impl (Source/FormalStokes.cpp:664-723; FsIterationFns::full_stokes_fs,
+ * LwFormalInterface.hpp:117): polarised formal solution of every wavelength -- DELO-Bezier3
+ * (piecewise_stokes_bezier3_1d_impl, :166-340) where a polarised line is active, the scalar Bezier3
+ * solver elsewhere (as the reference, whatever formalSolver says).  Writes I and Quv, and J / dJ when
+ * updateJ; no Gamma, no rates.  Quv at wavelengths without a polarised line is 0 (the reference leaves
+ * whatever the last polarised ray left in its scratch there). */
+int lwb200_formal_sol_full_stokes(LwB200Context* ctx, int updateJ, int upOnly, double* dJMax, int64_t* dJMaxIdx);
 
 /* Replaces time_dependent_update_impl (Source/UpdatePopulations.cpp:120-151;
  * FsIterationFns::time_dep_update, LwFormalInterface.hpp:120): backward-Euler population update

@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 LINE, CONTINUUM = 0, 1
 BC_UNINITIALISED, BC_ZERO, BC_THERMALISED, BC_PERIODIC, BC_CALLABLE = range(5)
@@ -19,7 +19,7 @@ FS_NAMES = {'piecewise_linear_1d': FS_LINEAR, 'piecewise_besser_1d': FS_BESSER,
             'piecewise_bezier3_1d': FS_BEZIER3}
 
 (ATMOS, BACKGR, POPS, NSTAR, GAMMA, JBAR, PROFILE, INTENS, RATES, DEPTH, ADAMP,
- GAMMA_FINAL, PRD) = (1 << i for i in range(13))
+ GAMMA_FINAL, PRD, STOKES) = (1 << i for i in range(14))
 ALL_INPUTS = 0x7f
 ITER_INPUTS = POPS | NSTAR | GAMMA
 ITER_OUTPUTS = GAMMA | JBAR | INTENS | RATES
@@ -40,6 +40,7 @@ class LwB200Transition(C.Structure):
         ('lambda0', C.c_double), ('dopplerWidth', C.c_double),
         ('wavelength', _dp), ('alpha', _dp), ('phi', _dp), ('wphi', _dp),
         ('rhoPrd', _dp), ('aDamp', _dp), ('Rij', _dp), ('Rji', _dp), ('Qelast', _dp),
+        ('polProfiles', _dp),
     ]
 
 
@@ -62,7 +63,7 @@ class LwB200Problem(C.Structure):
         ('wavelength', _dp), ('chiBg', _dp), ('etaBg', _dp), ('scaBg', _dp),
         ('lowerBcData', _dp), ('upperBcData', _dp), ('lowerBcIdx', _ip), ('upperBcIdx', _ip),
         ('J', _dp), ('I', _dp), ('depthChi', _dp), ('depthEta', _dp), ('depthI', _dp),
-        ('atoms', C.POINTER(LwB200Atom)),
+        ('atoms', C.POINTER(LwB200Atom)), ('Quv', _dp),
     ]
 
 
@@ -128,6 +129,7 @@ def load():
     lib.lwb200_stat_eq.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     lib.lwb200_redistribute_prd.argtypes = [vp, C.c_int32, C.c_double, C.c_int32, C.POINTER(C.c_int32), _dp,
                                             _ip, _dp, C.POINTER(C.c_int64)]
+    lib.lwb200_formal_sol_full_stokes.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.lwb200_time_dep_update.argtypes = [vp, C.c_int32, _dp, C.c_double, C.c_int32, C.c_int32,
                                            C.POINTER(C.c_int32)]
     lib.lwb200_kernel_time.argtypes = [vp, C.POINTER(C.c_double)]
@@ -136,7 +138,7 @@ def load():
                                       C.POINTER(C.c_int64)]
     for name in ('device_count', 'create', 'destroy', 'set_stream', 'set_lambda_range', 'upload',
                  'download', 'sync', 'compute_profiles', 'fs_iter', 'finalise', 'dj_max',
-                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update'):
+                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes'):
         getattr(lib, 'lwb200_' + name).restype = C.c_int
     if lib.lwb200_abi_version() != ABI_VERSION:
         raise LwB200Error('liblwb200.so ABI version mismatch; rebuild')
@@ -156,5 +158,5 @@ EXPORTED_SYMBOLS = [
     'lwb200_download', 'lwb200_sync', 'lwb200_compute_profiles', 'lwb200_fs_iter',
     'lwb200_finalise', 'lwb200_dj_max', 'lwb200_formal_sol', 'lwb200_stat_eq',
     'lwb200_device_buffer', 'lwb200_work_stats', 'lwb200_kernel_time', 'lwb200_redistribute_prd',
-    'lwb200_time_dep_update',
+    'lwb200_time_dep_update', 'lwb200_formal_sol_full_stokes',
 ]

@@ -41,6 +41,7 @@ class TransitionData:
     rhoPrd: Optional[np.ndarray] = None    # [Ncol, Nlambda, Nspace]
     aDamp: Optional[np.ndarray] = None     # [Ncol, Nspace]
     Qelast: Optional[np.ndarray] = None    # [Ncol, Nspace] PRD lines
+    polProfiles: Optional[np.ndarray] = None  # [6, Ncol, Nlambda, Nrays, 2, Nspace] phiQ,U,V psiQ,U,V
     Rij: Optional[np.ndarray] = None       # [Ncol, Nspace]
     Rji: Optional[np.ndarray] = None
     name: str = ''
@@ -105,6 +106,7 @@ class Problem:
     depthChi: Optional[np.ndarray] = None     # [Ncol, Nspect, Nrays, 2, Nspace]
     depthEta: Optional[np.ndarray] = None
     depthI: Optional[np.ndarray] = None
+    Quv: Optional[np.ndarray] = None          # [Ncol, 3, Nspect, Nrays]
     ne: Optional[np.ndarray] = None      # [Ncol, Nspace] (inputs of the synthetic generator; not on the path)
     vturb: Optional[np.ndarray] = None
     nHTot: Optional[np.ndarray] = None
@@ -178,7 +180,10 @@ class Problem:
                                     lambda0=t.lambda0, wavelength=t.wavelength, Aji=t.Aji,
                                     Bji=t.Bji, Bij=t.Bij, dopplerWidth=t.dopplerWidth,
                                     alpha=t.alpha, phi=sl(t.phi), wphi=sl(t.wphi),
-                                    rhoPrd=sl(t.rhoPrd), aDamp=sl(t.aDamp), Qelast=sl(t.Qelast), Rij=sl(t.Rij),
+                                    rhoPrd=sl(t.rhoPrd), aDamp=sl(t.aDamp), Qelast=sl(t.Qelast),
+                                    polProfiles=(None if t.polProfiles is None
+                                                 else np.ascontiguousarray(t.polProfiles[:, c:c + 1])),
+                                    Rij=sl(t.Rij),
                                     Rji=sl(t.Rji), name=t.name) for t in a.trans]
             atoms.append(AtomData(name=a.name, Nlevel=a.Nlevel, trans=trans, n=sl(a.n),
                                   nStar=sl(a.nStar), nTotal=sl(a.nTotal), vBroad=sl(a.vBroad),
@@ -191,7 +196,7 @@ class Problem:
                        upperBc=self.upperBc, lowerBcData=sl(self.lowerBcData),
                        upperBcData=sl(self.upperBcData), lowerBcIdx=self.lowerBcIdx,
                        upperBcIdx=self.upperBcIdx, depthChi=sl(self.depthChi),
-                       depthEta=sl(self.depthEta), depthI=sl(self.depthI), ne=sl(self.ne),
+                       depthEta=sl(self.depthEta), depthI=sl(self.depthI), Quv=sl(self.Quv), ne=sl(self.ne),
                        vturb=sl(self.vturb), nHTot=sl(self.nHTot), meta=dict(self.meta))
 
     # ------------------------------------------------------------ marshalling
@@ -214,6 +219,7 @@ class Problem:
         p.lowerBcIdx, p.upperBcIdx = capi.iptr(self.lowerBcIdx), capi.iptr(self.upperBcIdx)
         p.J, p.I = d(self.J), d(self.I)
         p.depthChi, p.depthEta, p.depthI = d(self.depthChi), d(self.depthEta), d(self.depthI)
+        p.Quv = d(self.Quv)
         atoms = (capi.LwB200Atom * len(self.atoms))()
         for ia, a in enumerate(self.atoms):
             ca = atoms[ia]
@@ -230,6 +236,7 @@ class Problem:
                 ct.phi, ct.wphi, ct.rhoPrd, ct.aDamp = d(t.phi), d(t.wphi), d(t.rhoPrd), d(t.aDamp)
                 ct.Rij, ct.Rji = d(t.Rij), d(t.Rji)
                 ct.Qelast = d(t.Qelast)
+                ct.polProfiles = d(t.polProfiles)
             keep.append(trans)
             ca.trans = C.cast(trans, C.POINTER(capi.LwB200Transition))
             ca.n, ca.nStar, ca.nTotal = d(a.n), d(a.nStar), d(a.nTotal)

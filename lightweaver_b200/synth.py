@@ -277,6 +277,49 @@ def voigt_profile(wavelength, lambda0, aDamp, vBroad, vlosMu):
     return np.ascontiguousarray(H / (np.sqrt(np.pi) * vBroad[:, None, None, None, :]))
 
 
+QELECTRON = 1.60217733E-19
+MELECTRON = 9.1093897E-31
+
+
+def polarised_profiles(wavelength, lambda0, aDamp, vBroad, vlosMu, B, cosGamma, cos2chi, sin2chi, gEff):
+    """Transition::compute_polarised_profiles (Source/FormalStokes.cpp:9-117) for a normal Zeeman
+    triplet (alpha = -1, 0, +1, unit strengths, shifts -gEff, 0, +gEff).  Returns
+    (phi [ncol, Nl, M, 2, K], pol [6, ncol, Nl, M, 2, K] = phiQ, phiU, phiV, psiQ, psiU, psiV).
+    B: [ncol, K] Tesla; cosGamma, cos2chi, sin2chi: [ncol, M, K]."""
+    from scipy.special import wofz
+    larmor = QELECTRON / (4.0 * np.pi * MELECTRON) * (lambda0 * NM_TO_M)
+    vB = larmor * B / vBroad                                          # [ncol, K]
+    sv = 1.0 / (np.sqrt(np.pi) * vBroad)
+    vBase = (wavelength - lambda0) * CLIGHT / lambda0
+    sign = np.array([-1.0, 1.0])
+    v = (vBase[None, :, None, None, None]
+         + sign[None, None, None, :, None] * vlosMu[:, None, :, None, :]) / vBroad[:, None, None, None, :]
+    a = np.broadcast_to(aDamp[:, None, None, None, :], v.shape)
+    comp = {}
+    for alpha, shift in ((-1, -gEff), (0, 0.0), (1, gEff)):
+        w = wofz((v - shift * vB[:, None, None, None, :]) + 1j * a)
+        comp[alpha] = (w.real, w.imag)
+    phi_sb, psi_sb = comp[-1]
+    phi_pi, psi_pi = comp[0]
+    phi_sr, psi_sr = comp[1]
+    cg = cosGamma[:, None, :, None, :]
+    sin2g = 1.0 - cg**2
+    c2 = cos2chi[:, None, :, None, :]
+    s2 = sin2chi[:, None, :, None, :]
+    s = sign[None, None, None, :, None]
+    svb = sv[:, None, None, None, :]
+    phi_sigma = phi_sr + phi_sb
+    phi_delta = 0.5 * phi_pi - 0.25 * phi_sigma
+    psi_sigma = psi_sr + psi_sb
+    psi_delta = 0.5 * psi_pi - 0.25 * psi_sigma
+    phi = (phi_delta * sin2g + 0.5 * phi_sigma) * svb
+    pol = np.stack([s * phi_delta * sin2g * c2 * svb, phi_delta * sin2g * s2 * svb + 0.0 * s,
+                    s * 0.5 * (phi_sr - phi_sb) * cg * svb,
+                    s * psi_delta * sin2g * c2 * svb, psi_delta * sin2g * s2 * svb + 0.0 * s,
+                    s * 0.5 * (psi_sr - psi_sb) * cg * svb])
+    return np.ascontiguousarray(phi), np.ascontiguousarray(pol)
+
+
 def planck_nu(wavelength_nm, T):
     """B_nu [J s^-1 m^-2 sr^-1 Hz^-1] (planck_nu, Source/LwMisc.hpp:29-46)."""
     x = HC / (KBOLTZMANN * NM_TO_M) / wavelength_nm / T
@@ -332,13 +375,15 @@ def collision_matrix(atom: ModelAtom, temperature, ne, nStar, rng):
 def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, seed=SEED,
                   formal_solver=capi.FS_BEZIER3, ndepth=None, detailed: Sequence[str] = (),
                   with_profiles=True, lambda_reference=500.0, col_range=None,
-                  alloc_phi=True, prd=None) -> Problem:
+                  alloc_phi=True, prd=None, polarised=None, Bmax=0.15) -> Problem:
     """Assemble a Problem for ``atoms`` in ``ncol`` FAL C columns.  ``col_range``
     = (c0, c1) keeps only that slice of the ``ncol`` columns (one column shard of
     a multi-GPU run; every rank sees the same seeded stack).  ``with_profiles``
     False leaves phi/wphi zero (to be made on the device); ``alloc_phi`` False
     does not even allocate host phi.  ``prd``: {atom name: [line indices]} treated with
-    angle-averaged PRD (rhoPrd = 1 to start with, Qelast = the collisional part of the damping)."""
+    angle-averaged PRD (rhoPrd = 1 to start with, Qelast = the collisional part of the damping).
+    ``polarised``: {atom name: [line indices]} given Zeeman-split polarised profiles in a smooth
+    synthetic magnetic field of up to ``Bmax`` Tesla (seeded, different in every column)."""
     rng = np.random.default_rng(seed + 1)
     atm = falc_columns(ncol, perturb=perturb, seed=seed, ndepth=ndepth)
     if col_range is not None:
@@ -348,6 +393,17 @@ def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, se
     K = T.shape[1]
     muz, wmu = gauss_legendre_mu(nrays)
     vlosMu = np.ascontiguousarray(muz[None, :, None] * atm['vz'][:, None, :])
+
+    if polarised:
+        prng = np.random.default_rng(seed + 7 + (0 if col_range is None else col_range[0]))
+        zn = np.linspace(0.0, 1.0, K)[None, :]
+        amp = prng.uniform(0.3, 1.0, (ncol, 1))
+        Bfield = Bmax * amp * (0.4 + 0.6 * zn)                       # stronger with depth
+        gammaB = prng.uniform(0.2, 1.3, (ncol, 1)) + 0.3 * np.sin(2.0 * np.pi * zn + prng.uniform(0, 6, (ncol, 1)))
+        chiB = prng.uniform(0.0, np.pi, (ncol, 1)) + 0.5 * zn
+        cosGamma = np.ascontiguousarray(muz[None, :, None] * np.cos(gammaB)[:, None, :])
+        cos2chi = np.ascontiguousarray(np.broadcast_to(np.cos(2.0 * chiB)[:, None, :], cosGamma.shape))
+        sin2chi = np.ascontiguousarray(np.broadcast_to(np.sin(2.0 * chiB)[:, None, :], cosGamma.shape))
 
     # --- wavelength grids (atomic_set.py:1048-1082) ---
     grids, owners = [], []
@@ -405,7 +461,15 @@ def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, se
                 t.rhoPrd = np.ones((ncol, t.Nlambda, K))
                 t.Qelast = np.ascontiguousarray(gamma - gRad)
             t.wphi = np.zeros((ncol, K))
-            if with_profiles:
+            is_pol = bool(polarised) and line_idx in polarised.get(atom.name, ())
+            if is_pol:
+                assert with_profiles, 'polarised profiles are made on the host'
+                t.phi, t.polProfiles = polarised_profiles(t.wavelength, t.lambda0, t.aDamp, vBroad, vlosMu,
+                                                          Bfield, cosGamma, cos2chi, sin2chi, gEff=1.1)
+                wlam = t.wlambda()
+                s = np.einsum('clmdk,l,m->ck', t.phi, wlam, 0.5 * wmu)
+                t.wphi = np.ascontiguousarray(1.0 / s)
+            elif with_profiles:
                 t.phi = voigt_profile(t.wavelength, t.lambda0, t.aDamp, vBroad, vlosMu)
                 wlam = t.wlambda()
                 s = np.einsum('clmdk,l,m->ck', t.phi, wlam, 0.5 * wmu)
@@ -424,6 +488,8 @@ def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, se
                    chiBg=chiBg, etaBg=etaBg, scaBg=scaBg, atoms=atom_data, vlosMu=vlosMu,
                    formalSolver=formal_solver, ne=np.ascontiguousarray(ne),
                    vturb=np.ascontiguousarray(vturb), nHTot=np.ascontiguousarray(nHTot))
+    if polarised:
+        prob.Quv = np.zeros((ncol, 3, L, nrays))
     prob.meta = {'atoms': [a.name for a in atoms], 'perturb': perturb, 'seed': seed}
     prob.prefill_gamma()
     return prob
@@ -463,6 +529,19 @@ def tiny_problem(ncol=1, nrays=3, seed=SEED, ndepth=None, perturb=False, **kw) -
     toy = ModelAtom('Toy', 12.0, 1e-4, lev, lines, cont)
     return build_problem([toy], ncol=ncol, nrays=nrays, seed=seed, ndepth=ndepth,
                          perturb=perturb, **kw)
+
+
+def config_c5(ncol=1024, nrays=5, seed=SEED, nl=1.0, **kw) -> Problem:
+    """Config 5: magnetised stack of perturbed FAL C columns, Ca II with the 854.2 nm line
+    Zeeman-split and polarised (full Stokes)."""
+    return build_problem([ca2_atom(nl)], ncol=ncol, nrays=nrays, perturb=True, seed=seed,
+                         polarised={'Ca': [4]}, **kw)
+
+
+def tiny_stokes_problem(ncol=1, nrays=3, **kw) -> Problem:
+    """tiny_problem with its 2-1 subordinate line polarised (the two resonance lines stay scalar, so
+    polarised and unpolarised wavelengths, overlapping and not, all occur)."""
+    return tiny_problem(ncol=ncol, nrays=nrays, polarised={'Toy': [2]}, **kw)
 
 
 def tiny_prd_problem(ncol=1, nrays=3, **kw) -> Problem:

@@ -1320,3 +1320,319 @@ done:
     return rc;
 }
 
+/* ------------------------------------------------------------------------ */
+/* Full Stokes: formal_sol_full_stokes_impl (FormalStokes.cpp:664-723), stokes_fs_core
+ * (:418-661), piecewise_stokes_bezier3_1d(_impl) (:166-413). */
+
+/* stokes_K, FormalStokes.cpp:119-143; chi is [7][K] */
+static void stokes_K(int k, const double* chi, int K, double chiI, double* Km)
+{
+    memset(Km, 0, sizeof(double) * 16);
+    Km[0 * 4 + 1] = chi[(size_t)1 * K + k];
+    Km[0 * 4 + 2] = chi[(size_t)2 * K + k];
+    Km[0 * 4 + 3] = chi[(size_t)3 * K + k];
+    Km[1 * 4 + 2] = chi[(size_t)6 * K + k];
+    Km[1 * 4 + 3] = chi[(size_t)5 * K + k];
+    Km[2 * 4 + 3] = chi[(size_t)4 * K + k];
+    for (int j = 0; j < 3; ++j)
+        for (int i = j + 1; i < 4; ++i)
+        {
+            Km[j * 4 + i] /= chiI;
+            Km[i * 4 + j] = Km[j * 4 + i];
+        }
+    Km[1 * 4 + 3] *= -1.0;
+    Km[2 * 4 + 1] *= -1.0;
+    Km[3 * 4 + 2] *= -1.0;
+}
+
+/* prod(a, b, c): c(j, i) += a(k, i) * b(j, k), FormalStokes.cpp:145-153 */
+static void prod44(const double* a, const double* b, double* c)
+{
+    memset(c, 0, sizeof(double) * 16);
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i)
+            for (int k = 0; k < 4; ++k)
+                c[j * 4 + i] += a[k * 4 + i] * b[j * 4 + k];
+}
+
+/* piecewise_stokes_bezier3_1d_impl, FormalStokes.cpp:166-340.  chi [7][K], S [4][K], I [4][K]. */
+static void stokes_bezier3_sweep(int Ndep, const double* height, const double* chi, const double* S, double* I,
+                                 double zmu, int toObs, const double* Istart)
+{
+    static const double id[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    const int K = Ndep;
+    int dk = -1, k_start = Ndep - 1, k_end = 0;
+    if (!toObs)
+    {
+        dk = 1;
+        k_start = 0;
+        k_end = Ndep - 1;
+    }
+    for (int n = 0; n < 4; ++n)
+        I[(size_t)n * K + k_start] = Istart[n];
+
+    int k = k_start + dk;
+    double ds_uw = fabs(height[k] - height[k - dk]) * zmu;
+    double ds_dw = fabs(height[k + dk] - height[k]) * zmu;
+    double dx_uw = (chi[k] - chi[k - dk]) / ds_uw;
+    double dx_c = cent_deriv(ds_uw, ds_dw, chi[k - dk], chi[k], chi[k + dk]);
+    double c1 = chi[k] - (ds_uw / 3.0) * dx_c;
+    double c2 = chi[k - dk] + (ds_uw / 3.0) * dx_uw;
+    double dtau_uw = ds_uw * (chi[k] + chi[k - dk] + c1 + c2) * 0.25;
+
+    double Ku[16], dKu[16], K0[16], dK0[16], Su[4], dSu[4], S0[4], dS0[4];
+    double Kd[16], K02[16], Ku2[16], Ma[16], Mb[16], Mc[16], Md[16], V0[4], Sd[4];
+    stokes_K(k_start, chi, K, chi[k_start], Ku);
+    stokes_K(k, chi, K, chi[k], K0);
+    for (int n = 0; n < 4; ++n)
+    {
+        Su[n] = S[(size_t)n * K + k_start];
+        S0[n] = S[(size_t)n * K + k];
+    }
+    for (int n = 0; n < 4; ++n)
+    {
+        dSu[n] = (S0[n] - Su[n]) / dtau_uw;
+        for (int m = 0; m < 4; ++m)
+            dKu[n * 4 + m] = (K0[n * 4 + m] - Ku[n * 4 + m]) / dtau_uw;
+    }
+    double ds_dw2 = 0.0, dtau_dw = 0.0, dx_dw = 0.0;
+    memset(Kd, 0, sizeof(Kd));
+    memset(Sd, 0, sizeof(Sd));
+    memset(dK0, 0, sizeof(dK0));
+    memset(dS0, 0, sizeof(dS0));
+    for (; k != k_end + dk; k += dk)
+    {
+        if (k == k_end)
+        {
+            for (int n = 0; n < 4; ++n)
+            {
+                dS0[n] = (S0[n] - Su[n]) / dtau_uw;
+                for (int m = 0; m < 4; ++m)
+                    dK0[n * 4 + m] = (K0[n * 4 + m] - Ku[n * 4 + m]) / dtau_uw;
+            }
+        }
+        else
+        {
+            if (k_end - k == dk)
+                dx_dw = (chi[k + dk] - chi[k]) / ds_dw;
+            else
+            {
+                ds_dw2 = fabs(height[k + 2 * dk] - height[k + dk]) * zmu;
+                dx_dw = cent_deriv(ds_dw, ds_dw2, chi[k], chi[k + dk], chi[k + 2 * dk]);
+            }
+            c1 = chi[k] + (ds_dw / 3.0) * dx_c;
+            c2 = chi[k + dk] - (ds_dw / 3.0) * dx_dw;
+            dtau_dw = ds_dw * (chi[k] + chi[k + dk] + c1 + c2) * 0.25;
+            stokes_K(k + dk, chi, K, chi[k + dk], Kd);
+            for (int n = 0; n < 4; ++n)
+                Sd[n] = S[(size_t)n * K + k + dk];
+            for (int q = 0; q < 16; ++q)
+                dK0[q] = cent_deriv(dtau_uw, dtau_dw, Ku[q], K0[q], Kd[q]);
+            for (int q = 0; q < 4; ++q)
+                dS0[q] = cent_deriv(dtau_uw, dtau_dw, Su[q], S0[q], Sd[q]);
+        }
+        prod44(Ku, Ku, Ku2);
+        prod44(K0, K0, K02);
+        double alpha, beta, gamma, delta, edt;
+        bezier3_coeffs(dtau_uw, &alpha, &beta, &gamma, &delta, &edt);
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i)
+            {
+                const int q = j * 4 + i;
+                double d = dtau_uw / 3.0 * (Ku2[q] + Ku[q] - dKu[q]) - Ku[q];
+                double e = dtau_uw / 3.0 * (K02[q] + K0[q] - dK0[q]) + K0[q];
+                Md[q] = id[j][i] + beta * K0[q] + delta * e;
+                Ma[q] = edt * id[j][i] - alpha * Ku[q] + gamma * d;
+                Mb[q] = alpha * id[j][i] + gamma * (id[j][i] - (dtau_uw / 3.0) * Ku[q]);
+                Mc[q] = beta * id[j][i] + delta * (id[j][i] + (dtau_uw / 3.0) * K0[q]);
+            }
+        for (int i = 0; i < 4; ++i)
+        {
+            V0[i] = 0.0;
+            for (int j = 0; j < 4; ++j)
+                V0[i] += Ma[i * 4 + j] * I[(size_t)j * K + k - dk] + Mb[i * 4 + j] * Su[j] + Mc[i * 4 + j] * S0[j];
+            V0[i] += (dtau_uw / 3.0) * (gamma * dSu[i] - delta * dS0[i]);
+        }
+        lwo_solve_lin_eq(4, Md, V0, 1);
+        for (int i = 0; i < 4; ++i)
+            I[(size_t)i * K + k] = V0[i];
+        memcpy(Su, S0, sizeof(Su));
+        memcpy(S0, Sd, sizeof(S0));
+        memcpy(dSu, dS0, sizeof(dSu));
+        memcpy(Ku, K0, sizeof(Ku));
+        memcpy(K0, Kd, sizeof(K0));
+        memcpy(dKu, dK0, sizeof(dKu));
+        dtau_uw = dtau_dw;
+        ds_uw = ds_dw;
+        ds_dw = ds_dw2;
+        dx_uw = dx_c;
+        dx_c = dx_dw;
+    }
+}
+
+int lwo_full_stokes(const LwB200Problem* p, int col, int updateJ, int upOnly, double* dJMaxOut, int64_t* dJMaxIdx)
+{
+    const int K = p->Nspace, M = p->Nrays, L = p->Nspect;
+    if (!p->Quv)
+        return 1;
+    const double* h = p->height + (size_t)col * K;
+    const double* T = p->temperature + (size_t)col * K;
+    Scratch* s = scratch_new(p);
+    double* chiTot = (double*)calloc((size_t)7 * K, sizeof(double));
+    double* etaTot = (double*)calloc((size_t)4 * K, sizeof(double));
+    double* S = (double*)calloc((size_t)4 * K, sizeof(double));
+    double* I = (double*)calloc((size_t)4 * K, sizeof(double)); /* persists over rays, as in the reference */
+    double dJMax = 0.0;
+    int64_t idx = 0;
+    for (int la = 0; la < L; ++la)
+    {
+        double* J = p->J + ((size_t)col * L + la) * K;
+        const double* bgChi = p->chiBg + ((size_t)col * L + la) * K;
+        const double* bgEta = p->etaBg + ((size_t)col * L + la) * K;
+        const double* bgSca = p->scaBg + ((size_t)col * L + la) * K;
+        const double wav = p->wavelength[la];
+        if (updateJ)
+        {
+            memcpy(s->JDag, J, sizeof(double) * K);
+            memset(J, 0, sizeof(double) * K);
+        }
+        for (int a = 0; a < p->Natom; ++a)
+            setup_wavelength(p, col, a, la, s);
+        const int contOnly = continua_only(p, la);
+        const int toObsStart = upOnly ? 1 : 0;
+        for (int mu = 0; mu < M; ++mu)
+            for (int toObs = toObsStart; toObs < 2; ++toObs)
+            {
+                /* NOTE: as in the reference, polarisedFrequency is only (re)determined when the
+                 * opacities are gathered; a continua-only wavelength has no polarised line. */
+                static int polarisedFrequency;
+                if (!contOnly || (mu == 0 && toObs == toObsStart))
+                {
+                    polarisedFrequency = 0;
+                    memset(chiTot, 0, sizeof(double) * 7 * K);
+                    memset(etaTot, 0, sizeof(double) * 4 * K);
+                    for (int pass = 0; pass < 2; ++pass) /* active atoms, then detailed ones */
+                        for (int a = 0; a < p->Natom; ++a)
+                        {
+                            const LwB200Atom* at = &p->atoms[a];
+                            if ((at->detailedStatic != 0) != (pass == 1))
+                                continue;
+                            const double* n = at->n + (size_t)col * at->Nlevel * K;
+                            for (int kr = 0; kr < at->Ntrans; ++kr)
+                            {
+                                const LwB200Transition* t = &at->trans[kr];
+                                if (!is_active(t, la))
+                                    continue;
+                                uv(p, col, a, kr, la, mu, toObs, s);
+                                const int Nl = t->Nred - t->Nblue, lt = la - t->Nblue;
+                                const size_t per = (size_t)Nl * M * 2 * K, arr = (size_t)p->Ncol * per;
+                                const size_t off = (size_t)col * per + (((size_t)lt * M + mu) * 2 + toObs) * K;
+                                for (int k = 0; k < K; ++k)
+                                {
+                                    double chi = n[(size_t)t->i * K + k] * s->Vij[k] - n[(size_t)t->j * K + k] * s->Vji[k];
+                                    double eta = n[(size_t)t->j * K + k] * s->Uji[k];
+                                    chiTot[k] += chi;
+                                    etaTot[k] += eta;
+                                    if (t->type == LWB200_LINE && t->polProfiles)
+                                    {
+                                        polarisedFrequency = 1;
+                                        const double phi = t->phi[off + k];
+                                        const double* pol = t->polProfiles + off + k;
+                                        double chiNoProfile = chi / phi;
+                                        chiTot[(size_t)1 * K + k] += chiNoProfile * pol[0 * arr];
+                                        chiTot[(size_t)2 * K + k] += chiNoProfile * pol[1 * arr];
+                                        chiTot[(size_t)3 * K + k] += chiNoProfile * pol[2 * arr];
+                                        chiTot[(size_t)4 * K + k] += chiNoProfile * pol[3 * arr];
+                                        chiTot[(size_t)5 * K + k] += chiNoProfile * pol[4 * arr];
+                                        chiTot[(size_t)6 * K + k] += chiNoProfile * pol[5 * arr];
+                                        double etaNoProfile = eta / phi;
+                                        etaTot[(size_t)1 * K + k] += etaNoProfile * pol[0 * arr];
+                                        etaTot[(size_t)2 * K + k] += etaNoProfile * pol[1 * arr];
+                                        etaTot[(size_t)3 * K + k] += etaNoProfile * pol[2 * arr];
+                                    }
+                                }
+                            }
+                        }
+                    for (int k = 0; k < K; ++k)
+                    {
+                        chiTot[k] += bgChi[k];
+                        S[k] = (etaTot[k] + bgEta[k] + bgSca[k] * s->JDag[k]) / chiTot[k];
+                    }
+                    if (polarisedFrequency)
+                        for (int n = 1; n < 4; ++n)
+                            for (int k = 0; k < K; ++k)
+                                S[(size_t)n * K + k] = etaTot[(size_t)n * K + k] / chiTot[k];
+                }
+                if (!polarisedFrequency)
+                {
+                    lwo_solve_ray(2, K, h, T, chiTot, S, p->muz[mu], toObs, wav, p->lowerBc, p->upperBc,
+                                  bc_value(p, col, la, mu, toObs), I, NULL);
+                }
+                else
+                {
+                    /* piecewise_stokes_bezier3_1d, :344-413 */
+                    const double zmu = 1.0 / p->muz[mu];
+                    int dk = -1, kStart = K - 1;
+                    if (!toObs)
+                    {
+                        dk = 1;
+                        kStart = 0;
+                    }
+                    double dtau_uw = 0.5 * zmu * (chiTot[kStart] + chiTot[kStart + dk]) * fabs(h[kStart] - h[kStart + dk]);
+                    double Iupw[4] = {0.0, 0.0, 0.0, 0.0};
+                    if (toObs)
+                    {
+                        if (p->lowerBc == LWB200_BC_THERMALISED)
+                        {
+                            double Bnu[2];
+                            planck_nu(2, &T[K - 2], wav, Bnu);
+                            Iupw[0] = Bnu[1] - (Bnu[0] - Bnu[1]) / dtau_uw;
+                        }
+                        else if (p->lowerBc == LWB200_BC_CALLABLE)
+                            Iupw[0] = bc_value(p, col, la, mu, toObs);
+                    }
+                    else
+                    {
+                        if (p->upperBc == LWB200_BC_THERMALISED)
+                        {
+                            double Bnu[2];
+                            planck_nu(2, &T[0], wav, Bnu);
+                            Iupw[0] = Bnu[0] - (Bnu[1] - Bnu[0]) / dtau_uw;
+                        }
+                        else if (p->upperBc == LWB200_BC_CALLABLE)
+                            Iupw[0] = bc_value(p, col, la, mu, toObs);
+                    }
+                    stokes_bezier3_sweep(K, h, chiTot, S, I, zmu, toObs, Iupw);
+                }
+                p->I[((size_t)col * L + la) * M + mu] = I[0];
+                for (int q = 0; q < 3; ++q)
+                    p->Quv[(((size_t)col * 3 + q) * L + la) * M + mu] = I[(size_t)(q + 1) * K];
+                if (updateJ)
+                {
+                    const double wmu = p->wmu[mu];
+                    for (int k = 0; k < K; ++k)
+                        J[k] += 0.5 * wmu * I[k];
+                }
+            }
+        if (updateJ)
+        {
+            double dJ = 0.0;
+            for (int k = 0; k < K; ++k)
+                dJ = dmax(fabs(1.0 - s->JDag[k] / J[k]), dJ);
+            if (dJMax < dJ)
+            {
+                dJMax = dJ;
+                idx = la;
+            }
+        }
+    }
+    free(chiTot);
+    free(etaTot);
+    free(S);
+    free(I);
+    scratch_free(s);
+    if (dJMaxOut) *dJMaxOut = updateJ ? dJMax : 0.0;
+    if (dJMaxIdx) *dJMaxIdx = updateJ ? idx : 0;
+    return 0;
+}
+

@@ -48,6 +48,12 @@ int lwo_solve_lin_eq(int N, double* A, double* b, int improve);
 int lwo_fs_iter_columns(const LwB200Problem* p, int col0, int ncol, unsigned flags,
                         int withStatEq, int nthreads);
 
+/* formal_sol_full_stokes_impl (FormalStokes.cpp:664-723) on column `col`: DELO-Bezier3 at wavelengths
+ * with a polarised line, scalar Bezier3 elsewhere; writes I, Quv (incl. the reference's stale values
+ * at unpolarised wavelengths: whatever the last polarised ray left in I(1..3, 0)) and, with updateJ,
+ * J and dJ (argmax index). */
+int lwo_full_stokes(const LwB200Problem* p, int col, int updateJ, int upOnly, double* dJMax, int64_t* dJMaxIdx);
+
 /* time_dependent_update_impl (UpdatePopulations.cpp:120-151) of atom `atom` on column `col`;
  * nOld is [Ncol][Nlevel][Nspace].  Returns 1 for "Singular Matrix". */
 int lwo_time_dep_update(const LwB200Problem* p, int col, int atom, const double* nOld, double dt);

@@ -37,6 +37,7 @@ def load():
     lib.lwo_stat_eq.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.lwo_solve_lin_eq.argtypes = [C.c_int, dp, dp, C.c_int]
     lib.lwo_fs_iter_columns.argtypes = [vp, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int]
+    lib.lwo_full_stokes.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, i64p]
     lib.lwo_time_dep_update.argtypes = [vp, C.c_int, C.c_int, dp, C.c_double]
     lib.lwo_redistribute_prd.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp,
                                          C.POINTER(C.c_int), dp, i64p]
@@ -69,6 +70,11 @@ class OracleContext:
         rc = self.lib.lwo_stat_eq(C.byref(self._cs), self.col, atom, kStart, kEnd, C.byref(ns))
         if rc != 0:
             raise RuntimeError('Singular Matrix')
+
+    def full_stokes(self, updateJ=False, upOnly=True):
+        dJ, idx = C.c_double(0.0), C.c_int64(0)
+        assert self.lib.lwo_full_stokes(C.byref(self._cs), self.col, int(updateJ), int(upOnly), C.byref(dJ), C.byref(idx)) == 0
+        return dJ.value, idx.value
 
     def time_dep_update(self, atom, nOld, dt):
         nOld = np.ascontiguousarray(nOld, dtype=np.float64)

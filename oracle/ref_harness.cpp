@@ -126,6 +126,11 @@ int lwref_create(const LwB200Problem* p, int col, const char* scheme, int Nthrea
         s.wavelength = F64View(const_cast<f64*>(p->wavelength), L);
         s.I = F64View3D(p->I + c * L * M, L, M, 1);
         s.J = F64View2D(p->J + c * L * K, L, K);
+        if (p->Quv)
+        {
+            s.Quv = F64View4D(p->Quv + c * 3 * L * M, 3, L, M, 1);
+            a.B = F64View(h->vzDummy.data(), K); // formal_sol_full_stokes_impl only checks that B exists
+        }
 
         auto& bg = h->background;
         bg.chi = F64View2D(const_cast<f64*>(p->chiBg) + c * L * K, L, K);
@@ -205,6 +210,18 @@ int lwref_create(const LwB200Problem* p, int col, const char* scheme, int Nthrea
                         t.rhoPrd = F64View2D(const_cast<f64*>(pt.rhoPrd) + c * Nl * K, Nl, K);
                     if (pt.Qelast)
                         t.Qelast = F64View(const_cast<f64*>(pt.Qelast) + c * K, K);
+                    if (pt.polProfiles)
+                    {
+                        const i64 per = Nl * M * 2 * K, arr = (i64)p->Ncol * per;
+                        f64* base = const_cast<f64*>(pt.polProfiles) + c * per;
+                        t.polarised = true;
+                        t.phiQ = F64View4D(base + 0 * arr, Nl, M, 2, K);
+                        t.phiU = F64View4D(base + 1 * arr, Nl, M, 2, K);
+                        t.phiV = F64View4D(base + 2 * arr, Nl, M, 2, K);
+                        t.psiQ = F64View4D(base + 3 * arr, Nl, M, 2, K);
+                        t.psiU = F64View4D(base + 4 * arr, Nl, M, 2, K);
+                        t.psiV = F64View4D(base + 5 * arr, Nl, M, 2, K);
+                    }
                 }
                 else
                 {
@@ -314,6 +331,24 @@ int lwref_formal_sol(LwRefHandle* hh, int upOnly)
     try
     {
         formal_sol(*h->ctx, upOnly != 0, ExtraParams{});
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// formal_sol_full_stokes (LwContext.single_stokes_fs, LwMiddleLayer.pyx): polarised formal solution.
+int lwref_full_stokes(LwRefHandle* hh, int updateJ, int upOnly, double* dJMax, int64_t* dJMaxIdx)
+{
+    auto* h = (LwRef*)hh;
+    try
+    {
+        IterationResult r = formal_sol_full_stokes(*h->ctx, updateJ != 0, upOnly != 0, ExtraParams{});
+        if (dJMax) *dJMax = r.dJMax;
+        if (dJMaxIdx) *dJMaxIdx = r.dJMaxIdx;
         return 0;
     }
     catch (const std::exception& e)

@@ -60,6 +60,7 @@ def load():
     lib.lwref_fs_iter.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int64)]
     lib.lwref_formal_sol.argtypes = [vp, C.c_int]
     lib.lwref_stat_eq.argtypes = [vp]
+    lib.lwref_full_stokes.argtypes = [vp, C.c_int, C.c_int, dp, C.POINTER(C.c_int64)]
     lib.lwref_time_dep_update.argtypes = [vp, C.c_int, dp, C.c_double]
     lib.lwref_redistribute_prd.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp,
                                            C.POINTER(C.c_int), dp, C.POINTER(C.c_int64)]
@@ -103,6 +104,11 @@ class RefContext:
 
     def stat_eq(self):
         _check(self.lib.lwref_stat_eq(self.h))
+
+    def full_stokes(self, updateJ=False, upOnly=True):
+        dJ, idx = C.c_double(0.0), C.c_int64(0)
+        _check(self.lib.lwref_full_stokes(self.h, int(updateJ), int(upOnly), C.byref(dJ), C.byref(idx)))
+        return dJ.value, idx.value
 
     def time_dep_update(self, activeIdx, nOld, dt):
         """nOld: [Nlevel, Nspace] of this context's column"""
