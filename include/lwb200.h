@@ -237,8 +237,10 @@ int lwb200_stat_eq(LwB200Context* ctx, int32_t atom, int32_t kStart, int32_t kEn
  * LwFormalInterface.hpp:117): polarised formal solution of every wavelength -- DELO-Bezier3
  * (piecewise_stokes_bezier3_1d_impl, :166-340) where a polarised line is active, the scalar Bezier3
  * solver elsewhere (as the reference, whatever formalSolver says).  Writes I and Quv, and J / dJ when
- * updateJ; no Gamma, no rates.  Quv at wavelengths without a polarised line is 0 (the reference leaves
- * whatever the last polarised ray left in its scratch there). */
+ * updateJ; no Gamma, no rates.  As in the reference, a pass that does not update J has no scattering
+ * term in its source function (stokes_fs_core fills JDag only under updateJ, FormalStokes.cpp:431-441).
+ * Quv at wavelengths without a polarised line is 0 (the reference leaves whatever the last polarised
+ * ray left in its scratch there). */
 int lwb200_formal_sol_full_stokes(LwB200Context* ctx, int updateJ, int upOnly, double* dJMax, int64_t* dJMaxIdx);
 
 /* Replaces time_dependent_update_impl (Source/UpdatePopulations.cpp:120-151;

@@ -186,6 +186,23 @@ class Context:
         self.download(capi.INTENS)
         return IterationUpdate()
 
+    def single_stokes_fs(self, recompute=False, updateJ=False, upOnly=True, extraParams=None):
+        """lw.Context.single_stokes_fs (LwMiddleLayer.pyx:3605-3645): full Stokes formal solution of
+        every wavelength from the current populations; I and Quv (and J when updateJ) are back in
+        the numpy buffers on return.  The polarised profiles are an input of this path (the
+        reference's setup_stokes / compute_polarised_profiles made them); recompute=True sends
+        them again."""
+        if self.problem.Quv is None:
+            raise capi.LwB200Error('single_stokes_fs: the problem has no polarised line')
+        first = not getattr(self, '_stokes_sent', False)
+        self.upload(capi.POPS | capi.JBAR | (capi.STOKES if (first or recompute) else 0))
+        self._stokes_sent = True
+        dJ, idx = C.c_double(0.0), C.c_int64(0)
+        capi.check(self.lib.lwb200_formal_sol_full_stokes(self._h, int(updateJ), int(upOnly), C.byref(dJ),
+                                                          C.byref(idx)))
+        self.download(capi.INTENS | capi.STOKES | (capi.JBAR if updateJ else 0))
+        return IterationUpdate(updatedJ=bool(updateJ), dJMax=dJ.value, dJMaxIdx=idx.value % self.problem.Nspect)
+
     def prd_redistribute(self, maxIter=3, tol=1e-2, extraParams=None):
         """lw.Context.prd_redistribute (LwMiddleLayer.pyx:3647-3684): update the emission-profile
         ratio rho of every angle-averaged PRD line from the current J, populations and rates, then

@@ -6,6 +6,7 @@
 #include "lwb200_profiles.cuh"
 #include "lwb200_pipeline.cuh"
 #include "lwb200_prd.cuh"
+#include "lwb200_stokes.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -119,12 +120,15 @@ struct PipelineLists
     int nKindLam[4];
     const unsigned char* laMask;
     int prdOnly;
+    const int* polLam; // full Stokes pass: wavelengths with a polarised line (stokes_kernel)
+    int nPolLam;
 };
 
 struct LwB200Context
 {
     bool prdPass = false;
     PipelineLists prdPl{};
+    int stokesFsMode = 0; // != 0: the pass is a full-Stokes formal solution (always Bezier3)
     Pinned stN, stNStar, stNTotal, stVBroad, stPrefill, stGamma, stNOut, stGammaOut, stRates;
     std::vector<Pending> pending;
     std::vector<void*> registered;
@@ -164,6 +168,13 @@ struct LwB200Context
     long long cTot = 0;
     int nKindLamPrd[4] = {0, 0, 0, 0}, nListMomentPrd = 0, prdListsFor = -1;
     bool prdUploaded = false;
+    // full Stokes (lwb200_formal_sol_full_stokes): pool of the polarised lines' six extra profiles
+    std::vector<long long> transPolOff; // per global transition, -1: not polarised
+    long long polTot = 0;
+    DevBuf<double> pol, Quv, Jdag;
+    DevBuf<int> dPolLam, dKindLamUnpol[4];
+    int nPolLam = 0, nKindLamUnpol[4] = {0, 0, 0, 0};
+    bool stokesLists = false, stokesUploaded = false;
     size_t smemGamma = 0;
     int KC = 0;
     int Ntile = 0;
@@ -451,6 +462,14 @@ int build_plan(LwB200Context* c)
         c->NCH = 4;
     }
 
+    // polarised lines: six extra profile arrays each, [6][Ncol][Nl][M][2][K] as on the host
+    c->transPolOff.assign(NT, -1);
+    for (int g = 0; g < NT; ++g)
+        if (c->devTrans[g].type == 0 && c->trans[g].t.polProfiles)
+        {
+            c->transPolOff[g] = c->polTot;
+            c->polTot += 6LL * c->devTrans[g].phiColStride * p.Ncol;
+        }
     // per-wavelength line slots and moment rows of the pipeline
     std::vector<LambdaLine> lamLine((size_t)L * 3);
     std::vector<int> momOff(L, 0);
@@ -477,6 +496,8 @@ int build_plan(LwB200Context* c)
             ll.levI = d.levI;
             ll.levJ = d.levJ;
             ll.lineIdx = d.lineIdx;
+            ll.polOff = c->transPolOff[g] >= 0 ? c->transPolOff[g] + (long long)lt * M * 2 * K : -1;
+            ll.polArr = d.phiColStride * p.Ncol;
             ll.slot = -1;
             for (int e = laOff[la]; e < laOff[la] + laCnt[la]; ++e)
                 if (entries[e].trans == g)
@@ -557,6 +578,14 @@ int build_plan(LwB200Context* c)
     }
     if (p.vlosMu && c->vlosMu.alloc(ncol * M * K))
         return 1;
+    if (c->polTot > 0)
+    {
+        if (!p.Quv)
+            return fail("polarised lines without a Quv output array");
+        if (c->pol.alloc((size_t)c->polTot) || c->Quv.alloc(ncol * 3 * L * M) || c->Jdag.alloc(ncol * L * K))
+            return 1;
+        CU(cudaMemset(c->Quv.p, 0, c->Quv.n * sizeof(double)));
+    }
     if (!c->prdLines.empty())
     {
         const size_t np = c->prdLines.size();
@@ -665,6 +694,7 @@ int build_plan(LwB200Context* c)
     P.chiC = c->chiC.p; P.etaC = c->etaC.p; P.mom = c->mom.p; P.momOff = c->dMomOff.p;
     P.laNLines = c->dLaNLines.p; P.lamLine = c->dLamLine.p; P.momRows = c->momRows;
     P.phiAsym = c->dPhiAsym.p;
+    P.pol = c->pol.p; P.Quv = c->Quv.p; P.Jdag = c->Jdag.p;
     return 0;
 }
 
@@ -831,6 +861,15 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }
+        if (pl.nPolLam > 0)
+        {
+            // polarised wavelengths: one thread per ray, concurrently with the scalar ray kernels
+            const int nRays = pl.nPolLam * 2 * c->prob.Nrays;
+            stokes_kernel<<<dim3((nRays + 127) / 128, nb), 128, 0, c->stream>>>(c->P, pl.polLam, pl.nPolLam, colBase,
+                                                                                (fsMode & 2) ? 1 : 0, (fsMode & 4) ? 1 : 0);
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
+        }
         for (int q = 0; q < nside; ++q)
         {
             CU(cudaEventRecord(c->evJoin[q], c->sideStream[q]));
@@ -875,7 +914,8 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
     if (MODE == MODE_ITER && !c->forceDirect)
     {
         // wavelengths with more than three overlapping lines go through the general kernel
-        if (launch_pipeline<NCH, SOLVER, false>(c, c->prdPass ? c->prdPl : full_lists(c), lambdaIterate, storeDepth, 0))
+        if (launch_pipeline<NCH, SOLVER, false>(c, c->prdPass ? c->prdPl : full_lists(c), lambdaIterate, storeDepth,
+                                                c->stokesFsMode))
             return 1;
         if (c->nListDirect > 0 && !c->prdPass)
         {
@@ -917,7 +957,7 @@ int launch_fs_long(LwB200Context* c, int lambdaIterate, int upOnly, int storeDep
     if (c->forceDirect)
         return fail("the general per-ray kernel is limited to Nspace <= 128");
     CU(cudaEventRecord(c->evK0, c->stream));
-    const int fsMode = MODE == MODE_ITER ? 0 : (upOnly ? 3 : 1);
+    const int fsMode = MODE == MODE_ITER ? c->stokesFsMode : (upOnly ? 3 : 1);
     if (launch_pipeline<4, SOLVER, true>(c, c->prdPass ? c->prdPl : full_lists(c), lambdaIterate, storeDepth, fsMode))
         return 1;
     CU(cudaEventRecord(c->evK1, c->stream));
@@ -928,7 +968,7 @@ int launch_fs_long(LwB200Context* c, int lambdaIterate, int upOnly, int storeDep
 template <int NCH, int MODE>
 int launch_fs_s(LwB200Context* c, int li, int uo, int sd)
 {
-    switch (c->prob.formalSolver)
+    switch (c->stokesFsMode ? (int)LWB200_FS_BEZIER3 : c->prob.formalSolver) // (full Stokes is always Bezier3)
     {
 #ifndef LWB200_DEV_FAST_BUILD // (variant timing builds instantiate NCH = 3 / bezier3 only)
     case LWB200_FS_LINEAR: return launch_fs_t<NCH, 0, MODE>(c, li, uo, sd);
@@ -946,7 +986,7 @@ int launch_fs(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
         return 1;
     if (c->prob.Nspace > 128)
     {
-        switch (c->prob.formalSolver)
+        switch (c->stokesFsMode ? (int)LWB200_FS_BEZIER3 : c->prob.formalSolver)
         {
 #ifndef LWB200_DEV_FAST_BUILD
         case LWB200_FS_LINEAR: return launch_fs_long<0, MODE>(c, lambdaIterate, upOnly, storeDepth);
@@ -1110,6 +1150,12 @@ int lwb200_destroy(LwB200Context* c)
     c->cmat.release();
     c->rhoPrev.release();
     c->nOld.release();
+    c->pol.release();
+    c->Quv.release();
+    c->Jdag.release();
+    c->dPolLam.release();
+    for (int q = 0; q < 4; ++q)
+        c->dKindLamUnpol[q].release();
     c->prdMax.release();
     c->prdIdx.release();
     for (int q = 0; q < 4; ++q)
@@ -1330,6 +1376,14 @@ int lwb200_upload(LwB200Context* c, uint32_t mask)
                 return 1;
         }
     }
+    if ((mask & LWB200_STOKES) && c->polTot > 0)
+    {
+        for (size_t g = 0; g < c->trans.size(); ++g)
+            if (c->transPolOff[g] >= 0)
+                CU(cudaMemcpyAsync(c->pol.p + c->transPolOff[g], c->trans[g].t.polProfiles,
+                                   (size_t)6 * c->devTrans[g].phiColStride * ncol * D, H2D, s));
+        c->stokesUploaded = true;
+    }
     if ((mask & LWB200_PRD) && !c->prdLines.empty())
     {
         for (size_t q = 0; q < c->prdLines.size(); ++q)
@@ -1372,6 +1426,8 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
         c->fetched = false;
         mask &= ~(uint32_t)(LWB200_JBAR | LWB200_INTENS);
     }
+    if ((mask & LWB200_STOKES) && c->polTot > 0)
+        CU(cudaMemcpyAsync(p.Quv, c->Quv.p, ncol * 3 * L * M * D, D2H, s));
     if (mask & LWB200_PRD)
         for (const DevPrdLine& ln : c->prdLines)
         {
@@ -1754,6 +1810,103 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
     }
     if (nIterOut)
         *nIterOut = iter;
+    return 0;
+}
+
+
+// formal_sol_full_stokes_impl (FormalStokes.cpp:664-723) on the device-resident state.
+int lwb200_formal_sol_full_stokes(LwB200Context* c, int updateJ, int upOnly, double* dJMax, int64_t* dJMaxIdx)
+{
+    CU(cudaSetDevice(c->device));
+    if (!c->nstarUploaded)
+        return fail("lwb200_formal_sol_full_stokes: inputs have not been uploaded (lwb200_upload)");
+    if (c->polTot == 0)
+        return fail("lwb200_formal_sol_full_stokes: the problem has no polarised line");
+    if (!c->stokesUploaded)
+        return fail("lwb200_formal_sol_full_stokes: polarised profiles have not been uploaded (LWB200_STOKES)");
+    if (c->laLo != 0 || c->laHi != c->prob.Nspect)
+        return fail("lwb200_formal_sol_full_stokes: not available on a wavelength shard");
+    if (c->prob.Nspace < 3)
+        return fail("lwb200_formal_sol_full_stokes: needs at least three depth points");
+    if (refresh_tile_lists(c))
+        return 1;
+    const LwB200Problem& p = c->prob;
+    const int L = p.Nspect;
+    if (!c->stokesLists)
+    {
+        std::vector<int> pol, unpol[4];
+        for (int la = 0; la < L; ++la)
+        {
+            bool isPol = false;
+            for (size_t g = 0; g < c->trans.size(); ++g)
+                if (c->transPolOff[g] >= 0 && la >= c->devTrans[g].Nblue && la < c->devTrans[g].Nred)
+                    isPol = true;
+            if (isPol)
+            {
+                if (c->laKind[la] >= 4)
+                    return fail("lwb200_formal_sol_full_stokes: a polarised line overlaps more than two other lines");
+                pol.push_back(la);
+            }
+            else if (c->laKind[la] < 4)
+                unpol[c->laKind[la]].push_back(la);
+            else
+                return fail("lwb200_formal_sol_full_stokes: more than three overlapping lines at one wavelength");
+        }
+        if (c->dPolLam.upload(pol))
+            return 1;
+        c->nPolLam = (int)pol.size();
+        for (int q = 0; q < 4; ++q)
+        {
+            if (c->dKindLamUnpol[q].upload(unpol[q]))
+                return 1;
+            c->nKindLamUnpol[q] = (int)unpol[q].size();
+        }
+        c->stokesLists = true;
+    }
+    cudaStream_t s = c->stream;
+    c->forceDirect = false;
+    c->fetchEarly = false;
+    c->lastLaunches = 0;
+    CU(cudaMemsetAsync(c->Quv.p, 0, c->Quv.n * sizeof(double), s));
+    if (updateJ)
+    {
+        // the polarised rays add into J atomically: keep J-dagger aside and clear their rows
+        CU(cudaMemcpyAsync(c->Jdag.p, c->J.p, c->J.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        stokes_zero_rows_kernel<<<dim3(c->nPolLam, p.Ncol), 128, 0, s>>>(c->P, c->dPolLam.p, c->nPolLam);
+        CU(cudaGetLastError());
+        c->lastLaunches += 1;
+    }
+    PipelineLists pl = full_lists(c);
+    for (int q = 0; q < 4; ++q)
+    {
+        pl.kindLam[q] = c->dKindLamUnpol[q].p;
+        pl.nKindLam[q] = c->nKindLamUnpol[q];
+    }
+    pl.polLam = c->dPolLam.p;
+    pl.nPolLam = c->nPolLam;
+    c->prdPass = true; // (custom lists; also keeps the general kernel out)
+    c->prdPl = pl;
+    c->stokesFsMode = (updateJ ? 4 : (1 | 8)) | (upOnly ? 2 : 0);
+    const int rc = launch_fs<MODE_ITER>(c, 0, 0, 0);
+    c->prdPass = false;
+    c->stokesFsMode = 0;
+    if (rc)
+        return 1;
+    if (updateJ)
+    {
+        stokes_dj_kernel<<<dim3(c->nPolLam, p.Ncol), 32, 0, s>>>(c->P, c->dPolLam.p, c->nPolLam);
+        CU(cudaGetLastError());
+        c->lastLaunches += 1;
+        if (dJMax || dJMaxIdx)
+            return lwb200_dj_max(c, dJMax, dJMaxIdx);
+    }
+    else
+    {
+        if (dJMax)
+            *dJMax = 0.0;
+        if (dJMaxIdx)
+            *dJMaxIdx = 0;
+    }
     return 0;
 }
 

@@ -77,6 +77,8 @@ struct LambdaLine
     int slot;               // accumulator slot of the line within the wavelength's tile
     double lambda0, Bij, Bji_Bij, Aji_Bji;
     double wlaS;            // wlambda * 4 pi / (h c)  (times wphi(k) gives wla)
+    long long polOff;       // polarised line: element offset of phiQ(lt, 0, 0, 0) of column 0 in the pol pool; else -1
+    long long polArr;       // stride between the six polarised profile arrays (phiQ, phiU, phiV, psiQ, psiU, psiV)
 };
 
 struct DevProblem
@@ -117,6 +119,10 @@ struct DevProblem
     const LambdaLine* lamLine; // [L][3]
     int momRows;
     const int* phiAsym;       // 0: phi(.., dir 0, .) == phi(.., dir 1, .) everywhere (static atmosphere)
+    // full Stokes (lwb200_stokes.cuh)
+    const double* pol;        // polarised profile pool
+    double* Quv;              // [Ncol][3][L][M]
+    double* Jdag;             // [Ncol][L][K] copy of J taken before a J-updating Stokes pass
 };
 
 // U, V for one transition at one (wavelength, ray, depth): Transition::uv

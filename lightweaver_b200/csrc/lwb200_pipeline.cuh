@@ -124,8 +124,14 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
            int lambdaIterate, int storeDepth, int fsMode)
 {
     // fsMode: 0 Gamma iteration; 1 formal solution only (formal_sol_impl, :721-781: emergent I,
-    // nothing else written); 3 the same with up-going rays only (upOnly)
+    // nothing else written); bit 1 (2): up-going rays only (upOnly); 4: J, dJ and I but no moments
+    // (the unpolarised wavelengths of a J-updating full-Stokes pass)
+    // 8: no scattering term in the source function (J-dagger taken as 0): what the reference's
+    // full-Stokes pass does when it does not update J (stokes_fs_core only fills JDag under updateJ,
+    // FormalStokes.cpp:431-441, :593)
     const bool fsOnly = (fsMode & 1) != 0;
+    const bool noMoments = (fsMode & 4) != 0;
+    const bool noScatter = (fsMode & 8) != 0;
     const int dirFirst = (fsMode & 2) ? 1 : 0;
     constexpr int NLA = NL > 0 ? NL : 1;
     constexpr int NPAIR = NL > 1 ? NL * (NL - 1) / 2 : 1;
@@ -169,7 +175,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
             chiC[j] = v ? __ldg(P.chiC + rowB + k) : 1.0;
             etaC[j] = v ? __ldg(P.etaC + rowB + k) : 0.0;
             const double sca = v ? __ldg(P.scaBg + rowLK + k) : 0.0;
-            const double JDag = v ? P.J[rowLK + k] : 0.0;
+            const double JDag = (v && !noScatter) ? P.J[rowLK + k] : 0.0;
             scaJ[j] = sca * JDag;
         }
         // line slots: chi = chiC + sum_l cX_l phi_l, eta = etaC + sum_l cE_l phi_l
@@ -438,6 +444,8 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
                 P.J[rowLK + k] = mJ[j];
                 const double d = fabs(1.0 - JDag / mJ[j]);
                 dJ = (d < dJ) ? dJ : d;
+                if (noMoments)
+                    continue;
                 mom[k] = mP[j];
                 if (NL > 0)
                 {

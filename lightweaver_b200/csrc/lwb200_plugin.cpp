@@ -46,6 +46,8 @@ struct Mirror
     std::deque<std::vector<LwB200Transition>> trans;
     std::vector<Atom*> hostAtoms;
     std::vector<double> lowerBc, upperBc;
+    std::deque<std::vector<double>> polStage;                    // six polarised profiles per polarised line
+    std::vector<std::pair<const Transition*, size_t>> polSrc;   // (line, index into polStage)
     bool uploadedStatic = false;
     bool hasDepth = false;
     uint64_t fpProfiles = 0, fpBackground = 0, fpAtmos = 0, fpJ = 0;
@@ -144,6 +146,7 @@ void build_mirror(Context& ctx, Mirror& m)
     p.scaBg = bg.sca.data;
     p.J = spect.J.data;
     p.I = spect.I.data;
+    p.Quv = spect.Quv ? spect.Quv.data : nullptr;
     if (spect.I.shape(2) != 1)
         throw std::runtime_error("mali_full_precond_B200: spect.I must have one outgoing point per ray");
     auto bind_bc = [&](AtmosphericBoundaryCondition& bc, int& nmu, const double*& data, const int32_t*& idx)
@@ -173,6 +176,8 @@ void build_mirror(Context& ctx, Mirror& m)
     }
 
     m.atoms.clear();
+    m.polStage.clear();
+    m.polSrc.clear();
     m.trans.clear();
     m.hostAtoms.clear();
     auto add_atoms = [&](std::vector<Atom*>& list, bool detailed)
@@ -215,6 +220,14 @@ void build_mirror(Context& ctx, Mirror& m)
                 ft.Rij = t->Rij.data;
                 ft.Rji = t->Rji.data;
                 ft.Qelast = t->Qelast ? t->Qelast.data : nullptr;
+                if (t->type == LINE && t->polarised && t->phiQ)
+                {
+                    // the six extra profiles are separate arrays in the reference: staged contiguously
+                    const size_t per = (size_t)(t->Nred - t->Nblue) * M * 2 * K;
+                    m.polStage.emplace_back(6 * per);
+                    ft.polProfiles = m.polStage.back().data();
+                    m.polSrc.push_back({t, m.polStage.size() - 1});
+                }
                 tv.push_back(ft);
             }
             fa.trans = tv.data();
@@ -382,6 +395,60 @@ IterationResult b200_redistribute_prd(Context& ctx, int maxIter, f64 tol, ExtraP
     return result;
 }
 
+// FsIterationFns::full_stokes_fs (LwFormalInterface.hpp:117): polarised formal solution.
+IterationResult b200_full_stokes_fs(Context& ctx, bool updateJ, bool upOnly, ExtraParams params)
+{
+    if (params.contains("J20"))
+        return formal_sol_full_stokes_impl(ctx, updateJ, upOnly, params); // J20 is not handled on the device
+    size_t nPol = 0;
+    for (auto* list : {&ctx.activeAtoms, &ctx.detailedAtoms})
+        for (Atom* a : *list)
+            for (Transition* t : a->trans)
+                nPol += (t->type == LINE && t->polarised && t->phiQ) ? 1 : 0;
+    if (nPol == 0 || !ctx.spect->Quv)
+        return formal_sol_full_stokes_impl(ctx, updateJ, upOnly, params);
+    {
+        // setup_stokes() allocates the polarised profiles after the Context (and possibly our
+        // mirror) was made: a mirror that does not know them is rebuilt
+        std::unique_lock<std::mutex> lock(g_mutex);
+        auto it = g_mirrors.find(&ctx);
+        if (it != g_mirrors.end() && it->second->polSrc.size() != nPol)
+        {
+            destroy_mirror(it->second.get());
+            g_mirrors.erase(it);
+            ctx.methodScratch = nullptr;
+        }
+    }
+    Mirror& m = mirror_for(ctx);
+    sync_inputs(ctx, m, false);
+    // (re)stage the polarised profiles: setup_stokes(recompute) rewrites them in place
+    for (auto& src : m.polSrc)
+    {
+        const Transition* t = src.first;
+        const size_t per = (size_t)(t->Nred - t->Nblue) * m.prob.Nrays * 2 * m.prob.Nspace;
+        const f64* arrs[6] = {t->phiQ.data, t->phiU.data, t->phiV.data, t->psiQ.data, t->psiU.data, t->psiV.data};
+        for (int a = 0; a < 6; ++a)
+            std::memcpy(m.polStage[src.second].data() + a * per, arrs[a], per * sizeof(f64));
+    }
+    check(lwb200_upload(m.dev, LWB200_STOKES | LWB200_PROFILE), "lwb200_upload");
+    double dJMax = 0.0;
+    int64_t dJIdx = 0;
+    check(lwb200_formal_sol_full_stokes(m.dev, updateJ ? 1 : 0, upOnly ? 1 : 0, &dJMax, &dJIdx),
+          "lwb200_formal_sol_full_stokes");
+    check(lwb200_download(m.dev, LWB200_INTENS | LWB200_STOKES | (updateJ ? LWB200_JBAR : 0)), "lwb200_download");
+    check(lwb200_sync(m.dev), "lwb200_sync");
+    if (updateJ)
+        m.fpJ = fingerprint(1469598103934665603ULL, m.prob.J, (size_t)m.prob.Nspect * m.prob.Nspace);
+    IterationResult result{};
+    result.updatedJ = updateJ;
+    if (updateJ)
+    {
+        result.dJMax = dJMax;
+        result.dJMaxIdx = (int)dJIdx;
+    }
+    return result;
+}
+
 IterationResult b200_simple_fs(Context& ctx, bool upOnly, ExtraParams params)
 {
     (void)params;
@@ -497,7 +564,7 @@ FsIterationFns fs_iteration_fns_provider()
         "mali_full_precond_B200",
         b200_fs_iter,
         b200_simple_fs,
-        formal_sol_full_stokes_impl,
+        b200_full_stokes_fs,
         b200_redistribute_prd,
         b200_stat_eq,
         b200_time_dep_update,

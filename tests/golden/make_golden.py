@@ -41,6 +41,8 @@ def input_digest(p):
             if t.Qelast is not None:
                 h.update(t.Qelast.tobytes())
                 h.update(t.aDamp.tobytes())
+            if t.polProfiles is not None:
+                h.update(t.polProfiles.tobytes())
     return h.hexdigest()
 
 
@@ -62,7 +64,18 @@ PRD_CASES = {
 }
 
 
+# full Stokes: two Gamma iterations (scalar), then single_stokes_fs(updateJ=False, upOnly=True), then
+# formal_sol_full_stokes(updateJ=True, upOnly=False)
+STOKES_CASES = {
+    'tiny_stokes': (synth.tiny_stokes_problem, dict(perturb=True), 2, None),
+    'c5_stokes_1col': (synth.config_c5, dict(ncol=1), 2, 8),
+}
+
+
 def build_case(name):
+    if name in STOKES_CASES:
+        fn, kw, niter, jstride = STOKES_CASES[name]
+        return fn(**kw), niter, jstride
     if name in PRD_CASES:
         fn, kw, niter, jstride, _ = PRD_CASES[name]
     else:
@@ -112,14 +125,41 @@ def run_reference(p, niter, prd=None):
     return snaps
 
 
+def polarised_mask(p):
+    """[Nspect] bool: wavelengths where a polarised line is active (where Quv is meaningful; elsewhere
+    the reference reports whatever the last polarised ray left in its scratch)."""
+    m = np.zeros(p.Nspect, dtype=bool)
+    for a in p.atoms:
+        for t in a.trans:
+            if t.polProfiles is not None:
+                m[t.Nblue:t.Nred] = True
+    return m
+
+
+def run_reference_stokes(p, niter):
+    snaps = run_reference(p, niter)
+    ctx = reflib.RefContext(p)
+    out = {}
+    ctx.full_stokes(updateJ=False, upOnly=True)
+    out['up_I'], out['up_Quv'] = p.I.copy(), p.Quv.copy()
+    dJ, _ = ctx.full_stokes(updateJ=True, upOnly=False)
+    out['uj_I'], out['uj_Quv'], out['uj_J'], out['uj_dJ'] = p.I.copy(), p.Quv.copy(), p.J.copy(), np.array(dJ)
+    ctx.close()
+    return snaps, out
+
+
 def main():
     only = sys.argv[1:]
-    for name in list(CASES) + list(PRD_CASES):
+    for name in list(CASES) + list(PRD_CASES) + list(STOKES_CASES):
         if only and name not in only:
             continue
         p, niter, jstride = build_case(name)
         digest = input_digest(p)
-        snaps = run_reference(p, niter, PRD_CASES[name][4] if name in PRD_CASES else None)
+        stokes = None
+        if name in STOKES_CASES:
+            snaps, stokes = run_reference_stokes(p, niter)
+        else:
+            snaps = run_reference(p, niter, PRD_CASES[name][4] if name in PRD_CASES else None)
         out = {'input_digest': np.array(digest), 'niter': np.array(niter),
                'jstride': np.array(0 if jstride is None else jstride)}
         for it, s in enumerate(snaps):
@@ -127,6 +167,9 @@ def main():
                 if k in ('J', 'prd_J') and jstride is not None:
                     v = v[:, ::jstride]
                 out[f'it{it}_{k}'] = v
+        if stokes is not None:
+            for k, v in stokes.items():
+                out['stokes_' + k] = v[:, ::jstride] if (k == 'uj_J' and jstride) else v
         path = os.path.join(HERE, name + '.npz')
         np.savez_compressed(path, **out)
         print(name, 'L', p.Nspect, 'K', p.Nspace, 'size %.0f KB' % (os.path.getsize(path) / 1024))

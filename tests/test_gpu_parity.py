@@ -12,8 +12,8 @@ import pytest
 from lightweaver_b200 import capi, synth
 from lightweaver_b200.context import Context, ExplodingMatrixError
 from oracle import oraclelib
-from tests.golden.make_golden import CASES, PRD_CASES, build_case, input_digest
-from tests.test_oracle import check_prd_snapshot, check_snapshot, load_golden
+from tests.golden.make_golden import CASES, PRD_CASES, STOKES_CASES, build_case, input_digest
+from tests.test_oracle import check_prd_snapshot, check_snapshot, check_stokes_snapshot, load_golden
 from tests.util import compare_problems, gamma_err, rel_err
 
 pytestmark = pytest.mark.gpu
@@ -273,6 +273,47 @@ def test_cuda_prd_vs_oracle_columns(ndepth):
         for c in range(q.Ncol):
             oraclelib.OracleContext(q, col=c).stat_eq()
         assert compare_problems(p, q)['n'] <= TOL_N
+    ctx.close()
+
+
+@pytest.mark.parametrize('name', list(STOKES_CASES))
+def test_cuda_stokes_matches_reference_golden(name):
+    """Gamma iterations, then single_stokes_fs (up-going rays) and a J-updating full-Stokes pass,
+    against the reference's outputs.  Quv compared (relative to max I) where a polarised line is active."""
+    p, niter, jstride = build_case(name)
+    g = load_golden(name)
+    assert input_digest(p) == str(g['input_digest'])
+    ctx = Context(p)
+    for it in range(niter):
+        ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+        ctx.stat_equil()
+    ctx.single_stokes_fs(updateJ=False, upOnly=True)
+    check_stokes_snapshot(p, g, 'up', jstride, TOL, False)
+    upd = ctx.single_stokes_fs(updateJ=True, upOnly=False)
+    check_stokes_snapshot(p, g, 'uj', jstride, TOL, False)
+    assert abs(upd.dJMax - float(g['stokes_uj_dJ'])) <= TOL * max(upd.dJMax, 1.0)
+    ctx.close()
+
+
+@pytest.mark.parametrize('ndepth', [None, 150])
+def test_cuda_stokes_vs_oracle_columns(ndepth):
+    """Full Stokes on a perturbed magnetised two-column stack (also deeper than one warp)."""
+    from tests.golden.make_golden import polarised_mask
+    p = synth.tiny_stokes_problem(ncol=2, perturb=True, ndepth=ndepth)
+    q = p.clone()
+    ctx = Context(p)
+    ctx.formal_sol_gamma_matrices()
+    oracle_iter(q, stat_eq=False)
+    m = polarised_mask(p)
+    for uj, uo in ((False, True), (True, False), (False, False)):
+        upd = ctx.single_stokes_fs(updateJ=uj, upOnly=uo)
+        dJ = max(oraclelib.OracleContext(q, col=c).full_stokes(updateJ=uj, upOnly=uo)[0] for c in range(q.Ncol))
+        assert rel_err(p.I, q.I) <= TOL
+        assert np.abs(p.Quv[:, :, m] - q.Quv[:, :, m]).max() <= TOL * np.abs(q.I).max()
+        assert np.all(p.Quv[:, :, ~m] == 0.0)
+        if uj:
+            assert rel_err(p.J, q.J) <= TOL and abs(upd.dJMax - dJ) <= TOL * max(dJ, 1.0)
+    assert np.abs(p.Quv).max() > 1e-3 * p.I.max()
     ctx.close()
 
 

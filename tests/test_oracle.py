@@ -9,7 +9,7 @@ import pytest
 
 from lightweaver_b200 import capi, synth
 from oracle import oraclelib, reflib
-from tests.golden.make_golden import CASES, PRD_CASES, build_case, input_digest
+from tests.golden.make_golden import CASES, PRD_CASES, STOKES_CASES, build_case, input_digest, polarised_mask
 from tests.util import compare_problems, rel_err
 
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
@@ -99,6 +99,59 @@ def test_oracle_prd_matches_reference_golden(name):
         o.stat_eq()
         for ia, a in enumerate(p.atoms):
             assert rel_err(a.n, g[f'it{it}_n{ia}']) <= 1e-11
+
+
+def check_stokes_snapshot(p, g, tag, jstride, tol, quv_everywhere):
+    """I, Quv (and J) after a full-Stokes pass against the reference's.  quv_everywhere: also compare
+    Quv at wavelengths without a polarised line (bit-level restatements only: the reference leaves
+    stale scratch values there, the device returns 0)."""
+    errs = {'I': rel_err(p.I, g[f'stokes_{tag}_I'])}
+    m = slice(None) if quv_everywhere else polarised_mask(p)
+    scale = np.abs(g[f'stokes_{tag}_I']).max()
+    errs['Quv'] = float(np.abs(p.Quv[:, :, m] - g[f'stokes_{tag}_Quv'][:, :, m]).max() / scale)
+    if tag == 'uj':
+        J = p.J if not jstride else p.J[:, ::jstride]
+        errs['J'] = rel_err(J, g['stokes_uj_J'])
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, f'stokes {tag}: {bad}'
+    return errs
+
+
+@pytest.mark.parametrize('name', list(STOKES_CASES))
+def test_oracle_stokes_matches_reference_golden(name):
+    """formal_sol_full_stokes: the C restatement against the reference's own outputs."""
+    p, niter, jstride = build_case(name)
+    g = load_golden(name)
+    assert input_digest(p) == str(g['input_digest']), 'synthetic input generator drifted; regenerate goldens'
+    o = oraclelib.OracleContext(p)
+    for it in range(niter):
+        p.prefill_gamma()
+        o.fs_iter(lambdaIterate=(it == 0))
+        o.stat_eq()
+    o.full_stokes(updateJ=False, upOnly=True)
+    check_stokes_snapshot(p, g, 'up', jstride, 1e-12, True)
+    dJ, _ = o.full_stokes(updateJ=True, upOnly=False)
+    check_stokes_snapshot(p, g, 'uj', jstride, 1e-12, True)
+    assert abs(dJ - float(g['stokes_uj_dJ'])) <= 1e-12 * max(dJ, 1.0)
+
+
+@pytest.mark.ref
+def test_oracle_stokes_vs_reference_live():
+    """Bit-level agreement of the full-Stokes restatement with the compiled reference."""
+    p = synth.tiny_stokes_problem(ncol=2, perturb=True, nrays=2)
+    q = p.clone()
+    p.prefill_gamma()
+    q.prefill_gamma()
+    for c in range(2):
+        r, o = reflib.RefContext(p, col=c), oraclelib.OracleContext(q, col=c)
+        r.fs_iter()
+        o.fs_iter()
+        for uj, uo in ((False, True), (True, False)):
+            assert r.full_stokes(updateJ=uj, upOnly=uo)[0] == o.full_stokes(updateJ=uj, upOnly=uo)[0]
+            assert np.array_equal(p.I[c], q.I[c]) and np.array_equal(p.Quv[c], q.Quv[c])
+            assert np.array_equal(p.J[c], q.J[c])
+        r.close()
+    assert np.abs(p.Quv).max() > 1e-3 * p.I.max()
 
 
 @pytest.mark.ref
@@ -261,9 +314,9 @@ def test_cabi_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     """ctypes mirrors of the POD structs have the C sizes (LP64)."""
     import ctypes as C
-    assert C.sizeof(capi.LwB200Transition) == 6 * 4 + 5 * 8 + 9 * 8
+    assert C.sizeof(capi.LwB200Transition) == 6 * 4 + 5 * 8 + 10 * 8
     assert C.sizeof(capi.LwB200Atom) == 4 * 4 + 7 * 8
-    assert C.sizeof(capi.LwB200Problem) == 12 * 4 + 19 * 8
+    assert C.sizeof(capi.LwB200Problem) == 12 * 4 + 20 * 8
 
 
 def test_create_fails_loudly_without_gpu():

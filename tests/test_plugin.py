@@ -110,6 +110,31 @@ def test_reference_core_redistributes_prd_through_the_b200_scheme():
 @needs_plugin
 @pytest.mark.ref
 @pytest.mark.gpu
+def test_reference_core_full_stokes_through_the_b200_scheme():
+    """formal_sol_full_stokes dispatches to the scheme's full_stokes_fs slot."""
+    from tests.golden.make_golden import polarised_mask
+    p = synth.tiny_stokes_problem(perturb=True)
+    q = p.clone()
+    gpu = reflib.RefContext(p, scheme=PLUGIN)
+    cpu = reflib.RefContext(q, scheme='scalar')
+    for prob, ctx in ((p, gpu), (q, cpu)):
+        prob.prefill_gamma()
+        ctx.fs_iter()
+    m = polarised_mask(p)
+    for uj, uo in ((False, True), (True, False)):
+        a = gpu.full_stokes(updateJ=uj, upOnly=uo)
+        b = cpu.full_stokes(updateJ=uj, upOnly=uo)
+        assert rel_err(p.I, q.I) <= 1e-9
+        assert np.abs(p.Quv[:, :, m] - q.Quv[:, :, m]).max() <= 1e-9 * np.abs(q.I).max()
+        if uj:
+            assert rel_err(p.J, q.J) <= 1e-9 and abs(a[0] - b[0]) <= 1e-9 * max(b[0], 1.0)
+    gpu.close()
+    cpu.close()
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.gpu
 def test_reference_core_time_dep_update_through_the_b200_scheme():
     p = synth.tiny_problem(perturb=True)
     q = p.clone()
