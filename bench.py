@@ -71,6 +71,13 @@ def build_workload(name, columns, rank=0, world=1, for_gpu=True):
                                          '(configs[3]; each step = Gamma iteration + up to 3 PRD sub-iterations on '
                                          'fixed LTE populations -- no stat-eq, the synthetic atom is not meant to be '
                                          'iterated to convergence with PRD; points counted for the Gamma iteration only)')
+    if name == 'c5':
+        from lightweaver_b200.sharding import partition_columns
+        c0, c1 = partition_columns(columns, world)[rank]
+        p = synth.config_c5(ncol=columns, col_range=(c0, c1))
+        return p, (f'1.5D magnetised stack of {columns} perturbed FAL C columns x 82 depths, Ca II with the 854.2 nm '
+                   'line Zeeman-split and polarised, 5 rays (configs[4]; each step = one J-updating full-Stokes '
+                   'formal solution of every wavelength, formal_sol_full_stokes(updateJ=True, upOnly=False))')
     if name == 'c3':
         from lightweaver_b200.sharding import partition_columns
         c0, c1 = partition_columns(columns, world)[rank]
@@ -180,11 +187,15 @@ def time_reference(problem, steps, warmup, budget_s=120.0):
                     'sample': f'full workload, {steps} timed Gamma iterations + stat_eq, Nthreads={cores}'}
         # column stack: sample of columns, one Context per column, thread pool over columns
         from concurrent.futures import ThreadPoolExecutor
-        ncs = min(problem.Ncol, 4 * cores)
+        is_stokes = problem.Quv is not None
+        ncs = min(problem.Ncol, (1 if is_stokes else 4) * cores)
         problem.prefill_gamma()
         ctxs = [reflib.RefContext(problem, col=c, scheme=scheme, Nthreads=1) for c in range(ncs)]
 
         def one(c):
+            if is_stokes:
+                # the reference's full-Stokes formal solution is single-threaded (FormalStokes.cpp:707-711)
+                return c.full_stokes(updateJ=True, upOnly=False)[0]
             return c.time_fs_iter(0, 1, True)[0]
         with ThreadPoolExecutor(cores) as ex:
             t0 = time.perf_counter()
@@ -225,13 +236,16 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     problem, desc = build_workload(args.workload, args.columns, rank, world)
-    column_sharded = args.workload == 'c3'
+    column_sharded = args.workload in ('c3', 'c5')
+    stokes = args.workload == 'c5'
     laRange = None
     if world > 1 and not column_sharded:
         laRange = sharding.partition_wavelengths(problem, world)[rank]
     stream = torch.cuda.current_stream()
     ctx = Context(problem, device=local_rank, stream=stream, laRange=laRange, upload=False)
-    if column_sharded:
+    if stokes:
+        ctx.upload(capi.ALL_INPUTS | capi.STOKES)
+    elif column_sharded:
         ctx.upload(capi.ALL_INPUTS & ~capi.PROFILE)
         ctx.update_deps(background=False, profiles_on_device=True)
     else:
@@ -245,6 +259,9 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
     def step():
+        if stokes:
+            capi.check(ctx.lib.lwb200_formal_sol_full_stokes(ctx._h, 1, 0, None, None))
+            return
         if world > 1 and not column_sharded:
             sharding.sharded_gamma_iteration(shard, group=None, want_dJ=False)
         else:
@@ -265,17 +282,24 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     # kernels launched per step, counted by the library itself (lwb200_work_stats)
     per_step = 0
-    if world > 1 and not column_sharded:
+    if stokes:
+        step()
+        per_step += ctx.work_stats()[2]
+    elif world > 1 and not column_sharded:
         sharding.sharded_gamma_iteration(shard, group=None, want_dJ=False)
         per_step += 1  # the all-reduce
     else:
         ctx.fs_iter_device(want_dJ=False)
-    per_step += ctx.work_stats()[2]
-    if with_prd:
+    if not stokes:
+        per_step += ctx.work_stats()[2]
+    if stokes:
+        pass
+    elif with_prd:
         ctx.prd_redistribute_device(maxIter=3, tol=1e-2)
     else:
         ctx.stat_eq_device()
-    per_step += ctx.work_stats()[2]
+    if not stokes:
+        per_step += ctx.work_stats()[2]
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -327,9 +351,15 @@ def run_ours(args, rank, world, local_rank):
     d2h = problem.J.nbytes + problem.I.nbytes + sum(a.n.nbytes for a in problem.active_atoms())
     d2h += sum(a.Gamma.nbytes for a in problem.active_atoms())
     d2h += sum(t_.Rij.nbytes + t_.Rji.nbytes for a in problem.atoms for t_ in a.trans)
+    if stokes:
+        h2d = sum(a.n.nbytes for a in problem.atoms) + problem.J.nbytes
+        d2h = problem.I.nbytes + problem.Quv.nbytes + problem.J.nbytes
     e2e = None
     if world == 1 or column_sharded:
         def api_step():
+            if stokes:
+                ctx.single_stokes_fs(updateJ=True, upOnly=False)
+                return
             ctx.formal_sol_gamma_matrices()
             if with_prd:
                 ctx.prd_redistribute(maxIter=3, tol=1e-2)
@@ -348,7 +378,8 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {'value': pts_total / te.item(), 'unit': 'points/s', 'ms_per_step': te.item() * 1e3,
                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-               'api': 'Context.formal_sol_gamma_matrices() + Context.stat_equil() on host numpy buffers'}
+               'api': ('Context.single_stokes_fs(updateJ=True, upOnly=False) on host numpy buffers' if stokes else
+                       'Context.formal_sol_gamma_matrices() + Context.stat_equil() on host numpy buffers')}
     else:
         # lambda-sharded: each rank uploads the (replicated) small inputs, reads back its J rows
         for _ in range(2):
@@ -482,9 +513,11 @@ def _main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c3', 'c4'])
-    ap.add_argument('--columns', type=int, default=4096)
+    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c3', 'c4', 'c5'])
+    ap.add_argument('--columns', type=int, default=None, help='columns of the c3 (4096) / c5 (1024) stacks')
     args = ap.parse_args()
+    if args.columns is None:
+        args.columns = 1024 if args.workload == 'c5' else 4096
 
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
