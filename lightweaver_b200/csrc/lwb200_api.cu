@@ -122,6 +122,7 @@ struct PipelineLists
     int prdOnly;
     const int* polLam; // full Stokes pass: wavelengths with a polarised line (stokes_kernel)
     int nPolLam;
+    int fullRange;     // the lists cover the whole spectrum whatever the context's wavelength shard
 };
 
 struct LwB200Context
@@ -809,14 +810,15 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
     if (set_smem_attr(gamma_kernel, c->device))
         return 1;
     const int Ncol = c->prob.Ncol, KP = c->P.KP, K = c->P.K;
+    const int laLo = pl.fullRange ? 0 : c->laLo, laHi = pl.fullRange ? c->prob.Nspect : c->laHi;
     const int threads = MULTI ? 32 * ((K + 32 * NCH - 1) / (32 * NCH)) : c->nwarps * 32;
     for (int colBase = 0; colBase < Ncol; colBase += c->batchCols)
     {
         const int nb = std::min(c->batchCols, Ncol - colBase);
         if (pl.nMoment > 0)
         {
-            continuum_kernel<<<dim3(pl.nMoment, nb), KP, 0, c->stream>>>(c->P, pl.moment, c->laLo, c->laHi,
-                                                                        colBase, pl.laMask);
+            continuum_kernel<<<dim3(pl.nMoment, nb), KP, 0, c->stream>>>(c->P, pl.moment, laLo, laHi, colBase,
+                                                                        pl.laMask);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }
@@ -893,7 +895,7 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
         {
             const int KC = c->KC;
             gamma_kernel<<<dim3(pl.nMoment, nb, (K + KC - 1) / KC), KC, c->smemGamma, c->stream>>>(
-                c->P, pl.moment, c->laLo, c->laHi, colBase, pl.laMask, pl.prdOnly);
+                c->P, pl.moment, laLo, laHi, colBase, pl.laMask, pl.prdOnly);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }
@@ -1695,8 +1697,9 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
     for (int q = 0; q < nLines; ++q)
         if (c->prdLines[q].cOff < 0)
             return fail("lwb200_redistribute_prd: atom of a PRD line without collisional rates C");
-    if (c->laLo != 0 || c->laHi != c->prob.Nspect)
-        return fail("lwb200_redistribute_prd: not available on a wavelength shard");
+    // On a wavelength shard the redistribution runs REPLICATED over the whole spectrum (it needs all of
+    // J -- the caller all-gathers the J rows first, sharding.sharded_prd_redistribute -- and the PRD
+    // wavelengths are a small subset): its work lists do not depend on the shard.
     if (refresh_tile_lists(c))
         return 1;
     const LwB200Problem& p = c->prob;
@@ -1752,6 +1755,7 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
     }
     pl.laMask = c->dPrdMask.p;
     pl.prdOnly = 1;
+    pl.fullRange = 1;
 
     // Ng(0, 0, 0, rho): the change of the first redistribution is measured against the rho we start from
     CU(cudaMemcpyAsync(c->rhoPrev.p, c->rhoPrd.p, c->rhoPrd.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -1825,7 +1829,7 @@ int lwb200_formal_sol_full_stokes(LwB200Context* c, int updateJ, int upOnly, dou
     if (!c->stokesUploaded)
         return fail("lwb200_formal_sol_full_stokes: polarised profiles have not been uploaded (LWB200_STOKES)");
     if (c->laLo != 0 || c->laHi != c->prob.Nspect)
-        return fail("lwb200_formal_sol_full_stokes: not available on a wavelength shard");
+        return fail("lwb200_formal_sol_full_stokes: not available on a wavelength shard (column-shard instead)");
     if (c->prob.Nspace < 3)
         return fail("lwb200_formal_sol_full_stokes: needs at least three depth points");
     if (refresh_tile_lists(c))
@@ -1884,6 +1888,7 @@ int lwb200_formal_sol_full_stokes(LwB200Context* c, int updateJ, int upOnly, dou
     }
     pl.polLam = c->dPolLam.p;
     pl.nPolLam = c->nPolLam;
+    pl.fullRange = 1;
     c->prdPass = true; // (custom lists; also keeps the general kernel out)
     c->prdPl = pl;
     c->stokesFsMode = (updateJ ? 4 : (1 | 8)) | (upOnly ? 2 : 0);

@@ -118,6 +118,14 @@ class ShardBackend:
     def stat_eq(self):
         raise NotImplementedError
 
+    def j_tensor(self):
+        """torch tensor [Nspect, Nspace] viewing this rank's copy of J (1D atmospheres)."""
+        raise NotImplementedError
+
+    def prd_redistribute(self, maxIter: int, tol: float):
+        """Angle-averaged PRD sub-iterations over the whole spectrum; returns the number taken."""
+        raise NotImplementedError
+
 
 class GpuLambdaShard(ShardBackend):
     def __init__(self, ctx):
@@ -139,6 +147,14 @@ class GpuLambdaShard(ShardBackend):
 
     def stat_eq(self):
         self.ctx.stat_eq_device()
+
+    def j_tensor(self):
+        ptr, nbytes = self.ctx.device_buffer(capi.BUF_J)
+        p = self.ctx.problem
+        return device_tensor(ptr, nbytes, self.ctx.device).view(p.Ncol * p.Nspect, p.Nspace)
+
+    def prd_redistribute(self, maxIter=3, tol=1e-2):
+        return self.ctx.prd_redistribute_device(maxIter=maxIter, tol=tol)
 
 
 def reduce_dj(dJ: float, idx: int, group=None, device='cpu'):
@@ -170,6 +186,22 @@ def sharded_gamma_iteration(shard: ShardBackend, lambdaIterate=False, group=None
         t = shard.accum_tensor()
         dJ, idx = reduce_dj(dJ, idx, group, device=t.device)
     return dJ, idx
+
+
+def sharded_prd_redistribute(shard: ShardBackend, ranges: Sequence[Tuple[int, int]], rank: int, maxIter=3,
+                             tol=1e-2, group=None):
+    """PRD redistribution after a lambda-sharded Gamma iteration (1D atmospheres).  The scattering
+    integral of a PRD line needs J over the whole line, and the rates it uses are already identical on
+    every rank (they came out of the all-reduce), so: ONE all-gather of the J rows, then every rank
+    runs the redistribution and its formal solution over the PRD wavelengths REPLICATED -- they are a
+    small subset of the spectrum, and no further exchange is needed.  Afterwards rho, the PRD lines'
+    rates and J at the PRD wavelengths are up to date on every rank."""
+    J = shard.j_tensor()
+    lo, hi = ranges[rank]
+    full = gather_rows(J[lo:hi].clone(), ranges, group)
+    if full is not J:
+        J[:full.shape[0]].copy_(full)
+    return shard.prd_redistribute(maxIter, tol)
 
 
 def gather_rows(local_rows, ranges: Sequence[Tuple[int, int]], group=None):

@@ -383,6 +383,46 @@ def test_lambda_shards_sum_to_full_iteration():
         c.close()
 
 
+def test_prd_on_a_wavelength_shard_runs_replicated():
+    """lwb200_redistribute_prd on a lambda-sharded context (after the accumulators were summed and the
+    J rows gathered, as sharding.sharded_prd_redistribute does) equals the un-sharded call."""
+    import torch
+    from lightweaver_b200.sharding import GpuLambdaShard
+    p = synth.tiny_prd_problem(perturb=True)
+    full = p.clone()
+    cf = Context(full)
+    cf.formal_sol_gamma_matrices()
+    cf.prd_redistribute(maxIter=2, tol=1e-6)
+    L = p.Nspect
+    split = L // 2
+    parts = [p.clone(), p.clone()]
+    ctxs = [Context(parts[0], laRange=(0, split)), Context(parts[1], laRange=(split, L))]
+    shards = []
+    for c, pp in zip(ctxs, parts):
+        pp.prefill_gamma()
+        c.upload(capi.ITER_INPUTS | capi.PRD)
+        c.fs_iter_device(deferFinalise=True, want_dJ=False)
+        shards.append(GpuLambdaShard(c))
+    torch.cuda.synchronize()
+    total = shards[0].accum_tensor() + shards[1].accum_tensor()     # the all-reduce
+    J = torch.cat([shards[0].j_tensor()[:split], shards[1].j_tensor()[split:]])  # the all-gather
+    for sh in shards:
+        sh.accum_tensor().copy_(total)
+        sh.j_tensor().copy_(J)
+        sh.finalise()
+        assert sh.prd_redistribute(maxIter=2, tol=1e-6) == 2
+    for c, pp in zip(ctxs, parts):
+        c.download(capi.PRD | capi.JBAR | capi.RATES | capi.INTENS)
+        for a, b in zip(pp.atoms, full.atoms):
+            for t, u in zip(a.trans, b.trans):
+                if t.rhoPrd is not None:
+                    assert rel_err(t.rhoPrd, u.rhoPrd) <= TOL
+                    assert rel_err(t.Rij, u.Rij, floor=1e-30) <= TOL
+        assert rel_err(pp.J, full.J) <= TOL
+    for c in ctxs + [cf]:
+        c.close()
+
+
 def test_singular_matrix_raises():
     p = synth.tiny_problem()
     ctx = Context(p)

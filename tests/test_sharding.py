@@ -90,6 +90,13 @@ class OracleShard(sharding.ShardBackend):
     def stat_eq(self):
         self.ctx.stat_eq()
 
+    def j_tensor(self):
+        return torch.from_numpy(self.p.J[0])
+
+    def prd_redistribute(self, maxIter=3, tol=1e-2):
+        nl = sum(1 for a in self.p.atoms for t in a.trans if t.rhoPrd is not None)
+        return self.ctx.redistribute_prd(maxIter=maxIter, tol=tol, nlines=nl)['nIter']
+
 
 def _free_port():
     s = socket.socket()
@@ -139,3 +146,45 @@ def test_lambda_sharded_iteration_over_gloo(tmp_path):
     assert rel_err(got['R'], q.atoms[0].trans[0].Rij, floor=1e-30) <= 1e-12
     for (dJ, idx), (rdJ, ridx) in zip(got['dJ'], ref):
         assert abs(dJ - rdJ) <= 1e-12 * max(rdJ, 1.0) and int(idx) == ridx
+
+
+def _prd_worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    p = synth.tiny_prd_problem()
+    ranges = sharding.partition_wavelengths(p, world)
+    shard = OracleShard(p, ranges[rank])
+    for it in range(2):
+        sharding.sharded_gamma_iteration(shard, lambdaIterate=(it == 0), want_dJ=False)
+        n = sharding.sharded_prd_redistribute(shard, ranges, rank, maxIter=2, tol=1e-6)
+        assert n == 2
+        shard.stat_eq()
+    lines = [t for t in p.atoms[0].trans if t.rhoPrd is not None]
+    np.savez(out % rank, rho=lines[0].rhoPrd, n=p.atoms[0].n, Rij=lines[0].Rij,
+             Jprd=p.J[0, lines[0].Nblue:lines[0].Nred])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_lambda_sharded_prd_over_gloo(tmp_path):
+    """PRD after a lambda-sharded iteration: J all-gathered, redistribution replicated; every rank ends
+    with the state of the single-process run."""
+    out = str(tmp_path / 'rank%d.npz')
+    port = _free_port()
+    mp.spawn(_prd_worker, args=(2, port, out), nprocs=2, join=True)
+    q = synth.tiny_prd_problem()
+    o = oraclelib.OracleContext(q)
+    for it in range(2):
+        q.prefill_gamma()
+        o.fs_iter(lambdaIterate=(it == 0))
+        o.redistribute_prd(maxIter=2, tol=1e-6, nlines=2)
+        o.stat_eq()
+    line = [t for t in q.atoms[0].trans if t.rhoPrd is not None][0]
+    for rank in range(2):
+        got = np.load(out % rank)
+        assert rel_err(got['rho'], line.rhoPrd) <= 1e-9
+        assert rel_err(got['n'], q.atoms[0].n) <= 1e-9
+        assert rel_err(got['Rij'], line.Rij, floor=1e-30) <= 1e-9
+        assert rel_err(got['Jprd'], q.J[0, line.Nblue:line.Nred]) <= 1e-9
+
