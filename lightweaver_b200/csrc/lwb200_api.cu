@@ -127,7 +127,7 @@ struct PipelineLists
 
 struct LwB200Context
 {
-    bool prdPass = false;
+    bool customLists = false; // launch_fs uses prdPl instead of the context-wide lists (PRD and Stokes passes)
     PipelineLists prdPl{};
     int stokesFsMode = 0; // != 0: the pass is a full-Stokes formal solution (always Bezier3)
     Pinned stN, stNStar, stNTotal, stVBroad, stPrefill, stGamma, stNOut, stGammaOut, stRates;
@@ -337,7 +337,8 @@ int build_plan(LwB200Context* c)
         maxNlevel = std::max(maxNlevel, c->atoms[a].Nlevel);
     const size_t scratchFs = (size_t)c->nwarps * 2 * maxNlevel * 32 * sizeof(double);
     const int KC = std::min(KP, 128); // depths per gamma_kernel CTA
-    const size_t scratchGamma = (size_t)2 * maxNlevel * KC * sizeof(double);
+    const int RS = K <= 128 ? K : KC; // its shared-memory row stride (no padding rows when one chunk covers K)
+    const size_t scratchGamma = (size_t)2 * maxNlevel * RS * sizeof(double);
     const size_t scratchBytes = std::max(scratchFs, scratchGamma);
     const size_t smemLimit = 200 * 1024;
     if (scratchBytes + 4 * KC * sizeof(double) > smemLimit)
@@ -346,7 +347,7 @@ int build_plan(LwB200Context* c)
     // per slot: 4 accumulator rows (+ 3 rows of staged per-depth data in gamma_kernel); keep a
     // CTA under ~48 KB so that several share an SM and the L1 keeps some room
     const size_t accBudget = std::min<size_t>(smemLimit - scratchBytes, 32 * 1024);
-    const int slotCap = (int)std::max<size_t>(accBudget / (4 * KC * sizeof(double)), 1);
+    const int slotCap = (int)std::max<size_t>(accBudget / (4 * RS * sizeof(double)), 1);
     if ((long long)std::max(ncont, 1) * p.Ncol * K > 0x7fffffffLL)
         return fail("gRatio block exceeds 2^31 elements");
     const long long targetCtas = 148LL * 16;
@@ -377,7 +378,7 @@ int build_plan(LwB200Context* c)
                         add.push_back(g);
                 if ((int)(slots.size() + add.size()) > slotCap && pos > start)
                     break;
-                if ((int)(slots.size() + add.size()) * 4 * KC * sizeof(double) + scratchBytes > smemLimit)
+                if ((int)(slots.size() + add.size()) * 4 * (size_t)KP * sizeof(double) + scratchBytes > smemLimit)
                     return fail("too many transitions active at one wavelength for shared memory");
                 slots.insert(slots.end(), add.begin(), add.end());
                 ++pos;
@@ -447,7 +448,7 @@ int build_plan(LwB200Context* c)
     laOff[L] = (int)entries.size();
     c->Ntile = (int)c->tileLa.size() - 1;
     c->smemBytes = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchFs;
-    c->smemGamma = (size_t)maxSlots * 4 * KC * sizeof(double) + scratchGamma;
+    c->smemGamma = (size_t)maxSlots * 4 * RS * sizeof(double) + scratchGamma;
     c->KC = KC;
     if (c->smemGamma > smemLimit)
         return fail("wavelength tile too large for shared memory");
@@ -916,10 +917,10 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
     if (MODE == MODE_ITER && !c->forceDirect)
     {
         // wavelengths with more than three overlapping lines go through the general kernel
-        if (launch_pipeline<NCH, SOLVER, false>(c, c->prdPass ? c->prdPl : full_lists(c), lambdaIterate, storeDepth,
+        if (launch_pipeline<NCH, SOLVER, false>(c, c->customLists ? c->prdPl : full_lists(c), lambdaIterate, storeDepth,
                                                 c->stokesFsMode))
             return 1;
-        if (c->nListDirect > 0 && !c->prdPass)
+        if (c->nListDirect > 0 && !c->customLists)
         {
             auto kern = fs_kernel<NCH, SOLVER, MODE_ITER>;
             if (set_smem_attr(kern, c->device))
@@ -960,7 +961,7 @@ int launch_fs_long(LwB200Context* c, int lambdaIterate, int upOnly, int storeDep
         return fail("the general per-ray kernel is limited to Nspace <= 128");
     CU(cudaEventRecord(c->evK0, c->stream));
     const int fsMode = MODE == MODE_ITER ? c->stokesFsMode : (upOnly ? 3 : 1);
-    if (launch_pipeline<4, SOLVER, true>(c, c->prdPass ? c->prdPl : full_lists(c), lambdaIterate, storeDepth, fsMode))
+    if (launch_pipeline<4, SOLVER, true>(c, c->customLists ? c->prdPl : full_lists(c), lambdaIterate, storeDepth, fsMode))
         return 1;
     CU(cudaEventRecord(c->evK1, c->stream));
     c->kernelTimed = true;
@@ -1782,10 +1783,10 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
         prd_zero_rates_kernel<<<grid_for((size_t)nLines * p.Ncol * K), 256, 0, s>>>(c->P, c->dPrdLines.p, nLines);
         CU(cudaGetLastError());
         c->lastLaunches += 3;
-        c->prdPass = true;
+        c->customLists = true;
         c->prdPl = pl;
         const int rc = launch_fs<MODE_ITER>(c, 0, 0, 0);
-        c->prdPass = false;
+        c->customLists = false;
         if (rc)
             return 1;
         dj_reduce_kernel<<<1, 256, 0, s>>>(c->dJ.p, p.Ncol, L, 0, L, c->djOut.p, c->djIdx.p, c->dPrdMask.p);
@@ -1889,11 +1890,11 @@ int lwb200_formal_sol_full_stokes(LwB200Context* c, int updateJ, int upOnly, dou
     pl.polLam = c->dPolLam.p;
     pl.nPolLam = c->nPolLam;
     pl.fullRange = 1;
-    c->prdPass = true; // (custom lists; also keeps the general kernel out)
+    c->customLists = true; // (custom lists; also keeps the general kernel out)
     c->prdPl = pl;
     c->stokesFsMode = (updateJ ? 4 : (1 | 8)) | (upOnly ? 2 : 0);
     const int rc = launch_fs<MODE_ITER>(c, 0, 0, 0);
-    c->prdPass = false;
+    c->customLists = false;
     c->stokesFsMode = 0;
     if (rc)
         return 1;

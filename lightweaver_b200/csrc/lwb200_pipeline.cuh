@@ -491,7 +491,9 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
     constexpr int NLA = NL > 0 ? NL : 1;
     constexpr int NQ = NL + 1;
     const int K = P.K;
-    const int tid = threadIdx.x, nthr = blockDim.x, KC = blockDim.x; // shared-memory row stride
+    // shared-memory row stride: the depth count itself when one chunk covers the column (no padding
+    // rows: shared memory per CTA is what sets this kernel's occupancy), else the chunk width
+    const int tid = threadIdx.x, KC = (gridDim.z == 1) ? K : (int)blockDim.x, nthr = KC;
     const double lambda = __ldg(P.wavelength + la);
     const double rlambda = 1.0 / lambda;
     constexpr double hc_k = kHC / (kKBoltzmann * kNmToM);
@@ -698,15 +700,15 @@ gamma_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int
 {
     extern __shared__ double smem[];
     // depth chunk of this CTA: blockDim.x consecutive depths (one chunk covers Nspace <= 128)
-    const int K = P.K, KC = blockDim.x;
+    const int K = P.K, KC = blockDim.x, RS = (gridDim.z == 1) ? K : KC; // RS: shared-memory row stride
     const int tile = tileList[blockIdx.x];
     const int cb = blockIdx.y, col = colBase + cb;
     const int kk = threadIdx.x, k = blockIdx.z * KC + kk;
     const int slot0 = P.tileSlotOff[tile];
     const int nslot = P.tileSlotOff[tile + 1] - slot0;
-    double* acc = smem;                                   // [nslot][4][KC]  partial sums, one writer each
-    double* Xs = smem + (size_t)P.maxSlots * 4 * KC;      // [maxNlevel][KC]
-    double* Us = Xs + (size_t)P.maxNlevel * blockDim.x;
+    double* acc = smem;                                   // [nslot][4][RS]  partial sums, one writer each
+    double* Xs = smem + (size_t)P.maxSlots * 4 * RS;      // [maxNlevel][RS]
+    double* Us = Xs + (size_t)P.maxNlevel * RS;
     if (k < K)
     {
         // Shared memory is private per thread here (its own depth column of every row): the
@@ -714,10 +716,10 @@ gamma_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int
         // resident CTAs per SM, i.e. shared memory per CTA: only the accumulators live there.
         for (int s = 0; s < nslot; ++s)
         {
-            acc[(s * 4 + 0) * KC + kk] = 0.0;
-            acc[(s * 4 + 1) * KC + kk] = 0.0;
-            acc[(s * 4 + 2) * KC + kk] = 0.0;
-            acc[(s * 4 + 3) * KC + kk] = 0.0;
+            acc[(s * 4 + 0) * RS + kk] = 0.0;
+            acc[(s * 4 + 1) * RS + kk] = 0.0;
+            acc[(s * 4 + 2) * RS + kk] = 0.0;
+            acc[(s * 4 + 3) * RS + kk] = 0.0;
         }
         const double Tk = __ldg(P.temperature + (size_t)col * K + k);
         // W0 = sum_r w over both directions of every mu, in the ray order of ray_kernel
@@ -751,7 +753,7 @@ gamma_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int
 #pragma unroll
             for (int q = 0; q < 4; ++q)
             {
-                const double v = acc[(s * 4 + q) * KC + kk];
+                const double v = acc[(s * 4 + q) * RS + kk];
                 if (rows[q] >= 0 && v != 0.0)
                     atomicAdd(P.accum + ((size_t)col * P.AccTot + rows[q]) * K + k, v);
             }
