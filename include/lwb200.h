@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LWB200_ABI_VERSION 3
+#define LWB200_ABI_VERSION 4
 
 /* TransitionType, Source/LwTransition.hpp:10-14 */
 enum { LWB200_LINE = 0, LWB200_CONTINUUM = 1 };
@@ -87,7 +87,9 @@ typedef struct LwB200Atom {
     const double* vBroad;    /* [Ncol][Nspace]; only read by *_compute_profiles */
     double* Gamma;           /* [Ncol][Nlevel][Nlevel][Nspace] in (crsw*C prefill) / out; NULL if detailedStatic */
     const double* C;         /* [Ncol][Nlevel][Nlevel][Nspace] collisional rates (Atom::C); only read by
-                                lwb200_redistribute_prd, may be NULL otherwise */
+                                lwb200_redistribute_prd and lwb200_nr_post_update, may be NULL otherwise */
+    const double* stages;    /* [Nlevel] ionisation stage of every level (Atom::stages); only read by
+                                lwb200_nr_post_update, may be NULL otherwise */
 } LwB200Atom;
 
 /* What the hot path reads from / writes to a Context (Source/LwContext.hpp:20-45). */
@@ -125,6 +127,8 @@ typedef struct LwB200Problem {
     LwB200Atom* atoms;         /* [Natom] */
     double* Quv;               /* [Ncol][3][Nspect][Nrays] out of lwb200_formal_sol_full_stokes: spect.Quv(s, la, mu, 0)
                                   (LwMisc.hpp:94), or NULL */
+    double* ne;                /* [Ncol][Nspace] electron density (atmos.ne): in/out of lwb200_nr_post_update,
+                                  or NULL */
 } LwB200Problem;
 
 /* Input/output groups for lwb200_upload / lwb200_download. */
@@ -250,6 +254,28 @@ int lwb200_formal_sol_full_stokes(LwB200Context* ctx, int updateJ, int upOnly, d
  * lwb200_fs_iter, or an LWB200_GAMMA_FINAL upload). */
 int lwb200_time_dep_update(LwB200Context* ctx, int32_t atom, const double* nOld, double dt, int32_t kStart,
                            int32_t kEnd, int32_t* nSingular);
+
+/* Inputs of lwb200_nr_post_update that are not part of the problem. */
+typedef struct LwB200NrUpdate {
+    int32_t Natom;              /* atoms taking part in the charge-conservation system */
+    int32_t timeDependent;      /* nPrev / dt are valid (NrTimeDependentData, Lightweaver.hpp:12-16) */
+    const int32_t* atomIdx;     /* [Natom] indices into problem->atoms (active atoms) */
+    const double* const* dC;    /* NULL, or [Natom] pointers to [Ncol][Nlevel][Nlevel][Nspace] finite-difference
+                                   dC/dne */
+    const double* backgroundNe; /* [Ncol][Nspace] */
+    const double* const* nPrev; /* [Natom] pointers to [Ncol][Nlevel][Nspace] (timeDependent) */
+    double dt;
+    double crswVal;
+} LwB200NrUpdate;
+
+/* Replaces nr_post_update_impl (Source/UpdatePopulations.cpp:230-394; FsIterationFns::nr_post_update,
+ * LwFormalInterface.hpp:121-125): one Newton-Raphson step of the coupled statistical-equilibrium (or
+ * backward-Euler) + charge-conservation system of the listed atoms, per depth: (sum Nlevel + 1)^2
+ * unknowns through the same LU solve.  Updates the atoms' populations and problem->ne on the device
+ * and on the host (ne is copied back by the call; populations with LWB200_POPS).  Gamma is the
+ * finalised matrix on the device. */
+int lwb200_nr_post_update(LwB200Context* ctx, const LwB200NrUpdate* upd, int32_t kStart, int32_t kEnd,
+                          int32_t* nSingular);
 
 /* Replaces redistribute_prd_lines (Source/Prd.cpp:648-658, PrdTemplates.hpp:164-351;
  * FsIterationFns::redistribute_prd, LwFormalInterface.hpp:118) for angle-averaged PRD lines:

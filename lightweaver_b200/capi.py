@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 LINE, CONTINUUM = 0, 1
 BC_UNINITIALISED, BC_ZERO, BC_THERMALISED, BC_PERIODIC, BC_CALLABLE = range(5)
@@ -50,6 +50,7 @@ class LwB200Atom(C.Structure):
         ('detailedStatic', C.c_int32), ('reserved', C.c_int32),
         ('trans', C.POINTER(LwB200Transition)),
         ('n', _dp), ('nStar', _dp), ('nTotal', _dp), ('vBroad', _dp), ('Gamma', _dp), ('C', _dp),
+        ('stages', _dp),
     ]
 
 
@@ -63,8 +64,38 @@ class LwB200Problem(C.Structure):
         ('wavelength', _dp), ('chiBg', _dp), ('etaBg', _dp), ('scaBg', _dp),
         ('lowerBcData', _dp), ('upperBcData', _dp), ('lowerBcIdx', _ip), ('upperBcIdx', _ip),
         ('J', _dp), ('I', _dp), ('depthChi', _dp), ('depthEta', _dp), ('depthI', _dp),
-        ('atoms', C.POINTER(LwB200Atom)), ('Quv', _dp),
+        ('atoms', C.POINTER(LwB200Atom)), ('Quv', _dp), ('ne', _dp),
     ]
+
+
+class LwB200NrUpdate(C.Structure):
+    _fields_ = [
+        ('Natom', C.c_int32), ('timeDependent', C.c_int32), ('atomIdx', _ip),
+        ('dC', C.POINTER(_dp)), ('backgroundNe', _dp), ('nPrev', C.POINTER(_dp)),
+        ('dt', C.c_double), ('crswVal', C.c_double),
+    ]
+
+
+def make_nr_update(atomIdx, backgroundNe, dC=None, nPrev=None, dt=0.0, crswVal=1.0):
+    """(LwB200NrUpdate, keepalive) from numpy arrays: atomIdx list of ints, backgroundNe [Ncol, K],
+    dC / nPrev optional lists (one array per atom)."""
+    u = LwB200NrUpdate()
+    idx = np.ascontiguousarray(atomIdx, dtype=np.int32)
+    keep = [idx, backgroundNe]
+    u.Natom = len(idx)
+    u.atomIdx = iptr(idx)
+    u.backgroundNe = dptr(backgroundNe)
+    u.timeDependent = int(nPrev is not None)
+    u.dt, u.crswVal = float(dt), float(crswVal)
+    for name, arrs in (('dC', dC), ('nPrev', nPrev)):
+        if arrs is None:
+            setattr(u, name, C.POINTER(_dp)())
+            continue
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
+        ptrs = (_dp * len(arrs))(*[dptr(a) for a in arrs])
+        keep += [arrs, ptrs]
+        setattr(u, name, C.cast(ptrs, C.POINTER(_dp)))
+    return u, keep
 
 
 def dptr(a):
@@ -130,6 +161,7 @@ def load():
     lib.lwb200_redistribute_prd.argtypes = [vp, C.c_int32, C.c_double, C.c_int32, C.POINTER(C.c_int32), _dp,
                                             _ip, _dp, C.POINTER(C.c_int64)]
     lib.lwb200_formal_sol_full_stokes.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.lwb200_nr_post_update.argtypes = [vp, C.POINTER(LwB200NrUpdate), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     lib.lwb200_time_dep_update.argtypes = [vp, C.c_int32, _dp, C.c_double, C.c_int32, C.c_int32,
                                            C.POINTER(C.c_int32)]
     lib.lwb200_kernel_time.argtypes = [vp, C.POINTER(C.c_double)]
@@ -138,7 +170,7 @@ def load():
                                       C.POINTER(C.c_int64)]
     for name in ('device_count', 'create', 'destroy', 'set_stream', 'set_lambda_range', 'upload',
                  'download', 'sync', 'compute_profiles', 'fs_iter', 'finalise', 'dj_max',
-                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes'):
+                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes', 'nr_post_update'):
         getattr(lib, 'lwb200_' + name).restype = C.c_int
     if lib.lwb200_abi_version() != ABI_VERSION:
         raise LwB200Error('liblwb200.so ABI version mismatch; rebuild')
@@ -159,4 +191,5 @@ EXPORTED_SYMBOLS = [
     'lwb200_finalise', 'lwb200_dj_max', 'lwb200_formal_sol', 'lwb200_stat_eq',
     'lwb200_device_buffer', 'lwb200_work_stats', 'lwb200_kernel_time', 'lwb200_redistribute_prd',
     'lwb200_time_dep_update', 'lwb200_formal_sol_full_stokes',
+    'lwb200_nr_post_update',
 ]

@@ -279,6 +279,28 @@ class Context:
             upd.dPopsMaxIdx.append(int(d.argmax()))
         return upd, prevTimePops
 
+    def nr_post_update(self, atoms, dC, backgroundNe, timeDependentData=None, extraParams=None):
+        """lw.Context._nr_post_update_impl (LwMiddleLayer.pyx:3533-3564): one Newton-Raphson step of the
+        populations of ``atoms`` (AtomData objects or indices of active atoms) and of the electron
+        density (charge conservation).  ``dC``: list of finite-difference dC/dne arrays (one per atom)
+        or an empty list; ``timeDependentData``: {'dt': ..., 'nPrev': [...]} or None.  Populations and
+        ``problem.ne`` are updated in place."""
+        idx = [a if isinstance(a, int) else self.problem.atoms.index(a) for a in atoms]
+        nPrev = dt = None
+        if timeDependentData is not None:
+            dt, nPrev = timeDependentData['dt'], list(timeDependentData['nPrev'])
+        upd, keep = capi.make_nr_update(idx, np.ascontiguousarray(backgroundNe, dtype=np.float64),
+                                        dC=list(dC) if dC is not None and len(dC) > 0 else None, nPrev=nPrev,
+                                        dt=dt or 0.0, crswVal=self.crsw)
+        self.upload(capi.POPS | capi.GAMMA_FINAL)
+        ns = C.c_int32(0)
+        rc = self.lib.lwb200_nr_post_update(self._h, C.byref(upd), -1, -1, C.byref(ns))
+        if rc != 0:
+            if ns.value > 0:
+                raise ExplodingMatrixError('Singular Matrix')
+            capi.check(rc)
+        self.download(capi.POPS)
+
     def update_deps(self, temperature=True, ne=True, vturb=True, vlos=True, B=True,
                     background=True, hprd=True, quiet=True, profiles_on_device=False):
         """lw.Context.update_deps (LwMiddleLayer.pyx:3244-3288) as seen from the

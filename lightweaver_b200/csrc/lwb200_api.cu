@@ -163,6 +163,8 @@ struct LwB200Context
     std::vector<int> prdLineDetailed;
     DevBuf<DevPrdLine> dPrdLines;
     DevBuf<double> qelast, cmat, rhoPrev, prdMax, nOld;
+    DevBuf<double> nrScratch, nrDC, nrPrev, nrStages, nrBgNe, neDev;
+    DevBuf<NrAtom> nrAtoms;
     DevBuf<int> prdIdx, dKindLamPrd[4], dListMomentPrd;
     DevBuf<unsigned char> dPrdMask;
     std::vector<long long> atomCOff;
@@ -1153,6 +1155,13 @@ int lwb200_destroy(LwB200Context* c)
     c->cmat.release();
     c->rhoPrev.release();
     c->nOld.release();
+    c->nrScratch.release();
+    c->nrDC.release();
+    c->nrPrev.release();
+    c->nrStages.release();
+    c->nrBgNe.release();
+    c->neDev.release();
+    c->nrAtoms.release();
     c->pol.release();
     c->Quv.release();
     c->Jdag.release();
@@ -1913,6 +1922,135 @@ int lwb200_formal_sol_full_stokes(LwB200Context* c, int updateJ, int upOnly, dou
         if (dJMaxIdx)
             *dJMaxIdx = 0;
     }
+    return 0;
+}
+
+
+// nr_post_update_impl (UpdatePopulations.cpp:292-394) on the device-resident populations and Gamma.
+int lwb200_nr_post_update(LwB200Context* c, const LwB200NrUpdate* u, int32_t kStart, int32_t kEnd,
+                          int32_t* nSingular)
+{
+    CU(cudaSetDevice(c->device));
+    const LwB200Problem& p = c->prob;
+    const int K = p.Nspace;
+    const size_t ncol = p.Ncol, D = sizeof(double);
+    if (!u || u->Natom < 1 || !u->atomIdx || !u->backgroundNe)
+        return fail("lwb200_nr_post_update: bad update description");
+    if (!p.ne)
+        return fail("lwb200_nr_post_update: the problem has no electron density (ne)");
+    if (kStart < 0 && kEnd < 0)
+    {
+        kStart = 0;
+        kEnd = K;
+    }
+    if (kStart < 0 || kEnd > K || kStart >= kEnd)
+        return fail("lwb200_nr_post_update: bad depth range");
+    cudaStream_t s = c->stream;
+    std::vector<NrAtom> atoms;
+    std::vector<double> stages;
+    long long dcTot = 0, prevTot = 0;
+    int Neqn = 1;
+    for (int a = 0; a < u->Natom; ++a)
+    {
+        const int ia = u->atomIdx[a];
+        if (ia < 0 || ia >= p.Natom || c->atoms[ia].detailedStatic)
+            return fail("lwb200_nr_post_update: atom index out of range or detailed-static");
+        const LwB200Atom& at = c->atoms[ia];
+        if (!at.C || !at.stages)
+            return fail("lwb200_nr_post_update: atom without C or stages");
+        NrAtom na{};
+        na.atom = ia;
+        na.N = at.Nlevel;
+        na.levOff = c->atomLevOff[ia];
+        na.gammaOff = c->atomGammaOff[ia];
+        na.transBeg = 0;
+        for (size_t g = 0; g < c->trans.size(); ++g)
+            if (c->trans[g].atom == ia)
+            {
+                na.transBeg = (int)g - c->trans[g].kr;
+                break;
+            }
+        na.transEnd = na.transBeg + at.Ntrans;
+        na.cOff = c->atomCOff[ia];
+        na.dcOff = (u->dC && u->dC[a]) ? dcTot : -1;
+        na.prevOff = prevTot;
+        na.stageOff = (int)stages.size();
+        dcTot += (long long)at.Nlevel * at.Nlevel * K;
+        prevTot += (long long)at.Nlevel * K;
+        for (int l = 0; l < at.Nlevel; ++l)
+            stages.push_back(at.stages[l]);
+        atoms.push_back(na);
+        Neqn += at.Nlevel;
+    }
+    if (Neqn > 64)
+        return fail("lwb200_nr_post_update: more than 63 levels in the coupled system");
+    if (u->timeDependent && !u->nPrev)
+        return fail("lwb200_nr_post_update: timeDependent without nPrev");
+    // inputs: C of every atom with one (same packing as the PRD path), dC, nPrev, stages, backgroundNe, ne
+    if (c->cmat.n < (size_t)std::max<long long>(c->cTot, 1) * ncol)
+    {
+        c->cmat.release();
+        if (c->cmat.alloc((size_t)std::max<long long>(c->cTot, 1) * ncol))
+            return 1;
+    }
+    auto ensure = [&](DevBuf<double>& b, size_t count) {
+        if (b.n >= count)
+            return 0;
+        b.release();
+        return b.alloc(std::max<size_t>(count, 1));
+    };
+    if (ensure(c->nrDC, (size_t)dcTot * ncol) || ensure(c->nrPrev, (size_t)prevTot * ncol)
+        || ensure(c->nrStages, stages.size()) || ensure(c->nrBgNe, ncol * K) || ensure(c->neDev, ncol * K)
+        || ensure(c->nrScratch, ncol * (size_t)(kEnd - kStart) * 2 * Neqn * Neqn))
+        return 1;
+    c->nrAtoms.release();
+    if (c->nrAtoms.upload(atoms))
+        return 1;
+    const auto H2D = cudaMemcpyHostToDevice;
+    for (size_t a = 0; a < atoms.size(); ++a)
+    {
+        const LwB200Atom& at = c->atoms[atoms[a].atom];
+        const size_t n2k = (size_t)at.Nlevel * at.Nlevel * K, nk = (size_t)at.Nlevel * K;
+        if (copy2d(c->cmat.p + atoms[a].cOff, (size_t)c->cTot * D, at.C, n2k * D, n2k * D, ncol, H2D, s))
+            return 1;
+        if (atoms[a].dcOff >= 0
+            && copy2d(c->nrDC.p + atoms[a].dcOff, (size_t)dcTot * D, u->dC[a], n2k * D, n2k * D, ncol, H2D, s))
+            return 1;
+        if (u->timeDependent
+            && copy2d(c->nrPrev.p + atoms[a].prevOff, (size_t)prevTot * D, u->nPrev[a], nk * D, nk * D, ncol, H2D, s))
+            return 1;
+    }
+    CU(cudaMemcpyAsync(c->nrStages.p, stages.data(), stages.size() * D, H2D, s));
+    CU(cudaMemcpyAsync(c->nrBgNe.p, u->backgroundNe, ncol * K * D, H2D, s));
+    CU(cudaMemcpyAsync(c->neDev.p, p.ne, ncol * K * D, H2D, s));
+    CU(cudaMemsetAsync(c->dSingular.p, 0, sizeof(int), s));
+    c->lastLaunches = 0;
+    const size_t total = ncol * (size_t)(kEnd - kStart);
+    if (Neqn <= 16)
+        nr_update_kernel<16><<<grid_for(total, 64), 64, 0, s>>>(
+            c->P, c->nrAtoms.p, (int)atoms.size(), Neqn, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, c->cmat.p,
+            c->cTot, c->nrDC.p, dcTot, c->nrPrev.p, prevTot, c->nrStages.p, c->nrBgNe.p, c->neDev.p,
+            u->timeDependent ? 1 : 0, u->dt, u->crswVal, c->nrScratch.p, c->dSingular.p);
+    else if (Neqn <= 32)
+        nr_update_kernel<32><<<grid_for(total, 64), 64, 0, s>>>(
+            c->P, c->nrAtoms.p, (int)atoms.size(), Neqn, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, c->cmat.p,
+            c->cTot, c->nrDC.p, dcTot, c->nrPrev.p, prevTot, c->nrStages.p, c->nrBgNe.p, c->neDev.p,
+            u->timeDependent ? 1 : 0, u->dt, u->crswVal, c->nrScratch.p, c->dSingular.p);
+    else
+        nr_update_kernel<64><<<grid_for(total, 64), 64, 0, s>>>(
+            c->P, c->nrAtoms.p, (int)atoms.size(), Neqn, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, c->cmat.p,
+            c->cTot, c->nrDC.p, dcTot, c->nrPrev.p, prevTot, c->nrStages.p, c->nrBgNe.p, c->neDev.p,
+            u->timeDependent ? 1 : 0, u->dt, u->crswVal, c->nrScratch.p, c->dSingular.p);
+    CU(cudaGetLastError());
+    c->lastLaunches += 1;
+    int ns = 0;
+    CU(cudaMemcpyAsync(&ns, c->dSingular.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(p.ne, c->neDev.p, ncol * K * D, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (nSingular)
+        *nSingular = ns;
+    if (ns > 0)
+        return fail("Singular Matrix");
     return 0;
 }
 

@@ -754,6 +754,179 @@ __global__ void stat_eq_kernel(const DevProblem P, int atomSel, int kStart, int 
     }
 }
 
+// ---------------------------------------------------------------------------
+// nr_post_update_impl with F / Ftd (UpdatePopulations.cpp:230-394): one Newton-Raphson step of the
+// coupled rate + charge-conservation system, (sum Nlevel + 1)^2 unknowns per (column, depth).  One
+// thread per system; the matrix and its copy (for the refinement step of solve_lin_eq) live in a global
+// scratch slice per system, the right-hand side in local memory.
+struct NrAtom
+{
+    int atom;        // index into the problem's atoms
+    int N;           // levels
+    int levOff;      // row of level 0 in the packed population arrays
+    int gammaOff;    // row of Gamma(0, 0) in the packed Gamma arrays
+    int transBeg, transEnd;
+    long long cOff;  // element offset of C(0, 0, 0) within one column of the C buffer
+    long long dcOff; // element offset of dC(0, 0, 0) within one column of the dC buffer, -1: none
+    long long prevOff; // element offset of nPrev(0, 0) within one column of the nPrev buffer
+    int stageOff;    // offset into the packed stages array
+};
+
+template <int MAXN>
+__global__ void nr_update_kernel(const DevProblem P, const NrAtom* __restrict__ atoms, int Natom, int Neqn,
+                                 int kStart, int kEnd, const double* __restrict__ gamma, double* __restrict__ n,
+                                 const double* __restrict__ nTotal, const double* __restrict__ cmat,
+                                 long long cColStride, const double* __restrict__ dC, long long dcColStride,
+                                 const double* __restrict__ nPrev, long long prevColStride,
+                                 const double* __restrict__ stages, const double* __restrict__ bgNe,
+                                 double* __restrict__ ne, int timeDep, double dt, double crswVal,
+                                 double* __restrict__ scratch, int* __restrict__ nSingular)
+{
+    const int nk = kEnd - kStart, K = P.K;
+    const size_t total = (size_t)P.Ncol * nk;
+    const double theta = 1.0;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x)
+    {
+        const int k = kStart + idx % nk;
+        const int col = idx / nk;
+        double* dF = scratch + idx * 2 * (size_t)Neqn * Neqn;
+        double* dFCopy = dF + (size_t)Neqn * Neqn;
+        double Fg[MAXN], FgCopy[MAXN], res[MAXN];
+        int index[MAXN];
+        for (int q = 0; q < Neqn * Neqn; ++q)
+            dF[q] = 0.0;
+        const double nek = ne[(size_t)col * K + k];
+        for (int q = 0; q < Neqn; ++q)
+            Fg[q] = 0.0;
+        Fg[Neqn - 1] = nek;
+        int start = 0;
+        for (int a = 0; a < Natom; ++a)
+        {
+            const NrAtom at = atoms[a];
+            const int N = at.N;
+            const double* G = gamma + ((size_t)col * P.GammaTot + at.gammaOff) * K + k;
+            const double* nn = n + ((size_t)col * P.NlevTot + at.levOff) * K + k;
+            for (int l = 0; l < N; ++l)
+            {
+                double f = 0.0;
+                if (timeDep)
+                {
+                    for (int ll = 0; ll < N; ++ll)
+                        f += G[(size_t)(l * N + ll) * K] * nn[(size_t)ll * K];
+                    f *= theta * dt;
+                    f -= nn[(size_t)l * K] - nPrev[(size_t)col * prevColStride + at.prevOff + (size_t)l * K + k];
+                }
+                else
+                {
+                    for (int ll = 0; ll < N; ++ll)
+                        f -= G[(size_t)(l * N + ll) * K] * nn[(size_t)ll * K];
+                }
+                Fg[start + l] = f;
+            }
+            double nTotCur = 0.0, eleContrib = 0.0;
+            for (int ll = 0; ll < N; ++ll)
+                nTotCur += nn[(size_t)ll * K];
+            Fg[start + N - 1] = nTotCur - nTotal[((size_t)col * P.Natom + at.atom) * K + k];
+            for (int ll = 0; ll < N; ++ll)
+                eleContrib += stages[at.stageOff + ll] * nn[(size_t)ll * K];
+            Fg[Neqn - 1] -= eleContrib;
+            start += N;
+        }
+        Fg[Neqn - 1] -= bgNe[(size_t)col * K + k];
+
+        start = 0;
+        for (int a = 0; a < Natom; ++a)
+        {
+            const NrAtom at = atoms[a];
+            const int N = at.N;
+            const double* G = gamma + ((size_t)col * P.GammaTot + at.gammaOff) * K + k;
+            const double* Cm = cmat + (size_t)col * cColStride + at.cOff + k;
+            const double* nn = n + ((size_t)col * P.NlevTot + at.levOff) * K + k;
+            for (int l = 0; l < N; ++l)
+                for (int ll = 0; ll < N; ++ll)
+                {
+                    double v = -G[(size_t)(l * N + ll) * K];
+                    if (timeDep)
+                    {
+                        v *= -theta * dt;
+                        if (l == ll)
+                            v -= 1.0;
+                    }
+                    dF[(start + l) * Neqn + start + ll] = v;
+                }
+            for (int g = at.transBeg; g < at.transEnd; ++g)
+            {
+                const DevTrans& t = P.trans[g];
+                if (t.type != 0)
+                {
+                    const double preconRji = G[(size_t)(t.i * N + t.j) * K] - crswVal * Cm[(size_t)(t.i * N + t.j) * K];
+                    double entry = -(preconRji / nek) * nn[(size_t)t.j * K];
+                    if (timeDep)
+                        entry *= -theta * dt;
+                    dF[(start + t.i) * Neqn + Neqn - 1] += entry;
+                }
+            }
+            if (at.dcOff >= 0)
+            {
+                const double* d = dC + (size_t)col * dcColStride + at.dcOff + k;
+                for (int i = 0; i < N; ++i)
+                {
+                    double entry = 0.0;
+                    for (int ll = 0; ll < N; ++ll)
+                        entry -= d[(size_t)(i * N + ll) * K] * nn[(size_t)ll * K];
+                    if (timeDep)
+                        entry *= -theta * dt;
+                    dF[(start + i) * Neqn + Neqn - 1] += entry;
+                }
+            }
+            for (int q = 0; q < Neqn; ++q)
+                dF[(start + N - 1) * Neqn + q] = 0.0;
+            for (int ll = 0; ll < N; ++ll)
+            {
+                dF[(start + N - 1) * Neqn + start + ll] = 1.0;
+                dF[(Neqn - 1) * Neqn + start + ll] = -stages[at.stageOff + ll];
+            }
+            start += N;
+        }
+        dF[(Neqn - 1) * Neqn + Neqn - 1] = 1.0;
+        for (int i = 0; i < Neqn; ++i)
+        {
+            Fg[i] *= -1.0;
+            FgCopy[i] = Fg[i];
+        }
+        for (int q = 0; q < Neqn * Neqn; ++q)
+            dFCopy[q] = dF[q];
+        // solve_lin_eq with one refinement step (LuSolve.cpp:103-133)
+        if (!lu_decompose_dev<MAXN>(Neqn, dF, index))
+        {
+            atomicAdd(nSingular, 1);
+            continue;
+        }
+        lu_backsub_dev(Neqn, dF, index, Fg);
+        for (int i = 0; i < Neqn; ++i)
+        {
+            double r = FgCopy[i];
+            for (int j = 0; j < Neqn; ++j)
+                r -= dFCopy[i * Neqn + j] * Fg[j];
+            res[i] = r;
+        }
+        lu_backsub_dev(Neqn, dF, index, res);
+        for (int i = 0; i < Neqn; ++i)
+            Fg[i] += res[i];
+        start = 0;
+        for (int a = 0; a < Natom; ++a)
+        {
+            const NrAtom at = atoms[a];
+            double* nn = n + ((size_t)col * P.NlevTot + at.levOff) * K + k;
+            for (int ll = 0; ll < at.N; ++ll)
+                nn[(size_t)ll * K] += Fg[start + ll];
+            start += at.N;
+        }
+        ne[(size_t)col * K + k] = nek + Fg[Neqn - 1];
+    }
+}
+
 // (max, first index) over dJ[Ncol][L] restricted to [laLo, laHi): what the
 // reference's threaded branch returns (:688, :700-703).  Single block.
 __global__ void dj_reduce_kernel(const double* __restrict__ dJ, int Ncol, int L, int laLo, int laHi,

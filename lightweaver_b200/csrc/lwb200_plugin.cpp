@@ -147,6 +147,7 @@ void build_mirror(Context& ctx, Mirror& m)
     p.J = spect.J.data;
     p.I = spect.I.data;
     p.Quv = spect.Quv ? spect.Quv.data : nullptr;
+    p.ne = atmos.ne ? atmos.ne.data : nullptr;
     if (spect.I.shape(2) != 1)
         throw std::runtime_error("mali_full_precond_B200: spect.I must have one outgoing point per ray");
     auto bind_bc = [&](AtmosphericBoundaryCondition& bc, int& nmu, const double*& data, const int32_t*& idx)
@@ -194,6 +195,7 @@ void build_mirror(Context& ctx, Mirror& m)
             fa.vBroad = a->vBroad.data;
             fa.Gamma = detailed ? nullptr : a->Gamma.data;
             fa.C = a->C ? a->C.data : nullptr;
+            fa.stages = a->stages ? a->stages.data : nullptr;
             m.trans.emplace_back();
             auto& tv = m.trans.back();
             for (Transition* t : a->trans)
@@ -522,6 +524,58 @@ void b200_time_dep_update(Atom* atom, F64View2D nOld, f64 dt, ExtraParams params
     check(lwb200_sync(m->dev), "lwb200_sync");
 }
 
+// FsIterationFns::nr_post_update (LwFormalInterface.hpp:121-125): Newton-Raphson step with charge conservation.
+void b200_nr_post_update(Context& ctx, std::vector<Atom*>* atoms, const std::vector<F64View3D>& dC,
+                         F64View backgroundNe, const NrTimeDependentData& timeDepData, f64 crswVal,
+                         ExtraParams params, int spaceStart, int spaceEnd)
+{
+    Mirror* m = nullptr;
+    std::vector<int32_t> idx;
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        for (Atom* a : *atoms)
+        {
+            auto it = g_atoms.find(a);
+            if (it == g_atoms.end() || (m && it->second.first != m))
+            {
+                m = nullptr;
+                break;
+            }
+            m = it->second.first;
+            idx.push_back(it->second.second);
+        }
+    }
+    if (!m || !m->dev || !m->prob.ne || idx.size() != atoms->size())
+    {
+        nr_post_update_impl(ctx, atoms, dC, backgroundNe, timeDepData, crswVal, params, spaceStart, spaceEnd);
+        return;
+    }
+    std::vector<const double*> dCp, prevP;
+    for (const auto& v : dC)
+        dCp.push_back(v.data);
+    for (const auto& v : timeDepData.nPrev)
+        prevP.push_back(v.data);
+    LwB200NrUpdate u{};
+    u.Natom = (int32_t)idx.size();
+    u.timeDependent = timeDepData.nPrev.size() != 0 ? 1 : 0;
+    u.atomIdx = idx.data();
+    u.dC = dCp.empty() ? nullptr : dCp.data();
+    u.backgroundNe = backgroundNe.data;
+    u.nPrev = prevP.empty() ? nullptr : prevP.data();
+    u.dt = timeDepData.dt;
+    u.crswVal = crswVal;
+    check(lwb200_upload(m->dev, LWB200_POPS | LWB200_GAMMA_FINAL), "lwb200_upload");
+    int32_t nSingular = 0;
+    if (lwb200_nr_post_update(m->dev, &u, spaceStart, spaceEnd, &nSingular) != 0)
+    {
+        if (nSingular > 0)
+            throw std::runtime_error("Singular Matrix");
+        raise("lwb200_nr_post_update");
+    }
+    check(lwb200_download(m->dev, LWB200_POPS), "lwb200_download");
+    check(lwb200_sync(m->dev), "lwb200_sync");
+}
+
 void b200_alloc_global_scratch(Context* ctx)
 {
     // Called from ThreadData::initialise (ThreadStorage.cpp:484-493), i.e. BEFORE
@@ -568,7 +622,7 @@ FsIterationFns fs_iteration_fns_provider()
         b200_redistribute_prd,
         b200_stat_eq,
         b200_time_dep_update,
-        nr_post_update_impl,
+        b200_nr_post_update,
         nullptr, // alloc_per_atom
         nullptr, // free_per_atom
         nullptr, // alloc_per_trans

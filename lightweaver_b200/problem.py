@@ -73,6 +73,7 @@ class AtomData:
     vBroad: Optional[np.ndarray] = None    # [Ncol, Nspace]
     Gamma: Optional[np.ndarray] = None     # [Ncol, Nlevel, Nlevel, Nspace]
     C: Optional[np.ndarray] = None         # [Ncol, Nlevel, Nlevel, Nspace] collisional rates
+    stages: Optional[np.ndarray] = None    # [Nlevel] ionisation stage of every level (float64)
     detailedStatic: bool = False
 
     @property
@@ -187,7 +188,7 @@ class Problem:
                                     Rji=sl(t.Rji), name=t.name) for t in a.trans]
             atoms.append(AtomData(name=a.name, Nlevel=a.Nlevel, trans=trans, n=sl(a.n),
                                   nStar=sl(a.nStar), nTotal=sl(a.nTotal), vBroad=sl(a.vBroad),
-                                  Gamma=sl(a.Gamma), C=sl(a.C), detailedStatic=a.detailedStatic))
+                                  Gamma=sl(a.Gamma), C=sl(a.C), stages=a.stages, detailedStatic=a.detailedStatic))
         return Problem(Nspace=self.Nspace, Nrays=self.Nrays, height=sl(self.height),
                        temperature=sl(self.temperature), muz=self.muz, wmu=self.wmu,
                        wavelength=self.wavelength, chiBg=sl(self.chiBg), etaBg=sl(self.etaBg),
@@ -220,6 +221,7 @@ class Problem:
         p.J, p.I = d(self.J), d(self.I)
         p.depthChi, p.depthEta, p.depthI = d(self.depthChi), d(self.depthEta), d(self.depthI)
         p.Quv = d(self.Quv)
+        p.ne = d(self.ne)
         atoms = (capi.LwB200Atom * len(self.atoms))()
         for ia, a in enumerate(self.atoms):
             ca = atoms[ia]
@@ -242,6 +244,7 @@ class Problem:
             ca.n, ca.nStar, ca.nTotal = d(a.n), d(a.nStar), d(a.nTotal)
             ca.vBroad, ca.Gamma = d(a.vBroad), d(a.Gamma)
             ca.C = d(a.C)
+            ca.stages = d(a.stages)
         keep.append(atoms)
         p.atoms = C.cast(atoms, C.POINTER(capi.LwB200Atom))
         self._keepalive.append((p, keep))

@@ -481,7 +481,8 @@ def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, se
         is_detailed = atom.name in detailed
         atom_data[ia] = AtomData(name=atom.name, Nlevel=len(atom.levels), trans=trans_lists[ia],
                                  n=nStar.copy(), nStar=nStar, nTotal=nTotal, vBroad=vBroad,
-                                 C=None if is_detailed else Cm, detailedStatic=is_detailed)
+                                 C=None if is_detailed else Cm, detailedStatic=is_detailed,
+                                 stages=np.array([float(lv.stage) for lv in atom.levels]))
 
     prob = Problem(Nspace=K, Nrays=nrays, height=np.ascontiguousarray(atm['height']),
                    temperature=np.ascontiguousarray(T), muz=muz, wmu=wmu, wavelength=grid,

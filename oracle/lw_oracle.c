@@ -1010,6 +1010,142 @@ int lwo_time_dep_update(const LwB200Problem* p, int col, int atom, const double*
     return rc;
 }
 
+/* nr_post_update_impl with F / Ftd, UpdatePopulations.cpp:230-394, on column `col`. */
+int lwo_nr_post_update(const LwB200Problem* p, int col, const LwB200NrUpdate* u)
+{
+    const int K = p->Nspace;
+    const int fdCollisionRates = u->dC != NULL;
+    const int timeDep = u->timeDependent != 0;
+    int Nlevel = 0;
+    for (int a = 0; a < u->Natom; ++a)
+        Nlevel += p->atoms[u->atomIdx[a]].Nlevel;
+    const int Neqn = Nlevel + 1;
+    double* dF = (double*)malloc(sizeof(double) * Neqn * Neqn);
+    double* Fg = (double*)malloc(sizeof(double) * Neqn);
+    double* ne = p->ne + (size_t)col * K;
+    const double* bgNe = u->backgroundNe + (size_t)col * K;
+    const double theta = 1.0;
+    int rc = 0;
+    if (!p->ne)
+        rc = 1;
+    for (int k = 0; k < K && !rc; ++k)
+    {
+        memset(dF, 0, sizeof(double) * Neqn * Neqn);
+        /* F (:230-258) / Ftd (:260-290) */
+        memset(Fg, 0, sizeof(double) * Neqn);
+        Fg[Neqn - 1] = ne[k];
+        int start = 0;
+        for (int a = 0; a < u->Natom; ++a)
+        {
+            const LwB200Atom* at = &p->atoms[u->atomIdx[a]];
+            const int N = at->Nlevel;
+            const double* G = at->Gamma + (size_t)col * N * N * K;
+            const double* n = at->n + (size_t)col * N * K;
+            for (int l = 0; l < N; ++l)
+            {
+                Fg[start + l] = 0.0;
+                if (timeDep)
+                {
+                    for (int ll = 0; ll < N; ++ll)
+                        Fg[start + l] += G[((size_t)l * N + ll) * K + k] * n[(size_t)ll * K + k];
+                    Fg[start + l] *= theta * u->dt;
+                    Fg[start + l] -= n[(size_t)l * K + k] - u->nPrev[a][((size_t)col * N + l) * K + k];
+                }
+                else
+                {
+                    for (int ll = 0; ll < N; ++ll)
+                        Fg[start + l] -= G[((size_t)l * N + ll) * K + k] * n[(size_t)ll * K + k];
+                }
+            }
+            double nTotCur = 0.0;
+            for (int ll = 0; ll < N; ++ll)
+                nTotCur += n[(size_t)ll * K + k];
+            Fg[start + N - 1] = nTotCur - at->nTotal[(size_t)col * K + k];
+            double eleContrib = 0.0;
+            for (int ll = 0; ll < N; ++ll)
+                eleContrib += at->stages[ll] * n[(size_t)ll * K + k];
+            Fg[Neqn - 1] -= eleContrib;
+            start += N;
+        }
+        Fg[Neqn - 1] -= bgNe[k];
+
+        start = 0;
+        for (int a = 0; a < u->Natom; ++a)
+        {
+            const LwB200Atom* at = &p->atoms[u->atomIdx[a]];
+            const int N = at->Nlevel;
+            const double* G = at->Gamma + (size_t)col * N * N * K;
+            const double* Cm = at->C + (size_t)col * N * N * K;
+            const double* n = at->n + (size_t)col * N * K;
+            for (int l = 0; l < N; ++l)
+                for (int ll = 0; ll < N; ++ll)
+                    dF[(start + l) * Neqn + start + ll] = -G[((size_t)l * N + ll) * K + k];
+            if (timeDep)
+            {
+                for (int l = 0; l < N; ++l)
+                    for (int ll = 0; ll < N; ++ll)
+                        dF[(start + l) * Neqn + start + ll] *= -theta * u->dt;
+                for (int l = 0; l < N; ++l)
+                    dF[(start + l) * Neqn + start + l] -= 1.0;
+            }
+            for (int tIdx = 0; tIdx < at->Ntrans; ++tIdx)
+            {
+                const LwB200Transition* t = &at->trans[tIdx];
+                if (t->type == LWB200_CONTINUUM)
+                {
+                    double preconRji = G[((size_t)t->i * N + t->j) * K + k] - u->crswVal * Cm[((size_t)t->i * N + t->j) * K + k];
+                    double entry = -(preconRji / ne[k]) * n[(size_t)t->j * K + k];
+                    if (timeDep)
+                        entry *= -theta * u->dt;
+                    dF[(start + t->i) * Neqn + Neqn - 1] += entry;
+                }
+            }
+            if (fdCollisionRates)
+            {
+                const double* dC = u->dC[a] + (size_t)col * N * N * K;
+                for (int i = 0; i < N; ++i)
+                {
+                    double entry = 0.0;
+                    for (int ll = 0; ll < N; ++ll)
+                        entry -= dC[((size_t)i * N + ll) * K + k] * n[(size_t)ll * K + k];
+                    if (timeDep)
+                        entry *= -theta * u->dt;
+                    dF[(start + i) * Neqn + Neqn - 1] += entry;
+                }
+            }
+            for (int q = 0; q < Neqn; ++q)
+                dF[(start + N - 1) * Neqn + q] = 0.0;
+            for (int ll = 0; ll < N; ++ll)
+            {
+                dF[(start + N - 1) * Neqn + start + ll] = 1.0;
+                dF[(Neqn - 1) * Neqn + start + ll] = -at->stages[ll];
+            }
+            start += N;
+        }
+        dF[(Neqn - 1) * Neqn + Neqn - 1] = 1.0;
+        for (int i = 0; i < Neqn; ++i)
+            Fg[i] *= -1.0;
+        if (lwo_solve_lin_eq(Neqn, dF, Fg, 1))
+        {
+            rc = 1;
+            break;
+        }
+        start = 0;
+        for (int a = 0; a < u->Natom; ++a)
+        {
+            const LwB200Atom* at = &p->atoms[u->atomIdx[a]];
+            double* n = at->n + (size_t)col * at->Nlevel * K;
+            for (int ll = 0; ll < at->Nlevel; ++ll)
+                n[(size_t)ll * K + k] += Fg[start + ll];
+            start += at->Nlevel;
+        }
+        ne[k] += Fg[Neqn - 1];
+    }
+    free(dF);
+    free(Fg);
+    return rc;
+}
+
 /* ------------------------------------------------------------------------ */
 /* Angle-averaged PRD: redistribute_prd_lines (Prd.cpp:648-658 ->
  * redistribute_prd_lines_template, PrdTemplates.hpp:164-351, Nthreads <= 1 branch). */

@@ -58,6 +58,10 @@ int lwo_full_stokes(const LwB200Problem* p, int col, int updateJ, int upOnly, do
  * nOld is [Ncol][Nlevel][Nspace].  Returns 1 for "Singular Matrix". */
 int lwo_time_dep_update(const LwB200Problem* p, int col, int atom, const double* nOld, double dt);
 
+/* nr_post_update_impl (UpdatePopulations.cpp:230-394) on column `col`: one Newton-Raphson step of the
+ * populations of the listed atoms and of p->ne.  Returns 1 for "Singular Matrix". */
+int lwo_nr_post_update(const LwB200Problem* p, int col, const LwB200NrUpdate* upd);
+
 /* redistribute_prd_lines for angle-averaged PRD lines (Prd.cpp:9-124, :468-658;
  * PrdTemplates.hpp:18-76, :164-291), Nthreads <= 1 branch, on column `col`.  dRho / dRhoIdx
  * [maxIter * NprdLines] in (iteration, line) order, dJPrdMax / dJPrdMaxIdx [maxIter];

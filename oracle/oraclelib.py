@@ -38,6 +38,7 @@ def load():
     lib.lwo_solve_lin_eq.argtypes = [C.c_int, dp, dp, C.c_int]
     lib.lwo_fs_iter_columns.argtypes = [vp, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int]
     lib.lwo_full_stokes.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, i64p]
+    lib.lwo_nr_post_update.argtypes = [vp, C.c_int, vp]
     lib.lwo_time_dep_update.argtypes = [vp, C.c_int, C.c_int, dp, C.c_double]
     lib.lwo_redistribute_prd.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp,
                                          C.POINTER(C.c_int), dp, i64p]
@@ -75,6 +76,11 @@ class OracleContext:
         dJ, idx = C.c_double(0.0), C.c_int64(0)
         assert self.lib.lwo_full_stokes(C.byref(self._cs), self.col, int(updateJ), int(upOnly), C.byref(dJ), C.byref(idx)) == 0
         return dJ.value, idx.value
+
+    def nr_post_update(self, upd):
+        """upd: capi.LwB200NrUpdate"""
+        if self.lib.lwo_nr_post_update(C.byref(self._cs), self.col, C.byref(upd)) != 0:
+            raise RuntimeError('Singular Matrix')
 
     def time_dep_update(self, atom, nOld, dt):
         nOld = np.ascontiguousarray(nOld, dtype=np.float64)

@@ -101,6 +101,8 @@ int lwref_create(const LwB200Problem* p, int col, const char* scheme, int Nthrea
         if (p->vlosMu)
             a.vlosMu = F64View2D(const_cast<f64*>(p->vlosMu) + c * M * K, M, K);
         a.muz = F64View(const_cast<f64*>(p->muz), M);
+        if (p->ne)
+            a.ne = F64View(p->ne + c * K, K);
         a.wmu = F64View(const_cast<f64*>(p->wmu), M);
 
         auto set_bc = [&](AtmosphericBoundaryCondition& bc, int type, int Nmu,
@@ -173,7 +175,7 @@ int lwref_create(const LwB200Problem* p, int col, const char* scheme, int Nthrea
             atom.nTotal = F64View(const_cast<f64*>(pa.nTotal) + c * K, K);
             if (pa.vBroad)
                 atom.vBroad = F64View(const_cast<f64*>(pa.vBroad) + c * K, K);
-            atom.stages = F64View(h->stagesDummy.data(), N);
+            atom.stages = pa.stages ? F64View(const_cast<f64*>(pa.stages), N) : F64View(h->stagesDummy.data(), N);
             if (!pa.detailedStatic)
             {
                 if (!pa.Gamma)
@@ -349,6 +351,38 @@ int lwref_full_stokes(LwRefHandle* hh, int updateJ, int upOnly, double* dJMax, i
         IterationResult r = formal_sol_full_stokes(*h->ctx, updateJ != 0, upOnly != 0, ExtraParams{});
         if (dJMax) *dJMax = r.dJMax;
         if (dJMaxIdx) *dJMaxIdx = r.dJMaxIdx;
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// nr_post_update (LwContext._nr_post_update_impl, LwMiddleLayer.pyx:3533-3564) on this column.
+int lwref_nr_post_update(LwRefHandle* hh, const LwB200NrUpdate* u)
+{
+    auto* h = (LwRef*)hh;
+    try
+    {
+        const i64 K = h->prob->Nspace, c = h->col;
+        std::vector<Atom*> atoms;
+        std::vector<F64View3D> dC;
+        NrTimeDependentData td{};
+        td.dt = u->dt;
+        for (int a = 0; a < u->Natom; ++a)
+        {
+            Atom* atom = &h->atoms.at(u->atomIdx[a]);
+            const i64 N = atom->Nlevel;
+            atoms.push_back(atom);
+            if (u->dC)
+                dC.emplace_back(const_cast<f64*>(u->dC[a]) + c * N * N * K, N, N, K);
+            if (u->timeDependent)
+                td.nPrev.emplace_back(const_cast<f64*>(u->nPrev[a]) + c * N * K, N, K);
+        }
+        nr_post_update(*h->ctx, &atoms, dC, F64View(const_cast<f64*>(u->backgroundNe) + c * K, K), td, u->crswVal,
+                       ExtraParams{}, -1, -1);
         return 0;
     }
     catch (const std::exception& e)

@@ -61,6 +61,7 @@ def load():
     lib.lwref_formal_sol.argtypes = [vp, C.c_int]
     lib.lwref_stat_eq.argtypes = [vp]
     lib.lwref_full_stokes.argtypes = [vp, C.c_int, C.c_int, dp, C.POINTER(C.c_int64)]
+    lib.lwref_nr_post_update.argtypes = [vp, vp]
     lib.lwref_time_dep_update.argtypes = [vp, C.c_int, dp, C.c_double]
     lib.lwref_redistribute_prd.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp,
                                            C.POINTER(C.c_int), dp, C.POINTER(C.c_int64)]
@@ -109,6 +110,10 @@ class RefContext:
         dJ, idx = C.c_double(0.0), C.c_int64(0)
         _check(self.lib.lwref_full_stokes(self.h, int(updateJ), int(upOnly), C.byref(dJ), C.byref(idx)))
         return dJ.value, idx.value
+
+    def nr_post_update(self, upd):
+        """upd: capi.LwB200NrUpdate"""
+        _check(self.lib.lwref_nr_post_update(self.h, C.byref(upd)))
 
     def time_dep_update(self, activeIdx, nOld, dt):
         """nOld: [Nlevel, Nspace] of this context's column"""

@@ -317,6 +317,28 @@ def test_cuda_stokes_vs_oracle_columns(ndepth):
     ctx.close()
 
 
+@pytest.mark.parametrize('timeDep,useDC', [(False, False), (True, True)])
+def test_nr_post_update_matches_oracle(timeDep, useDC):
+    """Newton-Raphson step with charge conservation (nr_post_update_impl): two atoms coupled through
+    the electron density, on a perturbed two-column stack."""
+    from tests.test_oracle import nr_case
+    p = synth.config_c1(nl=0.3, ncol=2, perturb=True)
+    q = p.clone()
+    ctx = Context(p)
+    ctx.formal_sol_gamma_matrices()
+    oracle_iter(q, stat_eq=False)
+    idx, bg, dC, nPrev = nr_case(q, timeDep, useDC)
+    td = {'dt': 0.05, 'nPrev': nPrev} if timeDep else None
+    ctx.nr_post_update(idx, dC if dC is not None else [], bg, timeDependentData=td)
+    upd, keep = capi.make_nr_update(idx, bg, dC=dC, nPrev=nPrev, dt=0.05, crswVal=1.0)
+    for c in range(q.Ncol):
+        oraclelib.OracleContext(q, col=c).nr_post_update(upd)
+    for a, b in zip(p.atoms, q.atoms):
+        assert rel_err(a.n, b.n) <= 1e-7     # (sum Nlevel + 1)^2 Newton system: conditioning ~1e8 x rounding
+    assert rel_err(p.ne, q.ne) <= 1e-7
+    ctx.close()
+
+
 def test_time_dependent_update_matches_oracle():
     """Backward-Euler population step (time_dependent_update_impl) on a perturbed two-column stack."""
     p = synth.tiny_problem(ncol=2, perturb=True)

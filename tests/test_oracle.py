@@ -154,6 +154,36 @@ def test_oracle_stokes_vs_reference_live():
     assert np.abs(p.Quv).max() > 1e-3 * p.I.max()
 
 
+def nr_case(pr, timeDep, useDC):
+    """A synthetic Newton-Raphson update for every active atom of problem pr."""
+    idx = [i for i, a in enumerate(pr.atoms) if not a.detailedStatic]
+    bg = np.ascontiguousarray(pr.ne - 0.9 * sum((pr.atoms[i].stages[None, :, None] * pr.atoms[i].n).sum(axis=1) for i in idx))
+    dC = [1e-3 * pr.atoms[i].C / pr.ne[:, None, None, :] for i in idx] if useDC else None
+    nPrev = ([pr.atoms[i].n * (1.0 + 0.01 * np.sin(np.arange(pr.Nspace)))[None, None, :] for i in idx]
+             if timeDep else None)
+    return idx, bg, dC, nPrev
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize('timeDep,useDC', [(False, False), (False, True), (True, False), (True, True)])
+def test_oracle_nr_post_update_vs_reference(timeDep, useDC):
+    """nr_post_update_impl (charge-conserving Newton-Raphson step): restatement against the compiled
+    reference, bit level, two atoms coupled through ne."""
+    p = synth.config_c1(nl=0.3)
+    q = p.clone()
+    r, o = reflib.RefContext(p), oraclelib.OracleContext(q)
+    for pr, ctx in ((p, r), (q, o)):
+        pr.prefill_gamma()
+        ctx.fs_iter()
+        idx, bg, dC, nPrev = nr_case(pr, timeDep, useDC)
+        upd, keep = capi.make_nr_update(idx, bg, dC=dC, nPrev=nPrev, dt=0.05, crswVal=1.0)
+        ctx.nr_post_update(upd)
+    for a, b in zip(p.atoms, q.atoms):
+        assert np.array_equal(a.n, b.n)
+    assert np.array_equal(p.ne, q.ne) and np.all(np.isfinite(p.ne))
+    r.close()
+
+
 @pytest.mark.ref
 def test_oracle_time_dep_update_vs_reference():
     """time_dependent_update_impl: restatement against the compiled reference (bit level)."""
@@ -315,8 +345,8 @@ def test_struct_layout_matches_header():
     """ctypes mirrors of the POD structs have the C sizes (LP64)."""
     import ctypes as C
     assert C.sizeof(capi.LwB200Transition) == 6 * 4 + 5 * 8 + 10 * 8
-    assert C.sizeof(capi.LwB200Atom) == 4 * 4 + 7 * 8
-    assert C.sizeof(capi.LwB200Problem) == 12 * 4 + 20 * 8
+    assert C.sizeof(capi.LwB200Atom) == 4 * 4 + 8 * 8
+    assert C.sizeof(capi.LwB200Problem) == 12 * 4 + 21 * 8
 
 
 def test_create_fails_loudly_without_gpu():

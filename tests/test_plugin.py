@@ -135,6 +135,29 @@ def test_reference_core_full_stokes_through_the_b200_scheme():
 @needs_plugin
 @pytest.mark.ref
 @pytest.mark.gpu
+def test_reference_core_nr_post_update_through_the_b200_scheme():
+    """nr_post_update dispatches to the scheme's slot: Newton-Raphson step with charge conservation."""
+    from tests.test_oracle import nr_case
+    p = synth.config_c1(nl=0.3)
+    q = p.clone()
+    gpu = reflib.RefContext(p, scheme=PLUGIN)
+    cpu = reflib.RefContext(q, scheme='scalar')
+    for prob, ctx in ((p, gpu), (q, cpu)):
+        prob.prefill_gamma()
+        ctx.fs_iter()
+        idx, bg, dC, nPrev = nr_case(prob, True, True)
+        upd, keep = capi.make_nr_update(idx, bg, dC=dC, nPrev=nPrev, dt=0.05, crswVal=1.0)
+        ctx.nr_post_update(upd)
+    for a, b in zip(p.atoms, q.atoms):
+        assert rel_err(a.n, b.n) <= 1e-7
+    assert rel_err(p.ne, q.ne) <= 1e-7
+    gpu.close()
+    cpu.close()
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.gpu
 def test_reference_core_time_dep_update_through_the_b200_scheme():
     p = synth.tiny_problem(perturb=True)
     q = p.clone()
