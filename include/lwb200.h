@@ -163,6 +163,8 @@ enum {
     LWB200_GENERAL_KERNEL = 1u << 3, /* run every wavelength through the general per-ray accumulation
                                         kernel (normally only wavelengths with > 3 overlapping lines);
                                         a cross-check of the moment pipeline, not a fast path */
+    LWB200_DJ_ASYNC       = 1u << 5, /* reduce dJ and send (max, index) to pinned host memory with the stream,
+                                        without synchronising; read it with lwb200_last_dj after lwb200_sync */
     LWB200_FETCH_EARLY    = 1u << 4  /* start copying J and I back to the host buffers as soon as the rays
                                         are done, overlapped with the Gamma accumulation; a following
                                         lwb200_download(JBAR | INTENS) then only waits for that copy */
@@ -246,6 +248,14 @@ int lwb200_stat_eq(LwB200Context* ctx, int32_t atom, int32_t kStart, int32_t kEn
  * Quv at wavelengths without a polarised line is 0 (the reference leaves whatever the last polarised
  * ray left in its scratch there). */
 int lwb200_formal_sol_full_stokes(LwB200Context* ctx, int updateJ, int upOnly, double* dJMax, int64_t* dJMaxIdx);
+
+/* Latency-hiding variants for a host that synchronises once per call sequence (the Python mirror):
+ * lwb200_stat_eq_async launches the solve and sends the singular-system count home with the stream;
+ * lwb200_last_singular / lwb200_last_dj read those results after the next lwb200_sync
+ * (lwb200_last_singular fails with "Singular Matrix" like lwb200_stat_eq). */
+int lwb200_stat_eq_async(LwB200Context* ctx, int32_t atom, int32_t kStart, int32_t kEnd);
+int lwb200_last_singular(LwB200Context* ctx, int32_t* nSingular);
+int lwb200_last_dj(LwB200Context* ctx, double* dJMax, int64_t* dJMaxIdx);
 
 /* Replaces time_dependent_update_impl (Source/UpdatePopulations.cpp:120-151;
  * FsIterationFns::time_dep_update, LwFormalInterface.hpp:120): backward-Euler population update

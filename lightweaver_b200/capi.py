@@ -24,7 +24,7 @@ ALL_INPUTS = 0x7f
 ITER_INPUTS = POPS | NSTAR | GAMMA
 ITER_OUTPUTS = GAMMA | JBAR | INTENS | RATES
 
-LAMBDA_ITERATE, STORE_DEPTH, DEFER_FINALISE, GENERAL_KERNEL, FETCH_EARLY = 1, 2, 4, 8, 16
+LAMBDA_ITERATE, STORE_DEPTH, DEFER_FINALISE, GENERAL_KERNEL, FETCH_EARLY, DJ_ASYNC = 1, 2, 4, 8, 16, 32
 
 BUF_ACCUM, BUF_J, BUF_I, BUF_POPS, BUF_GAMMA, BUF_DJ = range(6)
 
@@ -162,6 +162,9 @@ def load():
                                             _ip, _dp, C.POINTER(C.c_int64)]
     lib.lwb200_formal_sol_full_stokes.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.lwb200_nr_post_update.argtypes = [vp, C.POINTER(LwB200NrUpdate), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    lib.lwb200_stat_eq_async.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    lib.lwb200_last_singular.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.lwb200_last_dj.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.lwb200_time_dep_update.argtypes = [vp, C.c_int32, _dp, C.c_double, C.c_int32, C.c_int32,
                                            C.POINTER(C.c_int32)]
     lib.lwb200_kernel_time.argtypes = [vp, C.POINTER(C.c_double)]
@@ -170,7 +173,7 @@ def load():
                                       C.POINTER(C.c_int64)]
     for name in ('device_count', 'create', 'destroy', 'set_stream', 'set_lambda_range', 'upload',
                  'download', 'sync', 'compute_profiles', 'fs_iter', 'finalise', 'dj_max',
-                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes', 'nr_post_update'):
+                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes', 'nr_post_update', 'stat_eq_async', 'last_singular', 'last_dj'):
         getattr(lib, 'lwb200_' + name).restype = C.c_int
     if lib.lwb200_abi_version() != ABI_VERSION:
         raise LwB200Error('liblwb200.so ABI version mismatch; rebuild')
@@ -191,5 +194,5 @@ EXPORTED_SYMBOLS = [
     'lwb200_finalise', 'lwb200_dj_max', 'lwb200_formal_sol', 'lwb200_stat_eq',
     'lwb200_device_buffer', 'lwb200_work_stats', 'lwb200_kernel_time', 'lwb200_redistribute_prd',
     'lwb200_time_dep_update', 'lwb200_formal_sol_full_stokes',
-    'lwb200_nr_post_update',
+    'lwb200_nr_post_update', 'lwb200_stat_eq_async', 'lwb200_last_singular', 'lwb200_last_dj',
 ]

@@ -173,10 +173,15 @@ class Context:
             self.crsw = crsw
         self.problem.prefill_gamma(self.crsw)
         self.upload(capi.ITER_INPUTS)
-        dJ, idx = self.fs_iter_device(lambdaIterate=lambdaIterate, storeDepth=storeDepth,
-                                      generalKernel=general, fetchEarly=True)
+        # one host synchronisation for the whole call: dJ comes home with the stream (DJ_ASYNC), J and I
+        # start travelling as soon as the rays are done (FETCH_EARLY)
+        flags = ((capi.LAMBDA_ITERATE if lambdaIterate else 0) | (capi.STORE_DEPTH if storeDepth else 0)
+                 | (capi.GENERAL_KERNEL if general else 0) | capi.FETCH_EARLY | capi.DJ_ASYNC)
+        capi.check(self.lib.lwb200_fs_iter(self._h, flags, None, None))
         self.download(capi.ITER_OUTPUTS | (capi.DEPTH if storeDepth else 0))
-        return IterationUpdate(updatedJ=True, dJMax=dJ, dJMaxIdx=idx % self.problem.Nspect,
+        dJ, idx = C.c_double(), C.c_int64()
+        capi.check(self.lib.lwb200_last_dj(self._h, C.byref(dJ), C.byref(idx)))
+        return IterationUpdate(updatedJ=True, dJMax=dJ.value, dJMaxIdx=idx.value % self.problem.Nspect,
                                crsw=self.crsw)
 
     def formal_sol(self, upOnly=True, extraParams=None):
@@ -239,8 +244,13 @@ class Context:
         (what rel_diff_ng_accelerate reports without Ng acceleration)."""
         prev = [a.n.copy() for a in self.problem.active_atoms()]
         self.upload(capi.POPS | capi.GAMMA_FINAL)
-        self.stat_eq_device()
-        self.download(capi.POPS)
+        capi.check(self.lib.lwb200_stat_eq_async(self._h, -1, -1, -1))
+        self.download(capi.POPS)   # (synchronises)
+        ns = C.c_int32(0)
+        if self.lib.lwb200_last_singular(self._h, C.byref(ns)) != 0:
+            if ns.value > 0:
+                raise ExplodingMatrixError('Singular Matrix')
+            capi.check(1)
         upd = IterationUpdate(updatedPops=True)
         for p, a in zip(prev, self.problem.active_atoms()):
             with np.errstate(divide='ignore', invalid='ignore'):

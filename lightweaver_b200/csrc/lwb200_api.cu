@@ -127,6 +127,13 @@ struct PipelineLists
 
 struct LwB200Context
 {
+    // results of the *_async calls, in pinned host memory: valid after the next lwb200_sync
+    struct HostScalars
+    {
+        double dJ;
+        long long dJIdx;
+        int nSingular;
+    }* hs = nullptr;
     bool customLists = false; // launch_fs uses prdPl instead of the context-wide lists (PRD and Stokes passes)
     PipelineLists prdPl{};
     int stokesFsMode = 0; // != 0: the pass is a full-Stokes formal solution (always Bezier3)
@@ -136,7 +143,7 @@ struct LwB200Context
     cudaEvent_t evK0 = nullptr, evK1 = nullptr;
     cudaStream_t copyStream = nullptr;
     cudaEvent_t evRays = nullptr, evCopy = nullptr;
-    bool fetchEarly = false, fetched = false;
+    bool fetchEarly = false, fetched = false, outputsPinned = false;
     cudaStream_t sideStream[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t evFork = nullptr, evJoin[4] = {nullptr, nullptr, nullptr, nullptr};
     bool kernelTimed = false;
@@ -882,17 +889,23 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
         }
         if (fsMode != 0)
             continue;
-        if (c->fetchEarly && !pl.prdOnly && c->nListDirect == 0 && colBase + nb >= Ncol)
+        if (c->fetchEarly && !pl.prdOnly && c->nListDirect == 0)
         {
-            // J and I are final: send them home on the copy stream while Gamma is accumulated
+            // J and I of this batch of columns are final: send them home on the copy stream while
+            // Gamma is accumulated (and, in a column stack, while the next batches are computed)
             const LwB200Problem& p = c->prob;
-            const size_t nJ = (size_t)p.Ncol * p.Nspect * p.Nspace, nI = (size_t)p.Ncol * p.Nspect * p.Nrays;
+            const size_t perJ = (size_t)p.Nspect * p.Nspace, perI = (size_t)p.Nspect * p.Nrays;
             CU(cudaEventRecord(c->evRays, c->stream));
             CU(cudaStreamWaitEvent(c->copyStream, c->evRays, 0));
-            CU(cudaMemcpyAsync(p.J, c->J.p, nJ * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
-            CU(cudaMemcpyAsync(p.I, c->I.p, nI * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
-            CU(cudaEventRecord(c->evCopy, c->copyStream));
-            c->fetched = true;
+            CU(cudaMemcpyAsync(p.J + colBase * perJ, c->J.p + colBase * perJ, nb * perJ * sizeof(double),
+                               cudaMemcpyDeviceToHost, c->copyStream));
+            CU(cudaMemcpyAsync(p.I + colBase * perI, c->I.p + colBase * perI, nb * perI * sizeof(double),
+                               cudaMemcpyDeviceToHost, c->copyStream));
+            if (colBase + nb >= Ncol)
+            {
+                CU(cudaEventRecord(c->evCopy, c->copyStream));
+                c->fetched = true;
+            }
         }
         if (pl.nMoment > 0)
         {
@@ -1090,15 +1103,18 @@ int lwb200_create(const LwB200Problem* problem, int device, LwB200Context** out)
         lwb200_destroy(c);
         return 1;
     }
-    // pin the two large per-iteration outputs in place (J, I) so that their
-    // device->host copies are true async DMA; failure to pin is not an error
+    // pin the two per-iteration outputs J and I in place so that their device->host copies are
+    // true async DMA -- both, whatever their size: a copy into pageable memory blocks the host until
+    // the stream reaches it, which would serialise the launch of everything behind the early fetch
+    // (LWB200_FETCH_EARLY).  Failure to pin is not an error (the early fetch is then skipped).
     {
         const size_t nJ = (size_t)problem->Ncol * problem->Nspect * problem->Nspace * sizeof(double);
         const size_t nI = (size_t)problem->Ncol * problem->Nspect * problem->Nrays * sizeof(double);
-        if (nJ >= (1u << 20) && cudaHostRegister(problem->J, nJ, cudaHostRegisterDefault) == cudaSuccess)
+        if (nJ > 0 && cudaHostRegister(problem->J, nJ, cudaHostRegisterDefault) == cudaSuccess)
             c->registered.push_back(problem->J);
-        if (nI >= (1u << 20) && cudaHostRegister(problem->I, nI, cudaHostRegisterDefault) == cudaSuccess)
+        if (nI > 0 && cudaHostRegister(problem->I, nI, cudaHostRegisterDefault) == cudaSuccess)
             c->registered.push_back(problem->I);
+        c->outputsPinned = c->registered.size() == 2;
         cudaGetLastError();
     }
     *out = c;
@@ -1141,6 +1157,8 @@ int lwb200_destroy(LwB200Context* c)
             cudaStreamDestroy(c->sideStream[q]);
         }
     }
+    if (c->hs)
+        cudaFreeHost(c->hs);
     if (c->evK0)
         cudaEventDestroy(c->evK0);
     if (c->evK1)
@@ -1551,6 +1569,53 @@ int lwb200_finalise(LwB200Context* c)
     return 0;
 }
 
+static int ensure_host_scalars(LwB200Context* c)
+{
+    if (c->hs)
+        return 0;
+    CU(cudaHostAlloc((void**)&c->hs, sizeof(*c->hs), cudaHostAllocDefault));
+    c->hs->dJ = 0.0;
+    c->hs->dJIdx = 0;
+    c->hs->nSingular = 0;
+    return 0;
+}
+
+// dJ reduction whose result lands in pinned host memory with the stream (no host synchronisation)
+static int dj_max_async(LwB200Context* c)
+{
+    if (ensure_host_scalars(c))
+        return 1;
+    dj_reduce_kernel<<<1, 256, 0, c->stream>>>(c->dJ.p, c->P.Ncol, c->P.L, c->laLo, c->laHi, c->djOut.p,
+                                               c->djIdx.p);
+    CU(cudaGetLastError());
+    c->lastLaunches += 1;
+    CU(cudaMemcpyAsync(&c->hs->dJ, c->djOut.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&c->hs->dJIdx, c->djIdx.p, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+int lwb200_last_dj(LwB200Context* c, double* dJMax, int64_t* dJMaxIdx)
+{
+    if (!c->hs)
+        return fail("lwb200_last_dj: no asynchronous dJ reduction has been requested");
+    if (dJMax)
+        *dJMax = c->hs->dJ;
+    if (dJMaxIdx)
+        *dJMaxIdx = c->hs->dJIdx;
+    return 0;
+}
+
+int lwb200_last_singular(LwB200Context* c, int32_t* nSingular)
+{
+    if (!c->hs)
+        return fail("lwb200_last_singular: no asynchronous population update has been requested");
+    if (nSingular)
+        *nSingular = c->hs->nSingular;
+    if (c->hs->nSingular > 0)
+        return fail("Singular Matrix");
+    return 0;
+}
+
 int lwb200_dj_max(LwB200Context* c, double* dJMax, int64_t* dJMaxIdx)
 {
     CU(cudaSetDevice(c->device));
@@ -1577,7 +1642,7 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
         return fail("lwb200_fs_iter: inputs have not been uploaded (lwb200_upload)");
     const int storeDepth = (flags & LWB200_STORE_DEPTH) ? 1 : 0;
     c->forceDirect = (flags & LWB200_GENERAL_KERNEL) != 0;
-    c->fetchEarly = (flags & LWB200_FETCH_EARLY) != 0 && !c->forceDirect;
+    c->fetchEarly = (flags & LWB200_FETCH_EARLY) != 0 && !c->forceDirect && c->outputsPinned;
     if (c->fetched)
     {
         // an early copy nobody collected: it must not race with this iteration's writes of J
@@ -1594,6 +1659,8 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
     if (!(flags & LWB200_DEFER_FINALISE))
         if (lwb200_finalise(c))
             return 1;
+    if (flags & LWB200_DJ_ASYNC)
+        return dj_max_async(c);
     if (dJMax || dJMaxIdx)
         return lwb200_dj_max(c, dJMax, dJMaxIdx);
     return 0;
@@ -1609,7 +1676,7 @@ int lwb200_formal_sol(LwB200Context* c, int upOnly)
 }
 
 static int population_update(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd, int32_t* nSingular,
-                             const double* nOldHost, double dt, const char* who)
+                             const double* nOldHost, double dt, const char* who, bool async = false)
 {
     CU(cudaSetDevice(c->device));
     const int K = c->prob.Nspace;
@@ -1664,6 +1731,13 @@ static int population_update(LwB200Context* c, int32_t atom, int32_t kStart, int
             c->lastLaunches += 1;
         }
     }
+    if (async)
+    {
+        if (ensure_host_scalars(c))
+            return 1;
+        CU(cudaMemcpyAsync(&c->hs->nSingular, c->dSingular.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        return 0;
+    }
     int ns = 0;
     CU(cudaMemcpyAsync(&ns, c->dSingular.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1677,6 +1751,11 @@ static int population_update(LwB200Context* c, int32_t atom, int32_t kStart, int
 int lwb200_stat_eq(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd, int32_t* nSingular)
 {
     return population_update(c, atom, kStart, kEnd, nSingular, nullptr, 0.0, "lwb200_stat_eq");
+}
+
+int lwb200_stat_eq_async(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd)
+{
+    return population_update(c, atom, kStart, kEnd, nullptr, nullptr, 0.0, "lwb200_stat_eq_async", true);
 }
 
 int lwb200_time_dep_update(LwB200Context* c, int32_t atom, const double* nOld, double dt, int32_t kStart,

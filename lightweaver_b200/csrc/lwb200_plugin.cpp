@@ -329,7 +329,8 @@ IterationResult b200_fs_iter(Context& ctx, bool lambdaIterate, ExtraParams param
 {
     Mirror& m = mirror_for(ctx);
     sync_inputs(ctx, m, true);
-    uint32_t flags = (lambdaIterate ? LWB200_LAMBDA_ITERATE : 0) | LWB200_FETCH_EARLY;
+    // one host synchronisation per call: dJ and J / I travel with the stream
+    uint32_t flags = (lambdaIterate ? LWB200_LAMBDA_ITERATE : 0) | LWB200_FETCH_EARLY | LWB200_DJ_ASYNC;
     const bool storeDepth = ctx.depthData && ctx.depthData->fill;
     if (storeDepth)
         flags |= LWB200_STORE_DEPTH;
@@ -337,9 +338,10 @@ IterationResult b200_fs_iter(Context& ctx, bool lambdaIterate, ExtraParams param
         flags |= LWB200_GENERAL_KERNEL;
     double dJMax = 0.0;
     int64_t dJIdx = 0;
-    check(lwb200_fs_iter(m.dev, flags, &dJMax, &dJIdx), "lwb200_fs_iter");
+    check(lwb200_fs_iter(m.dev, flags, nullptr, nullptr), "lwb200_fs_iter");
     check(lwb200_download(m.dev, LWB200_ITER_OUTPUTS | (storeDepth ? LWB200_DEPTH : 0)), "lwb200_download");
     check(lwb200_sync(m.dev), "lwb200_sync");
+    check(lwb200_last_dj(m.dev, &dJMax, &dJIdx), "lwb200_last_dj");
     m.fpJ = fingerprint(1469598103934665603ULL, m.prob.J, (size_t)m.prob.Nspect * m.prob.Nspace);
     IterationResult result{};
     result.updatedJ = true;
@@ -482,15 +484,16 @@ void b200_stat_eq(Atom* atom, ExtraParams params, int spaceStart, int spaceEnd)
         return;
     }
     check(lwb200_upload(m->dev, LWB200_POPS | LWB200_GAMMA_FINAL), "lwb200_upload");
+    check(lwb200_stat_eq_async(m->dev, idx, spaceStart, spaceEnd), "lwb200_stat_eq_async");
+    check(lwb200_download(m->dev, LWB200_POPS), "lwb200_download");
+    check(lwb200_sync(m->dev), "lwb200_sync");
     int32_t nSingular = 0;
-    if (lwb200_stat_eq(m->dev, idx, spaceStart, spaceEnd, &nSingular) != 0)
+    if (lwb200_last_singular(m->dev, &nSingular) != 0)
     {
         if (nSingular > 0)
             throw std::runtime_error("Singular Matrix"); // as lu_decompose does, LuSolve.cpp:22-23
-        raise("lwb200_stat_eq");
+        raise("lwb200_stat_eq_async");
     }
-    check(lwb200_download(m->dev, LWB200_POPS), "lwb200_download");
-    check(lwb200_sync(m->dev), "lwb200_sync");
 }
 
 // FsIterationFns::time_dep_update (LwFormalInterface.hpp:120): backward-Euler step of one atom.
