@@ -265,11 +265,13 @@ def run_ours(args, rank, world, local_rank):
         if world > 1 and not column_sharded:
             sharding.sharded_gamma_iteration(shard, group=None, want_dJ=False)
         else:
-            ctx.fs_iter_device(want_dJ=False)
+            # dJ and the singular-matrix flag come home with the stream (pinned memory): the
+            # iteration loop is never stalled by a host round trip; both are checked below
+            ctx.fs_iter_device(asyncDJ=True)
         if with_prd:
             ctx.prd_redistribute_device(maxIter=3, tol=1e-2)
         else:
-            ctx.stat_eq_device()
+            ctx.stat_eq_device(wait=False)
 
     def barrier():
         if world > 1:
@@ -289,7 +291,7 @@ def run_ours(args, rank, world, local_rank):
         sharding.sharded_gamma_iteration(shard, group=None, want_dJ=False)
         per_step += 1  # the all-reduce
     else:
-        ctx.fs_iter_device(want_dJ=False)
+        ctx.fs_iter_device(asyncDJ=True)
     if not stokes:
         per_step += ctx.work_stats()[2]
     if stokes:
@@ -297,7 +299,7 @@ def run_ours(args, rank, world, local_rank):
     elif with_prd:
         ctx.prd_redistribute_device(maxIter=3, tol=1e-2)
     else:
-        ctx.stat_eq_device()
+        ctx.stat_eq_device(wait=False)
     if not stokes:
         per_step += ctx.work_stats()[2]
     barrier()
@@ -316,6 +318,13 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     clk = clocks.stop()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if not stokes and not with_prd:
+        ctx.sync()
+        ctx.check_singular()   # raises if any timed step met a singular system
+        if not (world > 1 and not column_sharded):
+            dj_last = ctx.last_dj()[0]
+            if not (dj_last == dj_last and dj_last >= 0.0):
+                raise SystemExit(f'bench.py: bad dJ {dj_last}')
     if clk.get('samples', 0) < 3:
         # the timed region is shorter than nvidia-smi's sampling period (a 1D atmosphere is < 1 ms
         # per step): sample the clocks under the SAME step repeated, untimed, for about a second

@@ -252,7 +252,8 @@ int lwb200_formal_sol_full_stokes(LwB200Context* ctx, int updateJ, int upOnly, d
 /* Latency-hiding variants for a host that synchronises once per call sequence (the Python mirror):
  * lwb200_stat_eq_async launches the solve and sends the singular-system count home with the stream;
  * lwb200_last_singular / lwb200_last_dj read those results after the next lwb200_sync
- * (lwb200_last_singular fails with "Singular Matrix" like lwb200_stat_eq). */
+ * (lwb200_last_singular fails with "Singular Matrix" like lwb200_stat_eq; the count is cumulative over
+ * the asynchronous updates launched since it was last collected). */
 int lwb200_stat_eq_async(LwB200Context* ctx, int32_t atom, int32_t kStart, int32_t kEnd);
 int lwb200_last_singular(LwB200Context* ctx, int32_t* nSingular);
 int lwb200_last_dj(LwB200Context* ctx, double* dJMax, int64_t* dJMaxIdx);

@@ -119,12 +119,16 @@ class Context:
 
     # ------------------------------------------------- device-resident calls
     def fs_iter_device(self, lambdaIterate=False, storeDepth=False, deferFinalise=False,
-                       want_dJ=True, generalKernel=False, fetchEarly=False):
-        """One Gamma iteration on device-resident data (no host copies)."""
+                       want_dJ=True, generalKernel=False, fetchEarly=False, asyncDJ=False):
+        """One Gamma iteration on device-resident data (no host copies).  asyncDJ: dJ is reduced
+        on the device and travels with the stream; read it with last_dj() after a sync()."""
         flags = ((capi.LAMBDA_ITERATE if lambdaIterate else 0) | (capi.STORE_DEPTH if storeDepth else 0)
                  | (capi.DEFER_FINALISE if deferFinalise else 0)
                  | (capi.GENERAL_KERNEL if generalKernel else 0)
                  | (capi.FETCH_EARLY if fetchEarly else 0))
+        if asyncDJ:
+            capi.check(self.lib.lwb200_fs_iter(self._h, flags | capi.DJ_ASYNC, None, None))
+            return None
         if want_dJ:
             dJ, idx = C.c_double(), C.c_int64()
             capi.check(self.lib.lwb200_fs_iter(self._h, flags, C.byref(dJ), C.byref(idx)))
@@ -140,7 +144,27 @@ class Context:
         capi.check(self.lib.lwb200_dj_max(self._h, C.byref(dJ), C.byref(idx)))
         return dJ.value, idx.value
 
-    def stat_eq_device(self, atom=-1, kStart=-1, kEnd=-1):
+    def last_dj(self):
+        """(dJMax, flat index) of the last asyncDJ iteration; valid after sync()."""
+        dJ, idx = C.c_double(), C.c_int64()
+        capi.check(self.lib.lwb200_last_dj(self._h, C.byref(dJ), C.byref(idx)))
+        return dJ.value, idx.value
+
+    def check_singular(self):
+        """Raise ExplodingMatrixError if the last wait=False population update met a singular
+        system; valid after sync()."""
+        ns = C.c_int32(0)
+        if self.lib.lwb200_last_singular(self._h, C.byref(ns)) != 0:
+            if ns.value > 0:
+                raise ExplodingMatrixError('Singular Matrix')
+            capi.check(1)
+
+    def stat_eq_device(self, atom=-1, kStart=-1, kEnd=-1, wait=True):
+        """Statistical equilibrium on device-resident data.  wait=False: no host synchronisation;
+        call check_singular() after the next sync()."""
+        if not wait:
+            capi.check(self.lib.lwb200_stat_eq_async(self._h, atom, kStart, kEnd))
+            return
         ns = C.c_int32(0)
         rc = self.lib.lwb200_stat_eq(self._h, atom, kStart, kEnd, C.byref(ns))
         if rc != 0:

@@ -15,6 +15,7 @@
 #include <set>
 #include <string>
 #include <utility>
+#include <thread>
 #include <vector>
 
 using namespace lwb200;
@@ -110,6 +111,27 @@ struct Pending
     size_t bytes;
 };
 
+// Host-side pack / scatter of the per-atom arrays of a column stack: a few threads once the
+// copy is large enough to be worth them (one 1D atmosphere never is).
+template <typename F>
+static void host_parallel_for(size_t n, size_t bytes, F body)
+{
+    unsigned T = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (bytes < ((size_t)4 << 20) || n < 2 * T || T == 1)
+    {
+        body((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t per = (n + T - 1) / T;
+    for (unsigned t = 1; t < T; ++t)
+        if (t * per < n)
+            pool.emplace_back([=] { body(t * per, std::min(n, (t + 1) * per)); });
+    body((size_t)0, std::min(n, per));
+    for (auto& th : pool)
+        th.join();
+}
+
 // What one pass of the pipeline covers: every wavelength of the context's range (the Gamma
 // iteration) or the wavelengths touched by the redistributed PRD lines (rates-only pass).
 struct PipelineLists
@@ -133,7 +155,7 @@ struct LwB200Context
         double dJ;
         long long dJIdx;
         int nSingular;
-    }* hs = nullptr;
+    }* hs = nullptr, *hsDev = nullptr;
     bool customLists = false; // launch_fs uses prdPl instead of the context-wide lists (PRD and Stokes passes)
     PipelineLists prdPl{};
     int stokesFsMode = 0; // != 0: the pass is a full-Stokes formal solution (always Bezier3)
@@ -202,7 +224,12 @@ struct LwB200Context
     DevBuf<double> depthChi, depthEta, depthI, djOut;
     DevBuf<int> lowerBcIdx, upperBcIdx, dLaOff, dLaCnt, dTileLambda, dLaHasLine, dTileLa, dTileSlotOff, dTileSlotTrans;
     DevBuf<int> dAtomNlevel, dAtomLevOff, dAtomGammaOff, dAtomDetailed, dSingular, dPhiAsym;
-    DevBuf<long long> djIdx;
+    DevBuf<long long> djIdx, djPartIdx;
+    DevBuf<double> djPartMax;
+    DevBuf<unsigned> djTicket;
+    cudaEvent_t evDj = nullptr;
+    bool singularPending = false; // an asynchronous population update whose singular count is uncollected
+    bool djEarly = false, djDone = false; // dJ reduced on a side stream while Gamma is accumulated
     DevBuf<DevTrans> dTrans;
     DevBuf<DevEntry> dEntries;
     std::vector<DevLine> devLines;
@@ -360,7 +387,9 @@ int build_plan(LwB200Context* c)
     if ((long long)std::max(ncont, 1) * p.Ncol * K > 0x7fffffffLL)
         return fail("gRatio block exceeds 2^31 elements");
     const long long targetCtas = 148LL * 16;
-    const int tileLen = (int)std::max<long long>(4, std::min<long long>(32, ((long long)L * p.Ncol) / targetCtas));
+    int tileLen = (int)std::max<long long>(4, std::min<long long>(32, ((long long)L * p.Ncol) / targetCtas));
+    if (const char* e = std::getenv("LWB200_TILE_LEN")) // tuning aid
+        tileLen = std::max(1, std::atoi(e));
 
     std::vector<DevEntry> entries;
     std::vector<int> laCnt(L, 0);
@@ -581,7 +610,8 @@ int build_plan(LwB200Context* c)
         || c->rhoPrd.alloc((size_t)std::max<long long>(rhoOff, 1))
         || c->accum.alloc(ncol * AccTot * K) || c->prefill.alloc(ncol * std::max(GammaTot, 1) * K)
         || c->gamma.alloc(ncol * std::max(GammaTot, 1) * K) || c->dJ.alloc(ncol * L) || c->djOut.alloc(1)
-        || c->djIdx.alloc(1) || c->dSingular.alloc(1) || c->dPhiAsym.alloc(1))
+        || c->djIdx.alloc(1) || c->djPartIdx.alloc(256) || c->djPartMax.alloc(256) || c->djTicket.alloc(1)
+        || c->dSingular.alloc(1) || c->dPhiAsym.alloc(1))
         return 1;
     {
         const int one = 1; // until the profiles have been looked at, assume nothing
@@ -611,6 +641,7 @@ int build_plan(LwB200Context* c)
     CU(cudaMemset(c->prefill.p, 0, c->prefill.n * sizeof(double)));
     CU(cudaMemset(c->gamma.p, 0, c->gamma.n * sizeof(double)));
     CU(cudaMemset(c->dJ.p, 0, c->dJ.n * sizeof(double)));
+    CU(cudaMemset(c->djTicket.p, 0, sizeof(unsigned)));
     CU(cudaMemset(c->rhoPrd.p, 0, c->rhoPrd.n * sizeof(double)));
     if (p.depthChi && p.depthEta && p.depthI)
     {
@@ -771,6 +802,31 @@ int check_phi_symmetry(LwB200Context* c)
     return 0;
 }
 
+// (max, argmax) of dJ over [laLo, laHi) of every column into djOut / djIdx, on stream s
+static int launch_dj_reduce(LwB200Context* c, cudaStream_t s, int laLo, int laHi, const unsigned char* mask)
+{
+    const long long total = (long long)c->P.Ncol * (laHi - laLo);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(256, (total + 1023) / 1024));
+    dj_reduce_kernel<<<grid, 256, 0, s>>>(c->dJ.p, c->P.Ncol, c->P.L, laLo, laHi, c->djOut.p, c->djIdx.p, mask,
+                                          c->djPartMax.p, c->djPartIdx.p, c->djTicket.p);
+    CU(cudaGetLastError());
+    c->lastLaunches += 1;
+    return 0;
+}
+
+int ensure_host_scalars(LwB200Context* c)
+{
+    if (c->hs)
+        return 0;
+    // mapped: the population kernels count singular systems straight into it (no copy to wait for)
+    CU(cudaHostAlloc((void**)&c->hs, sizeof(*c->hs), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void**)&c->hsDev, c->hs, 0));
+    c->hs->dJ = 0.0;
+    c->hs->dJIdx = 0;
+    c->hs->nSingular = 0;
+    return 0;
+}
+
 int ensure_side_streams(LwB200Context* c)
 {
     if (c->evFork)
@@ -787,6 +843,7 @@ int ensure_side_streams(LwB200Context* c)
     CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->evRays, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->evCopy, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->evDj, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
     return 0;
 }
@@ -906,6 +963,20 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
                 CU(cudaEventRecord(c->evCopy, c->copyStream));
                 c->fetched = true;
             }
+        }
+        if (c->djEarly && colBase + nb >= Ncol)
+        {
+            // J is complete: reduce dJ on an idle side stream while Gamma is accumulated; the result
+            // lands in pinned host memory (HostScalars)
+            cudaStream_t sd = c->sideStream[0];
+            CU(cudaEventRecord(c->evRays, c->stream));
+            CU(cudaStreamWaitEvent(sd, c->evRays, 0));
+            if (launch_dj_reduce(c, sd, laLo, laHi, nullptr))
+                return 1;
+            CU(cudaMemcpyAsync(&c->hs->dJ, c->djOut.p, sizeof(double), cudaMemcpyDeviceToHost, sd));
+            CU(cudaMemcpyAsync(&c->hs->dJIdx, c->djIdx.p, sizeof(long long), cudaMemcpyDeviceToHost, sd));
+            CU(cudaEventRecord(c->evDj, sd));
+            c->djDone = true;
         }
         if (pl.nMoment > 0)
         {
@@ -1150,6 +1221,7 @@ int lwb200_destroy(LwB200Context* c)
         cudaEventDestroy(c->evFork);
         cudaEventDestroy(c->evRays);
         cudaEventDestroy(c->evCopy);
+        cudaEventDestroy(c->evDj);
         cudaStreamDestroy(c->copyStream);
         for (int q = 0; q < 4; ++q)
         {
@@ -1199,6 +1271,9 @@ int lwb200_destroy(LwB200Context* c)
     c->dListDirect.release();
     c->dListAll.release();
     c->djIdx.release();
+    c->djPartIdx.release();
+    c->djPartMax.release();
+    c->djTicket.release();
     c->dTrans.release();
     c->dEntries.release();
     c->dLines.release();
@@ -1225,8 +1300,14 @@ int lwb200_sync(LwB200Context* c)
 {
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    size_t bytes = 0;
     for (const Pending& q : c->pending)
-        std::memcpy(q.dst, q.src, q.bytes);
+        bytes += q.bytes;
+    const Pending* pend = c->pending.data();
+    host_parallel_for(c->pending.size(), bytes, [pend](size_t b, size_t e) {
+        for (size_t q = b; q < e; ++q)
+            std::memcpy(pend[q].dst, pend[q].src, pend[q].bytes);
+    });
     c->pending.clear();
     return 0;
 }
@@ -1273,8 +1354,11 @@ static int upload_packed(LwB200Context* c, Pinned& st, double* dev, int totalRow
         const size_t r = rows(a);
         if (!src || r == 0)
             continue;
-        for (size_t col = 0; col < ncol; ++col)
-            std::memcpy(st.p + (col * totalRows + off(a)) * K, src + col * r * K, r * K * sizeof(double));
+        double* dst = st.p + off(a) * K;
+        host_parallel_for(ncol, ncol * r * K * sizeof(double), [=](size_t b, size_t e) {
+            for (size_t col = b; col < e; ++col)
+                std::memcpy(dst + col * totalRows * K, src + col * r * K, r * K * sizeof(double));
+        });
     }
     CU(cudaMemcpyAsync(dev, st.p, total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(st.ev, c->stream));
@@ -1561,34 +1645,29 @@ int lwb200_finalise(LwB200Context* c)
     CU(cudaSetDevice(c->device));
     if (c->P.GammaTot > 0)
     {
-        const size_t total = (size_t)c->P.Ncol * c->P.Natom * c->P.K;
-        finalise_kernel<<<grid_for(total), 256, 0, c->stream>>>(c->P, c->prefill.p, c->gamma.p);
+        const size_t total = (size_t)c->P.Ncol * c->P.Natom * c->P.maxNlevel * c->P.K;
+        finalise_kernel<<<grid_for(total, 128), 128, 0, c->stream>>>(c->P, c->prefill.p, c->gamma.p);
         CU(cudaGetLastError());
         c->lastLaunches += 1;
     }
     return 0;
 }
 
-static int ensure_host_scalars(LwB200Context* c)
-{
-    if (c->hs)
-        return 0;
-    CU(cudaHostAlloc((void**)&c->hs, sizeof(*c->hs), cudaHostAllocDefault));
-    c->hs->dJ = 0.0;
-    c->hs->dJIdx = 0;
-    c->hs->nSingular = 0;
-    return 0;
-}
 
 // dJ reduction whose result lands in pinned host memory with the stream (no host synchronisation)
 static int dj_max_async(LwB200Context* c)
 {
     if (ensure_host_scalars(c))
         return 1;
-    dj_reduce_kernel<<<1, 256, 0, c->stream>>>(c->dJ.p, c->P.Ncol, c->P.L, c->laLo, c->laHi, c->djOut.p,
-                                               c->djIdx.p);
-    CU(cudaGetLastError());
-    c->lastLaunches += 1;
+    if (c->djDone)
+    {
+        // already reduced beside the Gamma stage
+        c->djDone = false;
+        CU(cudaStreamWaitEvent(c->stream, c->evDj, 0));
+        return 0;
+    }
+    if (launch_dj_reduce(c, c->stream, c->laLo, c->laHi, nullptr))
+        return 1;
     CU(cudaMemcpyAsync(&c->hs->dJ, c->djOut.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(&c->hs->dJIdx, c->djIdx.p, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     return 0;
@@ -1609,6 +1688,7 @@ int lwb200_last_singular(LwB200Context* c, int32_t* nSingular)
 {
     if (!c->hs)
         return fail("lwb200_last_singular: no asynchronous population update has been requested");
+    c->singularPending = false;
     if (nSingular)
         *nSingular = c->hs->nSingular;
     if (c->hs->nSingular > 0)
@@ -1619,10 +1699,19 @@ int lwb200_last_singular(LwB200Context* c, int32_t* nSingular)
 int lwb200_dj_max(LwB200Context* c, double* dJMax, int64_t* dJMaxIdx)
 {
     CU(cudaSetDevice(c->device));
-    dj_reduce_kernel<<<1, 256, 0, c->stream>>>(c->dJ.p, c->P.Ncol, c->P.L, c->laLo, c->laHi, c->djOut.p,
-                                               c->djIdx.p);
-    CU(cudaGetLastError());
-    c->lastLaunches += 1;
+    if (c->djDone)
+    {
+        c->djDone = false;
+        CU(cudaStreamWaitEvent(c->stream, c->evDj, 0));
+        CU(cudaStreamSynchronize(c->stream));
+        if (dJMax)
+            *dJMax = c->hs->dJ;
+        if (dJMaxIdx)
+            *dJMaxIdx = c->hs->dJIdx;
+        return 0;
+    }
+    if (launch_dj_reduce(c, c->stream, c->laLo, c->laHi, nullptr))
+        return 1;
     double m = 0.0;
     long long idx = 0;
     CU(cudaMemcpyAsync(&m, c->djOut.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1652,9 +1741,16 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
     if (storeDepth && !c->depthChi.p)
         return fail("lwb200_fs_iter: STORE_DEPTH without depth arrays in the problem");
     c->lastLaunches = 0;
+    const bool wantDj = (flags & LWB200_DJ_ASYNC) || dJMax || dJMaxIdx;
+    c->djDone = false;
+    c->djEarly = wantDj && !c->forceDirect && c->nListDirect == 0;
+    if (c->djEarly && ensure_host_scalars(c))
+        return 1;
     // zero_rates + fresh partial sums (:605-612, :643)
     CU(cudaMemsetAsync(c->accum.p, 0, c->accum.n * sizeof(double), c->stream));
-    if (launch_fs<MODE_ITER>(c, (flags & LWB200_LAMBDA_ITERATE) ? 1 : 0, 0, storeDepth))
+    const int rcFs = launch_fs<MODE_ITER>(c, (flags & LWB200_LAMBDA_ITERATE) ? 1 : 0, 0, storeDepth);
+    c->djEarly = false;
+    if (rcFs)
         return 1;
     if (!(flags & LWB200_DEFER_FINALISE))
         if (lwb200_finalise(c))
@@ -1690,7 +1786,19 @@ static int population_update(LwB200Context* c, int32_t atom, int32_t kStart, int
     if (atom >= c->prob.Natom)
         return fail(std::string(who) + ": atom index out of range");
     c->lastLaunches = 0;
-    CU(cudaMemsetAsync(c->dSingular.p, 0, sizeof(int), c->stream));
+    // asynchronous updates count singular systems cumulatively until lwb200_last_singular collects them
+    int* dSingular = c->dSingular.p;
+    if (async)
+    {
+        if (ensure_host_scalars(c))
+            return 1;
+        if (!c->singularPending)
+            c->hs->nSingular = 0;
+        dSingular = &c->hsDev->nSingular;
+    }
+    else
+        CU(cudaMemsetAsync(c->dSingular.p, 0, sizeof(int), c->stream));
+    c->singularPending = async;
     const double* nOldDev = nullptr;
     if (nOldHost)
     {
@@ -1720,24 +1828,19 @@ static int population_update(LwB200Context* c, int32_t atom, int32_t kStart, int
             const size_t total = (size_t)(atom >= 0 ? 1 : c->prob.Natom) * c->prob.Ncol * (kEnd - kStart);
             if (maxN <= 8)
                 stat_eq_kernel<8><<<grid_for(total, 64), 64, 0, c->stream>>>(
-                    c->P, atom, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, c->dSingular.p, nOldDev, dt);
+                    c->P, atom, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, dSingular, nOldDev, dt);
             else if (maxN <= 16)
                 stat_eq_kernel<16><<<grid_for(total, 64), 64, 0, c->stream>>>(
-                    c->P, atom, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, c->dSingular.p, nOldDev, dt);
+                    c->P, atom, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, dSingular, nOldDev, dt);
             else
                 stat_eq_kernel<32><<<grid_for(total, 64), 64, 0, c->stream>>>(
-                    c->P, atom, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, c->dSingular.p, nOldDev, dt);
+                    c->P, atom, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, dSingular, nOldDev, dt);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }
     }
     if (async)
-    {
-        if (ensure_host_scalars(c))
-            return 1;
-        CU(cudaMemcpyAsync(&c->hs->nSingular, c->dSingular.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         return 0;
-    }
     int ns = 0;
     CU(cudaMemcpyAsync(&ns, c->dSingular.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1877,7 +1980,8 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
         c->customLists = false;
         if (rc)
             return 1;
-        dj_reduce_kernel<<<1, 256, 0, s>>>(c->dJ.p, p.Ncol, L, 0, L, c->djOut.p, c->djIdx.p, c->dPrdMask.p);
+        if (launch_dj_reduce(c, s, 0, L, c->dPrdMask.p))
+            return 1;
         CU(cudaGetLastError());
         c->lastLaunches += 1;
         double m = 0.0;

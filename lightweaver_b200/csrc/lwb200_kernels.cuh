@@ -546,37 +546,38 @@ __global__ void ratio_kernel(const DevProblem P, double* gRatio)
 }
 
 // finalise_Gamma (:491-508): Gamma = prefill (crsw*C) + radiative partial sums,
-// then diagonal = -(column sum).  One thread per (column, atom, depth).
+// then diagonal = -(column sum).  One thread per (column, atom, level i, depth): column i of
+// the atom's Gamma at one depth, loads issued together (nothing here aliases).
 __global__ void finalise_kernel(const DevProblem P, const double* __restrict__ prefill,
                                 double* __restrict__ gamma)
 {
-    const size_t total = (size_t)P.Ncol * P.Natom * P.K;
+    const double* __restrict__ accum = P.accum;
+    const int maxN = P.maxNlevel;
+    const size_t total = (size_t)P.Ncol * P.Natom * maxN * P.K;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x)
     {
         const int k = idx % P.K;
-        const int atom = (idx / P.K) % P.Natom;
-        const int col = idx / ((size_t)P.K * P.Natom);
-        if (P.atomDetailed[atom])
-            continue;
+        const int i = (idx / P.K) % maxN;
+        const int atom = (idx / ((size_t)P.K * maxN)) % P.Natom;
+        const int col = idx / ((size_t)P.K * maxN * P.Natom);
         const int N = P.atomNlevel[atom];
+        if (P.atomDetailed[atom] || i >= N)
+            continue;
         const size_t gOff = ((size_t)col * P.GammaTot + P.atomGammaOff[atom]) * P.K + k;
         const size_t aOff = ((size_t)col * P.AccTot + P.atomGammaOff[atom]) * P.K + k;
-        for (int i = 0; i < N; ++i)
+        double diag = 0.0;
+        for (int j = 0; j < N; ++j)
         {
-            double diag = 0.0;
-            for (int j = 0; j < N; ++j)
-            {
-                if (j == i)
-                    continue;
-                // Gamma(j, i): rate from i to j
-                const size_t r = (size_t)(j * N + i) * P.K;
-                const double v = prefill[gOff + r] + P.accum[aOff + r];
-                gamma[gOff + r] = v;
-                diag += v;
-            }
-            gamma[gOff + (size_t)(i * N + i) * P.K] = -diag;
+            if (j == i)
+                continue;
+            // Gamma(j, i): rate from i to j
+            const size_t r = (size_t)(j * N + i) * P.K;
+            const double v = prefill[gOff + r] + accum[aOff + r];
+            gamma[gOff + r] = v;
+            diag += v;
         }
+        gamma[gOff + (size_t)(i * N + i) * P.K] = -diag;
     }
 }
 
@@ -672,6 +673,182 @@ __device__ inline void lu_backsub_dev(int N, const double* A, const int* index, 
     }
 }
 
+// Register-resident forms of the two routines above for small atoms (N <= 7: beyond that the matrix no longer fits the register file): every loop is
+// unrolled over the compile-time N and the pivoting row exchanges are selects, so the matrix
+// never lives in local memory.  Same operations in the same order (including the reference's
+// "all candidates zero => row 0" pivot and the skip-leading-zeros forward substitution).
+template <int N>
+__device__ __forceinline__ bool lu_decompose_small(double (&A)[N][N], int (&index)[N])
+{
+    constexpr double Tiny = 1e-20;
+    double vv[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+    {
+        double big = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+        {
+            const double v = fabs(A[i][j]);
+            big = (big < v) ? v : big;
+        }
+        if (big == 0.0)
+            return false;
+        vv[i] = 1.0 / big;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+    {
+#pragma unroll
+        for (int i = 0; i < j; ++i)
+        {
+            double sum = A[i][j];
+#pragma unroll
+            for (int k = 0; k < i; ++k)
+                sum -= A[i][k] * A[k][j];
+            A[i][j] = sum;
+        }
+        int iMax = 0;
+        double big = 0.0;
+#pragma unroll
+        for (int i = j; i < N; ++i)
+        {
+            double sum = A[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k)
+                sum -= A[i][k] * A[k][j];
+            A[i][j] = sum;
+            const double cand = vv[i] * fabs(sum);
+            if (big < cand)
+            {
+                big = cand;
+                iMax = i;
+            }
+        }
+        // exchange rows j and iMax (iMax is j, a later row, or -- degenerate -- row 0)
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+        {
+            const double tj = A[j][k];
+            double ti = tj;
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+                if ((r == 0 || r > j) && r != j)
+                    ti = (r == iMax) ? A[r][k] : ti;
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+                if ((r == 0 || r > j) && r != j)
+                    A[r][k] = (r == iMax) ? tj : A[r][k];
+            A[j][k] = ti;
+        }
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+            if ((r == 0 || r > j) && r != j)
+                vv[r] = (r == iMax) ? vv[j] : vv[r];
+        index[j] = iMax;
+        if (A[j][j] == 0.0)
+            A[j][j] = Tiny;
+        const double temp = 1.0 / A[j][j];
+#pragma unroll
+        for (int i = j + 1; i < N; ++i)
+            A[i][j] *= temp;
+    }
+    return true;
+}
+
+template <int N>
+__device__ __forceinline__ void lu_backsub_small(const double (&A)[N][N], const int (&index)[N], double (&b)[N])
+{
+    int ii = -1;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+    {
+        const int ip = index[i];
+        const double bi = b[i];
+        double sum = bi; // b[ip], then b[ip] = b[i]
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+            if ((r == 0 || r > i) && r != i)
+            {
+                sum = (r == ip) ? b[r] : sum;
+                b[r] = (r == ip) ? bi : b[r];
+            }
+        if (ii >= 0)
+        {
+#pragma unroll
+            for (int j = 0; j < i; ++j)
+                if (j >= ii)
+                    sum -= A[i][j] * b[j];
+        }
+        else if (sum != 0.0)
+            ii = i;
+        b[i] = sum;
+    }
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i)
+    {
+        double sum = b[i];
+#pragma unroll
+        for (int j = i + 1; j < N; ++j)
+            sum -= A[i][j] * b[j];
+        b[i] = sum / A[i][i];
+    }
+}
+
+// One stat-eq / backward-Euler system of an N-level atom in registers; false: singular.
+template <int N>
+__device__ __noinline__ bool population_solve_small(const double* __restrict__ g, double* __restrict__ nk, size_t K,
+                                                    double nTot, const double* __restrict__ nOldK, double dt)
+{
+    double A[N][N], b[N], bCopy[N], res[N];
+    int index[N];
+    int iElim = 0;
+    double nMax = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+    {
+        const double ni = nk[(size_t)i * K];
+        if (nMax < ni)
+        {
+            nMax = ni;
+            iElim = i;
+        }
+    }
+    // the system as the reference builds it; evaluated again for the refinement residual
+    auto elem = [&](int i, int j) {
+        const double gij = g[(size_t)(i * N + j) * K];
+        if (nOldK)
+            return (i == j) ? 1.0 - gij * dt : -gij * dt;
+        return (i == iElim) ? 1.0 : gij;
+    };
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+    {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            A[i][j] = elem(i, j);
+        b[i] = nOldK ? nOldK[(size_t)i * K] : ((i == iElim) ? nTot : 0.0);
+        bCopy[i] = b[i];
+    }
+    if (!lu_decompose_small<N>(A, index))
+        return false;
+    lu_backsub_small<N>(A, index, b);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+    {
+        double r = bCopy[i];
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            r -= elem(i, j) * b[j];
+        res[i] = r;
+    }
+    lu_backsub_small<N>(A, index, res);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        nk[(size_t)i * K] = b[i] + res[i];
+    return true;
+}
+
 // nOld != nullptr: time_dependent_update_impl (UpdatePopulations.cpp:120-151) instead -- the
 // backward-Euler system (1 - Gamma dt) n = nOld of the same atom, depth by depth, through the
 // same solve_lin_eq.  nOld is [Ncol][Nlevel][K] of atom atomSel.
@@ -695,10 +872,29 @@ __global__ void stat_eq_kernel(const DevProblem P, int atomSel, int kStart, int 
         if (P.atomDetailed[atom])
             continue;
         const int N = P.atomNlevel[atom];
-        double A[MAXN * MAXN], ACopy[MAXN * MAXN], b[MAXN], bCopy[MAXN], res[MAXN];
-        int index[MAXN];
         const size_t gOff = ((size_t)col * P.GammaTot + P.atomGammaOff[atom]) * P.K + k;
         const size_t nOff = ((size_t)col * P.NlevTot + P.atomLevOff[atom]) * P.K + k;
+        if (N <= 7)
+        {
+            const double nTot = nOld ? 0.0 : nTotal[((size_t)col * P.Natom + atom) * P.K + k];
+            const double* nOldK = nOld ? nOld + (size_t)col * N * P.K + k : nullptr;
+            bool ok = true;
+            switch (N)
+            {
+            case 1: ok = population_solve_small<1>(gamma + gOff, n + nOff, P.K, nTot, nOldK, dt); break;
+            case 2: ok = population_solve_small<2>(gamma + gOff, n + nOff, P.K, nTot, nOldK, dt); break;
+            case 3: ok = population_solve_small<3>(gamma + gOff, n + nOff, P.K, nTot, nOldK, dt); break;
+            case 4: ok = population_solve_small<4>(gamma + gOff, n + nOff, P.K, nTot, nOldK, dt); break;
+            case 5: ok = population_solve_small<5>(gamma + gOff, n + nOff, P.K, nTot, nOldK, dt); break;
+            case 6: ok = population_solve_small<6>(gamma + gOff, n + nOff, P.K, nTot, nOldK, dt); break;
+            default: ok = population_solve_small<7>(gamma + gOff, n + nOff, P.K, nTot, nOldK, dt); break;
+            }
+            if (!ok)
+                atomicAdd_system(nSingular, 1); // may be mapped host memory
+            continue;
+        }
+        double A[MAXN * MAXN], ACopy[MAXN * MAXN], b[MAXN], bCopy[MAXN], res[MAXN];
+        int index[MAXN];
         int iElim = 0;
         double nMax = 0.0;
         for (int i = 0; i < N; ++i)
@@ -737,7 +933,7 @@ __global__ void stat_eq_kernel(const DevProblem P, int atomSel, int kStart, int 
             bCopy[i] = b[i];
         if (!lu_decompose_dev<MAXN>(N, A, index))
         {
-            atomicAdd(nSingular, 1);
+            atomicAdd_system(nSingular, 1); // may be mapped host memory
             continue;
         }
         lu_backsub_dev(N, A, index, b);
@@ -900,7 +1096,7 @@ __global__ void nr_update_kernel(const DevProblem P, const NrAtom* __restrict__ 
         // solve_lin_eq with one refinement step (LuSolve.cpp:103-133)
         if (!lu_decompose_dev<MAXN>(Neqn, dF, index))
         {
-            atomicAdd(nSingular, 1);
+            atomicAdd_system(nSingular, 1); // may be mapped host memory
             continue;
         }
         lu_backsub_dev(Neqn, dF, index, Fg);
@@ -928,31 +1124,10 @@ __global__ void nr_update_kernel(const DevProblem P, const NrAtom* __restrict__ 
 }
 
 // (max, first index) over dJ[Ncol][L] restricted to [laLo, laHi): what the
-// reference's threaded branch returns (:688, :700-703).  Single block.
-__global__ void dj_reduce_kernel(const double* __restrict__ dJ, int Ncol, int L, int laLo, int laHi,
-                                 double* outMax, long long* outIdx, const unsigned char* __restrict__ laMask = nullptr)
+// reference's threaded branch returns (:688, :700-703).  One launch: every CTA reduces a
+// grid-strided share into part[], the last one to finish (ticket counter) reduces the parts.
+__device__ __forceinline__ void dj_block_reduce(double* sMax, long long* sIdx)
 {
-    __shared__ double sMax[256];
-    __shared__ long long sIdx[256];
-    double best = -1.0;
-    long long bestIdx = 0;
-    const long long span = laHi - laLo;
-    const long long total = (long long)Ncol * span;
-    for (long long q = threadIdx.x; q < total; q += blockDim.x)
-    {
-        const long long col = q / span;
-        const long long la = laLo + q % span;
-        if (laMask && !laMask[la])
-            continue;
-        const double v = dJ[col * L + la];
-        if (best < v)
-        {
-            best = v;
-            bestIdx = col * L + la;
-        }
-    }
-    sMax[threadIdx.x] = best;
-    sIdx[threadIdx.x] = bestIdx;
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1)
     {
@@ -968,10 +1143,68 @@ __global__ void dj_reduce_kernel(const double* __restrict__ dJ, int Ncol, int L,
         }
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(256)
+dj_reduce_kernel(const double* __restrict__ dJ, int Ncol, int L, int laLo, int laHi, double* outMax,
+                 long long* outIdx, const unsigned char* __restrict__ laMask, double* partMax,
+                 long long* partIdx, unsigned* ticket)
+{
+    __shared__ double sMax[256];
+    __shared__ long long sIdx[256];
+    __shared__ bool last;
+    double best = -1.0;
+    long long bestIdx = 0;
+    const long long span = laHi - laLo;
+    const long long total = (long long)Ncol * span;
+    // (col, la) of this thread's elements advance by a fixed stride: no division in the loop
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long dcol = span > 0 ? stride / span : 0, dla = span > 0 ? stride % span : 0;
+    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long col = span > 0 ? q / span : 0, la = span > 0 ? q % span : 0;
+    for (; q < total; q += stride)
+    {
+        if (!laMask || laMask[laLo + la])
+        {
+            const long long idx = col * L + laLo + la;
+            const double v = dJ[idx];
+            if (best < v)
+            {
+                best = v;
+                bestIdx = idx;
+            }
+        }
+        col += dcol;
+        la += dla;
+        if (la >= span)
+        {
+            la -= span;
+            ++col;
+        }
+    }
+    sMax[threadIdx.x] = best;
+    sIdx[threadIdx.x] = bestIdx;
+    dj_block_reduce(sMax, sIdx);
+    if (threadIdx.x == 0)
+    {
+        partMax[blockIdx.x] = sMax[0];
+        partIdx[blockIdx.x] = sIdx[0];
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last)
+        return;
+    __threadfence();
+    const bool have = threadIdx.x < gridDim.x; // gridDim.x <= 256
+    sMax[threadIdx.x] = have ? ((volatile double*)partMax)[threadIdx.x] : -1.0;
+    sIdx[threadIdx.x] = have ? ((volatile long long*)partIdx)[threadIdx.x] : 0;
+    dj_block_reduce(sMax, sIdx);
     if (threadIdx.x == 0)
     {
         *outMax = sMax[0] < 0.0 ? 0.0 : sMax[0];
         *outIdx = sIdx[0];
+        *ticket = 0;
     }
 }
 

@@ -532,6 +532,20 @@ def tiny_problem(ncol=1, nrays=3, seed=SEED, ndepth=None, perturb=False, **kw) -
                          perturb=perturb, **kw)
 
 
+def nine_level_problem(ncol=1, nrays=3, seed=SEED, ndepth=None, perturb=False, **kw) -> Problem:
+    """An 8-level + continuum toy atom: beyond the register-resident population solver (N <= 7), so the
+    general per-depth LU path is exercised."""
+    E = [0.0, 60000.0, 70000.0, 75000.0, 80000.0, 83000.0, 86000.0, 88000.0]
+    lev = [Level(e, 2.0 * (q + 1), 0) for q, e in enumerate(E)] + [Level(100000.0, 1, 1)]
+    lines = [LineSpec(1, 0, 3.0e8, 15, 5.0, 60.0), LineSpec(2, 0, 4.0e7, 11, 3.0, 30.0),
+             LineSpec(3, 1, 2.0e7, 11, 3.0, 30.0), LineSpec(4, 1, 1.0e7, 11, 3.0, 30.0),
+             LineSpec(5, 2, 8.0e6, 11, 3.0, 30.0), LineSpec(6, 3, 6.0e6, 11, 3.0, 30.0),
+             LineSpec(7, 4, 5.0e6, 11, 3.0, 30.0)]
+    cont = [ContSpec(8, q, 6.0e-22 * (q + 1), 6, 0.4 * 1e7 / (100000.0 - e)) for q, e in enumerate(E)]
+    toy = ModelAtom('Toy9', 12.0, 1e-4, lev, lines, cont)
+    return build_problem([toy], ncol=ncol, nrays=nrays, seed=seed, ndepth=ndepth, perturb=perturb, **kw)
+
+
 def config_c5(ncol=1024, nrays=5, seed=SEED, nl=1.0, **kw) -> Problem:
     """Config 5: magnetised stack of perturbed FAL C columns, Ca II with the 854.2 nm line
     Zeeman-split and polarised (full Stokes)."""

@@ -457,6 +457,26 @@ def test_singular_matrix_raises():
     ctx.close()
 
 
+def test_nine_level_atom_takes_the_general_lu_path():
+    # Nlevel = 9 > 7: the per-depth systems go through the local-memory LU instead of the
+    # register-resident one; both follow LuSolve.cpp:8-133
+    p = synth.nine_level_problem(ncol=2, perturb=True)
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+        ctx.stat_equil()
+        oracle_iter(q, lambdaIterate=(it == 0))
+        assert_close(p, q)
+    p.atoms[0].Gamma[0, 2, :, 10] = 0.0
+    p.atoms[0].Gamma[0, 1, :, 10] = 0.0
+    for j in range(3, 9):
+        p.atoms[0].Gamma[0, j, :, 10] = 0.0
+    with pytest.raises(ExplodingMatrixError):
+        ctx.stat_equil()
+    ctx.close()
+
+
 def test_device_profiles_match_host_voigt():
     """lwb200_compute_profiles (device Voigt) vs the Faddeeva-based host profiles."""
     p = synth.config_c1(ncol=2, perturb=True, nl=0.3)
