@@ -205,6 +205,16 @@ int lwb200_set_stream(LwB200Context* ctx, void* cudaStream);
  * la in [laStart, laEnd).  Default [0, Nspect). */
 int lwb200_set_lambda_range(LwB200Context* ctx, int32_t laStart, int32_t laEnd);
 
+/* Column mask of a 1.5D stack: columns converge one by one, and a retired column (active[col] == 0)
+ * is skipped by every kernel of lwb200_fs_iter / lwb200_formal_sol / lwb200_stat_eq /
+ * lwb200_time_dep_update from then on -- its J, I, Gamma, rates and populations stay as they are,
+ * and dJ is taken over the active columns only.  The launch grids shrink with the mask, so the tail
+ * of a convergence run costs what its remaining columns cost.  (The reference iterates one Context
+ * per column and simply stops calling the converged ones: iterate_ctx.py:85-88.)
+ * active: [Ncol] bytes, or NULL for "all columns" (the default).  PRD, full-Stokes and
+ * Newton-Raphson calls are refused while a mask is set. */
+int lwb200_set_active_columns(LwB200Context* ctx, const uint8_t* active);
+
 /* Host -> device / device -> host copies of the groups in `mask`, using the
  * host pointers registered at create time.  Asynchronous on the context's
  * stream; lwb200_sync waits. */

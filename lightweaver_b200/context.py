@@ -89,6 +89,18 @@ class Context:
     def set_lambda_range(self, laStart, laEnd):
         capi.check(self.lib.lwb200_set_lambda_range(self._h, int(laStart), int(laEnd)))
 
+    def set_active_columns(self, active=None):
+        """Retire converged columns of a stack: ``active`` is a boolean array [Ncol] (None: all
+        columns again).  Retired columns are skipped by the Gamma iteration, the formal solution
+        and the population update; their arrays keep their values."""
+        if active is None:
+            capi.check(self.lib.lwb200_set_active_columns(self._h, None))
+            return
+        a = np.ascontiguousarray(np.asarray(active).astype(np.uint8))
+        if a.shape != (self.problem.Ncol,):
+            raise ValueError('active must have one entry per column')
+        capi.check(self.lib.lwb200_set_active_columns(self._h, a.ctypes.data_as(C.POINTER(C.c_uint8))))
+
     def upload(self, mask):
         capi.check(self.lib.lwb200_upload(self._h, mask))
 

@@ -228,6 +228,9 @@ struct LwB200Context
     DevBuf<double> djPartMax;
     DevBuf<unsigned> djTicket;
     cudaEvent_t evDj = nullptr;
+    DevBuf<int> dColList;             // active columns of a masked stack
+    DevBuf<unsigned char> dColActive;
+    int nActiveCol = -1;              // -1: no mask
     bool singularPending = false; // an asynchronous population update whose singular count is uncollected
     bool djEarly = false, djDone = false; // dJ reduced on a side stream while Gamma is accumulated
     DevBuf<DevTrans> dTrans;
@@ -802,13 +805,19 @@ int check_phi_symmetry(LwB200Context* c)
     return 0;
 }
 
+// columns a launch covers: the active ones of a masked stack
+static inline int launch_columns(const LwB200Context* c)
+{
+    return c->nActiveCol >= 0 ? c->nActiveCol : c->prob.Ncol;
+}
+
 // (max, argmax) of dJ over [laLo, laHi) of every column into djOut / djIdx, on stream s
 static int launch_dj_reduce(LwB200Context* c, cudaStream_t s, int laLo, int laHi, const unsigned char* mask)
 {
     const long long total = (long long)c->P.Ncol * (laHi - laLo);
     const int grid = (int)std::max<long long>(1, std::min<long long>(256, (total + 1023) / 1024));
     dj_reduce_kernel<<<grid, 256, 0, s>>>(c->dJ.p, c->P.Ncol, c->P.L, laLo, laHi, c->djOut.p, c->djIdx.p, mask,
-                                          c->djPartMax.p, c->djPartIdx.p, c->djTicket.p);
+                                          c->djPartMax.p, c->djPartIdx.p, c->djTicket.p, c->P.colActive);
     CU(cudaGetLastError());
     c->lastLaunches += 1;
     return 0;
@@ -876,7 +885,7 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
         return 1;
     if (set_smem_attr(gamma_kernel, c->device))
         return 1;
-    const int Ncol = c->prob.Ncol, KP = c->P.KP, K = c->P.K;
+    const int Ncol = launch_columns(c), KP = c->P.KP, K = c->P.K;
     const int laLo = pl.fullRange ? 0 : c->laLo, laHi = pl.fullRange ? c->prob.Nspect : c->laHi;
     const int threads = MULTI ? 32 * ((K + 32 * NCH - 1) / (32 * NCH)) : c->nwarps * 32;
     for (int colBase = 0; colBase < Ncol; colBase += c->batchCols)
@@ -1011,7 +1020,7 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
             auto kern = fs_kernel<NCH, SOLVER, MODE_ITER>;
             if (set_smem_attr(kern, c->device))
                 return 1;
-            dim3 grid(c->nListDirect, c->prob.Ncol);
+            dim3 grid(c->nListDirect, launch_columns(c));
             kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListDirect.p, c->laLo, c->laHi,
                                                              lambdaIterate, 0, storeDepth);
             CU(cudaGetLastError());
@@ -1023,7 +1032,7 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
         auto kern = fs_kernel<NCH, SOLVER, MODE>;
         if (set_smem_attr(kern, c->device))
             return 1;
-        dim3 grid(c->nListAll, c->prob.Ncol);
+        dim3 grid(c->nListAll, launch_columns(c));
         kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListAll.p, c->laLo, c->laHi, lambdaIterate,
                                                          upOnly, storeDepth);
         CU(cudaGetLastError());
@@ -1271,6 +1280,8 @@ int lwb200_destroy(LwB200Context* c)
     c->dListDirect.release();
     c->dListAll.release();
     c->djIdx.release();
+    c->dColList.release();
+    c->dColActive.release();
     c->djPartIdx.release();
     c->djPartMax.release();
     c->djTicket.release();
@@ -1293,6 +1304,36 @@ int lwb200_set_lambda_range(LwB200Context* c, int32_t laStart, int32_t laEnd)
         return fail("lwb200_set_lambda_range: bad range");
     c->laLo = laStart;
     c->laHi = laEnd;
+    return 0;
+}
+
+int lwb200_set_active_columns(LwB200Context* c, const uint8_t* active)
+{
+    CU(cudaSetDevice(c->device));
+    // the kernels in flight still read the previous list
+    CU(cudaStreamSynchronize(c->stream));
+    c->dColList.release();
+    c->dColActive.release();
+    c->P.colList = nullptr;
+    c->P.colActive = nullptr;
+    c->nActiveCol = -1;
+    if (!active)
+        return 0;
+    std::vector<int> list;
+    std::vector<unsigned char> mask(c->prob.Ncol);
+    for (int col = 0; col < c->prob.Ncol; ++col)
+    {
+        mask[col] = active[col] ? 1 : 0;
+        if (active[col])
+            list.push_back(col);
+    }
+    if ((int)list.size() == c->prob.Ncol)
+        return 0; // nothing retired
+    if ((!list.empty() && c->dColList.upload(list)) || c->dColActive.upload(mask))
+        return 1;
+    c->P.colList = c->dColList.p;
+    c->P.colActive = c->dColActive.p;
+    c->nActiveCol = (int)list.size();
     return 0;
 }
 
@@ -1731,7 +1772,7 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
         return fail("lwb200_fs_iter: inputs have not been uploaded (lwb200_upload)");
     const int storeDepth = (flags & LWB200_STORE_DEPTH) ? 1 : 0;
     c->forceDirect = (flags & LWB200_GENERAL_KERNEL) != 0;
-    c->fetchEarly = (flags & LWB200_FETCH_EARLY) != 0 && !c->forceDirect && c->outputsPinned;
+    c->fetchEarly = (flags & LWB200_FETCH_EARLY) != 0 && !c->forceDirect && c->outputsPinned && c->nActiveCol < 0;
     if (c->fetched)
     {
         // an early copy nobody collected: it must not race with this iteration's writes of J
@@ -1747,7 +1788,16 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
     if (c->djEarly && ensure_host_scalars(c))
         return 1;
     // zero_rates + fresh partial sums (:605-612, :643)
-    CU(cudaMemsetAsync(c->accum.p, 0, c->accum.n * sizeof(double), c->stream));
+    if (c->nActiveCol < 0)
+        CU(cudaMemsetAsync(c->accum.p, 0, c->accum.n * sizeof(double), c->stream));
+    else if (c->nActiveCol > 0)
+    {
+        zero_accum_kernel<<<grid_for((size_t)c->nActiveCol * c->P.AccTot * c->P.K), 256, 0, c->stream>>>(c->P, c->nActiveCol);
+        CU(cudaGetLastError());
+        c->lastLaunches += 1;
+    }
+    else
+        return fail("lwb200_fs_iter: every column is retired");
     const int rcFs = launch_fs<MODE_ITER>(c, (flags & LWB200_LAMBDA_ITERATE) ? 1 : 0, 0, storeDepth);
     c->djEarly = false;
     if (rcFs)
@@ -1875,6 +1925,8 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
                             int64_t* dJPrdMaxIdx)
 {
     CU(cudaSetDevice(c->device));
+    if (c->nActiveCol >= 0)
+        return fail("lwb200_redistribute_prd: not available while a column mask is set (lwb200_set_active_columns)");
     if (nIterOut)
         *nIterOut = 0;
     // the lines taking part: active atoms' always, detailed ones on request
@@ -2015,6 +2067,8 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
 int lwb200_formal_sol_full_stokes(LwB200Context* c, int updateJ, int upOnly, double* dJMax, int64_t* dJMaxIdx)
 {
     CU(cudaSetDevice(c->device));
+    if (c->nActiveCol >= 0)
+        return fail("lwb200_formal_sol_full_stokes: not available while a column mask is set (lwb200_set_active_columns)");
     if (!c->nstarUploaded)
         return fail("lwb200_formal_sol_full_stokes: inputs have not been uploaded (lwb200_upload)");
     if (c->polTot == 0)
@@ -2114,6 +2168,8 @@ int lwb200_nr_post_update(LwB200Context* c, const LwB200NrUpdate* u, int32_t kSt
                           int32_t* nSingular)
 {
     CU(cudaSetDevice(c->device));
+    if (c->nActiveCol >= 0)
+        return fail("lwb200_nr_post_update: not available while a column mask is set (lwb200_set_active_columns)");
     const LwB200Problem& p = c->prob;
     const int K = p.Nspace;
     const size_t ncol = p.Ncol, D = sizeof(double);

@@ -120,10 +120,19 @@ struct DevProblem
     int momRows;
     const int* phiAsym;       // 0: phi(.., dir 0, .) == phi(.., dir 1, .) everywhere (static atmosphere)
     // full Stokes (lwb200_stokes.cuh)
+    // column mask of a stack (lwb200_set_active_columns): retired columns are skipped by every kernel
+    const int* colList;             // active column indices, ascending; nullptr: all columns
+    const unsigned char* colActive; // [Ncol]; nullptr: all columns
     const double* pol;        // polarised profile pool
     double* Quv;              // [Ncol][3][L][M]
     double* Jdag;             // [Ncol][L][K] copy of J taken before a J-updating Stokes pass
 };
+
+// q-th column of the launch: the q-th active column when a mask is set
+__device__ __forceinline__ int column_of(const DevProblem& P, int q)
+{
+    return P.colList ? __ldg(P.colList + q) : q;
+}
 
 // U, V for one transition at one (wavelength, ray, depth): Transition::uv
 // (LwTransition.hpp:93-144) with gij from Atom::setup_wavelength
@@ -186,7 +195,7 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
     extern __shared__ double smem[];
     const int K = P.K, M = P.M, L = P.L, KP = P.KP;
     const int tile = tileList[blockIdx.x];
-    const int col = blockIdx.y;
+    const int col = column_of(P, blockIdx.y);
     const int warp = threadIdx.x >> 5;
     const int nwarp = blockDim.x >> 5;
     const int lane = lane_id();
@@ -545,6 +554,17 @@ __global__ void ratio_kernel(const DevProblem P, double* gRatio)
     }
 }
 
+// zero_rates + fresh Gamma partial sums of the active columns of a masked stack (the whole
+// buffer is a plain memset otherwise)
+__global__ void zero_accum_kernel(const DevProblem P, int nActive)
+{
+    const size_t per = (size_t)P.AccTot * P.K;
+    const size_t total = (size_t)nActive * per;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x)
+        P.accum[(size_t)column_of(P, (int)(idx / per)) * per + idx % per] = 0.0;
+}
+
 // finalise_Gamma (:491-508): Gamma = prefill (crsw*C) + radiative partial sums,
 // then diagonal = -(column sum).  One thread per (column, atom, level i, depth): column i of
 // the atom's Gamma at one depth, loads issued together (nothing here aliases).
@@ -562,7 +582,7 @@ __global__ void finalise_kernel(const DevProblem P, const double* __restrict__ p
         const int atom = (idx / ((size_t)P.K * maxN)) % P.Natom;
         const int col = idx / ((size_t)P.K * maxN * P.Natom);
         const int N = P.atomNlevel[atom];
-        if (P.atomDetailed[atom] || i >= N)
+        if (P.atomDetailed[atom] || i >= N || (P.colActive && !P.colActive[col]))
             continue;
         const size_t gOff = ((size_t)col * P.GammaTot + P.atomGammaOff[atom]) * P.K + k;
         const size_t aOff = ((size_t)col * P.AccTot + P.atomGammaOff[atom]) * P.K + k;
@@ -869,7 +889,7 @@ __global__ void stat_eq_kernel(const DevProblem P, int atomSel, int kStart, int 
         const int k = kStart + idx % nk;
         const int col = (idx / nk) % P.Ncol;
         const int atom = atomSel >= 0 ? atomSel : (int)(idx / ((size_t)nk * P.Ncol));
-        if (P.atomDetailed[atom])
+        if (P.atomDetailed[atom] || (P.colActive && !P.colActive[col]))
             continue;
         const int N = P.atomNlevel[atom];
         const size_t gOff = ((size_t)col * P.GammaTot + P.atomGammaOff[atom]) * P.K + k;
@@ -1148,7 +1168,7 @@ __device__ __forceinline__ void dj_block_reduce(double* sMax, long long* sIdx)
 __global__ void __launch_bounds__(256)
 dj_reduce_kernel(const double* __restrict__ dJ, int Ncol, int L, int laLo, int laHi, double* outMax,
                  long long* outIdx, const unsigned char* __restrict__ laMask, double* partMax,
-                 long long* partIdx, unsigned* ticket)
+                 long long* partIdx, unsigned* ticket, const unsigned char* __restrict__ colActive)
 {
     __shared__ double sMax[256];
     __shared__ long long sIdx[256];
@@ -1164,7 +1184,7 @@ dj_reduce_kernel(const double* __restrict__ dJ, int Ncol, int L, int laLo, int l
     long long col = span > 0 ? q / span : 0, la = span > 0 ? q % span : 0;
     for (; q < total; q += stride)
     {
-        if (!laMask || laMask[laLo + la])
+        if ((!laMask || laMask[laLo + la]) && (!colActive || colActive[col]))
         {
             const long long idx = col * L + laLo + la;
             const double v = dJ[idx];

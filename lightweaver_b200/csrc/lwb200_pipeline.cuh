@@ -65,7 +65,7 @@ __global__ void continuum_kernel(const DevProblem P, const int* __restrict__ til
 {
     const int K = P.K, L = P.L;
     const int tile = tileList[blockIdx.x];
-    const int cb = blockIdx.y, col = colBase + cb;
+    const int cb = blockIdx.y, col = column_of(P, colBase + cb);
     const int k = threadIdx.x;
     if (k >= K)
         return;
@@ -137,7 +137,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
     constexpr int NPAIR = NL > 1 ? NL * (NL - 1) / 2 : 1;
     __shared__ double commBuf[MULTI ? 7 * 8 : 1];
     const int K = P.K, M = P.M, L = P.L;
-    const int cb = blockIdx.y, col = colBase + cb;
+    const int cb = blockIdx.y, col = column_of(P, colBase + cb);
     // warp index made provably warp-uniform: every loop below stays convergent
     const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0);
     DepthComm<MULTI> cm;
@@ -702,7 +702,7 @@ gamma_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int
     // depth chunk of this CTA: blockDim.x consecutive depths (one chunk covers Nspace <= 128)
     const int K = P.K, KC = blockDim.x, RS = (gridDim.z == 1) ? K : KC; // RS: shared-memory row stride
     const int tile = tileList[blockIdx.x];
-    const int cb = blockIdx.y, col = colBase + cb;
+    const int cb = blockIdx.y, col = column_of(P, colBase + cb);
     const int kk = threadIdx.x, k = blockIdx.z * KC + kk;
     const int slot0 = P.tileSlotOff[tile];
     const int nslot = P.tileSlotOff[tile + 1] - slot0;

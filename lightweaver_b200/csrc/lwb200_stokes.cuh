@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(128)
 stokes_kernel(const DevProblem P, const int* __restrict__ polLam, int nPol, int colBase, int upOnly, int updateJ)
 {
     const int K = P.K, M = P.M, L = P.L;
-    const int cb = blockIdx.y, col = colBase + cb;
+    const int cb = blockIdx.y, col = column_of(P, colBase + cb);
     const int ray = blockIdx.x * blockDim.x + threadIdx.x;
     if (ray >= nPol * 2 * M)
         return;

@@ -477,6 +477,55 @@ def test_nine_level_atom_takes_the_general_lu_path():
     ctx.close()
 
 
+def test_retired_columns_are_skipped_and_keep_their_values():
+    # 1.5D stack with a column mask (lwb200_set_active_columns): the reference iterates one Context
+    # per column and stops calling the converged ones; here the kernels skip them
+    p = synth.tiny_problem(ncol=3, perturb=True)
+    q = p.clone()
+    ctx = Context(p)
+
+    def oracle_cols(cols, lambdaIterate):
+        kept = q.atoms[0].Gamma.copy()
+        q.prefill_gamma()
+        for c in range(q.Ncol):
+            if c not in cols:
+                q.atoms[0].Gamma[c] = kept[c]   # a column nobody iterates keeps its Gamma
+        dj = 0.0
+        for c in cols:
+            o = oraclelib.OracleContext(q, col=c)
+            dj = max(dj, o.fs_iter(lambdaIterate=lambdaIterate)[0])
+            o.stat_eq()
+        return dj
+
+    ctx.formal_sol_gamma_matrices(lambdaIterate=True)
+    ctx.stat_equil()
+    oracle_cols([0, 1, 2], True)
+    assert_close(p, q)
+
+    ctx.set_active_columns([True, False, True])
+    a = p.atoms[0]
+    frozen = [x[1].copy() for x in (p.J, p.I, a.n, a.Gamma)] + [t.Rij[1].copy() for t in a.trans]
+    for it in range(2):
+        upd = ctx.formal_sol_gamma_matrices()
+        ctx.stat_equil()
+        dj = oracle_cols([0, 2], False)
+        assert abs(upd.dJMax - dj) <= 1e-9 * dj
+        now = [x[1] for x in (p.J, p.I, a.n)] + [t.Rij[1] for t in a.trans]
+        for was, cur in zip(frozen[:3] + frozen[4:], now):
+            assert np.array_equal(was, cur)
+        assert np.array_equal(frozen[3], a.Gamma[1])
+        assert_close(p, q)
+
+    with pytest.raises(capi.LwB200Error):
+        ctx.prd_redistribute_device()
+    ctx.set_active_columns(None)
+    ctx.formal_sol_gamma_matrices()
+    ctx.stat_equil()
+    oracle_cols([0, 1, 2], False)
+    assert_close(p, q)
+    ctx.close()
+
+
 def test_device_profiles_match_host_voigt():
     """lwb200_compute_profiles (device Voigt) vs the Faddeeva-based host profiles."""
     p = synth.config_c1(ncol=2, perturb=True, nl=0.3)
