@@ -891,13 +891,7 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
     for (int colBase = 0; colBase < Ncol; colBase += c->batchCols)
     {
         const int nb = std::min(c->batchCols, Ncol - colBase);
-        if (pl.nMoment > 0)
-        {
-            continuum_kernel<<<dim3(pl.nMoment, nb), KP, 0, c->stream>>>(c->P, pl.moment, laLo, laHi, colBase,
-                                                                        pl.laMask);
-            CU(cudaGetLastError());
-            c->lastLaunches += 1;
-        }
+        constexpr int contPerBlock = 4; // wavelengths per continuum_kernel CTA
         int nkinds = 0;
         for (int q = 0; q < 4; ++q)
             nkinds += pl.nKindLam[q] > 0 ? 1 : 0;
@@ -921,6 +915,10 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
             const int nw = c->nwarps;
             dim3 grid(MULTI ? nLam : (nLam + nw * perWarp - 1) / (nw * perWarp), nb);
             const int* list = pl.kindLam[q];
+            continuum_kernel<<<dim3((nLam + contPerBlock - 1) / contPerBlock, nb), KP, 0, s>>>(c->P, list, nLam,
+                                                                                              contPerBlock, colBase);
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
             switch (q)
             {
             case 0:
@@ -943,6 +941,10 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
         {
             // polarised wavelengths: one thread per ray, concurrently with the scalar ray kernels
             const int nRays = pl.nPolLam * 2 * c->prob.Nrays;
+            continuum_kernel<<<dim3((pl.nPolLam + contPerBlock - 1) / contPerBlock, nb), KP, 0, c->stream>>>(
+                c->P, pl.polLam, pl.nPolLam, contPerBlock, colBase);
+            CU(cudaGetLastError());
+            c->lastLaunches += 1;
             stokes_kernel<<<dim3((nRays + 127) / 128, nb), 128, 0, c->stream>>>(c->P, pl.polLam, pl.nPolLam, colBase,
                                                                                 (fsMode & 2) ? 1 : 0, (fsMode & 4) ? 1 : 0);
             CU(cudaGetLastError());

@@ -59,12 +59,13 @@ __global__ void phi_symmetry_kernel(const double* __restrict__ phi, size_t nPair
 }
 
 // ---------------------------------------------------------------------------
-// Stage 1: chiC, etaC.  Grid (tiles, columns of the batch), one thread per depth.
-__global__ void continuum_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi,
-                                 int colBase, const unsigned char* __restrict__ laMask)
+// Stage 1: chiC, etaC of the wavelengths of one kind.  Grid (groups of `perBlock` wavelengths of the
+// list, columns of the batch), one thread per depth.  Launched on the stream of that kind's ray
+// kernel, so the (latency-bound) continuum stage of one kind overlaps the rays of the others.
+__global__ void continuum_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int perBlock,
+                                 int colBase)
 {
     const int K = P.K, L = P.L;
-    const int tile = tileList[blockIdx.x];
     const int cb = blockIdx.y, col = column_of(P, colBase + cb);
     const int k = threadIdx.x;
     if (k >= K)
@@ -72,12 +73,10 @@ __global__ void continuum_kernel(const DevProblem P, const int* __restrict__ til
     const double Tk = __ldg(P.temperature + (size_t)col * K + k);
     const double* ncol = P.n + (size_t)col * P.NlevTot * K + k;
     const double* gcol = P.gRatio + (size_t)col * K + k;
-    const int tlBeg = P.tileLa[tile], tlEnd = P.tileLa[tile + 1];
-    for (int tl = tlBeg; tl < tlEnd; ++tl)
+    const int qBeg = blockIdx.x * perBlock, qEnd = min(nLam, qBeg + perBlock);
+    for (int q = qBeg; q < qEnd; ++q)
     {
-        const int la = P.tileLambda[tl];
-        if (la < laLo || la >= laHi || (laMask && !laMask[la]))
-            continue;
+        const int la = lamList[q];
         const double lambda = __ldg(P.wavelength + la);
         const double rlambda = 1.0 / lambda;
         constexpr double hc_k = kHC / (kKBoltzmann * kNmToM);
