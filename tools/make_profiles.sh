@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py --steps 2 --warmup 3 > $OUT/${TAG}_launches_c2.log 2>&1
 # 2. full captures of the pipeline kernels: one Gamma iteration of c2 and of a 128-column stack
 for WL in c2 c3; do
-  if [ $WL = c2 ]; then ARGS="1 2 c2"; N=6; else ARGS="128 2 c3"; N=4; fi
+  if [ $WL = c2 ]; then ARGS="1 2 c2"; N=9; else ARGS="128 2 c3"; N=5; fi
   ncu --set full --clock-control none --import-source on -k regex:"continuum_kernel|ray_kernel|gamma_kernel|fs_kernel" -s $N -c $N \
       -o $OUT/${TAG}_full_$WL -f python tools/prof_c3.py $ARGS > $OUT/${TAG}_full_$WL.log 2>&1
   python tools/ncu_summary.py $OUT/${TAG}_full_$WL.ncu-rep > $OUT/${TAG}_summary_$WL.txt 2>&1
