@@ -390,7 +390,7 @@ int build_plan(LwB200Context* c)
     if ((long long)std::max(ncont, 1) * p.Ncol * K > 0x7fffffffLL)
         return fail("gRatio block exceeds 2^31 elements");
     const long long targetCtas = 148LL * 16;
-    int tileLen = (int)std::max<long long>(4, std::min<long long>(32, ((long long)L * p.Ncol) / targetCtas));
+    int tileLen = (int)std::max<long long>(1, std::min<long long>(32, ((long long)L * p.Ncol) / targetCtas));
     if (const char* e = std::getenv("LWB200_TILE_LEN")) // tuning aid
         tileLen = std::max(1, std::atoi(e));
 

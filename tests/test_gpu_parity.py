@@ -56,9 +56,13 @@ def test_cuda_matches_reference_golden(name):
     ctx.close()
 
 
-@pytest.mark.parametrize('solver', [capi.FS_BEZIER3, capi.FS_BESSER, capi.FS_LINEAR])
-def test_cuda_vs_oracle_multicolumn_c1(solver):
-    """Config-3-shaped: perturbed FAL C columns with velocity fields, H + Ca II."""
+@pytest.mark.parametrize('solver,tileLen', [(capi.FS_BEZIER3, None), (capi.FS_BESSER, None), (capi.FS_LINEAR, None),
+                                            (capi.FS_BEZIER3, 7), (capi.FS_BEZIER3, 32)])
+def test_cuda_vs_oracle_multicolumn_c1(solver, tileLen, monkeypatch):
+    """Config-3-shaped: perturbed FAL C columns with velocity fields, H + Ca II.  tileLen: wavelengths
+    per Gamma tile (the planner picks 1 for a problem this small; larger stacks get up to 32)."""
+    if tileLen is not None:
+        monkeypatch.setenv('LWB200_TILE_LEN', str(tileLen))
     p = synth.config_c1(ncol=3, perturb=True, formal_solver=solver, nl=0.4)
     q = p.clone()
     ctx = Context(p)

@@ -39,7 +39,12 @@ elif wl == 'c1':
     ctx = Context(p)
 else:
     p = synth.config_c2()
-    ctx = Context(p)
+    import os
+    if os.environ.get('PROF_SHARDS'):   # time one wavelength shard of an N-way partition
+        from lightweaver_b200 import sharding
+        ctx = Context(p, laRange=sharding.partition_wavelengths(p, int(os.environ['PROF_SHARDS']))[0])
+    else:
+        ctx = Context(p)
 ts = []
 for it in range(nit):
     ctx.fs_iter_device(want_dJ=False)
