@@ -61,6 +61,8 @@ struct DevEntry
     int nOffI, nOffJ;  // levI * K, levJ * K: element offsets into one column of n
     int gOff;          // contIdx * Ncol * K: element offset of the continuum's gRatio block
     int prd;           // line with rhoPrd (angle-averaged PRD)
+    int accIJ, accJI;  // rows of the packed accumulator for Gamma(i,j), Gamma(j,i); -1: none
+    int accRij, accRji;
 };
 
 // Per (wavelength, overlapping-line slot) descriptor built by the planner (<= 3 slots).

@@ -482,7 +482,17 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
 #define LWB200_GAMMA_MINBLOCKS 4
 #endif
 
-template <int NL>
+// one fp64 RED into a row of a column's packed accumulator (acc points at this thread's depth)
+__device__ __forceinline__ void red_row(double* acc, int row, int K, double v)
+{
+    if (row >= 0 && v != 0.0)
+        atomicAdd(acc + (size_t)row * K, v);
+}
+
+// DIRECT = false: acc is this thread's column of the tile's shared-memory accumulator, flushed by the
+// caller; DIRECT = true: acc is this thread's depth of the column's global accumulator and every
+// contribution is a RED (no accumulator in shared memory: CTAs per SM set by registers alone).
+template <int NL, bool DIRECT = false>
 __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int col, int cb, int k, double Tk,
                                              double W0, double* __restrict__ acc, double* __restrict__ Xs,
                                              double* __restrict__ Us, const bool prdOnly)
@@ -649,7 +659,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
                     wla = lsWla[l];
                 }
             }
-            double* a4 = acc + t.slot * 4 * KC;
+            double* a4 = DIRECT ? acc : acc + t.slot * 4 * KC;
             if (!detailed && !prdOnly)
             {
                 // chi_atom(m) = sum_q p_q X_q(m), U_atom(m) = sum_q p_q U_q(m)
@@ -682,11 +692,30 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
                     XUji = fma(Xj[q], mi, XUji);
                 }
                 // sum_r w [(Uji + Vji Ieff) - Psi* chi(i) U(j)],  Ieff = I - Psi* eta_atom
-                a4[0] += (ugv * Wq + gv * (Aq - EBq) - XUij) * wla;
-                a4[KC] += (v * (Aq - EBq) - XUji) * wla;
+                const double gIJ = (ugv * Wq + gv * (Aq - EBq) - XUij) * wla;
+                const double gJI = (v * (Aq - EBq) - XUji) * wla;
+                if (DIRECT)
+                {
+                    red_row(a4, t.accIJ, K, gIJ);
+                    red_row(a4, t.accJI, K, gJI);
+                }
+                else
+                {
+                    a4[0] += gIJ;
+                    a4[KC] += gJI;
+                }
             }
-            a4[2 * KC] += (v * Aq) * wla;
-            a4[3 * KC] += (ugv * Wq + gv * Aq) * wla;
+            const double rIJ = (v * Aq) * wla, rJI = (ugv * Wq + gv * Aq) * wla;
+            if (DIRECT)
+            {
+                red_row(a4, t.accRij, K, rIJ);
+                red_row(a4, t.accRji, K, rJI);
+            }
+            else
+            {
+                a4[2 * KC] += rIJ;
+                a4[3 * KC] += rJI;
+            }
         }
         e0 = e1;
     }
@@ -758,6 +787,40 @@ gamma_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int
             }
         }
     }
+}
+
+// The Gamma stage of small problems (a 1D atmosphere, a wavelength shard): one CTA per wavelength
+// of one kind, contributions go straight to the global accumulator.  No shared-memory accumulator
+// means the CTAs per SM are set by the registers of that kind alone -- this stage is bound by the
+// latency of its dependent loads, i.e. by resident warps -- and each kind follows its own ray kernel
+// on that kernel's stream.  Column stacks keep gamma_kernel: its tiles amortise the REDs.
+__host__ __device__ constexpr int gamma_direct_min_blocks(int NL)
+{
+    return NL == 0 ? 8 : NL == 1 ? 6 : NL == 2 ? 5 : 4;
+}
+
+template <int NL>
+__global__ void __launch_bounds__(128, gamma_direct_min_blocks(NL))
+gamma_direct_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int colBase, int prdOnly)
+{
+    extern __shared__ double smem[];
+    const int K = P.K, KC = blockDim.x, RS = (gridDim.z == 1) ? K : KC;
+    const int la = lamList[blockIdx.x];
+    const int cb = blockIdx.y, col = column_of(P, colBase + cb);
+    const int kk = threadIdx.x, k = blockIdx.z * KC + kk;
+    double* Xs = smem; // [maxNlevel][RS], one column per thread
+    double* Us = Xs + (size_t)P.maxNlevel * RS;
+    if (k >= K)
+        return;
+    const double Tk = __ldg(P.temperature + (size_t)col * K + k);
+    double W0 = 0.0;
+    for (int mu = 0; mu < P.M; ++mu)
+    {
+        const double w = 0.5 * __ldg(P.wmu + mu);
+        W0 += w;
+        W0 += w;
+    }
+    gamma_lambda<NL, true>(P, la, col, cb, k, Tk, W0, P.accum + (size_t)col * P.AccTot * K + k, Xs, Us, prdOnly != 0);
 }
 
 } // namespace lwb200

@@ -63,6 +63,7 @@ def test_cuda_vs_oracle_multicolumn_c1(solver, tileLen, monkeypatch):
     per Gamma tile (the planner picks 1 for a problem this small; larger stacks get up to 32)."""
     if tileLen is not None:
         monkeypatch.setenv('LWB200_TILE_LEN', str(tileLen))
+        monkeypatch.setenv('LWB200_GAMMA_DIRECT', '0')   # the tiled Gamma stage of large launches
     p = synth.config_c1(ncol=3, perturb=True, formal_solver=solver, nl=0.4)
     q = p.clone()
     ctx = Context(p)
@@ -251,9 +252,14 @@ def test_cuda_prd_matches_reference_golden(name):
     ctx.close()
 
 
-@pytest.mark.parametrize('ndepth', [None, 200])
-def test_cuda_prd_vs_oracle_columns(ndepth):
-    """Angle-averaged PRD on a perturbed two-column stack (also with several warps per column)."""
+@pytest.mark.parametrize('ndepth,tiled', [(None, False), (200, False), (None, True), (200, True)])
+def test_cuda_prd_vs_oracle_columns(ndepth, tiled, monkeypatch):
+    """Angle-averaged PRD on a perturbed two-column stack (also with several warps per column).
+    tiled: the Gamma stage of large launches (shared-memory tiles) instead of the per-wavelength one
+    a problem this small gets."""
+    if tiled:
+        monkeypatch.setenv('LWB200_GAMMA_DIRECT', '0')
+        monkeypatch.setenv('LWB200_TILE_LEN', '5')
     p = synth.tiny_prd_problem(ncol=2, perturb=True, ndepth=ndepth)
     q = p.clone()
     ctx = Context(p)
