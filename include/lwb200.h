@@ -259,6 +259,20 @@ int lwb200_stat_eq(LwB200Context* ctx, int32_t atom, int32_t kStart, int32_t kEn
  * ray left in its scratch there). */
 int lwb200_formal_sol_full_stokes(LwB200Context* ctx, int updateJ, int upOnly, double* dJMax, int64_t* dJMaxIdx);
 
+/* Ng acceleration of the populations on the device (Source/Ng.hpp:16-163; the reference runs one Ng
+ * object per atom on the host after every population update, LwMiddleLayer.pyx:3318-3346).
+ * lwb200_ng_configure = the Ng(Norder, Nperiod, Ndelay, n) constructor on the populations currently
+ * on the device, for every active atom (and column); lwb200_ng_accelerate = accelerate(n) followed
+ * by max_change(): *accelerated tells whether this call extrapolated, dMax / dMaxIdx [Natom] are the
+ * largest relative change between the last two stored solutions of each atom and its flat index
+ * (level * Nspace + depth, + column * Nlevel * Nspace in a stack; 0 for detailed-static atoms).
+ * Norder <= 4.  Norder = 0 tracks changes only, like the reference's default Ng(0, 0, 0).
+ * Configurations with max(Ndelay, Nperiod + 2) < Norder + 2 are refused: the reference indexes
+ * its history with a negative row there. */
+int lwb200_ng_configure(LwB200Context* ctx, int32_t Norder, int32_t Nperiod, int32_t Ndelay);
+int lwb200_ng_accelerate(LwB200Context* ctx, int32_t* accelerated, double* dMax, int64_t* dMaxIdx);
+int lwb200_ng_clear(LwB200Context* ctx);
+
 /* Latency-hiding variants for a host that synchronises once per call sequence (the Python mirror):
  * lwb200_stat_eq_async launches the solve and sends the singular-system count home with the stream;
  * lwb200_last_singular / lwb200_last_dj read those results after the next lwb200_sync

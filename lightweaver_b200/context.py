@@ -42,6 +42,7 @@ class IterationUpdate:
     updatedJPrd: bool = False
     dJPrdMax: List[float] = field(default_factory=list)
     dJPrdMaxIdx: List[int] = field(default_factory=list)
+    ngAccelerated: bool = False
 
 
 class Context:
@@ -88,6 +89,28 @@ class Context:
 
     def set_lambda_range(self, laStart, laEnd):
         capi.check(self.lib.lwb200_set_lambda_range(self._h, int(laStart), int(laEnd)))
+
+    def ng_configure(self, Norder=0, Nperiod=0, Ndelay=0):
+        """Ng acceleration of the populations on the device (lw.Context's ``ngOptions``): the
+        populations currently on the device become the first stored solution of every active atom."""
+        capi.check(self.lib.lwb200_ng_configure(self._h, int(Norder), int(Nperiod), int(Ndelay)))
+        self._ng = True
+
+    def ng_accelerate_device(self):
+        """Ng.accelerate + Ng.max_change on the device-resident populations of every active atom.
+        Returns (accelerated, dMax per atom, dMaxIdx per atom) over ALL atoms of the problem
+        (detailed-static ones report 0)."""
+        na = len(self.problem.atoms)
+        acc = C.c_int32(0)
+        dMax = np.zeros(na)
+        dIdx = np.zeros(na, dtype=np.int64)
+        rc = self.lib.lwb200_ng_accelerate(self._h, C.byref(acc), capi.dptr(dMax),
+                                           dIdx.ctypes.data_as(C.POINTER(C.c_int64)))
+        if rc != 0:
+            if b'Singular' in self.lib.lwb200_last_error():
+                raise ExplodingMatrixError('Singular Matrix')
+            capi.check(rc)
+        return bool(acc.value), dMax, dIdx
 
     def set_active_columns(self, active=None):
         """Retire converged columns of a stack: ``active`` is a boolean array [Ncol] (None: all
@@ -278,6 +301,20 @@ class Context:
         current Gamma (LwMiddleLayer.pyx:3461-3531); raises ExplodingMatrixError
         on a singular system.  Returns the relative population change per atom
         (what rel_diff_ng_accelerate reports without Ng acceleration)."""
+        if getattr(self, '_ng', False):
+            # Ng on the device: the update, the acceleration and the change tracking all run on the
+            # device-resident populations (rel_diff_ng_accelerate, LwMiddleLayer.pyx:3318-3346)
+            self.upload(capi.POPS | capi.GAMMA_FINAL)
+            self.stat_eq_device()
+            accelerated, dMax, dIdx = self.ng_accelerate_device()
+            self.download(capi.POPS)
+            upd = IterationUpdate(updatedPops=True)
+            upd.ngAccelerated = accelerated
+            for q, a in enumerate(self.problem.atoms):
+                if not a.detailedStatic:
+                    upd.dPops.append(float(dMax[q]))
+                    upd.dPopsMaxIdx.append(int(dIdx[q]))
+            return upd
         prev = [a.n.copy() for a in self.problem.active_atoms()]
         self.upload(capi.POPS | capi.GAMMA_FINAL)
         capi.check(self.lib.lwb200_stat_eq_async(self._h, -1, -1, -1))

@@ -7,6 +7,7 @@
 #include "lwb200_pipeline.cuh"
 #include "lwb200_prd.cuh"
 #include "lwb200_stokes.cuh"
+#include "lwb200_ng.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -234,6 +235,10 @@ struct LwB200Context
     size_t scratchGamma = 0;
     int gammaDirect = -1; // -1: by launch size
     cudaEvent_t evRaysKind[4] = {nullptr, nullptr, nullptr, nullptr};
+    // Ng acceleration of the populations (lwb200_ng.cuh)
+    DevBuf<double> ngRing, ngMax;
+    DevBuf<long long> ngIdx;
+    int ngOrder = -1, ngPeriod = 0, ngDelay = 0, ngCount = 0;
     bool singularPending = false; // an asynchronous population update whose singular count is uncollected
     bool djEarly = false, djDone = false; // dJ reduced on a side stream while Gamma is accumulated
     DevBuf<DevTrans> dTrans;
@@ -1328,6 +1333,9 @@ int lwb200_destroy(LwB200Context* c)
     c->dListDirect.release();
     c->dListAll.release();
     c->djIdx.release();
+    c->ngRing.release();
+    c->ngMax.release();
+    c->ngIdx.release();
     c->dColList.release();
     c->dColActive.release();
     c->djPartIdx.release();
@@ -1382,6 +1390,93 @@ int lwb200_set_active_columns(LwB200Context* c, const uint8_t* active)
     c->P.colList = c->dColList.p;
     c->P.colActive = c->dColActive.p;
     c->nActiveCol = (int)list.size();
+    return 0;
+}
+
+int lwb200_ng_configure(LwB200Context* c, int32_t Norder, int32_t Nperiod, int32_t Ndelay)
+{
+    CU(cudaSetDevice(c->device));
+    if (Norder < 0 || Norder > kNgMaxOrder)
+        return fail("lwb200_ng_configure: Norder must be 0.." + std::to_string(kNgMaxOrder));
+    if (Norder > 0 && Nperiod < 1)
+        return fail("lwb200_ng_configure: Nperiod must be >= 1");
+    Ndelay = std::max(Ndelay, Nperiod + 2); // Ng.hpp:34
+    if (Norder > 0 && Ndelay < Norder + 2)
+        return fail("lwb200_ng_configure: Ndelay < Norder + 2 (the reference reads outside its history there)");
+    const int R = Norder + 2;
+    c->ngRing.release();
+    c->ngMax.release();
+    c->ngIdx.release();
+    if (c->ngRing.alloc((size_t)R * c->n.n) || c->ngMax.alloc(c->prob.Natom) || c->ngIdx.alloc(c->prob.Natom))
+        return 1;
+    // the constructor keeps the current populations as the first solution (Ng.hpp:31-41)
+    CU(cudaMemsetAsync(c->ngRing.p, 0, c->ngRing.n * sizeof(double), c->stream));
+    CU(cudaMemcpyAsync(c->ngRing.p, c->n.p, c->n.n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->ngOrder = Norder;
+    c->ngPeriod = Nperiod;
+    c->ngDelay = Ndelay;
+    c->ngCount = 1;
+    return 0;
+}
+
+int lwb200_ng_clear(LwB200Context* c)
+{
+    CU(cudaSetDevice(c->device));
+    if (c->ngOrder < 0)
+        return fail("lwb200_ng_clear: lwb200_ng_configure has not been called");
+    CU(cudaMemsetAsync(c->ngRing.p, 0, c->ngRing.n * sizeof(double), c->stream));
+    c->ngCount = 0;
+    return 0;
+}
+
+int lwb200_ng_accelerate(LwB200Context* c, int32_t* accelerated, double* dMax, int64_t* dMaxIdx)
+{
+    CU(cudaSetDevice(c->device));
+    if (c->ngOrder < 0)
+        return fail("lwb200_ng_accelerate: lwb200_ng_configure has not been called");
+    const int R = c->ngOrder + 2, Natom = c->prob.Natom;
+    const size_t stride = c->n.n;
+    c->lastLaunches = 0;
+    // accelerate(): store the new solution (Ng.hpp:62-65)
+    CU(cudaMemcpyAsync(c->ngRing.p + (size_t)(c->ngCount % R) * stride, c->n.p, stride * sizeof(double),
+                       cudaMemcpyDeviceToDevice, c->stream));
+    c->ngCount += 1;
+    const bool go = c->ngOrder > 0 && c->ngCount >= c->ngDelay && ((c->ngCount - c->ngDelay) % c->ngPeriod) == 0;
+    if (accelerated)
+        *accelerated = go ? 1 : 0;
+    CU(cudaMemsetAsync(c->dSingular.p, 0, sizeof(int), c->stream));
+    if (go)
+    {
+        ng_accelerate_kernel<<<dim3(Natom, c->prob.Ncol), 256, 0, c->stream>>>(c->P, c->ngRing.p, R, stride, c->ngCount,
+                                                                              c->ngOrder, c->n.p, c->dSingular.p);
+        CU(cudaGetLastError());
+        c->lastLaunches += 1;
+    }
+    std::vector<double> hMax(Natom, 0.0);
+    std::vector<long long> hIdx(Natom, 0);
+    if (c->ngCount >= 2)
+    {
+        // max_change(): the last two stored solutions (Ng.hpp:138-156)
+        ng_max_change_kernel<<<Natom, 256, 0, c->stream>>>(c->P, c->ngRing.p + (size_t)((c->ngCount - 1) % R) * stride,
+                                                          c->ngRing.p + (size_t)((c->ngCount - 2) % R) * stride,
+                                                          c->ngMax.p, c->ngIdx.p);
+        CU(cudaGetLastError());
+        c->lastLaunches += 1;
+        CU(cudaMemcpyAsync(hMax.data(), c->ngMax.p, Natom * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(hIdx.data(), c->ngIdx.p, Natom * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    }
+    int ns = 0;
+    CU(cudaMemcpyAsync(&ns, c->dSingular.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int a = 0; a < Natom; ++a)
+    {
+        if (dMax)
+            dMax[a] = hMax[a];
+        if (dMaxIdx)
+            dMaxIdx[a] = hIdx[a];
+    }
+    if (ns > 0)
+        return fail("Singular Matrix");
     return 0;
 }
 

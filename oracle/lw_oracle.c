@@ -871,6 +871,95 @@ int lwo_solve_lin_eq(int N, double* A, double* b, int improve)
     return 0;
 }
 
+/* Ng acceleration of a sequence of solutions (Ng.hpp:16-163): the Ng(nOrder, nPeriod, nDelay, sol)
+ * constructor on sols[0], then accelerate() + max_change() on sols[1..nIter] in turn.
+ * out [nIter][len]: the solutions as accelerate() leaves them. */
+int lwo_ng_run(int Norder, int Nperiod, int Ndelay, int len, int nIter, const double* sols, double* out,
+               int* accelerated, double* dMax, int64_t* dMaxIdx)
+{
+    if (Norder < 0 || Norder > 8)
+        return 2;
+    const int R = Norder + 2;
+    Ndelay = Ndelay > Nperiod + 2 ? Ndelay : Nperiod + 2;               /* :34 */
+    /* the reference indexes previous(count - Norder - 2) at the first acceleration (:80-81): with
+     * Ndelay < Norder + 2 that row index is negative (undefined behaviour there); not restated */
+    if (Norder > 0 && Ndelay < Norder + 2)
+        return 2;
+    double* previous = (double*)calloc((size_t)R * len, sizeof(double));
+    double* Delta = (double*)malloc((size_t)(Norder + 1) * len * sizeof(double));
+    double* weight = (double*)malloc((size_t)len * sizeof(double));
+    int count = 0, rc = 0;
+    memcpy(previous, sols, sizeof(double) * len);                       /* :37-40 */
+    count = 1;
+    for (int it = 0; it < nIter && !rc; ++it)
+    {
+        double* sol = out + (size_t)it * len;
+        memcpy(sol, sols + (size_t)(it + 1) * len, sizeof(double) * len);
+        /* accelerate, :52-114 */
+        memcpy(previous + (size_t)(count % R) * len, sol, sizeof(double) * len);
+        count += 1;
+        accelerated[it] = 0;
+        if (Norder > 0 && count >= Ndelay && ((count - Ndelay) % Nperiod) == 0)
+        {
+            for (int i = 0; i <= Norder; ++i)
+            {
+                const double* a = previous + (size_t)((count - i - 1) % R) * len;
+                const double* b = previous + (size_t)((count - i - 2) % R) * len;
+                for (int k = 0; k < len; ++k)
+                    Delta[(size_t)i * len + k] = a[k] - b[k];
+            }
+            for (int k = 0; k < len; ++k)
+                weight[k] = 1.0 / fabs(sol[k]);
+            double A[64] = {0.0}, b[8] = {0.0};
+            for (int j = 0; j < Norder; ++j)
+            {
+                for (int k = 0; k < len; ++k)
+                    b[j] += weight[k] * Delta[k] * (Delta[k] - Delta[(size_t)(j + 1) * len + k]);
+                for (int i = 0; i < Norder; ++i)
+                    for (int k = 0; k < len; ++k)
+                        A[i * Norder + j] += weight[k] * (Delta[(size_t)(j + 1) * len + k] - Delta[k])
+                                             * (Delta[(size_t)(i + 1) * len + k] - Delta[k]);
+            }
+            if (lwo_solve_lin_eq(Norder, A, b, 1))
+            {
+                rc = 1;
+                break;
+            }
+            double* p0 = previous + (size_t)((count - 1) % R) * len;
+            for (int i = 0; i < Norder; ++i)
+            {
+                const double* pi = previous + (size_t)((count - i - 2) % R) * len;
+                for (int k = 0; k < len; ++k)
+                    sol[k] += b[i] * (pi[k] - p0[k]);
+            }
+            memcpy(p0, sol, sizeof(double) * len);
+            accelerated[it] = 1;
+        }
+        /* max_change, :138-156 */
+        dMax[it] = 0.0;
+        dMaxIdx[it] = 0;
+        if (count >= 2)
+        {
+            const double* old = previous + (size_t)((count - 2) % R) * len;
+            const double* cur = previous + (size_t)((count - 1) % R) * len;
+            for (int k = 0; k < len; ++k)
+                if (cur[k] != 0.0)
+                {
+                    const double change = fabs((cur[k] - old[k]) / cur[k]);
+                    if (dMax[it] < change)
+                    {
+                        dMax[it] = change;
+                        dMaxIdx[it] = k;
+                    }
+                }
+        }
+    }
+    free(previous);
+    free(Delta);
+    free(weight);
+    return rc;
+}
+
 /* stat_eq_impl, UpdatePopulations.cpp:7-47 */
 int lwo_stat_eq(const LwB200Problem* p, int col, int atom, int kStart, int kEnd, int* nSingular)
 {

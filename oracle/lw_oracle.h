@@ -70,6 +70,12 @@ int lwo_nr_post_update(const LwB200Problem* p, int col, const LwB200NrUpdate* up
 int lwo_redistribute_prd(const LwB200Problem* p, int col, int maxIter, double tol, int includeDetailed,
                          int* nIter, double* dRho, int* dRhoIdx, double* dJPrdMax, int64_t* dJPrdMaxIdx);
 
+/* Ng acceleration (Ng.hpp:16-163): constructor on sols[0], then accelerate() + max_change() on
+ * sols[1..nIter]; out [nIter][len] = the solutions as accelerate() leaves them.  Returns 1 for a
+ * singular acceleration system. */
+int lwo_ng_run(int Norder, int Nperiod, int Ndelay, int len, int nIter, const double* sols, double* out,
+               int* accelerated, double* dMax, int64_t* dMaxIdx);
+
 /* Transition::compute_phi / compute_wphi are NOT restated here (they need
  * Faddeeva); the tests use scipy.special.wofz (the same Faddeeva package). */
 

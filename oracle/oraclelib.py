@@ -36,6 +36,8 @@ def load():
     lib.lwo_formal_sol.argtypes = [vp, C.c_int, C.c_int]
     lib.lwo_stat_eq.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.lwo_solve_lin_eq.argtypes = [C.c_int, dp, dp, C.c_int]
+    lib.lwo_ng_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int), dp,
+                                  C.POINTER(C.c_int64)]
     lib.lwo_fs_iter_columns.argtypes = [vp, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int]
     lib.lwo_full_stokes.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, i64p]
     lib.lwo_nr_post_update.argtypes = [vp, C.c_int, vp]
@@ -130,3 +132,22 @@ def solve_lin_eq(A, b, improve=True):
     if rc:
         raise RuntimeError('Singular Matrix')
     return b
+
+
+def ng_run(Norder, Nperiod, Ndelay, sols):
+    """Ng(Norder, Nperiod, Ndelay, sols[0]) then accelerate() + max_change() on sols[1:] (Ng.hpp).
+    Returns (solutions after accelerate [nIter, len], accelerated [nIter], dMax, dMaxIdx)."""
+    lib = load()
+    sols = np.ascontiguousarray(sols, dtype=np.float64)
+    nIter, n = sols.shape[0] - 1, sols.shape[1]
+    out = np.zeros((nIter, n))
+    acc = np.zeros(nIter, dtype=np.int32)
+    dMax = np.zeros(nIter)
+    dIdx = np.zeros(nIter, dtype=np.int64)
+    dp = C.POINTER(C.c_double)
+    rc = lib.lwo_ng_run(Norder, Nperiod, Ndelay, n, nIter, sols.ctypes.data_as(dp), out.ctypes.data_as(dp),
+                       acc.ctypes.data_as(C.POINTER(C.c_int)), dMax.ctypes.data_as(dp),
+                       dIdx.ctypes.data_as(C.POINTER(C.c_int64)))
+    if rc:
+        raise RuntimeError('Singular Matrix')
+    return out, acc, dMax, dIdx

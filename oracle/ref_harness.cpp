@@ -569,6 +569,33 @@ int lwref_solve_ray(int solver, int Nspace, const double* height, const double* 
     }
 }
 
+// The reference's own Ng object (Source/Ng.hpp) driven over a prescribed sequence of solutions:
+// constructor on sols[0], then accelerate() + max_change() on sols[1..nIter].
+int lwref_ng_run(int Norder, int Nperiod, int Ndelay, int len, int nIter, const double* sols, double* out,
+                 int* accelerated, double* dMax, int64_t* dMaxIdx)
+{
+    try
+    {
+        std::vector<double> first(sols, sols + len);
+        Ng ng(Norder, Nperiod, Ndelay, F64View(first.data(), len));
+        for (int it = 0; it < nIter; ++it)
+        {
+            double* sol = out + (size_t)it * len;
+            std::memcpy(sol, sols + (size_t)(it + 1) * len, sizeof(double) * len);
+            accelerated[it] = ng.accelerate(F64View(sol, len)) ? 1 : 0;
+            const NgChange ch = ng.max_change();
+            dMax[it] = ch.dMax;
+            dMaxIdx[it] = ch.dMaxIdx;
+        }
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
 // solve_lin_eq (Source/LuSolve.cpp:103-133) on a caller-owned N x N system.
 int lwref_solve_lin_eq(int N, double* A, double* b, int improve)
 {

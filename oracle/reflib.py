@@ -70,6 +70,8 @@ def load():
     lib.lwref_solve_ray.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_int,
                                     C.c_double, C.c_int, C.c_int, dp, dp]
     lib.lwref_solve_lin_eq.argtypes = [C.c_int, dp, dp, C.c_int]
+    lib.lwref_ng_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int), dp,
+                                  C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 
@@ -180,3 +182,22 @@ def solve_lin_eq(A, b, improve=True):
     dp = C.POINTER(C.c_double)
     _check(lib.lwref_solve_lin_eq(A.shape[0], A.ctypes.data_as(dp), b.ctypes.data_as(dp), int(improve)))
     return b
+
+
+def ng_run(Norder, Nperiod, Ndelay, sols):
+    """Ng(Norder, Nperiod, Ndelay, sols[0]) then accelerate() + max_change() on sols[1:] (Ng.hpp).
+    Returns (solutions after accelerate [nIter, len], accelerated [nIter], dMax, dMaxIdx)."""
+    lib = load()
+    sols = np.ascontiguousarray(sols, dtype=np.float64)
+    nIter, n = sols.shape[0] - 1, sols.shape[1]
+    out = np.zeros((nIter, n))
+    acc = np.zeros(nIter, dtype=np.int32)
+    dMax = np.zeros(nIter)
+    dIdx = np.zeros(nIter, dtype=np.int64)
+    dp = C.POINTER(C.c_double)
+    rc = lib.lwref_ng_run(Norder, Nperiod, Ndelay, n, nIter, sols.ctypes.data_as(dp), out.ctypes.data_as(dp),
+                       acc.ctypes.data_as(C.POINTER(C.c_int)), dMax.ctypes.data_as(dp),
+                       dIdx.ctypes.data_as(C.POINTER(C.c_int64)))
+    if rc:
+        raise RuntimeError('Singular Matrix')
+    return out, acc, dMax, dIdx

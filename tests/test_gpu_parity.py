@@ -536,6 +536,65 @@ def test_retired_columns_are_skipped_and_keep_their_values():
     ctx.close()
 
 
+@pytest.mark.parametrize('opts', [(2, 3, 5), (3, 2, 5), (0, 0, 0), (4, 5, 12), (1, 1, 0)])
+def test_ng_acceleration_on_device_matches_oracle(opts):
+    # a prescribed sequence of population vectors (six geometric modes around a fixed point) through
+    # the device Ng and through the restatement of Ng.hpp (itself bit-identical to the reference's Ng)
+    p = synth.tiny_problem(ncol=2)
+    a = p.atoms[0]
+    ncol, N, K = a.n.shape
+    rng = np.random.default_rng(11)
+    fix = np.abs(rng.normal(size=(ncol, N * K))) + 1.0
+    V = rng.normal(size=(6, ncol, N * K))
+    r = np.array([0.95, 0.9, 0.8, 0.7, 0.5, 0.3])
+    nIter = 14
+    sols = np.array([fix + sum(0.3 * r[m] ** it * V[m] for m in range(6)) for it in range(nIter + 1)])
+    want = [oraclelib.ng_run(*opts, sols[:, c, :]) for c in range(ncol)]
+    ctx = Context(p)
+    a.n[...] = sols[0].reshape(ncol, N, K)
+    ctx.upload(capi.POPS)
+    ctx.ng_configure(*opts)
+    for it in range(nIter):
+        a.n[...] = sols[it + 1].reshape(ncol, N, K)
+        ctx.upload(capi.POPS)
+        acc, dMax, dIdx = ctx.ng_accelerate_device()
+        ctx.download(capi.POPS)
+        assert acc == bool(want[0][1][it])
+        for c in range(ncol):
+            # the device sums the normal equations in another order; their conditioning grows with
+            # Norder (measured: 4e-10 at Norder = 4), so the tolerance does too
+            assert rel_err(a.n[c].reshape(-1), want[c][0][it]) <= (1e-9 if opts[0] <= 3 else 1e-7)
+        dm = [want[c][2][it] for c in range(ncol)]
+        cbest = int(np.argmax(dm))
+        assert abs(dMax[0] - dm[cbest]) <= 1e-9 * max(dm[cbest], 1e-300)
+        assert dIdx[0] == cbest * N * K + want[cbest][3][it]
+    with pytest.raises(capi.LwB200Error):
+        ctx.ng_configure(3, 1, 0)     # the reference reads outside its history here
+    ctx.close()
+
+
+def test_ng_accelerated_iteration_converges_to_the_same_populations():
+    def converge(ng):
+        p = synth.tiny_problem()
+        ctx = Context(p)
+        if ng:
+            ctx.ng_configure(2, 3, 5)
+        nacc = 0
+        for it in range(60):
+            ctx.formal_sol_gamma_matrices(lambdaIterate=(it < 2))
+            upd = ctx.stat_equil()
+            nacc += int(upd.ngAccelerated)
+            if it > 3 and max(upd.dPops) < 1e-9:
+                break
+        ctx.close()
+        return p.atoms[0].n.copy(), it, nacc
+    plain, itPlain, _ = converge(False)
+    acc, itAcc, nacc = converge(True)
+    assert nacc > 0
+    assert rel_err(acc, plain) <= 1e-6
+    assert itAcc <= itPlain
+
+
 def test_device_profiles_match_host_voigt():
     """lwb200_compute_profiles (device Voigt) vs the Faddeeva-based host profiles."""
     p = synth.config_c1(ncol=2, perturb=True, nl=0.3)

@@ -357,3 +357,21 @@ def test_create_fails_loudly_without_gpu():
     from lightweaver_b200.context import Context
     with pytest.raises(capi.LwB200Error):
         Context(synth.tiny_problem())
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize('opts', [(2, 3, 5), (3, 2, 5), (0, 0, 0), (2, 2, 4), (4, 5, 12), (1, 1, 0)])
+def test_oracle_ng_vs_reference(opts):
+    """lwo_ng_run against the reference's own Ng object (Ng.hpp) over a prescribed sequence."""
+    rng = np.random.default_rng(5)
+    n = 60
+    fix = np.abs(rng.normal(size=n)) + 1.0
+    V = rng.normal(size=(6, n))
+    r = np.array([0.95, 0.9, 0.8, 0.7, 0.5, 0.3])
+    sols = np.array([fix + sum(0.3 * r[m] ** it * V[m] for m in range(6)) for it in range(15)])
+    a = oraclelib.ng_run(*opts, sols)
+    b = reflib.ng_run(*opts, sols)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    if opts[0] > 0:
+        assert a[1].sum() > 0
