@@ -272,6 +272,10 @@ int lwb200_formal_sol_full_stokes(LwB200Context* ctx, int updateJ, int upOnly, d
 int lwb200_ng_configure(LwB200Context* ctx, int32_t Norder, int32_t Nperiod, int32_t Ndelay);
 int lwb200_ng_accelerate(LwB200Context* ctx, int32_t* accelerated, double* dMax, int64_t* dMaxIdx);
 int lwb200_ng_clear(LwB200Context* ctx);
+/* lwb200_ng_accelerate(ctx, &accelerated, NULL, NULL) does not synchronise the host: dMax / dMaxIdx are
+ * read with lwb200_last_ng after the next lwb200_sync, a singular acceleration system is reported by
+ * lwb200_last_singular. */
+int lwb200_last_ng(LwB200Context* ctx, double* dMax, int64_t* dMaxIdx);
 
 /* Latency-hiding variants for a host that synchronises once per call sequence (the Python mirror):
  * lwb200_stat_eq_async launches the solve and sends the singular-system count home with the stream;

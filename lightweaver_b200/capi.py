@@ -153,6 +153,7 @@ def load():
     lib.lwb200_ng_configure.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     lib.lwb200_ng_accelerate.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.lwb200_ng_clear.argtypes = [vp]
+    lib.lwb200_last_ng.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.lwb200_upload.argtypes = [vp, C.c_uint32]
     lib.lwb200_download.argtypes = [vp, C.c_uint32]
     lib.lwb200_sync.argtypes = [vp]
@@ -193,7 +194,7 @@ def check(rc):
 
 EXPORTED_SYMBOLS = [
     'lwb200_last_error', 'lwb200_abi_version', 'lwb200_device_count', 'lwb200_create',
-    'lwb200_destroy', 'lwb200_set_stream', 'lwb200_set_lambda_range', 'lwb200_set_active_columns', 'lwb200_ng_configure', 'lwb200_ng_accelerate', 'lwb200_ng_clear', 'lwb200_upload',
+    'lwb200_destroy', 'lwb200_set_stream', 'lwb200_set_lambda_range', 'lwb200_set_active_columns', 'lwb200_ng_configure', 'lwb200_ng_accelerate', 'lwb200_ng_clear', 'lwb200_last_ng', 'lwb200_upload',
     'lwb200_download', 'lwb200_sync', 'lwb200_compute_profiles', 'lwb200_fs_iter',
     'lwb200_finalise', 'lwb200_dj_max', 'lwb200_formal_sol', 'lwb200_stat_eq',
     'lwb200_device_buffer', 'lwb200_work_stats', 'lwb200_kernel_time', 'lwb200_redistribute_prd',

@@ -301,36 +301,31 @@ class Context:
         current Gamma (LwMiddleLayer.pyx:3461-3531); raises ExplodingMatrixError
         on a singular system.  Returns the relative population change per atom
         (what rel_diff_ng_accelerate reports without Ng acceleration)."""
-        if getattr(self, '_ng', False):
-            # Ng on the device: the update, the acceleration and the change tracking all run on the
-            # device-resident populations (rel_diff_ng_accelerate, LwMiddleLayer.pyx:3318-3346)
-            self.upload(capi.POPS | capi.GAMMA_FINAL)
-            self.stat_eq_device()
-            accelerated, dMax, dIdx = self.ng_accelerate_device()
-            self.download(capi.POPS)
-            upd = IterationUpdate(updatedPops=True)
-            upd.ngAccelerated = accelerated
-            for q, a in enumerate(self.problem.atoms):
-                if not a.detailedStatic:
-                    upd.dPops.append(float(dMax[q]))
-                    upd.dPopsMaxIdx.append(int(dIdx[q]))
-            return upd
-        prev = [a.n.copy() for a in self.problem.active_atoms()]
+        # the update, the Ng step and the change tracking all run on the device-resident populations
+        # (rel_diff_ng_accelerate, LwMiddleLayer.pyx:3318-3346); one host synchronisation.  Without
+        # ng_configure this is the reference's default Ng(0, 0, 0): change tracking only.
         self.upload(capi.POPS | capi.GAMMA_FINAL)
+        if not getattr(self, '_ng', False):
+            self.ng_configure(0, 0, 0)      # first stored solution: the populations before this update
         capi.check(self.lib.lwb200_stat_eq_async(self._h, -1, -1, -1))
+        acc = C.c_int32(0)
+        capi.check(self.lib.lwb200_ng_accelerate(self._h, C.byref(acc), None, None))
         self.download(capi.POPS)   # (synchronises)
         ns = C.c_int32(0)
         if self.lib.lwb200_last_singular(self._h, C.byref(ns)) != 0:
             if ns.value > 0:
                 raise ExplodingMatrixError('Singular Matrix')
             capi.check(1)
+        na = len(self.problem.atoms)
+        dMax = np.zeros(na)
+        dIdx = np.zeros(na, dtype=np.int64)
+        capi.check(self.lib.lwb200_last_ng(self._h, capi.dptr(dMax), dIdx.ctypes.data_as(C.POINTER(C.c_int64))))
         upd = IterationUpdate(updatedPops=True)
-        for p, a in zip(prev, self.problem.active_atoms()):
-            with np.errstate(divide='ignore', invalid='ignore'):
-                d = np.abs(1.0 - p / a.n)
-            d = np.where(np.isfinite(d), d, 0.0)
-            upd.dPops.append(float(d.max()))
-            upd.dPopsMaxIdx.append(int(d.argmax()))
+        upd.ngAccelerated = bool(acc.value)
+        for q, a in enumerate(self.problem.atoms):
+            if not a.detailedStatic:
+                upd.dPops.append(float(dMax[q]))
+                upd.dPopsMaxIdx.append(int(dIdx[q]))
         return upd
 
     def time_dep_update(self, dt, prevTimePops=None, extraParams=None):

@@ -239,6 +239,8 @@ struct LwB200Context
     DevBuf<double> ngRing, ngMax;
     DevBuf<long long> ngIdx;
     int ngOrder = -1, ngPeriod = 0, ngDelay = 0, ngCount = 0;
+    double* ngHostMax = nullptr;   // pinned [Natom]: results of the last lwb200_ng_accelerate
+    long long* ngHostIdx = nullptr; // pinned [Natom]
     bool singularPending = false; // an asynchronous population update whose singular count is uncollected
     bool djEarly = false, djDone = false; // dJ reduced on a side stream while Gamma is accumulated
     DevBuf<DevTrans> dTrans;
@@ -1293,6 +1295,10 @@ int lwb200_destroy(LwB200Context* c)
     }
     if (c->hs)
         cudaFreeHost(c->hs);
+    if (c->ngHostMax)
+        cudaFreeHost(c->ngHostMax);
+    if (c->ngHostIdx)
+        cudaFreeHost(c->ngHostIdx);
     if (c->evK0)
         cudaEventDestroy(c->evK0);
     if (c->evK1)
@@ -1409,6 +1415,13 @@ int lwb200_ng_configure(LwB200Context* c, int32_t Norder, int32_t Nperiod, int32
     c->ngIdx.release();
     if (c->ngRing.alloc((size_t)R * c->n.n) || c->ngMax.alloc(c->prob.Natom) || c->ngIdx.alloc(c->prob.Natom))
         return 1;
+    if (!c->ngHostMax)
+    {
+        CU(cudaHostAlloc((void**)&c->ngHostMax, std::max(1, c->prob.Natom) * sizeof(double), cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&c->ngHostIdx, std::max(1, c->prob.Natom) * sizeof(long long), cudaHostAllocDefault));
+    }
+    if (ensure_host_scalars(c))
+        return 1;
     // the constructor keeps the current populations as the first solution (Ng.hpp:31-41)
     CU(cudaMemsetAsync(c->ngRing.p, 0, c->ngRing.n * sizeof(double), c->stream));
     CU(cudaMemcpyAsync(c->ngRing.p, c->n.p, c->n.n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -1444,16 +1457,31 @@ int lwb200_ng_accelerate(LwB200Context* c, int32_t* accelerated, double* dMax, i
     const bool go = c->ngOrder > 0 && c->ngCount >= c->ngDelay && ((c->ngCount - c->ngDelay) % c->ngPeriod) == 0;
     if (accelerated)
         *accelerated = go ? 1 : 0;
-    CU(cudaMemsetAsync(c->dSingular.p, 0, sizeof(int), c->stream));
+    // dMax == dMaxIdx == NULL: no host synchronisation; the results travel with the stream and are read
+    // with lwb200_last_ng after the next lwb200_sync (singular systems: lwb200_last_singular)
+    const bool async = !dMax && !dMaxIdx;
+    int* dSingular = c->dSingular.p;
+    if (async)
+    {
+        if (!c->singularPending)
+            c->hs->nSingular = 0;
+        c->singularPending = true;
+        dSingular = &c->hsDev->nSingular;
+    }
+    else
+        CU(cudaMemsetAsync(c->dSingular.p, 0, sizeof(int), c->stream));
     if (go)
     {
         ng_accelerate_kernel<<<dim3(Natom, c->prob.Ncol), 256, 0, c->stream>>>(c->P, c->ngRing.p, R, stride, c->ngCount,
-                                                                              c->ngOrder, c->n.p, c->dSingular.p);
+                                                                              c->ngOrder, c->n.p, dSingular);
         CU(cudaGetLastError());
         c->lastLaunches += 1;
     }
-    std::vector<double> hMax(Natom, 0.0);
-    std::vector<long long> hIdx(Natom, 0);
+    for (int a = 0; a < Natom; ++a)
+    {
+        c->ngHostMax[a] = 0.0;
+        c->ngHostIdx[a] = 0;
+    }
     if (c->ngCount >= 2)
     {
         // max_change(): the last two stored solutions (Ng.hpp:138-156)
@@ -1462,21 +1490,37 @@ int lwb200_ng_accelerate(LwB200Context* c, int32_t* accelerated, double* dMax, i
                                                           c->ngMax.p, c->ngIdx.p);
         CU(cudaGetLastError());
         c->lastLaunches += 1;
-        CU(cudaMemcpyAsync(hMax.data(), c->ngMax.p, Natom * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(hIdx.data(), c->ngIdx.p, Natom * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->ngHostMax, c->ngMax.p, Natom * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->ngHostIdx, c->ngIdx.p, Natom * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     }
+    if (async)
+        return 0;
     int ns = 0;
     CU(cudaMemcpyAsync(&ns, c->dSingular.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     for (int a = 0; a < Natom; ++a)
     {
         if (dMax)
-            dMax[a] = hMax[a];
+            dMax[a] = c->ngHostMax[a];
         if (dMaxIdx)
-            dMaxIdx[a] = hIdx[a];
+            dMaxIdx[a] = c->ngHostIdx[a];
     }
     if (ns > 0)
         return fail("Singular Matrix");
+    return 0;
+}
+
+int lwb200_last_ng(LwB200Context* c, double* dMax, int64_t* dMaxIdx)
+{
+    if (c->ngOrder < 0 || !c->ngHostMax)
+        return fail("lwb200_last_ng: lwb200_ng_configure has not been called");
+    for (int a = 0; a < c->prob.Natom; ++a)
+    {
+        if (dMax)
+            dMax[a] = c->ngHostMax[a];
+        if (dMaxIdx)
+            dMaxIdx[a] = c->ngHostIdx[a];
+    }
     return 0;
 }
 
