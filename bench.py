@@ -358,8 +358,9 @@ def run_ours(args, rank, world, local_rank):
     # vBroad and the prefill crsw*C are context state: they cross once and again only after update_deps()
     h2d = sum(a.n.nbytes for a in problem.atoms)
     h2d += sum(a.n.nbytes + a.Gamma.nbytes for a in problem.active_atoms())  # stat_equil: n, Gamma
-    h2d_lambda_sharded = h2d + sum(a.nStar.nbytes + a.nTotal.nbytes + (a.vBroad.nbytes if a.vBroad is not None else 0)
-                                   for a in problem.atoms)  # that loop re-sends ITER_INPUTS every step
+    # lambda-sharded loop: every rank sends the populations, reads back its own rows of J / I and the (replicated)
+    # Gamma, rates and populations
+    h2d_lambda_sharded = sum(a.n.nbytes for a in problem.atoms)
     d2h = problem.J.nbytes + problem.I.nbytes + sum(a.n.nbytes for a in problem.active_atoms())
     d2h += sum(a.Gamma.nbytes for a in problem.active_atoms())
     d2h += sum(t_.Rij.nbytes + t_.Rji.nbytes for a in problem.atoms for t_ in a.trans)
@@ -394,25 +395,28 @@ def run_ours(args, rank, world, local_rank):
                        'Context.formal_sol_gamma_matrices() + Context.stat_equil() on host numpy buffers')}
     else:
         # lambda-sharded: each rank uploads the (replicated) small inputs, reads back its J rows
+        # (the prefill crsw*C, nStar, nTotal, vBroad are context state, as in Context.formal_sol_gamma_matrices)
+        problem.prefill_gamma()
+        ctx.upload(capi.ITER_INPUTS)
         for _ in range(2):
-            problem.prefill_gamma()
-            ctx.upload(capi.ITER_INPUTS)
+            ctx.upload(capi.POPS)
             step()
-            ctx.download(capi.ITER_OUTPUTS | capi.POPS)
+            ctx.download(capi.ITER_OUTPUTS | capi.POPS | capi.OWN_ROWS)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            problem.prefill_gamma()
-            ctx.upload(capi.ITER_INPUTS)
+            ctx.upload(capi.POPS)
             step()
-            ctx.download(capi.ITER_OUTPUTS | capi.POPS)
+            ctx.download(capi.ITER_OUTPUTS | capi.POPS | capi.OWN_ROWS)
         barrier()
         e2e_s = (time.perf_counter() - t0) / args.steps
         te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {'value': pts_total / te.item(), 'unit': 'points/s', 'ms_per_step': te.item() * 1e3,
-               'h2d_bytes_per_step': int(h2d_lambda_sharded), 'd2h_bytes_per_step': int(d2h),
-               'api': 'per-rank upload(ITER_INPUTS) + sharded Gamma iteration + stat_eq + download'}
+               'h2d_bytes_per_step': int(h2d_lambda_sharded * world),
+               'd2h_bytes_per_step': int(problem.J.nbytes + problem.I.nbytes
+                                         + world * (d2h - problem.J.nbytes - problem.I.nbytes)),
+               'api': 'per rank: upload(POPS) + sharded Gamma iteration + stat_eq + download of Gamma, rates, populations and its own rows of J, I'}
 
     if rank != 0:
         ctx.close()

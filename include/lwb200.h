@@ -149,6 +149,8 @@ enum {
     LWB200_PRD     = 1u << 12, /* up: rhoPrd, Qelast, C, aDamp (inputs of lwb200_redistribute_prd);
                                   down: rhoPrd */
     LWB200_STOKES  = 1u << 13, /* up: the polarised profiles of every polarised line; down: Quv */
+    LWB200_OWN_ROWS = 1u << 14, /* down, with JBAR / INTENS: only the rows of the context's wavelength range
+                                   (lwb200_set_lambda_range) -- what a lambda-shard owns */
     LWB200_ALL_INPUTS  = 0x7fu,
     LWB200_ITER_INPUTS = LWB200_POPS | LWB200_NSTAR | LWB200_GAMMA,
     LWB200_ITER_OUTPUTS = LWB200_GAMMA | LWB200_JBAR | LWB200_INTENS | LWB200_RATES

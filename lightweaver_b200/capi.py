@@ -19,7 +19,7 @@ FS_NAMES = {'piecewise_linear_1d': FS_LINEAR, 'piecewise_besser_1d': FS_BESSER,
             'piecewise_bezier3_1d': FS_BEZIER3}
 
 (ATMOS, BACKGR, POPS, NSTAR, GAMMA, JBAR, PROFILE, INTENS, RATES, DEPTH, ADAMP,
- GAMMA_FINAL, PRD, STOKES) = (1 << i for i in range(14))
+ GAMMA_FINAL, PRD, STOKES, OWN_ROWS) = (1 << i for i in range(15))
 ALL_INPUTS = 0x7f
 ITER_INPUTS = POPS | NSTAR | GAMMA
 ITER_OUTPUTS = GAMMA | JBAR | INTENS | RATES

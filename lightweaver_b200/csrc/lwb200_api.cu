@@ -1776,10 +1776,14 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
             const LwB200Transition& t = c->trans[ln.trans].t;
             CU(cudaMemcpyAsync(t.rhoPrd, c->rhoPrd.p + ln.rhoOff, ncol * (size_t)ln.Nl * K * D, D2H, s));
         }
+    // rows [r0, r1) of every column's [L][.] arrays: the context's own wavelength range on request
+    const size_t r0 = (mask & LWB200_OWN_ROWS) ? (size_t)c->laLo : 0, r1 = (mask & LWB200_OWN_ROWS) ? (size_t)c->laHi : L;
     if (mask & LWB200_JBAR)
-        CU(cudaMemcpyAsync(p.J, c->J.p, ncol * L * K * D, D2H, s));
+        if (copy2d(p.J + r0 * K, L * K * D, c->J.p + r0 * K, L * K * D, (r1 - r0) * K * D, ncol, D2H, s))
+            return 1;
     if (mask & LWB200_INTENS)
-        CU(cudaMemcpyAsync(p.I, c->I.p, ncol * L * M * D, D2H, s));
+        if (copy2d(p.I + r0 * M, L * M * D, c->I.p + r0 * M, L * M * D, (r1 - r0) * M * D, ncol, D2H, s))
+            return 1;
     if (mask & LWB200_POPS)
     {
         const size_t rows = c->P.NlevTot;

@@ -402,8 +402,13 @@ def test_lambda_shards_sum_to_full_iteration():
         assert gamma_err(a.Gamma, b.Gamma) <= 1e-12
         for t, u in zip(a.trans, b.trans):
             assert rel_err(t.Rij, u.Rij, floor=1e-30) <= 1e-12
-    # J rows are disjoint per shard
-    ctxs[0].download(capi.JBAR)
+    # J rows are disjoint per shard; OWN_ROWS brings home only the rows a shard owns
+    parts[0].J[:, split:] = -7.0
+    parts[0].I[:, split:] = -7.0
+    ctxs[0].download(capi.JBAR | capi.INTENS | capi.OWN_ROWS)
+    assert np.all(parts[0].J[:, split:] == -7.0) and np.all(parts[0].I[:, split:] == -7.0)
+    cf.download(capi.INTENS)
+    assert rel_err(parts[0].I[:, :split], full.I[:, :split]) <= 1e-14
     ctxs[1].download(capi.JBAR)
     assert rel_err(parts[0].J[:, :split], full.J[:, :split]) <= 1e-14
     assert rel_err(parts[1].J[:, split:], full.J[:, split:]) <= 1e-14
