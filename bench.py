@@ -325,29 +325,28 @@ def run_ours(args, rank, world, local_rank):
             dj_last = ctx.last_dj()[0]
             if not (dj_last == dj_last and dj_last >= 0.0):
                 raise SystemExit(f'bench.py: bad dJ {dj_last}')
-    if clk.get('samples', 0) < 3:
-        # the timed region is shorter than nvidia-smi's sampling period (a 1D atmosphere is < 1 ms
-        # per step): sample the clocks under the SAME step repeated, untimed, for about a second
-        clocks = ClockSampler(local_rank)
-        clocks.start()
-        t_end = time.perf_counter() + 1.5
-        nprobe = 0
-        while time.perf_counter() < t_end:
-            for _ in range(20):
-                step()
-            torch.cuda.synchronize()
-            nprobe += 20
-        clk = clocks.stop()
-        clk['window'] = (f'{nprobe} untimed repeats of the same step right after the timed region '
-                         f'(the timed region itself lasts {total_ms:.1f} ms)')
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     pts = torch.tensor([pts_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if column_sharded:
-            dist.all_reduce(pts, op=dist.ReduceOp.SUM)
-        else:
-            dist.all_reduce(pts, op=dist.ReduceOp.SUM)
+        dist.all_reduce(pts, op=dist.ReduceOp.SUM)
+    # Short timed regions (a 1D atmosphere is < 1 ms per step) end before nvidia-smi has sampled the clocks
+    # three times: sample them under the SAME step repeated, untimed, for about a second and a half.  Whether
+    # to do so and how many repeats are derived from the all-reduced time, i.e. they are identical on every
+    # rank -- the lambda-sharded step contains a collective, so every rank must run it the same number of times.
+    if t.item() < 1200.0:
+        per_step_ms = max(t.item() / args.steps, 1e-3)
+        nprobe = 20 * int(min(max(1500.0 / per_step_ms, 20.0), 20000.0) // 20)
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        for q in range(nprobe):
+            step()
+            if q % 20 == 19:
+                torch.cuda.synchronize()
+        barrier()
+        clk = clocks.stop()
+        clk['window'] = (f'{nprobe} untimed repeats of the same step right after the timed region '
+                         f'(the timed region itself lasts {t.item():.1f} ms)')
     total_ms = t.item()
     pts_total = pts.item()
     ms_per_step = total_ms / args.steps
