@@ -87,6 +87,17 @@ def build_workload(name, columns, rank=0, world=1, for_gpu=True):
     raise SystemExit(f'unknown workload {name}')
 
 
+def clock_probe_repeats(total_ms, steps):
+    """Untimed repeats of the step under which the SM clocks are sampled when the timed region
+    (total_ms, already reduced over ranks) is too short for nvidia-smi: 0, or a multiple of 20 worth
+    about 1.5 s.  A pure function of rank-independent inputs: every rank of a lambda-sharded run must
+    repeat the step -- which contains an all-reduce -- the same number of times."""
+    if total_ms >= 1200.0:
+        return 0
+    per_step_ms = max(total_ms / max(steps, 1), 1e-3)
+    return 20 * int(min(max(1500.0 / per_step_ms, 20.0), 20000.0) // 20)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
@@ -334,9 +345,8 @@ def run_ours(args, rank, world, local_rank):
     # three times: sample them under the SAME step repeated, untimed, for about a second and a half.  Whether
     # to do so and how many repeats are derived from the all-reduced time, i.e. they are identical on every
     # rank -- the lambda-sharded step contains a collective, so every rank must run it the same number of times.
-    if t.item() < 1200.0:
-        per_step_ms = max(t.item() / args.steps, 1e-3)
-        nprobe = 20 * int(min(max(1500.0 / per_step_ms, 20.0), 20000.0) // 20)
+    nprobe = clock_probe_repeats(t.item(), args.steps)
+    if nprobe:
         clocks = ClockSampler(local_rank)
         clocks.start()
         for q in range(nprobe):

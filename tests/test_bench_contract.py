@@ -37,3 +37,18 @@ def test_gpu_arm_refuses_to_run_without_a_device():
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '1', '--warmup', '0'],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and 'no CPU fallback' in (r.stderr + r.stdout)
+
+
+def test_clock_probe_repeat_count_is_rank_independent():
+    """The probe count depends only on the all-reduced time and the step count (a lambda-sharded step
+    holds a collective: ranks must agree on how often they run it)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(os.path.dirname(__file__), '..', 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.clock_probe_repeats(5000.0, 20) == 0
+    for total, steps in ((12.0, 20), (2.6, 20), (575.0, 5), (150.0, 5), (0.0, 3)):
+        n = bench.clock_probe_repeats(total, steps)
+        assert n >= 20 and n % 20 == 0 and n <= 20000
+    assert bench.clock_probe_repeats(12.0, 20) == bench.clock_probe_repeats(12.0, 20)
