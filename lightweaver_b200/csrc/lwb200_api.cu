@@ -1963,7 +1963,9 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
         return fail("lwb200_fs_iter: inputs have not been uploaded (lwb200_upload)");
     const int storeDepth = (flags & LWB200_STORE_DEPTH) ? 1 : 0;
     c->forceDirect = (flags & LWB200_GENERAL_KERNEL) != 0;
-    c->fetchEarly = (flags & LWB200_FETCH_EARLY) != 0 && !c->forceDirect && c->outputsPinned && c->nActiveCol < 0;
+    // (a wavelength shard or a masked stack owns only part of J / I: no wholesale early copy there)
+    c->fetchEarly = (flags & LWB200_FETCH_EARLY) != 0 && !c->forceDirect && c->outputsPinned && c->nActiveCol < 0
+                    && c->laLo == 0 && c->laHi == c->prob.Nspect;
     if (c->fetched)
     {
         // an early copy nobody collected: it must not race with this iteration's writes of J
