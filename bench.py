@@ -20,12 +20,20 @@ with Gamma-iterations/s alongside.
              its CUDA-event time, against the measured HBM copy bandwidth
   cpu_baseline  the reference's own multithreaded SIMD CPU path on this box's host cores
 
-Workloads: c2 (default; configs[1]: FAL C 1D, H + Ca II + Mg II + Na I + He I,
-~1e4 wavelengths x 10 rays; lambda-sharded with one all-reduce of the packed
-[Gamma|R] buffer per step when N > 1), c3 (configs[2]: stack of perturbed FAL C
-columns, H + Ca II, 5 rays; column-sharded, no data-path collective), c1
-(configs[0]).  `--impl reference` times the reference's CPU implementation
-(oracle/_ref, else the C port) on the same workload.
+Workloads: c3 (DEFAULT headline; configs[2]: stack of 4096 perturbed FAL C columns,
+H + Ca II, 5 rays -- the largest single-GPU configuration; column-sharded, no
+data-path collective when N > 1), c2 (configs[1]: FAL C 1D, H + Ca II + Mg II +
+Na I + He I, ~1e4 wavelengths x 10 rays; lambda-sharded with one all-reduce of the
+packed [Gamma|R] buffer per step when N > 1), c1 (configs[0]), c4 (PRD), c5 (full
+Stokes).  The default run also measures c2 and reports it in the same JSON line
+under "secondary" (so the scaling run exposes both the column-sharded and the
+lambda-sharded curve); `--workload X` runs X alone.  `--impl reference` times the
+reference's CPU implementation (oracle/_ref, else the C port) on the same workload.
+
+Every run ends with an UNTIMED parity spot check of the very state it timed
+("parity_check"): a few columns (c3) / the whole atmosphere (1D workloads) are
+stepped once more on the device and compared with the oracle started from the
+same device state.
 """
 import argparse
 import json
@@ -238,20 +246,134 @@ def time_reference(problem, steps, warmup, budget_s=120.0):
 
 
 # ------------------------------------------------------------------------ ours
-def run_ours(args, rank, world, local_rank):
+METRIC = 'depth*lambda*mu*column ray-depth points/s, fp64 Gamma iteration (formal solution + Gamma/rates + stat-eq)'
+PLUGIN = os.path.join(ROOT, 'lightweaver_b200', 'liblwb200_plugin.so')
+
+
+def workload_config(workload, desc, problem, columns):
+    """The `config` object of the JSON line: a pure function of the workload, identical in both arms."""
+    column_stack = workload in ('c3', 'c5')
+    ncol = columns if column_stack else 1
+    return {'workload': f'{workload}: {desc}', 'Nspace': problem.Nspace, 'Nspect': problem.Nspect,
+            'Nrays': problem.Nrays, 'Ncolumns': ncol,
+            'points_per_step': float(ncol) * problem.Nspace * problem.Nspect * problem.Nrays * 2,
+            'formal_solver': 'piecewise_bezier3_1d',
+            'l2': f'{L2_FLUSH_BYTES >> 20} MiB buffer written between timed steps (untimed); per-step CUDA events summed'}
+
+
+def _packed_views(ctx, problem):
+    """torch views (no copies) of the library's packed device buffers of this context."""
+    from lightweaver_b200.sharding import device_tensor
+    Ncol, L, K, M = problem.Ncol, problem.Nspect, problem.Nspace, problem.Nrays
+    nlev = sum(a.Nlevel for a in problem.atoms)
+    ngam = sum(a.Nlevel * a.Nlevel for a in problem.atoms if not a.detailedStatic)
+    v = {}
+    for name, which, shape in (('J', capi.BUF_J, (Ncol, L, K)), ('I', capi.BUF_I, (Ncol, L, M)),
+                               ('n', capi.BUF_POPS, (Ncol, nlev, K)), ('Gamma', capi.BUF_GAMMA, (Ncol, max(ngam, 1), K))):
+        ptr, nbytes = ctx.device_buffer(which)
+        v[name] = device_tensor(ptr, nbytes, ctx.device).view(*shape)
+    return v
+
+
+def parity_spot_check(ctx, problem, workload, columns, col0, step, laRange=None, ranges=None, rank=0, world=1,
+                      ncheck=4, tol=1e-9):
+    """UNTIMED check of the run that was just timed: read the device state (populations, J) of a few
+    columns, run ONE more step on the device, and compare its I, J, Gamma and populations with the
+    oracle (oracle/lw_oracle.c, bit-identical to the reference's scalar scheme) started from that same
+    state on host-made (Faddeeva) profiles.  Collective-free on column stacks; on a lambda-sharded run
+    every rank takes part (the J rows are gathered) and rank 0 compares.  Returns the dict that goes
+    into the JSON line as "parity_check"."""
+    import torch
+    from lightweaver_b200 import sharding
+    from oracle import oraclelib
+    from tests.util import gamma_err, rel_err
+    v = _packed_views(ctx, problem)
+    Ncol = problem.Ncol
+    cols = sorted(set(int(c) for c in np.linspace(0, Ncol - 1, min(ncheck, Ncol))))
+    torch.cuda.synchronize()
+    lambda_sharded = laRange is not None and world > 1
+    if lambda_sharded:
+        lo, hi = laRange
+        Jfull = sharding.gather_rows(v['J'][0, lo:hi].clone(), ranges)
+        J0 = Jfull.cpu().numpy()[None]
+    else:
+        J0 = v['J'][cols].cpu().numpy()
+    n0 = v['n'][cols].cpu().numpy()
+    step()
+    torch.cuda.synchronize()
+    ctx.check_singular()
+    out = {k: v[k][cols].cpu().numpy() for k in ('I', 'J', 'Gamma', 'n')}
+    if rank != 0 and lambda_sharded:
+        return None
+    err = {'I': 0.0, 'J': 0.0, 'Gamma': 0.0, 'n': 0.0}
+    for qi, c in enumerate(cols):
+        if workload == 'c3':
+            q = synth.config_c3(ncol=columns, col_range=(col0 + c, col0 + c + 1))
+        else:
+            q = build_workload(workload, columns, for_gpu=False)[0]
+        q.J[0] = J0[qi]
+        lev = gam = 0
+        for a in q.atoms:
+            a.n[0] = n0[qi, lev:lev + a.Nlevel]
+            lev += a.Nlevel
+        q.prefill_gamma()
+        o = oraclelib.OracleContext(q)
+        o.fs_iter(lambdaIterate=False)
+        o.stat_eq()
+        rows = slice(*laRange) if lambda_sharded else slice(None)
+        err['I'] = max(err['I'], rel_err(out['I'][qi][rows], q.I[0][rows]))
+        err['J'] = max(err['J'], rel_err(out['J'][qi][rows], q.J[0][rows]))
+        lev = 0
+        for a in q.atoms:
+            err['n'] = max(err['n'], rel_err(out['n'][qi, lev:lev + a.Nlevel], a.n[0]))
+            lev += a.Nlevel
+            if a.detailedStatic:
+                continue
+            N2 = a.Nlevel * a.Nlevel
+            G = out['Gamma'][qi, gam:gam + N2].reshape(a.Nlevel, a.Nlevel, -1)
+            err['Gamma'] = max(err['Gamma'], gamma_err(G, a.Gamma[0]))
+            gam += N2
+    ok = err['I'] <= tol and err['J'] <= tol and err['Gamma'] <= tol and err['n'] <= 10 * tol
+    return {'ok': bool(ok), 'against': 'oracle/lw_oracle.c (bit-identical to the reference scalar scheme) from the '
+            'same device state, one untimed step after the timed region',
+            'columns_checked': [col0 + c for c in cols], 'max_rel_err': err,
+            'tol': {'I': tol, 'J': tol, 'Gamma (norm-wise per depth)': tol, 'n': 10 * tol}}
+
+
+def plugin_e2e(problem, steps):
+    """e2e through the REAL drop-in boundary for a 1D atmosphere: the reference's own compiled core
+    (oracle/_ref/liblwref.so = Lightweaver's C++ `formal_sol_gamma_matrices` / `stat_eq` entry points) loads
+    liblwb200_plugin.so with ITS plugin manager and calls the scheme `mali_full_precond_B200` on HOST
+    buffers -- the same harness call the reference arm times with the AVX2FMA scheme.  The reference
+    core is only the caller here; every kernel is ours."""
+    from oracle import reflib
+    if not (reflib.available() and os.path.exists(PLUGIN)):
+        return None
+    problem.prefill_gamma()
+    r = reflib.RefContext(problem, scheme=PLUGIN, Nthreads=1)
+    try:
+        ts = r.time_fs_iter(3, steps, True)
+    finally:
+        r.close()
+    return float(np.median(ts))
+
+
+def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_baseline=True):
     import torch
     import torch.distributed as dist
     from lightweaver_b200.context import Context
     from lightweaver_b200 import sharding
 
-    torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    problem, desc = build_workload(args.workload, args.columns, rank, world)
-    column_sharded = args.workload in ('c3', 'c5')
-    stokes = args.workload == 'c5'
-    laRange = None
+    problem, desc = build_workload(workload, columns, rank, world)
+    column_sharded = workload in ('c3', 'c5')
+    stokes = workload == 'c5'
+    with_prd = workload == 'c4'
+    col0 = sharding.partition_columns(columns, world)[rank][0] if column_sharded else 0
+    laRange = ranges = None
     if world > 1 and not column_sharded:
-        laRange = sharding.partition_wavelengths(problem, world)[rank]
+        ranges = sharding.partition_wavelengths(problem, world)
+        laRange = ranges[rank]
     stream = torch.cuda.current_stream()
     ctx = Context(problem, device=local_rank, stream=stream, laRange=laRange, upload=False)
     if stokes:
@@ -260,20 +382,20 @@ def run_ours(args, rank, world, local_rank):
         ctx.upload(capi.ALL_INPUTS & ~capi.PROFILE)
         ctx.update_deps(background=False, profiles_on_device=True)
     else:
-        ctx.upload(capi.ALL_INPUTS | (capi.PRD if args.workload == 'c4' else 0))
+        ctx.upload(capi.ALL_INPUTS | (capi.PRD if with_prd else 0))
     ctx.sync()
-    with_prd = args.workload == 'c4'
     if with_prd and world > 1:
         raise SystemExit('bench.py: the PRD workload (c4) runs on one GPU')
     shard = sharding.GpuLambdaShard(ctx)
     pts_local, alg_bytes, _ = ctx.work_stats()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    lambda_sharded = world > 1 and not column_sharded
 
     def step():
         if stokes:
             capi.check(ctx.lib.lwb200_formal_sol_full_stokes(ctx._h, 1, 0, None, None))
             return
-        if world > 1 and not column_sharded:
+        if lambda_sharded:
             sharding.sharded_gamma_iteration(shard, group=None, want_dJ=False)
         else:
             # dJ and the singular-matrix flag come home with the stream (pinned memory): the
@@ -298,7 +420,7 @@ def run_ours(args, rank, world, local_rank):
     if stokes:
         step()
         per_step += ctx.work_stats()[2]
-    elif world > 1 and not column_sharded:
+    elif lambda_sharded:
         sharding.sharded_gamma_iteration(shard, group=None, want_dJ=False)
         per_step += 1  # the all-reduce
     else:
@@ -332,7 +454,7 @@ def run_ours(args, rank, world, local_rank):
     if not stokes and not with_prd:
         ctx.sync()
         ctx.check_singular()   # raises if any timed step met a singular system
-        if not (world > 1 and not column_sharded):
+        if not lambda_sharded:
             dj_last = ctx.last_dj()[0]
             if not (dj_last == dj_last and dj_last >= 0.0):
                 raise SystemExit(f'bench.py: bad dJ {dj_last}')
@@ -362,14 +484,22 @@ def run_ours(args, rank, world, local_rank):
     ms_per_step = total_ms / args.steps
     value = pts_total / (ms_per_step * 1e-3)
 
-    # ---- end to end through the public API with host buffers
-    # per step: the populations (Gamma iteration), then populations + Gamma (stat_equil).  nStar / nTotal /
-    # vBroad and the prefill crsw*C are context state: they cross once and again only after update_deps()
-    h2d = sum(a.n.nbytes for a in problem.atoms)
-    h2d += sum(a.n.nbytes + a.Gamma.nbytes for a in problem.active_atoms())  # stat_equil: n, Gamma
-    # lambda-sharded loop: every rank sends the populations, reads back its own rows of J / I and the (replicated)
-    # Gamma, rates and populations
-    h2d_lambda_sharded = sum(a.n.nbytes for a in problem.atoms)
+    # ---- untimed parity spot check of the state just timed
+    parity = None
+    if not stokes and not with_prd:
+        try:
+            parity = parity_spot_check(ctx, problem, workload, columns, col0, step, laRange=laRange, ranges=ranges,
+                                       rank=rank, world=world)
+        except Exception as e:  # reported, never fatal for the measurement itself
+            parity = {'ok': False, 'error': f'{type(e).__name__}: {e}'}
+        barrier()
+
+    # ---- end to end with HOST buffers (h2d / d2h counted from the arrays that cross)
+    # Per call the boundary sends what the reference's caller may have changed since the last call --
+    # populations, nStar / nTotal / vBroad and the prefill crsw*C (LwMiddleLayer.pyx:3198-3203 refills Gamma
+    # on EVERY call) -- and brings home everything the caller reads: J, I, Gamma, rates, populations.
+    h2d = sum(2 * a.n.nbytes + a.nStar.nbytes + a.nTotal.nbytes + a.vBroad.nbytes for a in problem.atoms)
+    h2d += sum(2 * a.Gamma.nbytes for a in problem.active_atoms())  # prefill (fs_iter) + final Gamma (stat_equil)
     d2h = problem.J.nbytes + problem.I.nbytes + sum(a.n.nbytes for a in problem.active_atoms())
     d2h += sum(a.Gamma.nbytes for a in problem.active_atoms())
     d2h += sum(t_.Rij.nbytes + t_.Rji.nbytes for a in problem.atoms for t_ in a.trans)
@@ -377,7 +507,18 @@ def run_ours(args, rank, world, local_rank):
         h2d = sum(a.n.nbytes for a in problem.atoms) + problem.J.nbytes
         d2h = problem.I.nbytes + problem.Quv.nbytes + problem.J.nbytes
     e2e = None
-    if world == 1 or column_sharded:
+    if world == 1 and not column_sharded and not with_prd:
+        # a 1D atmosphere: through the plugin the reference's own core loads (the real drop-in boundary)
+        ctx.sync()
+        sec = plugin_e2e(problem.clone(), args.steps)
+        if sec is not None:
+            e2e = {'value': pts_total / sec, 'unit': 'points/s', 'ms_per_step': sec * 1e3,
+                   'h2d_bytes_per_step': int(h2d + problem.J.nbytes), 'd2h_bytes_per_step': int(d2h),
+                   'api': ('reference core (oracle/_ref/liblwref.so: Lightweaver formal_sol_gamma_matrices + stat_eq) -> '
+                           'FsIterationFnsManager -> liblwb200_plugin.so fs_iteration_fns_provider -> b200_fs_iter / '
+                           'b200_stat_eq on host buffers; per call: H2D of n, nStar, nTotal, vBroad, crsw*C (+ J, '
+                           'background, profiles, atmosphere when their fingerprint changed), D2H of J, I, Gamma, rates, n')}
+    if e2e is None and (world == 1 or column_sharded):
         def api_step():
             if stokes:
                 ctx.single_stokes_fs(updateJ=True, upOnly=False)
@@ -399,33 +540,39 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {'value': pts_total / te.item(), 'unit': 'points/s', 'ms_per_step': te.item() * 1e3,
-               'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-               'api': ('Context.single_stokes_fs(updateJ=True, upOnly=False) on host numpy buffers' if stokes else
-                       'Context.formal_sol_gamma_matrices() + Context.stat_equil() on host numpy buffers')}
-    else:
+               'h2d_bytes_per_step': int(h2d) * (world if column_sharded else 1),
+               'd2h_bytes_per_step': int(d2h) * (world if column_sharded else 1),
+               'api': ('C-ABI (lwb200_upload / lwb200_formal_sol_full_stokes / lwb200_download) on host numpy buffers'
+                       if stokes else
+                       'C-ABI of include/lwb200.h through its ctypes mirror (Context.formal_sol_gamma_matrices + '
+                       'stat_equil): lwb200_upload(POPS|NSTAR|GAMMA) -> lwb200_fs_iter -> lwb200_download(J, I, Gamma, '
+                       'rates) -> lwb200_upload(POPS|GAMMA_FINAL) -> lwb200_stat_eq -> lwb200_download(POPS), '
+                       'host numpy buffers')}
+    elif e2e is None:
         # lambda-sharded: each rank uploads the (replicated) small inputs, reads back its J rows
-        # (the prefill crsw*C, nStar, nTotal, vBroad are context state, as in Context.formal_sol_gamma_matrices)
         problem.prefill_gamma()
-        ctx.upload(capi.ITER_INPUTS)
         for _ in range(2):
-            ctx.upload(capi.POPS)
+            ctx.upload(capi.ITER_INPUTS)
             step()
             ctx.download(capi.ITER_OUTPUTS | capi.POPS | capi.OWN_ROWS)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            ctx.upload(capi.POPS)
+            ctx.upload(capi.ITER_INPUTS)
             step()
             ctx.download(capi.ITER_OUTPUTS | capi.POPS | capi.OWN_ROWS)
         barrier()
         e2e_s = (time.perf_counter() - t0) / args.steps
         te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        up = sum(a.n.nbytes + a.nStar.nbytes + a.nTotal.nbytes + a.vBroad.nbytes for a in problem.atoms)
+        up += sum(a.Gamma.nbytes for a in problem.active_atoms())
         e2e = {'value': pts_total / te.item(), 'unit': 'points/s', 'ms_per_step': te.item() * 1e3,
-               'h2d_bytes_per_step': int(h2d_lambda_sharded * world),
+               'h2d_bytes_per_step': int(up * world),
                'd2h_bytes_per_step': int(problem.J.nbytes + problem.I.nbytes
                                          + world * (d2h - problem.J.nbytes - problem.I.nbytes)),
-               'api': 'per rank: upload(POPS) + sharded Gamma iteration + stat_eq + download of Gamma, rates, populations and its own rows of J, I'}
+               'api': 'C-ABI per rank: lwb200_upload(POPS|NSTAR|GAMMA) + sharded Gamma iteration + stat_eq + download of '
+                      'Gamma, rates, populations and its own rows of J, I'}
 
     if rank != 0:
         ctx.close()
@@ -439,8 +586,8 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic = tj.get(args.workload)
-            if args.workload == 'c3' and tj.get('c3_per_column'):
+            traffic = tj.get(workload)
+            if workload == 'c3' and tj.get('c3_per_column'):
                 traffic = tj['c3_per_column'] * problem.Ncol
         except Exception:
             traffic = None
@@ -457,20 +604,17 @@ def run_ours(args, rank, world, local_rank):
         pass
     fp64_ach = flop_pt * pts_local / (kms * 1e-3) / 1e12
     line = {
-        'metric': 'depth*lambda*mu*column ray-depth points/s, fp64 Gamma iteration (formal solution + Gamma/rates + stat-eq)',
+        'metric': METRIC,
         'value': value, 'unit': 'points/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_per_step, 'gamma_iter_per_s': 1e3 / ms_per_step,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: {desc}', 'Nspace': problem.Nspace, 'Nspect': problem.Nspect,
-                   'Nrays': problem.Nrays, 'Ncolumns': args.columns if column_sharded else 1,
-                   'points_per_step': pts_total,
-                   'formal_solver': 'piecewise_bezier3_1d',
-                   'parallelism': ('1 GPU' if world == 1 else
-                                   (f'column-sharded x{world}, no data-path collective' if column_sharded else
-                                    f'lambda-sharded x{world}, one all-reduce(sum) of packed [Gamma|R] per step')),
-                   'l2': f'{L2_FLUSH_BYTES >> 20} MiB buffer written between timed steps (untimed); per-step CUDA events summed'},
+        'config': workload_config(workload, desc, problem, columns),
+        'parallelism': ('1 GPU' if world == 1 else
+                        (f'column-sharded x{world}, no data-path collective' if column_sharded else
+                         f'lambda-sharded x{world}, one all-reduce(sum) of packed [Gamma|R] per step')),
         'e2e': e2e,
         'gpu_launches': launches,
+        'parity_check': parity,
         'roofline': {'bound': 'hbm', 'kernel': 'continuum_kernel + ray_kernel<NL=0..3> + gamma_kernel (one launch set per iteration)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                      'alg_bytes_per_launch': alg_bytes, 'kernel_ms': kms,
@@ -481,10 +625,10 @@ def run_ours(args, rank, world, local_rank):
                               'peak_source': 'tools/fp64_peak.cu on this pool (profiles/*_fp64_peak.json)'}},
         'clocks': clk,
     }
-    if world == 1:
+    if world == 1 and with_cpu_baseline:
         try:
-            ref_problem, _ = build_workload(args.workload, min(args.columns, 64), for_gpu=False)
-            cb = time_reference(ref_problem, steps=10, warmup=2, budget_s=25.0)
+            ref_problem, _ = build_workload(workload, min(columns, 64), for_gpu=False)
+            cb = time_reference(ref_problem, steps=10, warmup=2, budget_s=25.0 if workload == args.workload else 12.0)
             line['cpu_baseline'] = {'value': cb['value'], 'unit': 'points/s', 'cores': cb['cores'],
                                     'kind': cb['kind'], 'sample': cb['sample'], 'scheme': cb['scheme']}
         except Exception as e:  # the baseline must never take the bench line down
@@ -494,27 +638,48 @@ def run_ours(args, rank, world, local_rank):
     return line
 
 
-def run_reference(args, rank, world):
-    if rank != 0:
-        return None
-    problem, desc = build_workload(args.workload, min(args.columns, 64), for_gpu=False)
-    cb = time_reference(problem, steps=args.steps, warmup=args.warmup, budget_s=150.0)
-    scale = (args.columns / problem.Ncol) if args.workload == 'c3' else 1.0
+def run_ours(args, rank, world, local_rank):
+    import torch
+    torch.cuda.set_device(local_rank)
+    line = bench_workload(args, args.workload, args.columns, rank, world, local_rank)
+    if args.secondary and args.workload == 'c3':
+        # the lambda-sharded 1D workload (configs[1]) beside the column-sharded headline, same launch
+        sec = bench_workload(args, 'c2', args.columns, rank, world, local_rank)
+        if line is not None and sec is not None:
+            keep = ('value', 'unit', 'ms_per_step', 'gamma_iter_per_s', 'scaling', 'config', 'parallelism', 'e2e',
+                    'gpu_launches', 'parity_check', 'roofline', 'cpu_baseline')
+            line['secondary'] = {'c2_lambda_sharded': {k: sec[k] for k in keep if k in sec}}
+    return line
+
+
+def reference_line(args, workload, columns, world):
+    problem, desc = build_workload(workload, min(columns, 64), for_gpu=False)
+    cb = time_reference(problem, steps=args.steps, warmup=args.warmup, budget_s=150.0 if workload == args.workload else 40.0)
+    scale = (columns / problem.Ncol) if workload in ('c3', 'c5') else 1.0
     ms = cb['sec_per_step'] * 1e3 * scale
-    line = {
+    return {
         'impl': 'reference',
-        'metric': 'depth*lambda*mu*column ray-depth points/s, fp64 Gamma iteration (formal solution + Gamma/rates + stat-eq)',
+        'metric': METRIC,
         'value': cb['value'], 'unit': 'points/s', 'n_gpus': world, 'steps': cb['steps'], 'warmup': args.warmup,
         'ms_per_step': ms, 'gamma_iter_per_s': 1e3 / ms, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: {desc}', 'Nspace': problem.Nspace, 'Nspect': problem.Nspect,
-                   'Nrays': problem.Nrays, 'Ncolumns': args.columns if args.workload == 'c3' else 1,
-                   'parallelism': f'{cb["cores"]} host threads, {cb["scheme"]}'},
+        'config': workload_config(workload, desc, problem, columns),
+        'parallelism': f'{cb["cores"]} host threads, {cb["scheme"]}',
         'cpu_baseline': {'value': cb['value'], 'unit': 'points/s', 'cores': cb['cores'], 'kind': cb['kind'],
                          'sample': cb['sample'], 'scheme': cb['scheme']},
         'e2e': {'value': cb['value'], 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    line = reference_line(args, args.workload, args.columns, world)
+    if args.secondary and args.workload == 'c3':
+        sec = reference_line(args, 'c2', args.columns, world)
+        keep = ('value', 'unit', 'ms_per_step', 'gamma_iter_per_s', 'config', 'parallelism', 'cpu_baseline', 'e2e')
+        line['secondary'] = {'c2_lambda_sharded': {k: sec[k] for k in keep}}
     return line
 
 
@@ -538,8 +703,10 @@ def _main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c3', 'c4', 'c5'])
+    ap.add_argument('--workload', default='c3', choices=['c1', 'c2', 'c3', 'c4', 'c5'])
     ap.add_argument('--columns', type=int, default=None, help='columns of the c3 (4096) / c5 (1024) stacks')
+    ap.add_argument('--no-secondary', dest='secondary', action='store_false',
+                    help='default run (c3): do not also measure the lambda-sharded c2 workload')
     args = ap.parse_args()
     if args.columns is None:
         args.columns = 1024 if args.workload == 'c5' else 4096

@@ -67,9 +67,6 @@ class Context:
         if laRange is not None:
             self.set_lambda_range(*laRange)
         self.crsw = 1.0
-        self._nstar_sent = False    # nStar / nTotal / vBroad are on the device (they change with update_deps only)
-        self._c_version = 0         # bumped whenever the host may have recomputed the collisional rates
-        self._prefill_key = None    # (crsw, _c_version) of the Gamma prefill crsw*C held by the device
         if upload:
             self.upload(capi.ALL_INPUTS)
 
@@ -115,11 +112,6 @@ class Context:
             capi.check(rc)
         return bool(acc.value), dMax, dIdx
 
-    def collisions_changed(self):
-        """Tell the context that the host changed the collisional rates ``atom.C`` in place outside
-        update_deps(): the next Gamma iteration rebuilds and re-sends the prefill crsw*C."""
-        self._c_version += 1
-
     def set_active_columns(self, active=None):
         """Retire converged columns of a stack: ``active`` is a boolean array [Ncol] (None: all
         columns again).  Retired columns are skipped by the Gamma iteration, the formal solution
@@ -134,10 +126,6 @@ class Context:
 
     def upload(self, mask):
         capi.check(self.lib.lwb200_upload(self._h, mask))
-        if mask & capi.NSTAR:
-            self._nstar_sent = True
-        if mask & capi.GAMMA:
-            self._prefill_key = None   # whatever the caller sent replaces the cached crsw*C
 
     def download(self, mask, sync=True):
         capi.check(self.lib.lwb200_download(self._h, mask))
@@ -242,18 +230,12 @@ class Context:
         general = bool(extraParams and extraParams.get('generalKernel', False))
         if crsw is not None:
             self.crsw = crsw
-        # per-iteration inputs: the populations.  nStar, nTotal and vBroad change with update_deps only;
-        # the prefill crsw*C is rebuilt and sent only when crsw or the collisional rates changed
-        # (collisions_changed() / update_deps()) -- the reference recomputes C in update_deps only.
-        mask = capi.POPS
-        if not self._nstar_sent:
-            mask |= capi.NSTAR
-        key = (float(self.crsw), self._c_version)
-        if key != self._prefill_key:
-            self.problem.prefill_gamma(self.crsw)
-            mask |= capi.GAMMA
-        self.upload(mask)
-        self._prefill_key = key
+        # What the reference's caller may have changed since the last call travels on EVERY call, as in the
+        # plugin shim (lwb200_plugin.cpp sync_inputs): the populations, nStar / nTotal / vBroad, and the
+        # prefill Gamma = crsw*C, which lw.Context refills before entering C++ each time
+        # (LwMiddleLayer.pyx:3198-3203).
+        self.problem.prefill_gamma(self.crsw)
+        self.upload(capi.POPS | capi.NSTAR | capi.GAMMA)
         # one host synchronisation for the whole call: dJ comes home with the stream (DJ_ASYNC), J and I
         # start travelling as soon as the rays are done (FETCH_EARLY)
         flags = ((capi.LAMBDA_ITERATE if lambdaIterate else 0) | (capi.STORE_DEPTH if storeDepth else 0)
@@ -408,7 +390,6 @@ class Context:
         populations, background) is re-mirrored.  With profiles_on_device the
         Voigt profiles are regenerated on the GPU from aDamp/vBroad/vlosMu
         instead of being uploaded."""
-        self._c_version += 1   # temperature / ne changed: the host recomputed the collisional rates
         mask = capi.ATMOS | capi.NSTAR | capi.POPS
         if background:
             mask |= capi.BACKGR

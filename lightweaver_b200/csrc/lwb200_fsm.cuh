@@ -71,6 +71,15 @@ __device__ __forceinline__ double exp_fast(double x)
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
+// exp_fast for arguments that are not bounded below (the Boltzmann factor exp(-hc / (k lambda T)) of a
+// bound-free continuum at a short wavelength and a cool depth): the exponent arithmetic of exp_fast
+// wraps for x < -708.4, where the reference's libm exp() has long underflowed to (sub)normal nothing.
+__device__ __forceinline__ double exp_fast_underflow(double x)
+{
+    const double e = exp_fast((x < -708.0) ? -708.0 : x);
+    return (x < -708.0) ? 0.0 : e;
+}
+
 template <int NCH>
 struct GeometryR
 {

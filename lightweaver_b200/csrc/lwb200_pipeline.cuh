@@ -86,7 +86,7 @@ __global__ void continuum_kernel(const DevProblem P, const int* __restrict__ lam
         const size_t rowLK = ((size_t)col * L + la) * K + k;
         double chiC = __ldg(P.chiBg + rowLK);
         double etaC = __ldg(P.etaBg + rowLK);
-        const double expfac = exp_fast(-hc_kl / Tk);
+        const double expfac = exp_fast_underflow(-hc_kl / Tk);
         const int eBeg = P.laOff[la], eEnd = eBeg + P.laCnt[la];
         for (int e = eBeg; e < eEnd; ++e)
         {
@@ -535,7 +535,7 @@ __device__ __forceinline__ void gamma_lambda(const DevProblem& P, int la, int co
             }
         }
     }
-    const double expfac = exp_fast(-hc_kl / Tk);
+    const double expfac = exp_fast_underflow(-hc_kl / Tk);
 
     // line slots of this wavelength
     int lsTrans[NLA], lsAtom[NLA], lsI[NLA], lsJ[NLA];

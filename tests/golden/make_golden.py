@@ -54,6 +54,9 @@ CASES = {
     'tiny_k40_2col': (synth.tiny_problem, dict(ncol=2, ndepth=40, perturb=True), 2, None),
     'tiny_k100': (synth.tiny_problem, dict(ndepth=100, nrays=2), 2, None),
     'c1_bezier3': (synth.config_c1, dict(), 3, 16),
+    # configs[1] at its real size: 5 active atoms, 10 rays, ~1e4 wavelengths, up to 3 overlapping
+    # cross-atom lines -- the workload the lambda-sharded numbers are quoted on
+    'c2_bezier3': (synth.config_c2, dict(), 2, 16),
 }
 
 # angle-averaged PRD: every iteration is formal_sol_gamma_matrices, prd_redistribute(maxIter, tol),

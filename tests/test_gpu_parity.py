@@ -683,6 +683,61 @@ def test_column_stack_properties_at_scale():
     ctx.close()
 
 
+def test_short_wavelength_continuum_boltzmann_factor_underflows_to_zero():
+    """A bound-free continuum reaching down to 2 nm: exp(-hc / (k lambda T)) underflows (x < -708) at the cool
+    depths; the reference's libm exp() gives 0 there and so must the device's table-free exp."""
+    lev = [synth.Level(0.0, 2, 0), synth.Level(60000.0, 6, 0), synth.Level(100000.0, 1, 1)]
+    lines = [synth.LineSpec(1, 0, 3.0e8, 15, 5.0, 60.0)]
+    cont = [synth.ContSpec(2, 0, 6.0e-22, 12, 2.0), synth.ContSpec(2, 1, 1.2e-21, 8, 100.0)]
+    toy = synth.ModelAtom('ToyX', 12.0, 1e-4, lev, lines, cont)
+    p = synth.build_problem([toy], ncol=2, nrays=3, perturb=True)
+    assert (1.4388e7 / (p.wavelength.min() * p.temperature.min())) > 720.0
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices()
+        ctx.stat_equil()
+        oracle_iter(q)
+        assert_close(p, q)
+    ctx.close()
+
+
+def test_c3_shaped_stack_sampled_columns_match_oracle():
+    """configs[2] as bench.py runs it: a stack of >= 1024 perturbed FAL C columns (H + Ca II, 5 rays)
+    with profiles MADE ON THE DEVICE, several 512-column batches, the tiled gamma_kernel and the early
+    J / I fetch of the public API -- sampled columns against the oracle on host-made (Faddeeva)
+    profiles of the same seeded columns."""
+    ncol = 1024
+    p = synth.config_c3(ncol=ncol, with_profiles=False, alloc_phi=False)
+    ctx = Context(p, upload=False)
+    ctx.upload(capi.ALL_INPUTS & ~capi.PROFILE)
+    ctx.update_deps(background=False, profiles_on_device=True)
+    sample = [0, 1, 255, 511, 512, 513, 777, 1023]
+    qs = [synth.config_c3(ncol=ncol, col_range=(c, c + 1)) for c in sample]
+    for q, c in zip(qs, sample):
+        assert np.array_equal(q.temperature[0], p.temperature[c]) and np.array_equal(q.chiBg[0], p.chiBg[c])
+    for it in range(2):
+        upd = ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+        ctx.stat_equil()
+        dJref = 0.0
+        for q, c in zip(qs, sample):
+            (dJ, _), = oracle_iter(q, lambdaIterate=(it == 0))
+            dJref = max(dJref, dJ)
+            assert rel_err(p.I[c], q.I[0]) <= TOL and rel_err(p.J[c], q.J[0]) <= TOL, (it, c)
+            for a, b in zip(p.atoms, q.atoms):
+                assert gamma_err(a.Gamma[c], b.Gamma[0]) <= TOL, (it, c, a.name)
+                assert rel_err(a.n[c], b.n[0]) <= TOL_N, (it, c, a.name)
+                for t, u in zip(a.trans, b.trans):
+                    assert rel_err(t.Rij[c], u.Rij[0], floor=1e-30) <= TOL, (it, c, t.name)
+                    assert rel_err(t.Rji[c], u.Rji[0], floor=1e-30) <= TOL, (it, c, t.name)
+        assert upd.dJMax >= dJref * (1.0 - 1e-9)   # the stack's dJ is the max over ALL its columns
+    # populations conserved and Gamma columns sum to zero in every column of the stack
+    for a in p.atoms:
+        assert np.abs(a.Gamma.sum(axis=1)).max() <= 1e-9 * np.abs(a.Gamma).max()
+        assert rel_err(a.n.sum(axis=1), a.nTotal) <= 1e-12
+    ctx.close()
+
+
 def _overlap_problem(nlines):
     """A toy atom whose `nlines` lines all overlap (same-atom cross moments), plus a
     second atom with an overlapping line (cross-atom case)."""
