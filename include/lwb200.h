@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LWB200_ABI_VERSION 4
+#define LWB200_ABI_VERSION 5
 
 /* TransitionType, Source/LwTransition.hpp:10-14 */
 enum { LWB200_LINE = 0, LWB200_CONTINUUM = 1 };
@@ -151,6 +151,7 @@ enum {
     LWB200_STOKES  = 1u << 13, /* up: the polarised profiles of every polarised line; down: Quv */
     LWB200_OWN_ROWS = 1u << 14, /* down, with JBAR / INTENS: only the rows of the context's wavelength range
                                    (lwb200_set_lambda_range) -- what a lambda-shard owns */
+    LWB200_ZPLANE  = 1u << 15, /* down only: the ZPlaneUp / ZPlaneDown arrays registered with lwb200_set_zplane */
     LWB200_ALL_INPUTS  = 0x7fu,
     LWB200_ITER_INPUTS = LWB200_POPS | LWB200_NSTAR | LWB200_GAMMA,
     LWB200_ITER_OUTPUTS = LWB200_GAMMA | LWB200_JBAR | LWB200_INTENS | LWB200_RATES
@@ -190,6 +191,9 @@ typedef struct LwB200Context LwB200Context; /* opaque */
 const char* lwb200_last_error(void);
 int lwb200_abi_version(void);
 int lwb200_device_count(int* count);
+/* Kernels this library has launched in this process so far, over all contexts: lets a host (or a test
+ * of the plugin shim, which owns its contexts privately) prove that a call ran on the device. */
+int64_t lwb200_global_launch_count(void);
 
 /* Replaces Context::initialise_threads / ThreadData::initialise
  * (Source/ThreadStorage.cpp:480-536): takes the problem description, keeps the
@@ -216,6 +220,14 @@ int lwb200_set_lambda_range(LwB200Context* ctx, int32_t laStart, int32_t laEnd);
  * active: [Ncol] bytes, or NULL for "all columns" (the default).  PRD, full-Stokes and
  * Newton-Raphson calls are refused while a mask is set. */
 int lwb200_set_active_columns(LwB200Context* ctx, const uint8_t* active);
+
+/* The ZPlaneDecomposition extra parameters of intensity_core_opt
+ * (Source/SimdFullIterationTemplates.hpp:254-281, :351-360): when registered, every formal solution
+ * (lwb200_fs_iter, lwb200_formal_sol) also records I(1) of each up-going ray into zPlaneUp(la, mu) and
+ * I(Nz - 2) of each down-going ray into zPlaneDown(la, mu).  Host arrays [Ncol][Nspect][Nrays], either
+ * may be NULL; both NULL switches the recording off again.  They come home with
+ * lwb200_download(LWB200_ZPLANE). */
+int lwb200_set_zplane(LwB200Context* ctx, double* zPlaneUp, double* zPlaneDown);
 
 /* Host -> device / device -> host copies of the groups in `mask`, using the
  * host pointers registered at create time.  Asynchronous on the context's
@@ -295,6 +307,17 @@ int lwb200_last_dj(LwB200Context* ctx, double* dJMax, int64_t* dJMaxIdx);
  * lwb200_fs_iter, or an LWB200_GAMMA_FINAL upload). */
 int lwb200_time_dep_update(LwB200Context* ctx, int32_t atom, const double* nOld, double dt, int32_t kStart,
                            int32_t kEnd, int32_t* nSingular);
+
+/* stat_eq_impl / time_dependent_update_impl (Source/UpdatePopulations.cpp:7-47, :120-151) for an atom
+ * that belongs to no device context: FsIterationFns::stat_eq and ::time_dep_update receive only an
+ * Atom*, and a caller may update populations before any formal solution has run on its Context (e.g.
+ * after the escape-probability initial solution).  Self-contained: host arrays in, host populations
+ * out, synchronous.  Gamma [Ncol][Nlevel][Nlevel][Nspace] finalised, n [Ncol][Nlevel][Nspace] in/out,
+ * nTotal [Ncol][Nspace]; nOld [Ncol][Nlevel][Nspace] or NULL (statistical equilibrium), dt used with
+ * nOld.  Depths [kStart, kEnd) (both < 0: all). */
+int lwb200_population_solve(int device, int32_t Ncol, int32_t Nlevel, int32_t Nspace, const double* Gamma,
+                            double* n, const double* nTotal, const double* nOld, double dt, int32_t kStart,
+                            int32_t kEnd, int32_t* nSingular);
 
 /* Inputs of lwb200_nr_post_update that are not part of the problem. */
 typedef struct LwB200NrUpdate {

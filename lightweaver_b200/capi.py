@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 LINE, CONTINUUM = 0, 1
 BC_UNINITIALISED, BC_ZERO, BC_THERMALISED, BC_PERIODIC, BC_CALLABLE = range(5)
@@ -19,7 +19,7 @@ FS_NAMES = {'piecewise_linear_1d': FS_LINEAR, 'piecewise_besser_1d': FS_BESSER,
             'piecewise_bezier3_1d': FS_BEZIER3}
 
 (ATMOS, BACKGR, POPS, NSTAR, GAMMA, JBAR, PROFILE, INTENS, RATES, DEPTH, ADAMP,
- GAMMA_FINAL, PRD, STOKES, OWN_ROWS) = (1 << i for i in range(15))
+ GAMMA_FINAL, PRD, STOKES, OWN_ROWS, ZPLANE) = (1 << i for i in range(16))
 ALL_INPUTS = 0x7f
 ITER_INPUTS = POPS | NSTAR | GAMMA
 ITER_OUTPUTS = GAMMA | JBAR | INTENS | RATES
@@ -172,13 +172,17 @@ def load():
     lib.lwb200_last_dj.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.lwb200_time_dep_update.argtypes = [vp, C.c_int32, _dp, C.c_double, C.c_int32, C.c_int32,
                                            C.POINTER(C.c_int32)]
+    lib.lwb200_set_zplane.argtypes = [vp, _dp, _dp]
+    lib.lwb200_population_solve.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, C.c_double,
+                                            C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    lib.lwb200_global_launch_count.restype = C.c_int64
     lib.lwb200_kernel_time.argtypes = [vp, C.POINTER(C.c_double)]
     lib.lwb200_device_buffer.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.lwb200_work_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.POINTER(C.c_int64)]
     for name in ('device_count', 'create', 'destroy', 'set_stream', 'set_lambda_range', 'upload',
                  'download', 'sync', 'compute_profiles', 'fs_iter', 'finalise', 'dj_max',
-                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes', 'nr_post_update', 'stat_eq_async', 'last_singular', 'last_dj'):
+                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes', 'nr_post_update', 'stat_eq_async', 'last_singular', 'last_dj', 'set_zplane', 'population_solve'):
         getattr(lib, 'lwb200_' + name).restype = C.c_int
     if lib.lwb200_abi_version() != ABI_VERSION:
         raise LwB200Error('liblwb200.so ABI version mismatch; rebuild')
@@ -200,4 +204,5 @@ EXPORTED_SYMBOLS = [
     'lwb200_device_buffer', 'lwb200_work_stats', 'lwb200_kernel_time', 'lwb200_redistribute_prd',
     'lwb200_time_dep_update', 'lwb200_formal_sol_full_stokes',
     'lwb200_nr_post_update', 'lwb200_stat_eq_async', 'lwb200_last_singular', 'lwb200_last_dj',
+    'lwb200_set_zplane', 'lwb200_population_solve', 'lwb200_global_launch_count',
 ]

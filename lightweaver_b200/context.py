@@ -228,6 +228,7 @@ class Context:
         True."""
         storeDepth = bool(extraParams and extraParams.get('storeDepthData', False))
         general = bool(extraParams and extraParams.get('generalKernel', False))
+        zplane = self._bind_zplane(extraParams)
         if crsw is not None:
             self.crsw = crsw
         # What the reference's caller may have changed since the last call travels on EVERY call, as in the
@@ -241,17 +242,36 @@ class Context:
         flags = ((capi.LAMBDA_ITERATE if lambdaIterate else 0) | (capi.STORE_DEPTH if storeDepth else 0)
                  | (capi.GENERAL_KERNEL if general else 0) | capi.FETCH_EARLY | capi.DJ_ASYNC)
         capi.check(self.lib.lwb200_fs_iter(self._h, flags, None, None))
-        self.download(capi.ITER_OUTPUTS | (capi.DEPTH if storeDepth else 0))
+        self.download(capi.ITER_OUTPUTS | (capi.DEPTH if storeDepth else 0) | (capi.ZPLANE if zplane else 0))
         dJ, idx = C.c_double(), C.c_int64()
         capi.check(self.lib.lwb200_last_dj(self._h, C.byref(dJ), C.byref(idx)))
         return IterationUpdate(updatedJ=True, dJMax=dJ.value, dJMaxIdx=idx.value % self.problem.Nspect,
                                crsw=self.crsw)
 
+    def _bind_zplane(self, extraParams):
+        """The ZPlaneDecomposition extra parameters (SimdFullIterationTemplates.hpp:254-281):
+        extraParams = {'ZPlaneDecomposition': True, 'ZPlaneUp': array [Ncol, Nspect, Nrays] and / or
+        'ZPlaneDown': ...}; the arrays receive I(1) of the up-going / I(Nz - 2) of the down-going rays."""
+        up = down = None
+        if extraParams and extraParams.get('ZPlaneDecomposition', False):
+            up, down = extraParams.get('ZPlaneUp'), extraParams.get('ZPlaneDown')
+            shape = (self.problem.Ncol, self.problem.Nspect, self.problem.Nrays)
+            for a in (up, down):
+                if a is not None and (a.shape != shape or a.dtype != np.float64 or not a.flags.c_contiguous):
+                    raise ValueError(f'ZPlaneUp / ZPlaneDown must be C-contiguous float64 arrays of shape {shape}')
+        on = up is not None or down is not None
+        if on or getattr(self, '_zplane', False):
+            capi.check(self.lib.lwb200_set_zplane(self._h, capi.dptr(up), capi.dptr(down)))
+        self._zplane = on
+        self._zplane_keep = (up, down)
+        return on
+
     def formal_sol(self, upOnly=True, extraParams=None):
         """lw.Context.formal_sol: intensity only (LwMiddleLayer.pyx:3212-3241)."""
+        zplane = self._bind_zplane(extraParams)
         self.upload(capi.POPS | capi.NSTAR | capi.JBAR)
         capi.check(self.lib.lwb200_formal_sol(self._h, int(upOnly)))
-        self.download(capi.INTENS)
+        self.download(capi.INTENS | (capi.ZPLANE if zplane else 0))
         return IterationUpdate()
 
     def single_stokes_fs(self, recompute=False, updateJ=False, upOnly=True, extraParams=None):

@@ -38,27 +38,22 @@ def build_cuda(force=False, verbose=False):
 
 
 def build_plugin(force=False):
-    """The C++ shim that exports fs_iteration_fns_provider / fs_provider.  Like the
-    reference's own SIMD plugins (setup.py:255-258) it is compiled against the
-    reference's headers and linked with the reference core, so it can only be
-    (re)built where /root/reference exists; elsewhere the prebuilt .so is used."""
+    """The C++ shim that exports fs_iteration_fns_provider / fs_provider.  It is compiled against the
+    reference's HEADERS (the provider structs, Context& and ExtraParams cross that boundary as C++
+    types), so it can only be (re)built where a Lightweaver source tree exists (LW_REFERENCE_SRC);
+    elsewhere the prebuilt .so is used.  It links NO reference object code -- only liblwb200.so."""
     out = os.path.join(PKG, 'liblwb200_plugin.so')
     src = os.path.join(HERE, 'lwb200_plugin.cpp')
     if not os.path.exists(src):
         return None
     if not os.path.isdir(REF_SRC):
         return out if os.path.exists(out) else None
-    refdir = os.path.join(ROOT, 'oracle', '_ref')
-    core = os.path.join(refdir, 'lwcore.o')
-    if not os.path.exists(core) or not os.path.exists(os.path.join(refdir, 'libenkiTS.so')):
-        subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle'), '-j4', 'ref'], stdout=subprocess.DEVNULL)
-    deps = [src, os.path.join(ROOT, 'include', 'lwb200.h'), core]
+    deps = [src, os.path.join(ROOT, 'include', 'lwb200.h')]
     if not force and not _stale(out, deps):
         return out
-    cmd = ['g++', '-std=c++17', '-O2', '-fPIC', '-shared', '-Wno-sign-compare', '-I', REF_SRC,
-           '-I', os.path.join(ROOT, 'include'), '-o', out, src, core,
-           '-L', PKG, '-llwb200', '-L', refdir, '-lenkiTS', '-ldl', '-lpthread',
-           '-Wl,-rpath,$ORIGIN', '-Wl,-rpath,$ORIGIN/..', '-Wl,-rpath,$ORIGIN/../oracle/_ref']
+    cmd = ['g++', '-std=c++17', '-O2', '-fPIC', '-shared', '-Wno-sign-compare', '-Wl,--no-undefined',
+           '-I', REF_SRC, '-I', os.path.join(ROOT, 'include'), '-o', out, src,
+           '-L', PKG, '-llwb200', '-lpthread', '-Wl,-rpath,$ORIGIN']
     print(' '.join(cmd), flush=True)
     subprocess.check_call(cmd)
     return out

@@ -10,6 +10,7 @@
 #include "lwb200_ng.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,6 +25,26 @@ using namespace lwb200;
 namespace
 {
 thread_local std::string g_err;
+// kernels launched by this library in this process, over all contexts (lwb200_global_launch_count)
+std::atomic<long long> g_totalLaunches{0};
+
+// per-call launch counter of a context that also feeds the process-wide count
+struct LaunchCounter
+{
+    int64_t v = 0;
+    LaunchCounter& operator+=(int64_t n)
+    {
+        v += n;
+        g_totalLaunches += n;
+        return *this;
+    }
+    LaunchCounter& operator=(int64_t n)
+    {
+        v = n;
+        return *this;
+    }
+    operator int64_t() const { return v; }
+};
 
 int fail(const std::string& msg)
 {
@@ -215,7 +236,7 @@ struct LwB200Context
     int laLo = 0, laHi = 0;
     int NCH = 0;
     size_t smemBytes = 0;
-    int64_t lastLaunches = 0;
+    LaunchCounter lastLaunches;
     bool nstarUploaded = false;
 
     DevProblem P{};
@@ -245,6 +266,9 @@ struct LwB200Context
     bool djEarly = false, djDone = false; // dJ reduced on a side stream while Gamma is accumulated
     DevBuf<DevTrans> dTrans;
     DevBuf<DevEntry> dEntries;
+    // ZPlaneDecomposition (lwb200_set_zplane)
+    DevBuf<double> zUp, zDown;
+    double *zUpHost = nullptr, *zDownHost = nullptr;
     std::vector<DevLine> devLines;
     DevBuf<DevLine> dLines;
 };
@@ -1188,6 +1212,8 @@ extern "C"
 const char* lwb200_last_error(void) { return g_err.c_str(); }
 int lwb200_abi_version(void) { return LWB200_ABI_VERSION; }
 
+int64_t lwb200_global_launch_count(void) { return g_totalLaunches.load(); }
+
 int lwb200_device_count(int* count)
 {
     CU(cudaGetDeviceCount(count));
@@ -1350,6 +1376,8 @@ int lwb200_destroy(LwB200Context* c)
     c->dTrans.release();
     c->dEntries.release();
     c->dLines.release();
+    c->zUp.release();
+    c->zDown.release();
     delete c;
     return 0;
 }
@@ -1366,6 +1394,23 @@ int lwb200_set_lambda_range(LwB200Context* c, int32_t laStart, int32_t laEnd)
         return fail("lwb200_set_lambda_range: bad range");
     c->laLo = laStart;
     c->laHi = laEnd;
+    return 0;
+}
+
+int lwb200_set_zplane(LwB200Context* c, double* zPlaneUp, double* zPlaneDown)
+{
+    CU(cudaSetDevice(c->device));
+    const size_t count = (size_t)c->prob.Ncol * c->prob.Nspect * c->prob.Nrays;
+    // kernels in flight may still write through the previous pointers
+    CU(cudaStreamSynchronize(c->stream));
+    if (zPlaneUp && !c->zUp.p && c->zUp.alloc(count))
+        return 1;
+    if (zPlaneDown && !c->zDown.p && c->zDown.alloc(count))
+        return 1;
+    c->zUpHost = zPlaneUp;
+    c->zDownHost = zPlaneDown;
+    c->P.zPlaneUp = zPlaneUp ? c->zUp.p : nullptr;
+    c->P.zPlaneDown = zPlaneDown ? c->zDown.p : nullptr;
     return 0;
 }
 
@@ -1833,6 +1878,13 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
             }
         }
     }
+    if (mask & LWB200_ZPLANE)
+    {
+        if (c->zUpHost)
+            CU(cudaMemcpyAsync(c->zUpHost, c->zUp.p, ncol * L * M * D, D2H, s));
+        if (c->zDownHost)
+            CU(cudaMemcpyAsync(c->zDownHost, c->zDown.p, ncol * L * M * D, D2H, s));
+    }
     if ((mask & LWB200_DEPTH) && c->depthChi.p)
     {
         const size_t nd = ncol * L * M * 2 * K * D;
@@ -1864,9 +1916,11 @@ int lwb200_compute_profiles(LwB200Context* c)
     if (c->devLines.empty())
         return 0;
     c->lastLaunches = 0;
+    int64_t nLaunched = 0;
     int rc = launch_profiles(c->P, c->dLines.p, (int)c->devLines.size(), c->devLines.data(), c->transWave.p,
                              c->wlambdaTab.p, c->aDamp.p, c->vBroad.p, c->vlosMu.p, c->phi.p, c->wphi.p,
-                             c->stream, &c->lastLaunches);
+                             c->stream, &nLaunched);
+    c->lastLaunches += nLaunched;
     if (rc)
         return fail(std::string("lwb200_compute_profiles: ") + cudaGetErrorString((cudaError_t)rc));
     return check_phi_symmetry(c);
@@ -2102,6 +2156,90 @@ int lwb200_stat_eq(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd,
 int lwb200_stat_eq_async(LwB200Context* c, int32_t atom, int32_t kStart, int32_t kEnd)
 {
     return population_update(c, atom, kStart, kEnd, nullptr, nullptr, 0.0, "lwb200_stat_eq_async", true);
+}
+
+int lwb200_population_solve(int device, int32_t Ncol, int32_t Nlevel, int32_t Nspace, const double* Gamma,
+                            double* n, const double* nTotal, const double* nOld, double dt, int32_t kStart,
+                            int32_t kEnd, int32_t* nSingular)
+{
+    if (nSingular)
+        *nSingular = 0;
+    if (!Gamma || !n || (!nTotal && !nOld) || Ncol < 1 || Nlevel < 1 || Nlevel > 32 || Nspace < 1)
+        return fail("lwb200_population_solve: bad arguments");
+    if (kStart < 0 && kEnd < 0)
+    {
+        kStart = 0;
+        kEnd = Nspace;
+    }
+    if (kStart < 0 || kEnd > Nspace || kStart >= kEnd)
+        return fail("lwb200_population_solve: bad depth range");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev < 1)
+        return fail("lwb200_population_solve: no CUDA device (this back end has no CPU fallback)");
+    if (device < 0 || device >= ndev)
+        return fail("lwb200_population_solve: device index out of range");
+    CU(cudaSetDevice(device));
+    const size_t nk = (size_t)Ncol * Nlevel * Nspace, n2k = nk * Nlevel, D = sizeof(double);
+    DevBuf<double> dG, dN, dTot, dOld;
+    DevBuf<int> dMeta;
+    int rc = 1;
+    do
+    {
+        // one atom: Nlevel, level offset 0, Gamma offset 0, not detailed; then the singular counter
+        const std::vector<int> meta = {Nlevel, 0, 0, 0, 0};
+        if (dG.alloc(n2k) || dN.alloc(nk) || dTot.alloc((size_t)Ncol * Nspace) || (nOld && dOld.alloc(nk))
+            || dMeta.upload(meta))
+            break;
+        if (cudaMemcpy(dG.p, Gamma, n2k * D, cudaMemcpyHostToDevice) != cudaSuccess
+            || cudaMemcpy(dN.p, n, nk * D, cudaMemcpyHostToDevice) != cudaSuccess
+            || (nTotal && cudaMemcpy(dTot.p, nTotal, (size_t)Ncol * Nspace * D, cudaMemcpyHostToDevice) != cudaSuccess)
+            || (nOld && cudaMemcpy(dOld.p, nOld, nk * D, cudaMemcpyHostToDevice) != cudaSuccess))
+        {
+            fail("lwb200_population_solve: host to device copy failed");
+            break;
+        }
+        DevProblem P{};
+        P.Ncol = Ncol;
+        P.K = Nspace;
+        P.Natom = 1;
+        P.NlevTot = Nlevel;
+        P.GammaTot = Nlevel * Nlevel;
+        P.atomNlevel = dMeta.p;
+        P.atomLevOff = dMeta.p + 1;
+        P.atomGammaOff = dMeta.p + 2;
+        P.atomDetailed = dMeta.p + 3;
+        int* dSing = dMeta.p + 4;
+        const size_t total = (size_t)Ncol * (kEnd - kStart);
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((total + 63) / 64, 148 * 32));
+        if (Nlevel <= 8)
+            stat_eq_kernel<8><<<grid, 64>>>(P, 0, kStart, kEnd, dG.p, dN.p, dTot.p, dSing, nOld ? dOld.p : nullptr, dt);
+        else if (Nlevel <= 16)
+            stat_eq_kernel<16><<<grid, 64>>>(P, 0, kStart, kEnd, dG.p, dN.p, dTot.p, dSing, nOld ? dOld.p : nullptr, dt);
+        else
+            stat_eq_kernel<32><<<grid, 64>>>(P, 0, kStart, kEnd, dG.p, dN.p, dTot.p, dSing, nOld ? dOld.p : nullptr, dt);
+        g_totalLaunches += 1;
+        int ns = 0;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess)
+            e = cudaMemcpy(&ns, dSing, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(n, dN.p, nk * D, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess)
+        {
+            fail(std::string("lwb200_population_solve: ") + cudaGetErrorString(e));
+            break;
+        }
+        if (nSingular)
+            *nSingular = ns;
+        rc = ns > 0 ? fail("Singular Matrix") : 0;
+    } while (false);
+    dG.release();
+    dN.release();
+    dTot.release();
+    dOld.release();
+    dMeta.release();
+    return rc;
 }
 
 int lwb200_time_dep_update(LwB200Context* c, int32_t atom, const double* nOld, double dt, int32_t kStart,

@@ -128,7 +128,30 @@ struct DevProblem
     const double* pol;        // polarised profile pool
     double* Quv;              // [Ncol][3][L][M]
     double* Jdag;             // [Ncol][L][K] copy of J taken before a J-updating Stokes pass
+    // ZPlaneDecomposition (lwb200_set_zplane): [Ncol][L][M] each, nullptr: not recorded
+    double *zPlaneUp, *zPlaneDown;
 };
+
+// ZPlaneDecomposition of intensity_core_opt (SimdFullIterationTemplates.hpp:351-360): I(1) of an up-going
+// ray into zPlaneUp(la, mu), I(Nz - 2) of a down-going one into zPlaneDown(la, mu).  laneGlobal is the
+// position of this lane along depth in units of NCH points; ray = (col * L + la) * M + mu.
+template <int NCH>
+__device__ __forceinline__ void store_zplane(const DevProblem& P, int laneGlobal, const double (&I)[NCH], int dir,
+                                             size_t ray)
+{
+    double* dst = dir == 1 ? P.zPlaneUp : P.zPlaneDown;
+    if (!dst)
+        return;
+    const int k = dir == 1 ? 1 : P.K - 2;
+    if (laneGlobal == k / NCH)
+    {
+        double v = I[0];
+#pragma unroll
+        for (int j = 1; j < NCH; ++j)
+            v = (k % NCH == j) ? I[j] : v;
+        dst[ray] = v;
+    }
+}
 
 // q-th column of the launch: the q-th active column when a mask is set
 __device__ __forceinline__ int column_of(const DevProblem& P, int q)
@@ -383,6 +406,7 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
 
                 if (lane == 0)
                     P.I[((size_t)col * L + la) * M + mu] = I[0]; // spect.I(la, mu, 0) = I(0)
+                store_zplane<NCH>(P, lane, I, dir, ((size_t)col * L + la) * M + mu);
 
                 if (MODE != MODE_ITER)
                     continue;

@@ -389,6 +389,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
 
                 if (lane == 0)
                     P.I[((size_t)col * L + la) * M + mu] = I[0];
+                store_zplane<NCH>(P, lane, I, dir, ((size_t)col * L + la) * M + mu);
 #pragma unroll
                 for (int j = 0; j < NCH; ++j)
                 {

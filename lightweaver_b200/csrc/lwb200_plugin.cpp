@@ -6,35 +6,51 @@
 //   extern "C" FsIterationFns fs_iteration_fns_provider();   (Source/FormalInterface.cpp:62-81)
 //   extern "C" FormalSolver   fs_provider();                 (Source/FormalInterface.cpp:9-28)
 //
-// and implements `fs_iter`, `simple_fs`, `stat_eq` and the global-scratch hooks
-// of FsIterationFns (Source/LwFormalInterface.hpp:110-134) by marshalling the
-// reference's Context into the flat LwB200Problem of include/lwb200.h and
-// calling the C-ABI of liblwb200.so.  Everything below this file is plain C.
+// and implements EVERY function slot of FsIterationFns (Source/LwFormalInterface.hpp:110-134) --
+// fs_iter, simple_fs, full_stokes_fs, redistribute_prd, stat_eq, time_dep_update, nr_post_update and
+// the global-scratch hooks -- by marshalling the reference's Context into the flat LwB200Problem of
+// include/lwb200.h and calling the C-ABI of liblwb200.so.  Everything below this file is plain C.
 //
-// Like the reference's own SIMD plugins (setup.py:255-258) this translation unit
-// is COMPILED AGAINST THE REFERENCE HEADERS and linked with the reference core
-// (for the slots this back end does not replace: full Stokes, PRD
-// redistribution, time-dependent and charge-conservation updates keep the
-// core's `*_impl` functions, exactly as SimdImpl_AVX2FMA.cpp:652-656 does).  It
-// can therefore only be (re)built where the reference sources exist; no
-// reference source is copied into this repository.
+// This translation unit is compiled against the reference HEADERS (the provider structs, Context&
+// and ExtraParams cross the boundary as C++ types) but links NO reference object code: there is no
+// CPU fallback behind any slot.  A set-up the device path does not handle raises std::runtime_error
+// with the reason (Lightweaver turns it into a Python exception, LwMiddleLayer.pyx:336-350); the
+// formal solver behind fs_provider is this file's own host code.
 //
 // Use from Python:
 //   lw.LwCompiled.FsIterationSchemes.load_fns_from_path('liblwb200_plugin.so')
 //   ctx = lw.Context(..., fsIterScheme='mali_full_precond_B200', Nthreads=1)
+// Context holds the reference's thread pool by value, so its headers bring in the inline virtual
+// interface of the vendored task scheduler (TaskScheduler.h), whose vtables name three out-of-line
+// members.  This file never schedules a task: the members are declared hidden and given local bodies
+// below, so the plugin carries no undefined reference into (and no code from) the reference's libraries.
+#define ENKITS_API __attribute__((visibility("hidden")))
 #include "Lightweaver.hpp"
 #include "lwb200.h"
 
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
+
+namespace enki
+{
+void TaskScheduler::TaskComplete(ICompletable*, bool, uint32_t) { std::abort(); }
+void TaskScheduler::AddTaskSetToPipeInt(ITaskSet*, uint32_t) { std::abort(); }
+void TaskScheduler::AddPinnedTaskInt(IPinnedTask*) { std::abort(); }
+} // namespace enki
 
 namespace
 {
@@ -50,6 +66,7 @@ struct Mirror
     std::vector<std::pair<const Transition*, size_t>> polSrc;   // (line, index into polStage)
     bool uploadedStatic = false;
     bool hasDepth = false;
+    bool zplane = false;
     uint64_t fpProfiles = 0, fpBackground = 0, fpAtmos = 0, fpJ = 0;
     int solver = -1;
 };
@@ -70,24 +87,175 @@ void check(int rc, const char* what)
         raise(what);
 }
 
-// Sampled FNV-1a fingerprint of a host array: Python mutates phi / background /
-// atmosphere in place between calls without telling the plugin;
-// any update_deps() changes essentially every element, so sampling detects it.
+int device_index()
+{
+    if (const char* env = std::getenv("LWB200_DEVICE"))
+        return std::atoi(env);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Fingerprints.  Python mutates phi / background / atmosphere / J in place between calls without
+// telling the plugin, and a change may be LOCAL (a response-function run perturbs
+// one depth), so every element counts: h = sum_i mix(word_i + (i + 1) * C) mod 2^64 -- position
+// dependent, order independent, hence four independent lanes per thread and several threads for
+// the large arrays (the background of a 1e4-wavelength spectrum is 20 MB: ~0.3 ms).
+inline uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 32;
+    x *= 0xd6e8feb86659fd93ULL;
+    x ^= x >> 29;
+    return x;
+}
+
+uint64_t hash_range(const double* p, size_t i0, size_t i1, size_t stride)
+{
+    constexpr uint64_t C = 0x9e3779b97f4a7c15ULL;
+    uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+    size_t i = i0;
+    if (stride == 1)
+    {
+        for (; i + 4 <= i1; i += 4)
+        {
+            uint64_t w[4];
+            std::memcpy(w, p + i, 32);
+            h0 += mix64(w[0] + (i + 1) * C);
+            h1 += mix64(w[1] + (i + 2) * C);
+            h2 += mix64(w[2] + (i + 3) * C);
+            h3 += mix64(w[3] + (i + 4) * C);
+        }
+    }
+    for (; i < i1; i += stride)
+    {
+        uint64_t w;
+        std::memcpy(&w, p + i, 8);
+        h0 += mix64(w + (i + 1) * C);
+    }
+    return h0 + h1 + h2 + h3;
+}
+
+// A few persistent helper threads for the large arrays (std::thread start-up would cost as much
+// as the hashing itself).
+class HashPool
+{
+public:
+    static HashPool& get()
+    {
+        static HashPool pool;
+        return pool;
+    }
+    uint64_t run(const double* p, size_t n)
+    {
+        const size_t chunk = (size_t)1 << 17; // 1 MiB of doubles
+        const size_t nchunk = (n + chunk - 1) / chunk;
+        if (nchunk < 2 || workers.empty())
+            return hash_range(p, 0, n, 1);
+        std::lock_guard<std::mutex> serial(runMutex);
+        {
+            std::lock_guard<std::mutex> lock(m);
+            data = p;
+            len = n;
+            next.store(0);
+            total = nchunk;
+            chunkLen = chunk;
+            acc.store(0);
+            pending = (int)workers.size();
+            ++generation;
+        }
+        cv.notify_all();
+        work();
+        std::unique_lock<std::mutex> lock(m);
+        done.wait(lock, [&] { return pending == 0; });
+        return acc.load();
+    }
+    ~HashPool()
+    {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            quit = true;
+            ++generation;
+        }
+        cv.notify_all();
+        for (auto& t : workers)
+            t.join();
+    }
+
+private:
+    HashPool()
+    {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const unsigned nw = hw > 2 ? std::min(7u, hw - 1) : 0;
+        for (unsigned i = 0; i < nw; ++i)
+            workers.emplace_back([this] { loop(); });
+    }
+    void work()
+    {
+        uint64_t h = 0;
+        for (;;)
+        {
+            const size_t q = next.fetch_add(1);
+            if (q >= total)
+                break;
+            h += hash_range(data, q * chunkLen, std::min(len, (q + 1) * chunkLen), 1);
+        }
+        acc.fetch_add(h);
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;)
+        {
+            {
+                std::unique_lock<std::mutex> lock(m);
+                cv.wait(lock, [&] { return generation != seen; });
+                seen = generation;
+                if (quit)
+                    return;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> lock(m);
+                --pending;
+            }
+            done.notify_one();
+        }
+    }
+    std::vector<std::thread> workers;
+    std::mutex m, runMutex;
+    std::condition_variable cv, done;
+    const double* data = nullptr;
+    size_t len = 0, total = 0, chunkLen = 0;
+    std::atomic<size_t> next{0};
+    std::atomic<uint64_t> acc{0};
+    int pending = 0;
+    uint64_t generation = 0;
+    bool quit = false;
+};
+
+// every element of the array
 uint64_t fingerprint(uint64_t h, const double* p, size_t n)
 {
     if (!p || n == 0)
         return h;
-    const size_t stride = n > 8192 ? n / 4096 : 1;
-    auto mix = [&](double v)
-    {
-        uint64_t b;
-        std::memcpy(&b, &v, 8);
-        h = (h ^ b) * 1099511628211ULL;
-    };
-    for (size_t i = 0; i < n; i += stride)
-        mix(p[i]);
-    mix(p[n - 1]);
-    return h;
+    return mix64(h + 0x2545f4914f6cdd1dULL) + HashPool::get().run(p, n);
+}
+
+// a sample of a large array whose every element is ALSO covered by a small, fully hashed companion
+// (phi: its normalisation wphi(k) = 1 / sum phi(la, mu, dir, k) w, recomputed by the reference whenever
+// phi is, FormalScalar.cpp:106-134).  The stride is odd and not a multiple of any depth count in use,
+// so the sample walks through every depth.  LWB200_FINGERPRINT=full hashes these arrays entirely too.
+uint64_t fingerprint_sampled(uint64_t h, const double* p, size_t n)
+{
+    static const bool full = [] {
+        const char* e = std::getenv("LWB200_FINGERPRINT");
+        return e && std::string(e) == "full";
+    }();
+    if (!p || n == 0)
+        return h;
+    if (full || n <= 65536)
+        return fingerprint(h, p, n);
+    size_t stride = (n / 16384) | 1;
+    return mix64(h + 0x2545f4914f6cdd1dULL) + hash_range(p, 0, n, stride) + hash_range(p, n - 1, n, 1);
 }
 
 int solver_from_name(const char* name)
@@ -248,13 +416,11 @@ void build_mirror(Context& ctx, Mirror& m)
     }
     p.atoms = m.atoms.data();
 
-    int device = 0;
-    if (const char* env = std::getenv("LWB200_DEVICE"))
-        device = std::atoi(env);
-    check(lwb200_create(&p, device, &m.dev), "lwb200_create");
+    check(lwb200_create(&p, device_index(), &m.dev), "lwb200_create");
     for (size_t i = 0; i < m.hostAtoms.size(); ++i)
         g_atoms[m.hostAtoms[i]] = {&m, (int)i};
     m.uploadedStatic = false;
+    m.zplane = false;
 }
 
 Mirror& mirror_for(Context& ctx)
@@ -280,9 +446,14 @@ Mirror& mirror_for(Context& ctx)
     return ref;
 }
 
+uint64_t fingerprint_J(const Mirror& m)
+{
+    return fingerprint(1469598103934665603ULL, m.prob.J, (size_t)m.prob.Nspect * m.prob.Nspace);
+}
+
 // Bring the device mirror up to date with whatever the host changed since the
 // last call.  Small per-iteration arrays always travel; the large ones only when
-// their fingerprint changed.
+// their fingerprint (over EVERY element) changed.
 void sync_inputs(Context& ctx, Mirror& m, bool withGamma)
 {
     const LwB200Problem& p = m.prob;
@@ -291,6 +462,8 @@ void sync_inputs(Context& ctx, Mirror& m, bool withGamma)
     uint64_t fa = 1469598103934665603ULL, fb = fa, fpf = fa;
     fa = fingerprint(fa, p.height, K);
     fa = fingerprint(fa, p.temperature, K);
+    fa = fingerprint(fa, p.vlosMu, p.vlosMu ? M * K : 0);
+    fa = fingerprint(fa, p.ne, p.ne ? K : 0);
     fa = fingerprint(fa, p.lowerBcData, p.NlowerBcMu ? L * p.NlowerBcMu : 0);
     fa = fingerprint(fa, p.upperBcData, p.NupperBcMu ? L * p.NupperBcMu : 0);
     fb = fingerprint(fb, p.chiBg, L * K);
@@ -303,17 +476,20 @@ void sync_inputs(Context& ctx, Mirror& m, bool withGamma)
             if (t.type != LWB200_LINE)
                 continue;
             const size_t Nl = t.Nred - t.Nblue;
-            fpf = fingerprint(fpf, t.phi, Nl * M * 2 * K);
             fpf = fingerprint(fpf, t.wphi, K);
+            fpf = fingerprint(fpf, t.aDamp, t.aDamp ? K : 0);
+            fpf = fingerprint_sampled(fpf, t.phi, Nl * M * 2 * K);
             if (t.rhoPrd)
                 fpf = fingerprint(fpf, t.rhoPrd, Nl * K);
         }
-    const uint64_t fj = fingerprint(1469598103934665603ULL, p.J, L * K);
-    if (!m.uploadedStatic || fa != m.fpAtmos)
-        mask |= LWB200_ATMOS;
-    if (!m.uploadedStatic || fb != m.fpBackground)
+    const uint64_t fj = fingerprint_J(m);
+    const bool atmosChanged = !m.uploadedStatic || fa != m.fpAtmos;
+    // a changed atmosphere means update_deps() ran: profiles and background are re-sent with it
+    if (atmosChanged)
+        mask |= LWB200_ATMOS | LWB200_BACKGR | LWB200_PROFILE;
+    if (fb != m.fpBackground)
         mask |= LWB200_BACKGR;
-    if (!m.uploadedStatic || fpf != m.fpProfiles)
+    if (fpf != m.fpProfiles)
         mask |= LWB200_PROFILE;
     if (!m.uploadedStatic || fj != m.fpJ)
         mask |= LWB200_JBAR;
@@ -325,9 +501,36 @@ void sync_inputs(Context& ctx, Mirror& m, bool withGamma)
     (void)ctx;
 }
 
+// ZPlaneDecomposition (SimdFullIterationTemplates.hpp:254-281): register / unregister the output views.
+void bind_zplane(Mirror& m, ExtraParams& params)
+{
+    double *up = nullptr, *down = nullptr;
+    if (params.contains("ZPlaneDecomposition"))
+    {
+        const size_t L = m.prob.Nspect, M = m.prob.Nrays;
+        auto view = [&](const char* key) -> double*
+        {
+            if (!params.contains(key))
+                return nullptr;
+            F64View2D v = params.get_as<F64View2D>(key);
+            if (!v)
+                return nullptr;
+            if ((size_t)v.shape(0) != L || (size_t)v.shape(1) != M)
+                throw std::runtime_error(std::string("mali_full_precond_B200: ") + key + " must be [Nspect, Nrays]");
+            return v.data;
+        };
+        up = view("ZPlaneUp");
+        down = view("ZPlaneDown");
+    }
+    if (up || down || m.zplane)
+        check(lwb200_set_zplane(m.dev, up, down), "lwb200_set_zplane");
+    m.zplane = up || down;
+}
+
 IterationResult b200_fs_iter(Context& ctx, bool lambdaIterate, ExtraParams params)
 {
     Mirror& m = mirror_for(ctx);
+    bind_zplane(m, params);
     sync_inputs(ctx, m, true);
     // one host synchronisation per call: dJ and J / I travel with the stream
     uint32_t flags = (lambdaIterate ? LWB200_LAMBDA_ITERATE : 0) | LWB200_FETCH_EARLY | LWB200_DJ_ASYNC;
@@ -339,10 +542,11 @@ IterationResult b200_fs_iter(Context& ctx, bool lambdaIterate, ExtraParams param
     double dJMax = 0.0;
     int64_t dJIdx = 0;
     check(lwb200_fs_iter(m.dev, flags, nullptr, nullptr), "lwb200_fs_iter");
-    check(lwb200_download(m.dev, LWB200_ITER_OUTPUTS | (storeDepth ? LWB200_DEPTH : 0)), "lwb200_download");
+    check(lwb200_download(m.dev, LWB200_ITER_OUTPUTS | (storeDepth ? LWB200_DEPTH : 0) | (m.zplane ? LWB200_ZPLANE : 0)),
+          "lwb200_download");
     check(lwb200_sync(m.dev), "lwb200_sync");
     check(lwb200_last_dj(m.dev, &dJMax, &dJIdx), "lwb200_last_dj");
-    m.fpJ = fingerprint(1469598103934665603ULL, m.prob.J, (size_t)m.prob.Nspect * m.prob.Nspace);
+    m.fpJ = fingerprint_J(m);
     IterationResult result{};
     result.updatedJ = true;
     result.dJMax = dJMax;
@@ -365,7 +569,8 @@ IterationResult b200_redistribute_prd(Context& ctx, int maxIter, f64 tol, ExtraP
             if (a.trans[kr].rhoPrd && (!a.detailedStatic || includeDetailed))
             {
                 if (!a.trans[kr].Qelast || !a.C)
-                    return redistribute_prd_lines_scalar(ctx, maxIter, tol, params); // not ours to guess
+                    throw std::runtime_error("mali_full_precond_B200: a PRD line without Qelast, or its atom "
+                                             "without collisional rates C, cannot be redistributed");
                 ++nLines;
             }
     if (nLines == 0)
@@ -381,7 +586,7 @@ IterationResult b200_redistribute_prd(Context& ctx, int maxIter, f64 tol, ExtraP
           "lwb200_redistribute_prd");
     check(lwb200_download(m.dev, LWB200_PRD | LWB200_JBAR | LWB200_INTENS | LWB200_RATES), "lwb200_download");
     check(lwb200_sync(m.dev), "lwb200_sync");
-    m.fpJ = fingerprint(1469598103934665603ULL, m.prob.J, (size_t)m.prob.Nspect * m.prob.Nspace);
+    m.fpJ = fingerprint_J(m);
     IterationResult result{};
     result.updatedRho = true;
     result.updatedJPrd = true;
@@ -403,14 +608,18 @@ IterationResult b200_redistribute_prd(Context& ctx, int maxIter, f64 tol, ExtraP
 IterationResult b200_full_stokes_fs(Context& ctx, bool updateJ, bool upOnly, ExtraParams params)
 {
     if (params.contains("J20"))
-        return formal_sol_full_stokes_impl(ctx, updateJ, upOnly, params); // J20 is not handled on the device
+        throw std::runtime_error("mali_full_precond_B200: the J20 option of the full-Stokes formal solution "
+                                 "(FormalStokes.cpp:678) has no device kernel");
+    if (!ctx.atmos->B)
+        throw std::runtime_error("Magnetic field required"); // as formal_sol_full_stokes_impl, FormalStokes.cpp:670-671
     size_t nPol = 0;
     for (auto* list : {&ctx.activeAtoms, &ctx.detailedAtoms})
         for (Atom* a : *list)
             for (Transition* t : a->trans)
                 nPol += (t->type == LINE && t->polarised && t->phiQ) ? 1 : 0;
     if (nPol == 0 || !ctx.spect->Quv)
-        return formal_sol_full_stokes_impl(ctx, updateJ, upOnly, params);
+        throw std::runtime_error("mali_full_precond_B200: full-Stokes formal solution without a polarised line "
+                                 "(call setup_stokes first) or without spect.Quv");
     {
         // setup_stokes() allocates the polarised profiles after the Context (and possibly our
         // mirror) was made: a mirror that does not know them is rebuilt
@@ -442,7 +651,7 @@ IterationResult b200_full_stokes_fs(Context& ctx, bool updateJ, bool upOnly, Ext
     check(lwb200_download(m.dev, LWB200_INTENS | LWB200_STOKES | (updateJ ? LWB200_JBAR : 0)), "lwb200_download");
     check(lwb200_sync(m.dev), "lwb200_sync");
     if (updateJ)
-        m.fpJ = fingerprint(1469598103934665603ULL, m.prob.J, (size_t)m.prob.Nspect * m.prob.Nspace);
+        m.fpJ = fingerprint_J(m);
     IterationResult result{};
     result.updatedJ = updateJ;
     if (updateJ)
@@ -455,32 +664,51 @@ IterationResult b200_full_stokes_fs(Context& ctx, bool updateJ, bool upOnly, Ext
 
 IterationResult b200_simple_fs(Context& ctx, bool upOnly, ExtraParams params)
 {
-    (void)params;
     Mirror& m = mirror_for(ctx);
+    bind_zplane(m, params);
     sync_inputs(ctx, m, false);
     check(lwb200_formal_sol(m.dev, upOnly ? 1 : 0), "lwb200_formal_sol");
-    check(lwb200_download(m.dev, LWB200_INTENS), "lwb200_download");
+    check(lwb200_download(m.dev, LWB200_INTENS | (m.zplane ? LWB200_ZPLANE : 0)), "lwb200_download");
     check(lwb200_sync(m.dev), "lwb200_sync");
     return IterationResult{};
 }
 
+bool find_atom(Atom* atom, Mirror*& m, int& idx)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    auto it = g_atoms.find(atom);
+    if (it == g_atoms.end() || !it->second.first->dev)
+        return false;
+    m = it->second.first;
+    idx = it->second.second;
+    return true;
+}
+
+// stat_eq / time_dep_update for an atom no device context knows yet (FsIterationFns::stat_eq gets an
+// Atom* and nothing else, and a caller may update populations before the first formal solution of its
+// Context, e.g. after gamma_matrices_escape_prob): the self-contained device solve.
+void population_solve_standalone(Atom* atom, const f64* nOld, f64 dt, int spaceStart, int spaceEnd)
+{
+    const int N = atom->Nlevel, K = (int)atom->n.shape(1);
+    int32_t nSingular = 0;
+    if (lwb200_population_solve(device_index(), 1, N, K, atom->Gamma.data, atom->n.data, atom->nTotal.data, nOld, dt,
+                                spaceStart, spaceEnd, &nSingular)
+        != 0)
+    {
+        if (nSingular > 0)
+            throw std::runtime_error("Singular Matrix"); // as lu_decompose does, LuSolve.cpp:22-23
+        raise("lwb200_population_solve");
+    }
+}
+
 void b200_stat_eq(Atom* atom, ExtraParams params, int spaceStart, int spaceEnd)
 {
+    (void)params;
     Mirror* m = nullptr;
     int idx = -1;
+    if (!find_atom(atom, m, idx))
     {
-        std::lock_guard<std::mutex> lock(g_mutex);
-        auto it = g_atoms.find(atom);
-        if (it != g_atoms.end())
-        {
-            m = it->second.first;
-            idx = it->second.second;
-        }
-    }
-    if (!m || !m->dev)
-    {
-        // an atom this plugin has never seen (no fs_iter yet on its Context): the core's path
-        stat_eq_impl(atom, params, spaceStart, spaceEnd);
+        population_solve_standalone(atom, nullptr, 0.0, spaceStart, spaceEnd);
         return;
     }
     check(lwb200_upload(m->dev, LWB200_POPS | LWB200_GAMMA_FINAL), "lwb200_upload");
@@ -499,20 +727,12 @@ void b200_stat_eq(Atom* atom, ExtraParams params, int spaceStart, int spaceEnd)
 // FsIterationFns::time_dep_update (LwFormalInterface.hpp:120): backward-Euler step of one atom.
 void b200_time_dep_update(Atom* atom, F64View2D nOld, f64 dt, ExtraParams params, int spaceStart, int spaceEnd)
 {
+    (void)params;
     Mirror* m = nullptr;
     int idx = -1;
+    if (!find_atom(atom, m, idx))
     {
-        std::lock_guard<std::mutex> lock(g_mutex);
-        auto it = g_atoms.find(atom);
-        if (it != g_atoms.end())
-        {
-            m = it->second.first;
-            idx = it->second.second;
-        }
-    }
-    if (!m || !m->dev)
-    {
-        time_dependent_update_impl(atom, nOld, dt, params, spaceStart, spaceEnd);
+        population_solve_standalone(atom, nOld.data, dt, spaceStart, spaceEnd);
         return;
     }
     check(lwb200_upload(m->dev, LWB200_GAMMA_FINAL), "lwb200_upload");
@@ -532,27 +752,23 @@ void b200_nr_post_update(Context& ctx, std::vector<Atom*>* atoms, const std::vec
                          F64View backgroundNe, const NrTimeDependentData& timeDepData, f64 crswVal,
                          ExtraParams params, int spaceStart, int spaceEnd)
 {
-    Mirror* m = nullptr;
+    (void)params;
+    Mirror& mr = mirror_for(ctx); // (made here if this Context has not run a formal solution yet)
+    Mirror* m = &mr;
     std::vector<int32_t> idx;
     {
         std::lock_guard<std::mutex> lock(g_mutex);
         for (Atom* a : *atoms)
         {
             auto it = g_atoms.find(a);
-            if (it == g_atoms.end() || (m && it->second.first != m))
-            {
-                m = nullptr;
-                break;
-            }
-            m = it->second.first;
+            if (it == g_atoms.end() || it->second.first != m)
+                throw std::runtime_error("mali_full_precond_B200: nr_post_update on an atom that is not an active "
+                                         "atom of this Context");
             idx.push_back(it->second.second);
         }
     }
-    if (!m || !m->dev || !m->prob.ne || idx.size() != atoms->size())
-    {
-        nr_post_update_impl(ctx, atoms, dC, backgroundNe, timeDepData, crswVal, params, spaceStart, spaceEnd);
-        return;
-    }
+    if (!m->prob.ne)
+        throw std::runtime_error("mali_full_precond_B200: nr_post_update needs atmos.ne");
     std::vector<const double*> dCp, prevP;
     for (const auto& v : dC)
         dCp.push_back(v.data);
@@ -567,7 +783,7 @@ void b200_nr_post_update(Context& ctx, std::vector<Atom*>* atoms, const std::vec
     u.nPrev = prevP.empty() ? nullptr : prevP.data();
     u.dt = timeDepData.dt;
     u.crswVal = crswVal;
-    check(lwb200_upload(m->dev, LWB200_POPS | LWB200_GAMMA_FINAL), "lwb200_upload");
+    check(lwb200_upload(m->dev, LWB200_POPS | LWB200_NSTAR | LWB200_GAMMA_FINAL), "lwb200_upload");
     int32_t nSingular = 0;
     if (lwb200_nr_post_update(m->dev, &u, spaceStart, spaceEnd, &nSingular) != 0)
     {
@@ -606,6 +822,160 @@ void b200_free_global_scratch(Context* ctx)
     }
     ctx->methodScratch = nullptr;
 }
+
+// ---------------------------------------------------------------------------
+// The host formal solver behind fs_provider: piecewise Bezier3 short characteristics for ONE ray on
+// host vectors, in the two-phase form of the device solver (csrc/lwb200_fsm.cuh): first everything
+// that does not depend on the direction of the ray, in array-forward orientation -- the Steffen
+// derivatives of chi, the Bezier optical depth of every interval, the Steffen derivative of S in
+// optical depth -- then the sweep along the ray, whose last point is piecewise linear.
+// Arithmetic: Source/FormalScalar.cpp:209-325, :535-600, Bezier.hpp:58-127, LwInternal.hpp:90-110.
+inline double steffen_host(double dsUw, double dsDw, double slUw, double sl0)
+{
+    // slUw: slope over the upwind interval (length dsUw), sl0: over the downwind one (Bezier.hpp:58-65)
+    const double P0 = std::fabs((slUw * dsDw + sl0 * dsUw) / (dsDw + dsUw));
+    return (std::copysign(1.0, sl0) + std::copysign(1.0, slUw))
+           * std::fmin(std::fabs(slUw), std::fmin(std::fabs(sl0), 0.5 * P0));
+}
+
+struct HostRayScratch
+{
+    std::vector<double> ds, dChi, dtau, dS;
+    void resize(size_t K)
+    {
+        if (ds.size() < K)
+        {
+            ds.resize(K);
+            dChi.resize(K);
+            dtau.resize(K);
+            dS.resize(K);
+        }
+    }
+};
+
+void host_bezier3_ray(int K, const double* height, const double* chi, const double* S, double zmu, bool toObs,
+                      double Iupw, double* I, double* Psi)
+{
+    thread_local HostRayScratch w;
+    w.resize((size_t)K);
+    double *ds = w.ds.data(), *dChi = w.dChi.data(), *dtau = w.dtau.data(), *dS = w.dS.data();
+    // ---- direction-independent phase, forward (k ascending) orientation
+    for (int k = 0; k + 1 < K; ++k)
+        ds[k] = std::fabs(height[k] - height[k + 1]) * zmu;
+    dChi[0] = (chi[1] - chi[0]) / ds[0];
+    dChi[K - 1] = (chi[K - 1] - chi[K - 2]) / ds[K - 2];
+    for (int k = 1; k + 1 < K; ++k)
+        dChi[k] = steffen_host(ds[k - 1], ds[k], (chi[k] - chi[k - 1]) / ds[k - 1], (chi[k + 1] - chi[k]) / ds[k]);
+    for (int k = 0; k + 1 < K; ++k)
+    {
+        const double cA = chi[k] + (ds[k] / 3.0) * dChi[k];
+        const double cB = chi[k + 1] - (ds[k] / 3.0) * dChi[k + 1];
+        dtau[k] = ds[k] * (chi[k] + chi[k + 1] + cA + cB) * 0.25;
+    }
+    dS[0] = (S[1] - S[0]) / dtau[0];
+    dS[K - 1] = (S[K - 1] - S[K - 2]) / dtau[K - 2];
+    for (int k = 1; k + 1 < K; ++k)
+        dS[k] = steffen_host(dtau[k - 1], dtau[k], (S[k] - S[k - 1]) / dtau[k - 1], (S[k + 1] - S[k]) / dtau[k]);
+
+    // ---- the sweep
+    const int dk = toObs ? -1 : 1, kS = toObs ? K - 1 : 0, kE = toObs ? 0 : K - 1;
+    const double sgn = toObs ? -1.0 : 1.0; // derivative along the ray = sgn * forward derivative
+    double Iprev = Iupw;
+    I[kS] = Iupw;
+    if (Psi)
+        Psi[kS] = 0.0;
+    for (int k = kS + dk; k != kE; k += dk)
+    {
+        const int ku = k - dk;
+        const double dt = dtau[toObs ? k : k - 1];
+        const double dt2 = dt * dt, dt3 = dt2 * dt;
+        double alpha, beta, gamma, delta, edt;
+        if (dt < 5e-2)
+        {
+            edt = 1.0 - dt + 0.5 * dt2 - dt3 / 6.0;
+            alpha = 0.25 * dt - 0.2 * dt2 + dt3 / 12.0;
+            beta = 0.25 * dt - 0.05 * dt2 + dt3 / 120.0;
+            gamma = 0.25 * dt - 0.15 * dt2 + 0.05 * dt3;
+            delta = 0.25 * dt - 0.1 * dt2 + 0.025 * dt3;
+        }
+        else
+        {
+            edt = dt > 30.0 ? 0.0 : std::exp(-dt);
+            alpha = (6.0 - edt * (6.0 + 6.0 * dt + 3.0 * dt2 + dt3)) / dt3;
+            beta = (6.0 * edt - 6.0 + 6.0 * dt - 3.0 * dt2 + dt3) / dt3;
+            gamma = 3.0 * (2.0 * dt - 6.0 + edt * (6.0 + 4.0 * dt + dt2)) / dt3;
+            delta = 3.0 * (6.0 - 4.0 * dt + dt2 - 2.0 * edt * (3.0 + dt)) / dt3;
+        }
+        const double Cuw = S[ku] + (dt / 3.0) * (sgn * dS[ku]);
+        const double C0 = S[k] - (dt / 3.0) * (sgn * dS[k]);
+        Iprev = Iprev * edt + alpha * S[ku] + beta * S[k] + gamma * Cuw + delta * C0;
+        I[k] = Iprev;
+        if (Psi)
+            Psi[k] = beta + delta;
+    }
+    {
+        // last point: piecewise linear through w2()
+        const int k = kE, ku = kE - dk;
+        const double dt = 0.5 * zmu * (chi[k] + chi[ku]) * std::fabs(height[k] - height[ku]);
+        double w0, w1;
+        if (dt < 5.0E-4)
+        {
+            w0 = dt * (1.0 - 0.5 * dt);
+            w1 = (dt * dt) * (0.5 - dt * (1.0 / 3.0));
+        }
+        else if (dt > 50.0)
+            w0 = w1 = 1.0;
+        else
+        {
+            const double e = std::exp(-dt);
+            w0 = 1.0 - e;
+            w1 = w0 - dt * e;
+        }
+        I[k] = (1.0 - w0) * Iprev + w0 * S[k] - w1 * ((S[k] - S[ku]) / dt);
+        if (Psi)
+            Psi[k] = w0 - w1 / dt;
+    }
+    if (Psi)
+        for (int k = 0; k < K; ++k)
+            Psi[k] /= chi[k];
+}
+
+inline double planck_host(double T, double lambda)
+{
+    namespace C = Constants;
+    const double x = (C::HC / (C::KBoltzmann * C::NM_TO_M)) / lambda / T;
+    const double pre = (2.0 * C::HC) / (C::NM_TO_M * C::NM_TO_M * C::NM_TO_M) / (lambda * lambda * lambda);
+    return x <= 150.0 ? pre / (std::exp(x) - 1.0) : 0.0;
+}
+
+// LwFsFn (LwFormalInterface.hpp:33-34): boundary intensity as piecewise_bezier3_1d (FormalScalar.cpp:535-600).
+void b200_piecewise_bezier3_1d(LwInternal::FormalData* fd, int la, int mu, bool toObs, const F64View1D& wave)
+{
+    Atmosphere* atmos = fd->atmos;
+    const int K = atmos->Nspace;
+    if (K < 3)
+        throw std::runtime_error("piecewise_bezier3_1d_b200: needs at least three depth points");
+    const double zmu = 1.0 / atmos->muz(mu);
+    const double* h = atmos->height.data;
+    const double* chi = fd->chi.data;
+    const int kS = toObs ? K - 1 : 0, kN = toObs ? K - 2 : 1;
+    const double dtauB = 0.5 * zmu * (chi[kS] + chi[kN]) * std::fabs(h[kS] - h[kN]);
+    const AtmosphericBoundaryCondition& bc = toObs ? atmos->zLowerBc : atmos->zUpperBc;
+    double Iupw = 0.0;
+    if (bc.type == THERMALISED)
+    {
+        const double B0 = planck_host(atmos->temperature(kS), wave(la)), B1 = planck_host(atmos->temperature(kN), wave(la));
+        Iupw = B0 - (B1 - B0) / dtauB;
+    }
+    else if (bc.type == CALLABLE)
+    {
+        const int muIdx = bc.idxs(mu, int(toObs));
+        if (muIdx < 0)
+            throw std::runtime_error("piecewise_bezier3_1d_b200: boundary condition index missing for this ray");
+        Iupw = bc.bcData(la, muIdx, 0);
+    }
+    host_bezier3_ray(K, h, chi, fd->S.data, zmu, toObs, Iupw, fd->I.data, fd->Psi ? fd->Psi.data : nullptr);
+}
 } // namespace
 
 extern "C"
@@ -616,7 +986,7 @@ FsIterationFns fs_iteration_fns_provider()
         1,     // Ndim: 1D atmospheres only
         true,  // dimensionSpecific
         true,  // respectsFormalSolver (linear / besser / bezier3 kernels by name)
-        true,  // defaultPerAtomStorage (the delegated core functions use it)
+        true,  // defaultPerAtomStorage
         true,  // defaultWlaGijStorage
         "mali_full_precond_B200",
         b200_fs_iter,
@@ -637,12 +1007,11 @@ FsIterationFns fs_iteration_fns_provider()
 }
 
 // The per-ray LwFsFn hook cannot feed a GPU (one ray per call on host vectors,
-// LwFormalInterface.hpp:33-43); it is exported for API completeness with the
-// core's own host solver behind it.  Selecting it (or any of the three 1D
-// solver names) together with `mali_full_precond_B200` picks the matching
-// device kernel.
+// LwFormalInterface.hpp:33-43); what it exports is this back end's own host Bezier3 solver, numerically
+// the device solver's twin.  Selecting it (or any of the three 1D solver names) together with
+// `mali_full_precond_B200` picks the matching device kernel.
 FormalSolver fs_provider()
 {
-    return FormalSolver{LwInternal::piecewise_bezier3_1d, 1, 1, "piecewise_bezier3_1d_b200"};
+    return FormalSolver{b200_piecewise_bezier3_1d, 1, 1, "piecewise_bezier3_1d_b200"};
 }
 }

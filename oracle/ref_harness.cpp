@@ -50,6 +50,23 @@ struct LwRef
     FormalSolverManager fsManager;
     FsIterationFnsManager iterManager;
     std::unique_ptr<Context> ctx;
+    double *zUp = nullptr, *zDown = nullptr; // ZPlaneDecomposition outputs [Nspect][Nrays] (lwref_set_zplane)
+
+    // the ExtraParams a Python caller would pass (dict2ExtraParams, LwMiddleLayer.pyx:358-467)
+    ExtraParams params() const
+    {
+        ExtraParams ep{};
+        if (zUp || zDown)
+        {
+            const i64 L = prob->Nspect, M = prob->Nrays;
+            ep.insert("ZPlaneDecomposition", true);
+            if (zUp)
+                ep.insert("ZPlaneUp", F64View2D(zUp, L, M));
+            if (zDown)
+                ep.insert("ZPlaneDown", F64View2D(zDown, L, M));
+        }
+        return ep;
+    }
 };
 
 std::string harness_dir()
@@ -315,7 +332,7 @@ int lwref_fs_iter(LwRefHandle* hh, int lambdaIterate, double* dJMax, int64_t* dJ
     auto* h = (LwRef*)hh;
     try
     {
-        IterationResult r = formal_sol_gamma_matrices(*h->ctx, lambdaIterate != 0, ExtraParams{});
+        IterationResult r = formal_sol_gamma_matrices(*h->ctx, lambdaIterate != 0, h->params());
         if (dJMax) *dJMax = r.dJMax;
         if (dJMaxIdx) *dJMaxIdx = r.dJMaxIdx;
         return 0;
@@ -327,12 +344,22 @@ int lwref_fs_iter(LwRefHandle* hh, int lambdaIterate, double* dJMax, int64_t* dJ
     }
 }
 
+// extraParams {"ZPlaneDecomposition": True, "ZPlaneUp": up, "ZPlaneDown": down} for the following
+// lwref_fs_iter / lwref_formal_sol calls (SimdFullIterationTemplates.hpp:254-281); NULL, NULL: none.
+int lwref_set_zplane(LwRefHandle* hh, double* up, double* down)
+{
+    auto* h = (LwRef*)hh;
+    h->zUp = up;
+    h->zDown = down;
+    return 0;
+}
+
 int lwref_formal_sol(LwRefHandle* hh, int upOnly)
 {
     auto* h = (LwRef*)hh;
     try
     {
-        formal_sol(*h->ctx, upOnly != 0, ExtraParams{});
+        formal_sol(*h->ctx, upOnly != 0, h->params());
         return 0;
     }
     catch (const std::exception& e)
@@ -533,16 +560,49 @@ int lwref_time_fs_iter(LwRefHandle* hh, int nWarm, int nTimed, int withStatEq, d
     }
 }
 
+// The reference's formal-solver registry (Source/FormalInterface.cpp:9-37), shared by the calls below.
+static FormalSolverManager& solver_manager()
+{
+    static FormalSolverManager man;
+    return man;
+}
+
+// FormalSolverManager::load_fs_from_path (Source/FormalInterface.cpp:9-28): dlopen a plugin, look up
+// "fs_provider", append its solver.  *index receives its position in the registry, name (if not NULL)
+// a copy of FormalSolver::name.
+int lwref_load_formal_solver(const char* path, int* index, char* name, int nameLen)
+{
+    try
+    {
+        FormalSolverManager& man = solver_manager();
+        if (!man.load_fs_from_path(path))
+            throw std::runtime_error(std::string("load_fs_from_path failed: ") + path);
+        if (index)
+            *index = (int)man.formalSolvers.size() - 1;
+        if (name && nameLen > 0)
+        {
+            std::strncpy(name, man.formalSolvers.back().name, nameLen - 1);
+            name[nameLen - 1] = 0;
+        }
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
 // One ray through the reference's own 1D solvers (FormalSolverManager order:
-// 0 linear, 1 besser, 2 bezier3), for solver-level golden vectors.
+// 0 linear, 1 besser, 2 bezier3; >= 3: solvers loaded with lwref_load_formal_solver).
 int lwref_solve_ray(int solver, int Nspace, const double* height, const double* temperature,
                     const double* chi, const double* S, double muz, int toObs, double wavelength,
                     int lowerBc, int upperBc, double* I, double* Psi)
 {
     try
     {
-        FormalSolverManager man;
-        if (solver < 0 || solver > 2)
+        FormalSolverManager& man = solver_manager();
+        if (solver < 0 || solver >= (int)man.formalSolvers.size())
             throw std::runtime_error("bad solver index");
         Atmosphere atmos{};
         atmos.Nspace = Nspace; atmos.Nrays = 1; atmos.Ndim = 1; atmos.Nz = Nspace;

@@ -70,6 +70,8 @@ def load():
     lib.lwref_solve_ray.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_int,
                                     C.c_double, C.c_int, C.c_int, dp, dp]
     lib.lwref_solve_lin_eq.argtypes = [C.c_int, dp, dp, C.c_int]
+    lib.lwref_set_zplane.argtypes = [vp, dp, dp]
+    lib.lwref_load_formal_solver.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_char_p, C.c_int]
     lib.lwref_ng_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int), dp,
                                   C.POINTER(C.c_int64)]
     _lib = lib
@@ -104,6 +106,14 @@ class RefContext:
 
     def formal_sol(self, upOnly=True):
         _check(self.lib.lwref_formal_sol(self.h, int(upOnly)))
+
+    def set_zplane(self, up=None, down=None):
+        """ZPlaneDecomposition extra parameters for the following fs_iter / formal_sol calls: float64
+        arrays [Nspect, Nrays] (or None)."""
+        dp = C.POINTER(C.c_double)
+        self._zkeep = (up, down)
+        _check(self.lib.lwref_set_zplane(self.h, up.ctypes.data_as(dp) if up is not None else dp(),
+                                         down.ctypes.data_as(dp) if down is not None else dp()))
 
     def stat_eq(self):
         _check(self.lib.lwref_stat_eq(self.h))
@@ -173,6 +183,16 @@ def solve_ray(solver, height, temperature, chi, S, muz, toObs, wavelength, lower
                                int(toObs), float(wavelength), lowerBc, upperBc,
                                I.ctypes.data_as(dp), Psi.ctypes.data_as(dp) if want_psi else dp()))
     return I, Psi
+
+
+def load_formal_solver(path):
+    """The reference's FormalSolverManager.load_fs_from_path on a plugin; returns (index to pass to
+    solve_ray as `solver`, the solver's name)."""
+    lib = load()
+    idx = C.c_int(-1)
+    name = C.create_string_buffer(128)
+    _check(lib.lwref_load_formal_solver(os.fsencode(path), C.byref(idx), name, 128))
+    return idx.value, name.value.decode()
 
 
 def solve_lin_eq(A, b, improve=True):

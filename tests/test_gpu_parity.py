@@ -683,6 +683,32 @@ def test_column_stack_properties_at_scale():
     ctx.close()
 
 
+@pytest.mark.parametrize('ndepth,general', [(None, False), (None, True), (200, False)])
+def test_zplane_decomposition_matches_depth_intensities(ndepth, general):
+    """ZPlaneUp(la, mu) = I(1) of the up-going ray, ZPlaneDown(la, mu) = I(Nz - 2) of the down-going one
+    (SimdFullIterationTemplates.hpp:351-360), for a stack, through the moment pipeline, the general
+    per-ray kernel and the multi-warp (deep atmosphere) kernel -- against the oracle's depth data."""
+    p = synth.tiny_problem(ncol=2, perturb=True, ndepth=ndepth)
+    q = p.clone()
+    q.alloc_depth_data()
+    up = np.full((p.Ncol, p.Nspect, p.Nrays), -1.0)
+    down = np.full((p.Ncol, p.Nspect, p.Nrays), -1.0)
+    ctx = Context(p)
+    ep = {'ZPlaneDecomposition': True, 'ZPlaneUp': up, 'ZPlaneDown': down}
+    if general:
+        ep['generalKernel'] = True
+    oracle_iter(q, storeDepth=True, stat_eq=False)
+    # formal_sol(upOnly) from the same state (same J-dagger): only the up-going plane is written
+    ctx.formal_sol(upOnly=True, extraParams=ep)
+    assert rel_err(up, q.depthI[:, :, :, 1, 1]) <= TOL and (down == -1.0).all()
+    up[:] = -1.0
+    ctx.formal_sol_gamma_matrices(extraParams=ep)
+    assert rel_err(up, q.depthI[:, :, :, 1, 1]) <= TOL
+    assert rel_err(down, q.depthI[:, :, :, 0, p.Nspace - 2]) <= TOL
+    assert rel_err(p.I, q.I) <= TOL
+    ctx.close()
+
+
 def test_short_wavelength_continuum_boltzmann_factor_underflows_to_zero():
     """A bound-free continuum reaching down to 2 nm: exp(-hc / (k lambda T)) underflows (x < -708) at the cool
     depths; the reference's libm exp() gives 0 there and so must the device's table-free exp."""

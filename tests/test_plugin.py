@@ -28,6 +28,51 @@ def test_plugin_exports_provider_symbols():
 
 
 @needs_plugin
+def test_plugin_carries_no_reference_code():
+    """The shim is compiled against the reference headers only: it loads on its own (RTLD_NOW, no
+    reference library in the process), exports exactly the two provider symbols and needs no
+    library of the reference."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, '-c', f'import ctypes; ctypes.CDLL({PLUGIN!r})'], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    nm = subprocess.run(['nm', '-D', '--defined-only', PLUGIN], capture_output=True, text=True)
+    if nm.returncode == 0:
+        exported = [ln.split()[-1] for ln in nm.stdout.splitlines() if ' T ' in ln]
+        assert sorted(exported) == ['fs_iteration_fns_provider', 'fs_provider'], exported
+    ldd = subprocess.run(['ldd', PLUGIN], capture_output=True, text=True)
+    if ldd.returncode == 0:
+        assert 'enkiTS' not in ldd.stdout and 'lwref' not in ldd.stdout and 'oracle' not in ldd.stdout, ldd.stdout
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.parametrize('toObs', [False, True])
+@pytest.mark.parametrize('lowerBc,upperBc', [(capi.BC_THERMALISED, capi.BC_ZERO), (capi.BC_ZERO, capi.BC_THERMALISED)])
+def test_own_host_solver_behind_fs_provider_matches_the_reference(toObs, lowerBc, upperBc):
+    """fs_provider exports this back end's OWN host Bezier3 solver (the device solver's two-phase
+    arithmetic, serial): loaded by the reference's FormalSolverManager and run against the reference's
+    piecewise_bezier3_1d on the same rays, optically thin to thick."""
+    idx, name = reflib.load_formal_solver(PLUGIN)
+    assert name == 'piecewise_bezier3_1d_b200' and idx >= 3
+    p = synth.config_c1(nl=0.3)
+    rng = np.random.default_rng(7)
+    h, T = p.height[0], p.temperature[0]
+    for la in range(0, p.Nspect, 23):
+        chi = p.chiBg[0, la] * np.exp(rng.normal(0.0, 0.6, p.Nspace)) * 10.0 ** rng.uniform(-1, 3)
+        S = synth.planck_nu(p.wavelength[la], T) * np.exp(rng.normal(0.0, 0.4, p.Nspace))
+        for mu in (0.11, 0.5, 0.95):
+            a = reflib.solve_ray(2, h, T, chi, S, mu, toObs, p.wavelength[la], lowerBc, upperBc)
+            b = reflib.solve_ray(idx, h, T, chi, S, mu, toObs, p.wavelength[la], lowerBc, upperBc)
+            # (rounding-level agreement; the closed-form Bezier3 coefficients cancel strongly just above
+            # dt = 0.05 and amplify the last bit of dt, SURVEY.md 7-2)
+            assert rel_err(b[0], a[0]) <= 1e-10, (la, mu)
+            assert rel_err(b[1], a[1]) <= 1e-9, (la, mu)
+            c = reflib.solve_ray(idx, h, T, chi, S, mu, toObs, p.wavelength[la], lowerBc, upperBc, want_psi=False)
+            assert np.array_equal(c[0], b[0])
+
+
+@needs_plugin
 @pytest.mark.ref
 def test_reference_plugin_manager_loads_the_scheme():
     import torch
@@ -220,3 +265,152 @@ def test_plugin_singular_matrix_is_a_runtime_error():
     with pytest.raises(RuntimeError, match='Singular Matrix'):
         gpu.stat_eq()
     gpu.close()
+
+
+def _launches():
+    return capi.load().lwb200_global_launch_count()
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.gpu
+def test_every_plugin_slot_runs_on_the_device():
+    """No slot of the scheme has a CPU path behind it: each call of the reference core through the
+    plugin launches kernels of liblwb200.so (process-wide launch counter of the C-ABI)."""
+    from tests.test_oracle import nr_case
+    p = synth.tiny_prd_problem(perturb=True)
+    gpu = reflib.RefContext(p, scheme=PLUGIN)
+    p.prefill_gamma()
+
+    def ran(fn, *a, **kw):
+        n0 = _launches()
+        out = fn(*a, **kw)
+        assert _launches() > n0, fn.__name__
+        return out
+    ran(gpu.stat_eq)                       # before any formal solution: the self-contained device solve
+    p.prefill_gamma()
+    ran(gpu.fs_iter)                       # fs_iter
+    ran(gpu.redistribute_prd, maxIter=2, tol=1e-3, nlines=2)   # redistribute_prd
+    ran(gpu.stat_eq)                       # stat_eq
+    ran(gpu.formal_sol, upOnly=True)       # simple_fs
+    ran(gpu.time_dep_update, 0, p.atoms[0].n[0].copy(), 0.01)   # time_dep_update
+    idx, bg, dC, nPrev = nr_case(p, True, True)
+    upd, keep = capi.make_nr_update(idx, bg, dC=dC, nPrev=nPrev, dt=0.05, crswVal=1.0)
+    ran(gpu.nr_post_update, upd)           # nr_post_update
+    gpu.close()
+    s = synth.tiny_stokes_problem(perturb=True)
+    gs = reflib.RefContext(s, scheme=PLUGIN)
+    s.prefill_gamma()
+    ran(gs.fs_iter)
+    ran(gs.full_stokes, updateJ=True, upOnly=False)   # full_stokes_fs
+    gs.close()
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.gpu
+def test_stat_eq_before_any_formal_solution_matches_the_reference():
+    """FsIterationFns::stat_eq on an atom whose Context has not run a formal solution yet (e.g. after the
+    escape-probability start): the plugin's self-contained device solve against the reference's stat_eq."""
+    p = synth.config_c1(nl=0.3)
+    q = p.clone()
+    for prob in (p, q):
+        prob.prefill_gamma()   # Gamma = C: collisional rates only, columns do not sum to zero yet
+        for a in prob.atoms:
+            G = a.Gamma[0]
+            for i in range(a.Nlevel):
+                G[i, i] = 0.0
+            for i in range(a.Nlevel):
+                G[i, i] = -G[:, i].sum(axis=0)
+    gpu = reflib.RefContext(p, scheme=PLUGIN)
+    cpu = reflib.RefContext(q, scheme='scalar')
+    gpu.stat_eq()
+    cpu.stat_eq()
+    for a, b in zip(p.atoms, q.atoms):
+        assert rel_err(a.n, b.n) <= 1e-9
+        assert not np.array_equal(b.n, b.nStar)
+    gpu.close()
+    cpu.close()
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.gpu
+@pytest.mark.parametrize('which', ['both', 'up', 'down'])
+def test_zplane_decomposition_through_the_plugin(which):
+    """extraParams ZPlaneDecomposition / ZPlaneUp / ZPlaneDown (SimdFullIterationTemplates.hpp:254-281,
+    :351-360): the reference core with its scalar scheme against the same call through the B200 scheme,
+    for the Gamma iteration and for formal_sol."""
+    p = synth.config_c1(nl=0.4)
+    q = p.clone()
+    gpu = reflib.RefContext(p, scheme=PLUGIN)
+    cpu = reflib.RefContext(q, scheme='scalar')
+    shape = (p.Nspect, p.Nrays)
+    zs = []
+    for ctx in (gpu, cpu):
+        up = np.full(shape, -1.0) if which in ('both', 'up') else None
+        down = np.full(shape, -1.0) if which in ('both', 'down') else None
+        ctx.set_zplane(up, down)
+        zs.append((up, down))
+    for prob, ctx in ((p, gpu), (q, cpu)):
+        prob.prefill_gamma()
+        ctx.fs_iter()
+    for a, b in zip(zs[0], zs[1]):
+        if a is not None:
+            assert (b != -1.0).all() and rel_err(a, b) <= 1e-9
+    e = compare_problems(p, q)
+    assert e['I'] <= 1e-9 and e['J'] <= 1e-9 and e['Gamma'] <= 1e-9, e
+    for z in zs:
+        for a in z:
+            if a is not None:
+                a[:] = -1.0
+    gpu.formal_sol(upOnly=True)
+    cpu.formal_sol(upOnly=True)
+    for a, b in zip(zs[0], zs[1]):
+        if a is not None:
+            assert np.array_equal(a == -1.0, b == -1.0)      # upOnly leaves ZPlaneDown untouched
+            assert rel_err(a, b) <= 1e-9
+    # and switched off again: the arrays are no longer written
+    for ctx in (gpu, cpu):
+        ctx.set_zplane(None, None)
+    for z in zs:
+        for a in z:
+            if a is not None:
+                a[:] = -2.0
+    p.prefill_gamma()
+    gpu.fs_iter()
+    for a in zs[0]:
+        if a is not None:
+            assert (a == -2.0).all()
+    gpu.close()
+    cpu.close()
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.gpu
+def test_plugin_sees_a_single_depth_change():
+    """A response-function style update: the background changes at ONE depth of ONE wavelength, J at one
+    element, a profile at one depth (with its wphi).  The fingerprints cover every element."""
+    p = synth.config_c1(nl=0.5)
+    q = p.clone()
+    gpu = reflib.RefContext(p, scheme=PLUGIN)
+    cpu = reflib.RefContext(q, scheme='scalar')
+    for prob, ctx in ((p, gpu), (q, cpu)):
+        prob.prefill_gamma()
+        ctx.fs_iter()
+    k = 37
+    for prob in (p, q):
+        prob.chiBg[0, prob.Nspect // 3, k] *= 1.5
+        prob.etaBg[0, 5, k] *= 0.5
+        prob.J[0, 11, k] *= 1.25
+        t = prob.atoms[1].trans[0]
+        t.phi[0, :, :, :, k] *= 1.1
+        t.wphi[0, k] /= 1.1
+    for prob, ctx in ((p, gpu), (q, cpu)):
+        prob.prefill_gamma()
+        ctx.fs_iter()
+    e = compare_problems(p, q)
+    assert e['I'] <= 1e-9 and e['J'] <= 1e-9 and e['Gamma'] <= 1e-9 and e['R'] <= 1e-9, e
+    gpu.close()
+    cpu.close()
