@@ -269,6 +269,7 @@ struct LwB200Context
     // ZPlaneDecomposition (lwb200_set_zplane)
     DevBuf<double> zUp, zDown;
     double *zUpHost = nullptr, *zDownHost = nullptr;
+    bool zDownWritten = false; // the last formal solution swept the down-going rays too
     std::vector<DevLine> devLines;
     DevBuf<DevLine> dLines;
 };
@@ -1882,7 +1883,7 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
     {
         if (c->zUpHost)
             CU(cudaMemcpyAsync(c->zUpHost, c->zUp.p, ncol * L * M * D, D2H, s));
-        if (c->zDownHost)
+        if (c->zDownHost && c->zDownWritten) // (an up-only formal solution leaves ZPlaneDown as it is)
             CU(cudaMemcpyAsync(c->zDownHost, c->zDown.p, ncol * L * M * D, D2H, s));
     }
     if ((mask & LWB200_DEPTH) && c->depthChi.p)
@@ -2045,6 +2046,7 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
     }
     else
         return fail("lwb200_fs_iter: every column is retired");
+    c->zDownWritten = true;
     const int rcFs = launch_fs<MODE_ITER>(c, (flags & LWB200_LAMBDA_ITERATE) ? 1 : 0, 0, storeDepth);
     c->djEarly = false;
     if (rcFs)
@@ -2065,6 +2067,7 @@ int lwb200_formal_sol(LwB200Context* c, int upOnly)
     if (!c->nstarUploaded)
         return fail("lwb200_formal_sol: inputs have not been uploaded (lwb200_upload)");
     c->lastLaunches = 0;
+    c->zDownWritten = !upOnly;
     return launch_fs<MODE_FS>(c, 0, upOnly ? 1 : 0, 0);
 }
 
