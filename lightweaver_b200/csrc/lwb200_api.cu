@@ -5,6 +5,7 @@
 #include "lwb200_kernels.cuh"
 #include "lwb200_profiles.cuh"
 #include "lwb200_pipeline.cuh"
+#include "lwb200_gamma.cuh"
 #include "lwb200_prd.cuh"
 #include "lwb200_stokes.cuh"
 #include "lwb200_ng.cuh"
@@ -160,6 +161,8 @@ struct PipelineLists
 {
     const int* moment;
     int nMoment;
+    const int* gTiles; // tiles of the second-generation Gamma stage
+    int nGTiles;
     const int* kindLam[4];
     int nKindLam[4];
     const unsigned char* laMask;
@@ -266,6 +269,17 @@ struct LwB200Context
     bool djEarly = false, djDone = false; // dJ reduced on a side stream while Gamma is accumulated
     DevBuf<DevTrans> dTrans;
     DevBuf<DevEntry> dEntries;
+    // Gamma stage, second generation (lwb200_gamma.cuh): its own tiling and compact tables
+    DevBuf<GEntry> dGEntries;
+    DevBuf<GLam> dGLam;
+    DevBuf<GLine> dGLine;
+    DevBuf<int> dGTileLa, dGTileSlotOff, dGList, dGListPrd;
+    DevBuf<int4> dGTileSlotRows;
+    std::vector<int> gTileLa, gLamLa; // host copies: tile -> range of gLamLa (wavelength indices in tile order)
+    GammaPlan G{};
+    int gNC = 1, nGTile = 0, nGList = 0, nGListPrd = 0;
+    size_t gSmem = 0;
+    bool gammaV1 = false; // LWB200_GAMMA_V1=1: the first-generation gamma_kernel (A/B timing aid)
     // ZPlaneDecomposition (lwb200_set_zplane)
     DevBuf<double> zUp, zDown;
     double *zUpHost = nullptr, *zDownHost = nullptr;
@@ -600,6 +614,179 @@ int build_plan(LwB200Context* c)
     }
     c->momRows = std::max(momRows, 1);
 
+    // ---- Gamma stage, second generation: tiles of the moment wavelengths (kinds 0..3) and the compact
+    // per-wavelength tables its warps read (lwb200_gamma.cuh)
+    {
+        const int NCg = std::min(4, (K + 31) / 32); // depths per lane; a warp covers 32 * NCg depths
+        c->gNC = NCg;
+        const size_t rowBytes = (size_t)32 * NCg * sizeof(double);
+        int maxAct = 1;
+        for (int la = 0; la < L; ++la)
+            if (c->laKind[la] < 4)
+                maxAct = std::max(maxAct, (int)active[la].size());
+        if (maxAct > kGammaMaxEntries)
+            return fail("more than 32 active transitions at one wavelength");
+        // accumulator budget per warp: what is left of an SM's shared memory at ~6 resident warps
+        const int slotCapG = std::max(maxAct, (int)(((size_t)36 << 10) / (4 * rowBytes)));
+        int gTileLen = (int)std::max<long long>(1, std::min<long long>(32, ((long long)L * p.Ncol) / (148LL * 12)));
+        if (const char* e = std::getenv("LWB200_GTILE_LEN")) // tuning aid
+            gTileLen = std::max(1, std::atoi(e));
+        // the warp-per-tile Gamma stage pays off on column stacks; one atmosphere keeps the first generation
+        c->gammaV1 = p.Ncol < 8;
+        if (const char* e = std::getenv("LWB200_GAMMA_V1"))
+            c->gammaV1 = std::atoi(e) != 0;
+        std::vector<GEntry> gEntries;
+        std::vector<GLam> gLam;
+        std::vector<GLine> gLine;
+        std::vector<int> gTileSlotOff(1, 0);
+        std::vector<int4> gTileSlotRows;
+        c->gTileLa.assign(1, 0);
+        int gMaxSlots = 1;
+        constexpr double hc_k = kHC / (kKBoltzmann * kNmToM);
+        constexpr double twoHc = 2.0 * kHC / (kNmToM * kNmToM * kNmToM);
+        constexpr double hc_4pi = 0.25 * kHC / kPi;
+        int pos = 0;
+        while (pos < L)
+        {
+            if (c->laKind[pos] == 4)
+            {
+                ++pos;
+                continue;
+            }
+            std::vector<int> slots;
+            const int start = pos;
+            while (pos < L && pos - start < gTileLen && c->laKind[pos] < 4)
+            {
+                std::vector<int> add;
+                for (int g : active[pos])
+                    if (std::find(slots.begin(), slots.end(), g) == slots.end())
+                        add.push_back(g);
+                if ((int)(slots.size() + add.size()) > slotCapG && pos > start)
+                    break;
+                slots.insert(slots.end(), add.begin(), add.end());
+                ++pos;
+            }
+            for (int la = start; la < pos; ++la)
+            {
+                const double rlambda = 1.0 / p.wavelength[la];
+                GLam gl{};
+                gl.hc_kl = hc_k * rlambda;
+                gl.hcl = twoHc * (rlambda * rlambda * rlambda);
+                gl.la = la;
+                gl.eOff = (int)gEntries.size();
+                gl.eCnt = (int)active[la].size();
+                gl.momRow = momOff[la];
+                gl.nLines = laNLines[la];
+                // the wavelength's entries, in the order of the pipeline's DevEntry list
+                const int eBeg = laOff[la];
+                int nl = 0;
+                for (int q = 0; q < laCnt[la]; ++q)
+                {
+                    const DevEntry& en = entries[eBeg + q];
+                    const DevTrans& d = c->devTrans[en.trans];
+                    GEntry ge{};
+                    ge.al = en.al;
+                    ge.wlaF = en.wlaF;
+                    ge.accRow = (short)(4 * (std::find(slots.begin(), slots.end(), en.trans) - slots.begin()));
+                    ge.levI = (short)en.levI;
+                    ge.levJ = (short)en.levJ;
+                    ge.cont = (short)en.contIdx;
+                    ge.flags = (unsigned short)((en.prd ? GE_PRD : 0) | (en.detailed ? GE_DETAILED : 0));
+                    ge.type = (unsigned char)en.type;
+                    ge.i = (unsigned char)en.i;
+                    ge.j = (unsigned char)en.j;
+                    ge.lslot = (unsigned char)(d.type == 0 ? nl++ : 0);
+                    ge.groupLen = 0;
+                    ge.atomTag = (unsigned char)en.atom;
+                    gEntries.push_back(ge);
+                }
+                // atom groups: length on the first entry, first-writer / validity flags of the aggregates
+                for (size_t e = gl.eOff; e < gEntries.size();)
+                {
+                    size_t e1 = e + 1;
+                    while (e1 < gEntries.size() && gEntries[e1].atomTag == gEntries[e].atomTag)
+                        ++e1;
+                    gEntries[e].groupLen = (unsigned char)(e1 - e);
+                    unsigned touchedX = 0, touchedU = 0; // level bit masks (Nlevel <= 32)
+                    for (size_t q = e; q < e1; ++q)
+                    {
+                        GEntry& t = gEntries[q];
+                        if (t.type == 0)
+                            continue;
+                        if (!(touchedX & (1u << t.i)))
+                            t.flags |= GE_STORE_XI;
+                        touchedX |= 1u << t.i;
+                        if (!(touchedX & (1u << t.j)))
+                            t.flags |= GE_STORE_XJ;
+                        touchedX |= 1u << t.j;
+                        if (!(touchedU & (1u << t.j)))
+                            t.flags |= GE_STORE_UJ;
+                        touchedU |= 1u << t.j;
+                    }
+                    for (size_t q = e; q < e1; ++q)
+                    {
+                        GEntry& t = gEntries[q];
+                        t.flags |= (touchedX & (1u << t.i)) ? GE_XI_VALID : 0;
+                        t.flags |= (touchedX & (1u << t.j)) ? GE_XJ_VALID : 0;
+                        t.flags |= (touchedU & (1u << t.i)) ? GE_UI_VALID : 0;
+                        t.flags |= (touchedU & (1u << t.j)) ? GE_UJ_VALID : 0;
+                    }
+                    e = e1;
+                }
+                gLam.push_back(gl);
+                c->gLamLa.push_back(la);
+                for (int l = 0; l < 3; ++l)
+                {
+                    GLine gn{};
+                    gn.rhoOff = -1;
+                    if (l < laNLines[la] && c->laKind[la] < 4)
+                    {
+                        const LambdaLine& ll = lamLine[(size_t)la * 3 + l];
+                        gn.vB = hc_4pi * (ll.lambda0 * rlambda) * ll.Bij;
+                        gn.gS = ll.Bji_Bij;
+                        gn.AB = ll.Aji_Bji;
+                        gn.wlaS = ll.wlaS;
+                        gn.rhoOff = ll.rhoOff;
+                        gn.rhoColStride = ll.rhoColStride;
+                        gn.wphiRow = ll.lineIdx;
+                        gn.levI = (short)ll.levI;
+                        gn.levJ = (short)ll.levJ;
+                        gn.i = (unsigned char)ll.i;
+                        gn.j = (unsigned char)ll.j;
+                        gn.atomTag = (unsigned char)ll.atom;
+                    }
+                    gLine.push_back(gn);
+                }
+            }
+            for (int g : slots)
+            {
+                const DevTrans& d = c->devTrans[g];
+                gTileSlotRows.push_back(make_int4(d.accIJ, d.accJI, d.accRij, d.accRji));
+            }
+            gTileSlotOff.push_back((int)gTileSlotRows.size());
+            c->gTileLa.push_back((int)gLam.size());
+            gMaxSlots = std::max(gMaxSlots, (int)slots.size());
+        }
+        if (p.Natom > 255)
+            return fail("more than 255 atoms");
+        c->nGTile = (int)c->gTileLa.size() - 1;
+        c->gSmem = gamma_warp_smem(NCg, gMaxSlots, maxNlevel);
+        if (c->gSmem > smemLimit)
+            return fail("wavelength tile too large for shared memory (Gamma stage)");
+        if (c->dGEntries.upload(gEntries) || c->dGLam.upload(gLam) || c->dGLine.upload(gLine)
+            || c->dGTileLa.upload(c->gTileLa) || c->dGTileSlotOff.upload(gTileSlotOff)
+            || c->dGTileSlotRows.upload(gTileSlotRows))
+            return 1;
+        c->G.entries = c->dGEntries.p;
+        c->G.lam = c->dGLam.p;
+        c->G.line = c->dGLine.p;
+        c->G.tileLa = c->dGTileLa.p;
+        c->G.tileSlotOff = c->dGTileSlotOff.p;
+        c->G.tileSlotRows = c->dGTileSlotRows.p;
+        c->G.maxSlots = gMaxSlots;
+        c->G.maxNlevel = maxNlevel;
+    }
+
     // PRD lines (PrdTemplates.hpp:186-211: active atoms first, then detailed ones) and the packed
     // layouts of the inputs only lwb200_redistribute_prd reads
     c->atomCOff.assign(p.Natom, -1);
@@ -814,6 +1001,16 @@ int refresh_tile_lists(LwB200Context* c)
             return 1;
         c->nKindLam[q] = (int)kindLam[q].size();
     }
+    {
+        std::vector<int> gl;
+        for (int t = 0; t < c->nGTile; ++t)
+            if (!(c->gLamLa[c->gTileLa[t + 1] - 1] < c->laLo || c->gLamLa[c->gTileLa[t]] >= c->laHi))
+                gl.push_back(t);
+        c->dGList.release();
+        if (c->dGList.upload(gl))
+            return 1;
+        c->nGList = (int)gl.size();
+    }
     if (c->dListDirect.upload(dir) || c->dListAll.upload(all))
         return 1;
     c->nListDirect = (int)dir.size();
@@ -916,9 +1113,62 @@ PipelineLists full_lists(LwB200Context* c)
         pl.kindLam[q] = c->dKindLam[q].p;
         pl.nKindLam[q] = c->nKindLam[q];
     }
+    pl.gTiles = c->dGList.p;
+    pl.nGTiles = c->nGList;
     pl.laMask = nullptr;
     pl.prdOnly = 0;
     return pl;
+}
+
+// Second-generation Gamma stage: one warp per (tile, column, chunk of 32 * gNC depths), the warps of a CTA
+// on consecutive tiles of one column whose populations / continuum ratios they stage once in shared
+// memory when that leaves room for at least two warps.
+template <int NC, bool STAGE>
+int launch_gamma_tiles_t(LwB200Context* c, const PipelineLists& pl, int nb, int colBase, int laLo, int laHi,
+                         int warps, size_t smem, int warpDoubles)
+{
+    auto kern = gamma_tile_kernel<NC, STAGE>;
+    if (set_smem_attr(kern, c->device))
+        return 1;
+    const int chunk = 32 * NC;
+    const dim3 gg((pl.nGTiles + warps - 1) / warps, nb, (c->P.K + chunk - 1) / chunk);
+    kern<<<gg, 32 * warps, smem, c->stream>>>(c->P, c->G, pl.gTiles, pl.nGTiles, laLo, laHi, colBase, pl.laMask,
+                                             pl.prdOnly, warpDoubles);
+    CU(cudaGetLastError());
+    c->lastLaunches += 1;
+    return 0;
+}
+
+int launch_gamma_tiles(LwB200Context* c, const PipelineLists& pl, int nb, int colBase, int laLo, int laHi)
+{
+    const int NC = c->gNC;
+    const size_t warpBytes = gamma_warp_smem(NC, c->G.maxSlots, c->G.maxNlevel);
+    const size_t stageBytes = gamma_stage_smem(NC, c->P.NlevTot, c->P.Ncont);
+    const size_t budget = 216 * 1024;
+    // Measured on B200 (config 3, 512 columns): single-warp CTAs reading populations / ratios through the
+    // L1 13.9 ms per launch set, 5-warp CTAs with the column staged in shared memory 14.7 ms -- the staging
+    // costs a resident warp and a barrier.  Both stay selectable (tuning aids).
+    static const int envWarps = std::getenv("LWB200_GAMMA_WARPS") ? std::atoi(std::getenv("LWB200_GAMMA_WARPS")) : 1;
+    static const int envStage = std::getenv("LWB200_GAMMA_STAGE") ? std::atoi(std::getenv("LWB200_GAMMA_STAGE")) : 0;
+    const bool stage = envStage != 0 && stageBytes + 2 * warpBytes <= budget;
+    int warps = (int)((budget - (stage ? stageBytes : 0)) / warpBytes);
+    warps = std::max(1, std::min({warps, 8, pl.nGTiles, std::max(1, envWarps)}));
+    const size_t smem = (stage ? stageBytes : 0) + warps * warpBytes;
+    const int wd = (int)(warpBytes / sizeof(double));
+#define LWB200_GT(NCV)                                                                                           \
+    case NCV:                                                                                                    \
+        return stage ? launch_gamma_tiles_t<NCV, true>(c, pl, nb, colBase, laLo, laHi, warps, smem, wd)          \
+                     : launch_gamma_tiles_t<NCV, false>(c, pl, nb, colBase, laLo, laHi, warps, smem, wd);
+    switch (NC)
+    {
+        LWB200_GT(1)
+        LWB200_GT(2)
+        LWB200_GT(3)
+    default:
+        LWB200_GT(4)
+    }
+#undef LWB200_GT
+    return 0;
 }
 
 template <int NCH, int SOLVER, bool MULTI>
@@ -1066,13 +1316,18 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
                 c->fetched = true;
             }
         }
-        if (!direct && pl.nMoment > 0)
+        if (!direct && c->gammaV1 && pl.nMoment > 0)
         {
             const int KC = c->KC;
             gamma_kernel<<<dim3(pl.nMoment, nb, (K + KC - 1) / KC), KC, c->smemGamma, c->stream>>>(
                 c->P, pl.moment, laLo, laHi, colBase, pl.laMask, pl.prdOnly);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
+        }
+        else if (!direct && pl.nGTiles > 0)
+        {
+            if (launch_gamma_tiles(c, pl, nb, colBase, laLo, laHi))
+                return 1;
         }
     }
     return 0;
@@ -1379,6 +1634,14 @@ int lwb200_destroy(LwB200Context* c)
     c->dLines.release();
     c->zUp.release();
     c->zDown.release();
+    c->dGEntries.release();
+    c->dGLam.release();
+    c->dGLine.release();
+    c->dGTileLa.release();
+    c->dGTileSlotOff.release();
+    c->dGTileSlotRows.release();
+    c->dGList.release();
+    c->dGListPrd.release();
     delete c;
     return 0;
 }
@@ -2309,11 +2572,22 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
             if (any && c->tileKind[t] < 4)
                 tiles.push_back(t);
         }
+        std::vector<int> gtiles;
+        for (int t = 0; t < c->nGTile; ++t)
+        {
+            bool any = false;
+            for (int q = c->gTileLa[t]; q < c->gTileLa[t + 1]; ++q)
+                any = any || mask[c->gLamLa[q]];
+            if (any)
+                gtiles.push_back(t);
+        }
         c->dPrdMask.release();
         c->dListMomentPrd.release();
-        if (c->dPrdMask.upload(mask) || c->dListMomentPrd.upload(tiles))
+        c->dGListPrd.release();
+        if (c->dPrdMask.upload(mask) || c->dListMomentPrd.upload(tiles) || c->dGListPrd.upload(gtiles))
             return 1;
         c->nListMomentPrd = (int)tiles.size();
+        c->nGListPrd = (int)gtiles.size();
         for (int q = 0; q < 4; ++q)
         {
             c->dKindLamPrd[q].release();
@@ -2326,6 +2600,8 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
     PipelineLists pl{};
     pl.moment = c->dListMomentPrd.p;
     pl.nMoment = c->nListMomentPrd;
+    pl.gTiles = c->dGListPrd.p;
+    pl.nGTiles = c->nGListPrd;
     for (int q = 0; q < 4; ++q)
     {
         pl.kindLam[q] = c->dKindLamPrd[q].p;

@@ -63,6 +63,7 @@ def test_cuda_vs_oracle_multicolumn_c1(solver, tileLen, monkeypatch):
     per Gamma tile (the planner picks 1 for a problem this small; larger stacks get up to 32)."""
     if tileLen is not None:
         monkeypatch.setenv('LWB200_TILE_LEN', str(tileLen))
+        monkeypatch.setenv('LWB200_GTILE_LEN', str(tileLen))
         monkeypatch.setenv('LWB200_GAMMA_DIRECT', '0')   # the tiled Gamma stage of large launches
     p = synth.config_c1(ncol=3, perturb=True, formal_solver=solver, nl=0.4)
     q = p.clone()
@@ -260,6 +261,7 @@ def test_cuda_prd_vs_oracle_columns(ndepth, tiled, monkeypatch):
     if tiled:
         monkeypatch.setenv('LWB200_GAMMA_DIRECT', '0')
         monkeypatch.setenv('LWB200_TILE_LEN', '5')
+        monkeypatch.setenv('LWB200_GTILE_LEN', '5')
     p = synth.tiny_prd_problem(ncol=2, perturb=True, ndepth=ndepth)
     q = p.clone()
     ctx = Context(p)
