@@ -6,6 +6,7 @@
 #include "lwb200_profiles.cuh"
 #include "lwb200_pipeline.cuh"
 #include "lwb200_gamma.cuh"
+#include "lwb200_ray2.cuh"
 #include "lwb200_prd.cuh"
 #include "lwb200_stokes.cuh"
 #include "lwb200_ng.cuh"
@@ -277,9 +278,10 @@ struct LwB200Context
     DevBuf<int4> dGTileSlotRows;
     std::vector<int> gTileLa, gLamLa; // host copies: tile -> range of gLamLa (wavelength indices in tile order)
     GammaPlan G{};
-    int gNC = 1, nGTile = 0, nGList = 0, nGListPrd = 0;
+    int gNC = 1, nGTile = 0, nGList = 0, nGListPrd = 0, gWarps = 1, gStage = 0;
     size_t gSmem = 0;
     bool gammaV1 = false; // LWB200_GAMMA_V1=1: the first-generation gamma_kernel (A/B timing aid)
+    bool rayV1 = false;   // LWB200_RAY_V1=1: ray_kernel everywhere (A/B timing aid)
     // ZPlaneDecomposition (lwb200_set_zplane)
     DevBuf<double> zUp, zDown;
     double *zUpHost = nullptr, *zDownHost = nullptr;
@@ -631,10 +633,19 @@ int build_plan(LwB200Context* c)
         int gTileLen = (int)std::max<long long>(1, std::min<long long>(32, ((long long)L * p.Ncol) / (148LL * 12)));
         if (const char* e = std::getenv("LWB200_GTILE_LEN")) // tuning aid
             gTileLen = std::max(1, std::atoi(e));
-        // the warp-per-tile Gamma stage pays off on column stacks; one atmosphere keeps the first generation
-        c->gammaV1 = p.Ncol < 8;
+        // Measured on B200 under ncu (config 3, 128 columns): first generation 1121 us at 21 % resident warps,
+        // second generation 1260 us at 8 % -- fewer instructions (3.4e8 vs 4.3e8) but its shared-memory
+        // accumulators leave too few warps to hide their own latency.  The first generation stays the
+        // default; LWB200_GAMMA_V1=0 selects the second.
+        c->gammaV1 = true;
         if (const char* e = std::getenv("LWB200_GAMMA_V1"))
             c->gammaV1 = std::atoi(e) != 0;
+        if (const char* e = std::getenv("LWB200_RAY_V1"))
+            c->rayV1 = std::atoi(e) != 0;
+        if (const char* e = std::getenv("LWB200_GAMMA_WARPS"))
+            c->gWarps = std::max(1, std::atoi(e));
+        if (const char* e = std::getenv("LWB200_GAMMA_STAGE"))
+            c->gStage = std::atoi(e);
         std::vector<GEntry> gEntries;
         std::vector<GLam> gLam;
         std::vector<GLine> gLine;
@@ -1148,8 +1159,7 @@ int launch_gamma_tiles(LwB200Context* c, const PipelineLists& pl, int nb, int co
     // Measured on B200 (config 3, 512 columns): single-warp CTAs reading populations / ratios through the
     // L1 13.9 ms per launch set, 5-warp CTAs with the column staged in shared memory 14.7 ms -- the staging
     // costs a resident warp and a barrier.  Both stay selectable (tuning aids).
-    static const int envWarps = std::getenv("LWB200_GAMMA_WARPS") ? std::atoi(std::getenv("LWB200_GAMMA_WARPS")) : 1;
-    static const int envStage = std::getenv("LWB200_GAMMA_STAGE") ? std::atoi(std::getenv("LWB200_GAMMA_STAGE")) : 0;
+    const int envWarps = c->gWarps, envStage = c->gStage; // (read from the environment at context creation)
     const bool stage = envStage != 0 && stageBytes + 2 * warpBytes <= budget;
     int warps = (int)((budget - (stage ? stageBytes : 0)) / warpBytes);
     warps = std::max(1, std::min({warps, 8, pl.nGTiles, std::max(1, envWarps)}));
@@ -1230,6 +1240,35 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
                                                                                               contPerBlock, colBase);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
+            // Bezier3, one warp per wavelength, both directions: the two rays of a mu solved together
+            const bool pairKernel = SOLVER == 2 && !MULTI && !storeDepth && !(fsMode & 2) && !c->rayV1;
+            if (pairKernel)
+            {
+                if constexpr (SOLVER == 2 && !MULTI)
+                {
+#ifndef LWB200_RAY3_MINB
+#define LWB200_RAY3_MINB 3
+#endif
+#define LWB200_RAY3(NLV)                                                                                                   \
+    {                                                                                                                      \
+        auto kern = ray_smem_kernel<NCH, NLV, LWB200_RAY3_MINB>;                                                          \
+        if (set_smem_attr(kern, c->device))                                                                                \
+            return 1;                                                                                                      \
+        kern<<<grid, threads, ray_smem_bytes<NCH, NLV>(), s>>>(c->P, list, nLam, perWarp, colBase, lambdaIterate, fsMode); \
+    }
+                    {
+                        switch (q)
+                        {
+                        case 0: LWB200_RAY3(0) break;
+                        case 1: LWB200_RAY3(1) break;
+                        case 2: LWB200_RAY3(2) break;
+                        default: LWB200_RAY3(3) break;
+                        }
+                    }
+#undef LWB200_RAY3
+                }
+            }
+            else
             switch (q)
             {
             case 0:

@@ -241,27 +241,89 @@ __device__ __forceinline__ double pick(const double (&v)[NCH], int jx)
     return x;
 }
 
-// bezier3_sweep: the direction-dependent phase.  Bezier3 coefficients of every point
+// The two special points of a ray -- the first carries the boundary intensity (:551-597), the last is
+// piecewise linear through w2() (:307-321, LwInternal.hpp:90-110) -- depend on chi and S at the two
+// depth pairs (0, 1) and (K - 2, K - 1) only.  They are evaluated ONCE PER WAVELENGTH for all its rays
+// at once, lane r of the warp taking ray r = 2 mu + dir (ray_endpoints), instead of once per ray by every
+// lane: out of the ray loop go two serial chains of ~40 dependent fp64 operations (an exp and two
+// reciprocals) that no depth parallelism could hide.
+struct RayEnds
+{
+    double Iupw; // intensity entering at the first point
+    double aE;   // last point: I = aE * I_upw + bE, psi = pE
+    double bE;
+    double pE;
+};
+
+// depth k of a register array laid over the warp: valid in every lane
+template <int NCH>
+__device__ __forceinline__ double at_depth(const double (&v)[NCH], int k)
+{
+    return __shfl_sync(kFull, pick<NCH>(v, k % NCH), k / NCH);
+}
+
+// chiK / SK: opacity and source function of THIS LANE'S RAY at depths 0, 1, K - 2, K - 1;
+// dsTop = |h_0 - h_1|, dsBot = |h_{K-2} - h_{K-1}|; dir = 1: up-going (starts at the bottom).
+__device__ __forceinline__ RayEnds ray_endpoints(const double (&chiK)[4], const double (&SK)[4], double dsTop,
+                                                 double dsBot, double zmu, int dir, int bcType, double bcB0,
+                                                 double bcB1, double bcValue)
+{
+    RayEnds e;
+    const bool up = dir != 0;
+    // first point and its inner neighbour
+    const double chiS = up ? chiK[3] : chiK[0], chiSN = up ? chiK[2] : chiK[1];
+    const double dsS = up ? dsBot : dsTop;
+    double Iupw = 0.0;
+    if (bcType == 2)
+    {
+        const double dtau_b = 0.5 * zmu * (chiS + chiSN) * dsS;
+        Iupw = bcB0 - (bcB1 - bcB0) / dtau_b;
+    }
+    else if (bcType == 4)
+        Iupw = bcValue;
+    e.Iupw = Iupw;
+    // last point and its upwind neighbour
+    const double chiE = up ? chiK[0] : chiK[3], chiUE = up ? chiK[1] : chiK[2];
+    const double SE = up ? SK[0] : SK[3], SUE = up ? SK[1] : SK[2];
+    const double dsE = up ? dsTop : dsBot;
+    const double dt = 0.5 * zmu * (chiE + chiUE) * dsE;
+    double w0, w1;
+    if (dt < 5.0E-4)
+    {
+        w0 = dt * (1.0 - 0.5 * dt);
+        w1 = (dt * dt) * (0.5 - dt * (1.0 / 3.0));
+    }
+    else if (dt > 50.0)
+        w0 = w1 = 1.0;
+    else
+    {
+        const double ex = exp(-dt);
+        w0 = 1.0 - ex;
+        w1 = w0 - dt * ex;
+    }
+    const double dS = (SE - SUE) / dt;
+    e.aE = 1.0 - w0;
+    e.bE = w0 * SE - w1 * dS;
+    e.pE = (w0 - w1 / dt) / chiE;
+    return e;
+}
+
+// bezier3_coeffs: the direction-dependent phase.  Bezier3 coefficients of every point
 // (Bezier.hpp:81-127; both optical-depth regimes through selects, dt > 30 is the closed form
-// with edt = 0 term for term), then the two special points of the ray as warp-uniform
-// fix-ups computed once per ray instead of once per point: the last point is piecewise
-// linear through w2() (:307-321, LwInternal.hpp:90-110), the first carries the boundary
-// intensity (:551-597).  Outputs I and psi = Psi*/chi.
+// with edt = 0 term for term), then the two special points of the ray patched in from `ends`
+// (this ray's RayEnds, already broadcast).  Outputs the recurrence I_k = a_k I_upwind + b_k and
+// psi = Psi* / chi; padding lanes carry the identity.
 template <int NCH, bool DOWN, bool MULTI>
-__device__ __forceinline__ void bezier3_sweep(DepthComm<MULTI>& cm, const GeometryR<NCH>& g, const double (&chi)[NCH],
-                                              const double (&S)[NCH], const double (&rchi)[NCH],
-                                              const RayPre<NCH>& r, double zmu, int bcType, double bcB0,
-                                              double bcB1, double bcValue, double (&I)[NCH],
-                                              double (&psi)[NCH])
+__device__ __forceinline__ void bezier3_coeffs(DepthComm<MULTI>& cm, const GeometryR<NCH>& g, const double (&S)[NCH],
+                                               const double (&rchi)[NCH], const RayPre<NCH>& r, const RayEnds& ends,
+                                               double (&a)[NCH], double (&b)[NCH], double (&psi)[NCH])
 {
     const int lane = cm.lane_global();
     const int K = g.K;
     const int kS = DOWN ? 0 : K - 1;
     const int kE = DOWN ? K - 1 : 0;
     // upwind neighbours along the ray
-    double SU[NCH], dtU[NCH], rdtU[NCH], DSU[NCH], chiP[NCH], chiN[NCH];
-    shift_prev<NCH>(cm, chi, chiP);
-    shift_next<NCH>(cm, chi, chiN);
+    double SU[NCH], dtU[NCH], rdtU[NCH], DSU[NCH];
     if (DOWN)
     {
         shift_prev<NCH>(cm, S, SU);
@@ -282,12 +344,12 @@ __device__ __forceinline__ void bezier3_sweep(DepthComm<MULTI>& cm, const Geomet
         }
     }
 
-    double a[NCH], b[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j)
     {
         const double dt = dtU[j], rdt = rdtU[j];
-        const double ex = exp_fast(-clamp_dt(dt));
+        // (an optical depth beyond 30 takes edt = 0; the clamp only keeps exp_fast in its range)
+        const double ex = exp_fast(-((dt > 700.0) ? 700.0 : dt));
         const double dt2 = dt * dt, dt3 = dt2 * dt;
         const double edtC = sel(dt > 30.0, 0.0, ex);
         const double rdt3 = rdt * rdt * rdt;
@@ -311,71 +373,167 @@ __device__ __forceinline__ void bezier3_sweep(DepthComm<MULTI>& cm, const Geomet
         psi[j] = (beta + delta) * rchi[j];
     }
 
-    // ---- last point of the ray: piecewise linear
+    // ---- the two special points of the ray, and the identity in the padding lanes
+    const int jE = kE % NCH, laneE = kE / NCH, jS = kS % NCH, laneS = kS / NCH;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
     {
-        const int jE = kE % NCH, laneE = kE / NCH;
-        const double chiE = pick<NCH>(chi, jE), SE = pick<NCH>(S, jE), SUE = pick<NCH>(SU, jE);
-        const double chiUE = DOWN ? pick<NCH>(chiP, jE) : pick<NCH>(chiN, jE);
-        const double dsUE = DOWN ? pick<NCH>(g.dsfP, jE) : pick<NCH>(g.dsf, jE);
-        const double dt = 0.5 * zmu * (chiE + chiUE) * dsUE;
-        const double rdt = rcp_fast(dt);
-        const double ex = exp_fast(-clamp_dt(dt));
-        const bool tayE = dt < 5.0E-4, thickE = dt > 50.0;
-        const double w0m = 1.0 - ex;
-        const double w0 = sel(tayE, dt * (1.0 - 0.5 * dt), sel(thickE, 1.0, w0m));
-        const double w1 = sel(tayE, (dt * dt) * (0.5 - dt * (1.0 / 3.0)), sel(thickE, 1.0, w0m - dt * ex));
-        const double dS = (SE - SUE) * rdt;
-        const double aaE = 1.0 - w0;
-        const double bbE = w0 * SE - w1 * dS;
-        const double ppE = (w0 - w1 * rdt) * pick<NCH>(rchi, jE);
-        const bool hit = lane == laneE;
+        const bool last = lane == laneE && j == jE, first = lane == laneS && j == jS;
+        const bool pad = !DOWN && lane * NCH + j >= K; // (DOWN: padding comes after every real point, never used)
+        a[j] = first ? 0.0 : (last ? ends.aE : (pad ? 1.0 : a[j]));
+        b[j] = first ? ends.Iupw : (last ? ends.bE : (pad ? 0.0 : b[j]));
+        psi[j] = first ? 0.0 : (last ? ends.pE : psi[j]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The same Bezier3 step split ONCE MORE, by what it depends on.  Alpha .. delta and exp(-dt) are
+// functions of the optical depth of an INTERVAL (k, k + 1), whichever way a ray crosses it; the
+// recurrence coefficient of a point regroups as
+//     b = (alpha + gamma) S_uw + (beta + delta) S_0 + gamma dt/3 S'_uw - delta dt/3 S'_0
+// (C_uw = S_uw + dt/3 S'_uw, C_0 = S_0 - dt/3 S'_0 along the ray, Bezier.hpp:81-127 / FormalScalar.cpp:276-281),
+// so the expensive part -- the exp, the four cubic-over-cubic coefficients in both regimes -- is
+// evaluated per interval in array-forward orientation by ONE piece of code (interval_coeffs), shared
+// by the up and the down ray of a mu whenever they share opacities, and what is left per direction is
+// a handful of fused multiply-adds on shifted copies (ray_down / ray_up).  Besides the arithmetic saved,
+// this keeps the hot loop of the ray kernels small: measured with ncu on B200, the loop with both
+// directions' full coefficient code inlined (~40 KB of SASS) did not fit the 32 KB instruction cache
+// and stalled on instruction fetch as often as on the fp64 pipe.
+template <int NCH>
+struct RayCoef
+{
+    double ed[NCH]; // exp(-dt) of the interval (k, k + 1) (its Taylor / thick-limit forms as Bezier3_coeffs)
+    double AG[NCH]; // alpha + gamma
+    double GD[NCH]; // gamma dt / 3
+    double BD[NCH]; // beta + delta
+    double DD[NCH]; // delta dt / 3
+};
+
+template <int NCH>
+__device__ __forceinline__ void interval_coeffs(const RayPre<NCH>& r, RayCoef<NCH>& c)
+{
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+    {
+        const double dt = r.dtf[j], rdt = r.rdtf[j];
+        // (an optical depth beyond 30 takes edt = 0; the clamp only keeps exp_fast in its range)
+        const double ex = exp_fast(-((dt > 700.0) ? 700.0 : dt));
+        const double dt2 = dt * dt, dt3 = dt2 * dt;
+        const double edtC = sel(dt > 30.0, 0.0, ex);
+        const double rdt3 = rdt * rdt * rdt;
+        const double alphaC = (6.0 - edtC * (6.0 + 6.0 * dt + 3.0 * dt2 + dt3)) * rdt3;
+        const double betaC = (6.0 * edtC - 6.0 + 6.0 * dt - 3.0 * dt2 + dt3) * rdt3;
+        const double gammaC = 3.0 * (2.0 * dt - 6.0 + edtC * (6.0 + 4.0 * dt + dt2)) * rdt3;
+        const double deltaC = 3.0 * (6.0 - 4.0 * dt + dt2 - 2.0 * edtC * (3.0 + dt)) * rdt3;
+        const double edtT = 1.0 - dt + 0.5 * dt2 - dt3 * (1.0 / 6.0);
+        const double alphaT = 0.25 * dt - 0.2 * dt2 + dt3 * (1.0 / 12.0);
+        const double betaT = 0.25 * dt - 0.05 * dt2 + dt3 * (1.0 / 120.0);
+        const double gammaT = 0.25 * dt - 0.15 * dt2 + 0.05 * dt3;
+        const double deltaT = 0.25 * dt - 0.1 * dt2 + 0.025 * dt3;
+        const bool tay = dt < 5e-2;
+        const double alpha = sel(tay, alphaT, alphaC), beta = sel(tay, betaT, betaC);
+        const double gamma = sel(tay, gammaT, gammaC), delta = sel(tay, deltaT, deltaC);
+        const double dt3rd = dt * (1.0 / 3.0);
+        c.ed[j] = sel(tay, edtT, edtC);
+        c.AG[j] = alpha + gamma;
+        c.GD[j] = gamma * dt3rd;
+        c.BD[j] = beta + delta;
+        c.DD[j] = delta * dt3rd;
+    }
+}
+
+// down-going ray (k ascending): point k is reached through the interval (k - 1, k)
+template <int NCH>
+__device__ __forceinline__ void ray_down(const RayCoef<NCH>& c, const double (&S)[NCH], const double (&DSf)[NCH],
+                                         const double (&rchi)[NCH], const RayEnds& ends, int lane, int laneE, int jE,
+                                         double (&a)[NCH], double (&b)[NCH], double (&psi)[NCH])
+{
+    double X[NCH], edP[NCH], XP[NCH], BDP[NCH], DDP[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+        X[j] = fma(c.AG[j], S[j], c.GD[j] * DSf[j]);
+    shift_prev<NCH>(c.ed, edP);
+    shift_prev<NCH>(X, XP);
+    shift_prev<NCH>(c.BD, BDP);
+    shift_prev<NCH>(c.DD, DDP);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+    {
+        a[j] = edP[j];
+        b[j] = fma(-DDP[j], DSf[j], fma(BDP[j], S[j], XP[j]));
+        psi[j] = BDP[j] * rchi[j];
+    }
+    // first point: boundary intensity; last point: piecewise linear (ray_endpoints)
+    if (lane == 0)
+    {
+        a[0] = 0.0;
+        b[0] = ends.Iupw;
+        psi[0] = 0.0;
+    }
+    if (lane == laneE)
+    {
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
             if (j == jE)
             {
-                a[j] = sel(hit, aaE, a[j]);
-                b[j] = sel(hit, bbE, b[j]);
-                psi[j] = sel(hit, ppE, psi[j]);
+                a[j] = ends.aE;
+                b[j] = ends.bE;
+                psi[j] = ends.pE;
             }
     }
-    // ---- first point: boundary intensity
+}
+
+// up-going ray (k descending): point k is reached through the interval (k, k + 1); derivatives along the
+// ray are the negatives of the forward ones
+template <int NCH>
+__device__ __forceinline__ void ray_up(const RayCoef<NCH>& c, const double (&S)[NCH], const double (&SN)[NCH],
+                                       const double (&DSf)[NCH], const double (&rchi)[NCH], const RayEnds& ends,
+                                       int lane, int laneE, int jE, double (&a)[NCH], double (&b)[NCH],
+                                       double (&psi)[NCH])
+{
+    double DSfN[NCH];
+    shift_next<NCH>(DSf, DSfN);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
     {
-        const int jS = kS % NCH, laneS = kS / NCH;
-        double Iupw = bcValue;
-        if (bcType == 2)
-        {
-            const double chiDS = DOWN ? pick<NCH>(chiN, jS) : pick<NCH>(chiP, jS);
-            const double dsDS = DOWN ? pick<NCH>(g.dsf, jS) : pick<NCH>(g.dsfP, jS);
-            const double dtau_b = 0.5 * zmu * (pick<NCH>(chi, jS) + chiDS) * dsDS;
-            Iupw = bcB0 - (bcB1 - bcB0) * rcp_fast(dtau_b);
-        }
-        const bool hit = lane == laneS;
+        a[j] = c.ed[j];
+        b[j] = fma(c.DD[j], DSf[j], fma(c.BD[j], S[j], fma(-c.GD[j], DSfN[j], c.AG[j] * SN[j])));
+        psi[j] = c.BD[j] * rchi[j];
+    }
+    // last point (the top): piecewise linear; first point (the bottom): boundary intensity; the padding
+    // beyond the bottom comes first in this sweep and must carry the identity
+    if (lane == 0)
+    {
+        a[0] = ends.aE;
+        b[0] = ends.bE;
+        psi[0] = ends.pE;
+    }
+    if (lane >= laneE)
+    {
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
-            if (j == jS)
+        {
+            const bool first = lane == laneE && j == jE;
+            const bool pad = lane > laneE || j > jE;
+            if (first || pad)
             {
-                a[j] = sel(hit, 0.0, a[j]);
-                b[j] = sel(hit, Iupw, b[j]);
-                psi[j] = sel(hit, 0.0, psi[j]);
+                a[j] = first ? 0.0 : 1.0;
+                b[j] = first ? ends.Iupw : 0.0;
+                psi[j] = 0.0;
             }
-    }
-    if (DOWN)
-    {
-        // padding lanes (k >= K) come after every real point: whatever they hold is never used
-        affine_scan<NCH, true>(cm, a, b, I);
-    }
-    else
-    {
-        // padding lanes come first in the sweep: they must carry the identity
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
-        {
-            const bool valid = lane * NCH + j < K;
-            a[j] = sel(valid, a[j], 1.0);
-            b[j] = sel(valid, b[j], 0.0);
         }
-        affine_scan<NCH, false>(cm, a, b, I);
     }
+}
+
+// bezier3_sweep: coefficients + scan (kept for callers that do not pipeline the two).
+template <int NCH, bool DOWN, bool MULTI>
+__device__ __forceinline__ void bezier3_sweep(DepthComm<MULTI>& cm, const GeometryR<NCH>& g, const double (&S)[NCH],
+                                              const double (&rchi)[NCH], const RayPre<NCH>& r, const RayEnds& ends,
+                                              double (&I)[NCH], double (&psi)[NCH])
+{
+    double a[NCH], b[NCH];
+    bezier3_coeffs<NCH, DOWN>(cm, g, S, rchi, r, ends, a, b, psi);
+    affine_scan<NCH, DOWN>(cm, a, b, I);
 }
 
 // linear (SOLVER 0) and besser (SOLVER 1): local stencils only

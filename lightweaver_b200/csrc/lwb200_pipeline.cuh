@@ -135,6 +135,10 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
     constexpr int NLA = NL > 0 ? NL : 1;
     constexpr int NPAIR = NL > 1 ? NL * (NL - 1) / 2 : 1;
     __shared__ double commBuf[MULTI ? 7 * 8 : 1];
+    // chiC, etaC, scaJ and the line coefficients at the depths 0, 1, K - 2, K - 1 (ray_endpoints):
+    // per warp when a warp owns a wavelength, once per CTA when the CTA does
+    constexpr int NEND = 3 + 2 * (NL > 0 ? NL : 1);
+    __shared__ double endBufAll[MULTI ? 1 : 4][4][NEND];
     const int K = P.K, M = P.M, L = P.L;
     const int cb = blockIdx.y, col = column_of(P, colBase + cb);
     // warp index made provably warp-uniform: every loop below stays convergent
@@ -153,6 +157,9 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
 
     GeometryR<NCH> g;
     load_geometry_r<NCH>(cm, g, P.height + (size_t)col * K, K);
+    double(*endBuf)[NEND] = endBufAll[MULTI ? 0 : (warp & 3)];
+    const double dsTop = fabs(__ldg(P.height + (size_t)col * K) - __ldg(P.height + (size_t)col * K + 1));
+    const double dsBot = fabs(__ldg(P.height + (size_t)col * K + K - 2) - __ldg(P.height + (size_t)col * K + K - 1));
     const double* Tcol = P.temperature + (size_t)col * K;
     const double* ncol = P.n + (size_t)col * P.NlevTot * K;
 
@@ -180,10 +187,12 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
         // line slots: chi = chiC + sum_l cX_l phi_l, eta = etaC + sum_l cE_l phi_l
         double cX[NLA][NCH], cE[NLA][NCH];
         const double* ph[NLA];
+        const double* phRay[NLA]; // the same profile rows without this lane's depth offset
 #pragma unroll
         for (int l = 0; l < NLA; ++l)
         {
             ph[l] = P.phi;
+            phRay[l] = P.phi;
 #pragma unroll
             for (int j = 0; j < NCH; ++j)
                 cX[l][j] = cE[l][j] = 0.0;
@@ -194,7 +203,8 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
                 const double vB = hc_4pi * (ll.lambda0 * rlambda) * ll.Bij;
                 const double gS = ll.Bji_Bij;
                 const double* rho = (ll.rhoOff >= 0) ? P.rhoPrd + ll.rhoOff + (size_t)col * ll.rhoColStride : nullptr;
-                ph[l] = P.phi + ll.phiOff + (size_t)col * ll.phiColStride + lane * NCH;
+                phRay[l] = P.phi + ll.phiOff + (size_t)col * ll.phiColStride;
+                ph[l] = phRay[l] + lane * NCH;
 #pragma unroll
                 for (int j = 0; j < NCH; ++j)
                 {
@@ -223,6 +233,69 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
             Bbot0 = planck_nu(__ldg(Tcol + K - 1), lambda);
             Bbot1 = planck_nu(__ldg(Tcol + K - 2), lambda);
         }
+
+        // ---- Bezier3: boundary intensity and last-point coefficients of up to 32 rays at once, lane r taking
+        // ray rayBase + r = 2 mu + dir (ray_endpoints, lwb200_fsm.cuh)
+        RayEnds endsV{0.0, 0.0, 0.0, 0.0};
+        int endsBase = -1;
+        auto compute_ends = [&](int rayBase) {
+            const int kq[4] = {0, 1, K - 2, K - 1};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (lane == kq[q] / NCH)
+                {
+                    const int jq = kq[q] % NCH;
+                    endBuf[q][0] = pick<NCH>(chiC, jq);
+                    endBuf[q][1] = pick<NCH>(etaC, jq);
+                    endBuf[q][2] = pick<NCH>(scaJ, jq);
+#pragma unroll
+                    for (int l = 0; l < NLA; ++l)
+                    {
+                        endBuf[q][3 + 2 * l] = pick<NCH>(cX[l], jq);
+                        endBuf[q][4 + 2 * l] = pick<NCH>(cE[l], jq);
+                    }
+                }
+            if (MULTI)
+                __syncthreads();
+            else
+                __syncwarp();
+            const int rr = rayBase + lane_id();
+            if (rr < 2 * M)
+            {
+                const int mu = rr >> 1, dir = rr & 1;
+                const double zmu = 1.0 / __ldg(P.muz + mu);
+                double chiK[4], SK[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                {
+                    double c = endBuf[q][0], e = endBuf[q][1];
+                    if (NL > 0)
+                    {
+#pragma unroll
+                        for (int l = 0; l < NLA; ++l)
+                        {
+                            const double pq = __ldg(phRay[l] + (size_t)rr * K + kq[q]);
+                            c = fma(endBuf[q][3 + 2 * l], pq, c);
+                            e = fma(endBuf[q][4 + 2 * l], pq, e);
+                        }
+                    }
+                    chiK[q] = c;
+                    SK[q] = (e + endBuf[q][2]) / c;
+                }
+                const int bcType = dir ? P.lowerBc : P.upperBc;
+                double bcValue = 0.0;
+                if (bcType == 4)
+                    bcValue = dir ? P.lowerBcData[((size_t)col * L + la) * P.NlowerBcMu + P.lowerBcIdx[mu * 2 + 1]]
+                                  : P.upperBcData[((size_t)col * L + la) * P.NupperBcMu + P.upperBcIdx[mu * 2 + 0]];
+                endsV = ray_endpoints(chiK, SK, dsTop, dsBot, zmu, dir, bcType, dir ? Bbot0 : Btop0,
+                                      dir ? Bbot1 : Btop1, bcValue);
+            }
+            if (MULTI)
+                __syncthreads();
+            else
+                __syncwarp();
+            endsBase = rayBase;
+        };
 
         // ---- moments over the rays of this wavelength
         //   mJ = sum w I, mP = sum w Psi*, mW[l] = sum w p_l, mA[l] = sum w p_l I,
@@ -357,35 +430,46 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
                         }
                     }
                 }
-                int bcType;
-                double bcB0, bcB1, bcValue = 0.0;
-                if (dir == 1)
-                {
-                    bcType = P.lowerBc;
-                    bcB0 = Bbot0;
-                    bcB1 = Bbot1;
-                    if (bcType == 4)
-                        bcValue = P.lowerBcData[((size_t)col * L + la) * P.NlowerBcMu + P.lowerBcIdx[mu * 2 + 1]];
-                }
-                else
-                {
-                    bcType = P.upperBc;
-                    bcB0 = Btop0;
-                    bcB1 = Btop1;
-                    if (bcType == 4)
-                        bcValue = P.upperBcData[((size_t)col * L + la) * P.NupperBcMu + P.upperBcIdx[mu * 2 + 0]];
-                }
                 double I[NCH], psi[NCH];
                 if (SOLVER == 2)
                 {
+                    const int ray = 2 * mu + dir;
+                    if (endsBase < 0 || ray >= endsBase + 32)
+                        compute_ends(ray & ~31);
+                    const int rl = ray - endsBase;
+                    RayEnds ends;
+                    ends.Iupw = __shfl_sync(kFull, endsV.Iupw, rl);
+                    ends.aE = __shfl_sync(kFull, endsV.aE, rl);
+                    ends.bE = __shfl_sync(kFull, endsV.bE, rl);
+                    ends.pE = __shfl_sync(kFull, endsV.pE, rl);
                     if (dir == 0)
-                        bezier3_sweep<NCH, true>(cm, g, chi, S, rchi, pre, zmu, bcType, bcB0, bcB1, bcValue, I, psi);
+                        bezier3_sweep<NCH, true>(cm, g, S, rchi, pre, ends, I, psi);
                     else
-                        bezier3_sweep<NCH, false>(cm, g, chi, S, rchi, pre, zmu, bcType, bcB0, bcB1, bcValue, I, psi);
+                        bezier3_sweep<NCH, false>(cm, g, S, rchi, pre, ends, I, psi);
                 }
                 else
+                {
+                    int bcType;
+                    double bcB0, bcB1, bcValue = 0.0;
+                    if (dir == 1)
+                    {
+                        bcType = P.lowerBc;
+                        bcB0 = Bbot0;
+                        bcB1 = Bbot1;
+                        if (bcType == 4)
+                            bcValue = P.lowerBcData[((size_t)col * L + la) * P.NlowerBcMu + P.lowerBcIdx[mu * 2 + 1]];
+                    }
+                    else
+                    {
+                        bcType = P.upperBc;
+                        bcB0 = Btop0;
+                        bcB1 = Btop1;
+                        if (bcType == 4)
+                            bcValue = P.upperBcData[((size_t)col * L + la) * P.NupperBcMu + P.upperBcIdx[mu * 2 + 0]];
+                    }
                     local_stencil_ray<NCH, SOLVER>(cm, g, chi, S, rchi, muz, dir == 0, bcType, bcB0, bcB1, bcValue, I,
                                                    psi);
+                }
 
                 if (lane == 0)
                     P.I[((size_t)col * L + la) * M + mu] = I[0];

@@ -65,6 +65,7 @@ def test_cuda_vs_oracle_multicolumn_c1(solver, tileLen, monkeypatch):
         monkeypatch.setenv('LWB200_TILE_LEN', str(tileLen))
         monkeypatch.setenv('LWB200_GTILE_LEN', str(tileLen))
         monkeypatch.setenv('LWB200_GAMMA_DIRECT', '0')   # the tiled Gamma stage of large launches
+        monkeypatch.setenv('LWB200_GAMMA_V1', '1' if tileLen == 32 else '0')   # first / second generation
     p = synth.config_c1(ncol=3, perturb=True, formal_solver=solver, nl=0.4)
     q = p.clone()
     ctx = Context(p)
@@ -262,6 +263,7 @@ def test_cuda_prd_vs_oracle_columns(ndepth, tiled, monkeypatch):
         monkeypatch.setenv('LWB200_GAMMA_DIRECT', '0')
         monkeypatch.setenv('LWB200_TILE_LEN', '5')
         monkeypatch.setenv('LWB200_GTILE_LEN', '5')
+        monkeypatch.setenv('LWB200_GAMMA_V1', '0')
     p = synth.tiny_prd_problem(ncol=2, perturb=True, ndepth=ndepth)
     q = p.clone()
     ctx = Context(p)
@@ -781,10 +783,21 @@ def _overlap_problem(nlines):
     return synth.build_problem([a, b], nrays=3, perturb=True, ncol=2)
 
 
-@pytest.mark.parametrize('nlines', [1, 2, 3, 4])
-def test_overlapping_lines_moment_and_general_kernels(nlines):
+@pytest.mark.parametrize('nlines,gammaStage', [(1, None), (2, None), (3, None), (4, None), (1, 'v2'), (2, 'v2'), (3, 'v2'),
+                                               (2, 'v2staged'), (3, 'v1')])
+def test_overlapping_lines_moment_and_general_kernels(nlines, gammaStage, monkeypatch):
     """Up to 3 overlapping lines go through the moment kernel, more through the general
-    kernel; both must match the oracle, and each other."""
+    kernel; both must match the oracle, and each other.  gammaStage: force the tiled Gamma stage of
+    large launches (first generation / second generation / second generation with several warps per
+    CTA and the column staged in shared memory) instead of the per-wavelength one."""
+    if gammaStage:
+        monkeypatch.setenv('LWB200_GAMMA_DIRECT', '0')
+        monkeypatch.setenv('LWB200_GTILE_LEN', '6')
+        monkeypatch.setenv('LWB200_TILE_LEN', '6')
+        monkeypatch.setenv('LWB200_GAMMA_V1', '1' if gammaStage == 'v1' else '0')
+        if gammaStage == 'v2staged':
+            monkeypatch.setenv('LWB200_GAMMA_WARPS', '4')
+            monkeypatch.setenv('LWB200_GAMMA_STAGE', '1')
     p = _overlap_problem(nlines)
     q = p.clone()
     g = p.clone()
