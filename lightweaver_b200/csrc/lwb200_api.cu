@@ -274,7 +274,7 @@ struct LwB200Context
     DevBuf<GEntry> dGEntries;
     DevBuf<GLam> dGLam;
     DevBuf<GLine> dGLine;
-    DevBuf<int> dGTileLa, dGTileSlotOff, dGList, dGListPrd;
+    DevBuf<int> dGTileLa, dGTileSlotOff, dGList, dGListPrd, dGLamOfLa;
     DevBuf<int4> dGTileSlotRows;
     std::vector<int> gTileLa, gLamLa; // host copies: tile -> range of gLamLa (wavelength indices in tile order)
     GammaPlan G{};
@@ -619,7 +619,9 @@ int build_plan(LwB200Context* c)
     // ---- Gamma stage, second generation: tiles of the moment wavelengths (kinds 0..3) and the compact
     // per-wavelength tables its warps read (lwb200_gamma.cuh)
     {
-        const int NCg = std::min(4, (K + 31) / 32); // depths per lane; a warp covers 32 * NCg depths
+        int NCg = 1; // depths per lane; a warp covers 32 * NCg depths
+        if (const char* e = std::getenv("LWB200_GAMMA_NC")) // tuning aid
+            NCg = std::max(1, std::min(4, std::atoi(e)));
         c->gNC = NCg;
         const size_t rowBytes = (size_t)32 * NCg * sizeof(double);
         int maxAct = 1;
@@ -633,11 +635,12 @@ int build_plan(LwB200Context* c)
         int gTileLen = (int)std::max<long long>(1, std::min<long long>(32, ((long long)L * p.Ncol) / (148LL * 12)));
         if (const char* e = std::getenv("LWB200_GTILE_LEN")) // tuning aid
             gTileLen = std::max(1, std::atoi(e));
-        // Measured on B200 under ncu (config 3, 128 columns): first generation 1121 us at 21 % resident warps,
-        // second generation 1260 us at 8 % -- fewer instructions (3.4e8 vs 4.3e8) but its shared-memory
-        // accumulators leave too few warps to hide their own latency.  The first generation stays the
-        // default; LWB200_GAMMA_V1=0 selects the second.
-        c->gammaV1 = true;
+        // Measured on B200 under ncu (config 3, 128 columns): first generation 1114 us at 21 % resident warps;
+        // second generation with 3 depths per lane 1260 us at 8 % (fewer instructions, 3.4e8 vs 4.3e8, but its
+        // shared-memory accumulators leave too few warps to hide their own latency), with ONE depth per lane
+        // (a warp per 32 depths, 96 registers, 13 KB of shared memory) 902 us at 22 %.  LWB200_GAMMA_V1=1
+        // selects the first generation, LWB200_GAMMA_NC the depths per lane.
+        c->gammaV1 = false;
         if (const char* e = std::getenv("LWB200_GAMMA_V1"))
             c->gammaV1 = std::atoi(e) != 0;
         if (const char* e = std::getenv("LWB200_RAY_V1"))
@@ -796,6 +799,14 @@ int build_plan(LwB200Context* c)
         c->G.tileSlotRows = c->dGTileSlotRows.p;
         c->G.maxSlots = gMaxSlots;
         c->G.maxNlevel = maxNlevel;
+        {
+            std::vector<int> lamOfLa(L, -1);
+            for (size_t q = 0; q < c->gLamLa.size(); ++q)
+                lamOfLa[c->gLamLa[q]] = (int)q;
+            if (c->dGLamOfLa.upload(lamOfLa))
+                return 1;
+            c->G.lamOfLa = c->dGLamOfLa.p;
+        }
     }
 
     // PRD lines (PrdTemplates.hpp:186-211: active atoms first, then detailed ones) and the packed
@@ -1163,6 +1174,8 @@ int launch_gamma_tiles(LwB200Context* c, const PipelineLists& pl, int nb, int co
     const bool stage = envStage != 0 && stageBytes + 2 * warpBytes <= budget;
     int warps = (int)((budget - (stage ? stageBytes : 0)) / warpBytes);
     warps = std::max(1, std::min({warps, 8, pl.nGTiles, std::max(1, envWarps)}));
+    if (!stage)
+        warps = 1; // (the unstaged kernel is compiled for single-warp CTAs)
     const size_t smem = (stage ? stageBytes : 0) + warps * warpBytes;
     const int wd = (int)(warpBytes / sizeof(double));
 #define LWB200_GT(NCV)                                                                                           \
@@ -1236,8 +1249,8 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
             const int nw = c->nwarps;
             dim3 grid(MULTI ? nLam : (nLam + nw * perWarp - 1) / (nw * perWarp), nb);
             const int* list = pl.kindLam[q];
-            continuum_kernel<<<dim3((nLam + contPerBlock - 1) / contPerBlock, nb), KP, 0, s>>>(c->P, list, nLam,
-                                                                                              contPerBlock, colBase);
+            continuum_table_kernel<<<dim3((nLam + contPerBlock - 1) / contPerBlock, nb), KP, 0, s>>>(
+                c->P, c->G, list, nLam, contPerBlock, colBase);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
             // Bezier3, one warp per wavelength, both directions: the two rays of a mu solved together
@@ -1681,6 +1694,7 @@ int lwb200_destroy(LwB200Context* c)
     c->dGTileSlotRows.release();
     c->dGList.release();
     c->dGListPrd.release();
+    c->dGLamOfLa.release();
     delete c;
     return 0;
 }

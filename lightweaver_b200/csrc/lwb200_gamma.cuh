@@ -90,6 +90,7 @@ struct GammaPlan
     const GLam* lam;          // [sum over tiles of their wavelengths], tile order
     const GLine* line;        // [same][3]
     const int* tileLa;        // [Ntile + 1] offsets into lam
+    const int* lamOfLa;       // [L] position of a wavelength in `lam` (-1: not a moment wavelength)
     const int* tileSlotOff;   // [Ntile + 1]
     const int4* tileSlotRows; // per slot: rows of the packed accumulator for Gamma(i,j), Gamma(j,i), Rij, Rji (-1: none)
     int maxSlots, maxNlevel;
@@ -392,8 +393,11 @@ __device__ __forceinline__ void gamma_lambda_w(const DevProblem& P, const GLam& 
 // laMask / prdOnly: the rates-only pass of the PRD sub-iterations over the masked wavelengths.
 // NC: depths per lane (the chunk of a warp is 32 * NC depths; blockIdx.z walks the chunks of a column).
 // A CTA is blockDim.x / 32 warps on consecutive tiles of tileList, all in column blockIdx.y.
+#ifndef LWB200_GTILE_MINB
+#define LWB200_GTILE_MINB 20
+#endif
 template <int NC, bool STAGE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(STAGE ? 256 : 32, STAGE ? 1 : (NC == 1 ? LWB200_GTILE_MINB : 8))
 gamma_tile_kernel(const DevProblem P, const GammaPlan G, const int* __restrict__ tileList, int nTiles, int laLo,
                   int laHi, int colBase, const unsigned char* __restrict__ laMask, int prdOnly, int warpSmemDoubles)
 {
@@ -541,6 +545,51 @@ gamma_tile_kernel(const DevProblem P, const GammaPlan G, const int* __restrict__
                     atomicAdd(P.accum + ((size_t)col * P.AccTot + rows[q]) * K + k, v);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Stage 1 with the planner's tables: chiC, etaC of the wavelengths of one kind (continuum_kernel,
+// lwb200_pipeline.cuh, computes the per-wavelength scalars -- two divisions -- and decodes 80-byte
+// DevEntry records in every thread; here they come from GLam / GEntry and 1/T is taken once per thread).
+// Grid (groups of `perBlock` wavelengths of the list, columns of the batch), one thread per depth.
+__global__ void continuum_table_kernel(const DevProblem P, const GammaPlan G, const int* __restrict__ lamList, int nLam,
+                                       int perBlock, int colBase)
+{
+    const int K = P.K, L = P.L;
+    const int cb = blockIdx.y, col = column_of(P, colBase + cb);
+    const int k = threadIdx.x;
+    if (k >= K)
+        return;
+    const double rT = 1.0 / __ldg(P.temperature + (size_t)col * K + k);
+    const double* ncol = P.n + (size_t)col * P.NlevTot * K + k;
+    const double* gcol = P.gRatio + (size_t)col * K + k;
+    const size_t gStride = (size_t)P.Ncol * K;
+    const int qBeg = blockIdx.x * perBlock, qEnd = min(nLam, qBeg + perBlock);
+    for (int q = qBeg; q < qEnd; ++q)
+    {
+        const int la = lamList[q];
+        const GLam gl = G.lam[G.lamOfLa[la]];
+        const size_t rowLK = ((size_t)col * L + la) * K + k;
+        double chiC = __ldg(P.chiBg + rowLK);
+        double etaC = __ldg(P.etaBg + rowLK);
+        const double expfac = exp_fast_underflow(-gl.hc_kl * rT);
+        const GEntry* ents = G.entries + gl.eOff;
+        for (int e = 0; e < gl.eCnt; ++e)
+        {
+            const GEntry t = ents[e];
+            if (t.type == 0)
+                continue;
+            const double gk = __ldg(gcol + (size_t)t.cont * gStride) * expfac;
+            const double Vji = gk * t.al;
+            const double ni = __ldg(ncol + (size_t)t.levI * K);
+            const double nj = __ldg(ncol + (size_t)t.levJ * K);
+            chiC += ni * t.al - nj * Vji;
+            etaC += nj * (gl.hcl * Vji);
+        }
+        const size_t o = ((size_t)cb * L + la) * K + k;
+        P.chiC[o] = chiC;
+        P.etaC[o] = etaC;
     }
 }
 
