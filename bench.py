@@ -391,7 +391,7 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     lambda_sharded = world > 1 and not column_sharded
 
-    def step():
+    def plain_step():
         if stokes:
             capi.check(ctx.lib.lwb200_formal_sol_full_stokes(ctx._h, 1, 0, None, None))
             return
@@ -406,15 +406,37 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
         else:
             ctx.stat_eq_device(wait=False)
 
+    # A 1D atmosphere is ~15 launches of 10-100 us: the whole iteration (with the all-reduce of a wavelength
+    # shard) is captured once into a CUDA graph and replayed.  Column stacks (100 ms steps) launch directly.
+    graphed = None
+    use_graph = not column_sharded and not stokes and not with_prd
+
+    def step():
+        if graphed is not None:
+            graphed.replay()
+        else:
+            plain_step()
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     launches = 0
+    kernel_ms = []
     for _ in range(max(args.warmup, 3)):
-        step()
+        plain_step()
     barrier()
+    if use_graph:
+        for _ in range(5):   # (the launch-set time is not available inside a graph: taken from direct launches)
+            plain_step()
+            kernel_ms.append(ctx.kernel_time_ms())
+        barrier()
+    if use_graph:
+        graphed = sharding.GraphedIteration(shard, group=None)
+        for _ in range(3):
+            step()
+        barrier()
     # kernels launched per step, counted by the library itself (lwb200_work_stats)
     per_step = 0
     if stokes:
@@ -439,14 +461,14 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
     clocks = ClockSampler(local_rank)
     clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms = []
     barrier()
     for s in range(args.steps):
         flush.zero_()  # untimed L2 flush between steps
         ev[s][0].record(stream)
         step()
         ev[s][1].record(stream)
-        kernel_ms.append(ctx.kernel_time_ms())
+        if graphed is None:
+            kernel_ms.append(ctx.kernel_time_ms())
         launches += per_step
     barrier()
     clk = clocks.stop()
@@ -454,7 +476,7 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
     if not stokes and not with_prd:
         ctx.sync()
         ctx.check_singular()   # raises if any timed step met a singular system
-        if not lambda_sharded:
+        if not lambda_sharded and graphed is None:
             dj_last = ctx.last_dj()[0]
             if not (dj_last == dj_last and dj_last >= 0.0):
                 raise SystemExit(f'bench.py: bad dJ {dj_last}')
@@ -609,6 +631,8 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
         'ms_per_step': ms_per_step, 'gamma_iter_per_s': 1e3 / ms_per_step,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(workload, desc, problem, columns),
+        'launch': ('one CUDA graph per step (whole iteration incl. the collective)' if graphed is not None
+                   else 'direct kernel launches'),
         'parallelism': ('1 GPU' if world == 1 else
                         (f'column-sharded x{world}, no data-path collective' if column_sharded else
                          f'lambda-sharded x{world}, one all-reduce(sum) of packed [Gamma|R] per step')),

@@ -180,7 +180,9 @@ enum {
     LWB200_BUF_I     = 2,  /* [Ncol][Nspect][Nrays] */
     LWB200_BUF_POPS  = 3,  /* [Ncol][sum_a Nlevel][Nspace] */
     LWB200_BUF_GAMMA = 4,  /* [Ncol][sum_a Nlevel^2][Nspace] finalised */
-    LWB200_BUF_DJ    = 5   /* [Ncol][Nspect] per-wavelength max_k |1 - Jdag/J| */
+    LWB200_BUF_DJ    = 5,  /* [Ncol][Nspect] per-wavelength max_k |1 - Jdag/J| */
+    LWB200_BUF_DJMAX = 6   /* [1] the reduced dJ of the last lwb200_fs_iter / lwb200_dj_max over this context's
+                              wavelength range (what a lambda-sharded run max-reduces across ranks) */
 };
 
 typedef struct LwB200Context LwB200Context; /* opaque */

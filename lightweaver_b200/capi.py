@@ -26,7 +26,7 @@ ITER_OUTPUTS = GAMMA | JBAR | INTENS | RATES
 
 LAMBDA_ITERATE, STORE_DEPTH, DEFER_FINALISE, GENERAL_KERNEL, FETCH_EARLY, DJ_ASYNC = 1, 2, 4, 8, 16, 32
 
-BUF_ACCUM, BUF_J, BUF_I, BUF_POPS, BUF_GAMMA, BUF_DJ = range(6)
+BUF_ACCUM, BUF_J, BUF_I, BUF_POPS, BUF_GAMMA, BUF_DJ, BUF_DJMAX = range(7)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

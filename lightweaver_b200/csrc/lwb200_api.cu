@@ -1385,6 +1385,18 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
     return 0;
 }
 
+// a stream being captured into a CUDA graph (the caller replays whole iterations): no timing events there
+static bool stream_is_capturing(cudaStream_t s)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return st != cudaStreamCaptureStatusNone;
+}
+
 template <int NCH, int SOLVER, int MODE>
 int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
 {
@@ -1393,7 +1405,9 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
         CU(cudaEventCreate(&c->evK0));
         CU(cudaEventCreate(&c->evK1));
     }
-    CU(cudaEventRecord(c->evK0, c->stream));
+    const bool capturing = stream_is_capturing(c->stream);
+    if (!capturing)
+        CU(cudaEventRecord(c->evK0, c->stream));
     const int threads = c->nwarps * 32;
     if (MODE == MODE_ITER && !c->forceDirect)
     {
@@ -1424,8 +1438,11 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
         CU(cudaGetLastError());
         c->lastLaunches += 1;
     }
-    CU(cudaEventRecord(c->evK1, c->stream));
-    c->kernelTimed = true;
+    if (!capturing)
+    {
+        CU(cudaEventRecord(c->evK1, c->stream));
+        c->kernelTimed = true;
+    }
     return 0;
 }
 
@@ -1440,12 +1457,17 @@ int launch_fs_long(LwB200Context* c, int lambdaIterate, int upOnly, int storeDep
     }
     if (c->forceDirect)
         return fail("the general per-ray kernel is limited to Nspace <= 128");
-    CU(cudaEventRecord(c->evK0, c->stream));
+    const bool capturing = stream_is_capturing(c->stream);
+    if (!capturing)
+        CU(cudaEventRecord(c->evK0, c->stream));
     const int fsMode = MODE == MODE_ITER ? c->stokesFsMode : (upOnly ? 3 : 1);
     if (launch_pipeline<4, SOLVER, true>(c, c->customLists ? c->prdPl : full_lists(c), lambdaIterate, storeDepth, fsMode))
         return 1;
-    CU(cudaEventRecord(c->evK1, c->stream));
-    c->kernelTimed = true;
+    if (!capturing)
+    {
+        CU(cudaEventRecord(c->evK1, c->stream));
+        c->kernelTimed = true;
+    }
     return 0;
 }
 
@@ -2981,6 +3003,7 @@ int lwb200_device_buffer(LwB200Context* c, int32_t which, void** ptr, size_t* nb
     case LWB200_BUF_POPS: b = &c->n; break;
     case LWB200_BUF_GAMMA: b = &c->gamma; break;
     case LWB200_BUF_DJ: b = &c->dJ; break;
+    case LWB200_BUF_DJMAX: b = &c->djOut; break;
     default: return fail("lwb200_device_buffer: unknown buffer");
     }
     if (ptr)

@@ -29,20 +29,16 @@
 #include "lwb200.h"
 
 #include <algorithm>
-#include <atomic>
 #include <cmath>
-#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
-#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
-#include <thread>
 #include <vector>
 
 namespace enki
@@ -67,7 +63,7 @@ struct Mirror
     bool uploadedStatic = false;
     bool hasDepth = false;
     bool zplane = false;
-    uint64_t fpProfiles = 0, fpBackground = 0, fpAtmos = 0, fpJ = 0;
+    uint64_t fpProfiles = 0, fpBackground = 0, fpAtmos = 0;
     int solver = -1;
 };
 
@@ -95,11 +91,22 @@ int device_index()
 }
 
 // ---------------------------------------------------------------------------
-// Fingerprints.  Python mutates phi / background / atmosphere / J in place between calls without
-// telling the plugin, and a change may be LOCAL (a response-function run perturbs
-// one depth), so every element counts: h = sum_i mix(word_i + (i + 1) * C) mod 2^64 -- position
-// dependent, order independent, hence four independent lanes per thread and several threads for
-// the large arrays (the background of a 1e4-wavelength spectrum is 20 MB: ~0.3 ms).
+// Coherence.  Python mutates phi / background / atmosphere / J in place between calls without telling
+// the plugin.  What travels when:
+//   * populations, nStar / nTotal / vBroad, the prefill crsw*C and J: on EVERY call (small, or -- J --
+//     cheaper to send than to check: it is rewritten by every call anyway);
+//   * the atmosphere (height, temperature, ne, vlosMu, vturb, nHTot, boundary data): hashed over EVERY
+//     element on every call (a response-function run perturbs ONE depth); when it changed, update_deps()
+//     has run, and background and profiles are re-sent with it whatever their own fingerprints say;
+//   * every line's wphi, aDamp and rhoPrd: hashed over every element.  wphi(k) is the reference's own
+//     normalisation 1 / sum phi(la, mu, dir, k) w, recomputed whenever phi is (FormalScalar.cpp:106-134):
+//     a changed profile at any depth shows there;
+//   * the two big ones, phi and the background [Nspect][Nspace] arrays: a strided sample (odd stride:
+//     it walks through every depth) on every call.  They only change through compute_profiles() /
+//     update_background(), i.e. together with what is hashed fully above; LWB200_FINGERPRINT=full hashes
+//     them over every element too (for hosts that edit them by hand), at ~1 ms per 5 MB.
+// Hash: h = sum over 8 lanes of a rotate-add chain, bijective in every word, so a single changed element
+// always changes it.
 inline uint64_t mix64(uint64_t x)
 {
     x ^= x >> 32;
@@ -108,154 +115,63 @@ inline uint64_t mix64(uint64_t x)
     return x;
 }
 
-uint64_t hash_range(const double* p, size_t i0, size_t i1, size_t stride)
+inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+uint64_t hash_block(const double* p, size_t n, size_t stride, uint64_t seed)
 {
-    constexpr uint64_t C = 0x9e3779b97f4a7c15ULL;
-    uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-    size_t i = i0;
+    uint64_t h[8];
+    for (int l = 0; l < 8; ++l)
+        h[l] = seed + l * 0x9e3779b97f4a7c15ULL;
+    size_t i = 0;
     if (stride == 1)
     {
-        for (; i + 4 <= i1; i += 4)
+        for (; i + 8 <= n; i += 8)
         {
-            uint64_t w[4];
-            std::memcpy(w, p + i, 32);
-            h0 += mix64(w[0] + (i + 1) * C);
-            h1 += mix64(w[1] + (i + 2) * C);
-            h2 += mix64(w[2] + (i + 3) * C);
-            h3 += mix64(w[3] + (i + 4) * C);
+            uint64_t w[8];
+            std::memcpy(w, p + i, 64);
+            for (int l = 0; l < 8; ++l)
+                h[l] = rotl64(h[l], 29) + w[l];
         }
     }
-    for (; i < i1; i += stride)
+    for (size_t q = 0; i < n; i += stride, ++q)
     {
         uint64_t w;
         std::memcpy(&w, p + i, 8);
-        h0 += mix64(w + (i + 1) * C);
+        h[q & 7] = rotl64(h[q & 7], 29) + w;
     }
-    return h0 + h1 + h2 + h3;
+    uint64_t r = seed;
+    for (int l = 0; l < 8; ++l)
+        r = mix64(r + h[l]);
+    return r;
 }
 
-// A few persistent helper threads for the large arrays (std::thread start-up would cost as much
-// as the hashing itself).
-class HashPool
+bool fingerprint_full()
 {
-public:
-    static HashPool& get()
-    {
-        static HashPool pool;
-        return pool;
-    }
-    uint64_t run(const double* p, size_t n)
-    {
-        const size_t chunk = (size_t)1 << 17; // 1 MiB of doubles
-        const size_t nchunk = (n + chunk - 1) / chunk;
-        if (nchunk < 2 || workers.empty())
-            return hash_range(p, 0, n, 1);
-        std::lock_guard<std::mutex> serial(runMutex);
-        {
-            std::lock_guard<std::mutex> lock(m);
-            data = p;
-            len = n;
-            next.store(0);
-            total = nchunk;
-            chunkLen = chunk;
-            acc.store(0);
-            pending = (int)workers.size();
-            ++generation;
-        }
-        cv.notify_all();
-        work();
-        std::unique_lock<std::mutex> lock(m);
-        done.wait(lock, [&] { return pending == 0; });
-        return acc.load();
-    }
-    ~HashPool()
-    {
-        {
-            std::lock_guard<std::mutex> lock(m);
-            quit = true;
-            ++generation;
-        }
-        cv.notify_all();
-        for (auto& t : workers)
-            t.join();
-    }
-
-private:
-    HashPool()
-    {
-        const unsigned hw = std::thread::hardware_concurrency();
-        const unsigned nw = hw > 2 ? std::min(7u, hw - 1) : 0;
-        for (unsigned i = 0; i < nw; ++i)
-            workers.emplace_back([this] { loop(); });
-    }
-    void work()
-    {
-        uint64_t h = 0;
-        for (;;)
-        {
-            const size_t q = next.fetch_add(1);
-            if (q >= total)
-                break;
-            h += hash_range(data, q * chunkLen, std::min(len, (q + 1) * chunkLen), 1);
-        }
-        acc.fetch_add(h);
-    }
-    void loop()
-    {
-        uint64_t seen = 0;
-        for (;;)
-        {
-            {
-                std::unique_lock<std::mutex> lock(m);
-                cv.wait(lock, [&] { return generation != seen; });
-                seen = generation;
-                if (quit)
-                    return;
-            }
-            work();
-            {
-                std::lock_guard<std::mutex> lock(m);
-                --pending;
-            }
-            done.notify_one();
-        }
-    }
-    std::vector<std::thread> workers;
-    std::mutex m, runMutex;
-    std::condition_variable cv, done;
-    const double* data = nullptr;
-    size_t len = 0, total = 0, chunkLen = 0;
-    std::atomic<size_t> next{0};
-    std::atomic<uint64_t> acc{0};
-    int pending = 0;
-    uint64_t generation = 0;
-    bool quit = false;
-};
+    static const bool full = [] {
+        const char* e = std::getenv("LWB200_FINGERPRINT");
+        return e && std::string(e) == "full";
+    }();
+    return full;
+}
 
 // every element of the array
 uint64_t fingerprint(uint64_t h, const double* p, size_t n)
 {
     if (!p || n == 0)
         return h;
-    return mix64(h + 0x2545f4914f6cdd1dULL) + HashPool::get().run(p, n);
+    return hash_block(p, n, 1, mix64(h + 0x2545f4914f6cdd1dULL));
 }
 
-// a sample of a large array whose every element is ALSO covered by a small, fully hashed companion
-// (phi: its normalisation wphi(k) = 1 / sum phi(la, mu, dir, k) w, recomputed by the reference whenever
-// phi is, FormalScalar.cpp:106-134).  The stride is odd and not a multiple of any depth count in use,
-// so the sample walks through every depth.  LWB200_FINGERPRINT=full hashes these arrays entirely too.
+// a strided sample of a large array (see above), or all of it under LWB200_FINGERPRINT=full
 uint64_t fingerprint_sampled(uint64_t h, const double* p, size_t n)
 {
-    static const bool full = [] {
-        const char* e = std::getenv("LWB200_FINGERPRINT");
-        return e && std::string(e) == "full";
-    }();
     if (!p || n == 0)
         return h;
-    if (full || n <= 65536)
+    if (fingerprint_full() || n <= 8192)
         return fingerprint(h, p, n);
-    size_t stride = (n / 16384) | 1;
-    return mix64(h + 0x2545f4914f6cdd1dULL) + hash_range(p, 0, n, stride) + hash_range(p, n - 1, n, 1);
+    const size_t stride = (n / 1024) | 1; // (each sample is a cache line of its own: keep them few)
+    h = hash_block(p, n, stride, mix64(h + 0x2545f4914f6cdd1dULL));
+    return hash_block(p + n - 1, 1, 1, h);
 }
 
 int solver_from_name(const char* name)
@@ -446,29 +362,26 @@ Mirror& mirror_for(Context& ctx)
     return ref;
 }
 
-uint64_t fingerprint_J(const Mirror& m)
-{
-    return fingerprint(1469598103934665603ULL, m.prob.J, (size_t)m.prob.Nspect * m.prob.Nspace);
-}
-
-// Bring the device mirror up to date with whatever the host changed since the
-// last call.  Small per-iteration arrays always travel; the large ones only when
-// their fingerprint (over EVERY element) changed.
+// Bring the device mirror up to date with whatever the host changed since the last call (see "Coherence").
 void sync_inputs(Context& ctx, Mirror& m, bool withGamma)
 {
     const LwB200Problem& p = m.prob;
+    const Atmosphere& atmos = *ctx.atmos;
     const size_t K = p.Nspace, L = p.Nspect, M = p.Nrays;
-    uint32_t mask = LWB200_POPS | LWB200_NSTAR | (withGamma ? LWB200_GAMMA : 0);
+    uint32_t mask = LWB200_POPS | LWB200_NSTAR | LWB200_JBAR | (withGamma ? LWB200_GAMMA : 0);
     uint64_t fa = 1469598103934665603ULL, fb = fa, fpf = fa;
     fa = fingerprint(fa, p.height, K);
     fa = fingerprint(fa, p.temperature, K);
     fa = fingerprint(fa, p.vlosMu, p.vlosMu ? M * K : 0);
     fa = fingerprint(fa, p.ne, p.ne ? K : 0);
+    fa = fingerprint(fa, atmos.vturb.data, atmos.vturb ? K : 0);
+    fa = fingerprint(fa, atmos.nHTot.data, atmos.nHTot ? K : 0);
+    fa = fingerprint(fa, atmos.B.data, atmos.B ? K : 0);
     fa = fingerprint(fa, p.lowerBcData, p.NlowerBcMu ? L * p.NlowerBcMu : 0);
     fa = fingerprint(fa, p.upperBcData, p.NupperBcMu ? L * p.NupperBcMu : 0);
-    fb = fingerprint(fb, p.chiBg, L * K);
-    fb = fingerprint(fb, p.etaBg, L * K);
-    fb = fingerprint(fb, p.scaBg, L * K);
+    fb = fingerprint_sampled(fb, p.chiBg, L * K);
+    fb = fingerprint_sampled(fb, p.etaBg, L * K);
+    fb = fingerprint_sampled(fb, p.scaBg, L * K);
     for (const LwB200Atom& a : m.atoms)
         for (int kr = 0; kr < a.Ntrans; ++kr)
         {
@@ -482,23 +395,18 @@ void sync_inputs(Context& ctx, Mirror& m, bool withGamma)
             if (t.rhoPrd)
                 fpf = fingerprint(fpf, t.rhoPrd, Nl * K);
         }
-    const uint64_t fj = fingerprint_J(m);
-    const bool atmosChanged = !m.uploadedStatic || fa != m.fpAtmos;
     // a changed atmosphere means update_deps() ran: profiles and background are re-sent with it
-    if (atmosChanged)
+    if (!m.uploadedStatic || fa != m.fpAtmos)
         mask |= LWB200_ATMOS | LWB200_BACKGR | LWB200_PROFILE;
     if (fb != m.fpBackground)
         mask |= LWB200_BACKGR;
     if (fpf != m.fpProfiles)
         mask |= LWB200_PROFILE;
-    if (!m.uploadedStatic || fj != m.fpJ)
-        mask |= LWB200_JBAR;
     check(lwb200_upload(m.dev, mask), "lwb200_upload");
     m.fpAtmos = fa;
     m.fpBackground = fb;
     m.fpProfiles = fpf;
     m.uploadedStatic = true;
-    (void)ctx;
 }
 
 // ZPlaneDecomposition (SimdFullIterationTemplates.hpp:254-281): register / unregister the output views.
@@ -546,7 +454,6 @@ IterationResult b200_fs_iter(Context& ctx, bool lambdaIterate, ExtraParams param
           "lwb200_download");
     check(lwb200_sync(m.dev), "lwb200_sync");
     check(lwb200_last_dj(m.dev, &dJMax, &dJIdx), "lwb200_last_dj");
-    m.fpJ = fingerprint_J(m);
     IterationResult result{};
     result.updatedJ = true;
     result.dJMax = dJMax;
@@ -586,7 +493,6 @@ IterationResult b200_redistribute_prd(Context& ctx, int maxIter, f64 tol, ExtraP
           "lwb200_redistribute_prd");
     check(lwb200_download(m.dev, LWB200_PRD | LWB200_JBAR | LWB200_INTENS | LWB200_RATES), "lwb200_download");
     check(lwb200_sync(m.dev), "lwb200_sync");
-    m.fpJ = fingerprint_J(m);
     IterationResult result{};
     result.updatedRho = true;
     result.updatedJPrd = true;
@@ -650,8 +556,6 @@ IterationResult b200_full_stokes_fs(Context& ctx, bool updateJ, bool upOnly, Ext
           "lwb200_formal_sol_full_stokes");
     check(lwb200_download(m.dev, LWB200_INTENS | LWB200_STOKES | (updateJ ? LWB200_JBAR : 0)), "lwb200_download");
     check(lwb200_sync(m.dev), "lwb200_sync");
-    if (updateJ)
-        m.fpJ = fingerprint_J(m);
     IterationResult result{};
     result.updatedJ = updateJ;
     if (updateJ)

@@ -133,8 +133,13 @@ class GpuLambdaShard(ShardBackend):
         ptr, nbytes = ctx.device_buffer(capi.BUF_ACCUM)
         self._accum = device_tensor(ptr, nbytes, ctx.device)
 
-    def partial_iteration(self, lambdaIterate=False):
-        self.ctx.fs_iter_device(lambdaIterate=lambdaIterate, deferFinalise=True, want_dJ=False)
+    def partial_iteration(self, lambdaIterate=False, asyncDJ=False):
+        """asyncDJ: also reduce dJ over this shard's wavelengths on the device (BUF_DJMAX; no host sync)."""
+        self.ctx.fs_iter_device(lambdaIterate=lambdaIterate, deferFinalise=True, want_dJ=False, asyncDJ=asyncDJ)
+
+    def djmax_tensor(self):
+        ptr, nbytes = self.ctx.device_buffer(capi.BUF_DJMAX)
+        return device_tensor(ptr, nbytes, self.ctx.device)
 
     def accum_tensor(self):
         return self._accum
@@ -186,6 +191,54 @@ def sharded_gamma_iteration(shard: ShardBackend, lambdaIterate=False, group=None
         t = shard.accum_tensor()
         dJ, idx = reduce_dj(dJ, idx, group, device=t.device)
     return dJ, idx
+
+
+class GraphedIteration:
+    """One whole Gamma iteration of a shard -- zero the partial sums, continuum / ray / Gamma kernels
+    (forked over the library's side streams), the all-reduce of the packed [Gamma | R] buffer when there
+    is more than one rank, finalise, the statistical-equilibrium solve -- captured ONCE into a CUDA graph
+    and replayed: a 1D atmosphere is ~15 launches of 10-100 us each, so a wavelength shard on 8 GPUs is
+    bound by launch latency and by the host dispatch of the collective, not by its kernels.
+    dJ is reduced on the device inside the graph (and max-reduced across ranks): ``dJMax()`` reads it."""
+
+    def __init__(self, shard, group=None, lambdaIterate=False, with_stat_eq=True, warmup=3):
+        import torch
+        import torch.distributed as dist
+        self.shard = shard
+        ctx = shard.ctx
+        multi = dist.is_initialized() and dist.get_world_size(group) > 1
+        accum = shard.accum_tensor()
+        djmax = shard.djmax_tensor()
+
+        def body():
+            shard.partial_iteration(lambdaIterate, asyncDJ=True)
+            if multi:
+                dist.all_reduce(accum, op=dist.ReduceOp.SUM, group=group)
+                dist.all_reduce(djmax, op=dist.ReduceOp.MAX, group=group)
+            shard.finalise()
+            if with_stat_eq:
+                ctx.stat_eq_device(wait=False)
+        outer = torch.cuda.current_stream()
+        # the library launches on the stream it was given: warm up and capture on a side stream of ours
+        side = torch.cuda.Stream()
+        side.wait_stream(outer)
+        with torch.cuda.stream(side):
+            ctx.set_stream(side)
+            for _ in range(warmup):   # (first calls allocate work lists and opt in to shared memory sizes)
+                body()
+            side.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                body()
+        ctx.set_stream(outer)
+        outer.wait_stream(side)
+
+    def replay(self):
+        self.graph.replay()
+
+    def dJMax(self):
+        """The (all-rank) dJ of the last replay; synchronises."""
+        return float(self.shard.djmax_tensor().cpu()[0])
 
 
 def sharded_prd_redistribute(shard: ShardBackend, ranges: Sequence[Tuple[int, int]], rank: int, maxIter=3,

@@ -713,6 +713,31 @@ def test_zplane_decomposition_matches_depth_intensities(ndepth, general):
     ctx.close()
 
 
+def test_graphed_iteration_matches_oracle():
+    """sharding.GraphedIteration: the whole Gamma iteration + stat-eq captured into a CUDA graph and
+    replayed (what bench.py times for 1D atmospheres) gives what the direct launches give."""
+    import torch
+    from lightweaver_b200 import sharding
+    p = synth.config_c1(nl=0.4)
+    q = p.clone()
+    stream = torch.cuda.current_stream()
+    ctx = Context(p, stream=stream)
+    shard = sharding.GpuLambdaShard(ctx)
+    p.prefill_gamma()
+    ctx.upload(capi.GAMMA)
+    g = sharding.GraphedIteration(shard)        # (its warm-up iterations run on the uploaded state)
+    ctx.upload(capi.POPS | capi.JBAR)           # back to the initial state
+    for it in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        ctx.check_singular()
+        (dJ, _), = oracle_iter(q)
+        assert abs(g.dJMax() - dJ) <= 1e-9 * max(dJ, 1.0)
+        ctx.download(capi.ITER_OUTPUTS | capi.POPS)
+        assert_close(p, q)
+    ctx.close()
+
+
 def test_short_wavelength_continuum_boltzmann_factor_underflows_to_zero():
     """A bound-free continuum reaching down to 2 nm: exp(-hc / (k lambda T)) underflows (x < -708) at the cool
     depths; the reference's libm exp() gives 0 there and so must the device's table-free exp."""

@@ -400,9 +400,15 @@ def test_zplane_decomposition_through_the_plugin(which):
 @needs_plugin
 @pytest.mark.ref
 @pytest.mark.gpu
-def test_plugin_sees_a_single_depth_change():
-    """A response-function style update: the background changes at ONE depth of ONE wavelength, J at one
-    element, a profile at one depth (with its wphi).  The fingerprints cover every element."""
+@pytest.mark.parametrize('mode', ['update_deps', 'by_hand'])
+def test_plugin_sees_a_single_depth_change(mode, monkeypatch):
+    """A response-function style update: the atmosphere is perturbed at ONE depth and what depends on it
+    changes at that depth only -- the background of one wavelength, a profile (with its wphi), J at one
+    element.  'update_deps': the temperature changes too (what lw.Context.update_deps follows); the
+    atmosphere is hashed over every element and takes background and profiles with it.  'by_hand': only
+    the dependent arrays are edited; LWB200_FINGERPRINT=full hashes them over every element as well."""
+    if mode == 'by_hand':
+        monkeypatch.setenv('LWB200_FINGERPRINT', 'full')
     p = synth.config_c1(nl=0.5)
     q = p.clone()
     gpu = reflib.RefContext(p, scheme=PLUGIN)
@@ -412,6 +418,8 @@ def test_plugin_sees_a_single_depth_change():
         ctx.fs_iter()
     k = 37
     for prob in (p, q):
+        if mode == 'update_deps':
+            prob.temperature[0, k] *= 1.0 + 1e-3
         prob.chiBg[0, prob.Nspect // 3, k] *= 1.5
         prob.etaBg[0, 5, k] *= 0.5
         prob.J[0, 11, k] *= 1.25
