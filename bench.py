@@ -71,6 +71,9 @@ def build_workload(name, columns, rank=0, world=1, for_gpu=True):
     """Returns (problem, description).  For c3 each rank builds only its column shard."""
     if name == 'c1':
         return synth.config_c1(), 'FAL C 1D, H 6-level + Ca II 5+1-level, 5 rays (configs[0])'
+    if name == 'deep':
+        return synth.config_c1(ndepth=500), ('FAL C interpolated to 500 depths, H 6-level + Ca II 5+1-level, 5 rays: the '
+                                             "reference's own benchmark protocol (lightweaver/benchmark.py:19-45)")
     if name == 'c2':
         return synth.config_c2(), ('FAL C 1D, H + Ca II + Mg II + Na I + He I active, 10 rays '
                                    '(configs[1], synthetic atomic data)')
@@ -727,7 +730,7 @@ def _main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c3', choices=['c1', 'c2', 'c3', 'c4', 'c5'])
+    ap.add_argument('--workload', default='c3', choices=['c1', 'c2', 'c3', 'c4', 'c5', 'deep'])
     ap.add_argument('--columns', type=int, default=None, help='columns of the c3 (4096) / c5 (1024) stacks')
     ap.add_argument('--no-secondary', dest='secondary', action='store_false',
                     help='default run (c3): do not also measure the lambda-sharded c2 workload')

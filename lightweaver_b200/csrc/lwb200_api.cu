@@ -192,6 +192,7 @@ struct LwB200Context
     cudaStream_t copyStream = nullptr;
     cudaEvent_t evRays = nullptr, evCopy = nullptr;
     bool fetchEarly = false, fetched = false, outputsPinned = false;
+    bool ioPinned = false; // populations, Gamma, rates, nStar ... are pinned in place: strided DMA, no staging
     cudaStream_t sideStream[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t evFork = nullptr, evJoin[4] = {nullptr, nullptr, nullptr, nullptr};
     bool kernelTimed = false;
@@ -1607,6 +1608,44 @@ int lwb200_create(const LwB200Problem* problem, int device, LwB200Context** out)
         c->outputsPinned = c->registered.size() == 2;
         cudaGetLastError();
     }
+    // Column stacks: the per-iteration arrays (populations, Gamma, rates, nStar ...) are many per-atom /
+    // per-transition host buffers of [Ncol][rows][Nspace]; packing them into pinned staging and scattering
+    // them back costs more host time than the copies themselves (measured: 1024 columns, 8 ms for Gamma +
+    // rates of which 2 ms on the bus).  Pin them in place instead and let strided (2D) DMA copies do the
+    // packing.  Small problems keep the staging path (one copy per group beats dozens of tiny ones).
+    {
+        const size_t K = problem->Nspace, ncol = problem->Ncol;
+        size_t total = 0;
+        for (int a = 0; a < problem->Natom; ++a)
+            total += ncol * K * sizeof(double) * ((size_t)c->atoms[a].Nlevel * (c->atoms[a].Nlevel + 2) + 2 + 2 * c->atoms[a].Ntrans);
+        bool ok = total >= ((size_t)8 << 20) && !std::getenv("LWB200_NO_PIN_IO");
+        auto pin = [&](const void* ptr, size_t bytes) {
+            if (!ok || !ptr || bytes == 0)
+                return;
+            if (cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess)
+                c->registered.push_back(const_cast<void*>(ptr));
+            else
+                ok = false;
+        };
+        for (int a = 0; a < problem->Natom && ok; ++a)
+        {
+            const LwB200Atom& at = c->atoms[a];
+            const size_t nk = ncol * at.Nlevel * K * sizeof(double);
+            pin(at.n, nk);
+            pin(at.nStar, nk);
+            pin(at.nTotal, ncol * K * sizeof(double));
+            pin(at.vBroad, ncol * K * sizeof(double));
+            if (!at.detailedStatic)
+                pin(at.Gamma, nk * at.Nlevel);
+            for (int kr = 0; kr < at.Ntrans && ok; ++kr)
+            {
+                pin(c->atomTrans[a][kr].Rij, ncol * K * sizeof(double));
+                pin(c->atomTrans[a][kr].Rji, ncol * K * sizeof(double));
+            }
+        }
+        c->ioPinned = ok;
+        cudaGetLastError();
+    }
     *out = c;
     return 0;
 }
@@ -1958,6 +1997,20 @@ static int upload_packed(LwB200Context* c, Pinned& st, double* dev, int totalRow
 {
     const size_t K = c->prob.Nspace, ncol = c->prob.Ncol;
     const size_t total = ncol * (size_t)totalRows * K;
+    if (c->ioPinned)
+    {
+        // the host arrays are pinned in place: one strided DMA copy per atom packs them on the way
+        for (int a = 0; a < c->prob.Natom; ++a)
+        {
+            const double* src = ptr(a);
+            const size_t r = rows(a);
+            if (!src || r == 0)
+                continue;
+            CU(cudaMemcpy2DAsync(dev + off(a) * K, (size_t)totalRows * K * sizeof(double), src, r * K * sizeof(double),
+                                 r * K * sizeof(double), ncol, cudaMemcpyHostToDevice, c->stream));
+        }
+        return 0;
+    }
     if (stage_ready(st, total))
         return 1;
     for (int a = 0; a < c->prob.Natom; ++a)
@@ -2168,7 +2221,17 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
     if (mask & LWB200_INTENS)
         if (copy2d(p.I + r0 * M, L * M * D, c->I.p + r0 * M, L * M * D, (r1 - r0) * M * D, ncol, D2H, s))
             return 1;
-    if (mask & LWB200_POPS)
+    if ((mask & LWB200_POPS) && c->ioPinned)
+    {
+        const size_t rows = c->P.NlevTot;
+        for (int a = 0; a < p.Natom; ++a)
+        {
+            const size_t N = c->atoms[a].Nlevel;
+            CU(cudaMemcpy2DAsync(c->atoms[a].n, N * K * D, c->n.p + (size_t)c->atomLevOff[a] * K, rows * K * D, N * K * D,
+                                 ncol, D2H, s));
+        }
+    }
+    else if (mask & LWB200_POPS)
     {
         const size_t rows = c->P.NlevTot;
         if (stage_ready(c->stNOut, ncol * rows * K))
@@ -2182,7 +2245,19 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
                                       c->stNOut.p + (col * rows + c->atomLevOff[a]) * K, N * K * D});
         }
     }
-    if ((mask & LWB200_GAMMA) && c->P.GammaTot > 0)
+    if ((mask & LWB200_GAMMA) && c->P.GammaTot > 0 && c->ioPinned)
+    {
+        const size_t rows = c->P.GammaTot;
+        for (int a = 0; a < p.Natom; ++a)
+        {
+            if (c->atoms[a].detailedStatic)
+                continue;
+            const size_t N2 = (size_t)c->atoms[a].Nlevel * c->atoms[a].Nlevel;
+            CU(cudaMemcpy2DAsync(c->atoms[a].Gamma, N2 * K * D, c->gamma.p + (size_t)c->atomGammaOff[a] * K, rows * K * D,
+                                 N2 * K * D, ncol, D2H, s));
+        }
+    }
+    else if ((mask & LWB200_GAMMA) && c->P.GammaTot > 0)
     {
         const size_t rows = c->P.GammaTot;
         if (stage_ready(c->stGammaOut, ncol * rows * K))
@@ -2198,7 +2273,19 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
                                       c->stGammaOut.p + (col * rows + c->atomGammaOff[a]) * K, N2 * K * D});
         }
     }
-    if (mask & LWB200_RATES)
+    if ((mask & LWB200_RATES) && c->ioPinned)
+    {
+        for (size_t g = 0; g < c->trans.size(); ++g)
+        {
+            const LwB200Transition& t = c->trans[g].t;
+            const DevTrans& d = c->devTrans[g];
+            CU(cudaMemcpy2DAsync(t.Rij, K * D, c->accum.p + (size_t)d.accRij * K, (size_t)c->P.AccTot * K * D, K * D, ncol,
+                                 D2H, s));
+            CU(cudaMemcpy2DAsync(t.Rji, K * D, c->accum.p + (size_t)d.accRji * K, (size_t)c->P.AccTot * K * D, K * D, ncol,
+                                 D2H, s));
+        }
+    }
+    else if (mask & LWB200_RATES)
     {
         // the R rows are the tail of each column's accumulator block
         const size_t rows = 2 * c->trans.size();

@@ -37,6 +37,9 @@ if wl == 'c3':
 elif wl == 'c1':
     p = synth.config_c1()
     ctx = Context(p)
+elif wl == 'deep':
+    p = synth.config_c1(ndepth=500)
+    ctx = Context(p)
 else:
     p = synth.config_c2()
     import os
