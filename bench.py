@@ -521,10 +521,13 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
 
     # ---- end to end with HOST buffers (h2d / d2h counted from the arrays that cross)
     # Per call the boundary sends what the reference's caller may have changed since the last call --
-    # populations, nStar / nTotal / vBroad and the prefill crsw*C (LwMiddleLayer.pyx:3198-3203 refills Gamma
-    # on EVERY call) -- and brings home everything the caller reads: J, I, Gamma, rates, populations.
+    # populations, nStar / nTotal / vBroad -- and brings home everything the caller reads: J, I, Gamma, rates,
+    # populations.  The prologue Gamma = crsw*C (LwMiddleLayer.pyx:3198-3203) is made on the device from the
+    # resident collisional rates by the ctypes mirror (lwb200_set_collision_prefill); the plugin, which is
+    # handed a prefilled Gamma by the reference core, uploads it on every call.
     h2d = sum(2 * a.n.nbytes + a.nStar.nbytes + a.nTotal.nbytes + a.vBroad.nbytes for a in problem.atoms)
-    h2d += sum(2 * a.Gamma.nbytes for a in problem.active_atoms())  # prefill (fs_iter) + final Gamma (stat_equil)
+    h2d += sum(a.Gamma.nbytes for a in problem.active_atoms())  # the final Gamma stat_equil reads
+    gamma_prefill_bytes = sum(a.Gamma.nbytes for a in problem.active_atoms())
     d2h = problem.J.nbytes + problem.I.nbytes + sum(a.n.nbytes for a in problem.active_atoms())
     d2h += sum(a.Gamma.nbytes for a in problem.active_atoms())
     d2h += sum(t_.Rij.nbytes + t_.Rji.nbytes for a in problem.atoms for t_ in a.trans)
@@ -538,7 +541,7 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
         sec = plugin_e2e(problem.clone(), args.steps)
         if sec is not None:
             e2e = {'value': pts_total / sec, 'unit': 'points/s', 'ms_per_step': sec * 1e3,
-                   'h2d_bytes_per_step': int(h2d + problem.J.nbytes), 'd2h_bytes_per_step': int(d2h),
+                   'h2d_bytes_per_step': int(h2d + gamma_prefill_bytes + problem.J.nbytes), 'd2h_bytes_per_step': int(d2h),
                    'api': ('reference core (oracle/_ref/liblwref.so: Lightweaver formal_sol_gamma_matrices + stat_eq) -> '
                            'FsIterationFnsManager -> liblwb200_plugin.so fs_iteration_fns_provider -> b200_fs_iter / '
                            'b200_stat_eq on host buffers; per call: H2D of n, nStar, nTotal, vBroad, crsw*C (+ J, '
@@ -570,9 +573,9 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
                'api': ('C-ABI (lwb200_upload / lwb200_formal_sol_full_stokes / lwb200_download) on host numpy buffers'
                        if stokes else
                        'C-ABI of include/lwb200.h through its ctypes mirror (Context.formal_sol_gamma_matrices + '
-                       'stat_equil): lwb200_upload(POPS|NSTAR|GAMMA) -> lwb200_fs_iter -> lwb200_download(J, I, Gamma, '
-                       'rates) -> lwb200_upload(POPS|GAMMA_FINAL) -> lwb200_stat_eq -> lwb200_download(POPS), '
-                       'host numpy buffers')}
+                       'stat_equil): lwb200_upload(POPS|NSTAR) -> lwb200_fs_iter (prefill crsw*C from the device-resident '
+                       'collisional rates) -> lwb200_download(J, I, Gamma, rates) -> lwb200_upload(POPS|GAMMA_FINAL) -> '
+                       'lwb200_stat_eq -> lwb200_download(POPS), host numpy buffers')}
     elif e2e is None:
         # lambda-sharded: each rank uploads the (replicated) small inputs, reads back its J rows
         problem.prefill_gamma()

@@ -152,6 +152,8 @@ enum {
     LWB200_OWN_ROWS = 1u << 14, /* down, with JBAR / INTENS: only the rows of the context's wavelength range
                                    (lwb200_set_lambda_range) -- what a lambda-shard owns */
     LWB200_ZPLANE  = 1u << 15, /* down only: the ZPlaneUp / ZPlaneDown arrays registered with lwb200_set_zplane */
+    LWB200_COLLISIONS = 1u << 16, /* up only: C of every active atom, kept on the device so that the prefill
+                                   * crsw*C is made there (lwb200_set_collision_prefill) */
     LWB200_ALL_INPUTS  = 0x7fu,
     LWB200_ITER_INPUTS = LWB200_POPS | LWB200_NSTAR | LWB200_GAMMA,
     LWB200_ITER_OUTPUTS = LWB200_GAMMA | LWB200_JBAR | LWB200_INTENS | LWB200_RATES
@@ -248,6 +250,12 @@ int lwb200_compute_profiles(LwB200Context* ctx);
  * J, Gamma (onto the uploaded prefill) and Rij/Rji, finalises Gamma.
  * dJMax / dJMaxIdx may be NULL (no device->host sync is then forced). */
 int lwb200_fs_iter(LwB200Context* ctx, uint32_t flags, double* dJMax, int64_t* dJMaxIdx);
+/* The prologue of lw.Context.formal_sol_gamma_matrices, Gamma = crsw * C (Source/LwMiddleLayer.pyx:3198-3203),
+ * on the device: with enable != 0 the finalisation takes crsw times the collisional rates uploaded with
+ * LWB200_COLLISIONS instead of a prefill uploaded with LWB200_GAMMA, so a caller whose C is unchanged
+ * (fixCollisionalRates) neither forms the product on the host nor sends it.  Same rounding as the host's.
+ * A later upload of LWB200_GAMMA switches back to the uploaded prefill. */
+int lwb200_set_collision_prefill(LwB200Context* ctx, int enable, double crsw);
 /* Gamma = prefill + partial sums, diagonal = -column sum (finalise_Gamma, :491-508);
  * rates are unpacked.  Only needed after LWB200_DEFER_FINALISE. */
 int lwb200_finalise(LwB200Context* ctx);

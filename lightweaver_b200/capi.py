@@ -19,7 +19,7 @@ FS_NAMES = {'piecewise_linear_1d': FS_LINEAR, 'piecewise_besser_1d': FS_BESSER,
             'piecewise_bezier3_1d': FS_BEZIER3}
 
 (ATMOS, BACKGR, POPS, NSTAR, GAMMA, JBAR, PROFILE, INTENS, RATES, DEPTH, ADAMP,
- GAMMA_FINAL, PRD, STOKES, OWN_ROWS, ZPLANE) = (1 << i for i in range(16))
+ GAMMA_FINAL, PRD, STOKES, OWN_ROWS, ZPLANE, COLLISIONS) = (1 << i for i in range(17))
 ALL_INPUTS = 0x7f
 ITER_INPUTS = POPS | NSTAR | GAMMA
 ITER_OUTPUTS = GAMMA | JBAR | INTENS | RATES
@@ -160,6 +160,7 @@ def load():
     lib.lwb200_compute_profiles.argtypes = [vp]
     lib.lwb200_fs_iter.argtypes = [vp, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.lwb200_finalise.argtypes = [vp]
+    lib.lwb200_set_collision_prefill.argtypes = [vp, C.c_int, C.c_double]
     lib.lwb200_dj_max.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.lwb200_formal_sol.argtypes = [vp, C.c_int]
     lib.lwb200_stat_eq.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
@@ -182,7 +183,7 @@ def load():
                                       C.POINTER(C.c_int64)]
     for name in ('device_count', 'create', 'destroy', 'set_stream', 'set_lambda_range', 'upload',
                  'download', 'sync', 'compute_profiles', 'fs_iter', 'finalise', 'dj_max',
-                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes', 'nr_post_update', 'stat_eq_async', 'last_singular', 'last_dj', 'set_zplane', 'population_solve'):
+                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes', 'nr_post_update', 'stat_eq_async', 'last_singular', 'last_dj', 'set_zplane', 'population_solve', 'set_collision_prefill'):
         getattr(lib, 'lwb200_' + name).restype = C.c_int
     if lib.lwb200_abi_version() != ABI_VERSION:
         raise LwB200Error('liblwb200.so ABI version mismatch; rebuild')
@@ -205,4 +206,5 @@ EXPORTED_SYMBOLS = [
     'lwb200_time_dep_update', 'lwb200_formal_sol_full_stokes',
     'lwb200_nr_post_update', 'lwb200_stat_eq_async', 'lwb200_last_singular', 'lwb200_last_dj',
     'lwb200_set_zplane', 'lwb200_population_solve', 'lwb200_global_launch_count',
+    'lwb200_set_collision_prefill',
 ]

@@ -67,8 +67,10 @@ class Context:
         if laRange is not None:
             self.set_lambda_range(*laRange)
         self.crsw = 1.0
+        self._c_resident = False
         if upload:
             self.upload(capi.ALL_INPUTS)
+            self.collisions_changed()
 
     # --------------------------------------------------------------- plumbing
     def close(self):
@@ -126,6 +128,13 @@ class Context:
 
     def upload(self, mask):
         capi.check(self.lib.lwb200_upload(self._h, mask))
+
+    def collisions_changed(self):
+        """The collisional rates C of the active atoms are context state on the device (they change
+        with the atmosphere, not with the iteration): send them (again).  formal_sol_gamma_matrices
+        then makes the prefill Gamma = crsw*C on the device."""
+        self.upload(capi.COLLISIONS)
+        self._c_resident = True
 
     def download(self, mask, sync=True):
         capi.check(self.lib.lwb200_download(self._h, mask))
@@ -220,23 +229,25 @@ class Context:
     # ------------------------------------------- the reference's call surface
     def formal_sol_gamma_matrices(self, fixCollisionalRates=True, lambdaIterate=False,
                                   extraParams=None, crsw=None):
-        """lw.Context.formal_sol_gamma_matrices: Gamma = crsw*C (host prologue,
+        """lw.Context.formal_sol_gamma_matrices: Gamma = crsw*C (the prologue,
         LwMiddleLayer.pyx:3198-3203), then the device Gamma iteration; I, J,
         Gamma and the rates are back in the numpy buffers on return.  The
         collisional rates C are an input of this path (computed by the
-        reference's Python layer), so fixCollisionalRates is always honoured as
-        True."""
+        reference's Python layer); fixCollisionalRates=False re-sends them."""
         storeDepth = bool(extraParams and extraParams.get('storeDepthData', False))
         general = bool(extraParams and extraParams.get('generalKernel', False))
         zplane = self._bind_zplane(extraParams)
         if crsw is not None:
             self.crsw = crsw
         # What the reference's caller may have changed since the last call travels on EVERY call, as in the
-        # plugin shim (lwb200_plugin.cpp sync_inputs): the populations, nStar / nTotal / vBroad, and the
-        # prefill Gamma = crsw*C, which lw.Context refills before entering C++ each time
-        # (LwMiddleLayer.pyx:3198-3203).
-        self.problem.prefill_gamma(self.crsw)
-        self.upload(capi.POPS | capi.NSTAR | capi.GAMMA)
+        # plugin shim (lwb200_plugin.cpp sync_inputs): the populations and nStar / nTotal / vBroad.  The
+        # prologue Gamma = crsw*C (LwMiddleLayer.pyx:3198-3203) runs on the device from the resident C:
+        # fixCollisionalRates=False is the reference recomputing C first (compute_collisions on the host,
+        # outside this path), so C is sent again; otherwise neither the product nor its upload is paid.
+        if not fixCollisionalRates or not self._c_resident:
+            self.collisions_changed()
+        capi.check(self.lib.lwb200_set_collision_prefill(self._h, 1, float(self.crsw)))
+        self.upload(capi.POPS | capi.NSTAR)
         # one host synchronisation for the whole call: dJ comes home with the stream (DJ_ASYNC), J and I
         # start travelling as soon as the rays are done (FETCH_EARLY)
         flags = ((capi.LAMBDA_ITERATE if lambdaIterate else 0) | (capi.STORE_DEPTH if storeDepth else 0)
@@ -410,12 +421,13 @@ class Context:
         populations, background) is re-mirrored.  With profiles_on_device the
         Voigt profiles are regenerated on the GPU from aDamp/vBroad/vlosMu
         instead of being uploaded."""
-        mask = capi.ATMOS | capi.NSTAR | capi.POPS
+        mask = capi.ATMOS | capi.NSTAR | capi.POPS | capi.COLLISIONS
         if background:
             mask |= capi.BACKGR
         if not profiles_on_device:
             mask |= capi.PROFILE
         self.upload(mask)
+        self._c_resident = True
         if profiles_on_device:
             self.upload(capi.ADAMP)
             self.compute_profiles_device()

@@ -219,6 +219,9 @@ struct LwB200Context
     std::vector<int> prdLineDetailed;
     DevBuf<DevPrdLine> dPrdLines;
     DevBuf<double> qelast, cmat, rhoPrev, prdMax, nOld;
+    DevBuf<double> collC;          // C of every active atom, packed like `prefill` (LWB200_COLLISIONS)
+    bool prefillFromC = false;     // finalise with crswC * collC instead of the uploaded prefill
+    double crswC = 1.0;
     DevBuf<double> nrScratch, nrDC, nrPrev, nrStages, nrBgNe, neDev;
     DevBuf<NrAtom> nrAtoms;
     DevBuf<int> prdIdx, dKindLamPrd[4], dListMomentPrd;
@@ -1660,7 +1663,7 @@ int lwb200_destroy(LwB200Context* c)
                              &c->chiBg, &c->etaBg, &c->scaBg, &c->J, &c->I, &c->n, &c->nStar, &c->nTotal,
                              &c->vBroad, &c->gRatio, &c->phi, &c->wphi, &c->rhoPrd, &c->aDamp, &c->wlambdaTab,
                              &c->alphaTab, &c->transWave, &c->lowerBcData, &c->upperBcData, &c->accum,
-                             &c->prefill, &c->gamma, &c->dJ, &c->depthChi, &c->depthEta, &c->depthI, &c->djOut};
+                             &c->prefill, &c->gamma, &c->dJ, &c->depthChi, &c->depthEta, &c->depthI, &c->djOut, &c->collC};
     for (auto* b : dbl)
         b->release();
     DevBuf<int>* ints[] = {&c->lowerBcIdx, &c->upperBcIdx, &c->dLaOff, &c->dLaCnt, &c->dTileLambda, &c->dLaHasLine, &c->dTileLa,
@@ -2101,6 +2104,21 @@ int lwb200_upload(LwB200Context* c, uint32_t mask)
         if (upload_packed(c, c->stPrefill, c->prefill.p, c->P.GammaTot, gamRows, gamOff,
                           [&](int a) { return (const double*)c->atoms[a].Gamma; }))
             return 1;
+        c->prefillFromC = false; // (an uploaded prefill supersedes lwb200_set_collision_prefill)
+    }
+    if ((mask & LWB200_COLLISIONS) && c->P.GammaTot > 0)
+    {
+        // C of every active atom: with lwb200_set_collision_prefill the device makes Gamma's prefill
+        // crsw*C itself, and neither the host product nor its upload is paid per iteration
+        if (!c->collC.p)
+        {
+            if (c->collC.alloc(ncol * (size_t)c->P.GammaTot * K))
+                return fail("out of device memory (collision rates)");
+            CU(cudaMemsetAsync(c->collC.p, 0, c->collC.n * D, s)); // (an atom without C contributes nothing)
+        }
+        if (upload_packed(c, c->stPrefill, c->collC.p, c->P.GammaTot, gamRows, gamOff,
+                          [&](int a) { return c->atoms[a].detailedStatic ? nullptr : (const double*)c->atoms[a].C; }))
+            return 1;
     }
     if ((mask & LWB200_GAMMA_FINAL) && c->P.GammaTot > 0)
     {
@@ -2352,13 +2370,23 @@ int lwb200_compute_profiles(LwB200Context* c)
     return check_phi_symmetry(c);
 }
 
+int lwb200_set_collision_prefill(LwB200Context* c, int enable, double crsw)
+{
+    if (enable && !c->collC.p && c->P.GammaTot > 0)
+        return fail("lwb200_set_collision_prefill: the collisional rates have not been uploaded (LWB200_COLLISIONS)");
+    c->prefillFromC = enable != 0;
+    c->crswC = crsw;
+    return 0;
+}
+
 int lwb200_finalise(LwB200Context* c)
 {
     CU(cudaSetDevice(c->device));
     if (c->P.GammaTot > 0)
     {
         const size_t total = (size_t)c->P.Ncol * c->P.Natom * c->P.maxNlevel * c->P.K;
-        finalise_kernel<<<grid_for(total, 128), 128, 0, c->stream>>>(c->P, c->prefill.p, c->gamma.p);
+        finalise_kernel<<<grid_for(total, 128), 128, 0, c->stream>>>(
+            c->P, c->prefillFromC ? c->collC.p : c->prefill.p, c->prefillFromC ? c->crswC : 1.0, c->gamma.p);
         CU(cudaGetLastError());
         c->lastLaunches += 1;
     }

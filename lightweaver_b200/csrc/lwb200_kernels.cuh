@@ -594,7 +594,9 @@ __global__ void zero_accum_kernel(const DevProblem P, int nActive)
 // finalise_Gamma (:491-508): Gamma = prefill (crsw*C) + radiative partial sums,
 // then diagonal = -(column sum).  One thread per (column, atom, level i, depth): column i of
 // the atom's Gamma at one depth, loads issued together (nothing here aliases).
-__global__ void finalise_kernel(const DevProblem P, const double* __restrict__ prefill,
+// `prefill` is the caller's crsw*C (uploaded with LWB200_GAMMA, scale = 1), or C itself kept on the
+// device (LWB200_COLLISIONS) with scale = crsw: the product is rounded before the sum, as the host's is.
+__global__ void finalise_kernel(const DevProblem P, const double* __restrict__ prefill, double scale,
                                 double* __restrict__ gamma)
 {
     const double* __restrict__ accum = P.accum;
@@ -619,7 +621,7 @@ __global__ void finalise_kernel(const DevProblem P, const double* __restrict__ p
                 continue;
             // Gamma(j, i): rate from i to j
             const size_t r = (size_t)(j * N + i) * P.K;
-            const double v = prefill[gOff + r] + accum[aOff + r];
+            const double v = __dadd_rn(__dmul_rn(prefill[gOff + r], scale), accum[aOff + r]);
             gamma[gOff + r] = v;
             diag += v;
         }

@@ -79,6 +79,43 @@ def test_cuda_vs_oracle_multicolumn_c1(solver, tileLen, monkeypatch):
     ctx.close()
 
 
+def test_collisional_prefill_on_device_follows_crsw_and_changed_rates():
+    """Gamma = crsw * C (LwMiddleLayer.pyx:3198-3203) is made on the device from the resident collisional
+    rates: a crsw other than 1, rates changed on the host (fixCollisionalRates=False sends them again), and
+    an uploaded prefill taking over again (lwb200_upload(LWB200_GAMMA))."""
+    p = synth.tiny_problem(ncol=2, perturb=True)
+    q = p.clone()
+    ctx = Context(p)
+
+    def oracle(crsw):
+        q.prefill_gamma(crsw)
+        for c in range(q.Ncol):
+            o = oraclelib.OracleContext(q, col=c)
+            o.fs_iter(lambdaIterate=False)
+            o.stat_eq()
+
+    ctx.formal_sol_gamma_matrices(crsw=0.37)
+    ctx.stat_equil()
+    oracle(0.37)
+    assert_close(p, q)
+    for a, b in zip(p.active_atoms(), q.active_atoms()):
+        a.C *= 1.7
+        b.C *= 1.7
+    ctx.formal_sol_gamma_matrices(fixCollisionalRates=False, crsw=1.0)
+    ctx.stat_equil()
+    oracle(1.0)
+    assert_close(p, q)
+    # the device-resident path with an uploaded prefill (what the plugin and the sharded runs use)
+    p.prefill_gamma(0.5)
+    ctx.upload(capi.ITER_INPUTS)
+    ctx.fs_iter_device()
+    ctx.download(capi.ITER_OUTPUTS)
+    ctx.stat_equil()
+    oracle(0.5)
+    assert_close(p, q)
+    ctx.close()
+
+
 def test_dj_index_is_argmax_wavelength():
     p = synth.tiny_problem()
     q = p.clone()
