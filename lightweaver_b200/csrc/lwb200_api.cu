@@ -1839,7 +1839,7 @@ int lwb200_ng_configure(LwB200Context* c, int32_t Norder, int32_t Nperiod, int32
     c->ngRing.release();
     c->ngMax.release();
     c->ngIdx.release();
-    if (c->ngRing.alloc((size_t)R * c->n.n) || c->ngMax.alloc(c->prob.Natom) || c->ngIdx.alloc(c->prob.Natom))
+    if (c->ngRing.alloc((size_t)R * c->n.n) || c->ngMax.alloc((size_t)c->prob.Natom * (kNgParts + 1)) || c->ngIdx.alloc((size_t)c->prob.Natom * (kNgParts + 1)))
         return 1;
     if (!c->ngHostMax)
     {
@@ -1911,13 +1911,19 @@ int lwb200_ng_accelerate(LwB200Context* c, int32_t* accelerated, double* dMax, i
     if (c->ngCount >= 2)
     {
         // max_change(): the last two stored solutions (Ng.hpp:138-156)
-        ng_max_change_kernel<<<Natom, 256, 0, c->stream>>>(c->P, c->ngRing.p + (size_t)((c->ngCount - 1) % R) * stride,
-                                                          c->ngRing.p + (size_t)((c->ngCount - 2) % R) * stride,
-                                                          c->ngMax.p, c->ngIdx.p);
+        const size_t perAtom = (size_t)c->prob.Ncol * c->P.maxNlevel * c->P.K;
+        const int nParts = (int)std::min<size_t>(kNgParts, std::max<size_t>(1, perAtom / 4096));
+        ng_max_change_kernel<<<dim3(Natom, nParts), 256, 0, c->stream>>>(
+            c->P, c->ngRing.p + (size_t)((c->ngCount - 1) % R) * stride,
+            c->ngRing.p + (size_t)((c->ngCount - 2) % R) * stride, c->ngMax.p, c->ngIdx.p);
         CU(cudaGetLastError());
-        c->lastLaunches += 1;
-        CU(cudaMemcpyAsync(c->ngHostMax, c->ngMax.p, Natom * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(c->ngHostIdx, c->ngIdx.p, Natom * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        ng_max_change_final_kernel<<<Natom, kNgParts, 0, c->stream>>>(nParts, c->ngMax.p, c->ngIdx.p);
+        CU(cudaGetLastError());
+        c->lastLaunches += 2;
+        CU(cudaMemcpy2DAsync(c->ngHostMax, sizeof(double), c->ngMax.p, (kNgParts + 1) * sizeof(double), sizeof(double),
+                             Natom, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpy2DAsync(c->ngHostIdx, sizeof(long long), c->ngIdx.p, (kNgParts + 1) * sizeof(long long),
+                             sizeof(long long), Natom, cudaMemcpyDeviceToHost, c->stream));
     }
     if (async)
         return 0;

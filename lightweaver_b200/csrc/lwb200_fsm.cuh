@@ -13,16 +13,24 @@
 
 namespace lwb200
 {
-// 1/x to ~1 ulp: hardware seed + two Newton steps (no IEEE corner cases needed:
-// every argument here is a finite positive opacity, path length or optical depth)
+// 1/x to ~1 ulp: hardware seed (relative error e0 <= 2^-20) + one cubic step,
+// r = r0 (1 + e + e^2) with e = 1 - x r0, which leaves e0^3 < 2^-60 in three dependent fused
+// multiply-adds (two Newton steps take four).  No IEEE corner cases needed: every argument here is a
+// finite positive opacity, path length or optical depth.
 __device__ __forceinline__ double rcp_fast(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#ifdef LWB200_RCP_NEWTON2
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     r = fma(r, e, r);
+#else
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    r = fma(r, t, r);
+#endif
     return r;
 }
 

@@ -141,6 +141,11 @@ ng_accelerate_kernel(const DevProblem P, double* __restrict__ ring, int R, size_
 }
 
 // Ng::max_change (:138-156) per atom over every active column: max |(cur - old) / cur|, first index.
+// Grid (atom, part): every CTA reduces a contiguous share of the atom's [Ncol][Nlevel][K] elements into
+// slot 1 + part of that atom's row of outMax / outIdx (rows of kNgParts + 1); ng_max_change_final_kernel
+// folds the parts into slot 0.  (One CTA per atom was 4 ms on a 4096-column stack.)
+constexpr int kNgParts = 128;
+
 __global__ void __launch_bounds__(256)
 ng_max_change_kernel(const DevProblem P, const double* __restrict__ cur, const double* __restrict__ old,
                      double* __restrict__ outMax, long long* __restrict__ outIdx)
@@ -149,10 +154,13 @@ ng_max_change_kernel(const DevProblem P, const double* __restrict__ cur, const d
     __shared__ long long sIdx[256];
     const int atom = blockIdx.x;
     const long long len = (long long)P.atomNlevel[atom] * P.K;
+    const long long total = len * P.Ncol;
+    const long long per = (total + gridDim.y - 1) / gridDim.y;
+    const long long qBeg = per * blockIdx.y, qEnd = qBeg + per < total ? qBeg + per : total;
     double best = 0.0;
     long long bestIdx = 0;
     if (!P.atomDetailed[atom])
-        for (long long q = threadIdx.x; q < len * P.Ncol; q += blockDim.x)
+        for (long long q = qBeg + threadIdx.x; q < qEnd; q += blockDim.x)
         {
             const long long col = q / len, e = q % len;
             if (P.colActive && !P.colActive[col])
@@ -174,8 +182,26 @@ ng_max_change_kernel(const DevProblem P, const double* __restrict__ cur, const d
     dj_block_reduce(sMax, sIdx);
     if (threadIdx.x == 0)
     {
-        outMax[atom] = sMax[0];
-        outIdx[atom] = sIdx[0];
+        outMax[(size_t)atom * (kNgParts + 1) + 1 + blockIdx.y] = sMax[0];
+        outIdx[(size_t)atom * (kNgParts + 1) + 1 + blockIdx.y] = sIdx[0];
+    }
+}
+
+__global__ void __launch_bounds__(kNgParts)
+ng_max_change_final_kernel(int nParts, double* __restrict__ outMax, long long* __restrict__ outIdx)
+{
+    __shared__ double sMax[kNgParts];
+    __shared__ long long sIdx[kNgParts];
+    const size_t row = (size_t)blockIdx.x * (kNgParts + 1);
+    const bool have = (int)threadIdx.x < nParts;
+    sMax[threadIdx.x] = have ? outMax[row + 1 + threadIdx.x] : 0.0;
+    sIdx[threadIdx.x] = have ? outIdx[row + 1 + threadIdx.x] : 0;
+    dj_block_reduce(sMax, sIdx);
+    if (threadIdx.x == 0)
+    {
+        // (no change anywhere: index 0, as a serial first-max scan would report)
+        outMax[row] = sMax[0];
+        outIdx[row] = sMax[0] > 0.0 ? sIdx[0] : 0;
     }
 }
 

@@ -120,9 +120,12 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
     const int cb = blockIdx.y, col = column_of(P, colBase + cb);
     const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0);
     const int lane = lane_id();
-    double* warpS = dynS + 4 * RS + (size_t)(warp & 3) * (NCONST + NMOM) * RS;
+    constexpr int NPROW = NL > 0 ? NL : 0;    // this ray's profile rows, parked for the moment phase
+    double* warpS = dynS + 4 * RS + (size_t)(warp & 3) * (NCONST + NMOM + NPROW + 1) * RS;
     double* cS = warpS + lane;                // constants: this lane's element of chunk 0 of array 0
     double* mS = warpS + NCONST * RS + lane;  // moments
+    double* pS = warpS + (NCONST + NMOM) * RS + lane;          // profile rows of the current ray
+    double* jS = warpS + (NCONST + NMOM + NPROW) * RS + lane;  // J-dagger of this wavelength
 
     {
         DepthComm<false> cm{nullptr, 0, 1, 0};
@@ -151,6 +154,7 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
     const double* ncol = P.n + (size_t)col * P.NlevTot * K;
     auto cst = [&](int arr, int j) -> double& { return cS[(arr * NCH + j) * 32]; };
     auto momr = [&](int arr, int j) -> double& { return mS[(arr * NCH + j) * 32]; };
+    auto prow = [&](int arr, int j) -> double& { return pS[(arr * NCH + j) * 32]; };
 
     for (int q = first; q < min(first + perWarp, nLam); ++q)
     {
@@ -174,6 +178,7 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
             const double sca = v ? __ldg(P.scaBg + rowLK + k) : 0.0;
             const double JDag = (v && !noScatter) ? P.J[rowLK + k] : 0.0;
             cst(2, j) = sca * JDag;
+            jS[j * 32] = v ? P.J[rowLK + k] : 0.0;
 #pragma unroll
             for (int m = 0; m < NMOM; ++m)
                 momr(m, j) = 0.0;
@@ -319,10 +324,24 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
                 }
             }
         };
-        prefetch_row(0);
-        prefetch_row(1);
+        prefetch_row(shareDir ? 2 : 1);
+        prefetch_row(shareDir ? 4 : 2);
 
+        // The profile rows travel through registers ONE RAY AHEAD: they are loaded right after the previous
+        // ray's opacities are formed (into the registers those just freed -- the rows the moment phase needs
+        // are parked in shared memory meanwhile), so a ray never waits for the L1/L2 latency of its own loads.
         double S[NCH], rchi[NCH], SN[NCH], DSf[NCH], p[NLA][NCH];
+        auto load_row = [&](int row) {
+            if (NL > 0 && row < 2 * M)
+            {
+#pragma unroll
+                for (int l = 0; l < NLA; ++l)
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+                        p[l][j] = (lane * NCH + j < K) ? __ldg(ph[l] + (size_t)row * K + j) : 0.0;
+            }
+        };
+        load_row(0);
         RayCoef<NCH> coef;
         const int laneE = (K - 1) / NCH, jE = (K - 1) % NCH; // where the deepest point lives
 #pragma unroll 1
@@ -344,7 +363,6 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
 #pragma unroll
                     for (int j = 0; j < NCH; ++j)
                     {
-                        p[0][j] = 0.0;
                         S[j] = cst(0, j);
                         rchi[j] = cst(1, j);
                         pre.SN[j] = cst(2, j);
@@ -356,12 +374,7 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
                 else
                 {
                     double chi[NCH];
-                    prefetch_row(shareDir ? ray + 4 : ray + 2);
-#pragma unroll
-                    for (int l = 0; l < NLA; ++l)
-#pragma unroll
-                        for (int j = 0; j < NCH; ++j)
-                            p[l][j] = (lane * NCH + j < K) ? __ldg(ph[l] + (size_t)ray * K + j) : 0.0;
+                    prefetch_row(shareDir ? ray + 6 : ray + 3);
 #pragma unroll
                     for (int j = 0; j < NCH; ++j)
                     {
@@ -371,11 +384,13 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
                         {
                             c = fma(cst(3 + 2 * l, j), p[l][j], c);
                             e = fma(cst(4 + 2 * l, j), p[l][j], e);
+                            prow(l, j) = p[l][j];
                         }
                         chi[j] = c;
                         rchi[j] = rcp_fast(c);
                         S[j] = (e + cst(2, j)) * rchi[j]; // compute_source_fn (:169-179)
                     }
+                    load_row(shareDir ? ray + 2 : ray + 1);
                     bezier3_prepare_s<NCH>(g, lane, chi, S, muz, zmu, pre);
                 }
                 interval_coeffs<NCH>(pre, coef);
@@ -415,15 +430,16 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
                 momr(1, j) += wP;
                 if (NL > 0)
                 {
-                    double tq[NLA];
+                    double tq[NLA], pq[NLA];
 #pragma unroll
                     for (int l = 0; l < NLA; ++l)
                     {
-                        tq[l] = wP * p[l][j];
-                        momr(2 + 4 * l, j) = fma(w, p[l][j], momr(2 + 4 * l, j));
-                        momr(3 + 4 * l, j) = fma(wI, p[l][j], momr(3 + 4 * l, j));
+                        pq[l] = prow(l, j);
+                        tq[l] = wP * pq[l];
+                        momr(2 + 4 * l, j) = fma(w, pq[l], momr(2 + 4 * l, j));
+                        momr(3 + 4 * l, j) = fma(wI, pq[l], momr(3 + 4 * l, j));
                         momr(4 + 4 * l, j) += tq[l];
-                        momr(5 + 4 * l, j) = fma(tq[l], p[l][j], momr(5 + 4 * l, j));
+                        momr(5 + 4 * l, j) = fma(tq[l], pq[l], momr(5 + 4 * l, j));
                     }
                     if (NL > 1)
                     {
@@ -433,7 +449,7 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
 #pragma unroll
                             for (int b2 = a2 + 1; b2 < NLA; ++b2)
                             {
-                                momr(2 + 4 * NL + pr, j) = fma(tq[a2], p[b2][j], momr(2 + 4 * NL + pr, j));
+                                momr(2 + 4 * NL + pr, j) = fma(tq[a2], pq[b2], momr(2 + 4 * NL + pr, j));
                                 ++pr;
                             }
                     }
@@ -453,7 +469,7 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
             if (k < K)
             {
                 const double mJ = momr(0, j);
-                const double JDag = P.J[rowLK + k];
+                const double JDag = jS[j * 32];
                 P.J[rowLK + k] = mJ;
                 const double d = fabs(1.0 - JDag / mJ);
                 dJ = (d < dJ) ? dJ : d;
@@ -494,7 +510,8 @@ constexpr size_t ray_smem_bytes()
     constexpr int NPAIR = NL > 1 ? NL * (NL - 1) / 2 : 0;
     constexpr int NCONST = (3 + 2 * NLA) > 6 ? (3 + 2 * NLA) : 6;
     constexpr int NMOM = 2 + 4 * (NL > 0 ? NL : 0) + NPAIR;
-    return (size_t)(4 + 4 * (NCONST + NMOM)) * 32 * NCH * sizeof(double);
+    constexpr int NPROW = NL > 0 ? NL : 0;
+    return (size_t)(4 + 4 * (NCONST + NMOM + NPROW + 1)) * 32 * NCH * sizeof(double);
 }
 
 } // namespace lwb200
