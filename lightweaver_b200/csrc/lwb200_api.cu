@@ -192,6 +192,8 @@ struct LwB200Context
     cudaStream_t copyStream = nullptr;
     cudaEvent_t evRays = nullptr, evCopy = nullptr;
     bool fetchEarly = false, fetched = false, outputsPinned = false;
+    bool finaliseEarly = false;    // column stacks: finalise + send Gamma and the rates home batch by batch
+    bool finalisedEarly = false, fetchedGR = false;
     bool ioPinned = false; // populations, Gamma, rates, nStar ... are pinned in place: strided DMA, no staging
     cudaStream_t sideStream[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t evFork = nullptr, evJoin[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -853,7 +855,10 @@ int build_plan(LwB200Context* c)
         // columns per pipeline batch: chiC + etaC + moments of one batch stay under ~3 GB
         const size_t perCol = ((size_t)2 * L + c->momRows) * K * sizeof(double);
         const size_t cap = (size_t)3 << 30;
-        c->batchCols = (int)std::max<size_t>(1, std::min<size_t>(p.Ncol, std::min<size_t>(512, cap / perCol)));
+        size_t want = 512;
+        if (const char* e = std::getenv("LWB200_BATCH_COLS"))
+            want = (size_t)std::max(1, atoi(e));
+        c->batchCols = (int)std::max<size_t>(1, std::min<size_t>(p.Ncol, std::min<size_t>(want, cap / perCol)));
     }
 
     // ---- device allocations
@@ -1077,6 +1082,18 @@ static inline int launch_columns(const LwB200Context* c)
 }
 
 // (max, argmax) of dJ over [laLo, laHi) of every column into djOut / djIdx, on stream s
+// finalise_Gamma of columns [colBase, colBase + ncols) on the context's stream
+static int launch_finalise(LwB200Context* c, int colBase, int ncols)
+{
+    const size_t total = (size_t)ncols * c->P.Natom * c->P.maxNlevel * c->P.K;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((total + 127) / 128, 148 * 32));
+    finalise_kernel<<<grid, 128, 0, c->stream>>>(
+        c->P, c->prefillFromC ? c->collC.p : c->prefill.p, c->prefillFromC ? c->crswC : 1.0, c->gamma.p, colBase, ncols);
+    CU(cudaGetLastError());
+    c->lastLaunches += 1;
+    return 0;
+}
+
 static int launch_dj_reduce(LwB200Context* c, cudaStream_t s, int laLo, int laHi, const unsigned char* mask)
 {
     const long long total = (long long)c->P.Ncol * (laHi - laLo);
@@ -1368,7 +1385,7 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
                                cudaMemcpyDeviceToHost, c->copyStream));
             if (colBase + nb >= Ncol)
             {
-                CU(cudaEventRecord(c->evCopy, c->copyStream));
+                CU(cudaEventRecord(c->evCopy, c->copyStream)); // (recorded again behind Gamma and the rates below)
                 c->fetched = true;
             }
         }
@@ -1384,6 +1401,41 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
         {
             if (launch_gamma_tiles(c, pl, nb, colBase, laLo, laHi))
                 return 1;
+        }
+        if (c->finaliseEarly && c->fetchEarly && !pl.prdOnly && c->nListDirect == 0)
+        {
+            // this batch's Gamma and rates are complete as well: finalise its columns and send them home
+            // behind its J and I, under the following batches (only the last batch's copies are exposed)
+            const LwB200Problem& p = c->prob;
+            const size_t D = sizeof(double), Ks = (size_t)K;
+            if (c->P.GammaTot > 0 && launch_finalise(c, colBase, nb))
+                return 1;
+            CU(cudaEventRecord(c->evRays, c->stream));
+            CU(cudaStreamWaitEvent(c->copyStream, c->evRays, 0));
+            for (int a = 0; a < p.Natom; ++a)
+            {
+                if (c->atoms[a].detailedStatic)
+                    continue;
+                const size_t N2 = (size_t)c->atoms[a].Nlevel * c->atoms[a].Nlevel;
+                CU(cudaMemcpy2DAsync(c->atoms[a].Gamma + colBase * N2 * Ks, N2 * Ks * D,
+                                     c->gamma.p + ((size_t)colBase * c->P.GammaTot + c->atomGammaOff[a]) * Ks,
+                                     (size_t)c->P.GammaTot * Ks * D, N2 * Ks * D, nb, cudaMemcpyDeviceToHost, c->copyStream));
+            }
+            for (size_t g = 0; g < c->trans.size(); ++g)
+            {
+                const LwB200Transition& t = c->trans[g].t;
+                const DevTrans& d = c->devTrans[g];
+                const double* src = c->accum.p + (size_t)colBase * c->P.AccTot * Ks;
+                CU(cudaMemcpy2DAsync(t.Rij + colBase * Ks, Ks * D, src + (size_t)d.accRij * Ks, (size_t)c->P.AccTot * Ks * D,
+                                     Ks * D, nb, cudaMemcpyDeviceToHost, c->copyStream));
+                CU(cudaMemcpy2DAsync(t.Rji + colBase * Ks, Ks * D, src + (size_t)d.accRji * Ks, (size_t)c->P.AccTot * Ks * D,
+                                     Ks * D, nb, cudaMemcpyDeviceToHost, c->copyStream));
+            }
+            if (colBase + nb >= Ncol)
+            {
+                CU(cudaEventRecord(c->evCopy, c->copyStream));
+                c->finalisedEarly = c->fetchedGR = true;
+            }
         }
     }
     return 0;
@@ -2228,6 +2280,9 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
         CU(cudaStreamWaitEvent(s, c->evCopy, 0));
         c->fetched = false;
         mask &= ~(uint32_t)(LWB200_JBAR | LWB200_INTENS);
+        if (c->fetchedGR)
+            mask &= ~(uint32_t)(LWB200_GAMMA | LWB200_RATES);
+        c->fetchedGR = false;
     }
     if ((mask & LWB200_STOKES) && c->polTot > 0)
         CU(cudaMemcpyAsync(p.Quv, c->Quv.p, ncol * 3 * L * M * D, D2H, s));
@@ -2391,10 +2446,8 @@ int lwb200_finalise(LwB200Context* c)
     if (c->P.GammaTot > 0)
     {
         const size_t total = (size_t)c->P.Ncol * c->P.Natom * c->P.maxNlevel * c->P.K;
-        finalise_kernel<<<grid_for(total, 128), 128, 0, c->stream>>>(
-            c->P, c->prefillFromC ? c->collC.p : c->prefill.p, c->prefillFromC ? c->crswC : 1.0, c->gamma.p);
-        CU(cudaGetLastError());
-        c->lastLaunches += 1;
+        if (launch_finalise(c, 0, c->P.Ncol))
+            return 1;
     }
     return 0;
 }
@@ -2486,6 +2539,10 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
         CU(cudaStreamWaitEvent(c->stream, c->evCopy, 0));
         c->fetched = false;
     }
+    // column stacks with their per-iteration host arrays pinned in place: Gamma is finalised and, with the
+    // rates, sent home batch by batch (two or more batches; a single batch has nothing to hide them under)
+    c->finaliseEarly = c->fetchEarly && c->ioPinned && !(flags & LWB200_DEFER_FINALISE) && c->prob.Ncol > c->batchCols;
+    c->finalisedEarly = c->fetchedGR = false;
     if (storeDepth && !c->depthChi.p)
         return fail("lwb200_fs_iter: STORE_DEPTH without depth arrays in the problem");
     c->lastLaunches = 0;
@@ -2510,7 +2567,7 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
     c->djEarly = false;
     if (rcFs)
         return 1;
-    if (!(flags & LWB200_DEFER_FINALISE))
+    if (!(flags & LWB200_DEFER_FINALISE) && !c->finalisedEarly)
         if (lwb200_finalise(c))
             return 1;
     if (flags & LWB200_DJ_ASYNC)

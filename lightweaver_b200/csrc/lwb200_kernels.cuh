@@ -596,19 +596,20 @@ __global__ void zero_accum_kernel(const DevProblem P, int nActive)
 // the atom's Gamma at one depth, loads issued together (nothing here aliases).
 // `prefill` is the caller's crsw*C (uploaded with LWB200_GAMMA, scale = 1), or C itself kept on the
 // device (LWB200_COLLISIONS) with scale = crsw: the product is rounded before the sum, as the host's is.
+// Columns [colBase, colBase + ncols): a column stack finalises (and sends home) batch by batch.
 __global__ void finalise_kernel(const DevProblem P, const double* __restrict__ prefill, double scale,
-                                double* __restrict__ gamma)
+                                double* __restrict__ gamma, int colBase, int ncols)
 {
     const double* __restrict__ accum = P.accum;
     const int maxN = P.maxNlevel;
-    const size_t total = (size_t)P.Ncol * P.Natom * maxN * P.K;
+    const size_t total = (size_t)ncols * P.Natom * maxN * P.K;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x)
     {
         const int k = idx % P.K;
         const int i = (idx / P.K) % maxN;
         const int atom = (idx / ((size_t)P.K * maxN)) % P.Natom;
-        const int col = idx / ((size_t)P.K * maxN * P.Natom);
+        const int col = colBase + (int)(idx / ((size_t)P.K * maxN * P.Natom));
         const int N = P.atomNlevel[atom];
         if (P.atomDetailed[atom] || i >= N || (P.colActive && !P.colActive[col]))
             continue;
