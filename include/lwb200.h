@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LWB200_ABI_VERSION 5
+#define LWB200_ABI_VERSION 6
 
 /* TransitionType, Source/LwTransition.hpp:10-14 */
 enum { LWB200_LINE = 0, LWB200_CONTINUUM = 1 };
@@ -92,6 +92,33 @@ typedef struct LwB200Atom {
                                 lwb200_nr_post_update, may be NULL otherwise */
 } LwB200Atom;
 
+/* Hybrid PRD (Leenaarts et al. 2012): what configure_hprd_coeffs (Source/Prd.cpp:697-946) leaves in
+ * Spectrum::{prdActive, la_to_prdLa, hPrdIdxs, JCoeffs, JRest} (Source/LwMisc.hpp:94-104) and in
+ * Transition::hPrdCoeffs (Source/LwTransition.hpp:65) of every PRD line, flattened.  With it the emission
+ * profile ratio of a PRD line is interpolated per ray to the rest-frame wavelength
+ * (Transition::uv, LwTransition.hpp:115-130), the formal solution scatters w_mu/2 * frac * I into the
+ * rest-frame mean intensity JRest (SimdFullIterationTemplates.hpp:397-408), and the redistribution reads
+ * JRest instead of J (Prd.cpp:384-389, :484-489). */
+typedef struct LwB200HybridPrd {
+    int32_t NprdLa;            /* wavelengths at which a PRD line is active: rows of JRest */
+    int32_t NhPrd;             /* wavelengths that scatter into them (spect.hPrdIdxs.size()); the set depends on the
+                                  velocity field, so on the column: the largest count of any column (table stride) */
+    int32_t Nlines;            /* PRD lines carrying interpolation coefficients */
+    int32_t reserved;
+    const int32_t* prdLaOfLa;  /* [Nspect] spect.la_to_prdLa where spect.prdActive, else -1 */
+    const int32_t* hPrdLaOfLa; /* [Ncol][Nspect] spect.la_to_hPrdLa where spect.hPrdActive, else -1 */
+    double* JRest;             /* [Ncol][NprdLa][Nspace] out of the formal solutions, in of the redistribution */
+    const int64_t* JCoeffOff;  /* [Ncol * NhPrd * Nrays * 2 * Nspace + 1] offsets of JCoeffs(hPrdLa, mu, toObs, k) at
+                                  ((((col * NhPrd + hPrdLa) * Nrays + mu) * 2 + toObs) * Nspace + k) */
+    const int32_t* JCoeffIdx;  /* [JCoeffOff[last]] JInterpCoeffs::idx (row of JRest) */
+    const double* JCoeffFrac;  /* [JCoeffOff[last]] JInterpCoeffs::frac */
+    const int32_t* lineAtom;   /* [Nlines] index into problem->atoms */
+    const int32_t* lineTrans;  /* [Nlines] index into that atom's trans */
+    const int64_t* rhoCoefOff; /* [Nlines] element offset of a line's coefficients in rhoFrac / rhoI0 */
+    const double* rhoFrac;     /* per line [Ncol][Nlambda][Nrays][2][Nspace] RhoInterpCoeffs::frac */
+    const int32_t* rhoI0;      /* same shape: RhoInterpCoeffs::i0 (i1 is always i0 + 1) */
+} LwB200HybridPrd;
+
 /* What the hot path reads from / writes to a Context (Source/LwContext.hpp:20-45). */
 typedef struct LwB200Problem {
     int32_t abiVersion;    /* LWB200_ABI_VERSION */
@@ -129,6 +156,7 @@ typedef struct LwB200Problem {
                                   (LwMisc.hpp:94), or NULL */
     double* ne;                /* [Ncol][Nspace] electron density (atmos.ne): in/out of lwb200_nr_post_update,
                                   or NULL */
+    const LwB200HybridPrd* hprd; /* hybrid PRD tables, or NULL: every PRD line is angle-averaged */
 } LwB200Problem;
 
 /* Input/output groups for lwb200_upload / lwb200_download. */

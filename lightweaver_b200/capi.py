@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 LINE, CONTINUUM = 0, 1
 BC_UNINITIALISED, BC_ZERO, BC_THERMALISED, BC_PERIODIC, BC_CALLABLE = range(5)
@@ -54,6 +54,18 @@ class LwB200Atom(C.Structure):
     ]
 
 
+_lp = C.POINTER(C.c_int64)
+
+
+class LwB200HybridPrd(C.Structure):
+    _fields_ = [
+        ('NprdLa', C.c_int32), ('NhPrd', C.c_int32), ('Nlines', C.c_int32), ('reserved', C.c_int32),
+        ('prdLaOfLa', _ip), ('hPrdLaOfLa', _ip), ('JRest', _dp),
+        ('JCoeffOff', _lp), ('JCoeffIdx', _ip), ('JCoeffFrac', _dp),
+        ('lineAtom', _ip), ('lineTrans', _ip), ('rhoCoefOff', _lp), ('rhoFrac', _dp), ('rhoI0', _ip),
+    ]
+
+
 class LwB200Problem(C.Structure):
     _fields_ = [
         ('abiVersion', C.c_int32), ('Ncol', C.c_int32), ('Nspace', C.c_int32),
@@ -65,6 +77,7 @@ class LwB200Problem(C.Structure):
         ('lowerBcData', _dp), ('upperBcData', _dp), ('lowerBcIdx', _ip), ('upperBcIdx', _ip),
         ('J', _dp), ('I', _dp), ('depthChi', _dp), ('depthEta', _dp), ('depthI', _dp),
         ('atoms', C.POINTER(LwB200Atom)), ('Quv', _dp), ('ne', _dp),
+        ('hprd', C.POINTER(LwB200HybridPrd)),
     ]
 
 

@@ -82,6 +82,81 @@ class AtomData:
 
 
 @dataclass
+class HybridPrd:
+    """Hybrid-PRD tables (reference: what ``configure_hprd_coeffs``, Source/Prd.cpp:697-946, leaves in
+    ``Spectrum`` and in every PRD line's ``hPrdCoeffs``), flattened as ``LwB200HybridPrd`` lays them out."""
+    NprdLa: int
+    NhPrd: int
+    prdLaOfLa: np.ndarray     # [Nspect] int32
+    hPrdLaOfLa: np.ndarray    # [Ncol, Nspect] int32
+    JRest: np.ndarray         # [Ncol, NprdLa, Nspace]
+    JCoeffOff: np.ndarray     # [Ncol*NhPrd*Nrays*2*Nspace + 1] int64
+    JCoeffIdx: np.ndarray     # [nnz] int32
+    JCoeffFrac: np.ndarray    # [nnz]
+    lineAtom: np.ndarray      # [Nlines] int32
+    lineTrans: np.ndarray     # [Nlines] int32
+    rhoCoefOff: np.ndarray    # [Nlines] int64
+    rhoFrac: np.ndarray       # per line [Ncol, Nlambda, Nrays, 2, Nspace], back to back
+    rhoI0: np.ndarray         # int32, same layout
+
+    @staticmethod
+    def from_c(h, problem):
+        """Copy a C-side LwB200HybridPrd (malloc'ed by a configure routine) into numpy arrays."""
+        Ncol, L, K, M = problem.Ncol, problem.Nspect, problem.Nspace, problem.Nrays
+
+        def arr(ptr, n, dtype):
+            if n == 0:
+                return np.zeros(0, dtype=dtype)
+            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+        nRows = Ncol * h.NhPrd * M * 2 * K
+        off = arr(h.JCoeffOff, nRows + 1, np.int64)
+        nnz = int(off[-1])
+        nl = h.Nlines
+        lineAtom, lineTrans = arr(h.lineAtom, nl, np.int32), arr(h.lineTrans, nl, np.int32)
+        tot = sum(Ncol * problem.atoms[a].trans[t].Nlambda * M * 2 * K for a, t in zip(lineAtom, lineTrans))
+        return HybridPrd(NprdLa=h.NprdLa, NhPrd=h.NhPrd, prdLaOfLa=arr(h.prdLaOfLa, L, np.int32),
+                         hPrdLaOfLa=arr(h.hPrdLaOfLa, Ncol * L, np.int32).reshape(Ncol, L),
+                         JRest=arr(h.JRest, Ncol * h.NprdLa * K, np.float64).reshape(Ncol, h.NprdLa, K),
+                         JCoeffOff=off, JCoeffIdx=arr(h.JCoeffIdx, nnz, np.int32),
+                         JCoeffFrac=arr(h.JCoeffFrac, nnz, np.float64), lineAtom=lineAtom, lineTrans=lineTrans,
+                         rhoCoefOff=arr(h.rhoCoefOff, nl, np.int64), rhoFrac=arr(h.rhoFrac, tot, np.float64),
+                         rhoI0=arr(h.rhoI0, tot, np.int32))
+
+    def c_struct(self, keep):
+        h = capi.LwB200HybridPrd()
+        h.NprdLa, h.NhPrd, h.Nlines = self.NprdLa, self.NhPrd, len(self.lineAtom)
+        lp = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+        h.prdLaOfLa, h.hPrdLaOfLa = capi.iptr(self.prdLaOfLa), capi.iptr(self.hPrdLaOfLa)
+        h.JRest = capi.dptr(self.JRest)
+        h.JCoeffOff, h.JCoeffIdx, h.JCoeffFrac = lp(self.JCoeffOff), capi.iptr(self.JCoeffIdx), capi.dptr(self.JCoeffFrac)
+        h.lineAtom, h.lineTrans = capi.iptr(self.lineAtom), capi.iptr(self.lineTrans)
+        h.rhoCoefOff, h.rhoFrac, h.rhoI0 = lp(self.rhoCoefOff), capi.dptr(self.rhoFrac), capi.iptr(self.rhoI0)
+        keep.append(h)
+        return C.pointer(h)
+
+    def column(self, c, problem):
+        """The tables of column ``c`` alone (JRest is a view)."""
+        K, M = problem.Nspace, problem.Nrays
+        per = self.NhPrd * M * 2 * K
+        off = self.JCoeffOff[c * per:(c + 1) * per + 1]
+        e0, e1 = int(off[0]), int(off[-1])
+        fr, i0, ro, o = [], [], [], 0
+        for q, (a, t) in enumerate(zip(self.lineAtom, self.lineTrans)):
+            n = problem.atoms[a].trans[t].Nlambda * M * 2 * K
+            b = int(self.rhoCoefOff[q]) + c * n
+            fr.append(self.rhoFrac[b:b + n])
+            i0.append(self.rhoI0[b:b + n])
+            ro.append(o)
+            o += n
+        return HybridPrd(NprdLa=self.NprdLa, NhPrd=self.NhPrd, prdLaOfLa=self.prdLaOfLa,
+                         hPrdLaOfLa=np.ascontiguousarray(self.hPrdLaOfLa[c:c + 1]), JRest=self.JRest[c:c + 1],
+                         JCoeffOff=np.ascontiguousarray(off - e0), JCoeffIdx=np.ascontiguousarray(self.JCoeffIdx[e0:e1]),
+                         JCoeffFrac=np.ascontiguousarray(self.JCoeffFrac[e0:e1]), lineAtom=self.lineAtom,
+                         lineTrans=self.lineTrans, rhoCoefOff=np.asarray(ro, dtype=np.int64),
+                         rhoFrac=np.concatenate(fr) if fr else np.zeros(0), rhoI0=np.concatenate(i0) if i0 else np.zeros(0, np.int32))
+
+
+@dataclass
 class Problem:
     Nspace: int
     Nrays: int
@@ -111,6 +186,7 @@ class Problem:
     ne: Optional[np.ndarray] = None      # [Ncol, Nspace] (inputs of the synthetic generator; not on the path)
     vturb: Optional[np.ndarray] = None
     nHTot: Optional[np.ndarray] = None
+    hprd: Optional[HybridPrd] = None     # hybrid-PRD tables (None: every PRD line is angle-averaged)
     meta: dict = field(default_factory=dict)
     _keepalive: list = field(default_factory=list, repr=False)
 
@@ -198,7 +274,8 @@ class Problem:
                        upperBcData=sl(self.upperBcData), lowerBcIdx=self.lowerBcIdx,
                        upperBcIdx=self.upperBcIdx, depthChi=sl(self.depthChi),
                        depthEta=sl(self.depthEta), depthI=sl(self.depthI), Quv=sl(self.Quv), ne=sl(self.ne),
-                       vturb=sl(self.vturb), nHTot=sl(self.nHTot), meta=dict(self.meta))
+                       vturb=sl(self.vturb), nHTot=sl(self.nHTot), meta=dict(self.meta),
+                       hprd=None if self.hprd is None else self.hprd.column(c, self))
 
     # ------------------------------------------------------------ marshalling
     def c_struct(self):
@@ -247,6 +324,8 @@ class Problem:
             ca.stages = d(a.stages)
         keep.append(atoms)
         p.atoms = C.cast(atoms, C.POINTER(capi.LwB200Atom))
+        if self.hprd is not None:
+            p.hprd = self.hprd.c_struct(keep)
         self._keepalive.append((p, keep))
         return p
 

@@ -403,6 +403,18 @@ static void scratch_free(Scratch* s)
 
 static inline int is_active(const LwB200Transition* t, int la) { return la >= t->Nblue && la < t->Nred; }
 
+/* index of line (atom a, transition kr) in the hybrid-PRD tables (Transition::hPrdCoeffs set), or -1 */
+static int hprd_line(const LwB200Problem* p, int a, int kr)
+{
+    const LwB200HybridPrd* h = p->hprd;
+    if (!h)
+        return -1;
+    for (int q = 0; q < h->Nlines; ++q)
+        if (h->lineAtom[q] == a && h->lineTrans[q] == kr)
+            return q;
+    return -1;
+}
+
 /* Atom::setup_wavelength, LwAtom.hpp:82-128 */
 static void setup_wavelength(const LwB200Problem* p, int col, int a, int la, Scratch* s)
 {
@@ -432,7 +444,7 @@ static void setup_wavelength(const LwB200Problem* p, int col, int a, int la, Scr
                 g[k] = t->Bji / t->Bij;
                 w[k] = wlam * wphi[k] * pi4_hc;
             }
-            if (t->rhoPrd)
+            if (t->rhoPrd && hprd_line(p, a, kr) < 0) /* (t.rhoPrd && !t.hPrdCoeffs), LwAtom.hpp:121 */
             {
                 const double* rho = t->rhoPrd + ((size_t)col * Nl + lt) * K;
                 for (int k = 0; k < K; ++k)
@@ -469,6 +481,21 @@ static void uv(const LwB200Problem* p, int col, int a, int kr, int la, int mu, i
         {
             s->Vij[k] = hnu_4pi * t->Bij * ph[k];
             s->Vji[k] = g[k] * s->Vij[k];
+        }
+        /* the HPRD linear interpolation of rho to the rest-frame wavelength of this ray (:115-130) */
+        const int hq = hprd_line(p, a, kr);
+        if (hq >= 0)
+        {
+            const LwB200HybridPrd* h = p->hprd;
+            const size_t o = (size_t)h->rhoCoefOff[hq] + ((((size_t)col * Nl + lt) * M + mu) * 2 + toObs) * K;
+            const double* rho = t->rhoPrd + (size_t)col * Nl * K;
+            for (int k = 0; k < K; ++k)
+            {
+                const double frac = h->rhoFrac[o + k];
+                const int i0 = h->rhoI0[o + k], i1 = i0 + 1;
+                const double r = (1.0 - frac) * rho[(size_t)i0 * K + k] + frac * rho[(size_t)i1 * K + k];
+                s->Vji[k] *= r;
+            }
         }
         for (int k = 0; k < K; ++k)
             s->Uji[k] = t->Aji / t->Bji * s->Vji[k];
@@ -639,6 +666,20 @@ static double intensity_core_mode(const LwB200Problem* p, int col, int la, Scrat
                 const double halfwmu = 0.5 * p->wmu[mu];
                 for (int k = 0; k < K; ++k)
                     J[k] += halfwmu * s->I[k];
+                /* rest-frame mean intensity of hybrid PRD (:397-408) */
+                if (p->hprd && p->hprd->JRest)
+                {
+                    const LwB200HybridPrd* h = p->hprd;
+                    const int hPrdLa = h->hPrdLaOfLa[(size_t)col * L + la];
+                    if (hPrdLa >= 0)
+                    {
+                        double* JRest = h->JRest + (size_t)col * h->NprdLa * K;
+                        const size_t row = ((((size_t)col * h->NhPrd + hPrdLa) * M + mu) * 2 + toObs) * K;
+                        for (int k = 0; k < K; ++k)
+                            for (int64_t e = h->JCoeffOff[row + k]; e < h->JCoeffOff[row + k + 1]; ++e)
+                                JRest[(size_t)h->JCoeffIdx[e] * K + k] += 0.5 * p->wmu[mu] * h->JCoeffFrac[e] * s->I[k];
+                    }
+                }
 
                 for (int a = 0; a < p->Natom; ++a)
                 {
@@ -716,6 +757,8 @@ int lwo_fs_iter(const LwB200Problem* p, int col, unsigned flags, int laStart, in
             memset(p->atoms[a].trans[kr].Rij + (size_t)col * K, 0, sizeof(double) * K);
             memset(p->atoms[a].trans[kr].Rji + (size_t)col * K, 0, sizeof(double) * K);
         }
+    if (p->hprd && p->hprd->JRest) /* zero_Gamma_rates_JRest / :602-603 */
+        memset(p->hprd->JRest + (size_t)col * p->hprd->NprdLa * K, 0, sizeof(double) * p->hprd->NprdLa * K);
     double dJMax = 0.0, dJSerial = 0.0;
     int64_t idx = 0, idxSerial = 0;
     const int storeDepth = (flags & LWB200_STORE_DEPTH) && p->depthChi && p->depthEta && p->depthI;
@@ -1395,7 +1438,11 @@ static int prd_scatter_line(const LwB200Problem* p, int col, int a, int kr)
         double Jbar = t->Rij[(size_t)col * K + k] / t->Bij;
         for (int la = 0; la < Nl; ++la)
         {
-            Jk[la] = p->J[((size_t)col * L + la + t->Nblue) * K + k];
+            /* local mean intensity, in the rest frame if using HPRD (Prd.cpp:484-499) */
+            if (p->hprd && p->hprd->JRest)
+                Jk[la] = p->hprd->JRest[((size_t)col * p->hprd->NprdLa + p->hprd->prdLaOfLa[la + t->Nblue]) * K + k];
+            else
+                Jk[la] = p->J[((size_t)col * L + la + t->Nblue) * K + k];
             qWave[la] = (t->wavelength[la] - t->lambda0) * C_CLIGHT / (t->lambda0 * at->vBroad[(size_t)col * K + k]);
         }
         const double aDamp = t->aDamp[(size_t)col * K + k];
@@ -1470,12 +1517,19 @@ int lwo_redistribute_prd(const LwB200Problem* p, int col, int maxIter, double to
     }
     /* wavelengths touched by a PRD line (:225-240) */
     char* prdLa = (char*)calloc(L, 1);
-    for (int q = 0; q < nLines; ++q)
+    if (p->hprd && p->hprd->NhPrd > 0)
     {
-        const LwB200Transition* t = &p->atoms[lines[q][0]].trans[lines[q][1]];
-        for (int la = t->Nblue; la < t->Nred; ++la)
-            prdLa[la] = 1;
+        /* idxsForFs = spect.hPrdIdxs (:233-234) */
+        for (int la = 0; la < L; ++la)
+            prdLa[la] = p->hprd->hPrdLaOfLa[(size_t)col * L + la] >= 0;
     }
+    else
+        for (int q = 0; q < nLines; ++q)
+        {
+            const LwB200Transition* t = &p->atoms[lines[q][0]].trans[lines[q][1]];
+            for (int la = t->Nblue; la < t->Nred; ++la)
+                prdLa[la] = 1;
+        }
     Scratch* s = scratch_new(p);
     int iter = 0, rc = 0;
     while (iter < maxIter)
@@ -1516,6 +1570,8 @@ int lwo_redistribute_prd(const LwB200Problem* p, int col, int maxIter, double to
             memset(t->Rij + (size_t)col * K, 0, sizeof(double) * K);
             memset(t->Rji + (size_t)col * K, 0, sizeof(double) * K);
         }
+        if (p->hprd && p->hprd->JRest) /* PrdTemplates.hpp:57-58 */
+            memset(p->hprd->JRest + (size_t)col * p->hprd->NprdLa * K, 0, sizeof(double) * p->hprd->NprdLa * K);
         double dJMax = 0.0;
         int64_t dJIdx = 0;
         for (int la = 0; la < L; ++la)
@@ -1543,6 +1599,290 @@ done:
     free(prev);
     free(lines);
     return rc;
+}
+
+
+/* ------------------------------------------------------------------------ */
+/* configure_hprd_coeffs, Prd.cpp:697-946, column by column (every column of a stack is its own
+ * Context in the reference), flattened into LwB200HybridPrd.  The arrays are malloc'ed; release them
+ * with lwo_free_hprd. */
+typedef struct { int32_t idx; double frac; } JCoef;
+typedef struct { JCoef* v; int64_t n, cap; } JVec;
+
+static void jvec_push(JVec* q, int32_t idx, double frac)
+{
+    if (q->n == q->cap)
+    {
+        q->cap = q->cap ? 2 * q->cap : 4;
+        q->v = (JCoef*)realloc(q->v, sizeof(JCoef) * q->cap);
+    }
+    q->v[q->n].idx = idx;
+    q->v[q->n].frac = frac;
+    q->n += 1;
+}
+
+static const double* upper_bound_d(const double* first, const double* last, double value)
+{
+    /* std::upper_bound: first element greater than value */
+    while (first < last)
+    {
+        const double* mid = first + (last - first) / 2;
+        if (value < *mid)
+            last = mid;
+        else
+            first = mid + 1;
+    }
+    return first;
+}
+
+int lwo_configure_hprd(const LwB200Problem* p, int includeDetailed, LwB200HybridPrd* out)
+{
+    const int K = p->Nspace, M = p->Nrays, Nspect = p->Nspect, Ncol = p->Ncol;
+    const double sign[2] = {-1.0, 1.0};
+    memset(out, 0, sizeof(*out));
+    if (!p->vlosMu)
+        return 1;
+    /* prdLines: active atoms first, then (optionally) detailed ones (:711-734) */
+    int nLines = 0;
+    int32_t* lineAtom = (int32_t*)malloc(sizeof(int32_t) * 256);
+    int32_t* lineTrans = (int32_t*)malloc(sizeof(int32_t) * 256);
+    for (int pass = 0; pass < (includeDetailed ? 2 : 1); ++pass)
+        for (int a = 0; a < p->Natom; ++a)
+        {
+            if ((p->atoms[a].detailedStatic != 0) != (pass == 1))
+                continue;
+            for (int kr = 0; kr < p->atoms[a].Ntrans; ++kr)
+                if (p->atoms[a].trans[kr].rhoPrd && nLines < 256)
+                {
+                    lineAtom[nLines] = a;
+                    lineTrans[nLines] = kr;
+                    ++nLines;
+                }
+        }
+    if (nLines == 0)
+    {
+        free(lineAtom);
+        free(lineTrans);
+        return 0;
+    }
+    /* prdActive, la_to_prdLa (:739-757) */
+    char* prdActive = (char*)calloc(Nspect, 1);
+    int32_t* prdLaOfLa = (int32_t*)malloc(sizeof(int32_t) * Nspect);
+    int NprdLa = 0;
+    for (int la = 0; la < Nspect; ++la)
+    {
+        int present = 0;
+        for (int q = 0; q < nLines; ++q)
+            present = present || is_active(&p->atoms[lineAtom[q]].trans[lineTrans[q]], la);
+        prdLaOfLa[la] = -1;
+        if (present)
+        {
+            prdActive[la] = 1;
+            prdLaOfLa[la] = NprdLa++;
+        }
+    }
+    const double* wl = p->wavelength;
+    int32_t* hPrdLaOfLa = (int32_t*)malloc(sizeof(int32_t) * (size_t)Ncol * Nspect);
+    int* NhCol = (int*)calloc(Ncol, sizeof(int));
+    int NhPrd = 0;
+    for (int col = 0; col < Ncol; ++col)
+    {
+        const double* vlosMu = p->vlosMu + (size_t)col * M * K;
+        for (int la = 0; la < Nspect; ++la)
+        {
+            /* check_lambda_scatter_into_prd_region (:765-797) */
+            int scat = 0;
+            for (int mu = 0; mu < M && !scat; ++mu)
+                for (int toObs = 0; toObs <= 1 && !scat; ++toObs)
+                    for (int k = 0; k < K && !scat; ++k)
+                    {
+                        const double s = sign[toObs];
+                        const double fac = 1.0 + vlosMu[(size_t)mu * K + k] * s / C_CLIGHT;
+                        const int prevIndex = la - 1 > 0 ? la - 1 : 0;
+                        const int nextIndex = la + 1 < Nspect - 1 ? la + 1 : Nspect - 1;
+                        const double prevLambda = wl[prevIndex] * fac;
+                        const double nextLambda = wl[nextIndex] * fac;
+                        int i = la;
+                        for (; wl[i] > prevLambda && i > 0; --i);
+                        for (; i < Nspect; ++i)
+                        {
+                            const double lambdaI = wl[i];
+                            if (prdActive[i])
+                            {
+                                scat = 1;
+                                break;
+                            }
+                            else if (lambdaI > nextLambda)
+                                break;
+                        }
+                    }
+            hPrdLaOfLa[(size_t)col * Nspect + la] = scat ? NhCol[col]++ : -1;
+        }
+        if (NhCol[col] > NhPrd)
+            NhPrd = NhCol[col];
+    }
+    /* JCoeffs (:816-905) */
+    const size_t nRows = (size_t)Ncol * NhPrd * M * 2 * K;
+    JVec* rows = (JVec*)calloc(nRows ? nRows : 1, sizeof(JVec));
+    for (int col = 0; col < Ncol; ++col)
+    {
+        const double* vlosMu = p->vlosMu + (size_t)col * M * K;
+        for (int idx = 0; idx < Nspect; ++idx)
+        {
+            const int hPrdLa = hPrdLaOfLa[(size_t)col * Nspect + idx];
+            if (hPrdLa < 0)
+                continue;
+            for (int mu = 0; mu < M; ++mu)
+                for (int toObs = 0; toObs <= 1; ++toObs)
+                    for (int k = 0; k < K; ++k)
+                    {
+                        JVec* cv = &rows[((((size_t)col * NhPrd + hPrdLa) * M + mu) * 2 + toObs) * K + k];
+                        const double s = sign[toObs];
+                        const double fac = 1.0 + vlosMu[(size_t)mu * K + k] * s / C_CLIGHT;
+                        const int prevIndex = idx - 1 > 0 ? idx - 1 : 0;
+                        const int nextIndex = idx + 1 < Nspect - 1 ? idx + 1 : Nspect - 1;
+                        const double prevLambda = wl[prevIndex] * fac;
+                        const double lambdaRest = wl[idx] * fac;
+                        const double nextLambda = wl[nextIndex] * fac;
+                        int doLowerHalf = 1, doUpperHalf = 1;
+                        if (prevIndex == idx)
+                        {
+                            doLowerHalf = 0;
+                            for (int i = 0; i < Nspect; ++i)
+                            {
+                                if (wl[i] <= lambdaRest && prdActive[i])
+                                    jvec_push(cv, prdLaOfLa[i], 1.0);
+                                else
+                                    break;
+                            }
+                        }
+                        else if (nextIndex == idx)
+                        {
+                            doUpperHalf = 0;
+                            for (int i = Nspect - 1; i >= 0; --i)
+                            {
+                                if (wl[i] > lambdaRest && prdActive[i])
+                                    jvec_push(cv, prdLaOfLa[i], 1.0);
+                                else
+                                    break;
+                            }
+                        }
+                        int i = idx;
+                        /* (the reference reads wavelength(-1) when the roll-back passes the first point:
+                         * `spect.wavelength(i) > prevLambda && i >= 0` tests the array first; guarded here) */
+                        for (; i >= 0 && wl[i] > prevLambda; --i);
+                        if (i < 0)
+                            i = 0;
+                        for (; i < Nspect; ++i)
+                        {
+                            const double lambdaI = wl[i];
+                            if (lambdaI > nextLambda)
+                                break;
+                            if (doLowerHalf && prdActive[i] && lambdaI > prevLambda && lambdaI <= lambdaRest)
+                            {
+                                const double frac = (lambdaI - prevLambda) / (lambdaRest - prevLambda);
+                                jvec_push(cv, prdLaOfLa[i], frac);
+                            }
+                            else if (doUpperHalf && prdActive[i] && lambdaI > lambdaRest && lambdaI < nextLambda)
+                            {
+                                const double frac = (lambdaI - lambdaRest) / (nextLambda - lambdaRest);
+                                jvec_push(cv, prdLaOfLa[i], 1.0 - frac);
+                            }
+                        }
+                    }
+        }
+    }
+    int64_t* off = (int64_t*)malloc(sizeof(int64_t) * (nRows + 1));
+    int64_t nnz = 0;
+    for (size_t r = 0; r < nRows; ++r)
+    {
+        off[r] = nnz;
+        nnz += rows[r].n;
+    }
+    off[nRows] = nnz;
+    int32_t* cIdx = (int32_t*)malloc(sizeof(int32_t) * (nnz ? nnz : 1));
+    double* cFrac = (double*)malloc(sizeof(double) * (nnz ? nnz : 1));
+    for (size_t r = 0; r < nRows; ++r)
+    {
+        for (int64_t e = 0; e < rows[r].n; ++e)
+        {
+            cIdx[off[r] + e] = rows[r].v[e].idx;
+            cFrac[off[r] + e] = rows[r].v[e].frac;
+        }
+        free(rows[r].v);
+    }
+    free(rows);
+    /* hPrdCoeffs of every PRD line (:907-945) */
+    int64_t* rhoOff = (int64_t*)malloc(sizeof(int64_t) * nLines);
+    int64_t tot = 0;
+    for (int q = 0; q < nLines; ++q)
+    {
+        const LwB200Transition* t = &p->atoms[lineAtom[q]].trans[lineTrans[q]];
+        rhoOff[q] = tot;
+        tot += (int64_t)Ncol * (t->Nred - t->Nblue) * M * 2 * K;
+    }
+    double* rhoFrac = (double*)malloc(sizeof(double) * tot);
+    int32_t* rhoI0 = (int32_t*)malloc(sizeof(int32_t) * tot);
+    for (int q = 0; q < nLines; ++q)
+    {
+        const LwB200Transition* t = &p->atoms[lineAtom[q]].trans[lineTrans[q]];
+        const int Nl = t->Nred - t->Nblue;
+        const double* w = t->wavelength;
+        for (int col = 0; col < Ncol; ++col)
+        {
+            const double* vlosMu = p->vlosMu + (size_t)col * M * K;
+            for (int lt = 0; lt < Nl; ++lt)
+                for (int mu = 0; mu < M; ++mu)
+                    for (int toObs = 0; toObs <= 1; ++toObs)
+                        for (int k = 0; k < K; ++k)
+                        {
+                            const double s = sign[toObs];
+                            const double lambdaRest = w[lt] * (1.0 + vlosMu[(size_t)mu * K + k] * s / C_CLIGHT);
+                            const size_t o = (size_t)rhoOff[q] + ((((size_t)col * Nl + lt) * M + mu) * 2 + toObs) * K + k;
+                            if (lambdaRest <= w[0])
+                            {
+                                rhoFrac[o] = 0.0;
+                                rhoI0[o] = 0;
+                            }
+                            else if (lambdaRest >= w[Nl - 1])
+                            {
+                                rhoFrac[o] = 1.0;
+                                rhoI0[o] = Nl - 2;
+                            }
+                            else
+                            {
+                                const double* it = upper_bound_d(w, w + Nl, lambdaRest) - 1;
+                                rhoFrac[o] = (lambdaRest - *it) / (*(it + 1) - *it);
+                                rhoI0[o] = (int32_t)(it - w);
+                            }
+                        }
+        }
+    }
+    free(prdActive);
+    free(NhCol);
+    out->NprdLa = NprdLa;
+    out->NhPrd = NhPrd;
+    out->Nlines = nLines;
+    out->prdLaOfLa = prdLaOfLa;
+    out->hPrdLaOfLa = hPrdLaOfLa;
+    out->JRest = (double*)calloc((size_t)Ncol * NprdLa * K, sizeof(double));
+    out->JCoeffOff = off;
+    out->JCoeffIdx = cIdx;
+    out->JCoeffFrac = cFrac;
+    out->lineAtom = lineAtom;
+    out->lineTrans = lineTrans;
+    out->rhoCoefOff = rhoOff;
+    out->rhoFrac = rhoFrac;
+    out->rhoI0 = rhoI0;
+    return 0;
+}
+
+void lwo_free_hprd(LwB200HybridPrd* h)
+{
+    free((void*)h->prdLaOfLa); free((void*)h->hPrdLaOfLa); free(h->JRest); free((void*)h->JCoeffOff);
+    free((void*)h->JCoeffIdx); free((void*)h->JCoeffFrac); free((void*)h->lineAtom); free((void*)h->lineTrans);
+    free((void*)h->rhoCoefOff); free((void*)h->rhoFrac); free((void*)h->rhoI0);
+    memset(h, 0, sizeof(*h));
 }
 
 /* ------------------------------------------------------------------------ */

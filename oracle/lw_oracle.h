@@ -70,6 +70,15 @@ int lwo_nr_post_update(const LwB200Problem* p, int col, const LwB200NrUpdate* up
 int lwo_redistribute_prd(const LwB200Problem* p, int col, int maxIter, double tol, int includeDetailed,
                          int* nIter, double* dRho, int* dRhoIdx, double* dJPrdMax, int64_t* dJPrdMaxIdx);
 
+/* configure_hprd_coeffs (Prd.cpp:697-946) for every column of the problem (each column is its own Context
+ * in the reference), flattened into LwB200HybridPrd: prdActive / la_to_prdLa, hPrdActive / la_to_hPrdLa,
+ * JCoeffs, a zeroed JRest and the hPrdCoeffs of every PRD line.  With problem->hprd pointing at the result,
+ * lwo_fs_iter accumulates JRest (SimdFullIterationTemplates.hpp:397-408), uv interpolates rho per ray
+ * (LwTransition.hpp:115-130) and lwo_redistribute_prd works in the rest frame over hPrdIdxs.
+ * The arrays are malloc'ed: lwo_free_hprd.  Returns 1 without vlosMu. */
+int lwo_configure_hprd(const LwB200Problem* p, int includeDetailed, LwB200HybridPrd* out);
+void lwo_free_hprd(LwB200HybridPrd* h);
+
 /* Ng acceleration (Ng.hpp:16-163): constructor on sols[0], then accelerate() + max_change() on
  * sols[1..nIter]; out [nIter][len] = the solutions as accelerate() leaves them.  Returns 1 for a
  * singular acceleration system. */

@@ -44,8 +44,32 @@ def load():
     lib.lwo_time_dep_update.argtypes = [vp, C.c_int, C.c_int, dp, C.c_double]
     lib.lwo_redistribute_prd.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp,
                                          C.POINTER(C.c_int), dp, i64p]
+    lib.lwo_configure_hprd.argtypes = [vp, C.c_int, vp]
+    lib.lwo_free_hprd.argtypes = [vp]
+    lib.lwo_free_hprd.restype = None
     _lib = lib
     return lib
+
+
+def configure_hprd(problem, includeDetailed=False):
+    """configure_hprd_coeffs (Prd.cpp:697-946) restated, for every column of the problem: returns a
+    lightweaver_b200.problem.HybridPrd (assign it to problem.hprd to switch the hybrid scheme on)."""
+    from lightweaver_b200 import capi
+    from lightweaver_b200.problem import HybridPrd
+    lib = load()
+    keep, problem.hprd = problem.hprd, None
+    try:
+        cs = problem.c_struct()
+    finally:
+        problem.hprd = keep
+    h = capi.LwB200HybridPrd()
+    rc = lib.lwo_configure_hprd(C.byref(cs), int(includeDetailed), C.byref(h))
+    if rc != 0:
+        raise RuntimeError('configure_hprd: the problem has no vlosMu')
+    try:
+        return HybridPrd.from_c(h, problem) if h.Nlines > 0 else None
+    finally:
+        lib.lwo_free_hprd(C.byref(h))
 
 
 class OracleContext:

@@ -467,6 +467,113 @@ int lwref_redistribute_prd(LwRefHandle* hh, int maxIter, double tol, int include
     }
 }
 
+// configure_hprd_coeffs (LwContext.configure_hprd_coeffs -> update_threads, LwMiddleLayer.pyx): hybrid PRD of
+// this handle's column, done by the reference itself.  The tables it builds are exported, flattened exactly
+// like LwB200HybridPrd lays out ONE column, so that the oracle's restatement can be compared with them:
+//   prdLaOfLa [Nspect], hPrdLaOfLa [Nspect], JCoeffOff [NhPrd*M*2*K + 1], JCoeffIdx / JCoeffFrac [nnz],
+//   per PRD line (the order of configure_hprd_coeffs) rhoFrac / rhoI0 [Nl*M*2*K] back to back.
+// Every out pointer may be NULL; counts[0..3] = NprdLa, NhPrd, nnz, Nlines.
+int lwref_configure_hprd(LwRefHandle* hh, int includeDetailed)
+{
+    auto* h = (LwRef*)hh;
+    try
+    {
+        configure_hprd_coeffs(*h->ctx, includeDetailed != 0);
+        h->ctx->update_threads();
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+int lwref_hprd_export(LwRefHandle* hh, int includeDetailed, int64_t* counts, int32_t* prdLaOfLa, int32_t* hPrdLaOfLa,
+                      int64_t* JCoeffOff, int32_t* JCoeffIdx, double* JCoeffFrac, double* rhoFrac, int32_t* rhoI0)
+{
+    auto* h = (LwRef*)hh;
+    auto& spect = h->spect;
+    const i64 K = h->prob->Nspace, M = h->prob->Nrays, L = h->prob->Nspect;
+    if (!spect.JRest)
+    {
+        g_err = "hybrid PRD has not been configured";
+        return 1;
+    }
+    const i64 NprdLa = spect.JRest.shape(0), NhPrd = (i64)spect.hPrdIdxs.size();
+    for (i64 la = 0; la < L; ++la)
+    {
+        if (prdLaOfLa) prdLaOfLa[la] = spect.prdActive(la) ? spect.la_to_prdLa(la) : -1;
+        if (hPrdLaOfLa) hPrdLaOfLa[la] = spect.hPrdActive(la) ? spect.la_to_hPrdLa(la) : -1;
+    }
+    i64 nnz = 0;
+    for (i64 q = 0; q < NhPrd; ++q)
+        for (i64 mu = 0; mu < M; ++mu)
+            for (int toObs = 0; toObs < 2; ++toObs)
+                for (i64 k = 0; k < K; ++k)
+                {
+                    const auto& v = spect.JCoeffs(q, mu, toObs, k);
+                    if (JCoeffOff) JCoeffOff[((q * M + mu) * 2 + toObs) * K + k] = nnz;
+                    for (const auto& c : v)
+                    {
+                        if (JCoeffIdx) JCoeffIdx[nnz] = c.idx;
+                        if (JCoeffFrac) JCoeffFrac[nnz] = c.frac;
+                        ++nnz;
+                    }
+                }
+    if (JCoeffOff) JCoeffOff[NhPrd * M * 2 * K] = nnz;
+    i64 nLines = 0, o = 0;
+    auto lines_of = [&](std::vector<Atom*>& atoms) {
+        for (auto* a : atoms)
+            for (auto* t : a->trans)
+                if (t->rhoPrd)
+                {
+                    ++nLines;
+                    const i64 Nl = t->wavelength.shape(0);
+                    for (i64 lt = 0; lt < Nl; ++lt)
+                        for (i64 mu = 0; mu < M; ++mu)
+                            for (int toObs = 0; toObs < 2; ++toObs)
+                                for (i64 k = 0; k < K; ++k, ++o)
+                                {
+                                    const auto& c = t->hPrdCoeffs(lt, mu, toObs, k);
+                                    if (rhoFrac) rhoFrac[o] = c.frac;
+                                    if (rhoI0) rhoI0[o] = c.i0;
+                                    if (c.i1 != c.i0 + 1)
+                                        throw std::runtime_error("hPrdCoeffs: i1 != i0 + 1");
+                                }
+                }
+    };
+    try
+    {
+        lines_of(h->ctx->activeAtoms);
+        if (includeDetailed)
+            lines_of(h->ctx->detailedAtoms);
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+    if (counts)
+    {
+        counts[0] = NprdLa; counts[1] = NhPrd; counts[2] = nnz; counts[3] = nLines;
+    }
+    return 0;
+}
+
+// the reference's rest-frame mean intensity JRest [NprdLa][Nspace] of this column
+int lwref_get_jrest(LwRefHandle* hh, double* out)
+{
+    auto* h = (LwRef*)hh;
+    if (!h->spect.JRest)
+    {
+        g_err = "hybrid PRD has not been configured";
+        return 1;
+    }
+    std::memcpy(out, h->spect.JRest.dataStore.data(), sizeof(double) * h->spect.JRest.shape(0) * h->spect.JRest.shape(1));
+    return 0;
+}
+
 // stat_eq over every active atom (LwContext.stat_equil, LwMiddleLayer.pyx:3509-3514).
 int lwref_stat_eq(LwRefHandle* hh)
 {

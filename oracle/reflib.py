@@ -65,6 +65,10 @@ def load():
     lib.lwref_time_dep_update.argtypes = [vp, C.c_int, dp, C.c_double]
     lib.lwref_redistribute_prd.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp,
                                            C.POINTER(C.c_int), dp, C.POINTER(C.c_int64)]
+    lib.lwref_configure_hprd.argtypes = [vp, C.c_int]
+    i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    lib.lwref_hprd_export.argtypes = [vp, C.c_int, i64p, i32p, i32p, i64p, i32p, dp, dp, i32p]
+    lib.lwref_get_jrest.argtypes = [vp, dp]
     lib.lwref_compute_profiles.argtypes = [vp]
     lib.lwref_time_fs_iter.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
     lib.lwref_solve_ray.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_int,
@@ -117,6 +121,49 @@ class RefContext:
 
     def stat_eq(self):
         _check(self.lib.lwref_stat_eq(self.h))
+
+    def configure_hprd(self, includeDetailed=False):
+        """The reference's own configure_hprd_coeffs + update_threads on this column.  Returns its tables as a
+        one-column lightweaver_b200.problem.HybridPrd (JRest zeroed; read the reference's with jrest())."""
+        import numpy as np
+        from lightweaver_b200.problem import HybridPrd
+        _check(self.lib.lwref_configure_hprd(self.h, int(includeDetailed)))
+        p = self.problem
+        K, M, L = p.Nspace, p.Nrays, p.Nspect
+        i32p, i64p, dp = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
+        counts = np.zeros(4, dtype=np.int64)
+        args0 = [i32p(), i32p(), i64p(), i32p(), dp(), dp(), i32p()]
+        _check(self.lib.lwref_hprd_export(self.h, int(includeDetailed), counts.ctypes.data_as(i64p), *args0))
+        NprdLa, NhPrd, nnz, nl = (int(x) for x in counts)
+        lines = [(ia, it) for pass_ in ((False, True) if includeDetailed else (False,))
+                 for ia, a in enumerate(p.atoms) if bool(a.detailedStatic) == pass_
+                 for it, t in enumerate(a.trans) if t.rhoPrd is not None]
+        assert len(lines) == nl
+        tot = sum(p.atoms[a].trans[t].Nlambda * M * 2 * K for a, t in lines)
+        prdLa, hPrdLa = np.zeros(L, np.int32), np.zeros(L, np.int32)
+        off = np.zeros(NhPrd * M * 2 * K + 1, np.int64)
+        cIdx, cFrac = np.zeros(max(nnz, 1), np.int32), np.zeros(max(nnz, 1))
+        rFrac, rI0 = np.zeros(max(tot, 1)), np.zeros(max(tot, 1), np.int32)
+        _check(self.lib.lwref_hprd_export(self.h, int(includeDetailed), counts.ctypes.data_as(i64p),
+                                          prdLa.ctypes.data_as(i32p), hPrdLa.ctypes.data_as(i32p),
+                                          off.ctypes.data_as(i64p), cIdx.ctypes.data_as(i32p), cFrac.ctypes.data_as(dp),
+                                          rFrac.ctypes.data_as(dp), rI0.ctypes.data_as(i32p)))
+        self.NprdLa = NprdLa
+        ro, o = [], 0
+        for a, t in lines:
+            ro.append(o)
+            o += p.atoms[a].trans[t].Nlambda * M * 2 * K
+        return HybridPrd(NprdLa=NprdLa, NhPrd=NhPrd, prdLaOfLa=prdLa, hPrdLaOfLa=hPrdLa.reshape(1, L),
+                         JRest=np.zeros((1, NprdLa, K)), JCoeffOff=off, JCoeffIdx=cIdx[:nnz], JCoeffFrac=cFrac[:nnz],
+                         lineAtom=np.asarray([a for a, _ in lines], np.int32),
+                         lineTrans=np.asarray([t for _, t in lines], np.int32),
+                         rhoCoefOff=np.asarray(ro, np.int64), rhoFrac=rFrac[:tot], rhoI0=rI0[:tot])
+
+    def jrest(self):
+        import numpy as np
+        out = np.zeros((self.NprdLa, self.problem.Nspace))
+        _check(self.lib.lwref_get_jrest(self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
 
     def full_stokes(self, updateJ=False, upOnly=True):
         dJ, idx = C.c_double(0.0), C.c_int64(0)

@@ -226,6 +226,48 @@ def test_oracle_prd_vs_reference_live():
     r.close()
 
 
+HPRD_TABLES = ('prdLaOfLa', 'hPrdLaOfLa', 'JCoeffOff', 'JCoeffIdx', 'JCoeffFrac', 'lineAtom', 'lineTrans',
+               'rhoCoefOff', 'rhoFrac', 'rhoI0')
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize('vscale', [1.0, 8.0])
+def test_oracle_hybrid_prd_vs_reference_live(vscale):
+    """Hybrid PRD: the restated configure_hprd_coeffs builds the reference's own tables element for element,
+    and the formal solution (rho interpolated per ray, JRest scattered), the rest-frame redistribution and
+    the PRD formal solution over hPrdIdxs agree with the compiled reference to the bit.  vscale = 8 makes the
+    Doppler shifts larger than the core wavelength spacing (several entries per coefficient list)."""
+    p = synth.tiny_prd_problem(nrays=2, ndepth=50, perturb=True)
+    p.vlosMu *= vscale
+    q = p.clone()
+    r = reflib.RefContext(p)
+    href = r.configure_hprd()
+    q.hprd = oraclelib.configure_hprd(q)
+    assert (href.NprdLa, href.NhPrd) == (q.hprd.NprdLa, q.hprd.NhPrd)
+    for name in HPRD_TABLES:
+        assert np.array_equal(getattr(href, name), getattr(q.hprd, name)), name
+    assert href.NhPrd >= href.NprdLa > 0 and len(href.JCoeffIdx) > 0
+    o = oraclelib.OracleContext(q)
+    for it in range(2):
+        p.prefill_gamma()
+        q.prefill_gamma()
+        r.fs_iter()
+        o.fs_iter()
+        assert np.array_equal(r.jrest(), q.hprd.JRest[0]) and q.hprd.JRest.max() > 0.0
+        assert max(compare_problems(q, p).values()) <= 1e-14
+        a, b = r.redistribute_prd(maxIter=4, tol=1e-4, nlines=2), o.redistribute_prd(maxIter=4, tol=1e-4, nlines=2)
+        assert a['nIter'] == b['nIter']
+        assert np.array_equal(a['dRho'], b['dRho']) and np.array_equal(a['dJPrdMax'], b['dJPrdMax'])
+        for ta, tb in zip(p.atoms[0].trans, q.atoms[0].trans):
+            if ta.rhoPrd is not None:
+                assert np.array_equal(ta.rhoPrd, tb.rhoPrd)
+        assert np.array_equal(r.jrest(), q.hprd.JRest[0])
+        assert max(compare_problems(q, p).values()) <= 1e-14
+        r.stat_eq()
+        o.stat_eq()
+    r.close()
+
+
 @pytest.mark.ref
 @pytest.mark.parametrize('solver', [0, 1, 2])
 def test_oracle_solvers_vs_reference_rays(solver):
