@@ -278,6 +278,19 @@ int lwb200_compute_profiles(LwB200Context* ctx);
  * J, Gamma (onto the uploaded prefill) and Rij/Rji, finalises Gamma.
  * dJMax / dJMaxIdx may be NULL (no device->host sync is then forced). */
 int lwb200_fs_iter(LwB200Context* ctx, uint32_t flags, double* dJMax, int64_t* dJMaxIdx);
+/* Replaces configure_hprd_coeffs (Source/Prd.cpp:697-946) for every column of the problem: from the wavelength
+ * grid, the ranges of the PRD lines (lines with rhoPrd; those of detailed-static atoms on request) and
+ * vlosMu, fills *out with the tables of LwB200HybridPrd (JRest zeroed).  Host code, no device needed.  The
+ * arrays belong to the library until lwb200_free_hprd(out).  out->Nlines == 0: the problem has no PRD line. */
+int lwb200_configure_hprd(const LwB200Problem* problem, int includeDetailed, LwB200HybridPrd* out);
+void lwb200_free_hprd(LwB200HybridPrd* tables);
+
+/* Replace the hybrid-PRD tables of a context created with LwB200Problem::hprd (configure_hprd_coeffs run
+ * again after the velocity field changed, Source/Prd.cpp:697-946).  The tables must name the same PRD lines;
+ * the wavelengths that scatter into the PRD grid must stay within two grid points of the set the context was
+ * planned for (otherwise: error, create a new context).  JRest travels with LWB200_PRD. */
+int lwb200_set_hybrid_prd(LwB200Context* ctx, const LwB200HybridPrd* tables);
+
 /* The prologue of lw.Context.formal_sol_gamma_matrices, Gamma = crsw * C (Source/LwMiddleLayer.pyx:3198-3203),
  * on the device: with enable != 0 the finalisation takes crsw times the collisional rates uploaded with
  * LWB200_COLLISIONS instead of a prefill uploaded with LWB200_GAMMA, so a caller whose C is unchanged

@@ -67,6 +67,7 @@ class Context:
         if laRange is not None:
             self.set_lambda_range(*laRange)
         self.crsw = 1.0
+        self._hprd_keep = []
         self._c_resident = False
         if upload:
             self.upload(capi.ALL_INPUTS)
@@ -128,6 +129,14 @@ class Context:
 
     def upload(self, mask):
         capi.check(self.lib.lwb200_upload(self._h, mask))
+
+    def configure_hprd_coeffs(self, includeDetailed=False):
+        """lw.Context.configure_hprd_coeffs after the velocity field changed: rebuild the hybrid-PRD tables
+        and hand them to the device (the context must have been created with tables: call
+        problem.configure_hprd() before constructing it)."""
+        self.problem.configure_hprd(includeDetailed)
+        self._hprd_cs = self.problem.hprd.c_struct(self._hprd_keep)
+        capi.check(self.lib.lwb200_set_hybrid_prd(self._h, self._hprd_cs))
 
     def collisions_changed(self):
         """The collisional rates C of the active atoms are context state on the device (they change
@@ -253,7 +262,8 @@ class Context:
         flags = ((capi.LAMBDA_ITERATE if lambdaIterate else 0) | (capi.STORE_DEPTH if storeDepth else 0)
                  | (capi.GENERAL_KERNEL if general else 0) | capi.FETCH_EARLY | capi.DJ_ASYNC)
         capi.check(self.lib.lwb200_fs_iter(self._h, flags, None, None))
-        self.download(capi.ITER_OUTPUTS | (capi.DEPTH if storeDepth else 0) | (capi.ZPLANE if zplane else 0))
+        self.download(capi.ITER_OUTPUTS | (capi.DEPTH if storeDepth else 0) | (capi.ZPLANE if zplane else 0)
+                      | (capi.PRD if self.problem.hprd is not None else 0))   # (hybrid PRD: JRest)
         dJ, idx = C.c_double(), C.c_int64()
         capi.check(self.lib.lwb200_last_dj(self._h, C.byref(dJ), C.byref(idx)))
         return IterationUpdate(updatedJ=True, dJMax=dJ.value, dJMaxIdx=idx.value % self.problem.Nspect,

@@ -25,7 +25,7 @@ def _stale(target, deps):
 
 def build_cuda(force=False, verbose=False):
     out = os.path.join(PKG, 'liblwb200.so')
-    deps = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(('.cu', '.cuh'))]
+    deps = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(('.cu', '.cuh', '.inl'))]
     deps.append(os.path.join(ROOT, 'include', 'lwb200.h'))
     if not force and not _stale(out, deps):
         return out

@@ -16,6 +16,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <utility>
@@ -171,6 +174,7 @@ struct PipelineLists
     const int* polLam; // full Stokes pass: wavelengths with a polarised line (stokes_kernel)
     int nPolLam;
     int fullRange;     // the lists cover the whole spectrum whatever the context's wavelength shard
+    int directPrdOnly; // hybrid PRD: the pass is the general kernel in PRD-rates-only mode over the direct tiles
 };
 
 struct LwB200Context
@@ -221,6 +225,13 @@ struct LwB200Context
     std::vector<int> prdLineDetailed;
     DevBuf<DevPrdLine> dPrdLines;
     DevBuf<double> qelast, cmat, rhoPrev, prdMax, nOld;
+    // hybrid PRD (LwB200HybridPrd): the caller's tables (host pointers) and their device copies
+    bool hybrid = false;
+    LwB200HybridPrd hprdHost{};
+    std::vector<unsigned char> hprdPlanMask; // wavelengths the plan routes through the general kernel for it
+    DevBuf<int> dHprdLaOfLa, dPrdLaOfLa, dJCoeffIdx, dHprdI0;
+    DevBuf<long long> dJCoeffOff;
+    DevBuf<double> dJRest, dJCoeffFrac, dHprdFrac;
     DevBuf<double> collC;          // C of every active atom, packed like `prefill` (LWB200_COLLISIONS)
     bool prefillFromC = false;     // finalise with crswC * collC instead of the uploaded prefill
     double crswC = 1.0;
@@ -359,6 +370,15 @@ int build_plan(LwB200Context* c)
         tabOff += Nl;
         d.lineIdx = d.contIdx = -1;
         d.rhoOff = -1;
+        d.hprdOff = -1;
+        if (p.hprd)
+            for (int q = 0; q < p.hprd->Nlines; ++q)
+                if (p.hprd->lineAtom[q] == ht.atom && p.hprd->lineTrans[q] == ht.kr)
+                {
+                    if (t.type != LWB200_LINE || !t.rhoPrd)
+                        return fail("hybrid PRD coefficients for a transition that is not a PRD line");
+                    d.hprdOff = p.hprd->rhoCoefOff[q];
+                }
         if (t.type == LWB200_LINE)
         {
             d.lineIdx = nline++;
@@ -456,6 +476,24 @@ int build_plan(LwB200Context* c)
     c->laKind.resize(L);
     for (int la = 0; la < L; ++la)
         c->laKind[la] = kind_of(la);
+    c->hprdPlanMask.assign(L, 0);
+    if (p.hprd)
+    {
+        // Hybrid PRD: the emission profile ratio of a PRD line depends on the ray and the formal solution
+        // scatters into JRest, neither of which the moment pipeline carries: every wavelength that scatters
+        // into the PRD grid in ANY column (the sets differ with the velocity field), and two neighbours
+        // either side (room for a later lwb200_set_hybrid_prd), takes the general per-ray kernel.
+        for (int col = 0; col < p.Ncol; ++col)
+            for (int la = 0; la < L; ++la)
+                if (p.hprd->hPrdLaOfLa[(size_t)col * L + la] >= 0)
+                    for (int q = std::max(0, la - 2); q <= std::min(L - 1, la + 2); ++q)
+                        c->hprdPlanMask[q] = 1;
+        for (int la = 0; la < L; ++la)
+            if (c->hprdPlanMask[la])
+                c->laKind[la] = 4;
+        if (K > 128)
+            return fail("hybrid PRD is limited to Nspace <= 128 (general per-ray kernel)");
+    }
     int maxSlots = 1;
     size_t maxTileEntries = 1;
     c->tileLa.push_back(0);
@@ -1471,14 +1509,16 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
         if (launch_pipeline<NCH, SOLVER, false>(c, c->customLists ? c->prdPl : full_lists(c), lambdaIterate, storeDepth,
                                                 c->stokesFsMode))
             return 1;
-        if (c->nListDirect > 0 && !c->customLists)
+        if (c->nListDirect > 0 && (!c->customLists || c->prdPl.directPrdOnly))
         {
             auto kern = fs_kernel<NCH, SOLVER, MODE_ITER>;
             if (set_smem_attr(kern, c->device))
                 return 1;
+            const bool prdPass = c->customLists; // (hybrid PRD: the whole spectrum, PRD rates only)
             dim3 grid(c->nListDirect, launch_columns(c));
-            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListDirect.p, c->laLo, c->laHi,
-                                                             lambdaIterate, 0, storeDepth);
+            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListDirect.p, prdPass ? 0 : c->laLo,
+                                                             prdPass ? c->prob.Nspect : c->laHi, lambdaIterate, 0,
+                                                             storeDepth, prdPass ? 1 : 0);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }
@@ -1490,7 +1530,7 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
             return 1;
         dim3 grid(c->nListAll, launch_columns(c));
         kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListAll.p, c->laLo, c->laHi, lambdaIterate,
-                                                         upOnly, storeDepth);
+                                                         upOnly, storeDepth, 0);
         CU(cudaGetLastError());
         c->lastLaunches += 1;
     }
@@ -1593,6 +1633,73 @@ int grid_for(size_t total, int block = 256)
 }
 } // namespace
 
+// Hybrid PRD: device copies of the caller's tables (LwB200HybridPrd).  The plan was made for the lines and the
+// wavelength set of the tables the context was created with; new tables (a changed velocity field) must name
+// the same lines and stay within the planned set.
+static int upload_hybrid(LwB200Context* c, const LwB200HybridPrd* h)
+{
+    const LwB200Problem& p = c->prob;
+    const size_t K = p.Nspace, M = p.Nrays, L = p.Nspect, ncol = p.Ncol;
+    if (!h || !h->prdLaOfLa || !h->hPrdLaOfLa || !h->JCoeffOff || h->NprdLa < 1 || h->NhPrd < 1)
+        return fail("hybrid PRD: incomplete tables");
+    for (size_t col = 0; col < ncol; ++col)
+        for (size_t la = 0; la < L; ++la)
+            if (h->hPrdLaOfLa[col * L + la] >= 0 && !c->hprdPlanMask[la])
+                return fail("hybrid PRD: the new tables scatter from wavelengths outside the planned set; "
+                            "create a new context");
+    int nl = 0;
+    size_t rhoTot = 0;
+    for (size_t g = 0; g < c->trans.size(); ++g)
+        nl += c->devTrans[g].hprdOff >= 0 ? 1 : 0;
+    if (nl != h->Nlines)
+        return fail("hybrid PRD: the tables name other lines than the context was created with");
+    for (int q = 0; q < h->Nlines; ++q)
+    {
+        bool found = false;
+        for (size_t g = 0; g < c->trans.size(); ++g)
+            if (c->trans[g].atom == h->lineAtom[q] && c->trans[g].kr == h->lineTrans[q])
+            {
+                found = c->devTrans[g].hprdOff == h->rhoCoefOff[q];
+                rhoTot = std::max<size_t>(rhoTot, (size_t)h->rhoCoefOff[q]
+                                                       + ncol * (size_t)(c->devTrans[g].Nred - c->devTrans[g].Nblue) * M * 2 * K);
+            }
+        if (!found)
+            return fail("hybrid PRD: the tables name other lines than the context was created with");
+    }
+    const size_t nRows = ncol * (size_t)h->NhPrd * M * 2 * K;
+    const size_t nnz = (size_t)h->JCoeffOff[nRows];
+    DevBuf<int>* ib[] = {&c->dHprdLaOfLa, &c->dPrdLaOfLa, &c->dJCoeffIdx, &c->dHprdI0};
+    for (auto* b : ib)
+        b->release();
+    c->dJCoeffOff.release();
+    c->dJCoeffFrac.release();
+    c->dHprdFrac.release();
+    if (c->dHprdLaOfLa.upload(std::vector<int>(h->hPrdLaOfLa, h->hPrdLaOfLa + ncol * L))
+        || c->dPrdLaOfLa.upload(std::vector<int>(h->prdLaOfLa, h->prdLaOfLa + L))
+        || c->dJCoeffOff.upload(std::vector<long long>(h->JCoeffOff, h->JCoeffOff + nRows + 1))
+        || c->dJCoeffIdx.upload(std::vector<int>(h->JCoeffIdx, h->JCoeffIdx + nnz))
+        || c->dJCoeffFrac.upload(std::vector<double>(h->JCoeffFrac, h->JCoeffFrac + nnz))
+        || c->dHprdFrac.upload(std::vector<double>(h->rhoFrac, h->rhoFrac + rhoTot))
+        || c->dHprdI0.upload(std::vector<int>(h->rhoI0, h->rhoI0 + rhoTot)))
+        return 1;
+    if (c->dJRest.n != ncol * (size_t)h->NprdLa * K)
+    {
+        c->dJRest.release();
+        if (c->dJRest.alloc(ncol * (size_t)h->NprdLa * K))
+            return 1;
+    }
+    CU(cudaMemset(c->dJRest.p, 0, c->dJRest.n * sizeof(double)));
+    c->hprdHost = *h;
+    c->prob.hprd = &c->hprdHost;
+    c->hybrid = true;
+    DevProblem& P = c->P;
+    P.hprdLaOfLa = c->dHprdLaOfLa.p; P.prdLaOfLa = c->dPrdLaOfLa.p; P.JRest = c->dJRest.p;
+    P.JCoeffOff = c->dJCoeffOff.p; P.JCoeffIdx = c->dJCoeffIdx.p; P.JCoeffFrac = c->dJCoeffFrac.p;
+    P.hprdFrac = c->dHprdFrac.p; P.hprdI0 = c->dHprdI0.p;
+    P.NprdLa = h->NprdLa; P.NhPrd = h->NhPrd;
+    return 0;
+}
+
 extern "C"
 {
 const char* lwb200_last_error(void) { return g_err.c_str(); }
@@ -1644,7 +1751,7 @@ int lwb200_create(const LwB200Problem* problem, int device, LwB200Context** out)
     c->prob.atoms = c->atoms.data();
     c->laLo = 0;
     c->laHi = problem->Nspect;
-    if (build_plan(c))
+    if (build_plan(c) || (problem->hprd && upload_hybrid(c, problem->hprd)))
     {
         lwb200_destroy(c);
         return 1;
@@ -1723,6 +1830,8 @@ int lwb200_destroy(LwB200Context* c)
                            &c->dAtomGammaOff, &c->dAtomDetailed, &c->dSingular, &c->dPhiAsym};
     for (auto* b : ints)
         b->release();
+    c->dHprdLaOfLa.release(); c->dPrdLaOfLa.release(); c->dJCoeffIdx.release(); c->dHprdI0.release();
+    c->dJCoeffOff.release(); c->dJRest.release(); c->dJCoeffFrac.release(); c->dHprdFrac.release();
     for (void* r : c->registered)
         cudaHostUnregister(r);
     Pinned* pins[] = {&c->stN, &c->stNStar, &c->stNTotal, &c->stVBroad, &c->stPrefill, &c->stGamma,
@@ -2261,6 +2370,8 @@ int lwb200_upload(LwB200Context* c, uint32_t mask)
                        H2D, s))
                 return 1;
         }
+        if (c->hybrid && c->hprdHost.JRest)
+            CU(cudaMemcpyAsync(c->dJRest.p, c->hprdHost.JRest, c->dJRest.n * D, H2D, s));
         c->prdUploaded = true;
     }
     return 0;
@@ -2287,11 +2398,15 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
     if ((mask & LWB200_STOKES) && c->polTot > 0)
         CU(cudaMemcpyAsync(p.Quv, c->Quv.p, ncol * 3 * L * M * D, D2H, s));
     if (mask & LWB200_PRD)
+    {
         for (const DevPrdLine& ln : c->prdLines)
         {
             const LwB200Transition& t = c->trans[ln.trans].t;
             CU(cudaMemcpyAsync(t.rhoPrd, c->rhoPrd.p + ln.rhoOff, ncol * (size_t)ln.Nl * K * D, D2H, s));
         }
+        if (c->hybrid && c->hprdHost.JRest)
+            CU(cudaMemcpyAsync(c->hprdHost.JRest, c->dJRest.p, c->dJRest.n * D, D2H, s));
+    }
     // rows [r0, r1) of every column's [L][.] arrays: the context's own wavelength range on request
     const size_t r0 = (mask & LWB200_OWN_ROWS) ? (size_t)c->laLo : 0, r1 = (mask & LWB200_OWN_ROWS) ? (size_t)c->laHi : L;
     if (mask & LWB200_JBAR)
@@ -2431,6 +2546,15 @@ int lwb200_compute_profiles(LwB200Context* c)
     return check_phi_symmetry(c);
 }
 
+int lwb200_set_hybrid_prd(LwB200Context* c, const LwB200HybridPrd* tables)
+{
+    CU(cudaSetDevice(c->device));
+    if (!c->hybrid)
+        return fail("lwb200_set_hybrid_prd: the context was created without hybrid PRD tables (LwB200Problem::hprd)");
+    CU(cudaStreamSynchronize(c->stream));
+    return upload_hybrid(c, tables);
+}
+
 int lwb200_set_collision_prefill(LwB200Context* c, int enable, double crsw)
 {
     if (enable && !c->collC.p && c->P.GammaTot > 0)
@@ -2563,6 +2687,8 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
     else
         return fail("lwb200_fs_iter: every column is retired");
     c->zDownWritten = true;
+    if (c->hybrid) // zero_Gamma_rates_JRest (SimdFullIterationTemplates.hpp:521-586, :602-603)
+        CU(cudaMemsetAsync(c->dJRest.p, 0, c->dJRest.n * sizeof(double), c->stream));
     const int rcFs = launch_fs<MODE_ITER>(c, (flags & LWB200_LAMBDA_ITERATE) ? 1 : 0, 0, storeDepth);
     c->djEarly = false;
     if (rcFs)
@@ -2803,7 +2929,16 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
     c->fetchEarly = false;
 
     // wavelengths touched by a redistributed line (:225-240) and the work lists over them
-    if (c->prdListsFor != nLines)
+    if (c->hybrid && c->prdListsFor != -2 - nLines)
+    {
+        // hybrid PRD: the formal solution runs over the wavelengths that scatter into the PRD grid
+        // (idxsForFs = spect.hPrdIdxs, PrdTemplates.hpp:233-234), column by column, in the general kernel
+        c->dPrdMask.release();
+        if (c->dPrdMask.upload(c->hprdPlanMask))
+            return 1;
+        c->prdListsFor = -2 - nLines;
+    }
+    else if (!c->hybrid && c->prdListsFor != nLines)
     {
         std::vector<unsigned char> mask(L, 0);
         for (int q = 0; q < nLines; ++q)
@@ -2851,15 +2986,19 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
         c->prdListsFor = nLines;
     }
     PipelineLists pl{};
-    pl.moment = c->dListMomentPrd.p;
-    pl.nMoment = c->nListMomentPrd;
-    pl.gTiles = c->dGListPrd.p;
-    pl.nGTiles = c->nGListPrd;
-    for (int q = 0; q < 4; ++q)
+    if (!c->hybrid)
     {
-        pl.kindLam[q] = c->dKindLamPrd[q].p;
-        pl.nKindLam[q] = c->nKindLamPrd[q];
+        pl.moment = c->dListMomentPrd.p;
+        pl.nMoment = c->nListMomentPrd;
+        pl.gTiles = c->dGListPrd.p;
+        pl.nGTiles = c->nGListPrd;
+        for (int q = 0; q < 4; ++q)
+        {
+            pl.kindLam[q] = c->dKindLamPrd[q].p;
+            pl.nKindLam[q] = c->nKindLamPrd[q];
+        }
     }
+    pl.directPrdOnly = c->hybrid ? 1 : 0;
     pl.laMask = c->dPrdMask.p;
     pl.prdOnly = 1;
     pl.fullRange = 1;
@@ -2889,6 +3028,13 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
         prd_zero_rates_kernel<<<grid_for((size_t)nLines * p.Ncol * K), 256, 0, s>>>(c->P, c->dPrdLines.p, nLines);
         CU(cudaGetLastError());
         c->lastLaunches += 3;
+        if (c->hybrid)
+        {
+            // JRest is rebuilt by this pass (PrdTemplates.hpp:57-58); dJ of the wavelengths a column does not
+            // visit must not carry over from the Gamma iteration
+            CU(cudaMemsetAsync(c->dJRest.p, 0, c->dJRest.n * sizeof(double), s));
+            CU(cudaMemsetAsync(c->dJ.p, 0, c->dJ.n * sizeof(double), s));
+        }
         c->customLists = true;
         c->prdPl = pl;
         const int rc = launch_fs<MODE_ITER>(c, 0, 0, 0);
@@ -3228,3 +3374,5 @@ int lwb200_work_stats(LwB200Context* c, double* points, double* algBytes, int64_
     return 0;
 }
 } // extern "C"
+
+#include "lwb200_hprd_host.inl"

@@ -37,6 +37,8 @@ struct DevTrans
     long long phiOff;     // element offset of phi[col = 0] in the phi pool
     long long phiColStride;
     long long rhoOff;     // -1: no rhoPrd
+    long long hprdOff;    // hybrid PRD: element offset of the line's interpolation coefficients (column 0) in the
+                          // hprdFrac / hprdI0 pools, [Ncol][Nlambda][M][2][K]; -1: angle-averaged or no PRD
     double Aji_Bji;       // Aji / Bji
     double Bji_Bij;       // Bji / Bij
     double Bij;
@@ -130,6 +132,16 @@ struct DevProblem
     double* Jdag;             // [Ncol][L][K] copy of J taken before a J-updating Stokes pass
     // ZPlaneDecomposition (lwb200_set_zplane): [Ncol][L][M] each, nullptr: not recorded
     double *zPlaneUp, *zPlaneDown;
+    // hybrid PRD (LwB200HybridPrd): nullptr / 0 without it
+    const int* hprdLaOfLa;      // [Ncol][L] row of this column's JCoeffs tables, -1: the wavelength does not scatter
+    const int* prdLaOfLa;       // [L] row of JRest, -1: no PRD line active
+    double* JRest;              // [Ncol][NprdLa][K]
+    const long long* JCoeffOff; // CSR over ((((col * NhPrd + hPrdLa) * M + mu) * 2 + toObs) * K + k)
+    const int* JCoeffIdx;
+    const double* JCoeffFrac;
+    const double* hprdFrac;     // interpolation coefficients of every hybrid PRD line (DevTrans::hprdOff)
+    const int* hprdI0;
+    int NprdLa, NhPrd;
 };
 
 // ZPlaneDecomposition of intensity_core_opt (SimdFullIterationTemplates.hpp:351-360): I(1) of an up-going
@@ -178,10 +190,20 @@ __device__ __forceinline__ UV trans_uv(const DevProblem& P, const DevTrans& t, i
         const double p = __ldg(P.phi + t.phiOff + (long long)col * t.phiColStride
                                + ((long long)(lt * P.M + mu) * 2 + dir) * P.K + k);
         double g = t.Bji_Bij;
-        if (t.rhoOff >= 0)
+        if (t.rhoOff >= 0 && t.hprdOff < 0)
             g *= __ldg(P.rhoPrd + t.rhoOff + ((long long)col * (t.Nred - t.Nblue) + lt) * P.K + k);
         r.Vij = hnu_4pi * t.Bij * p;
         r.Vji = g * r.Vij;
+        if (t.hprdOff >= 0)
+        {
+            // hybrid PRD: rho interpolated to the rest-frame wavelength of this ray (LwTransition.hpp:115-130)
+            const long long Nl = t.Nred - t.Nblue;
+            const long long o = t.hprdOff + ((((long long)col * Nl + lt) * P.M + mu) * 2 + dir) * P.K + k;
+            const double frac = __ldg(P.hprdFrac + o);
+            const int i0 = __ldg(P.hprdI0 + o);
+            const double* rho = P.rhoPrd + t.rhoOff + (long long)col * Nl * P.K + k;
+            r.Vji *= (1.0 - frac) * __ldg(rho + (long long)i0 * P.K) + frac * __ldg(rho + (long long)(i0 + 1) * P.K);
+        }
         r.Uji = t.Aji_Bji * r.Vji;
     }
     else
@@ -215,8 +237,10 @@ __device__ __forceinline__ void smem_add(double* addr, double v) { atomicAdd(add
 template <int NCH, int SOLVER, int MODE>
 __global__ void __launch_bounds__(128)
 fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi, int lambdaIterate,
-          int upOnly, int storeDepth)
+          int upOnly, int storeDepth, int prdOnly)
 {
+    // prdOnly: the pass of formal_sol_prd_update_rates (PrdTemplates.hpp:18-76) under hybrid PRD: J, I, JRest
+    // and the rates of the PRD lines only, over the wavelengths that scatter into the PRD grid in THIS column.
     extern __shared__ double smem[];
     const int K = P.K, M = P.M, L = P.L, KP = P.KP;
     const int tile = tileList[blockIdx.x];
@@ -258,6 +282,9 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
     {
         const int la = P.tileLambda[tl];
         if (la < laLo || la >= laHi)
+            continue;
+        const int hPrdLa = P.hprdLaOfLa ? P.hprdLaOfLa[(size_t)col * L + la] : -1;
+        if (prdOnly && hPrdLa < 0)
             continue;
         const double lambda = __ldg(P.wavelength + la);
         const size_t rowLK = ((size_t)col * L + la) * K;
@@ -427,6 +454,22 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
                 for (int j = 0; j < NCH; ++j)
                     Jnew[j] += halfwmu * I[j]; // accumulate_J (:181-190)
 
+                if (hPrdLa >= 0)
+                {
+                    // rest-frame mean intensity of hybrid PRD (:397-408): several wavelengths scatter into
+                    // one row of JRest, so the sums are fp64 REDs
+                    const size_t row = ((((size_t)col * P.NhPrd + hPrdLa) * M + mu) * 2 + dir) * K;
+                    double* JRest = P.JRest + (size_t)col * P.NprdLa * K;
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+                    {
+                        const int k = g.k(j);
+                        if (k < K)
+                            for (long long e = P.JCoeffOff[row + k]; e < P.JCoeffOff[row + k + 1]; ++e)
+                                atomicAdd(JRest + (size_t)P.JCoeffIdx[e] * K + k, halfwmu * P.JCoeffFrac[e] * I[j]);
+                    }
+                }
+
                 if (lambdaIterate)
                 {
 #pragma unroll
@@ -444,7 +487,7 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
                     int e1 = e0 + 1;
                     while (e1 < eEnd && P.trans[P.entries[e1].trans].atom == atom)
                         ++e1;
-                    const bool detailed = P.atomDetailed[atom] != 0;
+                    const bool detailed = P.atomDetailed[atom] != 0 || prdOnly; // (prdOnly: no operator, no Gamma)
                     const int N = P.atomNlevel[atom];
                     double* Xs = scratch;                      // chi_atom[level][lane]
                     double* Us = scratch + P.maxNlevel * 32;   // U_atom[level][lane]
@@ -481,6 +524,8 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
                             {
                                 const DevEntry en = P.entries[e];
                                 const DevTrans& t = P.trans[en.trans];
+                                if (prdOnly && t.rhoOff < 0)
+                                    continue; // rates of the PRD lines only (:433-434, :455-456)
                                 const int lt = la - t.Nblue;
                                 const UV uv = trans_uv(P, t, col, lt, mu, dir, k, lambda, expfac[j]);
                                 const double wlamu = trans_wla(P, t, col, lt, k, lambda) * halfwmu;

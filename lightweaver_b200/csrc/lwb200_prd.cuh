@@ -117,7 +117,10 @@ __global__ void prd_scatter_kernel(const DevProblem P, const DevPrdLine* __restr
     const double* w = transWave + ln.tabOff;
     const double vB = vBroad[((size_t)col * P.Natom + ln.atom) * K + k];
     const double aDamp = aDampBuf[((size_t)ln.lineIdx * P.Ncol + col) * K + k];
-    const double* Jk = P.J + ((size_t)col * L + ln.Nblue) * K + k; // J(la' + Nblue, k) = Jk[la' * K]
+    // J(la' + Nblue, k) = Jk[la' * K]; the rest-frame mean intensity under hybrid PRD (Prd.cpp:484-499): the
+    // wavelengths of a line are consecutive rows of JRest
+    const double* Jk = P.JRest ? P.JRest + ((size_t)col * P.NprdLa + P.prdLaOfLa[ln.Nblue]) * K + k
+                               : P.J + ((size_t)col * L + ln.Nblue) * K + k;
     auto qWave = [&](int l) { return (w[l] - ln.lambda0) * kCLight / (ln.lambda0 * vB); };
 
     const double qEmit = qWave(la);

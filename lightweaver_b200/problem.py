@@ -329,6 +329,24 @@ class Problem:
         self._keepalive.append((p, keep))
         return p
 
+    def configure_hprd(self, includeDetailed=False):
+        """lw.Context.configure_hprd_coeffs: build the hybrid-PRD tables for the current velocity field
+        (lwb200_configure_hprd, host code of the CUDA library) and switch the hybrid scheme on for this
+        problem.  Returns the tables (None when the problem has no PRD line)."""
+        lib = capi.load()
+        keep, self.hprd = self.hprd, None
+        try:
+            cs = self.c_struct()
+        finally:
+            self.hprd = keep
+        h = capi.LwB200HybridPrd()
+        capi.check(lib.lwb200_configure_hprd(C.byref(cs), int(includeDetailed), C.byref(h)))
+        try:
+            self.hprd = HybridPrd.from_c(h, self) if h.Nlines > 0 else None
+        finally:
+            lib.lwb200_free_hprd(C.byref(h))
+        return self.hprd
+
     # ----------------------------------------------------------- conveniences
     def active_atoms(self):
         return [a for a in self.atoms if not a.detailedStatic]

@@ -509,10 +509,12 @@ def config_c2(nrays=10, nl=4.8, seed=SEED, **kw) -> Problem:
     return build_problem(atoms, ncol=1, nrays=nrays, seed=seed, **kw)
 
 
-def config_c4(nrays=5, nl=1.0, seed=SEED, **kw) -> Problem:
-    """Config 4: FAL C, H + Ca II + Mg II with the Mg II h and k lines in angle-averaged PRD."""
+def config_c4(nrays=5, nl=1.0, seed=SEED, ncol=1, **kw) -> Problem:
+    """Config 4: FAL C, H + Ca II + Mg II with the Mg II h and k lines in angle-averaged PRD.  With
+    perturb=True the column carries the velocity field of config 3: the case for the hybrid scheme
+    (Problem.configure_hprd)."""
     atoms = [h6_atom(nl), ca2_atom(nl), mg2_atom(nl)]
-    return build_problem(atoms, ncol=1, nrays=nrays, seed=seed, prd={'Mg': [0, 1]}, **kw)
+    return build_problem(atoms, ncol=ncol, nrays=nrays, seed=seed, prd={'Mg': [0, 1]}, **kw)
 
 
 def config_c3(ncol=4096, nrays=5, seed=SEED, **kw) -> Problem:

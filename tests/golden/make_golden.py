@@ -64,7 +64,12 @@ CASES = {
 PRD_CASES = {
     'tiny_prd': (synth.tiny_prd_problem, dict(perturb=True), 3, None, dict(maxIter=3, tol=1e-3)),
     'c4_prd': (synth.config_c4, dict(), 2, 16, dict(maxIter=3, tol=1e-2)),
+    # hybrid PRD (configure_hprd_coeffs, Prd.cpp:697-946): the same flow on columns with a velocity field,
+    # rho interpolated per ray to the rest frame, the redistribution fed by JRest
+    'tiny_hprd': (synth.tiny_prd_problem, dict(perturb=True, vscale=6.0), 3, None, dict(maxIter=3, tol=1e-3)),
+    'c4_hprd': (synth.config_c4, dict(perturb=True), 2, 16, dict(maxIter=3, tol=1e-2)),
 }
+HYBRID = ('tiny_hprd', 'c4_hprd')
 
 
 # full Stokes: two Gamma iterations (scalar), then single_stokes_fs(updateJ=False, upOnly=True), then
@@ -83,7 +88,17 @@ def build_case(name):
         fn, kw, niter, jstride, _ = PRD_CASES[name]
     else:
         fn, kw, niter, jstride = CASES[name]
-    return fn(**kw), niter, jstride
+    kw = dict(kw)
+    vscale = kw.pop('vscale', None)
+    p = fn(**kw)
+    if vscale is not None:
+        p.vlosMu *= vscale   # (Doppler shifts of several grid points; the profiles stay those of the generator)
+    if name in HYBRID:
+        # the tables the oracle and the CUDA path run with come from the product's own host routine
+        # (lwb200_configure_hprd, checked against the restatement and the reference in tests/test_oracle.py);
+        # the reference builds its own when the goldens are made
+        p.configure_hprd()
+    return p, niter, jstride
 
 
 def prd_snapshot(p, res):
@@ -98,16 +113,21 @@ def prd_snapshot(p, res):
     return snap
 
 
-def run_reference(p, niter, prd=None):
+def run_reference(p, niter, prd=None, hybrid=False):
     """iterate_ctx_se-style: first iteration pure Lambda, then MALI, stat_eq
     after each (lightweaver/iterate_ctx.py:157-176).  Returns per-iteration
     snapshots."""
     snaps = []
     ctxs = [reflib.RefContext(p, col=c) for c in range(p.Ncol)]
+    if hybrid:
+        for c in ctxs:
+            c.configure_hprd()
     for it in range(niter):
         p.prefill_gamma()
         dJ = [c.fs_iter(lambdaIterate=(it == 0)) for c in ctxs]
         snap = {'dJMax': np.array([d[0] for d in dJ]), 'I': p.I.copy(), 'J': p.J.copy()}
+        if hybrid:
+            snap['JRest'] = np.stack([c.jrest() for c in ctxs])
         for ia, a in enumerate(p.atoms):
             if not a.detailedStatic:
                 snap[f'Gamma{ia}'] = a.Gamma.copy()
@@ -118,6 +138,8 @@ def run_reference(p, niter, prd=None):
             assert p.Ncol == 1
             nl = sum(1 for a in p.atoms for t in a.trans if t.rhoPrd is not None)
             snap.update(prd_snapshot(p, ctxs[0].redistribute_prd(nlines=nl, **prd)))
+            if hybrid:
+                snap['prd_JRest'] = np.stack([c.jrest() for c in ctxs])
         for c in ctxs:
             c.stat_eq()
         for ia, a in enumerate(p.atoms):
@@ -162,7 +184,7 @@ def main():
         if name in STOKES_CASES:
             snaps, stokes = run_reference_stokes(p, niter)
         else:
-            snaps = run_reference(p, niter, PRD_CASES[name][4] if name in PRD_CASES else None)
+            snaps = run_reference(p, niter, PRD_CASES[name][4] if name in PRD_CASES else None, name in HYBRID)
         out = {'input_digest': np.array(digest), 'niter': np.array(niter),
                'jstride': np.array(0 if jstride is None else jstride)}
         for it, s in enumerate(snaps):

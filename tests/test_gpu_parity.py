@@ -327,6 +327,55 @@ def test_cuda_prd_vs_oracle_columns(ndepth, tiled, monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize('vscale', [1.0, 8.0])
+def test_cuda_hybrid_prd_vs_oracle_columns(vscale):
+    """Hybrid PRD on a three-column stack with different velocity fields: rho interpolated per ray to the
+    rest frame, JRest scattered by the formal solution, the redistribution fed by JRest and followed by the
+    PRD formal solution over each column's own scattering wavelengths -- against the restatement (itself
+    bit-identical to the reference, tests/test_oracle.py).  Then new tables for a changed velocity field
+    (lwb200_set_hybrid_prd) and one more iteration."""
+    p = synth.tiny_prd_problem(ncol=3, perturb=True)
+    p.vlosMu *= vscale
+    p.vlosMu[1] *= -0.5
+    p.configure_hprd()
+    q = p.clone()
+    ctx = Context(p)
+
+    def iterate():
+        ctx.formal_sol_gamma_matrices()
+        q.prefill_gamma()
+        for c in range(q.Ncol):
+            oraclelib.OracleContext(q, col=c).fs_iter()
+        assert rel_err(p.hprd.JRest, q.hprd.JRest) <= TOL and q.hprd.JRest.max() > 0.0
+        assert_close(p, q)
+        upd = ctx.prd_redistribute(maxIter=2, tol=1e-6)
+        dRho = [oraclelib.OracleContext(q, col=c).redistribute_prd(maxIter=2, tol=1e-6, nlines=2)['dRho'][:4]
+                for c in range(q.Ncol)]
+        assert upd.NprdSubIter == 2
+        assert rel_err(np.asarray(upd.dRho), np.max(dRho, axis=0)) <= TOL
+        for tp, tq in zip(p.atoms[0].trans, q.atoms[0].trans):
+            if tp.rhoPrd is not None:
+                assert rel_err(tp.rhoPrd, tq.rhoPrd) <= TOL
+        assert rel_err(p.hprd.JRest, q.hprd.JRest) <= TOL
+        e = compare_problems(p, q)
+        assert e['I'] <= TOL and e['J'] <= TOL and e['R'] <= TOL, e
+        ctx.stat_equil()
+        for c in range(q.Ncol):
+            oraclelib.OracleContext(q, col=c).stat_eq()
+        assert compare_problems(p, q)['n'] <= TOL_N
+
+    for it in range(2):
+        iterate()
+    # a changed velocity field: same profiles (they are inputs here), new interpolation tables
+    p.vlosMu *= 1.3
+    q.vlosMu *= 1.3
+    ctx.configure_hprd_coeffs()
+    q.hprd = oraclelib.configure_hprd(q)
+    q.hprd.JRest[...] = p.hprd.JRest
+    iterate()
+    ctx.close()
+
+
 @pytest.mark.parametrize('name', list(STOKES_CASES))
 def test_cuda_stokes_matches_reference_golden(name):
     """Gamma iterations, then single_stokes_fs (up-going rays) and a J-updating full-Stokes pass,

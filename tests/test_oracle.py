@@ -36,6 +36,8 @@ def check_snapshot(p, g, it, jstride, tol, what=('I', 'J', 'Gamma', 'R')):
             for it_, t in enumerate(a.trans):
                 errs[f'R{ia}_{it_}'] = max(rel_err(t.Rij, g[f'it{it}_Rij{ia}_{it_}'], floor=1e-30),
                                           rel_err(t.Rji, g[f'it{it}_Rji{ia}_{it_}'], floor=1e-30))
+    if f'it{it}_JRest' in g.files and 'J' in what:
+        errs['JRest'] = rel_err(p.hprd.JRest, g[f'it{it}_JRest'])
     bad = {k: v for k, v in errs.items() if not v <= tol}
     assert not bad, f'iteration {it}: {bad}'
     return errs
@@ -70,6 +72,8 @@ def check_prd_snapshot(p, g, it, jstride, res, tol):
             'I': rel_err(p.I, g[f'it{it}_prd_I'])}
     J = p.J if not jstride else p.J[:, ::jstride]
     errs['J'] = rel_err(J, g[f'it{it}_prd_J'])
+    if f'it{it}_prd_JRest' in g.files:
+        errs['JRest'] = rel_err(p.hprd.JRest, g[f'it{it}_prd_JRest'])
     for ia, a in enumerate(p.atoms):
         for it_, t in enumerate(a.trans):
             if t.rhoPrd is not None:
@@ -224,6 +228,26 @@ def test_oracle_prd_vs_reference_live():
         r.stat_eq()
         o.stat_eq()
     r.close()
+
+
+@pytest.mark.parametrize('includeDetailed', [False, True])
+def test_product_hprd_tables_match_the_restatement(includeDetailed):
+    """lwb200_configure_hprd (host code of the CUDA library, organised by binary searches) builds the tables
+    of the restated configure_hprd_coeffs element for element: a three-column stack with different velocity
+    fields, Doppler shifts of several grid points, one atom made detailed-static."""
+    p = synth.tiny_prd_problem(nrays=2, ndepth=40, perturb=True, ncol=3)
+    p.vlosMu *= 8.0
+    p.vlosMu[1] *= -12.0
+    p.atoms[0].detailedStatic = includeDetailed
+    a = oraclelib.configure_hprd(p, includeDetailed)
+    b = p.configure_hprd(includeDetailed)
+    assert (a.NprdLa, a.NhPrd) == (b.NprdLa, b.NhPrd) and a.NhPrd > a.NprdLa > 0
+    for name in HPRD_TABLES:
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    assert not np.array_equal(a.column(0, p).JCoeffFrac, a.column(1, p).JCoeffFrac)
+    c1 = a.column(1, p)
+    one = p.column(1)
+    assert np.array_equal(c1.JCoeffFrac, oraclelib.configure_hprd(one, includeDetailed).JCoeffFrac)
 
 
 HPRD_TABLES = ('prdLaOfLa', 'hPrdLaOfLa', 'JCoeffOff', 'JCoeffIdx', 'JCoeffFrac', 'lineAtom', 'lineTrans',
@@ -388,7 +412,8 @@ def test_struct_layout_matches_header():
     import ctypes as C
     assert C.sizeof(capi.LwB200Transition) == 6 * 4 + 5 * 8 + 10 * 8
     assert C.sizeof(capi.LwB200Atom) == 4 * 4 + 8 * 8
-    assert C.sizeof(capi.LwB200Problem) == 12 * 4 + 21 * 8
+    assert C.sizeof(capi.LwB200Problem) == 12 * 4 + 22 * 8
+    assert C.sizeof(capi.LwB200HybridPrd) == 4 * 4 + 11 * 8
 
 
 def test_create_fails_loudly_without_gpu():
