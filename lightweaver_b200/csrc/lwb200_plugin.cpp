@@ -60,6 +60,14 @@ struct Mirror
     std::vector<double> lowerBc, upperBc;
     std::deque<std::vector<double>> polStage;                    // six polarised profiles per polarised line
     std::vector<std::pair<const Transition*, size_t>> polSrc;   // (line, index into polStage)
+    // hybrid PRD: the reference's tables (Spectrum::JCoeffs, Transition::hPrdCoeffs ...) flattened
+    bool hybrid = false;
+    LwB200HybridPrd hprd{};
+    std::vector<int32_t> hPrdLaOfLa_, prdLaOfLa_, JCoeffIdx_, lineAtom_, lineTrans_, rhoI0_;
+    std::vector<int64_t> JCoeffOff_, rhoCoefOff_;
+    std::vector<double> JCoeffFrac_, rhoFrac_;
+    const void* hprdSig[2] = {nullptr, nullptr};
+    uint64_t fpVlos = 0;
     bool uploadedStatic = false;
     bool hasDepth = false;
     bool zplane = false;
@@ -201,8 +209,6 @@ void build_mirror(Context& ctx, Mirror& m)
     Background& bg = *ctx.background;
     if (atmos.Ndim != 1)
         throw std::runtime_error("mali_full_precond_B200 only handles 1D atmospheres");
-    if (spect.JRest)
-        throw std::runtime_error("mali_full_precond_B200: hybrid PRD (JRest) is not supported yet");
     const int K = atmos.Nspace, M = atmos.Nrays, L = (int)spect.wavelength.shape(0);
     m.solver = solver_from_name(ctx.formalSolver.name);
 
@@ -281,8 +287,6 @@ void build_mirror(Context& ctx, Mirror& m)
             auto& tv = m.trans.back();
             for (Transition* t : a->trans)
             {
-                if (t->hPrdCoeffs)
-                    throw std::runtime_error("mali_full_precond_B200: hybrid PRD lines are not supported yet");
                 LwB200Transition ft{};
                 ft.type = t->type == LINE ? LWB200_LINE : LWB200_CONTINUUM;
                 ft.i = t->i;
@@ -329,6 +333,91 @@ void build_mirror(Context& ctx, Mirror& m)
     }
     p.atoms = m.atoms.data();
 
+    // hybrid PRD (configure_hprd_coeffs has run, Prd.cpp:697-946): flatten the reference's own tables
+    m.hybrid = (bool)spect.JRest;
+    p.hprd = nullptr;
+    if (m.hybrid)
+    {
+        if (!spect.prdActive || !spect.hPrdActive || !atmos.vlosMu)
+            throw std::runtime_error("mali_full_precond_B200: spect.JRest without the tables of configure_hprd_coeffs");
+        const size_t NhPrd = spect.hPrdIdxs.size();
+        m.prdLaOfLa_.assign(L, -1);
+        m.hPrdLaOfLa_.assign(L, -1);
+        for (int la = 0; la < L; ++la)
+        {
+            if (spect.prdActive(la))
+                m.prdLaOfLa_[la] = spect.la_to_prdLa(la);
+            if (spect.hPrdActive(la))
+                m.hPrdLaOfLa_[la] = spect.la_to_hPrdLa(la);
+        }
+        m.JCoeffOff_.clear();
+        m.JCoeffIdx_.clear();
+        m.JCoeffFrac_.clear();
+        for (size_t q = 0; q < NhPrd; ++q)
+            for (int mu = 0; mu < M; ++mu)
+                for (int toObs = 0; toObs < 2; ++toObs)
+                    for (int k = 0; k < K; ++k)
+                    {
+                        m.JCoeffOff_.push_back((int64_t)m.JCoeffIdx_.size());
+                        for (const auto& c : spect.JCoeffs(q, mu, toObs, k))
+                        {
+                            m.JCoeffIdx_.push_back(c.idx);
+                            m.JCoeffFrac_.push_back(c.frac);
+                        }
+                    }
+        m.JCoeffOff_.push_back((int64_t)m.JCoeffIdx_.size());
+        if (m.JCoeffIdx_.empty())
+        {
+            m.JCoeffIdx_.push_back(0);
+            m.JCoeffFrac_.push_back(0.0);
+        }
+        m.lineAtom_.clear();
+        m.lineTrans_.clear();
+        m.rhoCoefOff_.clear();
+        m.rhoFrac_.clear();
+        m.rhoI0_.clear();
+        for (size_t ia = 0; ia < m.hostAtoms.size(); ++ia)
+            for (size_t kr = 0; kr < m.hostAtoms[ia]->trans.size(); ++kr)
+            {
+                Transition* t = m.hostAtoms[ia]->trans[kr];
+                if (!t->hPrdCoeffs)
+                    continue;
+                m.lineAtom_.push_back((int32_t)ia);
+                m.lineTrans_.push_back((int32_t)kr);
+                m.rhoCoefOff_.push_back((int64_t)m.rhoFrac_.size());
+                const int Nl = t->Nred - t->Nblue;
+                for (int lt = 0; lt < Nl; ++lt)
+                    for (int mu = 0; mu < M; ++mu)
+                        for (int toObs = 0; toObs < 2; ++toObs)
+                            for (int k = 0; k < K; ++k)
+                            {
+                                const auto& c = t->hPrdCoeffs(lt, mu, toObs, k);
+                                m.rhoFrac_.push_back(c.frac);
+                                m.rhoI0_.push_back(c.i0);
+                            }
+            }
+        LwB200HybridPrd& h = m.hprd;
+        h = LwB200HybridPrd{};
+        h.NprdLa = (int32_t)spect.JRest.shape(0);
+        h.NhPrd = (int32_t)NhPrd;
+        h.Nlines = (int32_t)m.lineAtom_.size();
+        h.prdLaOfLa = m.prdLaOfLa_.data();
+        h.hPrdLaOfLa = m.hPrdLaOfLa_.data();
+        h.JRest = spect.JRest.data();
+        h.JCoeffOff = m.JCoeffOff_.data();
+        h.JCoeffIdx = m.JCoeffIdx_.data();
+        h.JCoeffFrac = m.JCoeffFrac_.data();
+        h.lineAtom = m.lineAtom_.data();
+        h.lineTrans = m.lineTrans_.data();
+        h.rhoCoefOff = m.rhoCoefOff_.data();
+        h.rhoFrac = m.rhoFrac_.data();
+        h.rhoI0 = m.rhoI0_.data();
+        p.hprd = &h;
+        m.hprdSig[0] = spect.JRest.data();
+        m.hprdSig[1] = spect.JCoeffs.data();
+        m.fpVlos = fingerprint(1469598103934665603ULL, atmos.vlosMu.data, (size_t)M * K);
+    }
+
     check(lwb200_create(&p, device_index(), &m.dev), "lwb200_create");
     for (size_t i = 0; i < m.hostAtoms.size(); ++i)
         g_atoms[m.hostAtoms[i]] = {&m, (int)i};
@@ -344,8 +433,15 @@ Mirror& mirror_for(Context& ctx)
     if (it != g_mirrors.end())
     {
         Mirror& m = *it->second;
-        // rebuild when the formal solver changed or depth data appeared
-        if (m.dev && m.solver == solver_from_name(ctx.formalSolver.name) && (!wantDepth || m.hasDepth))
+        // rebuild when the formal solver changed, depth data appeared, or configure_hprd_coeffs ran (again):
+        // new tables, possibly another set of scattering wavelengths -- the plan depends on them
+        Spectrum& sp = *ctx.spect;
+        bool hprdSame = m.hybrid == (bool)sp.JRest;
+        if (hprdSame && m.hybrid)
+            hprdSame = m.hprdSig[0] == (const void*)sp.JRest.data() && m.hprdSig[1] == (const void*)sp.JCoeffs.data()
+                && m.fpVlos == fingerprint(1469598103934665603ULL, ctx.atmos->vlosMu.data,
+                                           (size_t)ctx.atmos->Nrays * ctx.atmos->Nspace);
+        if (m.dev && m.solver == solver_from_name(ctx.formalSolver.name) && (!wantDepth || m.hasDepth) && hprdSame)
             return m;
         destroy_mirror(&m);
         build_mirror(ctx, m);
@@ -447,7 +543,8 @@ IterationResult b200_fs_iter(Context& ctx, bool lambdaIterate, ExtraParams param
     double dJMax = 0.0;
     int64_t dJIdx = 0;
     check(lwb200_fs_iter(m.dev, flags, nullptr, nullptr), "lwb200_fs_iter");
-    check(lwb200_download(m.dev, LWB200_ITER_OUTPUTS | (storeDepth ? LWB200_DEPTH : 0) | (m.zplane ? LWB200_ZPLANE : 0)),
+    check(lwb200_download(m.dev, LWB200_ITER_OUTPUTS | (storeDepth ? LWB200_DEPTH : 0) | (m.zplane ? LWB200_ZPLANE : 0)
+                                     | (m.hybrid ? LWB200_PRD : 0)), // (hybrid PRD: spect.JRest)
           "lwb200_download");
     check(lwb200_sync(m.dev), "lwb200_sync");
     check(lwb200_last_dj(m.dev, &dJMax, &dJIdx), "lwb200_last_dj");

@@ -122,6 +122,51 @@ def test_reference_core_with_b200_scheme_matches_scalar_scheme(solver):
 @needs_plugin
 @pytest.mark.ref
 @pytest.mark.gpu
+def test_reference_core_hybrid_prd_through_the_b200_scheme():
+    """Hybrid PRD: the reference core runs configure_hprd_coeffs itself; the shim flattens ITS tables
+    (Spectrum::JCoeffs, hPrdIdxs, Transition::hPrdCoeffs), the device scatters into spect.JRest and
+    redistributes in the rest frame.  Against the reference core with its scalar scheme; then the velocity
+    field changes, configure_hprd_coeffs runs again and the shim must pick the new tables up."""
+    p = synth.tiny_prd_problem(perturb=True)
+    p.vlosMu *= 6.0
+    q = p.clone()
+    gpu = reflib.RefContext(p, scheme=PLUGIN)
+    cpu = reflib.RefContext(q, scheme='scalar')
+    gpu.configure_hprd()
+    cpu.configure_hprd()
+    for it in range(3):
+        if it == 2:
+            p.vlosMu *= 1.2
+            q.vlosMu *= 1.2
+            gpu.configure_hprd()
+            cpu.configure_hprd()
+        p.prefill_gamma()
+        q.prefill_gamma()
+        gpu.fs_iter()
+        cpu.fs_iter()
+        assert rel_err(gpu.jrest(), cpu.jrest()) <= 1e-9 and cpu.jrest().max() > 0.0
+        a = gpu.redistribute_prd(maxIter=3, tol=1e-3, nlines=2)
+        b = cpu.redistribute_prd(maxIter=3, tol=1e-3, nlines=2)
+        assert a['nIter'] == b['nIter']
+        n = a['nIter']
+        assert rel_err(a['dRho'][:2 * n], b['dRho'][:2 * n]) <= 1e-9
+        assert rel_err(a['dJPrdMax'], b['dJPrdMax']) <= 1e-9
+        for tp, tq in zip(p.atoms[0].trans, q.atoms[0].trans):
+            if tp.rhoPrd is not None:
+                assert rel_err(tp.rhoPrd, tq.rhoPrd) <= 1e-9
+        assert rel_err(gpu.jrest(), cpu.jrest()) <= 1e-9
+        e = compare_problems(p, q)
+        assert e['I'] <= 1e-9 and e['J'] <= 1e-9 and e['R'] <= 1e-9, e
+        gpu.stat_eq()
+        cpu.stat_eq()
+        assert compare_problems(p, q)['n'] <= 1e-8
+    gpu.close()
+    cpu.close()
+
+
+@needs_plugin
+@pytest.mark.ref
+@pytest.mark.gpu
 def test_reference_core_redistributes_prd_through_the_b200_scheme():
     """redistribute_prd_lines (Prd.cpp:648-653) dispatches to the scheme's redistribute_prd slot:
     the reference core with our plugin against the reference core with its scalar scheme."""
