@@ -101,8 +101,11 @@ __device__ __forceinline__ void bezier3_prepare_s(const GeomS<NCH>& g, int lane,
 // on an SM instead of two: the recurrence is bound by the latency a scheduler's two warps cannot hide, and
 // registers are what stood in the way of a third and fourth.
 // Same arithmetic and accumulation order as ray_kernel.
+#ifndef LWB200_RAY_WARPS
+#define LWB200_RAY_WARPS 4
+#endif
 template <int NCH, int NL, int MINB>
-__global__ void __launch_bounds__(128, MINB)
+__global__ void __launch_bounds__(32 * LWB200_RAY_WARPS, MINB)
 ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int perWarp, int colBase,
                 int lambdaIterate, int fsMode)
 {
@@ -121,7 +124,7 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
     const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0);
     const int lane = lane_id();
     constexpr int NPROW = NL > 0 ? NL : 0;    // this ray's profile rows, parked for the moment phase
-    double* warpS = dynS + 4 * RS + (size_t)(warp & 3) * (NCONST + NMOM + NPROW + 1) * RS;
+    double* warpS = dynS + 4 * RS + (size_t)(warp % LWB200_RAY_WARPS) * (NCONST + NMOM + NPROW + 1) * RS;
     double* cS = warpS + lane;                // constants: this lane's element of chunk 0 of array 0
     double* mS = warpS + NCONST * RS + lane;  // moments
     double* pS = warpS + (NCONST + NMOM) * RS + lane;          // profile rows of the current ray
@@ -511,7 +514,7 @@ constexpr size_t ray_smem_bytes()
     constexpr int NCONST = (3 + 2 * NLA) > 6 ? (3 + 2 * NLA) : 6;
     constexpr int NMOM = 2 + 4 * (NL > 0 ? NL : 0) + NPAIR;
     constexpr int NPROW = NL > 0 ? NL : 0;
-    return (size_t)(4 + 4 * (NCONST + NMOM + NPROW + 1)) * 32 * NCH * sizeof(double);
+    return (size_t)(4 + LWB200_RAY_WARPS * (NCONST + NMOM + NPROW + 1)) * 32 * NCH * sizeof(double);
 }
 
 } // namespace lwb200

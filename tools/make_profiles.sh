@@ -15,7 +15,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-fi
 for WL in c3 c2 deep; do
   case $WL in
     c3) ARGS="128 2 c3"; N=5;;
-    c2) ARGS="1 2 c2"; N=12;;
+    c2) ARGS="1 2 c2"; N=9;;
     deep) ARGS="1 2 deep"; N=5;;
   esac
   ncu --set full --clock-control none --import-source on -k "$KREGEX" -s $N -c $N \
@@ -23,7 +23,7 @@ for WL in c3 c2 deep; do
   python tools/ncu_summary.py $OUT/${TAG}_full_$WL.ncu-rep > $OUT/${TAG}_summary_$WL.txt 2>&1
   ncu -i $OUT/${TAG}_full_$WL.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_traffic.py > $OUT/${TAG}_traffic_$WL.json
 done
-python tools/ncu_lines.py $OUT/${TAG}_full_c3.ncu-rep ray_smem_kernelILi3ELi1 60 > $OUT/${TAG}_lines_c3_ray_NL1.txt 2>&1
+NCU_KERNEL_ID=::regex:ray_smem:1 python tools/ncu_lines.py $OUT/${TAG}_full_c3.ncu-rep ray_smem_kernelILi3ELi1 60 > $OUT/${TAG}_lines_c3_ray_NL1.txt 2>&1
 NCU_KERNEL_ID=::regex:gamma_tile:1 python tools/ncu_lines.py $OUT/${TAG}_full_c3.ncu-rep gamma_tile_kernelILi1 40 > $OUT/${TAG}_lines_c3_gamma.txt 2>&1
 rm -f $OUT/${TAG}_full_c2.ncu-rep $OUT/${TAG}_full_deep.ncu-rep
 ls -la $OUT | tail -20
