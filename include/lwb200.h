@@ -278,6 +278,14 @@ int lwb200_compute_profiles(LwB200Context* ctx);
  * J, Gamma (onto the uploaded prefill) and Rij/Rji, finalises Gamma.
  * dJMax / dJMaxIdx may be NULL (no device->host sync is then forced). */
 int lwb200_fs_iter(LwB200Context* ctx, uint32_t flags, double* dJMax, int64_t* dJMaxIdx);
+/* The "J20" extra parameter of formal_sol_full_stokes (Source/FormalStokes.cpp:676-681): J20 is the caller's
+ * [Ncol][Nspect][Nspace] radiation-field anisotropy, or NULL to switch the option off again.  While it is set,
+ * lwb200_formal_sol_full_stokes sends every wavelength through the Stokes solver, adds the scattering of the
+ * anisotropy it finds in the array to the I and Q emissivities of a J-updating pass (a pass that does not
+ * update J sees none, as in the reference, :433-437) and, with updateJ, leaves the new anisotropy
+ * sum_rays w_mu (3 mu^2 - 1) / (2 sqrt 2) I + w_mu 3 (mu^2 - 1) / (2 sqrt 2) Q in it (after lwb200_sync). */
+int lwb200_set_j20(LwB200Context* ctx, double* J20);
+
 /* Replaces configure_hprd_coeffs (Source/Prd.cpp:697-946) for every column of the problem: from the wavelength
  * grid, the ranges of the PRD lines (lines with rhoPrd; those of detailed-static atoms on request) and
  * vlosMu, fills *out with the tables of LwB200HybridPrd (JRest zeroed).  Host code, no device needed.  The

@@ -174,6 +174,7 @@ def load():
     lib.lwb200_fs_iter.argtypes = [vp, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.lwb200_finalise.argtypes = [vp]
     lib.lwb200_set_collision_prefill.argtypes = [vp, C.c_int, C.c_double]
+    lib.lwb200_set_j20.argtypes = [vp, _dp]
     lib.lwb200_set_hybrid_prd.argtypes = [vp, C.POINTER(LwB200HybridPrd)]
     lib.lwb200_configure_hprd.argtypes = [C.POINTER(LwB200Problem), C.c_int, C.POINTER(LwB200HybridPrd)]
     lib.lwb200_free_hprd.argtypes = [C.POINTER(LwB200HybridPrd)]
@@ -200,7 +201,7 @@ def load():
                                       C.POINTER(C.c_int64)]
     for name in ('device_count', 'create', 'destroy', 'set_stream', 'set_lambda_range', 'upload',
                  'download', 'sync', 'compute_profiles', 'fs_iter', 'finalise', 'dj_max',
-                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes', 'nr_post_update', 'stat_eq_async', 'last_singular', 'last_dj', 'set_zplane', 'population_solve', 'set_collision_prefill', 'set_hybrid_prd', 'configure_hprd'):
+                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes', 'nr_post_update', 'stat_eq_async', 'last_singular', 'last_dj', 'set_zplane', 'population_solve', 'set_collision_prefill', 'set_hybrid_prd', 'configure_hprd', 'set_j20'):
         getattr(lib, 'lwb200_' + name).restype = C.c_int
     if lib.lwb200_abi_version() != ABI_VERSION:
         raise LwB200Error('liblwb200.so ABI version mismatch; rebuild')
@@ -223,5 +224,5 @@ EXPORTED_SYMBOLS = [
     'lwb200_time_dep_update', 'lwb200_formal_sol_full_stokes',
     'lwb200_nr_post_update', 'lwb200_stat_eq_async', 'lwb200_last_singular', 'lwb200_last_dj',
     'lwb200_set_zplane', 'lwb200_population_solve', 'lwb200_global_launch_count',
-    'lwb200_set_collision_prefill', 'lwb200_set_hybrid_prd', 'lwb200_configure_hprd', 'lwb200_free_hprd',
+    'lwb200_set_collision_prefill', 'lwb200_set_j20', 'lwb200_set_hybrid_prd', 'lwb200_configure_hprd', 'lwb200_free_hprd',
 ]

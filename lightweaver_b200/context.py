@@ -303,6 +303,16 @@ class Context:
         them again."""
         if self.problem.Quv is None:
             raise capi.LwB200Error('single_stokes_fs: the problem has no polarised line')
+        # extraParams = {'J20': float64 array [Ncol, Nspect, Nspace]}: the radiation-field anisotropy
+        # (FormalStokes.cpp:676-681), read and -- with updateJ -- rewritten in place
+        J20 = extraParams.get('J20') if extraParams else None
+        if J20 is not None:
+            shape = (self.problem.Ncol, self.problem.Nspect, self.problem.Nspace)
+            if J20.shape != shape or J20.dtype != np.float64 or not J20.flags.c_contiguous:
+                raise ValueError(f'J20 must be a C-contiguous float64 array of shape {shape}')
+        if J20 is not None or getattr(self, '_j20', None) is not None:
+            capi.check(self.lib.lwb200_set_j20(self._h, capi.dptr(J20)))
+        self._j20 = J20
         first = not getattr(self, '_stokes_sent', False)
         self.upload(capi.POPS | capi.JBAR | (capi.STOKES if (first or recompute) else 0))
         self._stokes_sent = True

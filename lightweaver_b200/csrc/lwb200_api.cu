@@ -225,6 +225,9 @@ struct LwB200Context
     std::vector<int> prdLineDetailed;
     DevBuf<DevPrdLine> dPrdLines;
     DevBuf<double> qelast, cmat, rhoPrev, prdMax, nOld;
+    // the "J20" extra parameter of the Stokes pass: the caller's array and its device copies
+    double* j20Host = nullptr;
+    DevBuf<double> dJ20, dJ20dag;
     // hybrid PRD (LwB200HybridPrd): the caller's tables (host pointers) and their device copies
     bool hybrid = false;
     LwB200HybridPrd hprdHost{};
@@ -1835,6 +1838,7 @@ int lwb200_destroy(LwB200Context* c)
                            &c->dAtomGammaOff, &c->dAtomDetailed, &c->dSingular, &c->dPhiAsym};
     for (auto* b : ints)
         b->release();
+    c->dJ20.release(); c->dJ20dag.release();
     c->dHprdLaOfLa.release(); c->dPrdLaOfLa.release(); c->dJCoeffIdx.release(); c->dHprdI0.release();
     c->dJCoeffOff.release(); c->dJRest.release(); c->dJCoeffFrac.release(); c->dHprdFrac.release();
     for (void* r : c->registered)
@@ -2551,6 +2555,21 @@ int lwb200_compute_profiles(LwB200Context* c)
     return check_phi_symmetry(c);
 }
 
+int lwb200_set_j20(LwB200Context* c, double* J20)
+{
+    CU(cudaSetDevice(c->device));
+    if ((J20 != nullptr) != (c->j20Host != nullptr))
+        c->stokesLists = false; // (with J20 every wavelength goes through the Stokes solver)
+    c->j20Host = J20;
+    if (J20 && !c->dJ20.p)
+    {
+        const size_t n = (size_t)c->prob.Ncol * c->prob.Nspect * c->prob.Nspace;
+        if (c->dJ20.alloc(n) || c->dJ20dag.alloc(n))
+            return fail("out of device memory (J20)");
+    }
+    return 0;
+}
+
 int lwb200_set_hybrid_prd(LwB200Context* c, const LwB200HybridPrd* tables)
 {
     CU(cudaSetDevice(c->device));
@@ -3085,10 +3104,13 @@ int lwb200_formal_sol_full_stokes(LwB200Context* c, int updateJ, int upOnly, dou
         return fail("lwb200_formal_sol_full_stokes: not available while a column mask is set (lwb200_set_active_columns)");
     if (!c->nstarUploaded)
         return fail("lwb200_formal_sol_full_stokes: inputs have not been uploaded (lwb200_upload)");
-    if (c->polTot == 0)
+    const bool j20 = c->j20Host != nullptr;
+    if (c->polTot == 0 && !j20)
         return fail("lwb200_formal_sol_full_stokes: the problem has no polarised line");
-    if (!c->stokesUploaded)
+    if (c->polTot > 0 && !c->stokesUploaded)
         return fail("lwb200_formal_sol_full_stokes: polarised profiles have not been uploaded (LWB200_STOKES)");
+    if (!c->Quv.p)
+        return fail("lwb200_formal_sol_full_stokes: the problem has no Quv array");
     if (c->laLo != 0 || c->laHi != c->prob.Nspect)
         return fail("lwb200_formal_sol_full_stokes: not available on a wavelength shard (column-shard instead)");
     if (c->prob.Nspace < 3)
@@ -3106,7 +3128,7 @@ int lwb200_formal_sol_full_stokes(LwB200Context* c, int updateJ, int upOnly, dou
             for (size_t g = 0; g < c->trans.size(); ++g)
                 if (c->transPolOff[g] >= 0 && la >= c->devTrans[g].Nblue && la < c->devTrans[g].Nred)
                     isPol = true;
-            if (isPol)
+            if (isPol || j20) // (J20: polarisedFrequency = true everywhere, FormalStokes.cpp:490)
             {
                 if (c->laKind[la] >= 4)
                     return fail("lwb200_formal_sol_full_stokes: a polarised line overlaps more than two other lines");
@@ -3133,6 +3155,20 @@ int lwb200_formal_sol_full_stokes(LwB200Context* c, int updateJ, int upOnly, dou
     c->fetchEarly = false;
     c->lastLaunches = 0;
     CU(cudaMemsetAsync(c->Quv.p, 0, c->Quv.n * sizeof(double), s));
+    c->P.j20 = j20 ? 1 : 0;
+    c->P.J20 = c->dJ20.p;
+    c->P.J20dag = nullptr;
+    if (j20)
+    {
+        // the caller's anisotropy is the J20-dagger of a J-updating pass, which rebuilds it from zero
+        CU(cudaMemcpyAsync(c->dJ20.p, c->j20Host, c->dJ20.n * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (updateJ)
+        {
+            CU(cudaMemcpyAsync(c->dJ20dag.p, c->dJ20.p, c->dJ20.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            CU(cudaMemsetAsync(c->dJ20.p, 0, c->dJ20.n * sizeof(double), s));
+            c->P.J20dag = c->dJ20dag.p;
+        }
+    }
     if (updateJ)
     {
         // the polarised rays add into J atomically: keep J-dagger aside and clear their rows
@@ -3156,8 +3192,11 @@ int lwb200_formal_sol_full_stokes(LwB200Context* c, int updateJ, int upOnly, dou
     const int rc = launch_fs<MODE_ITER>(c, 0, 0, 0);
     c->customLists = false;
     c->stokesFsMode = 0;
+    c->P.j20 = 0;
     if (rc)
         return 1;
+    if (j20 && updateJ) // (travels with the stream: in the caller's array after the next lwb200_sync)
+        CU(cudaMemcpyAsync(c->j20Host, c->dJ20.p, c->dJ20.n * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (updateJ)
     {
         stokes_dj_kernel<<<dim3(c->nPolLam, p.Ncol), 32, 0, s>>>(c->P, c->dPolLam.p, c->nPolLam);

@@ -132,6 +132,11 @@ struct DevProblem
     double* Jdag;             // [Ncol][L][K] copy of J taken before a J-updating Stokes pass
     // ZPlaneDecomposition (lwb200_set_zplane): [Ncol][L][M] each, nullptr: not recorded
     double *zPlaneUp, *zPlaneDown;
+    // the "J20" extra parameter of the Stokes pass (lwb200_set_j20): [Ncol][L][K] each, nullptr: off
+    double* J20;                // new anisotropy, accumulated by the J-updating pass
+    const double* J20dag;       // the one on entry; nullptr in a pass that does not update J (the reference's
+                                // J20Dag stays zero there, FormalStokes.cpp:433-437)
+    int j20;
     // hybrid PRD (LwB200HybridPrd): nullptr / 0 without it
     const int* hprdLaOfLa;      // [Ncol][L] row of this column's JCoeffs tables, -1: the wavelength does not scatter
     const int* prdLaOfLa;       // [L] row of JRest, -1: no PRD line active

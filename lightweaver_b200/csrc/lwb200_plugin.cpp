@@ -607,9 +607,15 @@ IterationResult b200_redistribute_prd(Context& ctx, int maxIter, f64 tol, ExtraP
 // FsIterationFns::full_stokes_fs (LwFormalInterface.hpp:117): polarised formal solution.
 IterationResult b200_full_stokes_fs(Context& ctx, bool updateJ, bool upOnly, ExtraParams params)
 {
+    // the "J20" extra parameter (FormalStokes.cpp:676-681): the anisotropy array, read and rewritten in place
+    double* j20 = nullptr;
     if (params.contains("J20"))
-        throw std::runtime_error("mali_full_precond_B200: the J20 option of the full-Stokes formal solution "
-                                 "(FormalStokes.cpp:678) has no device kernel");
+    {
+        F64View2D v = params.get_as<F64View2D>("J20");
+        if (!v || v.shape(0) != ctx.spect->wavelength.shape(0) || v.shape(1) != ctx.atmos->Nspace)
+            throw std::runtime_error("mali_full_precond_B200: J20 must be [Nspect, Nspace]");
+        j20 = v.data;
+    }
     if (!ctx.atmos->B)
         throw std::runtime_error("Magnetic field required"); // as formal_sol_full_stokes_impl, FormalStokes.cpp:670-671
     size_t nPol = 0;
@@ -617,7 +623,7 @@ IterationResult b200_full_stokes_fs(Context& ctx, bool updateJ, bool upOnly, Ext
         for (Atom* a : *list)
             for (Transition* t : a->trans)
                 nPol += (t->type == LINE && t->polarised && t->phiQ) ? 1 : 0;
-    if (nPol == 0 || !ctx.spect->Quv)
+    if ((nPol == 0 && !j20) || !ctx.spect->Quv)
         throw std::runtime_error("mali_full_precond_B200: full-Stokes formal solution without a polarised line "
                                  "(call setup_stokes first) or without spect.Quv");
     {
@@ -644,6 +650,7 @@ IterationResult b200_full_stokes_fs(Context& ctx, bool updateJ, bool upOnly, Ext
             std::memcpy(m.polStage[src.second].data() + a * per, arrs[a], per * sizeof(f64));
     }
     check(lwb200_upload(m.dev, LWB200_STOKES | LWB200_PROFILE), "lwb200_upload");
+    check(lwb200_set_j20(m.dev, j20), "lwb200_set_j20");
     double dJMax = 0.0;
     int64_t dJIdx = 0;
     check(lwb200_formal_sol_full_stokes(m.dev, updateJ ? 1 : 0, upOnly ? 1 : 0, &dJMax, &dJIdx),

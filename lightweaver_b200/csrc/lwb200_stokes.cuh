@@ -159,6 +159,13 @@ stokes_kernel(const DevProblem P, const int* __restrict__ polLam, int nPol, int 
     const double* Jsrc = updateJ ? P.Jdag + rowLK : nullptr;
     const double* height = P.height + (size_t)col * K;
     const double zmu = 1.0 / __ldg(P.muz + mu);
+    // the "J20" extra parameter (FormalStokes.cpp:485-486, :575-583): the anisotropy of the last J-updating pass
+    // scatters into the I and Q emissivities of every wavelength
+    const double inv2root2 = 1.0 / (2.0 * sqrt(2.0));
+    const double mu2 = __ldg(P.muz + mu) * __ldg(P.muz + mu);
+    const double wJ20_I = inv2root2 * (3.0 * mu2 - 1.0);
+    const double wJ20_Q = inv2root2 * 3.0 * (mu2 - 1.0);
+    const double* J20src = (P.j20 && P.J20dag) ? P.J20dag + rowLK : nullptr;
 
     // line slots of this wavelength (<= 3), constants of Transition::uv (LwTransition.hpp:93-130)
     double vB[3], gS[3], AB[3];
@@ -193,6 +200,12 @@ stokes_kernel(const DevProblem P, const int* __restrict__ polLam, int nPol, int 
         for (int q = 1; q < 7; ++q)
             chi[q] = 0.0;
         eta[1] = eta[2] = eta[3] = 0.0;
+        if (J20src)
+        {
+            const double sj = __ldg(P.scaBg + rowLK + k) * J20src[k];
+            eta[0] += wJ20_I * sj;
+            eta[1] = wJ20_Q * sj;
+        }
         for (int l = 0; l < NL; ++l)
         {
             const double ni = __ldg(ncol + (size_t)levI[l] * K + k);
@@ -267,8 +280,13 @@ stokes_kernel(const DevProblem P, const int* __restrict__ polLam, int nPol, int 
     }
     const double w = 0.5 * __ldg(P.wmu + mu);
     double* Jrow = P.J + rowLK;
+    // J20(la, k) += wJ20_I wmu I + wJ20_Q wmu Q  (:642-648; the full quadrature weight, not half of it)
+    double* J20row = (P.j20 && updateJ) ? P.J20 + rowLK : nullptr;
+    const double wI20 = wJ20_I * __ldg(P.wmu + mu), wQ20 = wJ20_Q * __ldg(P.wmu + mu);
     if (updateJ)
         atomicAdd(Jrow + k_start, w * Iprev[0]);
+    if (J20row)
+        atomicAdd(J20row + k_start, wI20 * Iprev[0]);
 
     // set-up at the first interior point (:190-216)
     int k = k_start + dk;
@@ -357,6 +375,8 @@ stokes_kernel(const DevProblem P, const int* __restrict__ polLam, int nPol, int 
             Iprev[i] = V0[i];
         if (updateJ)
             atomicAdd(Jrow + k, w * V0[0]);
+        if (J20row)
+            atomicAdd(J20row + k, wI20 * V0[0] + wQ20 * V0[1]);
         // shuffle along (:326-338)
         pu = p0;
         p0 = pd;

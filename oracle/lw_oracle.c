@@ -2037,9 +2037,19 @@ static void stokes_bezier3_sweep(int Ndep, const double* height, const double* c
 
 int lwo_full_stokes(const LwB200Problem* p, int col, int updateJ, int upOnly, double* dJMaxOut, int64_t* dJMaxIdx)
 {
+    return lwo_full_stokes_j20(p, col, updateJ, upOnly, NULL, dJMaxOut, dJMaxIdx);
+}
+
+/* J20all: the "J20" extra parameter (FormalStokes.cpp:676-681), [Ncol][Nspect][Nspace], or NULL. */
+int lwo_full_stokes_j20(const LwB200Problem* p, int col, int updateJ, int upOnly, double* J20all, double* dJMaxOut,
+                        int64_t* dJMaxIdx)
+{
     const int K = p->Nspace, M = p->Nrays, L = p->Nspect;
     if (!p->Quv)
         return 1;
+    double* J20 = J20all ? J20all + (size_t)col * L * K : NULL;
+    double* J20Dag = (double*)calloc(K, sizeof(double)); /* F64Arr(Nspace): zero until a J-updating wavelength fills it */
+    const double inv2root2 = 1.0 / (2.0 * sqrt(2.0));
     const double* h = p->height + (size_t)col * K;
     const double* T = p->temperature + (size_t)col * K;
     Scratch* s = scratch_new(p);
@@ -2060,12 +2070,22 @@ int lwo_full_stokes(const LwB200Problem* p, int col, int updateJ, int upOnly, do
         {
             memcpy(s->JDag, J, sizeof(double) * K);
             memset(J, 0, sizeof(double) * K);
+            if (J20)
+            {
+                memcpy(J20Dag, J20 + (size_t)la * K, sizeof(double) * K);
+                memset(J20 + (size_t)la * K, 0, sizeof(double) * K);
+            }
         }
         for (int a = 0; a < p->Natom; ++a)
             setup_wavelength(p, col, a, la, s);
-        const int contOnly = continua_only(p, la);
+        /* (need full integration if we're doing J20, :469-471) */
+        const int contOnly = J20 ? 0 : continua_only(p, la);
         const int toObsStart = upOnly ? 1 : 0;
         for (int mu = 0; mu < M; ++mu)
+        {
+            const double mu2 = sq(p->muz[mu]);
+            const double wJ20_I = inv2root2 * (3.0 * mu2 - 1.0);
+            const double wJ20_Q = inv2root2 * 3.0 * (mu2 - 1.0);
             for (int toObs = toObsStart; toObs < 2; ++toObs)
             {
                 /* NOTE: as in the reference, polarisedFrequency is only (re)determined when the
@@ -2073,7 +2093,7 @@ int lwo_full_stokes(const LwB200Problem* p, int col, int updateJ, int upOnly, do
                 static int polarisedFrequency;
                 if (!contOnly || (mu == 0 && toObs == toObsStart))
                 {
-                    polarisedFrequency = 0;
+                    polarisedFrequency = J20 ? 1 : 0; /* bool polarisedFrequency = J20 || false  (:490) */
                     memset(chiTot, 0, sizeof(double) * 7 * K);
                     memset(etaTot, 0, sizeof(double) * 4 * K);
                     for (int pass = 0; pass < 2; ++pass) /* active atoms, then detailed ones */
@@ -2117,6 +2137,12 @@ int lwo_full_stokes(const LwB200Problem* p, int col, int updateJ, int upOnly, do
                                     }
                                 }
                             }
+                        }
+                    if (J20) /* :575-583 */
+                        for (int k = 0; k < K; ++k)
+                        {
+                            etaTot[k] += wJ20_I * bgSca[k] * J20Dag[k];
+                            etaTot[(size_t)1 * K + k] += wJ20_Q * bgSca[k] * J20Dag[k];
                         }
                     for (int k = 0; k < K; ++k)
                     {
@@ -2177,8 +2203,16 @@ int lwo_full_stokes(const LwB200Problem* p, int col, int updateJ, int upOnly, do
                     const double wmu = p->wmu[mu];
                     for (int k = 0; k < K; ++k)
                         J[k] += 0.5 * wmu * I[k];
+                    if (J20) /* :642-648 */
+                    {
+                        const double wmuJ20_I = wJ20_I * wmu;
+                        const double wmuJ20_Q = wJ20_Q * wmu;
+                        for (int k = 0; k < K; ++k)
+                            J20[(size_t)la * K + k] += wmuJ20_I * I[k] + wmuJ20_Q * I[(size_t)1 * K + k];
+                    }
                 }
             }
+        }
         if (updateJ)
         {
             double dJ = 0.0;
@@ -2195,6 +2229,7 @@ int lwo_full_stokes(const LwB200Problem* p, int col, int updateJ, int upOnly, do
     free(etaTot);
     free(S);
     free(I);
+    free(J20Dag);
     scratch_free(s);
     if (dJMaxOut) *dJMaxOut = updateJ ? dJMax : 0.0;
     if (dJMaxIdx) *dJMaxIdx = updateJ ? idx : 0;

@@ -53,6 +53,12 @@ int lwo_fs_iter_columns(const LwB200Problem* p, int col0, int ncol, unsigned fla
  * at unpolarised wavelengths: whatever the last polarised ray left in I(1..3, 0)) and, with updateJ,
  * J and dJ (argmax index). */
 int lwo_full_stokes(const LwB200Problem* p, int col, int updateJ, int upOnly, double* dJMax, int64_t* dJMaxIdx);
+/* The same with the "J20" extra parameter (FormalStokes.cpp:433-437, :469-471, :485-490, :575-583, :642-648):
+ * J20 [Ncol][Nspect][Nspace] is the radiation-field anisotropy of the last J-updating pass on entry (its
+ * scattering term enters the I and Q emissivities, every wavelength goes through the Stokes solver) and,
+ * with updateJ, the new one on return.  NULL: lwo_full_stokes. */
+int lwo_full_stokes_j20(const LwB200Problem* p, int col, int updateJ, int upOnly, double* J20, double* dJMax,
+                        int64_t* dJMaxIdx);
 
 /* time_dependent_update_impl (UpdatePopulations.cpp:120-151) of atom `atom` on column `col`;
  * nOld is [Ncol][Nlevel][Nspace].  Returns 1 for "Singular Matrix". */

@@ -40,6 +40,7 @@ def load():
                                   C.POINTER(C.c_int64)]
     lib.lwo_fs_iter_columns.argtypes = [vp, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int]
     lib.lwo_full_stokes.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, i64p]
+    lib.lwo_full_stokes_j20.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, i64p]
     lib.lwo_nr_post_update.argtypes = [vp, C.c_int, vp]
     lib.lwo_time_dep_update.argtypes = [vp, C.c_int, C.c_int, dp, C.c_double]
     lib.lwo_redistribute_prd.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp,
@@ -98,9 +99,15 @@ class OracleContext:
         if rc != 0:
             raise RuntimeError('Singular Matrix')
 
-    def full_stokes(self, updateJ=False, upOnly=True):
+    def full_stokes(self, updateJ=False, upOnly=True, J20=None):
+        """J20: the 'J20' extra parameter for the whole problem, float64 [Ncol, Nspect, Nspace], or None"""
         dJ, idx = C.c_double(0.0), C.c_int64(0)
-        assert self.lib.lwo_full_stokes(C.byref(self._cs), self.col, int(updateJ), int(upOnly), C.byref(dJ), C.byref(idx)) == 0
+        if J20 is None:
+            assert self.lib.lwo_full_stokes(C.byref(self._cs), self.col, int(updateJ), int(upOnly), C.byref(dJ), C.byref(idx)) == 0
+        else:
+            assert J20.dtype == np.float64 and J20.flags.c_contiguous
+            assert self.lib.lwo_full_stokes_j20(C.byref(self._cs), self.col, int(updateJ), int(upOnly),
+                                                J20.ctypes.data_as(C.POINTER(C.c_double)), C.byref(dJ), C.byref(idx)) == 0
         return dJ.value, idx.value
 
     def nr_post_update(self, upd):

@@ -370,12 +370,22 @@ int lwref_formal_sol(LwRefHandle* hh, int upOnly)
 }
 
 // formal_sol_full_stokes (LwContext.single_stokes_fs, LwMiddleLayer.pyx): polarised formal solution.
+int lwref_full_stokes_j20(LwRefHandle* hh, int updateJ, int upOnly, double* J20, double* dJMax, int64_t* dJMaxIdx);
 int lwref_full_stokes(LwRefHandle* hh, int updateJ, int upOnly, double* dJMax, int64_t* dJMaxIdx)
+{
+    return lwref_full_stokes_j20(hh, updateJ, upOnly, nullptr, dJMax, dJMaxIdx);
+}
+
+// J20: the "J20" extra parameter of this column, [Nspect][Nspace], or NULL
+int lwref_full_stokes_j20(LwRefHandle* hh, int updateJ, int upOnly, double* J20, double* dJMax, int64_t* dJMaxIdx)
 {
     auto* h = (LwRef*)hh;
     try
     {
-        IterationResult r = formal_sol_full_stokes(*h->ctx, updateJ != 0, upOnly != 0, ExtraParams{});
+        ExtraParams params{};
+        if (J20)
+            params.insert("J20", F64View2D(J20, h->prob->Nspect, h->prob->Nspace));
+        IterationResult r = formal_sol_full_stokes(*h->ctx, updateJ != 0, upOnly != 0, params);
         if (dJMax) *dJMax = r.dJMax;
         if (dJMaxIdx) *dJMaxIdx = r.dJMaxIdx;
         return 0;

@@ -61,6 +61,7 @@ def load():
     lib.lwref_formal_sol.argtypes = [vp, C.c_int]
     lib.lwref_stat_eq.argtypes = [vp]
     lib.lwref_full_stokes.argtypes = [vp, C.c_int, C.c_int, dp, C.POINTER(C.c_int64)]
+    lib.lwref_full_stokes_j20.argtypes = [vp, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int64)]
     lib.lwref_nr_post_update.argtypes = [vp, vp]
     lib.lwref_time_dep_update.argtypes = [vp, C.c_int, dp, C.c_double]
     lib.lwref_redistribute_prd.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp,
@@ -165,9 +166,16 @@ class RefContext:
         _check(self.lib.lwref_get_jrest(self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
 
-    def full_stokes(self, updateJ=False, upOnly=True):
+    def full_stokes(self, updateJ=False, upOnly=True, J20=None):
+        """J20: the 'J20' extra parameter of THIS column, float64 [Nspect, Nspace] (a view is fine as long
+        as it is C-contiguous), or None"""
         dJ, idx = C.c_double(0.0), C.c_int64(0)
-        _check(self.lib.lwref_full_stokes(self.h, int(updateJ), int(upOnly), C.byref(dJ), C.byref(idx)))
+        if J20 is None:
+            _check(self.lib.lwref_full_stokes(self.h, int(updateJ), int(upOnly), C.byref(dJ), C.byref(idx)))
+        else:
+            assert J20.flags.c_contiguous and J20.shape == (self.problem.Nspect, self.problem.Nspace)
+            _check(self.lib.lwref_full_stokes_j20(self.h, int(updateJ), int(upOnly),
+                                                  J20.ctypes.data_as(C.POINTER(C.c_double)), C.byref(dJ), C.byref(idx)))
         return dJ.value, idx.value
 
     def nr_post_update(self, upd):

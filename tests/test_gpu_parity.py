@@ -417,6 +417,39 @@ def test_cuda_stokes_vs_oracle_columns(ndepth):
     ctx.close()
 
 
+def test_cuda_stokes_j20_vs_oracle_columns():
+    """The 'J20' extra parameter of the full-Stokes formal solution (FormalStokes.cpp:676-681) on a perturbed
+    magnetised two-column stack: two J-updating passes (the second scatters the anisotropy the first one built
+    into the I and Q emissivities of every wavelength), a pass that does not update J (sees no anisotropy, as in
+    the reference), then the option switched off again."""
+    from tests.golden.make_golden import polarised_mask
+    p = synth.tiny_stokes_problem(ncol=2, perturb=True)
+    q = p.clone()
+    ctx = Context(p)
+    ctx.formal_sol_gamma_matrices()
+    oracle_iter(q, stat_eq=False)
+    m = polarised_mask(p)
+    Ja = np.zeros((p.Ncol, p.Nspect, p.Nspace))
+    Jb = np.zeros_like(Ja)
+    scale = np.abs(q.I).max()
+    for n, (uj, uo) in enumerate(((True, False), (True, False), (False, True))):
+        upd = ctx.single_stokes_fs(updateJ=uj, upOnly=uo, extraParams={'J20': Ja})
+        dJ = max(oraclelib.OracleContext(q, col=c).full_stokes(updateJ=uj, upOnly=uo, J20=Jb)[0] for c in range(q.Ncol))
+        assert rel_err(p.I, q.I) <= TOL
+        assert np.abs(p.Quv - q.Quv).max() <= TOL * scale
+        assert np.abs(Ja - Jb).max() <= TOL * np.abs(Jb).max() and np.abs(Jb).max() > 0.0
+        if uj:
+            assert rel_err(p.J, q.J) <= TOL and abs(upd.dJMax - dJ) <= TOL * max(dJ, 1.0)
+        if n == 1:
+            assert np.abs(p.Quv[:, 0][:, ~m]).max() > 0.0   # polarised by the anisotropy alone
+    # without the option again: unpolarised wavelengths take the scalar solver, Quv = 0 there
+    ctx.single_stokes_fs(updateJ=False, upOnly=True)
+    for c in range(q.Ncol):
+        oraclelib.OracleContext(q, col=c).full_stokes(updateJ=False, upOnly=True)
+    assert rel_err(p.I, q.I) <= TOL and np.all(p.Quv[:, :, ~m] == 0.0)
+    ctx.close()
+
+
 @pytest.mark.parametrize('timeDep,useDC', [(False, False), (True, True)])
 def test_nr_post_update_matches_oracle(timeDep, useDC):
     """Newton-Raphson step with charge conservation (nr_post_update_impl): two atoms coupled through

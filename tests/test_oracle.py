@@ -250,6 +250,40 @@ def test_product_hprd_tables_match_the_restatement(includeDetailed):
     assert np.array_equal(c1.JCoeffFrac, oraclelib.configure_hprd(one, includeDetailed).JCoeffFrac)
 
 
+@pytest.mark.ref
+def test_oracle_stokes_j20_vs_reference_live():
+    """The 'J20' extra parameter of the full-Stokes formal solution (FormalStokes.cpp:433-437, :469-471, :575-583,
+    :642-648): two J-updating passes (the second one scatters the anisotropy the first one built into the I and Q
+    emissivities of EVERY wavelength) and a pass that does not update J, restatement against the compiled reference."""
+    p = synth.tiny_stokes_problem(perturb=True)
+    q = p.clone()
+    r, o = reflib.RefContext(p), oraclelib.OracleContext(q)
+    for it in range(2):
+        p.prefill_gamma()
+        q.prefill_gamma()
+        r.fs_iter()
+        o.fs_iter()
+        r.stat_eq()
+        o.stat_eq()
+    pol = np.zeros(p.Nspect, dtype=bool)
+    for a_ in p.atoms:
+        for t in a_.trans:
+            if t.polProfiles is not None:
+                pol[t.Nblue:t.Nred] = True
+    Ja, Jb = np.zeros((1, p.Nspect, p.Nspace)), np.zeros((1, p.Nspect, p.Nspace))
+    for n, (updateJ, upOnly) in enumerate(((True, False), (True, False), (False, True))):
+        a = r.full_stokes(updateJ=updateJ, upOnly=upOnly, J20=Ja[0])
+        b = o.full_stokes(updateJ=updateJ, upOnly=upOnly, J20=Jb)
+        assert a[0] == b[0]
+        assert np.array_equal(Ja, Jb) and np.abs(Ja).max() > 0.0
+        assert np.array_equal(p.I, q.I) and np.array_equal(p.J, q.J)
+        assert np.array_equal(p.Quv, q.Quv) and (np.abs(p.Quv) > 0).any()
+        if n == 1:
+            # the anisotropy of the first pass polarises wavelengths no polarised line touches
+            assert np.abs(p.Quv[0, 0][~pol]).max() > 0.0
+    r.close()
+
+
 HPRD_TABLES = ('prdLaOfLa', 'hPrdLaOfLa', 'JCoeffOff', 'JCoeffIdx', 'JCoeffFrac', 'lineAtom', 'lineTrans',
                'rhoCoefOff', 'rhoFrac', 'rhoI0')
 

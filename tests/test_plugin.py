@@ -218,6 +218,14 @@ def test_reference_core_full_stokes_through_the_b200_scheme():
         assert np.abs(p.Quv[:, :, m] - q.Quv[:, :, m]).max() <= 1e-9 * np.abs(q.I).max()
         if uj:
             assert rel_err(p.J, q.J) <= 1e-9 and abs(a[0] - b[0]) <= 1e-9 * max(b[0], 1.0)
+    # the "J20" extra parameter (FormalStokes.cpp:676-681) travels through ExtraParams to the device
+    Ja, Jb = np.zeros((p.Nspect, p.Nspace)), np.zeros((p.Nspect, p.Nspace))
+    for uj, uo in ((True, False), (True, False), (False, True)):
+        gpu.full_stokes(updateJ=uj, upOnly=uo, J20=Ja)
+        cpu.full_stokes(updateJ=uj, upOnly=uo, J20=Jb)
+        assert rel_err(p.I, q.I) <= 1e-9 and rel_err(p.J, q.J) <= 1e-9
+        assert np.abs(p.Quv - q.Quv).max() <= 1e-9 * np.abs(q.I).max()
+        assert np.abs(Ja - Jb).max() <= 1e-9 * np.abs(Jb).max() and np.abs(Jb).max() > 0.0
     gpu.close()
     cpu.close()
 
