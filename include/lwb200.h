@@ -52,7 +52,8 @@ typedef struct LwB200Transition {
     int32_t type;          /* LWB200_LINE / LWB200_CONTINUUM */
     int32_t i, j;          /* lower / upper level */
     int32_t Nblue, Nred;   /* active on the global grid for la in [Nblue, Nred) */
-    int32_t reserved;
+    int32_t polarised;     /* != 0: a polarised line whose six extra profiles are only ever made on the device
+                              (lwb200_compute_polarised_profiles), so polProfiles may be NULL */
     double Aji, Bji, Bij;  /* lines */
     double lambda0;
     double dopplerWidth;   /* c/lambda0 for lines, 1 for continua (LwMiddleLayer.pyx:1799,1815) */
@@ -182,6 +183,7 @@ enum {
     LWB200_ZPLANE  = 1u << 15, /* down only: the ZPlaneUp / ZPlaneDown arrays registered with lwb200_set_zplane */
     LWB200_COLLISIONS = 1u << 16, /* up only: C of every active atom, kept on the device so that the prefill
                                    * crsw*C is made there (lwb200_set_collision_prefill) */
+    LWB200_POLPROF = 1u << 17,    /* down only: the six polarised profiles of every polarised line with a host array */
     LWB200_ALL_INPUTS  = 0x7fu,
     LWB200_ITER_INPUTS = LWB200_POPS | LWB200_NSTAR | LWB200_GAMMA,
     LWB200_ITER_OUTPUTS = LWB200_GAMMA | LWB200_JBAR | LWB200_INTENS | LWB200_RATES
@@ -278,6 +280,27 @@ int lwb200_compute_profiles(LwB200Context* ctx);
  * J, Gamma (onto the uploaded prefill) and Rij/Rji, finalises Gamma.
  * dJMax / dJMaxIdx may be NULL (no device->host sync is then forced). */
 int lwb200_fs_iter(LwB200Context* ctx, uint32_t flags, double* dJMax, int64_t* dJMaxIdx);
+/* The Zeeman components of one polarised line (ZeemanComponents, Source/LwMisc.hpp:106-111). */
+typedef struct LwB200Zeeman {
+    int32_t atom;          /* index into problem->atoms */
+    int32_t trans;         /* index into that atom's trans */
+    int32_t Ncomponent;
+    int32_t reserved;
+    const int32_t* alpha;  /* [Ncomponent] -1 (sigma blue), 0 (pi), +1 (sigma red) */
+    const double* shift;   /* [Ncomponent] in Larmor units */
+    const double* strength;/* [Ncomponent] */
+} LwB200Zeeman;
+
+/* Replaces Transition::compute_polarised_profiles (Source/FormalStokes.cpp:9-117) on the device for the listed
+ * lines: phi, wphi and phiQ, phiU, phiV, psiQ, psiU, psiV from aDamp, vBroad and vlosMu already uploaded, the
+ * magnetic field strength B [Ncol][Nspace] (Tesla) and the projections cosGamma, cos2chi, sin2chi
+ * [Ncol][Nrays][Nspace] of Atmosphere::update_projections.  The Voigt and Faraday-Voigt functions are the real and
+ * imaginary parts of w(v + i a), evaluated as in lwb200_compute_profiles.  The lines must have been declared
+ * polarised at lwb200_create (polProfiles or the `polarised` flag).  Download group LWB200_POLPROF brings the
+ * six profiles home into polProfiles where that is not NULL. */
+int lwb200_compute_polarised_profiles(LwB200Context* ctx, const LwB200Zeeman* lines, int32_t nLines, const double* B,
+                                      const double* cosGamma, const double* cos2chi, const double* sin2chi);
+
 /* The "J20" extra parameter of formal_sol_full_stokes (Source/FormalStokes.cpp:676-681): J20 is the caller's
  * [Ncol][Nspect][Nspace] radiation-field anisotropy, or NULL to switch the option off again.  While it is set,
  * lwb200_formal_sol_full_stokes sends every wavelength through the Stokes solver, adds the scattering of the

@@ -19,7 +19,7 @@ FS_NAMES = {'piecewise_linear_1d': FS_LINEAR, 'piecewise_besser_1d': FS_BESSER,
             'piecewise_bezier3_1d': FS_BEZIER3}
 
 (ATMOS, BACKGR, POPS, NSTAR, GAMMA, JBAR, PROFILE, INTENS, RATES, DEPTH, ADAMP,
- GAMMA_FINAL, PRD, STOKES, OWN_ROWS, ZPLANE, COLLISIONS) = (1 << i for i in range(17))
+ GAMMA_FINAL, PRD, STOKES, OWN_ROWS, ZPLANE, COLLISIONS, POLPROF) = (1 << i for i in range(18))
 ALL_INPUTS = 0x7f
 ITER_INPUTS = POPS | NSTAR | GAMMA
 ITER_OUTPUTS = GAMMA | JBAR | INTENS | RATES
@@ -35,7 +35,7 @@ _ip = C.POINTER(C.c_int32)
 class LwB200Transition(C.Structure):
     _fields_ = [
         ('type', C.c_int32), ('i', C.c_int32), ('j', C.c_int32),
-        ('Nblue', C.c_int32), ('Nred', C.c_int32), ('reserved', C.c_int32),
+        ('Nblue', C.c_int32), ('Nred', C.c_int32), ('polarised', C.c_int32),
         ('Aji', C.c_double), ('Bji', C.c_double), ('Bij', C.c_double),
         ('lambda0', C.c_double), ('dopplerWidth', C.c_double),
         ('wavelength', _dp), ('alpha', _dp), ('phi', _dp), ('wphi', _dp),
@@ -63,6 +63,13 @@ class LwB200HybridPrd(C.Structure):
         ('prdLaOfLa', _ip), ('hPrdLaOfLa', _ip), ('JRest', _dp),
         ('JCoeffOff', _lp), ('JCoeffIdx', _ip), ('JCoeffFrac', _dp),
         ('lineAtom', _ip), ('lineTrans', _ip), ('rhoCoefOff', _lp), ('rhoFrac', _dp), ('rhoI0', _ip),
+    ]
+
+
+class LwB200Zeeman(C.Structure):
+    _fields_ = [
+        ('atom', C.c_int32), ('trans', C.c_int32), ('Ncomponent', C.c_int32), ('reserved', C.c_int32),
+        ('alpha', _ip), ('shift', _dp), ('strength', _dp),
     ]
 
 
@@ -175,6 +182,7 @@ def load():
     lib.lwb200_finalise.argtypes = [vp]
     lib.lwb200_set_collision_prefill.argtypes = [vp, C.c_int, C.c_double]
     lib.lwb200_set_j20.argtypes = [vp, _dp]
+    lib.lwb200_compute_polarised_profiles.argtypes = [vp, C.POINTER(LwB200Zeeman), C.c_int32, _dp, _dp, _dp, _dp]
     lib.lwb200_set_hybrid_prd.argtypes = [vp, C.POINTER(LwB200HybridPrd)]
     lib.lwb200_configure_hprd.argtypes = [C.POINTER(LwB200Problem), C.c_int, C.POINTER(LwB200HybridPrd)]
     lib.lwb200_free_hprd.argtypes = [C.POINTER(LwB200HybridPrd)]
@@ -201,7 +209,7 @@ def load():
                                       C.POINTER(C.c_int64)]
     for name in ('device_count', 'create', 'destroy', 'set_stream', 'set_lambda_range', 'upload',
                  'download', 'sync', 'compute_profiles', 'fs_iter', 'finalise', 'dj_max',
-                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes', 'nr_post_update', 'stat_eq_async', 'last_singular', 'last_dj', 'set_zplane', 'population_solve', 'set_collision_prefill', 'set_hybrid_prd', 'configure_hprd', 'set_j20'):
+                 'formal_sol', 'stat_eq', 'device_buffer', 'work_stats', 'kernel_time', 'redistribute_prd', 'time_dep_update', 'formal_sol_full_stokes', 'nr_post_update', 'stat_eq_async', 'last_singular', 'last_dj', 'set_zplane', 'population_solve', 'set_collision_prefill', 'set_hybrid_prd', 'configure_hprd', 'set_j20', 'compute_polarised_profiles'):
         getattr(lib, 'lwb200_' + name).restype = C.c_int
     if lib.lwb200_abi_version() != ABI_VERSION:
         raise LwB200Error('liblwb200.so ABI version mismatch; rebuild')
@@ -224,5 +232,5 @@ EXPORTED_SYMBOLS = [
     'lwb200_time_dep_update', 'lwb200_formal_sol_full_stokes',
     'lwb200_nr_post_update', 'lwb200_stat_eq_async', 'lwb200_last_singular', 'lwb200_last_dj',
     'lwb200_set_zplane', 'lwb200_population_solve', 'lwb200_global_launch_count',
-    'lwb200_set_collision_prefill', 'lwb200_set_j20', 'lwb200_set_hybrid_prd', 'lwb200_configure_hprd', 'lwb200_free_hprd',
+    'lwb200_set_collision_prefill', 'lwb200_set_j20', 'lwb200_compute_polarised_profiles', 'lwb200_set_hybrid_prd', 'lwb200_configure_hprd', 'lwb200_free_hprd',
 ]

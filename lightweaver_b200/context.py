@@ -235,6 +235,30 @@ class Context:
     def compute_profiles_device(self):
         capi.check(self.lib.lwb200_compute_profiles(self._h))
 
+    def compute_polarised_profiles_device(self):
+        """Transition::compute_polarised_profiles (what lw.Context.setup_stokes / update_deps(B=True) run per
+        polarised line, FormalStokes.cpp:9-117) on the device: phi, wphi and the six polarised profiles of every
+        line with a Zeeman pattern, from the problem's B, cosGamma, cos2chi, sin2chi."""
+        p = self.problem
+        if p.B is None or p.cosGamma is None or p.cos2chi is None or p.sin2chi is None:
+            raise capi.LwB200Error('compute_polarised_profiles: the problem has no magnetic field / projections')
+        lines = [(ia, it, t) for ia, a in enumerate(p.atoms) for it, t in enumerate(a.trans) if t.zeeman is not None]
+        if not lines:
+            return
+        arr = (capi.LwB200Zeeman * len(lines))()
+        keep = []
+        for z, (ia, it, t) in zip(arr, lines):
+            al, sh, st = (np.ascontiguousarray(t.zeeman[0], dtype=np.int32),
+                          np.ascontiguousarray(t.zeeman[1], dtype=np.float64),
+                          np.ascontiguousarray(t.zeeman[2], dtype=np.float64))
+            keep += [al, sh, st]
+            z.atom, z.trans, z.Ncomponent = ia, it, len(al)
+            z.alpha, z.shift, z.strength = capi.iptr(al), capi.dptr(sh), capi.dptr(st)
+        capi.check(self.lib.lwb200_compute_polarised_profiles(self._h, arr, len(lines), capi.dptr(p.B),
+                                                              capi.dptr(p.cosGamma), capi.dptr(p.cos2chi),
+                                                              capi.dptr(p.sin2chi)))
+        self._stokes_sent = True
+
     # ------------------------------------------- the reference's call surface
     def formal_sol_gamma_matrices(self, fixCollisionalRates=True, lambdaIterate=False,
                                   extraParams=None, crsw=None):

@@ -613,7 +613,7 @@ int build_plan(LwB200Context* c)
     // polarised lines: six extra profile arrays each, [6][Ncol][Nl][M][2][K] as on the host
     c->transPolOff.assign(NT, -1);
     for (int g = 0; g < NT; ++g)
-        if (c->devTrans[g].type == 0 && c->trans[g].t.polProfiles)
+        if (c->devTrans[g].type == 0 && (c->trans[g].t.polProfiles || c->trans[g].t.polarised))
         {
             c->transPolOff[g] = c->polTot;
             c->polTot += 6LL * c->devTrans[g].phiColStride * p.Ncol;
@@ -2353,8 +2353,13 @@ int lwb200_upload(LwB200Context* c, uint32_t mask)
     {
         for (size_t g = 0; g < c->trans.size(); ++g)
             if (c->transPolOff[g] >= 0)
+            {
+                if (!c->trans[g].t.polProfiles)
+                    return fail("LWB200_STOKES upload of a polarised line without host profiles "
+                                "(use lwb200_compute_polarised_profiles)");
                 CU(cudaMemcpyAsync(c->pol.p + c->transPolOff[g], c->trans[g].t.polProfiles,
                                    (size_t)6 * c->devTrans[g].phiColStride * ncol * D, H2D, s));
+            }
         c->stokesUploaded = true;
     }
     if ((mask & LWB200_PRD) && !c->prdLines.empty())
@@ -2406,6 +2411,11 @@ int lwb200_download(LwB200Context* c, uint32_t mask)
     }
     if ((mask & LWB200_STOKES) && c->polTot > 0)
         CU(cudaMemcpyAsync(p.Quv, c->Quv.p, ncol * 3 * L * M * D, D2H, s));
+    if ((mask & LWB200_POLPROF) && c->polTot > 0)
+        for (size_t g = 0; g < c->trans.size(); ++g)
+            if (c->transPolOff[g] >= 0 && c->trans[g].t.polProfiles)
+                CU(cudaMemcpyAsync(const_cast<double*>(c->trans[g].t.polProfiles), c->pol.p + c->transPolOff[g],
+                                   (size_t)6 * c->devTrans[g].phiColStride * ncol * D, D2H, s));
     if (mask & LWB200_PRD)
     {
         for (const DevPrdLine& ln : c->prdLines)
@@ -2552,6 +2562,89 @@ int lwb200_compute_profiles(LwB200Context* c)
     c->lastLaunches += nLaunched;
     if (rc)
         return fail(std::string("lwb200_compute_profiles: ") + cudaGetErrorString((cudaError_t)rc));
+    return check_phi_symmetry(c);
+}
+
+int lwb200_compute_polarised_profiles(LwB200Context* c, const LwB200Zeeman* zl, int32_t nLines, const double* B,
+                                      const double* cosGamma, const double* cos2chi, const double* sin2chi)
+{
+    CU(cudaSetDevice(c->device));
+    if (!zl || nLines < 1 || !B || !cosGamma || !cos2chi || !sin2chi)
+        return fail("lwb200_compute_polarised_profiles: null argument");
+    if (!c->vlosMu.p)
+        return fail("lwb200_compute_polarised_profiles: the problem has no vlosMu");
+    const LwB200Problem& p = c->prob;
+    const size_t K = p.Nspace, M = p.Nrays, ncol = p.Ncol;
+    cudaStream_t s = c->stream;
+    std::vector<int> alpha;
+    std::vector<double> shift, strength;
+    std::vector<DevZeeman> dz;
+    for (int q = 0; q < nLines; ++q)
+    {
+        int g = -1;
+        for (size_t t = 0; t < c->trans.size(); ++t)
+            if (c->trans[t].atom == zl[q].atom && c->trans[t].kr == zl[q].trans)
+                g = (int)t;
+        if (g < 0 || c->devTrans[g].type != 0 || c->transPolOff[g] < 0)
+            return fail("lwb200_compute_polarised_profiles: not a line declared polarised at lwb200_create");
+        if (zl[q].Ncomponent < 1 || !zl[q].alpha || !zl[q].shift || !zl[q].strength)
+            return fail("lwb200_compute_polarised_profiles: empty Zeeman pattern");
+        DevZeeman z{};
+        z.line = -1;
+        for (size_t l = 0; l < c->devLines.size(); ++l)
+            if (c->devLines[l].lineIdx == c->devTrans[g].lineIdx)
+                z.line = (int)l;
+        z.nComp = zl[q].Ncomponent;
+        z.compOff = (int)alpha.size();
+        z.polOff = c->transPolOff[g];
+        z.polArr = c->devTrans[g].phiColStride * (long long)ncol;
+        alpha.insert(alpha.end(), zl[q].alpha, zl[q].alpha + z.nComp);
+        shift.insert(shift.end(), zl[q].shift, zl[q].shift + z.nComp);
+        strength.insert(strength.end(), zl[q].strength, zl[q].strength + z.nComp);
+        dz.push_back(z);
+    }
+    DevBuf<int> dAlpha;
+    DevBuf<double> dShift, dStrength, dB, dAng;
+    auto cleanup = [&]() {
+        dAlpha.release(); dShift.release(); dStrength.release(); dB.release(); dAng.release();
+    };
+    if (dAlpha.upload(alpha) || dShift.upload(shift) || dStrength.upload(strength) || dB.alloc(ncol * K)
+        || dAng.alloc(3 * ncol * M * K))
+    {
+        cleanup();
+        return 1;
+    }
+    const size_t na = ncol * M * K;
+    cudaError_t e = cudaMemcpyAsync(dB.p, B, ncol * K * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dAng.p, cosGamma, na * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dAng.p + na, cos2chi, na * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dAng.p + 2 * na, sin2chi, na * sizeof(double), cudaMemcpyHostToDevice, s);
+    c->lastLaunches = 0;
+    for (size_t q = 0; q < dz.size() && e == cudaSuccess; ++q)
+    {
+        const size_t total = (size_t)c->devLines[dz[q].line].Nl * M * 2 * K * ncol;
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((total + 127) / 128, 148 * 64));
+        pol_profile_kernel<<<grid, 128, 0, s>>>(c->P, c->dLines.p, dz[q], dAlpha.p, dShift.p, dStrength.p, c->transWave.p,
+                                                c->aDamp.p, c->vBroad.p, c->vlosMu.p, dB.p, dAng.p, dAng.p + na,
+                                                dAng.p + 2 * na, c->phi.p, c->pol.p);
+        e = cudaGetLastError();
+        c->lastLaunches += 1;
+    }
+    if (e == cudaSuccess)
+    {
+        // wphi of every line from the profiles now on the device (compute_wphi order, FormalScalar.cpp:106-134)
+        const size_t total = c->devLines.size() * ncol * K;
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((total + 127) / 128, 148 * 32));
+        wphi_kernel<<<grid, 128, 0, s>>>(c->P, c->dLines.p, (int)c->devLines.size(), c->wlambdaTab.p, c->phi.p, c->wphi.p);
+        e = cudaGetLastError();
+        c->lastLaunches += 1;
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(s); // (the temporaries go away below)
+    cleanup();
+    if (e != cudaSuccess)
+        return fail(std::string("lwb200_compute_polarised_profiles: ") + cudaGetErrorString(e));
+    c->stokesUploaded = true;
     return check_phi_symmetry(c);
 }
 

@@ -42,6 +42,8 @@ class TransitionData:
     aDamp: Optional[np.ndarray] = None     # [Ncol, Nspace]
     Qelast: Optional[np.ndarray] = None    # [Ncol, Nspace] PRD lines
     polProfiles: Optional[np.ndarray] = None  # [6, Ncol, Nlambda, Nrays, 2, Nspace] phiQ,U,V psiQ,U,V
+    polarised: bool = False                # polarised line whose profiles may live on the device only
+    zeeman: Optional[tuple] = None         # (alpha int32 [N], shift [N], strength [N]): ZeemanComponents
     Rij: Optional[np.ndarray] = None       # [Ncol, Nspace]
     Rji: Optional[np.ndarray] = None
     name: str = ''
@@ -187,6 +189,10 @@ class Problem:
     vturb: Optional[np.ndarray] = None
     nHTot: Optional[np.ndarray] = None
     hprd: Optional[HybridPrd] = None     # hybrid-PRD tables (None: every PRD line is angle-averaged)
+    B: Optional[np.ndarray] = None       # [Ncol, Nspace] magnetic field strength (atmos.B), Tesla
+    cosGamma: Optional[np.ndarray] = None  # [Ncol, Nrays, Nspace] projections of Atmosphere::update_projections
+    cos2chi: Optional[np.ndarray] = None
+    sin2chi: Optional[np.ndarray] = None
     meta: dict = field(default_factory=dict)
     _keepalive: list = field(default_factory=list, repr=False)
 
@@ -260,6 +266,7 @@ class Problem:
                                     rhoPrd=sl(t.rhoPrd), aDamp=sl(t.aDamp), Qelast=sl(t.Qelast),
                                     polProfiles=(None if t.polProfiles is None
                                                  else np.ascontiguousarray(t.polProfiles[:, c:c + 1])),
+                                    polarised=t.polarised, zeeman=t.zeeman,
                                     Rij=sl(t.Rij),
                                     Rji=sl(t.Rji), name=t.name) for t in a.trans]
             atoms.append(AtomData(name=a.name, Nlevel=a.Nlevel, trans=trans, n=sl(a.n),
@@ -275,7 +282,8 @@ class Problem:
                        upperBcIdx=self.upperBcIdx, depthChi=sl(self.depthChi),
                        depthEta=sl(self.depthEta), depthI=sl(self.depthI), Quv=sl(self.Quv), ne=sl(self.ne),
                        vturb=sl(self.vturb), nHTot=sl(self.nHTot), meta=dict(self.meta),
-                       hprd=None if self.hprd is None else self.hprd.column(c, self))
+                       hprd=None if self.hprd is None else self.hprd.column(c, self),
+                       B=sl(self.B), cosGamma=sl(self.cosGamma), cos2chi=sl(self.cos2chi), sin2chi=sl(self.sin2chi))
 
     # ------------------------------------------------------------ marshalling
     def c_struct(self):
@@ -316,6 +324,7 @@ class Problem:
                 ct.Rij, ct.Rji = d(t.Rij), d(t.Rji)
                 ct.Qelast = d(t.Qelast)
                 ct.polProfiles = d(t.polProfiles)
+                ct.polarised = int(t.polarised or t.polProfiles is not None)
             keep.append(trans)
             ca.trans = C.cast(trans, C.POINTER(capi.LwB200Transition))
             ca.n, ca.nStar, ca.nTotal = d(a.n), d(a.nStar), d(a.nTotal)

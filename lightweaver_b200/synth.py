@@ -466,6 +466,8 @@ def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, se
                 assert with_profiles, 'polarised profiles are made on the host'
                 t.phi, t.polProfiles = polarised_profiles(t.wavelength, t.lambda0, t.aDamp, vBroad, vlosMu,
                                                           Bfield, cosGamma, cos2chi, sin2chi, gEff=1.1)
+                t.polarised = True   # (a normal Zeeman triplet)
+                t.zeeman = (np.array([-1, 0, 1], dtype=np.int32), np.array([-1.1, 0.0, 1.1]), np.ones(3))
                 wlam = t.wlambda()
                 s = np.einsum('clmdk,l,m->ck', t.phi, wlam, 0.5 * wmu)
                 t.wphi = np.ascontiguousarray(1.0 / s)
@@ -491,6 +493,8 @@ def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, se
                    vturb=np.ascontiguousarray(vturb), nHTot=np.ascontiguousarray(nHTot))
     if polarised:
         prob.Quv = np.zeros((ncol, 3, L, nrays))
+        prob.B = np.ascontiguousarray(Bfield)
+        prob.cosGamma, prob.cos2chi, prob.sin2chi = cosGamma, cos2chi, sin2chi
     prob.meta = {'atoms': [a.name for a in atoms], 'perturb': perturb, 'seed': seed}
     prob.prefill_gamma()
     return prob

@@ -632,6 +632,44 @@ int lwref_compute_profiles(LwRefHandle* hh)
     }
 }
 
+// Transition::compute_polarised_profiles (FormalStokes.cpp:9-117) of one polarised line of this column, by the
+// reference itself: B [Nspace], cosGamma / cos2chi / sin2chi [Nrays][Nspace], the Zeeman pattern.  Writes the
+// line's phi, wphi and its six polarised profiles (the problem's host arrays).
+int lwref_compute_polarised_profiles(LwRefHandle* hh, int atomIdx, int transIdx, const double* B, const double* cosGamma,
+                                     const double* cos2chi, const double* sin2chi, int nComp, const int32_t* alpha,
+                                     const double* shift, const double* strength)
+{
+    auto* h = (LwRef*)hh;
+    try
+    {
+        const i64 K = h->prob->Nspace, M = h->prob->Nrays;
+        if (atomIdx < 0 || atomIdx >= (int)h->atoms.size())
+            throw std::runtime_error("atom index out of range");
+        Atom& a = h->atoms[atomIdx];
+        if (transIdx < 0 || transIdx >= (int)a.trans.size())
+            throw std::runtime_error("transition index out of range");
+        Transition* t = a.trans[transIdx];
+        if (!t->polarised || !t->aDamp || !a.vBroad || !h->atmos.vlosMu)
+            throw std::runtime_error("compute_polarised_profiles needs a polarised line with aDamp, vBroad and vlosMu");
+        Atmosphere atm = h->atmos;
+        atm.B = F64View(const_cast<f64*>(B), K);
+        atm.cosGamma = F64View2D(const_cast<f64*>(cosGamma), M, K);
+        atm.cos2chi = F64View2D(const_cast<f64*>(cos2chi), M, K);
+        atm.sin2chi = F64View2D(const_cast<f64*>(sin2chi), M, K);
+        ZeemanComponents z;
+        z.alpha = I32View(const_cast<i32*>(alpha), nComp);
+        z.shift = F64View(const_cast<f64*>(shift), nComp);
+        z.strength = F64View(const_cast<f64*>(strength), nComp);
+        t->compute_polarised_profiles(atm, t->aDamp, a.vBroad, z);
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+}
+
 // Timing protocol of lightweaver/benchmark.py:84-89 / BASELINE.md section 3:
 // nWarm + nTimed calls, Gamma re-filled from its value at entry before each
 // call, steady_clock around the C++ call only.  seconds[] receives nTimed

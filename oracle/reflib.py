@@ -71,6 +71,7 @@ def load():
     lib.lwref_hprd_export.argtypes = [vp, C.c_int, i64p, i32p, i32p, i64p, i32p, dp, dp, i32p]
     lib.lwref_get_jrest.argtypes = [vp, dp]
     lib.lwref_compute_profiles.argtypes = [vp]
+    lib.lwref_compute_polarised_profiles.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, C.c_int, i32p, dp, dp]
     lib.lwref_time_fs_iter.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
     lib.lwref_solve_ray.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_int,
                                     C.c_double, C.c_int, C.c_int, dp, dp]
@@ -204,6 +205,23 @@ class RefContext:
 
     def compute_profiles(self):
         _check(self.lib.lwref_compute_profiles(self.h))
+
+    def compute_polarised_profiles(self, col=0):
+        """The reference's Transition::compute_polarised_profiles for every line of the problem with a Zeeman
+        pattern, on column ``col`` (the one this context was made for): rewrites phi, wphi, polProfiles."""
+        import numpy as np
+        p = self.problem
+        dp, i32p = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        for ia, a in enumerate(p.atoms):
+            for it, t in enumerate(a.trans):
+                if t.zeeman is None:
+                    continue
+                al, sh, st = (np.ascontiguousarray(t.zeeman[0], dtype=np.int32), np.ascontiguousarray(t.zeeman[1]),
+                              np.ascontiguousarray(t.zeeman[2]))
+                arrs = [np.ascontiguousarray(x[col]) for x in (p.B, p.cosGamma, p.cos2chi, p.sin2chi)]
+                _check(self.lib.lwref_compute_polarised_profiles(
+                    self.h, ia, it, *[x.ctypes.data_as(dp) for x in arrs], len(al), al.ctypes.data_as(i32p),
+                    sh.ctypes.data_as(dp), st.ctypes.data_as(dp)))
 
     def set_depth_fill(self, fill):
         _check(self.lib.lwref_set_depth_fill(self.h, int(fill)))

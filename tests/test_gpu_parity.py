@@ -417,6 +417,54 @@ def test_cuda_stokes_vs_oracle_columns(ndepth):
     ctx.close()
 
 
+def test_device_polarised_profiles_match_host_and_feed_the_stokes_solver():
+    """lwb200_compute_polarised_profiles (Transition::compute_polarised_profiles, FormalStokes.cpp:9-117) on a
+    perturbed magnetised two-column stack: the Voigt AND Faraday-Voigt functions on the device against the host
+    profiles (Faddeeva w(z); themselves checked against the reference's routine in tests/test_oracle.py), then a
+    context whose polarised lines carry NO host profiles at all runs the full-Stokes formal solution on the
+    device-made ones."""
+    p = synth.tiny_stokes_problem(ncol=2, perturb=True)
+    q = p.clone()
+    host = [(t.phi.copy(), t.wphi.copy(), t.polProfiles.copy()) for a in p.atoms for t in a.trans if t.zeeman is not None]
+    for a in p.atoms:
+        for t in a.trans:
+            if t.zeeman is not None:
+                t.phi[...] = 0.0
+                t.wphi[...] = 0.0
+                t.polProfiles[...] = 0.0
+    ctx = Context(p)
+    ctx.compute_polarised_profiles_device()
+    ctx.download(capi.PROFILE | capi.POLPROF)
+    dev = [(t.phi, t.wphi, t.polProfiles) for a in p.atoms for t in a.trans if t.zeeman is not None]
+    for (phi0, wphi0, pol0), (phi1, wphi1, pol1) in zip(host, dev):
+        scale = np.abs(phi0).max()
+        assert np.abs(phi1 - phi0).max() <= 1e-12 * scale
+        assert np.abs(pol1 - pol0).max() <= 1e-12 * scale
+        assert rel_err(wphi1, wphi0) <= 1e-11
+    ctx.close()
+    # no host profiles at all: the lines are only flagged polarised
+    r = q.clone()
+    for a in r.atoms:
+        for t in a.trans:
+            if t.zeeman is not None:
+                t.polProfiles = None
+                t.polarised = True
+    ctx = Context(r)
+    ctx.compute_polarised_profiles_device()
+    ctx.formal_sol_gamma_matrices()
+    oracle_iter(q, stat_eq=False)
+    assert_close(r, q)
+    for uj, uo in ((False, True), (True, False)):
+        ctx.single_stokes_fs(updateJ=uj, upOnly=uo)
+        for c in range(q.Ncol):
+            oraclelib.OracleContext(q, col=c).full_stokes(updateJ=uj, upOnly=uo)
+        from tests.golden.make_golden import polarised_mask
+        m = polarised_mask(q)
+        assert rel_err(r.I, q.I) <= TOL
+        assert np.abs(r.Quv[:, :, m] - q.Quv[:, :, m]).max() <= TOL * np.abs(q.I).max()
+    ctx.close()
+
+
 def test_cuda_stokes_j20_vs_oracle_columns():
     """The 'J20' extra parameter of the full-Stokes formal solution (FormalStokes.cpp:676-681) on a perturbed
     magnetised two-column stack: two J-updating passes (the second scatters the anisotropy the first one built

@@ -251,6 +251,31 @@ def test_product_hprd_tables_match_the_restatement(includeDetailed):
 
 
 @pytest.mark.ref
+def test_polarised_profile_generator_vs_reference():
+    """The host formula the GPU tests check device-made polarised profiles against (synth.polarised_profiles:
+    scipy's Faddeeva w(z), a normal Zeeman triplet) is the reference's own Transition::compute_polarised_profiles
+    (FormalStokes.cpp:9-117, its vendored Faddeeva package) to rounding: phi, wphi and the six extra profiles."""
+    p = synth.tiny_stokes_problem(perturb=True)
+    want = [(t.phi.copy(), t.wphi.copy(), t.polProfiles.copy()) for a in p.atoms for t in a.trans if t.zeeman is not None]
+    assert want
+    for a in p.atoms:
+        for t in a.trans:
+            if t.zeeman is not None:
+                t.phi[...] = 0.0
+                t.wphi[...] = 0.0
+                t.polProfiles[...] = 0.0
+    r = reflib.RefContext(p)
+    r.compute_polarised_profiles()
+    got = [(t.phi, t.wphi, t.polProfiles) for a in p.atoms for t in a.trans if t.zeeman is not None]
+    for (phi0, wphi0, pol0), (phi1, wphi1, pol1) in zip(want, got):
+        scale = np.abs(phi0).max()
+        assert np.abs(phi1 - phi0).max() <= 1e-13 * scale
+        assert np.abs(pol1 - pol0).max() <= 1e-13 * scale and np.abs(pol0[3:]).max() > 1e-3 * scale
+        assert rel_err(wphi1, wphi0) <= 1e-12
+    r.close()
+
+
+@pytest.mark.ref
 def test_oracle_stokes_j20_vs_reference_live():
     """The 'J20' extra parameter of the full-Stokes formal solution (FormalStokes.cpp:433-437, :469-471, :575-583,
     :642-648): two J-updating passes (the second one scatters the anisotropy the first one built into the I and Q
