@@ -2073,12 +2073,14 @@ int lwb200_ng_accelerate(LwB200Context* c, int32_t* accelerated, double* dMax, i
         CU(cudaGetLastError());
         c->lastLaunches += 1;
     }
-    for (int a = 0; a < Natom; ++a)
+    if (c->ngCount < 2)
     {
-        c->ngHostMax[a] = 0.0;
-        c->ngHostIdx[a] = 0;
+        // nothing to compare yet: zeros, written by the stream like every other result (the pinned host words may
+        // still be the target of the previous call's copy, so the host does not touch them)
+        CU(cudaMemsetAsync(c->ngMax.p, 0, c->ngMax.n * sizeof(double), c->stream));
+        CU(cudaMemsetAsync(c->ngIdx.p, 0, c->ngIdx.n * sizeof(long long), c->stream));
     }
-    if (c->ngCount >= 2)
+    else
     {
         // max_change(): the last two stored solutions (Ng.hpp:138-156)
         const size_t perAtom = (size_t)c->prob.Ncol * c->P.maxNlevel * c->P.K;
@@ -2090,11 +2092,11 @@ int lwb200_ng_accelerate(LwB200Context* c, int32_t* accelerated, double* dMax, i
         ng_max_change_final_kernel<<<Natom, kNgParts, 0, c->stream>>>(nParts, c->ngMax.p, c->ngIdx.p);
         CU(cudaGetLastError());
         c->lastLaunches += 2;
-        CU(cudaMemcpy2DAsync(c->ngHostMax, sizeof(double), c->ngMax.p, (kNgParts + 1) * sizeof(double), sizeof(double),
-                             Natom, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpy2DAsync(c->ngHostIdx, sizeof(long long), c->ngIdx.p, (kNgParts + 1) * sizeof(long long),
-                             sizeof(long long), Natom, cudaMemcpyDeviceToHost, c->stream));
     }
+    CU(cudaMemcpy2DAsync(c->ngHostMax, sizeof(double), c->ngMax.p, (kNgParts + 1) * sizeof(double), sizeof(double),
+                         Natom, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpy2DAsync(c->ngHostIdx, sizeof(long long), c->ngIdx.p, (kNgParts + 1) * sizeof(long long),
+                         sizeof(long long), Natom, cudaMemcpyDeviceToHost, c->stream));
     if (async)
         return 0;
     int ns = 0;

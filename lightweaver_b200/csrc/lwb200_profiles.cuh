@@ -14,7 +14,9 @@
 //              t_m = v + (m + 1/2) h, which keeps every node at least h/2 away from the pole,
 //              plus the residue correction 2 Re[exp(-z^2)] / (1 + exp(2 pi a / h))
 //              (Matta & Reichel 1971); with h = 1/2 the truncation error is e^{-4 pi^2} ~ 1e-17.
-// Both agree with Faddeeva's w(z) to < 3e-14 relative for a in [1e-4, 1] (tools/voigt_check.py).
+// Both agree with Faddeeva's w(z) to < 3e-14 relative for a in [1e-4, 1]
+// (tests/test_gpu_parity.py::test_device_profiles_match_host_voigt; the imaginary part:
+// ::test_device_polarised_profiles_match_host_and_feed_the_stokes_solver).
 #pragma once
 #include "lwb200_kernels.cuh"
 
