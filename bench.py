@@ -67,8 +67,11 @@ def measured_peaks():
         return 6650.0, 'B200_PROFILING.md fallback (of fallback)'
 
 
-def build_workload(name, columns, rank=0, world=1, for_gpu=True):
-    """Returns (problem, description).  For c3 each rank builds only its column shard."""
+def build_workload(name, columns, rank=0, world=1, for_gpu=True, desc_columns=None):
+    """Returns (problem, description).  For c3 each rank builds only its column shard.  desc_columns: the
+    column count the DESCRIPTION names (the reference arm times a bounded sample of the stack but its
+    `config` must read exactly like ours)."""
+    dcol = columns if desc_columns is None else desc_columns
     if name == 'c1':
         return synth.config_c1(), 'FAL C 1D, H 6-level + Ca II 5+1-level, 5 rays (configs[0])'
     if name == 'deep':
@@ -86,7 +89,7 @@ def build_workload(name, columns, rank=0, world=1, for_gpu=True):
         from lightweaver_b200.sharding import partition_columns
         c0, c1 = partition_columns(columns, world)[rank]
         p = synth.config_c5(ncol=columns, col_range=(c0, c1))
-        return p, (f'1.5D magnetised stack of {columns} perturbed FAL C columns x 82 depths, Ca II with the 854.2 nm '
+        return p, (f'1.5D magnetised stack of {dcol} perturbed FAL C columns x 82 depths, Ca II with the 854.2 nm '
                    'line Zeeman-split and polarised, 5 rays (configs[4]; each step = one J-updating full-Stokes '
                    'formal solution of every wavelength, formal_sol_full_stokes(updateJ=True, upOnly=False))')
     if name == 'c3':
@@ -94,7 +97,7 @@ def build_workload(name, columns, rank=0, world=1, for_gpu=True):
         c0, c1 = partition_columns(columns, world)[rank]
         p = synth.config_c3(ncol=columns, col_range=(c0, c1), with_profiles=not for_gpu,
                             alloc_phi=not for_gpu)
-        return p, f'1.5D stack of {columns} perturbed FAL C columns x 82 depths, H + Ca II, 5 rays (configs[2])'
+        return p, f'1.5D stack of {dcol} perturbed FAL C columns x 82 depths, H + Ca II, 5 rays (configs[2])'
     raise SystemExit(f'unknown workload {name}')
 
 
@@ -683,7 +686,7 @@ def run_ours(args, rank, world, local_rank):
 
 
 def reference_line(args, workload, columns, world):
-    problem, desc = build_workload(workload, min(columns, 64), for_gpu=False)
+    problem, desc = build_workload(workload, min(columns, 64), for_gpu=False, desc_columns=columns)
     cb = time_reference(problem, steps=args.steps, warmup=args.warmup, budget_s=150.0 if workload == args.workload else 40.0)
     scale = (columns / problem.Ncol) if workload in ('c3', 'c5') else 1.0
     ms = cb['sec_per_step'] * 1e3 * scale

@@ -52,3 +52,17 @@ def test_clock_probe_repeat_count_is_rank_independent():
         n = bench.clock_probe_repeats(total, steps)
         assert n >= 20 and n % 20 == 0 and n <= 20000
     assert bench.clock_probe_repeats(12.0, 20) == bench.clock_probe_repeats(12.0, 20)
+
+
+def test_both_arms_describe_the_same_config():
+    """`config` is a pure function of the workload: the reference arm, which times a bounded sample of a
+    column stack, must print exactly the `config` our arm prints (the driver compares them)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ours, d0 = bench.build_workload('c3', 8, rank=0, world=1)
+    sample, d1 = bench.build_workload('c3', 4, for_gpu=False, desc_columns=8)
+    assert bench.workload_config('c3', d0, ours, 8) == bench.workload_config('c3', d1, sample, 8)
+    a, da = bench.build_workload('c2', 4096)
+    assert bench.workload_config('c2', da, a, 4096)['Ncolumns'] == 1
