@@ -62,6 +62,7 @@ class Context:
         self._cs = problem.c_struct()
         self._h = C.c_void_p()
         capi.check(self.lib.lwb200_create(C.byref(self._cs), device, C.byref(self._h)))
+        self._stream, self._laRange = stream, laRange
         if stream is not None:
             self.set_stream(stream)
         if laRange is not None:
@@ -136,7 +137,32 @@ class Context:
         problem.configure_hprd() before constructing it)."""
         self.problem.configure_hprd(includeDetailed)
         self._hprd_cs = self.problem.hprd.c_struct(self._hprd_keep)
-        capi.check(self.lib.lwb200_set_hybrid_prd(self._h, self._hprd_cs))
+        if self.lib.lwb200_set_hybrid_prd(self._h, self._hprd_cs) != 0:
+            msg = (self.lib.lwb200_last_error() or b'').decode()
+            if 'create a new context' not in msg:
+                raise capi.LwB200Error(msg)
+            # the new velocity field scatters from wavelengths the plan did not route through the general
+            # kernel: plan again (what the plugin shim does whenever configure_hprd_coeffs has run)
+            self._rebuild()
+
+    def _rebuild(self):
+        """A new device context for the problem as it is now (same stream, wavelength range and options);
+        every input travels again."""
+        self.lib.lwb200_destroy(self._h)
+        self._h = C.c_void_p()
+        self._cs = self.problem.c_struct()
+        capi.check(self.lib.lwb200_create(C.byref(self._cs), self.device, C.byref(self._h)))
+        if self._stream is not None:
+            self.set_stream(self._stream)
+        if self._laRange is not None:
+            self.set_lambda_range(*self._laRange)
+        self._ng = False
+        self._stokes_sent = False
+        self._zplane = False
+        self.upload(capi.ALL_INPUTS)
+        self.collisions_changed()
+        if any(t.rhoPrd is not None for a in self.problem.atoms for t in a.trans):
+            self.upload(capi.PRD)
 
     def collisions_changed(self):
         """The collisional rates C of the active atoms are context state on the device (they change
