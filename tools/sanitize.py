@@ -1,0 +1,51 @@
+"""Small end-to-end exercise of every kernel family for compute-sanitizer (development aid):
+    compute-sanitizer --tool memcheck python tools/sanitize.py"""
+import sys
+sys.path.insert(0, '.')
+import numpy as np
+from lightweaver_b200 import synth, capi
+from lightweaver_b200.context import Context
+
+p = synth.tiny_problem(ncol=2, perturb=True)
+ctx = Context(p)
+for it in range(2):
+    ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+    ctx.stat_equil()
+ctx.formal_sol()
+ctx.close()
+print('scalar ok', flush=True)
+
+p = synth.tiny_prd_problem(ncol=2, perturb=True)
+p.configure_hprd()
+ctx = Context(p)
+ctx.formal_sol_gamma_matrices()
+ctx.prd_redistribute(maxIter=2, tol=1e-6)
+ctx.stat_equil()
+ctx.close()
+print('hybrid prd ok', flush=True)
+
+p = synth.tiny_prd_problem(ncol=2, perturb=True, ndepth=150)
+ctx = Context(p)
+ctx.formal_sol_gamma_matrices()
+ctx.prd_redistribute(maxIter=2, tol=1e-6)
+ctx.close()
+print('deep prd ok', flush=True)
+
+p = synth.tiny_stokes_problem(ncol=2, perturb=True)
+ctx = Context(p)
+ctx.compute_polarised_profiles_device()
+ctx.formal_sol_gamma_matrices()
+J20 = np.zeros((p.Ncol, p.Nspect, p.Nspace))
+ctx.single_stokes_fs(updateJ=True, upOnly=False, extraParams={'J20': J20})
+ctx.single_stokes_fs(updateJ=False, upOnly=True)
+ctx.close()
+print('stokes ok', flush=True)
+
+p = synth.config_c3(ncol=600, with_profiles=False, alloc_phi=False)
+ctx = Context(p, upload=False)
+ctx.upload(capi.ALL_INPUTS & ~capi.PROFILE)
+ctx.update_deps(background=False, profiles_on_device=True)
+ctx.formal_sol_gamma_matrices()
+ctx.stat_equil()
+ctx.close()
+print('column stack ok', flush=True)
