@@ -397,7 +397,11 @@ __device__ __forceinline__ void gamma_lambda_w(const DevProblem& P, const GLam& 
 #define LWB200_GTILE_MINB 20
 #endif
 template <int NC, bool STAGE>
-__global__ void __launch_bounds__(STAGE ? 256 : 32, STAGE ? 1 : (NC == 1 ? LWB200_GTILE_MINB : 8))
+#ifndef LWB200_GSTAGE_THREADS
+#define LWB200_GSTAGE_THREADS 256
+#endif
+__global__ void __launch_bounds__(STAGE ? LWB200_GSTAGE_THREADS : 32,
+                                  STAGE ? (LWB200_GSTAGE_THREADS == 32 ? 16 : 1) : (NC == 1 ? LWB200_GTILE_MINB : 8))
 gamma_tile_kernel(const DevProblem P, const GammaPlan G, const int* __restrict__ tileList, int nTiles, int laLo,
                   int laHi, int colBase, const unsigned char* __restrict__ laMask, int prdOnly, int warpSmemDoubles)
 {

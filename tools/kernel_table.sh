@@ -2,7 +2,7 @@
 # development aid (under gpurun): per-kernel duration / instructions / pipe utilisation of ONE Gamma iteration
 #   tools/kernel_table.sh <tag> <ncol> <workload>     -> gpurun_out/<tag>_ktable.txt
 TAG=$1; NCOL=${2:-128}; WL=${3:-c3}
-M=gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,sass__inst_executed_local_loads,dram__bytes_read.sum,dram__bytes_write.sum
+M=gpu__time_duration.sum,smsp__inst_executed.sum,l1tex__t_sector_hit_rate.pct,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,sass__inst_executed_local_loads,dram__bytes_read.sum,dram__bytes_write.sum
 ncu --metrics $M --clock-control none -k regex:"continuum|ray_|gamma" -s 5 -c 5 --csv --log-file gpurun_out/${TAG}_ktable.csv python tools/prof_c3.py $NCOL 3 $WL > gpurun_out/${TAG}_ktable.log 2>&1
 python - <<PY
 import csv,collections
