@@ -7,6 +7,7 @@
 #include "lwb200_pipeline.cuh"
 #include "lwb200_gamma.cuh"
 #include "lwb200_ray2.cuh"
+#include "lwb200_fslong.cuh"
 #include "lwb200_prd.cuh"
 #include "lwb200_stokes.cuh"
 #include "lwb200_ng.cuh"
@@ -494,8 +495,6 @@ int build_plan(LwB200Context* c)
         for (int la = 0; la < L; ++la)
             if (c->hprdPlanMask[la])
                 c->laKind[la] = 4;
-        if (K > 128)
-            return fail("hybrid PRD is limited to Nspace <= 128 (general per-ray kernel)");
     }
     int maxSlots = 1;
     size_t maxTileEntries = 1;
@@ -517,7 +516,8 @@ int build_plan(LwB200Context* c)
                         add.push_back(g);
                 if ((int)(slots.size() + add.size()) > slotCap && pos > start)
                     break;
-                if ((int)(slots.size() + add.size()) * 4 * (size_t)KP * sizeof(double) + scratchBytes > smemLimit)
+                // (the [slot][4][depth] tile of fs_kernel; deep atmospheres use fs_long_kernel, which keeps none)
+                if (K <= 128 && (int)(slots.size() + add.size()) * 4 * (size_t)KP * sizeof(double) + scratchBytes > smemLimit)
                     return fail("too many transitions active at one wavelength for shared memory");
                 slots.insert(slots.end(), add.begin(), add.end());
                 ++pos;
@@ -601,12 +601,12 @@ int build_plan(LwB200Context* c)
     c->NCH = (K + 31) / 32;
     if (K > 128)
     {
-        // beyond one warp per column: ray_kernel in multi-warp mode (4 depths per lane, up to 8 warps)
+        // beyond one warp per column: ray_kernel in multi-warp mode (4 depths per lane, up to 8 warps);
+        // wavelengths of kind 4 (more than three overlapping lines, hybrid PRD) take fs_long_kernel
         if (K > 1024)
             return fail("Nspace > 1024 is not supported");
-        for (int la = 0; la < L; ++la)
-            if (c->laKind[la] == 4)
-                return fail("more than three overlapping lines at one wavelength with Nspace > 128 is not supported");
+        if (fs_long_smem(maxNlevel, 32 * ((K + 127) / 128)) > smemLimit)
+            return fail("atom too large for the shared-memory scratch");
         c->NCH = 4;
     }
 
@@ -1559,14 +1559,31 @@ int launch_fs_long(LwB200Context* c, int lambdaIterate, int upOnly, int storeDep
         CU(cudaEventCreate(&c->evK0));
         CU(cudaEventCreate(&c->evK1));
     }
-    if (c->forceDirect)
-        return fail("the general per-ray kernel is limited to Nspace <= 128");
     const bool capturing = stream_is_capturing(c->stream);
     if (!capturing)
         CU(cudaEventRecord(c->evK0, c->stream));
     const int fsMode = MODE == MODE_ITER ? c->stokesFsMode : (upOnly ? 3 : 1);
-    if (launch_pipeline<4, SOLVER, true>(c, c->customLists ? c->prdPl : full_lists(c), lambdaIterate, storeDepth, fsMode))
+    if (!c->forceDirect
+        && launch_pipeline<4, SOLVER, true>(c, c->customLists ? c->prdPl : full_lists(c), lambdaIterate, storeDepth, fsMode))
         return 1;
+    // the wavelengths the moment pipeline does not carry (more than three overlapping lines, hybrid PRD) --
+    // or, on request (LWB200_GENERAL_KERNEL), all of them -- go through the general multi-warp kernel
+    const bool all = c->forceDirect;
+    const int nTiles = all ? c->nListAll : c->nListDirect;
+    if (nTiles > 0 && (all || MODE != MODE_ITER || !c->customLists || c->prdPl.directPrdOnly))
+    {
+        auto kern = fs_long_kernel<SOLVER>;
+        if (set_smem_attr(kern, c->device))
+            return 1;
+        const int K = c->prob.Nspace, threads = 32 * ((K + 127) / 128);
+        const bool prdPass = MODE == MODE_ITER && c->customLists && !all; // (hybrid PRD: the whole spectrum, PRD rates only)
+        dim3 grid(nTiles, launch_columns(c));
+        kern<<<grid, threads, fs_long_smem(c->P.maxNlevel, threads), c->stream>>>(
+            c->P, all ? c->dListAll.p : c->dListDirect.p, prdPass ? 0 : c->laLo, prdPass ? c->prob.Nspect : c->laHi,
+            lambdaIterate, upOnly, storeDepth, prdPass ? 1 : 0, MODE == MODE_ITER ? 0 : 1);
+        CU(cudaGetLastError());
+        c->lastLaunches += 1;
+    }
     if (!capturing)
     {
         CU(cudaEventRecord(c->evK1, c->stream));

@@ -207,6 +207,21 @@ def test_deep_static_atmosphere_shares_directions():
     ctx.close()
 
 
+@pytest.mark.parametrize('solver', [capi.FS_BEZIER3, capi.FS_BESSER, capi.FS_LINEAR])
+def test_deep_atmosphere_general_kernel_on_request(solver):
+    """Nspace > 128 through the general multi-warp kernel (fs_long_kernel) for every wavelength: Gamma
+    iteration and the plain formal solution, every solver."""
+    p = synth.tiny_problem(ndepth=260, nrays=2, ncol=2, perturb=True, formal_solver=solver)
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0), extraParams={'generalKernel': True})
+        ctx.stat_equil()
+        oracle_iter(q, lambdaIterate=(it == 0))
+        assert_close(p, q)
+    ctx.close()
+
+
 def test_too_many_depths_fails_loudly():
     p = synth.tiny_problem(ndepth=1100, nrays=2, with_profiles=False)
     with pytest.raises(capi.LwB200Error):
@@ -327,14 +342,14 @@ def test_cuda_prd_vs_oracle_columns(ndepth, tiled, monkeypatch):
     ctx.close()
 
 
-@pytest.mark.parametrize('vscale', [1.0, 8.0])
-def test_cuda_hybrid_prd_vs_oracle_columns(vscale):
+@pytest.mark.parametrize('vscale,ndepth', [(1.0, None), (8.0, None), (3.0, 200)])
+def test_cuda_hybrid_prd_vs_oracle_columns(vscale, ndepth):
     """Hybrid PRD on a three-column stack with different velocity fields: rho interpolated per ray to the
     rest frame, JRest scattered by the formal solution, the redistribution fed by JRest and followed by the
     PRD formal solution over each column's own scattering wavelengths -- against the restatement (itself
     bit-identical to the reference, tests/test_oracle.py).  Then new tables for a changed velocity field
     (lwb200_set_hybrid_prd) and one more iteration."""
-    p = synth.tiny_prd_problem(ncol=3, perturb=True)
+    p = synth.tiny_prd_problem(ncol=3, perturb=True, ndepth=ndepth)
     p.vlosMu *= vscale
     p.vlosMu[1] *= -0.5
     p.configure_hprd()
@@ -868,7 +883,7 @@ def test_column_stack_properties_at_scale():
     ctx.close()
 
 
-@pytest.mark.parametrize('ndepth,general', [(None, False), (None, True), (200, False)])
+@pytest.mark.parametrize('ndepth,general', [(None, False), (None, True), (200, False), (200, True)])
 def test_zplane_decomposition_matches_depth_intensities(ndepth, general):
     """ZPlaneUp(la, mu) = I(1) of the up-going ray, ZPlaneDown(la, mu) = I(Nz - 2) of the down-going one
     (SimdFullIterationTemplates.hpp:351-360), for a stack, through the moment pipeline, the general
@@ -974,7 +989,7 @@ def test_c3_shaped_stack_sampled_columns_match_oracle():
     ctx.close()
 
 
-def _overlap_problem(nlines):
+def _overlap_problem(nlines, ndepth=None):
     """A toy atom whose `nlines` lines all overlap (same-atom cross moments), plus a
     second atom with an overlapping line (cross-atom case)."""
     lev = [synth.Level(0.0, 2, 0)] + [synth.Level(60000.0 + 18.0 * i, 4 + 2 * i, 0) for i in range(nlines)]
@@ -986,7 +1001,27 @@ def _overlap_problem(nlines):
     lev2 = [synth.Level(0.0, 2, 0), synth.Level(60010.0, 6, 0), synth.Level(90000.0, 1, 1)]
     b = synth.ModelAtom('Oth', 20.0, 3e-5, lev2, [synth.LineSpec(1, 0, 1.0e8, 21, 5.0, 80.0)],
                         [synth.ContSpec(2, 0, 5.0e-22, 8, 50.0), synth.ContSpec(2, 1, 8.0e-22, 8, 80.0)])
-    return synth.build_problem([a, b], nrays=3, perturb=True, ncol=2)
+    return synth.build_problem([a, b], nrays=3, perturb=True, ncol=2, ndepth=ndepth)
+
+
+def test_four_overlapping_lines_in_a_deep_atmosphere():
+    """More than three overlapping lines with Nspace > 128: those wavelengths go through the general
+    multi-warp kernel beside the moment pipeline; then the plain formal solution over both."""
+    p = _overlap_problem(4, ndepth=200)
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+        ctx.stat_equil()
+        oracle_iter(q, lambdaIterate=(it == 0))
+        assert_close(p, q)
+    for upOnly in (True, False):
+        p.I[:] = -1.0
+        ctx.formal_sol(upOnly=upOnly)
+        for c in range(q.Ncol):
+            oraclelib.OracleContext(q, col=c).formal_sol(upOnly=upOnly)
+        assert rel_err(p.I, q.I) <= TOL
+    ctx.close()
 
 
 @pytest.mark.parametrize('nlines,gammaStage', [(1, None), (2, None), (3, None), (4, None), (1, 'v2'), (2, 'v2'), (3, 'v2'),
