@@ -921,7 +921,7 @@ int build_plan(LwB200Context* c)
         || c->dSingular.alloc(1) || c->dPhiAsym.alloc(1))
         return 1;
     {
-        const int one = 1; // until the profiles have been looked at, assume nothing
+        const int one = 3; // until the profiles have been looked at, assume nothing
         CU(cudaMemcpy(c->dPhiAsym.p, &one, sizeof(int), cudaMemcpyHostToDevice));
     }
     if (p.vlosMu && c->vlosMu.alloc(ncol * M * K))
@@ -1114,7 +1114,7 @@ int check_phi_symmetry(LwB200Context* c)
         return 0;
     CU(cudaMemsetAsync(c->dPhiAsym.p, 0, sizeof(int), c->stream));
     const size_t nPairs = c->phi.n / ((size_t)2 * c->P.K);
-    phi_symmetry_kernel<<<148 * 8, 256, 0, c->stream>>>(c->phi.p, nPairs, c->P.K, c->dPhiAsym.p);
+    phi_symmetry_kernel<<<148 * 8, 256, 0, c->stream>>>(c->phi.p, nPairs, c->P.K, c->P.M, c->dPhiAsym.p);
     CU(cudaGetLastError());
     return 0;
 }
@@ -1319,7 +1319,10 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
             CU(cudaGetLastError());
             c->lastLaunches += 1;
             // Bezier3, one warp per wavelength, both directions: the two rays of a mu solved together
-            const bool pairKernel = SOLVER == 2 && !MULTI && !storeDepth && !(fsMode & 2) && !c->rayV1;
+            // (ray_smem_kernel evaluates the end points of all rays of a wavelength in one go, lane per ray,
+            // before it reuses the rows they are made from: up to 32 rays)
+            const bool pairKernel = SOLVER == 2 && !MULTI && !storeDepth && !(fsMode & 2) && !c->rayV1
+                && 2 * c->prob.Nrays <= 32;
             if (pairKernel)
             {
                 if constexpr (SOLVER == 2 && !MULTI)

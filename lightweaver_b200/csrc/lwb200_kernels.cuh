@@ -122,7 +122,8 @@ struct DevProblem
     const int* laNLines;      // [L] number of overlapping lines
     const LambdaLine* lamLine; // [L][3]
     int momRows;
-    const int* phiAsym;       // 0: phi(.., dir 0, .) == phi(.., dir 1, .) everywhere (static atmosphere)
+    const int* phiAsym;       // bit 0 clear: phi(.., dir 0, .) == phi(.., dir 1, .) everywhere; bit 1 clear: phi does
+                              // not depend on the ray at all (static atmosphere)
     // full Stokes (lwb200_stokes.cuh)
     // column mask of a stack (lwb200_set_active_columns): retired columns are skipped by every kernel
     const int* colList;             // active column indices, ascending; nullptr: all columns

@@ -42,9 +42,11 @@ __host__ __device__ constexpr int moment_rows(int NL) { return 1 + 4 * NL + NL *
 // (They are whenever vlos = 0 and the profile is the default Voigt; a line model that
 // overrides compute_phi may break it, which is why the data is checked, not the flags.)
 // The phi pool is a sequence of [2][K] blocks.  Runs after every profile upload / generation.
-__global__ void phi_symmetry_kernel(const double* __restrict__ phi, size_t nPairs, int K, int* __restrict__ asym)
+// Bit 1 of the flag: do the profiles depend on mu?  (Every line's block of the pool is [..][M][2][K]: the M
+// pairs of one (column, line wavelength) are consecutive, and are compared with the first of them.)
+__global__ void phi_symmetry_kernel(const double* __restrict__ phi, size_t nPairs, int K, int M, int* __restrict__ asym)
 {
-    bool diff = false;
+    bool diff = false, muDiff = false;
     const size_t total = nPairs * (size_t)K;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x)
@@ -52,10 +54,14 @@ __global__ void phi_symmetry_kernel(const double* __restrict__ phi, size_t nPair
         const size_t pair = idx / K;
         const int k = (int)(idx % K);
         const double a = phi[pair * 2 * K + k], b = phi[(pair * 2 + 1) * K + k];
+        const double r0 = phi[(pair / M) * M * 2 * K + k];
         diff |= (__double_as_longlong(a) != __double_as_longlong(b));
+        muDiff |= (__double_as_longlong(a) != __double_as_longlong(r0));
     }
     if (__any_sync(kFull, diff) && lane_id() == 0)
         atomicOr(asym, 1);
+    if (__any_sync(kFull, muDiff || diff) && lane_id() == 0)
+        atomicOr(asym, 2);
 }
 
 // ---------------------------------------------------------------------------
@@ -316,7 +322,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
         RayPre<NCH> pre;
         // the up and down rays of one mu share opacities, source function and the whole
         // direction-independent phase of the solver when their profiles are identical
-        const bool shareDir = (SOLVER == 2) && !storeDepth && dirFirst == 0 && (__ldg(P.phiAsym) == 0);
+        const bool shareDir = (SOLVER == 2) && !storeDepth && dirFirst == 0 && ((__ldg(P.phiAsym) & 1) == 0);
 
         // line-free wavelengths: chi and S are the same for every ray; interpolation data once at mu = 1
         RayPre<NCH> pre1;

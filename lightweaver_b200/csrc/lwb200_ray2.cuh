@@ -284,20 +284,37 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
             asm volatile("prefetch.global.L2 [%0];" ::"l"(P.J + nLK));
         }
 
-        const bool shareDir = NL == 0 || __ldg(P.phiAsym) == 0;
+        const int phiFlags = NL == 0 ? 0 : __ldg(P.phiAsym);
+        const bool shareDir = (phiFlags & 1) == 0;
+        // static atmosphere: the profiles do not depend on the ray at all, a line wavelength is then solved
+        // like a line-free one (chi and S once per wavelength) and its line moments are products of the
+        // profile with the two scalar moments
+        const bool muShare = NL > 0 && phiFlags == 0;
 
         // line-free wavelengths: chi and S are the same for every ray; interpolation data once at mu = 1,
         // parked in the constants' rows (chiC, etaC, sigma J-dagger are not needed any more)
-        if (NL == 0)
+        if (NL == 0 || muShare)
         {
             double chi[NCH], S[NCH], rchi[NCH];
             RayPre<NCH> pre1;
 #pragma unroll
             for (int j = 0; j < NCH; ++j)
             {
-                chi[j] = cst(0, j);
-                rchi[j] = rcp_fast(chi[j]);
-                S[j] = (cst(1, j) + cst(2, j)) * rchi[j]; // compute_source_fn (:169-179)
+                double c = cst(0, j), e = cst(1, j);
+                if (NL > 0)
+                {
+#pragma unroll
+                    for (int l = 0; l < NLA; ++l)
+                    {
+                        const double pq = (lane * NCH + j < K) ? __ldg(ph[l] + j) : 0.0;
+                        c = fma(cst(3 + 2 * l, j), pq, c);
+                        e = fma(cst(4 + 2 * l, j), pq, e);
+                        prow(l, j) = pq;
+                    }
+                }
+                chi[j] = c;
+                rchi[j] = rcp_fast(c);
+                S[j] = (e + cst(2, j)) * rchi[j]; // compute_source_fn (:169-179)
             }
             bezier3_prepare_s<NCH>(g, lane, chi, S, 1.0, 1.0, pre1);
             __syncwarp(); // (compute_ends has read the constants of other lanes)
@@ -327,8 +344,11 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
                 }
             }
         };
-        prefetch_row(shareDir ? 2 : 1);
-        prefetch_row(shareDir ? 4 : 2);
+        if (!muShare)
+        {
+            prefetch_row(shareDir ? 2 : 1);
+            prefetch_row(shareDir ? 4 : 2);
+        }
 
         // The profile rows travel through registers ONE RAY AHEAD: they are loaded right after the previous
         // ray's opacities are formed (into the registers those just freed -- the rows the moment phase needs
@@ -344,7 +364,8 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
                         p[l][j] = (lane * NCH + j < K) ? __ldg(ph[l] + (size_t)row * K + j) : 0.0;
             }
         };
-        load_row(0);
+        if (!muShare)
+            load_row(0);
         RayCoef<NCH> coef;
         const int laneE = (K - 1) / NCH, jE = (K - 1) % NCH; // where the deepest point lives
 #pragma unroll 1
@@ -361,7 +382,7 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
                 const double muz = __ldg(P.muz + mu);
                 const double zmu = rcp_fast(muz);
                 RayPre<NCH> pre;
-                if (NL == 0)
+                if (NL == 0 || muShare)
                 {
 #pragma unroll
                     for (int j = 0; j < NCH; ++j)
@@ -431,7 +452,7 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
                 const double wP = lambdaIterate ? 0.0 : w * psi[j];
                 momr(0, j) += wI;
                 momr(1, j) += wP;
-                if (NL > 0)
+                if (NL > 0 && !muShare)
                 {
                     double tq[NLA], pq[NLA];
 #pragma unroll
@@ -465,6 +486,14 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
         // ---- J row, dJ (:477-485) and the moment rows
         double dJ = 0.0;
         double* mom = P.mom + ((size_t)cb * P.momRows + P.momOff[la]) * K;
+        double W0 = 0.0; // sum of the ray weights, in ray order
+        if (muShare)
+            for (int mu = 0; mu < M; ++mu)
+            {
+                const double w = 0.5 * __ldg(P.wmu + mu);
+                W0 += w;
+                W0 += w;
+            }
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
         {
@@ -479,7 +508,32 @@ ray_smem_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, i
                 if (noMoments)
                     continue;
                 mom[k] = momr(1, j);
-                if (NL > 0)
+                if (NL > 0 && muShare)
+                {
+                    // ray-independent profiles: sum_r w f_r p^a = p^a sum_r w f_r
+                    const double mP = momr(1, j);
+                    double tq[NLA], pq[NLA];
+#pragma unroll
+                    for (int l = 0; l < NLA; ++l)
+                    {
+                        pq[l] = prow(l, j);
+                        tq[l] = mP * pq[l];
+                        mom[(size_t)(1 + 4 * l) * K + k] = W0 * pq[l];
+                        mom[(size_t)(2 + 4 * l) * K + k] = mJ * pq[l];
+                        mom[(size_t)(3 + 4 * l) * K + k] = tq[l];
+                        mom[(size_t)(4 + 4 * l) * K + k] = tq[l] * pq[l];
+                    }
+                    int pr = 0;
+#pragma unroll
+                    for (int a2 = 0; a2 < NLA; ++a2)
+#pragma unroll
+                        for (int b2 = a2 + 1; b2 < NLA; ++b2)
+                        {
+                            mom[(size_t)(1 + 4 * NL + pr) * K + k] = tq[a2] * pq[b2];
+                            ++pr;
+                        }
+                }
+                else if (NL > 0)
                 {
 #pragma unroll
                     for (int l = 0; l < NLA; ++l)

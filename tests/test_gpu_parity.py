@@ -222,6 +222,20 @@ def test_deep_atmosphere_general_kernel_on_request(solver):
     ctx.close()
 
 
+@pytest.mark.parametrize('nrays', [16, 17, 20])
+def test_many_rays_per_wavelength(nrays):
+    """More than 32 rays (2 Nrays) per wavelength: the end points of the rays are evaluated 32 at a time."""
+    p = synth.tiny_problem(nrays=nrays, ncol=2, perturb=True)
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+        ctx.stat_equil()
+        oracle_iter(q, lambdaIterate=(it == 0))
+        assert_close(p, q)
+    ctx.close()
+
+
 def test_too_many_depths_fails_loudly():
     p = synth.tiny_problem(ndepth=1100, nrays=2, with_profiles=False)
     with pytest.raises(capi.LwB200Error):
