@@ -176,6 +176,8 @@ struct PipelineLists
     int nPolLam;
     int fullRange;     // the lists cover the whole spectrum whatever the context's wavelength shard
     int directPrdOnly; // hybrid PRD: the pass is the general kernel in PRD-rates-only mode over the direct tiles
+    const int* directPrd; // angle-averaged PRD: general-kernel tiles holding redistributed wavelengths (laMask selects them)
+    int nDirectPrd;
 };
 
 struct LwB200Context
@@ -221,6 +223,7 @@ struct LwB200Context
     DevBuf<double> chiC, etaC, mom;
     int nKindLam[4] = {0, 0, 0, 0}, nListMoment = 0, nListDirect = 0, nListAll = 0, listLo = -1, listHi = -1;
     int batchCols = 1, momRows = 0;
+    bool batchTaper = true;  // LWB200_BATCH_TAPER=0: uniform batches (tuning aid)
     // angle-averaged PRD (lwb200_redistribute_prd): lines with rhoPrd, active atoms first
     std::vector<DevPrdLine> prdLines;
     std::vector<int> prdLineDetailed;
@@ -241,11 +244,11 @@ struct LwB200Context
     double crswC = 1.0;
     DevBuf<double> nrScratch, nrDC, nrPrev, nrStages, nrBgNe, neDev;
     DevBuf<NrAtom> nrAtoms;
-    DevBuf<int> prdIdx, dKindLamPrd[4], dListMomentPrd;
+    DevBuf<int> prdIdx, dKindLamPrd[4], dListMomentPrd, dListDirectPrd;
     DevBuf<unsigned char> dPrdMask;
     std::vector<long long> atomCOff;
     long long cTot = 0;
-    int nKindLamPrd[4] = {0, 0, 0, 0}, nListMomentPrd = 0, prdListsFor = -1;
+    int nKindLamPrd[4] = {0, 0, 0, 0}, nListMomentPrd = 0, nListDirectPrd = 0, prdListsFor = -1;
     bool prdUploaded = false;
     // full Stokes (lwb200_formal_sol_full_stokes): pool of the polarised lines' six extra profiles
     std::vector<long long> transPolOff; // per global transition, -1: not polarised
@@ -903,6 +906,8 @@ int build_plan(LwB200Context* c)
         if (const char* e = std::getenv("LWB200_BATCH_COLS"))
             want = (size_t)std::max(1, atoi(e));
         c->batchCols = (int)std::max<size_t>(1, std::min<size_t>(p.Ncol, std::min<size_t>(want, cap / perCol)));
+        if (const char* e = std::getenv("LWB200_BATCH_TAPER"))
+            c->batchTaper = atoi(e) != 0;
     }
 
     // ---- device allocations
@@ -1269,9 +1274,16 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
     const int Ncol = launch_columns(c), KP = c->P.KP, K = c->P.K;
     const int laLo = pl.fullRange ? 0 : c->laLo, laHi = pl.fullRange ? c->prob.Nspect : c->laHi;
     const int threads = MULTI ? 32 * ((K + 32 * NCH - 1) / (32 * NCH)) : c->nwarps * 32;
-    for (int colBase = 0; colBase < Ncol; colBase += c->batchCols)
+    // With the early fetch each batch's results travel home under the following batches, and what is exposed
+    // is the last batch's copies: the last full batch is cut into halves of halves (512 -> 256, 128, 64, 64).
+    const bool taper = c->fetchEarly && c->finaliseEarly && fsMode == 0 && !pl.prdOnly && c->batchTaper;
+    for (int colBase = 0, nbNext = 0; colBase < Ncol; colBase += nbNext)
     {
-        const int nb = std::min(c->batchCols, Ncol - colBase);
+        int nbThis = std::min(c->batchCols, Ncol - colBase);
+        if (taper && Ncol - colBase <= c->batchCols && nbThis >= 128)
+            nbThis = (nbThis + 1) / 2;
+        nbNext = nbThis;
+        const int nb = nbThis;
         constexpr int contPerBlock = 4; // wavelengths per continuum_kernel CTA
         // small launches (one small atmosphere, a wavelength shard of a larger one): the Gamma stage
         // goes per kind and straight to the global accumulator (gamma_direct_kernel); measured on B200:
@@ -1520,16 +1532,19 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
         if (launch_pipeline<NCH, SOLVER, false>(c, c->customLists ? c->prdPl : full_lists(c), lambdaIterate, storeDepth,
                                                 c->stokesFsMode))
             return 1;
-        if (c->nListDirect > 0 && (!c->customLists || c->prdPl.directPrdOnly))
+        const bool maskPass = c->customLists && !c->prdPl.directPrdOnly; // angle-averaged PRD sub-iteration
+        const int nDirect = maskPass ? c->prdPl.nDirectPrd : c->nListDirect;
+        if (nDirect > 0)
         {
             auto kern = fs_kernel<NCH, SOLVER, MODE_ITER>;
             if (set_smem_attr(kern, c->device))
                 return 1;
-            const bool prdPass = c->customLists; // (hybrid PRD: the whole spectrum, PRD rates only)
-            dim3 grid(c->nListDirect, launch_columns(c));
-            kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListDirect.p, prdPass ? 0 : c->laLo,
-                                                             prdPass ? c->prob.Nspect : c->laHi, lambdaIterate, 0,
-                                                             storeDepth, prdPass ? 1 : 0);
+            const bool prdPass = c->customLists; // (PRD sub-iteration: the whole spectrum, PRD rates only)
+            dim3 grid(nDirect, launch_columns(c));
+            kern<<<grid, threads, c->smemBytes, c->stream>>>(
+                c->P, maskPass ? c->prdPl.directPrd : c->dListDirect.p, prdPass ? 0 : c->laLo,
+                prdPass ? c->prob.Nspect : c->laHi, lambdaIterate, 0, storeDepth, maskPass ? 2 : (prdPass ? 1 : 0),
+                maskPass ? c->prdPl.laMask : nullptr);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }
@@ -1541,7 +1556,7 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
             return 1;
         dim3 grid(c->nListAll, launch_columns(c));
         kern<<<grid, threads, c->smemBytes, c->stream>>>(c->P, c->dListAll.p, c->laLo, c->laHi, lambdaIterate,
-                                                         upOnly, storeDepth, 0);
+                                                         upOnly, storeDepth, 0, nullptr);
         CU(cudaGetLastError());
         c->lastLaunches += 1;
     }
@@ -1572,18 +1587,20 @@ int launch_fs_long(LwB200Context* c, int lambdaIterate, int upOnly, int storeDep
     // the wavelengths the moment pipeline does not carry (more than three overlapping lines, hybrid PRD) --
     // or, on request (LWB200_GENERAL_KERNEL), all of them -- go through the general multi-warp kernel
     const bool all = c->forceDirect;
-    const int nTiles = all ? c->nListAll : c->nListDirect;
-    if (nTiles > 0 && (all || MODE != MODE_ITER || !c->customLists || c->prdPl.directPrdOnly))
+    const bool prdPass = MODE == MODE_ITER && c->customLists && !all; // (PRD sub-iteration: the whole spectrum, PRD rates only)
+    const bool maskPass = prdPass && !c->prdPl.directPrdOnly;         // (angle-averaged: the masked wavelengths)
+    const int nTiles = all ? c->nListAll : (maskPass ? c->prdPl.nDirectPrd : c->nListDirect);
+    if (nTiles > 0)
     {
         auto kern = fs_long_kernel<SOLVER>;
         if (set_smem_attr(kern, c->device))
             return 1;
         const int K = c->prob.Nspace, threads = 32 * ((K + 127) / 128);
-        const bool prdPass = MODE == MODE_ITER && c->customLists && !all; // (hybrid PRD: the whole spectrum, PRD rates only)
         dim3 grid(nTiles, launch_columns(c));
         kern<<<grid, threads, fs_long_smem(c->P.maxNlevel, threads), c->stream>>>(
-            c->P, all ? c->dListAll.p : c->dListDirect.p, prdPass ? 0 : c->laLo, prdPass ? c->prob.Nspect : c->laHi,
-            lambdaIterate, upOnly, storeDepth, prdPass ? 1 : 0, MODE == MODE_ITER ? 0 : 1);
+            c->P, all ? c->dListAll.p : (maskPass ? c->prdPl.directPrd : c->dListDirect.p), prdPass ? 0 : c->laLo,
+            prdPass ? c->prob.Nspect : c->laHi, lambdaIterate, upOnly, storeDepth, maskPass ? 2 : (prdPass ? 1 : 0),
+            MODE == MODE_ITER ? 0 : 1, maskPass ? c->prdPl.laMask : nullptr);
         CU(cudaGetLastError());
         c->lastLaunches += 1;
     }
@@ -3083,21 +3100,19 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
         for (int q = 0; q < nLines; ++q)
             for (int la = c->prdLines[q].Nblue; la < c->prdLines[q].Nblue + c->prdLines[q].Nl; ++la)
                 mask[la] = 1;
-        std::vector<int> kindLam[4], tiles;
+        // (a redistributed wavelength with more than three overlapping lines is solved by the general kernel,
+        // like the rest of its kind: its tiles, masked)
+        std::vector<int> kindLam[4], tiles, dtiles;
         for (int la = 0; la < L; ++la)
-            if (mask[la])
-            {
-                if (c->laKind[la] >= 4)
-                    return fail("lwb200_redistribute_prd: a PRD line overlaps more than two other lines");
+            if (mask[la] && c->laKind[la] < 4)
                 kindLam[c->laKind[la]].push_back(la);
-            }
         for (int t = 0; t < c->Ntile; ++t)
         {
             bool any = false;
             for (int q = c->tileLa[t]; q < c->tileLa[t + 1]; ++q)
                 any = any || mask[c->tileLambda[q]];
-            if (any && c->tileKind[t] < 4)
-                tiles.push_back(t);
+            if (any)
+                (c->tileKind[t] < 4 ? tiles : dtiles).push_back(t);
         }
         std::vector<int> gtiles;
         for (int t = 0; t < c->nGTile; ++t)
@@ -3110,9 +3125,12 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
         }
         c->dPrdMask.release();
         c->dListMomentPrd.release();
+        c->dListDirectPrd.release();
         c->dGListPrd.release();
-        if (c->dPrdMask.upload(mask) || c->dListMomentPrd.upload(tiles) || c->dGListPrd.upload(gtiles))
+        if (c->dPrdMask.upload(mask) || c->dListMomentPrd.upload(tiles) || c->dGListPrd.upload(gtiles)
+            || c->dListDirectPrd.upload(dtiles))
             return 1;
+        c->nListDirectPrd = (int)dtiles.size();
         c->nListMomentPrd = (int)tiles.size();
         c->nGListPrd = (int)gtiles.size();
         for (int q = 0; q < 4; ++q)
@@ -3129,6 +3147,8 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
     {
         pl.moment = c->dListMomentPrd.p;
         pl.nMoment = c->nListMomentPrd;
+        pl.directPrd = c->dListDirectPrd.p;
+        pl.nDirectPrd = c->nListDirectPrd;
         pl.gTiles = c->dGListPrd.p;
         pl.nGTiles = c->nGListPrd;
         for (int q = 0; q < 4; ++q)

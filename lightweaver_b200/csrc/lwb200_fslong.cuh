@@ -24,7 +24,7 @@ inline size_t fs_long_smem(int maxNlevel, int threads) { return (size_t)2 * maxN
 template <int SOLVER>
 __global__ void __launch_bounds__(256, 1)
 fs_long_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi, int lambdaIterate,
-               int upOnly, int storeDepth, int prdOnly, int fsOnly)
+               int upOnly, int storeDepth, int prdOnly, int fsOnly, const unsigned char* __restrict__ laMask)
 {
     constexpr int NCH = 4;
     extern __shared__ double smem[];     // [2][maxNlevel][blockDim.x]: chi_atom / U_atom per level, one column per thread
@@ -69,7 +69,7 @@ fs_long_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, i
         if (la < laLo || la >= laHi)
             continue;
         const int hPrdLa = P.hprdLaOfLa ? P.hprdLaOfLa[(size_t)col * L + la] : -1;
-        if (prdOnly && hPrdLa < 0)
+        if ((prdOnly == 1 && hPrdLa < 0) || (prdOnly == 2 && !laMask[la]))
             continue;
         const double lambda = __ldg(P.wavelength + la);
         const size_t rowLK = ((size_t)col * L + la) * K;

@@ -243,10 +243,11 @@ __device__ __forceinline__ void smem_add(double* addr, double v) { atomicAdd(add
 template <int NCH, int SOLVER, int MODE>
 __global__ void __launch_bounds__(128)
 fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi, int lambdaIterate,
-          int upOnly, int storeDepth, int prdOnly)
+          int upOnly, int storeDepth, int prdOnly, const unsigned char* __restrict__ laMask)
 {
-    // prdOnly: the pass of formal_sol_prd_update_rates (PrdTemplates.hpp:18-76) under hybrid PRD: J, I, JRest
-    // and the rates of the PRD lines only, over the wavelengths that scatter into the PRD grid in THIS column.
+    // prdOnly: the pass of formal_sol_prd_update_rates (PrdTemplates.hpp:18-76): J, I, JRest and the rates of the
+    // PRD lines only.  1: hybrid PRD, over the wavelengths that scatter into the PRD grid in THIS column;
+    // 2: angle-averaged PRD, over the wavelengths of laMask (those of the redistributed lines).
     extern __shared__ double smem[];
     const int K = P.K, M = P.M, L = P.L, KP = P.KP;
     const int tile = tileList[blockIdx.x];
@@ -290,7 +291,7 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
         if (la < laLo || la >= laHi)
             continue;
         const int hPrdLa = P.hprdLaOfLa ? P.hprdLaOfLa[(size_t)col * L + la] : -1;
-        if (prdOnly && hPrdLa < 0)
+        if ((prdOnly == 1 && hPrdLa < 0) || (prdOnly == 2 && !laMask[la]))
             continue;
         const double lambda = __ldg(P.wavelength + la);
         const size_t rowLK = ((size_t)col * L + la) * K;

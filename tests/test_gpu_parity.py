@@ -1003,7 +1003,7 @@ def test_c3_shaped_stack_sampled_columns_match_oracle():
     ctx.close()
 
 
-def _overlap_problem(nlines, ndepth=None):
+def _overlap_problem(nlines, ndepth=None, prd=None):
     """A toy atom whose `nlines` lines all overlap (same-atom cross moments), plus a
     second atom with an overlapping line (cross-atom case)."""
     lev = [synth.Level(0.0, 2, 0)] + [synth.Level(60000.0 + 18.0 * i, 4 + 2 * i, 0) for i in range(nlines)]
@@ -1015,7 +1015,38 @@ def _overlap_problem(nlines, ndepth=None):
     lev2 = [synth.Level(0.0, 2, 0), synth.Level(60010.0, 6, 0), synth.Level(90000.0, 1, 1)]
     b = synth.ModelAtom('Oth', 20.0, 3e-5, lev2, [synth.LineSpec(1, 0, 1.0e8, 21, 5.0, 80.0)],
                         [synth.ContSpec(2, 0, 5.0e-22, 8, 50.0), synth.ContSpec(2, 1, 8.0e-22, 8, 80.0)])
-    return synth.build_problem([a, b], nrays=3, perturb=True, ncol=2, ndepth=ndepth)
+    return synth.build_problem([a, b], nrays=3, perturb=True, ncol=2, ndepth=ndepth, prd=prd)
+
+
+@pytest.mark.parametrize('ndepth', [None, 200])
+def test_prd_line_overlapping_three_other_lines(ndepth):
+    """A PRD line inside a blend of four lines: its wavelengths are beyond the moment pipeline, so the Gamma
+    iteration AND the formal solution of the PRD sub-iterations take the general kernel there (masked to the
+    redistributed wavelengths, PRD rates only)."""
+    p = _overlap_problem(4, ndepth=ndepth, prd={'Ovl': [0, 2]})
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices()
+        upd = ctx.prd_redistribute(maxIter=2, tol=1e-6)
+        q.prefill_gamma()
+        dRho = []
+        for c in range(q.Ncol):
+            o = oraclelib.OracleContext(q, col=c)
+            o.fs_iter()
+            dRho.append(o.redistribute_prd(maxIter=2, tol=1e-6, nlines=2)['dRho'][:4])
+        assert upd.NprdSubIter == 2
+        assert np.allclose(np.asarray(upd.dRho), np.max(dRho, axis=0), rtol=TOL, atol=1e-12)
+        for tp, tq in zip(p.atoms[0].trans, q.atoms[0].trans):
+            if tp.rhoPrd is not None:
+                assert rel_err(tp.rhoPrd, tq.rhoPrd) <= TOL
+        e = compare_problems(p, q)
+        assert e['I'] <= TOL and e['J'] <= TOL and e['R'] <= TOL, e
+        ctx.stat_equil()
+        for c in range(q.Ncol):
+            oraclelib.OracleContext(q, col=c).stat_eq()
+        assert compare_problems(p, q)['n'] <= TOL_N
+    ctx.close()
 
 
 def test_four_overlapping_lines_in_a_deep_atmosphere():
