@@ -1405,8 +1405,9 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
                 c->P, pl.polLam, pl.nPolLam, contPerBlock, colBase);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
-            stokes_kernel<<<dim3((nRays + 127) / 128, nb), 128, 0, c->stream>>>(c->P, pl.polLam, pl.nPolLam, colBase,
-                                                                                (fsMode & 2) ? 1 : 0, (fsMode & 4) ? 1 : 0);
+            static const bool stokesV1 = std::getenv("LWB200_STOKES_V1") && std::atoi(std::getenv("LWB200_STOKES_V1")) != 0;
+            (stokesV1 ? stokes_kernel_v1 : stokes_kernel)<<<dim3((nRays + 127) / 128, nb), 128, 0, c->stream>>>(
+                c->P, pl.polLam, pl.nPolLam, colBase, (fsMode & 2) ? 1 : 0, (fsMode & 4) ? 1 : 0);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }
