@@ -88,7 +88,8 @@ def build_workload(name, columns, rank=0, world=1, for_gpu=True, desc_columns=No
     if name == 'c5':
         from lightweaver_b200.sharding import partition_columns
         c0, c1 = partition_columns(columns, world)[rank]
-        p = synth.config_c5(ncol=columns, col_range=(c0, c1))
+        # (on the GPU side the profiles -- phi and the six polarised ones -- are made on the device)
+        p = synth.config_c5(ncol=columns, col_range=(c0, c1), with_profiles=not for_gpu, alloc_phi=not for_gpu)
         return p, (f'1.5D magnetised stack of {dcol} perturbed FAL C columns x 82 depths, Ca II with the 854.2 nm '
                    'line Zeeman-split and polarised, 5 rays (configs[4]; each step = one J-updating full-Stokes '
                    'formal solution of every wavelength, formal_sol_full_stokes(updateJ=True, upOnly=False))')
@@ -346,6 +347,47 @@ def parity_spot_check(ctx, problem, workload, columns, col0, step, laRange=None,
             'tol': {'I': tol, 'J': tol, 'Gamma (norm-wise per depth)': tol, 'n': 10 * tol}}
 
 
+def stokes_spot_check(ctx, problem, columns, col0, step, ncheck=4, tol=1e-9):
+    """parity_spot_check for the full-Stokes workload: J-dagger and the populations of a few columns are read
+    from the device, ONE more J-updating full-Stokes pass runs there (on device-made profiles), and its I, Q, U, V
+    (where a polarised line is active) and J are compared with the oracle's formal_sol_full_stokes of the same
+    columns started from that state on host-made (Faddeeva) profiles."""
+    import torch
+    from oracle import oraclelib
+    from tests.util import rel_err
+    v = _packed_views(ctx, problem)
+    Ncol = problem.Ncol
+    cols = sorted(set(int(c) for c in np.linspace(0, Ncol - 1, min(ncheck, Ncol))))
+    torch.cuda.synchronize()
+    J0 = v['J'][cols].cpu().numpy()
+    n0 = v['n'][cols].cpu().numpy()
+    step()
+    torch.cuda.synchronize()
+    ctx.download(capi.INTENS | capi.JBAR | capi.STOKES)
+    err = {'I': 0.0, 'QUV': 0.0, 'J': 0.0}
+    for qi, c in enumerate(cols):
+        q = synth.config_c5(ncol=columns, col_range=(col0 + c, col0 + c + 1))
+        q.J[0] = J0[qi]
+        lev = 0
+        for a in q.atoms:
+            a.n[0] = n0[qi, lev:lev + a.Nlevel]
+            lev += a.Nlevel
+        oraclelib.OracleContext(q).full_stokes(updateJ=True, upOnly=False)
+        pol = np.zeros(q.Nspect, dtype=bool)
+        for a in q.atoms:
+            for t_ in a.trans:
+                if t_.type == capi.LINE and t_.polProfiles is not None:
+                    pol[t_.Nblue:t_.Nred] = True
+        err['I'] = max(err['I'], rel_err(problem.I[c], q.I[0]))
+        err['J'] = max(err['J'], rel_err(problem.J[c], q.J[0]))
+        err['QUV'] = max(err['QUV'], float(np.abs(problem.Quv[c][:, pol] - q.Quv[0][:, pol]).max() / np.abs(q.I[0]).max()))
+    ok = all(e <= tol for e in err.values())
+    return {'ok': bool(ok), 'against': 'oracle/lw_oracle.c formal_sol_full_stokes (bit-identical to the reference) from '
+            'the same device state, one untimed pass after the timed region',
+            'columns_checked': [col0 + c for c in cols], 'max_rel_err': err,
+            'tol': {'I': tol, 'J': tol, 'Q, U, V at polarised wavelengths (relative to max I)': tol}}
+
+
 def plugin_e2e(problem, steps):
     """e2e through the REAL drop-in boundary for a 1D atmosphere: the reference's own compiled core
     (oracle/_ref/liblwref.so = Lightweaver's C++ `formal_sol_gamma_matrices` / `stat_eq` entry points) loads
@@ -383,7 +425,9 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
     stream = torch.cuda.current_stream()
     ctx = Context(problem, device=local_rank, stream=stream, laRange=laRange, upload=False)
     if stokes:
-        ctx.upload(capi.ALL_INPUTS | capi.STOKES)
+        ctx.upload(capi.ALL_INPUTS & ~capi.PROFILE)
+        ctx.update_deps(background=False, profiles_on_device=True)
+        ctx.compute_polarised_profiles_device()
     elif column_sharded:
         ctx.upload(capi.ALL_INPUTS & ~capi.PROFILE)
         ctx.update_deps(background=False, profiles_on_device=True)
@@ -514,10 +558,13 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
 
     # ---- untimed parity spot check of the state just timed
     parity = None
-    if not stokes and not with_prd:
+    if not with_prd:
         try:
-            parity = parity_spot_check(ctx, problem, workload, columns, col0, step, laRange=laRange, ranges=ranges,
-                                       rank=rank, world=world)
+            if stokes:
+                parity = stokes_spot_check(ctx, problem, columns, col0, step)
+            else:
+                parity = parity_spot_check(ctx, problem, workload, columns, col0, step, laRange=laRange, ranges=ranges,
+                                           rank=rank, world=world)
         except Exception as e:  # reported, never fatal for the measurement itself
             parity = {'ok': False, 'error': f'{type(e).__name__}: {e}'}
         barrier()
@@ -677,17 +724,31 @@ def run_ours(args, rank, world, local_rank):
     line = bench_workload(args, args.workload, args.columns, rank, world, local_rank)
     if args.secondary and args.workload == 'c3':
         # the lambda-sharded 1D workload (configs[1]) beside the column-sharded headline, same launch
+        keep = ('value', 'unit', 'ms_per_step', 'gamma_iter_per_s', 'scaling', 'config', 'parallelism', 'e2e',
+                'gpu_launches', 'parity_check', 'roofline', 'cpu_baseline')
         sec = bench_workload(args, 'c2', args.columns, rank, world, local_rank)
         if line is not None and sec is not None:
-            keep = ('value', 'unit', 'ms_per_step', 'gamma_iter_per_s', 'scaling', 'config', 'parallelism', 'e2e',
-                    'gpu_launches', 'parity_check', 'roofline', 'cpu_baseline')
             line['secondary'] = {'c2_lambda_sharded': {k: sec[k] for k in keep if k in sec}}
+        # the other BASELINE configs, so that one default run measures all five: the magnetised full-Stokes stack
+        # (configs[4]) and the small 1D cases (configs[0], configs[3])
+        # (one GPU only: a secondary that failed on one rank of a multi-rank launch would leave the others
+        # waiting in its reductions)
+        extra = [('c5_full_stokes_stack', 'c5', 1024), ('c1', 'c1', 1), ('c4_prd', 'c4', 1)] if world == 1 else []
+        for key, wl, cols in extra:
+            try:
+                sec = bench_workload(args, wl, cols, rank, world, local_rank, with_cpu_baseline=False)
+            except BaseException as e:  # (a secondary must never take the headline down)
+                sec = {'error': f'{type(e).__name__}: {e}'} if rank == 0 else None
+            if line is not None and sec is not None:
+                line['secondary'][key] = {k: sec[k] for k in keep + ('error',) if k in sec}
     return line
 
 
-def reference_line(args, workload, columns, world):
+def reference_line(args, workload, columns, world, budget_s=None):
     problem, desc = build_workload(workload, min(columns, 64), for_gpu=False, desc_columns=columns)
-    cb = time_reference(problem, steps=args.steps, warmup=args.warmup, budget_s=150.0 if workload == args.workload else 40.0)
+    if budget_s is None:
+        budget_s = 150.0 if workload == args.workload else 40.0
+    cb = time_reference(problem, steps=args.steps, warmup=args.warmup, budget_s=budget_s)
     scale = (columns / problem.Ncol) if workload in ('c3', 'c5') else 1.0
     ms = cb['sec_per_step'] * 1e3 * scale
     return {
@@ -713,6 +774,13 @@ def run_reference(args, rank, world):
         sec = reference_line(args, 'c2', args.columns, world)
         keep = ('value', 'unit', 'ms_per_step', 'gamma_iter_per_s', 'config', 'parallelism', 'cpu_baseline', 'e2e')
         line['secondary'] = {'c2_lambda_sharded': {k: sec[k] for k in keep}}
+        if world == 1:
+            for key, wl, cols in (('c5_full_stokes_stack', 'c5', 1024), ('c1', 'c1', 1), ('c4_prd', 'c4', 1)):
+                try:
+                    sec = reference_line(args, wl, cols, world, budget_s=15.0)
+                    line['secondary'][key] = {k: sec[k] for k in keep}
+                except Exception as e:
+                    line['secondary'][key] = {'error': f'{type(e).__name__}: {e}'}
     return line
 
 

@@ -386,6 +386,7 @@ def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, se
     synthetic magnetic field of up to ``Bmax`` Tesla (seeded, different in every column)."""
     rng = np.random.default_rng(seed + 1)
     atm = falc_columns(ncol, perturb=perturb, seed=seed, ndepth=ndepth)
+    ncol_full = ncol
     if col_range is not None:
         atm = {k: np.ascontiguousarray(v[col_range[0]:col_range[1]]) for k, v in atm.items()}
         ncol = col_range[1] - col_range[0]
@@ -395,12 +396,15 @@ def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, se
     vlosMu = np.ascontiguousarray(muz[None, :, None] * atm['vz'][:, None, :])
 
     if polarised:
-        prng = np.random.default_rng(seed + 7 + (0 if col_range is None else col_range[0]))
+        # (drawn for the whole stack, then cut: a column is the same whichever shard holds it)
+        prng = np.random.default_rng(seed + 7)
+        cut = slice(None) if col_range is None else slice(col_range[0], col_range[1])
         zn = np.linspace(0.0, 1.0, K)[None, :]
-        amp = prng.uniform(0.3, 1.0, (ncol, 1))
+        amp = prng.uniform(0.3, 1.0, (ncol_full, 1))[cut]
         Bfield = Bmax * amp * (0.4 + 0.6 * zn)                       # stronger with depth
-        gammaB = prng.uniform(0.2, 1.3, (ncol, 1)) + 0.3 * np.sin(2.0 * np.pi * zn + prng.uniform(0, 6, (ncol, 1)))
-        chiB = prng.uniform(0.0, np.pi, (ncol, 1)) + 0.5 * zn
+        gamma0, gamma1 = prng.uniform(0.2, 1.3, (ncol_full, 1))[cut], prng.uniform(0, 6, (ncol_full, 1))[cut]
+        gammaB = gamma0 + 0.3 * np.sin(2.0 * np.pi * zn + gamma1)
+        chiB = prng.uniform(0.0, np.pi, (ncol_full, 1))[cut] + 0.5 * zn
         cosGamma = np.ascontiguousarray(muz[None, :, None] * np.cos(gammaB)[:, None, :])
         cos2chi = np.ascontiguousarray(np.broadcast_to(np.cos(2.0 * chiB)[:, None, :], cosGamma.shape))
         sin2chi = np.ascontiguousarray(np.broadcast_to(np.sin(2.0 * chiB)[:, None, :], cosGamma.shape))
@@ -463,11 +467,11 @@ def build_problem(atoms: Sequence[ModelAtom], ncol=1, nrays=5, perturb=False, se
             t.wphi = np.zeros((ncol, K))
             is_pol = bool(polarised) and line_idx in polarised.get(atom.name, ())
             if is_pol:
-                assert with_profiles, 'polarised profiles are made on the host'
-                t.phi, t.polProfiles = polarised_profiles(t.wavelength, t.lambda0, t.aDamp, vBroad, vlosMu,
-                                                          Bfield, cosGamma, cos2chi, sin2chi, gEff=1.1)
                 t.polarised = True   # (a normal Zeeman triplet)
                 t.zeeman = (np.array([-1, 0, 1], dtype=np.int32), np.array([-1.1, 0.0, 1.1]), np.ones(3))
+            if is_pol and with_profiles:
+                t.phi, t.polProfiles = polarised_profiles(t.wavelength, t.lambda0, t.aDamp, vBroad, vlosMu,
+                                                          Bfield, cosGamma, cos2chi, sin2chi, gEff=1.1)
                 wlam = t.wlambda()
                 s = np.einsum('clmdk,l,m->ck', t.phi, wlam, 0.5 * wmu)
                 t.wphi = np.ascontiguousarray(1.0 / s)
