@@ -730,10 +730,12 @@ def run_ours(args, rank, world, local_rank):
         if line is not None and sec is not None:
             line['secondary'] = {'c2_lambda_sharded': {k: sec[k] for k in keep if k in sec}}
         # the other BASELINE configs, so that one default run measures all five: the magnetised full-Stokes stack
-        # (configs[4]) and the small 1D cases (configs[0], configs[3])
+        # (configs[4]) and the small 1D cases (configs[0], configs[3]); and the reference's own benchmark shape
+        # (lightweaver/benchmark.py:19-45: FAL C at 500 depths)
         # (one GPU only: a secondary that failed on one rank of a multi-rank launch would leave the others
         # waiting in its reductions)
-        extra = [('c5_full_stokes_stack', 'c5', 1024), ('c1', 'c1', 1), ('c4_prd', 'c4', 1)] if world == 1 else []
+        extra = ([('c5_full_stokes_stack', 'c5', 1024), ('c1', 'c1', 1), ('c4_prd', 'c4', 1),
+                  ('deep_500_depths_reference_benchmark_shape', 'deep', 1)] if world == 1 else [])
         for key, wl, cols in extra:
             try:
                 sec = bench_workload(args, wl, cols, rank, world, local_rank, with_cpu_baseline=False)
@@ -775,7 +777,8 @@ def run_reference(args, rank, world):
         keep = ('value', 'unit', 'ms_per_step', 'gamma_iter_per_s', 'config', 'parallelism', 'cpu_baseline', 'e2e')
         line['secondary'] = {'c2_lambda_sharded': {k: sec[k] for k in keep}}
         if world == 1:
-            for key, wl, cols in (('c5_full_stokes_stack', 'c5', 1024), ('c1', 'c1', 1), ('c4_prd', 'c4', 1)):
+            for key, wl, cols in (('c5_full_stokes_stack', 'c5', 1024), ('c1', 'c1', 1), ('c4_prd', 'c4', 1),
+                                  ('deep_500_depths_reference_benchmark_shape', 'deep', 1)):
                 try:
                     sec = reference_line(args, wl, cols, world, budget_s=15.0)
                     line['secondary'][key] = {k: sec[k] for k in keep}

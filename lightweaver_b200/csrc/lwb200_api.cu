@@ -224,6 +224,7 @@ struct LwB200Context
     int nKindLam[4] = {0, 0, 0, 0}, nListMoment = 0, nListDirect = 0, nListAll = 0, listLo = -1, listHi = -1;
     int batchCols = 1, momRows = 0;
     bool batchTaper = true;  // LWB200_BATCH_TAPER=0: uniform batches (tuning aid)
+    int phiFlagsHost = 3;    // host copy of the profile flags (deep atmospheres only; 3 = assume nothing)
     // angle-averaged PRD (lwb200_redistribute_prd): lines with rhoPrd, active atoms first
     std::vector<DevPrdLine> prdLines;
     std::vector<int> prdLineDetailed;
@@ -1113,6 +1114,17 @@ int set_smem_attr(Kern kern, int device)
     return 0;
 }
 
+static bool stream_is_capturing_fwd(cudaStream_t s)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return st != cudaStreamCaptureStatusNone;
+}
+
 int check_phi_symmetry(LwB200Context* c)
 {
     if (c->P.Nline == 0)
@@ -1121,6 +1133,14 @@ int check_phi_symmetry(LwB200Context* c)
     const size_t nPairs = c->phi.n / ((size_t)2 * c->P.K);
     phi_symmetry_kernel<<<148 * 8, 256, 0, c->stream>>>(c->phi.p, nPairs, c->P.K, c->P.M, c->dPhiAsym.p);
     CU(cudaGetLastError());
+    // deep atmospheres pick their ray kernel from the flags on the host (the profiles have just been uploaded or
+    // generated: one small synchronous read-back here, never inside an iteration)
+    c->phiFlagsHost = 3;
+    if (c->prob.Nspace > 128 && !stream_is_capturing_fwd(c->stream))
+    {
+        CU(cudaMemcpyAsync(&c->phiFlagsHost, c->dPhiAsym.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
     return 0;
 }
 
@@ -1361,6 +1381,25 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
                         }
                     }
 #undef LWB200_RAY3
+                }
+            }
+            else if (MULTI && SOLVER == 2 && q > 0 && c->phiFlagsHost == 0 && !storeDepth && !(fsMode & 2))
+            {
+                // deep static atmosphere: ray-independent profiles (flags read back after the symmetry check)
+                if constexpr (MULTI && SOLVER == 2)
+                {
+                    switch (q)
+                    {
+                    case 1:
+                        ray_kernel<NCH, SOLVER, 1, MULTI, true><<<grid, threads, 0, s>>>(c->P, list, nLam, perWarp, colBase, lambdaIterate, storeDepth, fsMode);
+                        break;
+                    case 2:
+                        ray_kernel<NCH, SOLVER, 2, MULTI, true><<<grid, threads, 0, s>>>(c->P, list, nLam, perWarp, colBase, lambdaIterate, storeDepth, fsMode);
+                        break;
+                    default:
+                        ray_kernel<NCH, SOLVER, 3, MULTI, true><<<grid, threads, 0, s>>>(c->P, list, nLam, perWarp, colBase, lambdaIterate, storeDepth, fsMode);
+                        break;
+                    }
                 }
             }
             else

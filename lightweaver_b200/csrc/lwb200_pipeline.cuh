@@ -123,7 +123,10 @@ __global__ void continuum_kernel(const DevProblem P, const int* __restrict__ lam
 // MULTI = true:  one CTA per wavelength, its warps laid over consecutive blocks of 32 * NCH
 //                depths (Nspace <= blockDim.x * NCH); neighbours and the scan carry cross
 //                warps through DepthComm.
-template <int NCH, int SOLVER, int NL, bool MULTI>
+// MUSHARE (Bezier3, NL > 0; chosen by the launcher from the profile flags): the profiles do not depend on
+//                the ray (static atmosphere): chi, S and the direction-independent solver phase once per
+//                wavelength as at line-free wavelengths, the line moments as products at the end.
+template <int NCH, int SOLVER, int NL, bool MULTI, bool MUSHARE = false>
 __global__ void __launch_bounds__(MULTI ? 256 : 128, MULTI ? 1 : LWB200_RAY_MINBLOCKS)
 ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int perWarp, int colBase,
            int lambdaIterate, int storeDepth, int fsMode)
@@ -322,25 +325,38 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
         RayPre<NCH> pre;
         // the up and down rays of one mu share opacities, source function and the whole
         // direction-independent phase of the solver when their profiles are identical
-        const bool shareDir = (SOLVER == 2) && !storeDepth && dirFirst == 0 && ((__ldg(P.phiAsym) & 1) == 0);
+        constexpr bool MS = MUSHARE && SOLVER == 2 && NL > 0;
+        const bool shareDir = MS || ((SOLVER == 2) && !storeDepth && dirFirst == 0 && ((__ldg(P.phiAsym) & 1) == 0));
 
         // line-free wavelengths: chi and S are the same for every ray; interpolation data once at mu = 1
         RayPre<NCH> pre1;
-        if (NL == 0)
+        if (NL == 0 || MS)
         {
 #pragma unroll
             for (int j = 0; j < NCH; ++j)
             {
-                chi[j] = chiC[j];
-                rchi[j] = rcp_fast(chiC[j]);
-                S[j] = (etaC[j] + scaJ[j]) * rchi[j]; // compute_source_fn (:169-179)
-                p[0][j] = 0.0;
+                double c = chiC[j], e = etaC[j];
+                if (MS)
+                {
+#pragma unroll
+                    for (int l = 0; l < NLA; ++l)
+                    {
+                        p[l][j] = (lane * NCH + j < K) ? __ldg(ph[l] + j) : 0.0;
+                        c = fma(cX[l][j], p[l][j], c);
+                        e = fma(cE[l][j], p[l][j], e);
+                    }
+                }
+                else
+                    p[0][j] = 0.0;
+                chi[j] = c;
+                rchi[j] = rcp_fast(c);
+                S[j] = (e + scaJ[j]) * rchi[j]; // compute_source_fn (:169-179)
             }
             if (SOLVER == 2)
                 bezier3_prepare<NCH>(cm, g, chi, S, 1.0, 1.0, pre1);
         }
         // profiles are fetched one ray ahead (NL <= 2; three lines leave no registers for it)
-        constexpr bool PREFETCH = (NL == 1 || NL == 2);
+        constexpr bool PREFETCH = (NL == 1 || NL == 2) && !MS;
         double pn[NLA][NCH];
         if (PREFETCH)
         {
@@ -356,7 +372,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
             const double muz = __ldg(P.muz + mu);
             const double zmu = rcp_fast(muz);
             const double w = 0.5 * __ldg(P.wmu + mu);
-            if (NL == 0 && SOLVER == 2)
+            if ((NL == 0 || MS) && SOLVER == 2)
             {
                 const RayPre<NCH>& q1 = pre1;
 #pragma unroll
@@ -373,7 +389,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
             {
                 if (dir < dirFirst)
                     continue;
-                if (NL > 0 && (dir == 0 || !shareDir))
+                if (NL > 0 && !MS && (dir == 0 || !shareDir))
                 {
                     const int row = 2 * mu + dir;
                     if (PREFETCH)
@@ -490,7 +506,7 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
                     const double wP = lambdaIterate ? 0.0 : w * psi[j];
                     mJ[j] += wI;
                     mP[j] += wP;
-                    if (NL > 0)
+                    if (NL > 0 && !MS)
                     {
                         double tq[NLA];
 #pragma unroll
@@ -537,7 +553,40 @@ ray_kernel(const DevProblem P, const int* __restrict__ lamList, int nLam, int pe
                 if (noMoments)
                     continue;
                 mom[k] = mP[j];
-                if (NL > 0)
+                if (MS)
+                {
+                    // ray-independent profiles: sum_r w f_r p^a = p^a sum_r w f_r
+                    double W0 = 0.0;
+                    for (int mu = 0; mu < M; ++mu)
+                    {
+                        const double w = 0.5 * __ldg(P.wmu + mu);
+                        W0 += w;
+                        W0 += w;
+                    }
+                    double tq[NLA];
+#pragma unroll
+                    for (int l = 0; l < NLA; ++l)
+                    {
+                        tq[l] = mP[j] * p[l][j];
+                        mom[(size_t)(1 + 4 * l) * K + k] = W0 * p[l][j];
+                        mom[(size_t)(2 + 4 * l) * K + k] = mJ[j] * p[l][j];
+                        mom[(size_t)(3 + 4 * l) * K + k] = tq[l];
+                        mom[(size_t)(4 + 4 * l) * K + k] = tq[l] * p[l][j];
+                    }
+                    if (NL > 1)
+                    {
+                        int pr = 0;
+#pragma unroll
+                        for (int a = 0; a < NLA; ++a)
+#pragma unroll
+                            for (int b = a + 1; b < NLA; ++b)
+                            {
+                                mom[(size_t)(1 + 4 * NL + pr) * K + k] = tq[a] * p[b][j];
+                                ++pr;
+                            }
+                    }
+                }
+                else if (NL > 0)
                 {
 #pragma unroll
                     for (int l = 0; l < NLA; ++l)

@@ -143,7 +143,8 @@ __device__ __forceinline__ void solve4(double (&A)[16], double (&b)[4])
 //     derivative of x, bit for bit), the 4x4 forms are expanded where the matrices are assembled;
 //   * the upwind slope of a step is the downwind slope of the step before: slopes are carried, and all
 //     twenty derivatives of a step share three reciprocals (steffen_r, lwb200_fsm.cuh);
-//   * K0^2 of this step is Ku^2 of the next: one structured product (the zero diagonal skipped) per step;
+//   * K^2 is a structured product (the zero diagonal skipped); carrying K0^2 into the next step as Ku^2 was
+//     measured slower than recomputing it (sixteen more live doubles at 255 registers);
 //   * the 4x4 system is solved in registers by straight-line code (solve4_reg).
 // Differences from the reference's arithmetic are at rounding level (reciprocal-multiply, the solver).
 struct StokesPt
@@ -248,7 +249,10 @@ __device__ __forceinline__ void solve4_reg(const double (&a)[4][4], double (&b)[
 
 // Grid: (ceil(nPol * 2 M / blockDim), columns of the batch).  upOnly: up-going rays only; updateJ: J (and
 // J20) rebuilt with fp64 REDs (J was zeroed and copied to Jdag by the launcher).
-__global__ void __launch_bounds__(128)
+#ifndef LWB200_STOKES_MINB
+#define LWB200_STOKES_MINB 2
+#endif
+__global__ void __launch_bounds__(128, LWB200_STOKES_MINB)
 stokes_kernel(const DevProblem P, const int* __restrict__ polLam, int nPol, int colBase, int upOnly, int updateJ)
 {
     const int K = P.K, M = P.M, L = P.L;
@@ -424,7 +428,7 @@ stokes_kernel(const DevProblem P, const int* __restrict__ polLam, int nPol, int 
     double c2 = pu.chiI + (ds_uw * (1.0 / 3.0)) * dx_uw;
     double dtau_uw = ds_uw * (p0.chiI + pu.chiI + c1 + c2) * 0.25;
     // slopes over the upwind interval; they are also the one-sided derivatives at the first point
-    double slK[6], slS[4], dKu[6], dSu[4], Ku2[16];
+    double slK[6], slS[4], dKu[6], dSu[4];
     {
         const double r = 1.0 / dtau_uw;
 #pragma unroll
@@ -433,9 +437,6 @@ stokes_kernel(const DevProblem P, const int* __restrict__ polLam, int nPol, int 
 #pragma unroll
         for (int n = 0; n < 4; ++n)
             dSu[n] = slS[n] = (p0.S[n] - pu.S[n]) * r;
-        double Ku[16];
-        stokes_expand(pu.k6, Ku);
-        stokes_square(Ku, Ku2);
     }
     double ds_dw2 = 0.0, dtau_dw = 0.0, dx_dw = 0.0;
 #pragma unroll 1
@@ -482,9 +483,10 @@ stokes_kernel(const DevProblem P, const int* __restrict__ polLam, int nPol, int 
                 dS0[n] = steffen_r(wU, wD, slS[n], slSd[n]);
             }
         }
-        double Ku[16], K0[16], dKuM[16], dK0M[16], K02[16];
+        double Ku[16], K0[16], dKuM[16], dK0M[16], Ku2[16], K02[16];
         stokes_expand(pu.k6, Ku);
         stokes_expand(p0.k6, K0);
+        stokes_square(Ku, Ku2);
         stokes_expand(dKu, dKuM);
         stokes_expand(dK0, dK0M);
         stokes_square(K0, K02);
@@ -536,9 +538,6 @@ stokes_kernel(const DevProblem P, const int* __restrict__ polLam, int nPol, int 
             dKu[q] = dK0[q];
             slK[q] = slKd[q];
         }
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-            Ku2[q] = K02[q];
         dtau_uw = dtau_dw;
         ds_uw = ds_dw;
         ds_dw = ds_dw2;

@@ -10,6 +10,9 @@ rows=list(csv.DictReader(l for l in open('gpurun_out/${TAG}_kbench.csv') if l.st
 per=collections.OrderedDict()
 for r in rows:
     per.setdefault(r['ID'],{'name':r['Kernel Name'][:70]})[r['Metric Name']]=r['Metric Value']
+def num(v):
+    try: return float(v.replace(',',''))
+    except Exception: return 0.0
 agg=collections.OrderedDict()
 for i,m in per.items():
     f=lambda x: num(m.get(x,"0"))

@@ -1,6 +1,6 @@
 """Small driver for ncu / variant timing: a few device-resident Gamma iterations.
 
-    python tools/prof_c3.py <ncol> <niter> <c3|c2|c1> [check]
+    python tools/prof_c3.py <ncol> <niter> <c3|c2|c1|c5|deep> [check]
 
 Prints the median formal-solution kernel time; with `check`, also the parity of two
 iterations of a small problem against the C oracle (development aid)."""
@@ -34,6 +34,12 @@ if wl == 'c3':
     ctx = Context(p, upload=False)
     ctx.upload(capi.ALL_INPUTS & ~capi.PROFILE)
     ctx.update_deps(background=False, profiles_on_device=True)
+elif wl == 'c5':
+    p = synth.config_c5(ncol=ncol, with_profiles=False, alloc_phi=False)
+    ctx = Context(p, upload=False)
+    ctx.upload(capi.ALL_INPUTS & ~capi.PROFILE)
+    ctx.update_deps(background=False, profiles_on_device=True)
+    ctx.compute_polarised_profiles_device()
 elif wl == 'c1':
     p = synth.config_c1()
     ctx = Context(p)
@@ -50,8 +56,11 @@ else:
         ctx = Context(p)
 ts = []
 for it in range(nit):
-    ctx.fs_iter_device(want_dJ=False)
-    ctx.stat_eq_device()
+    if wl == 'c5':   # one J-updating full-Stokes formal solution
+        capi.check(ctx.lib.lwb200_formal_sol_full_stokes(ctx._h, 1, 0, None, None))
+    else:
+        ctx.fs_iter_device(want_dJ=False)
+        ctx.stat_eq_device()
     ctx.sync()
     ts.append(ctx.kernel_time_ms())
 ms = float(np.median(ts[1:] if len(ts) > 1 else ts))
