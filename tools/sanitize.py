@@ -41,6 +41,31 @@ ctx.single_stokes_fs(updateJ=False, upOnly=True)
 ctx.close()
 print('stokes ok', flush=True)
 
+# static atmosphere (ray-independent profiles: the shared-phase path of both ray kernels), 82 and 300 depths
+for nd in (None, 300):
+    p = synth.tiny_problem(ndepth=nd, nrays=3)
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices()
+        ctx.stat_equil()
+    ctx.close()
+print('static ok', flush=True)
+
+# the deep general kernel: hybrid PRD at 200 depths, every wavelength on request, more than 32 rays per wavelength
+p = synth.tiny_prd_problem(ncol=2, perturb=True, ndepth=200)
+p.configure_hprd()
+ctx = Context(p)
+ctx.formal_sol_gamma_matrices()
+ctx.prd_redistribute(maxIter=2, tol=1e-6)
+ctx.formal_sol_gamma_matrices(extraParams={'generalKernel': True})
+ctx.formal_sol()
+ctx.close()
+p = synth.tiny_problem(nrays=17, ncol=2, perturb=True)
+ctx = Context(p)
+ctx.formal_sol_gamma_matrices()
+ctx.close()
+print('deep general / many rays ok', flush=True)
+
 p = synth.config_c3(ncol=600, with_profiles=False, alloc_phi=False)
 ctx = Context(p, upload=False)
 ctx.upload(capi.ALL_INPUTS & ~capi.PROFILE)
