@@ -427,7 +427,11 @@ int build_plan(LwB200Context* c)
         }
     // wavelengths with more than two overlapping lines go to the general kernel
     // kinds 0..3: that many overlapping lines, moment kernel; 4: more, general kernel
-    auto kind_of = [&](int la) { return laNLines[la] > 3 ? 4 : laNLines[la]; };
+    // (the Gamma stage of the moment pipeline stages at most kGammaMaxEntries active transitions per wavelength:
+    // a wavelength with more -- far UV of a large atom set -- takes the general kernel as well)
+    auto kind_of = [&](int la) {
+        return (laNLines[la] > 3 || (int)active[la].size() > kGammaMaxEntries) ? 4 : laNLines[la];
+    };
 
     // per-transition wavelength tables
     std::vector<double> wlambdaTab(tabOff), alphaTab(tabOff, 0.0);

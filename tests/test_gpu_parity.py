@@ -1018,6 +1018,40 @@ def _overlap_problem(nlines, ndepth=None, prd=None):
     return synth.build_problem([a, b], nrays=3, perturb=True, ncol=2, ndepth=ndepth, prd=prd)
 
 
+def _many_continua_problem(ndepth=None):
+    """Two 20-level atoms whose 19 bound-free continua each all overlap below 100 nm: 38 active
+    transitions at those wavelengths."""
+    atoms = []
+    for name, mass, ab, e0 in (('Big', 12.0, 1e-4, 60000.0), ('Bag', 24.0, 4e-5, 58000.0)):
+        lev = [synth.Level(0.0, 2, 0)] + [synth.Level(e0 + 1500.0 * i, 2 + 2 * (i % 4), 0) for i in range(18)]
+        lev.append(synth.Level(100000.0, 1, 1))
+        top = len(lev) - 1
+        lines = [synth.LineSpec(1, 0, 2.0e8, 15, 4.0, 40.0), synth.LineSpec(5, 0, 5.0e7, 11, 3.0, 30.0)]
+        cont = [synth.ContSpec(top, i, 4.0e-22 * (1 + i % 3), 6, 60.0) for i in range(top)]
+        atoms.append(synth.ModelAtom(name, mass, ab, lev, lines, cont))
+    return synth.build_problem(atoms, nrays=3, perturb=True, ncol=2, ndepth=ndepth)
+
+
+@pytest.mark.parametrize('ndepth', [None, 160])
+def test_more_than_32_active_transitions_at_one_wavelength(ndepth):
+    """The Gamma stage of the moment pipeline stages at most 32 active transitions per wavelength; the far
+    UV of this atom set has 38, and those wavelengths go through the general kernel instead."""
+    p = _many_continua_problem(ndepth)
+    nact = np.zeros(p.Nspect, dtype=int)
+    for a in p.atoms:
+        for t in a.trans:
+            nact[t.Nblue:t.Nred] += 1
+    assert nact.max() > 32
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+        ctx.stat_equil()
+        oracle_iter(q, lambdaIterate=(it == 0))
+        assert_close(p, q)
+    ctx.close()
+
+
 @pytest.mark.parametrize('ndepth', [None, 200])
 def test_prd_line_overlapping_three_other_lines(ndepth):
     """A PRD line inside a blend of four lines: its wavelengths are beyond the moment pipeline, so the Gamma
