@@ -611,10 +611,12 @@ int build_plan(LwB200Context* c)
     {
         // beyond one warp per column: ray_kernel in multi-warp mode (4 depths per lane, up to 8 warps);
         // wavelengths of kind 4 (more than three overlapping lines, hybrid PRD) take fs_long_kernel
-        if (K > 1024)
-            return fail("Nspace > 1024 is not supported");
+        // beyond 1024 depths (up to 4096) the general kernel with up to 32 warps per column does everything
+        if (K > 4096)
+            return fail("Nspace > 4096 is not supported");
         if (fs_long_smem(maxNlevel, 32 * ((K + 127) / 128)) > smemLimit)
-            return fail("atom too large for the shared-memory scratch");
+            return fail(K > 1024 ? "Nspace > 1024 with an atom of this many levels is not supported (shared-memory scratch)"
+                                 : "atom too large for the shared-memory scratch");
         c->NCH = 4;
     }
 
@@ -1625,24 +1627,29 @@ int launch_fs_long(LwB200Context* c, int lambdaIterate, int upOnly, int storeDep
     if (!capturing)
         CU(cudaEventRecord(c->evK0, c->stream));
     const int fsMode = MODE == MODE_ITER ? c->stokesFsMode : (upOnly ? 3 : 1);
-    if (!c->forceDirect
+    const int K = c->prob.Nspace, threads = 32 * ((K + 127) / 128);
+    const bool big = K > 1024; // (the moment pipeline's kernels stop at 8 warps per column)
+    if (big && fsMode != 0 && MODE == MODE_ITER)
+        return fail("the full-Stokes formal solution is limited to Nspace <= 1024");
+    const bool prdPass = MODE == MODE_ITER && c->customLists; // (PRD sub-iteration: the whole spectrum, PRD rates only)
+    const bool all = (c->forceDirect && !prdPass) || (big && !prdPass);
+    if (!all && !big
         && launch_pipeline<4, SOLVER, true>(c, c->customLists ? c->prdPl : full_lists(c), lambdaIterate, storeDepth, fsMode))
         return 1;
     // the wavelengths the moment pipeline does not carry (more than three overlapping lines, hybrid PRD) --
-    // or, on request (LWB200_GENERAL_KERNEL), all of them -- go through the general multi-warp kernel
-    const bool all = c->forceDirect;
-    const bool prdPass = MODE == MODE_ITER && c->customLists && !all; // (PRD sub-iteration: the whole spectrum, PRD rates only)
+    // or, on request (LWB200_GENERAL_KERNEL) and beyond 1024 depths, all of them -- go through the general
+    // multi-warp kernel
     const bool maskPass = prdPass && !c->prdPl.directPrdOnly;         // (angle-averaged: the masked wavelengths)
-    const int nTiles = all ? c->nListAll : (maskPass ? c->prdPl.nDirectPrd : c->nListDirect);
+    const bool allTiles = all || big;
+    const int nTiles = allTiles ? c->nListAll : (maskPass ? c->prdPl.nDirectPrd : c->nListDirect);
     if (nTiles > 0)
     {
-        auto kern = fs_long_kernel<SOLVER>;
+        auto kern = big ? fs_long_kernel<SOLVER, true> : fs_long_kernel<SOLVER, false>;
         if (set_smem_attr(kern, c->device))
             return 1;
-        const int K = c->prob.Nspace, threads = 32 * ((K + 127) / 128);
         dim3 grid(nTiles, launch_columns(c));
         kern<<<grid, threads, fs_long_smem(c->P.maxNlevel, threads), c->stream>>>(
-            c->P, all ? c->dListAll.p : (maskPass ? c->prdPl.directPrd : c->dListDirect.p), prdPass ? 0 : c->laLo,
+            c->P, allTiles ? c->dListAll.p : (maskPass ? c->prdPl.directPrd : c->dListDirect.p), prdPass ? 0 : c->laLo,
             prdPass ? c->prob.Nspect : c->laHi, lambdaIterate, upOnly, storeDepth, maskPass ? 2 : (prdPass ? 1 : 0),
             MODE == MODE_ITER ? 0 : 1, maskPass ? c->prdPl.laMask : nullptr);
         CU(cudaGetLastError());
@@ -1810,8 +1817,8 @@ int lwb200_create(const LwB200Problem* problem, int device, LwB200Context** out)
         return fail("lwb200_create: ABI version mismatch");
     if (problem->Nspace < 3 || problem->Nrays < 1 || problem->Nspect < 1 || problem->Ncol < 1 || problem->Natom < 1)
         return fail("lwb200_create: bad dimensions");
-    if (problem->Nspace > 1024)
-        return fail("lwb200_create: Nspace > 1024 is not supported");
+    if (problem->Nspace > 4096)
+        return fail("lwb200_create: Nspace > 4096 is not supported");
     if (problem->formalSolver < 0 || problem->formalSolver > 2)
         return fail("lwb200_create: formalSolver must be 0 (linear), 1 (besser) or 2 (bezier3)");
     int ndev = 0;
@@ -2853,7 +2860,7 @@ int lwb200_fs_iter(LwB200Context* c, uint32_t flags, double* dJMax, int64_t* dJM
     if (!c->nstarUploaded)
         return fail("lwb200_fs_iter: inputs have not been uploaded (lwb200_upload)");
     const int storeDepth = (flags & LWB200_STORE_DEPTH) ? 1 : 0;
-    c->forceDirect = (flags & LWB200_GENERAL_KERNEL) != 0;
+    c->forceDirect = (flags & LWB200_GENERAL_KERNEL) != 0 || c->prob.Nspace > 1024; // (beyond 1024 depths: always)
     // (a wavelength shard or a masked stack owns only part of J / I: no wholesale early copy there)
     c->fetchEarly = (flags & LWB200_FETCH_EARLY) != 0 && !c->forceDirect && c->outputsPinned && c->nActiveCol < 0
                     && c->laLo == 0 && c->laHi == c->prob.Nspect;

@@ -1,5 +1,5 @@
-// lwb200_fslong.cuh -- the general per-ray kernel for deep atmospheres (128 < Nspace <= 1024):
-// fs_long_kernel.
+// lwb200_fslong.cuh -- the general per-ray kernel for deep atmospheres (128 < Nspace <= 1024; with BIG,
+// as the only formal-solution kernel, up to 4096): fs_long_kernel.
 //
 // What fs_kernel (lwb200_kernels.cuh) does for one warp per wavelength -- any number of overlapping lines,
 // hybrid PRD (rho interpolated per ray, LwTransition.hpp:115-130; the formal solution scatters into JRest,
@@ -21,14 +21,16 @@ namespace lwb200
 {
 inline size_t fs_long_smem(int maxNlevel, int threads) { return (size_t)2 * maxNlevel * threads * sizeof(double); }
 
-template <int SOLVER>
-__global__ void __launch_bounds__(256, 1)
+// BIG: up to 32 warps (1024 < Nspace <= 4096) at 64 registers per thread -- the whole iteration of such a column
+// runs here (a functional path: the moment pipeline's kernels are sized for <= 8 warps per column).
+template <int SOLVER, bool BIG = false>
+__global__ void __launch_bounds__(BIG ? 1024 : 256, 1)
 fs_long_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int laHi, int lambdaIterate,
                int upOnly, int storeDepth, int prdOnly, int fsOnly, const unsigned char* __restrict__ laMask)
 {
     constexpr int NCH = 4;
     extern __shared__ double smem[];     // [2][maxNlevel][blockDim.x]: chi_atom / U_atom per level, one column per thread
-    __shared__ double commBuf[7 * 8];
+    __shared__ double commBuf[7 * (BIG ? 32 : 8)];
     __shared__ double endBuf[4][2];      // chi and S of the current ray at depths 0, 1, K - 2, K - 1
     const int K = P.K, M = P.M, L = P.L;
     const int tile = tileList[blockIdx.x];

@@ -236,8 +236,48 @@ def test_many_rays_per_wavelength(nrays):
     ctx.close()
 
 
+@pytest.mark.parametrize('ndepth,solver', [(1025, capi.FS_BEZIER3), (1500, capi.FS_BESSER), (2100, capi.FS_BEZIER3),
+                                           (4096, capi.FS_LINEAR)])
+def test_very_deep_atmospheres_general_kernel_with_up_to_32_warps(ndepth, solver):
+    """1024 < Nspace <= 4096: the general multi-warp kernel (up to 32 warps per column) is the only formal-solution
+    kernel; Gamma iteration, stat-eq and the plain formal solution against the oracle."""
+    p = synth.tiny_problem(ndepth=ndepth, nrays=2, ncol=2, perturb=True, formal_solver=solver)
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+        ctx.stat_equil()
+        oracle_iter(q, lambdaIterate=(it == 0))
+        assert_close(p, q)
+    p.I[:] = -1.0
+    ctx.formal_sol(upOnly=False)
+    for c in range(q.Ncol):
+        oraclelib.OracleContext(q, col=c).formal_sol(upOnly=False)
+    assert rel_err(p.I, q.I) <= TOL
+    ctx.close()
+
+
+def test_very_deep_prd_atmosphere():
+    """Angle-averaged PRD at 1300 depths: Gamma iteration and the PRD sub-iterations through the general kernel."""
+    p = synth.tiny_prd_problem(ncol=2, perturb=True, ndepth=1300)
+    q = p.clone()
+    ctx = Context(p)
+    ctx.formal_sol_gamma_matrices()
+    upd = ctx.prd_redistribute(maxIter=2, tol=1e-6)
+    q.prefill_gamma()
+    dRho = []
+    for c in range(q.Ncol):
+        o = oraclelib.OracleContext(q, col=c)
+        o.fs_iter()
+        dRho.append(o.redistribute_prd(maxIter=2, tol=1e-6, nlines=2)['dRho'][:4])
+    assert np.allclose(np.asarray(upd.dRho), np.max(dRho, axis=0), rtol=TOL, atol=1e-12)
+    e = compare_problems(p, q)
+    assert e['I'] <= TOL and e['J'] <= TOL and e['R'] <= TOL, e
+    ctx.close()
+
+
 def test_too_many_depths_fails_loudly():
-    p = synth.tiny_problem(ndepth=1100, nrays=2, with_profiles=False)
+    p = synth.tiny_problem(ndepth=4200, nrays=2, with_profiles=False)
     with pytest.raises(capi.LwB200Error):
         Context(p)
 
