@@ -246,6 +246,8 @@ struct LwB200Context
     DevBuf<double> nrScratch, nrDC, nrPrev, nrStages, nrBgNe, neDev;
     DevBuf<NrAtom> nrAtoms;
     DevBuf<int> prdIdx, dKindLamPrd[4], dListMomentPrd, dListDirectPrd;
+    DevBuf<double> statEqScratch;   // stat_eq_kernel<64>: matrices of atoms with more than 32 levels
+    bool generalViaLong = false;    // the general kernel's shared-memory tile does not fit: fs_long_kernel (REDs) instead
     DevBuf<unsigned char> dPrdMask;
     std::vector<long long> atomCOff;
     long long cTot = 0;
@@ -504,7 +506,7 @@ int build_plan(LwB200Context* c)
             if (c->hprdPlanMask[la])
                 c->laKind[la] = 4;
     }
-    int maxSlots = 1;
+    int maxSlots = 1, maxSlotsGeneral = 1;
     size_t maxTileEntries = 1;
     c->tileLa.push_back(0);
     c->tileSlotOff.push_back(0);
@@ -526,7 +528,7 @@ int build_plan(LwB200Context* c)
                     break;
                 // (the [slot][4][depth] tile of fs_kernel; deep atmospheres use fs_long_kernel, which keeps none)
                 if (K <= 128 && (int)(slots.size() + add.size()) * 4 * (size_t)KP * sizeof(double) + scratchBytes > smemLimit)
-                    return fail("too many transitions active at one wavelength for shared memory");
+                    c->generalViaLong = true; // (fs_kernel's tile of partial sums does not fit: fs_long_kernel accumulates with REDs)
                 slots.insert(slots.end(), add.begin(), add.end());
                 ++pos;
             }
@@ -593,19 +595,22 @@ int build_plan(LwB200Context* c)
             for (int g : slots)
                 c->tileSlotTrans.push_back(g);
             c->tileSlotOff.push_back((int)c->tileSlotTrans.size());
-            maxSlots = std::max(maxSlots, (int)slots.size());
+            (general ? maxSlotsGeneral : maxSlots) = std::max(general ? maxSlotsGeneral : maxSlots, (int)slots.size());
         }
     }
     laOff[L] = (int)entries.size();
     c->Ntile = (int)c->tileLa.size() - 1;
-    c->smemBytes = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchFs;
+    // (fs_kernel -- the general tiles, or every tile on request -- needs room for the largest tile of all, or leaves
+    // the general tiles to fs_long_kernel; both shared-memory kernels lay their scratch behind P.maxSlots slots)
+    if (!c->generalViaLong)
+        maxSlots = std::max(maxSlots, maxSlotsGeneral);
     c->smemGamma = (size_t)maxSlots * 4 * RS * sizeof(double) + scratchGamma;
+    c->smemBytes = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchFs;
     c->scratchGamma = scratchGamma;
     if (const char* e = std::getenv("LWB200_GAMMA_DIRECT")) // tuning aid: 0 never, 1 always
         c->gammaDirect = std::atoi(e);
     c->KC = KC;
-    if (c->smemGamma > smemLimit)
-        return fail("wavelength tile too large for shared memory");
+    // (c->smemGamma is what the first-generation gamma_kernel needs: checked where that kernel is selected)
     c->NCH = (K + 31) / 32;
     if (K > 128)
     {
@@ -700,6 +705,8 @@ int build_plan(LwB200Context* c)
         c->gammaV1 = false;
         if (const char* e = std::getenv("LWB200_GAMMA_V1"))
             c->gammaV1 = std::atoi(e) != 0;
+        if (c->gammaV1 && c->smemGamma > smemLimit)
+            return fail("wavelength tile too large for shared memory (first-generation Gamma stage)");
         if (const char* e = std::getenv("LWB200_RAY_V1"))
             c->rayV1 = std::atoi(e) != 0;
         if (const char* e = std::getenv("LWB200_GAMMA_WARPS"))
@@ -1430,6 +1437,10 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
             {
                 // this kind's share of the Gamma stage follows its rays on the same stream
                 CU(cudaEventRecord(c->evRaysKind[q], s));
+                if (c->scratchGamma > 48 * 1024 // (atoms of more than 36 levels: opt in to more shared memory)
+                    && (set_smem_attr(gamma_direct_kernel<0>, c->device) || set_smem_attr(gamma_direct_kernel<1>, c->device)
+                        || set_smem_attr(gamma_direct_kernel<2>, c->device) || set_smem_attr(gamma_direct_kernel<3>, c->device)))
+                    return 1;
                 const dim3 gg(nLam, nb, (K + c->KC - 1) / c->KC);
                 switch (q)
                 {
@@ -1560,6 +1571,24 @@ static bool stream_is_capturing(cudaStream_t s)
     return st != cudaStreamCaptureStatusNone;
 }
 
+// the general multi-warp kernel over a list of tiles (fs_long_kernel: any depth up to 4096, partial sums by RED)
+template <int SOLVER>
+int launch_general_long(LwB200Context* c, const int* tiles, int nTiles, int laLo, int laHi, int lambdaIterate, int upOnly,
+                        int storeDepth, int prdOnly, int fsOnly, const unsigned char* mask)
+{
+    const int K = c->prob.Nspace, threads = 32 * ((K + 127) / 128);
+    const bool big = threads > 256;
+    auto kern = big ? fs_long_kernel<SOLVER, true> : fs_long_kernel<SOLVER, false>;
+    if (set_smem_attr(kern, c->device))
+        return 1;
+    dim3 grid(nTiles, launch_columns(c));
+    kern<<<grid, threads, fs_long_smem(c->P.maxNlevel, threads), c->stream>>>(c->P, tiles, laLo, laHi, lambdaIterate, upOnly,
+                                                                             storeDepth, prdOnly, fsOnly, mask);
+    CU(cudaGetLastError());
+    c->lastLaunches += 1;
+    return 0;
+}
+
 template <int NCH, int SOLVER, int MODE>
 int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
 {
@@ -1580,7 +1609,15 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
             return 1;
         const bool maskPass = c->customLists && !c->prdPl.directPrdOnly; // angle-averaged PRD sub-iteration
         const int nDirect = maskPass ? c->prdPl.nDirectPrd : c->nListDirect;
-        if (nDirect > 0)
+        if (nDirect > 0 && c->generalViaLong)
+        {
+            const bool prdPass = c->customLists;
+            if (launch_general_long<SOLVER>(c, maskPass ? c->prdPl.directPrd : c->dListDirect.p, nDirect, prdPass ? 0 : c->laLo,
+                                            prdPass ? c->prob.Nspect : c->laHi, lambdaIterate, 0, storeDepth,
+                                            maskPass ? 2 : (prdPass ? 1 : 0), 0, maskPass ? c->prdPl.laMask : nullptr))
+                return 1;
+        }
+        else if (nDirect > 0)
         {
             auto kern = fs_kernel<NCH, SOLVER, MODE_ITER>;
             if (set_smem_attr(kern, c->device))
@@ -1594,6 +1631,12 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }
+    }
+    else if (c->nListAll > 0 && c->generalViaLong)
+    {
+        if (launch_general_long<SOLVER>(c, c->dListAll.p, c->nListAll, c->laLo, c->laHi, lambdaIterate, upOnly, storeDepth, 0,
+                                        MODE == MODE_ITER ? 0 : 1, nullptr))
+            return 1;
     }
     else if (c->nListAll > 0)
     {
@@ -1627,7 +1670,7 @@ int launch_fs_long(LwB200Context* c, int lambdaIterate, int upOnly, int storeDep
     if (!capturing)
         CU(cudaEventRecord(c->evK0, c->stream));
     const int fsMode = MODE == MODE_ITER ? c->stokesFsMode : (upOnly ? 3 : 1);
-    const int K = c->prob.Nspace, threads = 32 * ((K + 127) / 128);
+    const int K = c->prob.Nspace;
     const bool big = K > 1024; // (the moment pipeline's kernels stop at 8 warps per column)
     if (big && fsMode != 0 && MODE == MODE_ITER)
         return fail("the full-Stokes formal solution is limited to Nspace <= 1024");
@@ -1642,19 +1685,12 @@ int launch_fs_long(LwB200Context* c, int lambdaIterate, int upOnly, int storeDep
     const bool maskPass = prdPass && !c->prdPl.directPrdOnly;         // (angle-averaged: the masked wavelengths)
     const bool allTiles = all || big;
     const int nTiles = allTiles ? c->nListAll : (maskPass ? c->prdPl.nDirectPrd : c->nListDirect);
-    if (nTiles > 0)
-    {
-        auto kern = big ? fs_long_kernel<SOLVER, true> : fs_long_kernel<SOLVER, false>;
-        if (set_smem_attr(kern, c->device))
-            return 1;
-        dim3 grid(nTiles, launch_columns(c));
-        kern<<<grid, threads, fs_long_smem(c->P.maxNlevel, threads), c->stream>>>(
-            c->P, allTiles ? c->dListAll.p : (maskPass ? c->prdPl.directPrd : c->dListDirect.p), prdPass ? 0 : c->laLo,
-            prdPass ? c->prob.Nspect : c->laHi, lambdaIterate, upOnly, storeDepth, maskPass ? 2 : (prdPass ? 1 : 0),
-            MODE == MODE_ITER ? 0 : 1, maskPass ? c->prdPl.laMask : nullptr);
-        CU(cudaGetLastError());
-        c->lastLaunches += 1;
-    }
+    if (nTiles > 0
+        && launch_general_long<SOLVER>(c, allTiles ? c->dListAll.p : (maskPass ? c->prdPl.directPrd : c->dListDirect.p), nTiles,
+                                       prdPass ? 0 : c->laLo, prdPass ? c->prob.Nspect : c->laHi, lambdaIterate, upOnly,
+                                       storeDepth, maskPass ? 2 : (prdPass ? 1 : 0), MODE == MODE_ITER ? 0 : 1,
+                                       maskPass ? c->prdPl.laMask : nullptr))
+        return 1;
     if (!capturing)
     {
         CU(cudaEventRecord(c->evK1, c->stream));
@@ -1836,10 +1872,10 @@ int lwb200_create(const LwB200Problem* problem, int device, LwB200Context** out)
     for (int a = 0; a < problem->Natom; ++a)
     {
         const LwB200Atom& at = problem->atoms[a];
-        if (at.Nlevel < 1 || at.Nlevel > 32)
+        if (at.Nlevel < 1 || at.Nlevel > 64)
         {
             delete c;
-            return fail("lwb200_create: Nlevel must be in [1, 32]");
+            return fail("lwb200_create: Nlevel must be in [1, 64]");
         }
         c->atomTrans[a].assign(at.trans, at.trans + at.Ntrans);
         c->atoms[a].trans = c->atomTrans[a].data();
@@ -2981,9 +3017,18 @@ static int population_update(LwB200Context* c, int32_t atom, int32_t kStart, int
             else if (maxN <= 16)
                 stat_eq_kernel<16><<<grid_for(total, 64), 64, 0, c->stream>>>(
                     c->P, atom, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, dSingular, nOldDev, dt);
-            else
+            else if (maxN <= 32)
                 stat_eq_kernel<32><<<grid_for(total, 64), 64, 0, c->stream>>>(
                     c->P, atom, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, dSingular, nOldDev, dt);
+            else
+            {
+                // 33..64 levels: matrices in a global scratch block, one slice per thread of a bounded grid
+                const int blocks = std::min(grid_for(total, 64), 128);
+                if (!c->statEqScratch.p && c->statEqScratch.alloc((size_t)blocks * 64 * 2 * 64 * 64))
+                    return fail("out of device memory (stat-eq scratch)");
+                stat_eq_kernel<64><<<blocks, 64, 0, c->stream>>>(c->P, atom, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p,
+                                                               dSingular, nOldDev, dt, c->statEqScratch.p);
+            }
             CU(cudaGetLastError());
             c->lastLaunches += 1;
         }

@@ -953,11 +953,13 @@ __device__ __noinline__ bool population_solve_small(const double* __restrict__ g
 // nOld != nullptr: time_dependent_update_impl (UpdatePopulations.cpp:120-151) instead -- the
 // backward-Euler system (1 - Gamma dt) n = nOld of the same atom, depth by depth, through the
 // same solve_lin_eq.  nOld is [Ncol][Nlevel][K] of atom atomSel.
+// MAXN = 64 (atoms of 33..64 levels): the matrix and its copy do not live in per-thread local memory (64 KB per
+// thread, reserved for every resident thread of the device) but in a global scratch block of the launch's threads.
 template <int MAXN>
 __global__ void stat_eq_kernel(const DevProblem P, int atomSel, int kStart, int kEnd,
                                const double* __restrict__ gamma, double* __restrict__ n,
                                const double* __restrict__ nTotal, int* __restrict__ nSingular,
-                               const double* __restrict__ nOld, double dt)
+                               const double* __restrict__ nOld, double dt, double* __restrict__ scratch = nullptr)
 {
     // atomSel >= 0: that atom; atomSel < 0: every active atom in ONE launch (the systems of
     // different atoms are independent; in 1D there are only Nspace of them per atom)
@@ -994,7 +996,15 @@ __global__ void stat_eq_kernel(const DevProblem P, int atomSel, int kStart, int 
                 atomicAdd_system(nSingular, 1); // may be mapped host memory
             continue;
         }
-        double A[MAXN * MAXN], ACopy[MAXN * MAXN], b[MAXN], bCopy[MAXN], res[MAXN];
+        constexpr int NLOC = MAXN > 32 ? 1 : MAXN * MAXN;
+        double ALoc[NLOC], ACopyLoc[NLOC], b[MAXN], bCopy[MAXN], res[MAXN];
+        double* A = ALoc;
+        double* ACopy = ACopyLoc;
+        if (MAXN > 32)
+        {
+            A = scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2 * MAXN * MAXN;
+            ACopy = A + MAXN * MAXN;
+        }
         int index[MAXN];
         int iElim = 0;
         double nMax = 0.0;

@@ -1072,6 +1072,43 @@ def _many_continua_problem(ndepth=None):
     return synth.build_problem(atoms, nrays=3, perturb=True, ncol=2, ndepth=ndepth)
 
 
+def _large_atom_problem(nlev=40, ndepth=None):
+    """An atom of `nlev` levels (more than the 32 the per-thread LU of the population solve holds) whose
+    bound-free continua all overlap below 100 nm, and a small second atom."""
+    lev = [synth.Level(0.0, 2, 0)] + [synth.Level(55000.0 + 600.0 * i, 2 + 2 * (i % 4), 0) for i in range(nlev - 2)]
+    lev.append(synth.Level(100000.0, 1, 1))
+    top = len(lev) - 1
+    lines = [synth.LineSpec(1, 0, 2.0e8, 15, 4.0, 40.0), synth.LineSpec(7, 0, 5.0e7, 11, 3.0, 30.0),
+             synth.LineSpec(9, 1, 3.0e7, 11, 3.0, 30.0)]
+    cont = [synth.ContSpec(top, i, 4.0e-22 * (1 + i % 3), 5, 70.0) for i in range(top)]
+    big = synth.ModelAtom('Huge', 12.0, 1e-4, lev, lines, cont)
+    lev2 = [synth.Level(0.0, 2, 0), synth.Level(60010.0, 6, 0), synth.Level(90000.0, 1, 1)]
+    small = synth.ModelAtom('Oth', 20.0, 3e-5, lev2, [synth.LineSpec(1, 0, 1.0e8, 21, 5.0, 80.0)],
+                            [synth.ContSpec(2, 0, 5.0e-22, 8, 50.0), synth.ContSpec(2, 1, 8.0e-22, 8, 80.0)])
+    return synth.build_problem([big, small], nrays=3, perturb=True, ncol=2, ndepth=ndepth)
+
+
+@pytest.mark.parametrize('nlev,ndepth', [(40, None), (64, None), (40, 150)])
+def test_atoms_of_more_than_32_levels(nlev, ndepth):
+    """33..64 levels: the population solve keeps its matrices in a global scratch block; the 40+ overlapping
+    continua of the far UV neither fit the Gamma stage's entry table nor the general kernel's shared-memory
+    tile of partial sums, so those wavelengths accumulate with REDs (fs_long_kernel, at any depth)."""
+    p = _large_atom_problem(nlev, ndepth)
+    q = p.clone()
+    ctx = Context(p)
+    for it in range(2):
+        ctx.formal_sol_gamma_matrices(lambdaIterate=(it == 0))
+        ctx.stat_equil()
+        oracle_iter(q, lambdaIterate=(it == 0))
+        assert_close(p, q)
+    # every wavelength through the general kernel on request, and the plain formal solution
+    ctx.formal_sol_gamma_matrices(extraParams={'generalKernel': True})
+    oracle_iter(q, stat_eq=False)
+    e = compare_problems(p, q)
+    assert e['I'] <= TOL and e['J'] <= TOL and e['Gamma'] <= TOL and e['R'] <= TOL, e
+    ctx.close()
+
+
 @pytest.mark.parametrize('ndepth', [None, 160])
 def test_more_than_32_active_transitions_at_one_wavelength(ndepth):
     """The Gamma stage of the moment pipeline stages at most 32 active transitions per wavelength; the far
