@@ -3505,8 +3505,8 @@ int lwb200_nr_post_update(LwB200Context* c, const LwB200NrUpdate* u, int32_t kSt
         atoms.push_back(na);
         Neqn += at.Nlevel;
     }
-    if (Neqn > 64)
-        return fail("lwb200_nr_post_update: more than 63 levels in the coupled system");
+    if (Neqn > 160)
+        return fail("lwb200_nr_post_update: more than 159 levels in the coupled system");
     if (u->timeDependent && !u->nPrev)
         return fail("lwb200_nr_post_update: timeDependent without nPrev");
     // inputs: C of every atom with one (same packing as the PRD path), dC, nPrev, stages, backgroundNe, ne
@@ -3559,8 +3559,13 @@ int lwb200_nr_post_update(LwB200Context* c, const LwB200NrUpdate* u, int32_t kSt
             c->P, c->nrAtoms.p, (int)atoms.size(), Neqn, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, c->cmat.p,
             c->cTot, c->nrDC.p, dcTot, c->nrPrev.p, prevTot, c->nrStages.p, c->nrBgNe.p, c->neDev.p,
             u->timeDependent ? 1 : 0, u->dt, u->crswVal, c->nrScratch.p, c->dSingular.p);
-    else
+    else if (Neqn <= 64)
         nr_update_kernel<64><<<grid_for(total, 64), 64, 0, s>>>(
+            c->P, c->nrAtoms.p, (int)atoms.size(), Neqn, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, c->cmat.p,
+            c->cTot, c->nrDC.p, dcTot, c->nrPrev.p, prevTot, c->nrStages.p, c->nrBgNe.p, c->neDev.p,
+            u->timeDependent ? 1 : 0, u->dt, u->crswVal, c->nrScratch.p, c->dSingular.p);
+    else
+        nr_update_kernel<160><<<grid_for(total, 64), 64, 0, s>>>(
             c->P, c->nrAtoms.p, (int)atoms.size(), Neqn, kStart, kEnd, c->gamma.p, c->n.p, c->nTotal.p, c->cmat.p,
             c->cTot, c->nrDC.p, dcTot, c->nrPrev.p, prevTot, c->nrStages.p, c->nrBgNe.p, c->neDev.p,
             u->timeDependent ? 1 : 0, u->dt, u->crswVal, c->nrScratch.p, c->dSingular.p);

@@ -805,11 +805,14 @@ int lwo_formal_sol(const LwB200Problem* p, int col, int upOnly)
 }
 
 /* ------------------------------------------------------------------------ */
+/* largest linear system of the restatement (the reference allocates its work arrays to size) */
+#define LWO_MAX_SYSTEM 256
+
 /* lu_decompose, LuSolve.cpp:8-70.  Returns 1 for the "Singular Matrix" throw. */
 static int lu_decompose(int N, double* A, int* index)
 {
     const double Tiny = 1e-20;
-    double vv[64];
+    double vv[LWO_MAX_SYSTEM];
     for (int i = 0; i < N; ++i)
     {
         double big = 0.0;
@@ -889,17 +892,22 @@ static void lu_backsub(int N, const double* A, const int* index, double* b)
 /* solve_lin_eq, LuSolve.cpp:103-133 */
 int lwo_solve_lin_eq(int N, double* A, double* b, int improve)
 {
-    if (N > 64)
+    if (N > LWO_MAX_SYSTEM)
         return 2;
-    double ACopy[64 * 64], bCopy[64], residual[64];
-    int index[64];
+    double ACopySmall[64 * 64], bCopy[LWO_MAX_SYSTEM], residual[LWO_MAX_SYSTEM];
+    double* ACopy = N <= 64 ? ACopySmall : (double*)malloc(sizeof(double) * N * N);
+    int index[LWO_MAX_SYSTEM];
     if (improve)
     {
         memcpy(ACopy, A, sizeof(double) * N * N);
         memcpy(bCopy, b, sizeof(double) * N);
     }
     if (lu_decompose(N, A, index))
+    {
+        if (ACopy != ACopySmall)
+            free(ACopy);
         return 1;
+    }
     lu_backsub(N, A, index, b);
     if (improve)
     {
@@ -911,6 +919,8 @@ int lwo_solve_lin_eq(int N, double* A, double* b, int improve)
         for (int i = 0; i < N; ++i)
             b[i] += residual[i];
     }
+    if (ACopy != ACopySmall)
+        free(ACopy);
     return 0;
 }
 

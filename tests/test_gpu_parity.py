@@ -603,6 +603,26 @@ def test_nr_post_update_matches_oracle(timeDep, useDC):
     ctx.close()
 
 
+def test_nr_post_update_with_more_than_63_coupled_levels():
+    """The charge-conserving Newton-Raphson step of four 20-level atoms: 81 unknowns per depth."""
+    from tests.test_oracle import nr_case
+    p = _many_continua_problem(natoms=4)
+    assert sum(a.Nlevel for a in p.atoms) + 1 == 81
+    q = p.clone()
+    ctx = Context(p)
+    ctx.formal_sol_gamma_matrices()
+    oracle_iter(q, stat_eq=False)
+    idx, bg, dC, nPrev = nr_case(q, False, True)
+    ctx.nr_post_update(idx, dC, bg)
+    upd, keep = capi.make_nr_update(idx, bg, dC=dC, nPrev=None, dt=0.05, crswVal=1.0)
+    for c in range(q.Ncol):
+        oraclelib.OracleContext(q, col=c).nr_post_update(upd)
+    for a, b in zip(p.atoms, q.atoms):
+        assert rel_err(a.n, b.n) <= 1e-6
+    assert rel_err(p.ne, q.ne) <= 1e-6
+    ctx.close()
+
+
 def test_time_dependent_update_matches_oracle():
     """Backward-Euler population step (time_dependent_update_impl) on a perturbed two-column stack."""
     p = synth.tiny_problem(ncol=2, perturb=True)
@@ -1058,11 +1078,12 @@ def _overlap_problem(nlines, ndepth=None, prd=None):
     return synth.build_problem([a, b], nrays=3, perturb=True, ncol=2, ndepth=ndepth, prd=prd)
 
 
-def _many_continua_problem(ndepth=None):
-    """Two 20-level atoms whose 19 bound-free continua each all overlap below 100 nm: 38 active
+def _many_continua_problem(ndepth=None, natoms=2):
+    """Two (or more) 20-level atoms whose 19 bound-free continua each all overlap below 100 nm: 38 active
     transitions at those wavelengths."""
     atoms = []
-    for name, mass, ab, e0 in (('Big', 12.0, 1e-4, 60000.0), ('Bag', 24.0, 4e-5, 58000.0)):
+    for name, mass, ab, e0 in (('Big', 12.0, 1e-4, 60000.0), ('Bag', 24.0, 4e-5, 58000.0), ('Bog', 28.0, 3e-5, 57000.0),
+                               ('Bug', 32.0, 2e-5, 59000.0))[:natoms]:
         lev = [synth.Level(0.0, 2, 0)] + [synth.Level(e0 + 1500.0 * i, 2 + 2 * (i % 4), 0) for i in range(18)]
         lev.append(synth.Level(100000.0, 1, 1))
         top = len(lev) - 1
