@@ -695,7 +695,7 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
         'e2e': e2e,
         'gpu_launches': launches,
         'parity_check': parity,
-        'roofline': {'bound': 'hbm', 'kernel': 'continuum_kernel + ray_kernel<NL=0..3> + gamma_kernel (one launch set per iteration)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+        'roofline': {'bound': 'hbm', 'kernel': ('stokes_kernel + ray_smem_kernel<NL=0..3> (one J-updating full-Stokes pass)' if stokes else 'continuum_table_kernel + ray_smem_kernel<NL=0..3> (ray_kernel<..,MULTI> beyond 128 depths) + gamma_tile_kernel / gamma_direct_kernel (one launch set per iteration; dominant: the ray kernel, 58 % of it)'), 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                      'alg_bytes_per_launch': alg_bytes, 'kernel_ms': kms,
                      'kernel_share_of_step': kms / ms_per_step,
