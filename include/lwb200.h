@@ -77,7 +77,7 @@ typedef struct LwB200Transition {
 /* One atom (Source/LwAtom.hpp:42-80).  detailedStatic atoms contribute
  * opacity/emissivity and get rates but no Gamma (ctx.detailedAtoms). */
 typedef struct LwB200Atom {
-    int32_t Nlevel;
+    int32_t Nlevel;          /* 1 .. 64 */
     int32_t Ntrans;
     int32_t detailedStatic;
     int32_t reserved;
@@ -124,7 +124,8 @@ typedef struct LwB200HybridPrd {
 typedef struct LwB200Problem {
     int32_t abiVersion;    /* LWB200_ABI_VERSION */
     int32_t Ncol;
-    int32_t Nspace;
+    int32_t Nspace;        /* 3 .. 4096 (<= 128: one warp per column; <= 1024: up to 8 warps; beyond: the general
+                              kernel with up to 32 warps) */
     int32_t Nrays;
     int32_t Nspect;
     int32_t Natom;         /* active + detailed-static atoms */
