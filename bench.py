@@ -388,6 +388,36 @@ def stokes_spot_check(ctx, problem, columns, col0, step, ncheck=4, tol=1e-9):
             'tol': {'I': tol, 'J': tol, 'Q, U, V at polarised wavelengths (relative to max I)': tol}}
 
 
+def prd_spot_check(ctx, problem, step, tol=1e-9):
+    """parity_spot_check for the PRD workload (one 1D atmosphere): J, the populations and rho of the PRD lines are
+    read from the device, ONE more step (Gamma iteration + PRD sub-iterations) runs there, and its I, J, rho and
+    rates are compared with the oracle's formal solution + redistribute_prd_lines from that state."""
+    import torch
+    from oracle import oraclelib
+    from tests.util import rel_err
+    torch.cuda.synchronize()
+    ctx.download(capi.JBAR | capi.POPS | capi.PRD)
+    q = problem.clone()
+    step()
+    torch.cuda.synchronize()
+    ctx.download(capi.ITER_OUTPUTS | capi.PRD)
+    nprd = sum(1 for a in q.atoms for t_ in a.trans if t_.rhoPrd is not None)
+    q.prefill_gamma()
+    o = oraclelib.OracleContext(q)
+    o.fs_iter()
+    o.redistribute_prd(maxIter=3, tol=1e-2, nlines=nprd)
+    err = {'I': rel_err(problem.I, q.I), 'J': rel_err(problem.J, q.J), 'rho': 0.0, 'R': 0.0}
+    for a, b in zip(problem.atoms, q.atoms):
+        for ta, tb in zip(a.trans, b.trans):
+            if ta.rhoPrd is not None:
+                err['rho'] = max(err['rho'], rel_err(ta.rhoPrd, tb.rhoPrd))
+            err['R'] = max(err['R'], rel_err(ta.Rij, tb.Rij), rel_err(ta.Rji, tb.Rji))
+    ok = all(e <= tol for e in err.values())
+    return {'ok': bool(ok), 'against': 'oracle/lw_oracle.c formal solution + redistribute_prd_lines (bit-identical to the '
+            'reference) from the same device state, one untimed step after the timed region',
+            'max_rel_err': err, 'tol': {k: tol for k in err}}
+
+
 def plugin_e2e(problem, steps):
     """e2e through the REAL drop-in boundary for a 1D atmosphere: the reference's own compiled core
     (oracle/_ref/liblwref.so = Lightweaver's C++ `formal_sol_gamma_matrices` / `stat_eq` entry points) loads
@@ -558,9 +588,11 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
 
     # ---- untimed parity spot check of the state just timed
     parity = None
-    if not with_prd:
+    if True:
         try:
-            if stokes:
+            if with_prd:
+                parity = prd_spot_check(ctx, problem, step)
+            elif stokes:
                 parity = stokes_spot_check(ctx, problem, columns, col0, step)
             else:
                 parity = parity_spot_check(ctx, problem, workload, columns, col0, step, laRange=laRange, ranges=ranges,
