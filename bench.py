@@ -85,6 +85,12 @@ def build_workload(name, columns, rank=0, world=1, for_gpu=True, desc_columns=No
                                          '(configs[3]; each step = Gamma iteration + up to 3 PRD sub-iterations on '
                                          'fixed LTE populations -- no stat-eq, the synthetic atom is not meant to be '
                                          'iterated to convergence with PRD; points counted for the Gamma iteration only)')
+    if name == 'c4h':
+        p = synth.config_c4(nl=2.0)
+        p.configure_hprd()
+        return p, ('FAL C 1D, H + Ca II + Mg II, Mg II h&k in HYBRID PRD (configure_hprd_coeffs: rho interpolated per '
+                   'ray to the rest frame, JRest scattered by the formal solution), 5 rays (configs[3] as BASELINE words '
+                   'it; each step = Gamma iteration + up to 3 PRD sub-iterations, as c4)')
     if name == 'c5':
         from lightweaver_b200.sharding import partition_columns
         c0, c1 = partition_columns(columns, world)[rank]
@@ -446,7 +452,7 @@ def bench_workload(args, workload, columns, rank, world, local_rank, with_cpu_ba
     problem, desc = build_workload(workload, columns, rank, world)
     column_sharded = workload in ('c3', 'c5')
     stokes = workload == 'c5'
-    with_prd = workload == 'c4'
+    with_prd = workload in ('c4', 'c4h')
     col0 = sharding.partition_columns(columns, world)[rank][0] if column_sharded else 0
     laRange = ranges = None
     if world > 1 and not column_sharded:
@@ -766,7 +772,7 @@ def run_ours(args, rank, world, local_rank):
         # (lightweaver/benchmark.py:19-45: FAL C at 500 depths)
         # (one GPU only: a secondary that failed on one rank of a multi-rank launch would leave the others
         # waiting in its reductions)
-        extra = ([('c5_full_stokes_stack', 'c5', 1024), ('c1', 'c1', 1), ('c4_prd', 'c4', 1),
+        extra = ([('c5_full_stokes_stack', 'c5', 1024), ('c1', 'c1', 1), ('c4_prd', 'c4', 1), ('c4_hybrid_prd', 'c4h', 1),
                   ('deep_500_depths_reference_benchmark_shape', 'deep', 1)] if world == 1 else [])
         for key, wl, cols in extra:
             try:
@@ -810,7 +816,7 @@ def run_reference(args, rank, world):
         line['secondary'] = {'c2_lambda_sharded': {k: sec[k] for k in keep}}
         if world == 1:
             for key, wl, cols in (('c5_full_stokes_stack', 'c5', 1024), ('c1', 'c1', 1), ('c4_prd', 'c4', 1),
-                                  ('deep_500_depths_reference_benchmark_shape', 'deep', 1)):
+                                  ('c4_hybrid_prd', 'c4h', 1), ('deep_500_depths_reference_benchmark_shape', 'deep', 1)):
                 try:
                     sec = reference_line(args, wl, cols, world, budget_s=15.0)
                     line['secondary'][key] = {k: sec[k] for k in keep}
@@ -839,7 +845,7 @@ def _main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c3', choices=['c1', 'c2', 'c3', 'c4', 'c5', 'deep'])
+    ap.add_argument('--workload', default='c3', choices=['c1', 'c2', 'c3', 'c4', 'c4h', 'c5', 'deep'])
     ap.add_argument('--columns', type=int, default=None, help='columns of the c3 (4096) / c5 (1024) stacks')
     ap.add_argument('--no-secondary', dest='secondary', action='store_false',
                     help='default run (c3): do not also measure the lambda-sharded c2 workload')
