@@ -264,6 +264,7 @@ struct LwB200Context
     int KC = 0;
     int Ntile = 0;
     int nwarps = 4;
+    int fsWarps = 4;  // warps per CTA of the general kernel
     int laLo = 0, laHi = 0;
     int NCH = 0;
     size_t smemBytes = 0;
@@ -465,7 +466,9 @@ int build_plan(LwB200Context* c)
     int maxNlevel = 1;
     for (int a = 0; a < p.Natom; ++a)
         maxNlevel = std::max(maxNlevel, c->atoms[a].Nlevel);
-    const size_t scratchFs = (size_t)c->nwarps * 2 * maxNlevel * 32 * sizeof(double);
+    // (small problems: the general kernel splits the rays of a wavelength over its warps; 8 warps were measured no
+    // faster than 4 -- config 4 with hybrid PRD 1.21 vs 1.14 ms)
+    const size_t scratchFs = (size_t)c->fsWarps * 2 * maxNlevel * 32 * sizeof(double);
     const int KC = std::min(KP, 128); // depths per gamma_kernel CTA
     const int RS = K <= 128 ? K : KC; // its shared-memory row stride (no padding rows when one chunk covers K)
     const size_t scratchGamma = (size_t)2 * maxNlevel * RS * sizeof(double);
@@ -605,7 +608,7 @@ int build_plan(LwB200Context* c)
     if (!c->generalViaLong)
         maxSlots = std::max(maxSlots, maxSlotsGeneral);
     c->smemGamma = (size_t)maxSlots * 4 * RS * sizeof(double) + scratchGamma;
-    c->smemBytes = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchFs;
+    c->smemBytes = (size_t)maxSlots * 4 * KP * sizeof(double) + scratchFs + (size_t)c->fsWarps * KP * sizeof(double);
     c->scratchGamma = scratchGamma;
     if (const char* e = std::getenv("LWB200_GAMMA_DIRECT")) // tuning aid: 0 never, 1 always
         c->gammaDirect = std::atoi(e);
@@ -1600,7 +1603,7 @@ int launch_fs_t(LwB200Context* c, int lambdaIterate, int upOnly, int storeDepth)
     const bool capturing = stream_is_capturing(c->stream);
     if (!capturing)
         CU(cudaEventRecord(c->evK0, c->stream));
-    const int threads = c->nwarps * 32;
+    const int threads = c->fsWarps * 32;
     if (MODE == MODE_ITER && !c->forceDirect)
     {
         // wavelengths with more than three overlapping lines go through the general kernel
@@ -3274,7 +3277,7 @@ int lwb200_redistribute_prd(LwB200Context* c, int32_t maxIter, double tol, int32
             c->P, c->dPrdLines.p, c->transWave.p, c->qelast.p, c->cmat.p, c->cTot, c->vBroad.p, c->aDamp.p,
             c->rhoPrd.p);
         CU(cudaGetLastError());
-        prd_change_kernel<<<nLines, 256, 0, s>>>(c->dPrdLines.p, p.Ncol, K, c->rhoPrd.p, c->rhoPrev.p,
+        prd_change_kernel<<<nLines, 1024, 0, s>>>(c->dPrdLines.p, p.Ncol, K, c->rhoPrd.p, c->rhoPrev.p,
                                                  c->prdMax.p, c->prdIdx.p);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(hMax.data(), c->prdMax.p, nLines * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -261,6 +261,7 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
     double* acc = smem;                                   // [nslot][4][KP]
     double* scratch = smem + (size_t)P.maxSlots * 4 * KP  // per warp [2][maxNlevel][32]
         + (size_t)warp * 2 * P.maxNlevel * 32;
+    double* jbuf = smem + (size_t)P.maxSlots * 4 * KP + (size_t)nwarp * 2 * P.maxNlevel * 32; // [nwarp][KP], split mode
 
     if (MODE == MODE_ITER)
     {
@@ -284,8 +285,13 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
     const double Tbot1 = __ldg(P.temperature + (size_t)col * K + K - 2);
 
     const int tlBeg = P.tileLa[tile], tlEnd = P.tileLa[tile + 1];
+    // A tile with fewer wavelengths than the CTA has warps (one 1D atmosphere: tiles of one wavelength) would leave
+    // warps idle behind one warp's serial chain of 2 Nrays rays: the warps then SPLIT THE RAYS of every wavelength
+    // of the tile instead (ray r goes to warp r mod nwarp); the partial mean intensities meet in shared memory, the
+    // Gamma / rate sums are shared-memory atomics as before.  Every skip below is uniform over the CTA in that mode.
+    const bool split = (tlEnd - tlBeg) < nwarp;
 
-    for (int tl = tlBeg + warp; tl < tlEnd; tl += nwarp)
+    for (int tl = split ? tlBeg : tlBeg + warp; tl < tlEnd; tl += split ? 1 : nwarp)
     {
         const int la = P.tileLambda[tl];
         if (la < laLo || la >= laHi)
@@ -348,6 +354,8 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
             const double halfwmu = 0.5 * __ldg(P.wmu + mu);
             for (int dir = upOnly ? 1 : 0; dir < 2; ++dir)
             {
+                if (split && ((2 * mu + dir) % nwarp) != warp)
+                    continue;
                 // --- opacity, emissivity, source function for this ray
                 double chi[NCH], S[NCH];
                 {
@@ -438,8 +446,10 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
                 else
                     solve_ray<NCH, SOLVER, true, MODE == MODE_ITER>(g, chi, S, muz, bc, I, psi);
 
-                if (lane == 0)
-                    P.I[((size_t)col * L + la) * M + mu] = I[0]; // spect.I(la, mu, 0) = I(0)
+                // spect.I(la, mu, 0) = I(0): the reference stores it after both rays of a mu, the up-going one last
+                // (with the rays of a wavelength split over warps the two would race: only that one is stored)
+                if (lane == 0 && dir == 1)
+                    P.I[((size_t)col * L + la) * M + mu] = I[0];
                 store_zplane<NCH>(P, lane, I, dir, ((size_t)col * L + la) * M + mu);
 
                 if (MODE != MODE_ITER)
@@ -557,7 +567,33 @@ fs_kernel(const DevProblem P, const int* __restrict__ tileList, int laLo, int la
             }
         }
 
-        if (MODE == MODE_ITER)
+        if (MODE == MODE_ITER && split)
+        {
+            // the warps' partial sums of J, added in warp order by the first
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+            {
+                const int k = g.k(j);
+                if (k < K)
+                    jbuf[warp * KP + k] = Jnew[j];
+            }
+            __syncthreads();
+            if (warp == 0)
+            {
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+                {
+                    const int k = g.k(j);
+                    double sJ = 0.0;
+                    if (k < K)
+                        for (int w2 = 0; w2 < nwarp; ++w2)
+                            sJ += jbuf[w2 * KP + k];
+                    Jnew[j] = sJ;
+                }
+            }
+        }
+        if (MODE == MODE_ITER && (!split || warp == 0))
         {
             // J row and dJ = max_k |1 - Jdag/J|  (:477-485)
             double dJ = 0.0;

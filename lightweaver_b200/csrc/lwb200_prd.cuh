@@ -213,8 +213,8 @@ __global__ void prd_change_kernel(const DevPrdLine* __restrict__ lines, int Ncol
                                   const double* __restrict__ rhoPool, double* __restrict__ prevPool,
                                   double* __restrict__ outMax, int* __restrict__ outIdx)
 {
-    __shared__ double sMax[256];
-    __shared__ long long sIdx[256];
+    __shared__ double sMax[1024];   // (launched with up to 1024 threads: one block per line walks Nl * K * Ncol elements,
+    __shared__ long long sIdx[1024]; //  and in 1D that walk is the whole kernel)
     const DevPrdLine ln = lines[blockIdx.x];
     const long long per = (long long)ln.Nl * K, total = per * Ncol;
     double best = 0.0;
