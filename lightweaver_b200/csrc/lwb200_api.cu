@@ -1362,8 +1362,10 @@ int launch_pipeline(LwB200Context* c, const PipelineLists& pl, int lambdaIterate
             const int nw = c->nwarps;
             dim3 grid(MULTI ? nLam : (nLam + nw * perWarp - 1) / (nw * perWarp), nb);
             const int* list = pl.kindLam[q];
-            continuum_table_kernel<<<dim3((nLam + contPerBlock - 1) / contPerBlock, nb), KP, 0, s>>>(
-                c->P, c->G, list, nLam, contPerBlock, colBase);
+            // (a small launch -- one 1D atmosphere -- is a latency chain of dependent loads per wavelength: one
+            // wavelength per CTA there; config 1: 17 us with four)
+            const int cpb = (long long)nLam * nb <= 148LL * 64 ? 1 : contPerBlock;
+            continuum_table_kernel<<<dim3((nLam + cpb - 1) / cpb, nb), KP, 0, s>>>(c->P, c->G, list, nLam, cpb, colBase);
             CU(cudaGetLastError());
             c->lastLaunches += 1;
             // Bezier3, one warp per wavelength, both directions: the two rays of a mu solved together
