@@ -66,6 +66,28 @@ ctx.formal_sol_gamma_matrices()
 ctx.close()
 print('deep general / many rays ok', flush=True)
 
+# every wavelength through the general kernel at 82 depths (rays split over the warps of a CTA), a 40-level atom
+# (population solve with global scratch, general tiles by RED), and 1100 depths (32-warp general kernel)
+p = synth.tiny_problem(ncol=1, nrays=3)
+ctx = Context(p)
+ctx.formal_sol_gamma_matrices(extraParams={'generalKernel': True})
+ctx.stat_equil()
+ctx.close()
+lev = [synth.Level(0.0, 2, 0)] + [synth.Level(55000.0 + 600.0 * i, 2 + 2 * (i % 4), 0) for i in range(38)] + [synth.Level(100000.0, 1, 1)]
+big = synth.ModelAtom('Huge', 12.0, 1e-4, lev, [synth.LineSpec(1, 0, 2.0e8, 15, 4.0, 40.0)],
+                      [synth.ContSpec(39, i, 4.0e-22, 5, 70.0) for i in range(39)])
+p = synth.build_problem([big], nrays=2, perturb=True, ncol=2)
+ctx = Context(p)
+ctx.formal_sol_gamma_matrices()
+ctx.stat_equil()
+ctx.close()
+p = synth.tiny_problem(ndepth=1100, nrays=2, ncol=1)
+ctx = Context(p)
+ctx.formal_sol_gamma_matrices()
+ctx.stat_equil()
+ctx.close()
+print('ray split / large atom / very deep ok', flush=True)
+
 p = synth.config_c3(ncol=600, with_profiles=False, alloc_phi=False)
 ctx = Context(p, upload=False)
 ctx.upload(capi.ALL_INPUTS & ~capi.PROFILE)
