@@ -8,6 +8,7 @@
 #include "lwb200_gamma.cuh"
 #include "lwb200_ray2.cuh"
 #include "lwb200_fslong.cuh"
+#include "lwb200_fsgeneral.cuh"
 #include "lwb200_prd.cuh"
 #include "lwb200_stokes.cuh"
 #include "lwb200_ng.cuh"
